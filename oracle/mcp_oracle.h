@@ -1,0 +1,134 @@
+/*
+ * mcp_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of MCPower's per-simulation hot loop
+ * (reference: crates/engine-core/src/{rng,data_gen,batch,critvals,correction,
+ * distributions,scenarios,correlation}.rs).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * The product (mcpower_b200/csrc) never links, includes or calls it.
+ *
+ * Parity pinning (see oracle/README.md): bit-exact against the reference's
+ * RNG goldens (tests/golden_rng.rs, tests/rng_byte_identity.rs) and the saved
+ * sim-0 design matrices/outcomes in validation/data/<case>.rds; <=1e-10 relative
+ * against the frozen R lm goldens.  Sub-paths with no reference vector are
+ * listed as "unpinned" in DESIGN.md.
+ */
+#ifndef MCP_ORACLE_H
+#define MCP_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enum codes shared with the Python test harness (tests/orc.py) */
+enum { ORC_DIST_NORMAL = 0, ORC_DIST_BINARY = 1, ORC_DIST_RIGHT_SKEWED = 2, ORC_DIST_LEFT_SKEWED = 3,
+       ORC_DIST_HIGH_KURTOSIS = 4, ORC_DIST_UNIFORM = 5 };
+enum { ORC_RES_NORMAL = 0, ORC_RES_RIGHT_SKEWED = 1, ORC_RES_LEFT_SKEWED = 2, ORC_RES_HIGH_KURTOSIS = 3,
+       ORC_RES_UNIFORM = 4 };
+enum { ORC_OUT_CONTINUOUS = 0, ORC_OUT_BINARY = 1, ORC_OUT_COUNT = 2 };
+enum { ORC_EST_OLS = 0, ORC_EST_GLM = 1, ORC_EST_MLE = 2 };
+enum { ORC_CORR_NONE = 0, ORC_CORR_BONFERRONI = 1, ORC_CORR_HOLM = 2, ORC_CORR_BH = 3, ORC_CORR_TUKEY = 4 };
+enum { ORC_OK = 0, ORC_ERR_INVALID_SPEC = 1, ORC_ERR_NOT_PSD = 2, ORC_ERR_RANK = 3, ORC_ERR_CANCELLED = 4 };
+
+typedef struct {
+    int32_t n_non_factor, n_factor_dummies, n_factors, n_interactions;
+    const double* correlation;        /* k*k column-major (spec.rs:255) */
+    const int32_t* var_types;         /* k */
+    const uint8_t* var_pinned;        /* k or NULL */
+    const double* var_params;         /* k */
+    const int32_t* factor_n_levels;   /* n_factors */
+    const double* factor_proportions; /* sum(levels) */
+    const int32_t* factor_sampled;    /* n_factors: -1 inherit, 0 exact, 1 sampled; or NULL */
+    const int32_t* inter_ptr;         /* n_interactions+1 CSR offsets */
+    const int32_t* inter_cols;
+    const double* effect_sizes;       /* P */
+    int32_t n_marginal_targets;
+    const int32_t* target_indices;
+    int32_t n_contrasts;
+    const int32_t* contrast_pairs;    /* 2*n_contrasts (pos, neg) */
+    int32_t n_fit_columns;
+    const int32_t* fit_columns;
+    int32_t correction_method;
+    double alpha;
+    double posthoc_alpha;             /* NaN = inherit alpha */
+    int32_t hsk_driver;               /* -1 = linear predictor */
+    int32_t residual_dist, residual_pinned, outcome_kind, link_probit, estimator;
+    int32_t report_overall, factor_min_level_count;
+    int32_t has_cluster, sizing_fixed_size, sizing_value;
+    double tau_squared;
+    /* scenario block (spec.rs:117-176) */
+    double heterogeneity, hsk_ratio, corr_noise_sd, dist_change_prob;
+    int32_t n_new_dists;
+    const int32_t* new_dists;
+    double resid_change_prob;
+    int32_t n_resid_dists;
+    const int32_t* resid_dists;
+    double residual_df;
+    int32_t sampled_factor_proportions;
+    int32_t has_lme, re_dist;
+    double re_df, icc_noise_sd;
+} OrcSpec;
+
+/* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
+uint64_t orc_splitmix64(uint64_t z);
+uint64_t orc_pcg_mix64(uint64_t base_seed, uint64_t sim_id);
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+float orc_u32_to_unit_f32(uint32_t w);
+float orc_norm_inv_cdf_f32(float u);
+/* sequential stream draws: kind 0 = next_normal, 1 = next_uniform; returns f32 bit patterns */
+void orc_seq_stream(uint64_t base_seed, uint64_t sim_id, int kind, int n, uint32_t* out_bits);
+void orc_seq_categorical(uint64_t base_seed, uint64_t sim_id, const double* probs, int n_probs, int n, int32_t* out);
+void orc_planar_normals(uint64_t base_seed, uint64_t sim_id, uint32_t cls, uint32_t col, int n, uint32_t* out_bits);
+void orc_sample_t(uint64_t base_seed, uint64_t sim_id, double df, int n, double* out);
+void orc_draw_residual(uint64_t base_seed, uint64_t sim_id, int dist, double df, int n, double* out);
+
+/* ---- transforms (distributions.rs:32-56, data_gen.rs:1106-1182, marginals/t3.rs) ---- */
+double orc_exp(double x);
+double orc_log(double x);
+double orc_phi(double z);
+double orc_apply_marginal(double z, int dist, double param);
+double orc_t3_lookup(double percentile);
+double orc_poisson_quantile(double z, double lambda);
+
+/* ---- critical values (critvals.rs) ---- */
+double orc_norm_ppf(double p);
+double orc_t_ppf(double p, double df);
+double orc_chi2_ppf(double p, double k);
+double orc_f_ppf(double p, double dfn, double dfd);
+double orc_q_tukey_ppf(double p, double k, double df);
+/* per-N rows: t_unc[n_ss], corr[n_ss*m], posthoc[n_ss], overall[n_ss]; returns ORC_* */
+int orc_build_crit_table(const OrcSpec* spec, const uint32_t* sample_sizes, int n_ss, int n_predictors,
+                         double* t_unc_sq, double* corr_sq, double* posthoc_sq, double* overall);
+
+/* ---- corrections (correction.rs:16-115) ---- */
+void orc_apply_correction(int method, const double* t_sq, int t, double crit_unc, const double* crit_sq, uint8_t* out);
+
+/* ---- data generation (data_gen.rs:87-925): x col-major f32 [max_n x P], y f32 ---- */
+int orc_generate_sim(const OrcSpec* spec, uint64_t base_seed, uint64_t sim_id, int max_n, float* x, float* y,
+                     int32_t* cluster_ids /* max_n or NULL */);
+
+/* ---- OLS on supplied data (introspect.rs:174-293): col-major f64 design, narrowed to f32 first ---- */
+int orc_fit_ols(const double* x_colmajor, const double* y, int n, int p, double* betas, double* se, double* t_sq,
+                double* sigma_sq, double* sst, double* rss, int* converged);
+
+/* ---- GLM IRLS on supplied data; family 0 logit, 1 probit, 2 poisson ---- */
+int orc_fit_glm(const double* x_colmajor, const double* y, int n, int p, int family, const double* beta_start,
+                double* betas, double* se, double* deviance, double* deviance_null, int* converged, int* iters);
+
+/* ---- the batch driver (batch.rs:199-776, 795-1213) ----
+ * Outputs (caller-allocated, sim-major like spec.rs:552-600):
+ *   uncorrected/corrected [n_sims][n_ss][T], converged [n_sims][n_ss],
+ *   overall [n_sims][n_ss] (or NULL), factor_excluded [n_sims][n_ss][n_factors] (or NULL),
+ *   t_sq_capture [n_sims][n_ss][T] f64 (or NULL; NaN where not converged/excluded).
+ * sim ids run over [sim_begin, sim_begin + n_sims).  n_threads<=1 → serial. */
+int orc_run_batch(const OrcSpec* spec, const uint32_t* sample_sizes, int n_ss, uint32_t n_sims, uint64_t sim_begin,
+                  uint64_t base_seed, int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged,
+                  uint8_t* overall, uint8_t* factor_excluded, double* t_sq_capture);
+
+const char* orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

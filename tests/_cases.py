@@ -1,0 +1,116 @@
+"""Shared test helpers: load the committed reference fixtures and rebuild each
+validation case's `SimulationSpec` from its recorded description
+(tests/golden/make_fixtures.py documents where the fixtures come from)."""
+from __future__ import annotations
+
+import gzip
+import json
+import math
+import re
+from functools import lru_cache
+from pathlib import Path
+
+import numpy as np
+
+from mcpower_b200 import spec as S
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@lru_cache(maxsize=1)
+def validation_cases() -> dict:
+    with gzip.open(GOLDEN / "validation_cases.json.gz", "rt") as f:
+        return json.load(f)
+
+
+def _one(v):
+    return v[0] if isinstance(v, list) else v
+
+
+def case_arrays(case: dict):
+    n, p = case["n"], case["p"]
+    x = np.array(case["design_f32_colmajor"], dtype=np.uint32).view(np.float32).reshape(p, n).T
+    y = np.array(case["outcome_f32"], dtype=np.uint32).view(np.float32)
+    return x, y
+
+
+def golden_arrays(case: dict):
+    g = case["golden"]
+    return {k: np.array([float.fromhex(h) for h in g[k]]) for k in ("beta", "se", "stat", "crit")}
+
+
+def _phi_inv(p: float) -> float:
+    from scipy.stats import norm
+    return float(norm.ppf(p))
+
+
+def case_spec(case: dict) -> dict:
+    """SimulationSpec for a validation case (sim 0 of base_seed = splitmix64(seed), max_n = n)."""
+    d = case["spec"]
+    family = _one(d["family"])
+    cols = case["columns"]
+    k = sum(1 for c in cols if c.startswith("col_"))
+    factors = []
+    for vt in d.get("variable_types", []) or []:
+        m = re.match(r"\s*(\w+)\s*=\s*\(factor,([^)]*)\)", vt)
+        if m:
+            factors.append((m.group(1), [float(v) for v in m.group(2).split(",")]))
+    fac_names = [f[0] for f in factors]
+    effects = {}
+    for part in _one(d["effects"]).split(","):
+        name, val = part.split("=")
+        effects[name.strip()] = float(val)
+    # continuous variable names in order of first appearance in the formula
+    formula = _one(d["formula"]).split("~")[1]
+    names = []
+    for tok in re.findall(r"[A-Za-z_]\w*", formula.split("(")[0] if "(1|" in formula else formula):
+        if tok not in fac_names and tok not in names:
+            names.append(tok)
+    assert len(names) == k, (names, k, case["label"])
+    s = S.base_spec(k)
+    col_of = {nm: 1 + i for i, nm in enumerate(names)}
+    for nm in names:
+        s["effect_sizes"][col_of[nm]] = effects.get(nm, 0.0)
+    for c in d.get("correlations", []) or []:
+        m = re.match(r"\s*corr\((\w+),\s*(\w+)\)\s*=\s*([-\d.eE]+)", c)
+        a, b, r = col_of[m.group(1)] - 1, col_of[m.group(2)] - 1, float(m.group(3))
+        s["correlation"][a * k + b] = r
+        s["correlation"][b * k + a] = r
+    for fname, props in factors:
+        base = 1 + s["n_non_factor"] + s["n_factor_dummies"]
+        effs = [effects.get(f"{fname}[{lvl}]", 0.0) for lvl in range(2, len(props) + 1)]
+        s = S.add_factor(s, props, effs)
+        for lvl in range(2, len(props) + 1):
+            col_of[f"{fname}[{lvl}]"] = base + lvl - 2
+    n_inter = sum(1 for c in cols if c.startswith("interaction_"))
+    inter_keys = [key for key in effects if ":" in key]
+    assert len(inter_keys) == n_inter, (inter_keys, cols)
+    for key in inter_keys:
+        comps = [col_of[t.strip()] for t in key.split(":")]
+        s = S.add_interaction(s, comps, effects[key])
+    P = S.n_predictors(s)
+    assert P == case["p"], (P, case["p"])
+    s["target_indices"] = list(range(1, P))
+    if family == "logit":
+        s["outcome_kind"], s["estimator"] = "binary", "glm"
+        s["intercept"] = S.logit_intercept(_one(d["baseline_probability"]))
+        s["effect_sizes"][0] = s["intercept"]
+    elif family == "probit":
+        s["outcome_kind"], s["estimator"], s["link"] = "binary", "glm", "probit"
+        s["intercept"] = _phi_inv(_one(d["baseline_probability"]))
+        s["effect_sizes"][0] = s["intercept"]
+    elif family == "poisson":
+        s["outcome_kind"], s["estimator"] = "count", "glm"
+        s["intercept"] = math.log(_one(d["baseline_rate"]))
+        s["effect_sizes"][0] = s["intercept"]
+    elif family == "lme":
+        cl = d["cluster"]
+        icc = _one(cl["ICC"])
+        s["estimator"] = "mle"
+        s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": int(_one(cl["n_clusters"]))}},
+                        "tau_squared": icc / (1.0 - icc), "slopes": [], "extra_groupings": []}
+    return s
+
+
+def case_seed(case: dict) -> int:
+    return int(_one(case["spec"]["seed"]))
