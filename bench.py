@@ -1,0 +1,251 @@
+#!/usr/bin/env python3
+"""bench.py — OLS fits/s at BASELINE.json's metric shape (n=500, k=8 → P=9), whole job over N GPUs.
+
+A "step" is one pass of the hot path (engine_core::run_batch twin) over one batch of synthetic
+simulations: SIMS_PER_STEP sims per GPU, each generated and fitted on-chip.  Sims shard across
+ranks by global sim id with the same base seed — weak scaling, no data-path
+collective; the only exchange is one all-reduce of the per-cell integer counters.
+
+  value : fits/s from device time (CUDA events on the launch stream, max over ranks)
+  e2e   : fits/s through the public API (mcpower_b200.run_batch → C ABI) with host buffers: spec JSON
+          parse + lowering + H2D of the plan/tables + kernel + D2H of the counters, wall clock
+  roofline      : FP64-pipe view — algorithmic FP64 flop per fit ÷ measured DFMA peak
+  roofline_issue: instruction-issue view (the real bound) when profiles/inst_per_fit.json exists
+  cpu_baseline  : the oracle (CPU restatement of the reference algorithm) on all host threads, bounded sample
+
+`--impl reference` times the oracle alone (the Rust engine cannot be built here: no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ROWS = 500
+SIMS_PER_STEP = 1 << 22          # per GPU per step
+FLOP64_PER_FIT = 6.6e4           # 3.3e4 DFMA at n=500, P=9 (identity mix skipped: structural zeros)
+USER_SEED = 2137                 # configs/config.json default seed; base_seed = splitmix64(seed) (find_power.rs:259)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(spec, n_rows, seed, target_seconds, orc):
+    """Time the oracle on all host threads over a bounded sample (~target_seconds of CPU work)."""
+    threads = orc.host_threads()
+    n = 2000 * threads
+    orc.run_batch(spec, [n_rows], 256 * threads, seed, n_threads=threads)  # warm-up
+    t0 = time.perf_counter()
+    orc.run_batch(spec, [n_rows], n, seed, n_threads=threads)
+    dt = time.perf_counter() - t0
+    n_big = int(max(n, min(4_000_000, n * target_seconds / max(dt, 1e-6))))
+    t0 = time.perf_counter()
+    orc.run_batch(spec, [n_rows], n_big, seed, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_big / dt, threads, n_big, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sims-per-step", type=int, default=SIMS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from mcpower_b200 import spec as S
+    spec = S.headline_spec()
+    config = {"workload": "ols_n500_k8_p9 (BASELINE configs[1] metric shape M: 8 independent N(0,1) predictors, "
+                          "effects x1=x2=0.18, targets {x1,x2}, alpha=0.05, optimistic scenario)",
+              "n_rows": N_ROWS, "n_predictors": 9, "sims_per_step_per_gpu": args.sims_per_step,
+              "parallelism": f"sim-id sharding x{world}, counters all-reduced",
+              "l2_policy": "n/a - no input tensors: every dataset is generated on-chip from (spec, seed, sim_id)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import orc
+        seed = orc.splitmix64(USER_SEED)
+        threads = orc.host_threads()
+        per_step = 1500 * threads
+        for _ in range(args.warmup):
+            orc.run_batch(spec, [N_ROWS], per_step, seed, n_threads=threads)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            orc.run_batch(spec, [N_ROWS], per_step, seed, sim_begin=i * per_step, n_threads=threads)
+        dt = time.perf_counter() - t0
+        v = per_step * args.steps / dt
+        line = {"impl": "reference", "metric": "ols_fits_per_sec", "value": v, "unit": "fits/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
+                                 "sample": f"{per_step} sims x n={N_ROWS} per step, oracle/mcp_oracle.c (CPU restatement of "
+                                           "the reference algorithm; the Rust engine cannot be built here: no cargo/rustc)"},
+                "e2e": {"value": v, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import mcpower_b200 as M
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the CUDA backend has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seed = M.splitmix64(USER_SEED)
+    per = args.sims_per_step
+    launches = 0
+
+    def step(i, mode=M.MODE_COUNTS):
+        # global sim ids: step-major, rank-minor — the union over ranks is one contiguous id range
+        begin = (i * world + rank) * per
+        return M.run_batch(spec, [N_ROWS], per, seed, mode=mode, device=local_rank, sim_begin=begin)
+
+    for i in range(args.warmup):
+        step(i)
+    # ---- timed region 1: device time (value)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, total_counters = 0.0, None
+    for i in range(args.steps):
+        r = step(args.warmup + i)
+        dev_ms += r.kernel_ms
+        launches += r.gpu_launches
+        total_counters = r.counters.copy() if total_counters is None else total_counters + r.counters
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # ---- timed region 2: end-to-end through the public API (host buffers in, host counters out)
+    barrier()
+    t1 = time.perf_counter()
+    for i in range(args.steps):
+        r = step(args.warmup + args.steps + i)
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+
+    t = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
+    cnt = torch.from_numpy(total_counters.astype(np.int64)).cuda()
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)   # the path's only collective: integer counters per cell
+    dev_ms, wall, e2e_wall = (float(v) for v in t.tolist())
+    counters = cnt.cpu().numpy()
+    total_fits = per * args.steps * world
+    value = total_fits / (dev_ms * 1e-3)
+    e2e_value = total_fits / e2e_wall
+
+    if rank == 0:
+        power = counters[0, :2] / total_fits
+        plan_bytes = 20_000  # DevicePlan (~13 KB) + sample sizes + variant/threshold tables, per run_batch call
+        d2h = int(r.counters.nbytes)
+        dfma = M.pipe_bench(0, local_rank)
+        peak_tf = 2.0 * dfma / 1e12
+        ach_tf = (value / world) * FLOP64_PER_FIT / 1e12
+        line = {"metric": "ols_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * e2e_wall / args.steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": ach_tf / peak_tf, "traffic": None,
+                             "note": "per GPU; peak = measured DFMA throughput (mcp_pipe_bench kind 0) on this device, "
+                                     "not MEASURED_PEAKS.json (which has no FP64 entry); algorithmic 6.6e4 FP64 flop/fit"},
+                "power_x1_x2": [float(p) for p in power],
+                "wall_ms_per_step": 1e3 * wall / args.steps}
+        ipf = ROOT / "profiles" / "inst_per_fit.json"
+        if ipf.exists():
+            d = json.loads(ipf.read_text())
+            fmul = M.pipe_bench(1, local_rank)
+            sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            peak_issue = 148 * 4 * sm_clock_hz  # warp-instructions/s at one issue per SMSP per clock
+            ach_issue = (value / world) * d["warp_inst_per_fit"]
+            line["roofline_issue"] = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
+                                      "unit": "Gwarp-inst/s", "frac": ach_issue / peak_issue,
+                                      "warp_inst_per_fit": d["warp_inst_per_fit"], "source": d.get("source"),
+                                      "fp32_pair_thread_ops_per_s": fmul}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import orc
+            v, cores, n_big, dt = cpu_reference(spec, N_ROWS, seed, 12.0, orc)
+            line["cpu_baseline"] = {"value": v, "unit": "fits/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_big} sims x n={N_ROWS} in {dt:.1f} s, oracle/mcp_oracle.c on all host threads"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

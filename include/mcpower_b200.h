@@ -1,0 +1,106 @@
+/*
+ * mcpower_b200.h — C ABI of the B200-native MCPower hot-path backend (libmcpower_b200.so).
+ *
+ * Drop-in seam: engine_core::run_batch
+ *   pub fn run_batch(spec: &SimulationSpec, sample_sizes: &[u32], n_sims: u32, base_seed: u64,
+ *                    sink: Option<&dyn ProgressSink>) -> Result<BatchResult, EngineError>
+ *   (reference: crates/engine-core/src/batch.rs:130-146; callers find_power.rs:337,
+ *    find_sample_size.rs:213, single_core.rs, introspect.rs:7-8, bin/throughput.rs:668).
+ * A Rust `engine-cuda` crate binds these symbols with `extern "C"` (INTEGRATION.md shows the stub);
+ * the Python mirror in mcpower_b200/engine.py binds them with ctypes.
+ *
+ * Plain pointers and sizes only; no C++/torch types; nothing throws across the boundary.
+ * All functions return an McpStatus code; mcp_last_error() gives the message for the calling thread.
+ */
+#ifndef MCPOWER_B200_H
+#define MCPOWER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors EngineError (crates/engine-core/src/spec.rs:19-29) + backend-specific codes. */
+enum {
+    MCP_STATUS_OK = 0,
+    MCP_STATUS_INVALID_SPEC = 1,        /* EngineError::InvalidSpec(String)   */
+    MCP_STATUS_CORRELATION_NOT_PSD = 2, /* EngineError::CorrelationNotPSD     */
+    MCP_STATUS_RANK_DEFICIENT = 3,      /* EngineError::RankDeficient(u32)    */
+    MCP_STATUS_CANCELLED = 4,           /* EngineError::Cancelled             */
+    MCP_STATUS_CUDA_ERROR = 5,          /* no device / launch failure: never a silent CPU fallback */
+    MCP_STATUS_UNSUPPORTED = 6          /* spec feature outside the CUDA path's scope */
+};
+
+/* Output selection (bit-or). COUNTS = per-cell counters (what aggregate_batch derives,
+ * crates/engine-orchestrator/src/aggregation.rs:61-271); BYTES = the sim-major 0/1 tensors of
+ * BatchResult (spec.rs:552-600); CAPTURE = per-fit squared statistics (run_batch_st_capture,
+ * batch.rs:175-197, extended to every sample-size index). */
+enum { MCP_MODE_COUNTS = 1, MCP_MODE_BYTES = 2, MCP_MODE_CAPTURE = 4 };
+
+typedef struct McpOptions {
+    int32_t device;      /* CUDA ordinal; -1 = current device */
+    uint32_t mode;       /* MCP_MODE_*; 0 = COUNTS */
+    uint64_t sim_begin;  /* first GLOBAL sim id of this shard (multi-GPU: same base_seed, disjoint id ranges) */
+    uint32_t wave_sims;  /* sims per kernel launch; 0 = auto. Progress/cancel are polled between waves */
+    uint32_t reserved;
+} McpOptions;
+
+/* ProgressSink (spec.rs:38-52): report(current, total) ~50×/run; return 0 to request cancellation. */
+typedef int (*McpProgressFn)(uint64_t current, uint64_t total, void* user);
+
+/* Counter row layout per sample-size index (width = 4T + 4 + F):
+ *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
+ *   [2T+2,3T+3) histogram of #uncorrected-significant targets per sim
+ *   [3T+3,4T+4) histogram of #corrected-significant targets per sim
+ *   [4T+4,4T+4+F) sims with factor f sparse-excluded */
+typedef struct McpBatchResult {
+    uint32_t n_sims, n_sample_sizes, n_targets, n_factors;
+    uint8_t* uncorrected;     /* [n_sims][n_ss][T]  or NULL */
+    uint8_t* corrected;       /* [n_sims][n_ss][T]  or NULL */
+    uint8_t* converged;       /* [n_sims][n_ss]     or NULL */
+    uint8_t* overall;         /* [n_sims][n_ss]     or NULL (spec.report_overall) */
+    uint8_t* factor_excluded; /* [n_sims][n_ss][F]  or NULL */
+    double* t_sq;             /* [n_sims][n_ss][T]  or NULL (CAPTURE) */
+    uint32_t counter_width;
+    uint32_t gpu_launches;    /* kernels launched for this call */
+    uint64_t* counters;       /* [n_ss][counter_width] */
+    double kernel_ms;         /* device time of the power kernel(s), CUDA events on the launch stream */
+} McpBatchResult;
+
+/* run_batch twin. spec_json = serde JSON of SimulationSpec (same field names / enum spellings). */
+int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_sample_sizes,
+                  uint32_t n_sims, uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user,
+                  McpBatchResult** out);
+void mcp_free_result(McpBatchResult* result);
+
+/* introspect::capture_sim0_data twin (introspect.rs:104-155) for ANY sim id: the f32 design matrix
+ * (column-major, max_n × P) and outcome the power kernel generates for (base_seed, sim_id). */
+int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uint64_t base_seed, uint64_t sim_id,
+                     int32_t device, float* x_colmajor, float* y);
+
+/* introspect::fit_provided_data twin (introspect.rs:174-293), OLS: column-major f64 design (narrowed to
+ * f32 first, like the reference), n × p.  out = beta[p], se[p], t_sq[p], sigma_sq, sst, rss, converged. */
+int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t p, int32_t device, double* out);
+
+/* CritValueTable::build_with_tukey_k twin (critvals.rs:827-1012; host f64).
+ * t_unc_sq[n_ss], corr_sq[n_ss*T], posthoc_sq[n_ss], overall[n_ss]; any pointer may be NULL. */
+int mcp_crit_table(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_sample_sizes,
+                   uint32_t n_predictors, double* t_unc_sq, double* corr_sq, double* posthoc_sq, double* overall);
+
+/* rng::splitmix64_finalize (rng.rs:30): hosts derive base_seed = splitmix64(user_seed) (find_power.rs:259). */
+uint64_t mcp_splitmix64(uint64_t z);
+
+/* Measured pipe throughput (thread-operations per second on `device`) for the roofline denominators:
+ * kind 0 = DFMA, 1 = FMUL+FADD pair (counts 2 ops), 2 = Philox round mix (2 IMAD.WIDE + 2 LOP3 → counts 4 ops),
+ * 3 = F2F.F64.F32 + DADD (counts 2 ops), 4 = DADD. */
+int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s);
+
+int mcp_device_count(void);
+const char* mcp_last_error(void);
+const char* mcp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,635 @@
+// api.cu — host side of libmcpower_b200.so: spec lowering, launch, and the C ABI declared in
+// include/mcpower_b200.h.  There is no CPU execution path here: a missing device or a failed
+// launch is reported as MCP_STATUS_CUDA_ERROR, never papered over.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mcpower_b200.h"
+#include "critvals.hpp"
+#include "kernels.cuh"
+#include "spec.hpp"
+
+namespace mcp {
+
+static thread_local std::string g_last_error;
+static std::mutex g_plan_mutex;  // c_plan is one __constant__ symbol per device → one batch at a time per process
+
+#define CUDA_CHECK(expr)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            throw EngineError(MCP_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
+    } while (0)
+
+struct DeviceBuffers {
+    std::vector<void*> ptrs;
+    template <typename T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    template <typename T>
+    T* upload(const std::vector<T>& v) {
+        T* p = alloc<T>(v.size());
+        if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+    ~DeviceBuffers() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+// ---- exclusion variants (batch.rs:2502-2562) --------------------------------------------------
+static McpVariant make_variant(const Spec& s, int mask) {
+    McpVariant v;
+    std::memset(&v, 0, sizeof v);
+    const int base = 1 + s.k, nfd = s.n_fd, P = s.P();
+    std::vector<char> keep_dummy(nfd, 1);
+    int col = base;
+    for (size_t f = 0; f < s.factor_n_levels.size(); f++) {
+        const int width = s.factor_n_levels[f] - 1;
+        if (mask & (1 << f))
+            for (int d = 0; d < width; d++) keep_dummy[col + d - base] = 0;
+        col += width;
+    }
+    for (int c = 0; c < MCP_MAX_P; c++) v.remap[c] = -1;
+    int nk = 0;
+    for (int c = 0; c < P; c++) {
+        bool keep = true;
+        if (c >= base && c < base + nfd) keep = keep_dummy[c - base];
+        else if (c >= base + nfd)
+            for (int cu : s.interactions[c - base - nfd])
+                if (cu >= base && cu < base + nfd && !keep_dummy[cu - base]) keep = false;
+        if (keep && !s.fit_columns.empty()) keep = std::find(s.fit_columns.begin(), s.fit_columns.end(), c) != s.fit_columns.end();
+        if (keep) {
+            v.remap[c] = (int8_t)nk;
+            v.kept[nk++] = (int8_t)c;
+        }
+    }
+    v.p_red = nk;
+    v.valid = 1;
+    return v;
+}
+
+static double tukey_k_for_col(const Spec& s, int col) {  // batch.rs:2233-2250
+    const int base = 1 + s.k;
+    if (col < base) return crit::kNaN;
+    int cursor = base;
+    for (int l : s.factor_n_levels) {
+        if (col < cursor + l - 1) return (double)l;
+        cursor += l - 1;
+    }
+    return crit::kNaN;
+}
+
+// One CritValueTable row (critvals.rs:872-960 + overall 979-1003) for sample size n and `n_predictors` fitted columns.
+static void crit_row(const Spec& s, uint32_t n, int n_predictors, double* t_unc_sq, double* corr /*T*/, double* posthoc_sq,
+                     double* overall) {
+    const long df_signed = (long)n - (long)n_predictors;
+    if (df_signed < 1) invalid("df = N - P = " + std::to_string(n) + " - " + std::to_string(n_predictors) + " < 1");
+    const double df = (double)df_signed, alpha = s.alpha;
+    const bool use_t = s.estimator == E_OLS;  // EstimatorSpec::uses_student_t
+    auto quant = [&](double p) { return use_t ? crit::t_ppf(p, df) : crit::norm_ppf(p); };
+    const int m = s.T();
+    const double t_unc = quant(1.0 - alpha / 2.0);
+    if (t_unc_sq) *t_unc_sq = t_unc * t_unc;
+    if (corr) {
+        switch (s.correction) {
+            case C_NONE:
+                for (int i = 0; i < m; i++) corr[i] = t_unc * t_unc;
+                break;
+            case C_BONFERRONI: {
+                const double b = quant(1.0 - alpha / (2.0 * (double)m));
+                for (int i = 0; i < m; i++) corr[i] = b * b;
+                break;
+            }
+            case C_HOLM:
+                for (int i = 0; i < m; i++) {
+                    const double eff = alpha / (2.0 * (double)(m - i));
+                    const double t = eff < 1e-12 ? crit::kInf : quant(1.0 - eff);
+                    corr[i] = t * t;
+                }
+                break;
+            case C_BH:
+                for (int i = 0; i < m; i++) {
+                    const double eff = (double)(i + 1) / (double)m * alpha / 2.0;
+                    const double t = eff < 1e-12 ? crit::kInf : quant(1.0 - eff);
+                    corr[i] = t * t;
+                }
+                break;
+            case C_TUKEY:
+                for (int i = 0; i < m; i++) {
+                    const int nm = (int)s.target_indices.size();
+                    const int col = i < nm ? s.target_indices[i] : s.contrast_pairs[i - nm].first;
+                    const double t = crit::q_tukey_ppf(1.0 - alpha, tukey_k_for_col(s, col), df) / crit::kSqrt2;
+                    corr[i] = t * t;
+                }
+                break;
+        }
+    }
+    if (posthoc_sq) {
+        const double pa = std::isnan(s.posthoc_alpha) ? alpha : s.posthoc_alpha;
+        const double tp = quant(1.0 - pa / 2.0);
+        *posthoc_sq = tp * tp;
+    }
+    if (overall) {
+        const double npni = (double)std::max(n_predictors - 1, 0);
+        if (npni < 1.0) *overall = crit::kInf;
+        else if (s.estimator == E_OLS) *overall = crit::f_ppf(1.0 - alpha, npni, df);
+        else if (s.estimator == E_GLM) *overall = crit::chi2_ppf(1.0 - alpha, npni);
+        else *overall = crit::kInf;
+    }
+}
+
+// data_gen.rs:943-961 — the deterministic largest-remainder walk consumes no RNG, so its level
+// sequence is identical for every simulation: computed once per batch on the host.
+static std::vector<uint8_t> exact_walk_levels(const double* probs, int nl, int max_n) {
+    std::vector<uint8_t> out(max_n);
+    std::vector<uint32_t> counts(nl, 0);
+    double total = 0.0;
+    for (int g = 0; g < nl; g++) total += probs[g];
+    for (int i = 0; i < max_n; i++) {
+        uint32_t assigned = 0;
+        for (int g = 0; g < nl; g++) assigned += counts[g];
+        const double t = (double)(assigned + 1);
+        int best = 0;
+        double best_def = -crit::kInf;
+        for (int g = 0; g < nl; g++) {
+            const double def = (probs[g] / total) * t - (double)counts[g];
+            if (def > best_def) {
+                best_def = def;
+                best = g;
+            }
+        }
+        counts[best]++;
+        out[i] = (uint8_t)best;
+    }
+    return out;
+}
+
+static void check_supported(const Spec& s, bool generation_only = false) {
+    if (!generation_only && s.estimator != E_OLS) unsupported("estimator glm/mle (OLS arm only in this build; DESIGN.md §7)");
+    if (!generation_only && s.has_posthoc) unsupported("posthoc blocks");
+    if (s.has_upload) unsupported("uploaded-data marginals / bootstrap");
+    if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
+    if (s.has_between) unsupported("between_var_indices");
+    if (!s.is_optimistic()) unsupported("scenario perturbations (heterogeneity / heteroskedasticity / correlation noise / swaps)");
+    for (int v : s.var_types)
+        if (v >= 100) unsupported("uploaded_* variable types");
+    if (s.k > MCP_MAX_K) unsupported("n_non_factor > " + std::to_string(MCP_MAX_K));
+    if (s.P() > MCP_MAX_TEMPLATE_P) unsupported("n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
+    if (s.T() > MCP_MAX_T) unsupported("targets > " + std::to_string(MCP_MAX_T));
+    if (s.factor_n_levels.size() > MCP_MAX_FACTORS) unsupported("factors > " + std::to_string(MCP_MAX_FACTORS));
+    if (s.factor_proportions.size() > MCP_MAX_LEVELS) unsupported("Σ factor levels > " + std::to_string(MCP_MAX_LEVELS));
+    if (s.interactions.size() > MCP_MAX_INTER) unsupported("interactions > " + std::to_string(MCP_MAX_INTER));
+    size_t comps = 0;
+    for (auto& c : s.interactions) comps += c.size();
+    if (comps > MCP_MAX_INTER_COMP) unsupported("interaction components > " + std::to_string(MCP_MAX_INTER_COMP));
+    if (s.has_cluster && s.has_lme) unsupported("lme scenario knobs");
+}
+
+struct Lowered {
+    DevicePlan plan;
+    DeviceBuffers bufs;
+    int P = 0, T = 0, F = 0, n_ss = 0, cw = 0;
+};
+
+// SimulationSpec → DevicePlan (+ device-side tables).  Output pointers are filled by the caller.
+static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw, bool thresholds = true) {
+    DevicePlan& pl = lw.plan;
+    std::memset(&pl, 0, sizeof pl);
+    const int P = s.P(), T = s.T(), F = (int)s.factor_n_levels.size();
+    lw.P = P; lw.T = T; lw.F = F; lw.n_ss = (int)n_ss;
+    pl.k = s.k; pl.n_fd = s.n_fd; pl.n_factors = F; pl.n_inter = (int)s.interactions.size();
+    pl.P = P; pl.T = T; pl.n_marg = (int)s.target_indices.size(); pl.n_contrasts = (int)s.contrast_pairs.size();
+    pl.n_ss = (int)n_ss; pl.max_n = (int)ss[n_ss - 1];
+    pl.estimator = s.estimator; pl.outcome = s.outcome; pl.link_probit = s.link_probit; pl.correction = s.correction;
+    pl.report_overall = s.report_overall; pl.min_level_count = s.min_level_count;
+    // design
+    std::vector<double> L;
+    if (s.k > 0 && !correlation_llt(s.correlation, s.k, L))
+        throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
+    pl.l_identity = 1;
+    for (int j = 0; j < s.k; j++)
+        for (int m = 0; m < s.k; m++) {
+            const double v = L[(size_t)j * s.k + m];
+            pl.L[j * MCP_MAX_K + m] = v;
+            pl.corr[m * MCP_MAX_K + j] = s.correlation[(size_t)m * s.k + j];
+            if (v != (j == m ? 1.0 : 0.0)) pl.l_identity = 0;
+        }
+    pl.all_normal = 1;
+    for (int j = 0; j < s.k; j++) {
+        pl.var_type[j] = s.var_types[j];
+        pl.var_pinned[j] = j < (int)s.var_pinned.size() ? s.var_pinned[j] : 0;
+        pl.var_param[j] = j < (int)s.var_params.size() ? s.var_params[j] : 0.5;  // data_gen.rs:347
+        if (s.var_types[j] != D_NORMAL) pl.all_normal = 0;
+    }
+    int off = 0, col = 1 + s.k;
+    pl.exact_walk = 1;
+    for (int f = 0; f < F; f++) {
+        pl.f_levels[f] = s.factor_n_levels[f];
+        pl.f_off[f] = off;
+        pl.f_col[f] = col;
+        const int fs = f < (int)s.factor_sampled.size() ? s.factor_sampled[f] : -1;
+        pl.f_sampled[f] = fs < 0 ? (s.sampled_factor_proportions ? 1 : 0) : fs;
+        if (pl.f_sampled[f]) {
+            pl.exact_walk = 0;
+            pl.n_sampled_factors++;
+        }
+        for (int g = 0; g < s.factor_n_levels[f]; g++) pl.f_props[off + g] = s.factor_proportions[off + g];
+        off += s.factor_n_levels[f];
+        col += s.factor_n_levels[f] - 1;
+    }
+    int q = 0;
+    for (size_t j = 0; j < s.interactions.size(); j++) {
+        pl.inter_ptr[j] = q;
+        for (int c : s.interactions[j]) pl.inter_cols[q++] = c;
+    }
+    pl.inter_ptr[s.interactions.size()] = q;
+    for (int j = 0; j < P; j++) pl.beta[j] = s.effect_sizes[j];
+    for (int t = 0; t < pl.n_marg; t++) pl.target[t] = s.target_indices[t];
+    for (int t = 0; t < pl.n_contrasts; t++) {
+        pl.contrast[2 * t] = s.contrast_pairs[t].first;
+        pl.contrast[2 * t + 1] = s.contrast_pairs[t].second;
+    }
+    pl.residual_dist = s.residual_dist; pl.residual_pinned = s.residual_pinned; pl.residual_df = s.residual_df;
+    pl.has_cluster = s.has_cluster; pl.sizing_fixed_size = s.sizing_fixed_size; pl.sizing_value = s.sizing_value;
+    pl.tau_squared = s.tau_squared;
+    if (s.has_cluster) {
+        const int sv = std::max(s.sizing_value, 1);
+        pl.n_clusters = s.sizing_fixed_size ? pl.max_n / sv : sv;  // generation.rs n_clusters_at(max_n)
+    }
+    pl.optimistic = s.is_optimistic();
+
+    // variants + thresholds
+    const bool track = thresholds && F > 0 && s.min_level_count > 0;
+    if (!track) pl.min_level_count = 0;
+    const int nv = track ? (1 << F) : 1;
+    pl.n_variants = nv;
+    pl.base_variant = 0;
+    std::vector<McpVariant> variants(nv);
+    for (int m = 0; m < nv; m++) variants[m] = make_variant(s, m);
+    // which (variant, n_idx) pairs can occur?  Exact walks: exactly one mask per N (host-simulated).
+    std::vector<std::vector<uint8_t>> levels(F);
+    std::vector<uint8_t> levels_flat;
+    bool any_exact = false;
+    for (int f = 0; f < F; f++)
+        if (!pl.f_sampled[f]) {
+            levels[f] = exact_walk_levels(s.factor_proportions.data() + pl.f_off[f], s.factor_n_levels[f], pl.max_n);
+            any_exact = true;
+        }
+    if (any_exact) {
+        levels_flat.assign((size_t)F * pl.max_n, 0);
+        for (int f = 0; f < F; f++)
+            if (!levels[f].empty()) std::copy(levels[f].begin(), levels[f].end(), levels_flat.begin() + (size_t)f * pl.max_n);
+    }
+    std::vector<std::vector<char>> needed(nv, std::vector<char>(n_ss, track && !pl.exact_walk ? 1 : 0));
+    if (!track) {
+        for (uint32_t g = 0; g < n_ss; g++) needed[0][g] = 1;
+    } else if (pl.exact_walk) {
+        for (uint32_t g = 0; g < n_ss; g++) {
+            int mask = 0;
+            for (int f = 0; f < F; f++) {
+                std::vector<uint32_t> cnt(s.factor_n_levels[f], 0);
+                for (uint32_t i = 0; i < ss[g]; i++) cnt[levels[f][i]]++;
+                if (*std::min_element(cnt.begin(), cnt.end()) < (uint32_t)s.min_level_count) mask |= 1 << f;
+            }
+            needed[mask][g] = 1;
+        }
+    }
+    const double nan = crit::kNaN;
+    std::vector<double> c_unc((size_t)nv * n_ss, nan), c_corr((size_t)nv * n_ss * std::max(T, 1), nan), c_ov((size_t)nv * n_ss, nan);
+    // the full-model table is always validated first, like build_crit_tables at batch entry (batch.rs:349-350)
+    for (uint32_t g = 0; thresholds && g < n_ss; g++) {
+        double dummy;
+        crit_row(s, ss[g], P, &dummy, nullptr, nullptr, nullptr);
+    }
+    // thresholds depend on (N, p_red) only — memoise like reduced_crit_entry (batch.rs:2418-2437)
+    struct Memo { uint32_t n; int p; double unc, ov; std::vector<double> corr; };
+    std::vector<Memo> memo;
+    for (int m = 0; m < nv; m++)
+        for (uint32_t g = 0; g < n_ss; g++) {
+            if (!thresholds || !needed[m][g]) continue;
+            const int pr = variants[m].p_red;
+            if ((long)ss[g] - pr < 1) continue;
+            const Memo* hit = nullptr;
+            for (auto& e : memo)
+                if (e.n == ss[g] && e.p == pr) hit = &e;
+            if (!hit) {
+                Memo e{ss[g], pr, 0, 0, std::vector<double>(std::max(T, 1))};
+                crit_row(s, ss[g], pr, &e.unc, e.corr.data(), nullptr, &e.ov);
+                memo.push_back(e);
+                hit = &memo.back();
+            }
+            const size_t r = (size_t)m * n_ss + g;
+            c_unc[r] = hit->unc;
+            c_ov[r] = hit->ov;
+            for (int t = 0; t < T; t++) c_corr[r * T + t] = hit->corr[t];
+        }
+    std::vector<uint32_t> ssv(ss, ss + n_ss);
+    pl.ss = lw.bufs.upload(ssv);
+    pl.variants = lw.bufs.upload(variants);
+    pl.crit_unc = lw.bufs.upload(c_unc);
+    pl.crit_corr = lw.bufs.upload(c_corr);
+    pl.crit_overall = lw.bufs.upload(c_ov);
+    pl.levels = any_exact ? lw.bufs.upload(levels_flat) : nullptr;
+    bool need_t3 = false;
+    for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
+    if (need_t3) pl.t3_table = lw.bufs.upload(crit::build_t3_table());
+    pl.counter_width = mcp_counter_width(T, F);
+    lw.cw = pl.counter_width;
+    pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
+}
+
+// ---- kernel dispatch by P -----------------------------------------------------------------------
+template <int PT>
+static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
+    constexpr int SP = PT | 1;
+    size_t smem = (size_t)MCP_BLOCK * 4 * SP * sizeof(float);
+    if (lw.plan.smem_counters) smem += (size_t)lw.n_ss * lw.cw * sizeof(unsigned);
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        CUDA_CHECK(cudaFuncSetAttribute(ols_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done[dev & 63] = true;
+    }
+    const uint32_t blocks = (n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
+    ols_power_kernel<PT><<<blocks, MCP_BLOCK, smem, st>>>(base_seed, sim_begin, n_sims);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+#define MCP_FOR_EACH_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+static void dispatch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
+    switch (lw.P) {
+#define X(p) case p: launch_power<p>(lw, base_seed, sim_begin, n_sims, st); break;
+        MCP_FOR_EACH_P(X)
+#undef X
+        default: unsupported("n_predictors = " + std::to_string(lw.P));
+    }
+}
+
+static void select_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        throw EngineError(MCP_CUDA_ERROR, "no CUDA device available — the CUDA backend has no CPU fallback");
+    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
+}
+
+template <typename F>
+static int guarded(F&& body) {
+    try {
+        body();
+        return MCP_OK;
+    } catch (const EngineError& e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = std::string("internal error: ") + e.what();
+        return MCP_CUDA_ERROR;
+    }
+}
+
+}  // namespace mcp
+
+using namespace mcp;
+
+extern "C" {
+
+const char* mcp_last_error(void) { return g_last_error.c_str(); }
+const char* mcp_version(void) { return "mcpower_b200 0.1.0 (sm_100a)"; }
+uint64_t mcp_splitmix64(uint64_t z) { return splitmix64(z); }
+
+int mcp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void mcp_free_result(McpBatchResult* r) {
+    if (!r) return;
+    std::free(r->uncorrected);
+    std::free(r->corrected);
+    std::free(r->converged);
+    std::free(r->overall);
+    std::free(r->factor_excluded);
+    std::free(r->t_sq);
+    std::free(r->counters);
+    std::free(r);
+}
+
+int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
+                  uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user, McpBatchResult** out) {
+    return guarded([&] {
+        if (!out) invalid("out pointer is NULL");
+        *out = nullptr;
+        McpOptions opt{-1, MCP_MODE_COUNTS, 0, 0, 0};
+        if (options) opt = *options;
+        if (opt.mode == 0) opt.mode = MCP_MODE_COUNTS;
+        Spec s = parse_spec(spec_json, spec_len);
+        validate_spec(s, sample_sizes, n_ss);
+        check_supported(s);
+        select_device(opt.device);
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        Lowered lw;
+        lower(s, sample_sizes, n_ss, lw);
+        DevicePlan& pl = lw.plan;
+        const int T = lw.T, F = lw.F;
+        const bool bytes = opt.mode & MCP_MODE_BYTES, capture = opt.mode & MCP_MODE_CAPTURE;
+        const size_t cells = (size_t)n_sims * n_ss;
+        pl.counters = lw.bufs.alloc<unsigned long long>((size_t)n_ss * lw.cw);
+        CUDA_CHECK(cudaMemset(pl.counters, 0, (size_t)n_ss * lw.cw * sizeof(unsigned long long)));
+        if (bytes) {
+            pl.out_unc = lw.bufs.alloc<uint8_t>(cells * T);
+            pl.out_cor = lw.bufs.alloc<uint8_t>(cells * T);
+            pl.out_conv = lw.bufs.alloc<uint8_t>(cells);
+            if (s.report_overall) pl.out_overall = lw.bufs.alloc<uint8_t>(cells);
+            if (F > 0) pl.out_fx = lw.bufs.alloc<uint8_t>(cells * F);
+        }
+        if (capture) pl.out_tsq = lw.bufs.alloc<double>(cells * T);
+        CUDA_CHECK(cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan)));
+
+        McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
+        r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
+        r->counter_width = (uint32_t)lw.cw;
+        struct Guard { McpBatchResult* r; bool ok = false; ~Guard() { if (!ok) mcp_free_result(r); } } guard{r};
+
+        cudaStream_t st = 0;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        // batch.rs:449-450 — report ~50 times per run; cancellation is polled between waves
+        uint32_t wave = opt.wave_sims ? opt.wave_sims : (progress ? std::max<uint32_t>((n_sims + 49) / 50, MCP_BLOCK) : n_sims);
+        wave = std::max<uint32_t>(wave, 1);
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        bool cancelled = false;
+        for (uint64_t done = 0; done < n_sims;) {
+            const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_sims - done);
+            // the byte tensors are indexed by the sim's position in this call, so waves shift the base pointers
+            if (done > 0 && (bytes || capture)) {
+                DevicePlan shifted = pl;
+                if (bytes) {
+                    shifted.out_unc = pl.out_unc + done * n_ss * T;
+                    shifted.out_cor = pl.out_cor + done * n_ss * T;
+                    shifted.out_conv = pl.out_conv + done * n_ss;
+                    if (pl.out_overall) shifted.out_overall = pl.out_overall + done * n_ss;
+                    if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
+                }
+                if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
+                CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plan, &shifted, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st));
+            }
+            dispatch_power(lw, base_seed, opt.sim_begin + done, cnt, st);
+            r->gpu_launches++;
+            done += cnt;
+            if (progress) {
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                if (!progress(done, n_sims, user)) {
+                    cancelled = true;
+                    break;
+                }
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        r->kernel_ms = ms;
+        if (cancelled) throw EngineError(MCP_CANCELLED, "cancelled by host");  // partial results discarded (batch.rs:128-129)
+
+        auto fetch = [&](auto*& host, const auto* dev, size_t n) {
+            using Elem = std::remove_cv_t<std::remove_pointer_t<decltype(dev)>>;
+            host = static_cast<Elem*>(std::malloc(std::max<size_t>(n, 1) * sizeof(Elem)));
+            if (n) CUDA_CHECK(cudaMemcpy(host, dev, n * sizeof(Elem), cudaMemcpyDeviceToHost));
+        };
+        unsigned long long* cnt_host = nullptr;
+        fetch(cnt_host, pl.counters, (size_t)n_ss * lw.cw);
+        r->counters = reinterpret_cast<uint64_t*>(cnt_host);
+        if (bytes) {
+            fetch(r->uncorrected, pl.out_unc, cells * T);
+            fetch(r->corrected, pl.out_cor, cells * T);
+            fetch(r->converged, pl.out_conv, cells);
+            if (pl.out_overall) fetch(r->overall, pl.out_overall, cells);
+            if (pl.out_fx) fetch(r->factor_excluded, pl.out_fx, cells * F);
+        }
+        if (capture) fetch(r->t_sq, pl.out_tsq, cells * T);
+        guard.ok = true;
+        *out = r;
+    });
+}
+
+int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uint64_t base_seed, uint64_t sim_id, int32_t device,
+                     float* x_colmajor, float* y) {
+    return guarded([&] {
+        Spec s = parse_spec(spec_json, spec_len);
+        validate_spec(s, nullptr, 0);
+        check_supported(s, /*generation_only=*/true);
+        if (max_n == 0) invalid("max_n must be > 0");
+        select_device(device);
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        Lowered lw;
+        lower(s, &max_n, 1, lw, /*thresholds=*/false);
+        const int P = lw.P;
+        float* dx = lw.bufs.alloc<float>((size_t)max_n * P);
+        float* dy = lw.bufs.alloc<float>(max_n);
+        CUDA_CHECK(cudaMemcpyToSymbol(c_plan, &lw.plan, sizeof(DevicePlan)));
+        switch (P) {
+#define X(p) case p: dgp_dump_kernel<p><<<1, 32>>>(base_seed, sim_id, dx, dy); break;
+            MCP_FOR_EACH_P(X)
+#undef X
+            default: unsupported("n_predictors = " + std::to_string(P));
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * P * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(y, dy, (size_t)max_n * sizeof(float), cudaMemcpyDeviceToHost));
+    });
+}
+
+int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t p, int32_t device, double* out) {
+    return guarded([&] {
+        if (p < 1 || p > MCP_MAX_TEMPLATE_P) unsupported("p outside [1, " + std::to_string(MCP_MAX_TEMPLATE_P) + "]");
+        if (n <= p) invalid("df = N - P < 1");
+        select_device(device);
+        DeviceBuffers bufs;
+        double* dx = bufs.alloc<double>((size_t)n * p);
+        double* dy = bufs.alloc<double>(n);
+        double* dout = bufs.alloc<double>(3 * p + 4);
+        CUDA_CHECK(cudaMemcpy(dx, x_colmajor, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        switch ((int)p) {
+#define X(pp) case pp: fit_data_kernel<pp><<<1, 32>>>(dx, dy, (int)n, dout); break;
+            MCP_FOR_EACH_P(X)
+#undef X
+        }
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaMemcpy(out, dout, (3 * p + 4) * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int mcp_crit_table(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_predictors,
+                   double* t_unc_sq, double* corr_sq, double* posthoc_sq, double* overall) {
+    return guarded([&] {
+        Spec s = parse_spec(spec_json, spec_len);
+        const int T = s.T();
+        for (uint32_t g = 0; g < n_ss; g++)
+            crit_row(s, sample_sizes[g], (int)n_predictors, t_unc_sq ? t_unc_sq + g : nullptr, corr_sq ? corr_sq + (size_t)g * T : nullptr,
+                     posthoc_sq ? posthoc_sq + g : nullptr, overall ? overall + g : nullptr);
+    });
+}
+
+int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s) {
+    return guarded([&] {
+        select_device(device);
+        cudaDeviceProp prop;
+        int dev = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+        DeviceBuffers bufs;
+        double* sink = bufs.alloc<double>(1);
+        const int iters = 1 << 14, blocks = prop.multiProcessorCount * 8, threads = 256;
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        double ops_per_iter = 8;
+        auto run = [&](int it) {
+            switch (kind) {
+                case 0: pipe_bench_kernel<0><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
+                case 1: pipe_bench_kernel<1><<<blocks, threads>>>(it, sink); ops_per_iter = 16; break;
+                case 2: pipe_bench_kernel<2><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
+                case 3: pipe_bench_kernel<3><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
+                case 4: pipe_bench_kernel<4><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
+                default: invalid("unknown pipe_bench kind");
+            }
+        };
+        run(256);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            CUDA_CHECK(cudaEventRecord(e0));
+            run(iters);
+            CUDA_CHECK(cudaEventRecord(e1));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *thread_ops_per_s = ops_per_iter * (double)iters * (double)blocks * threads / (best * 1e-3);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// device_math.cuh — RNG and transform primitives of the MCPower data plane, sm_100a.
+//
+// This translation unit is compiled with -fmad=false: the reference's f32 kernel is
+// plain mul/add by contract (crates/engine-core/src/rng.rs:199-202,327-336), so nothing
+// may be contracted implicitly; every fused operation below is an explicit fma().
+// References are to crates/engine-core/src/.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+namespace mcp {
+
+// ---------------------------------------------------------------- seeds / Philox
+// rand_philox::splitmix64 (Mix13 finaliser; KAT tests/rng_byte_identity.rs:36-42)
+__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+// rng.rs:36-38
+__host__ __device__ inline uint64_t pcg_mix64(uint64_t base_seed, uint64_t sim_id) {
+    return splitmix64(base_seed ^ ((sim_id << 32) | (sim_id >> 32)));
+}
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+// Philox4x32-10 (Random123). 20 IMAD.WIDE.U32 + 20 LOP3 + key bumps per call.
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+// ---------------------------------------------------------------- f32 inverse-normal kernel (rng.rs:290-364)
+#define MCP_NI_BP 4.757499993e-01f
+#define MCP_NI_FLOOR 2.980232239e-08f
+#define MCP_NI_LN2 6.931471825e-01f
+
+// v = u - 0.5 with u = (2*(w>>9)+1)/2^24 (rand_philox::u32_to_unit_f32), built exactly with two
+// FADDs from the [1,2) mantissa trick instead of an I2F: (1 + k 2^-23) - 1.5 and + 2^-24 are both exact.
+__device__ __forceinline__ float word_to_v(uint32_t w) {
+    const float f = __uint_as_float(0x3f800000u | (w >> 9));
+    return (f - 1.5f) + 5.9604644775390625e-08f;
+}
+__device__ __forceinline__ float word_to_unit(uint32_t w) {
+    const float f = __uint_as_float(0x3f800000u | (w >> 9));
+    return (f - 1.0f) + 5.9604644775390625e-08f;
+}
+
+// central branch: v * Pc(v^2), 10 Horner steps of separate FMUL + FADD (no FFMA)
+__device__ __forceinline__ float ni_central(float v) {
+    const float r = v * v;
+    float a = 2.401336800e+08f;
+    a = a * r + -2.359132160e+08f;
+    a = a * r + 9.886485600e+07f;
+    a = a * r + -2.294391600e+07f;
+    a = a * r + 3.215264750e+06f;
+    a = a * r + -2.779154375e+05f;
+    a = a * r + 1.463396387e+04f;
+    a = a * r + -4.216123047e+02f;
+    a = a * r + 1.238584900e+01f;
+    a = a * r + 2.586458445e+00f;
+    a = a * r + 2.506664753e+00f;
+    return v * a;
+}
+
+// tail branch (|v| > BP): copysign(Pt(sqrt(-2 ln_f32(max(0.5-|v|, 2^-25)))), v)
+__device__ __noinline__ float ni_tail(float v) {
+    const float a = fabsf(v);
+    float t = 0.5f - a;
+    t = fmaxf(t, MCP_NI_FLOOR);
+    const uint32_t bits = __float_as_uint(t);
+    const float e = (float)((int)((bits >> 23) & 0xffu) - 127);
+    const float m = __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
+    float l = 4.342890903e-02f;
+    l = l * m + -4.048671722e-01f;
+    l = l * m + 1.593901396e+00f;
+    l = l * m + -3.492494345e+00f;
+    l = l * m + 5.046875954e+00f;
+    l = l * m + -2.786813021e+00f;
+    const float ln = (e + l) * MCP_NI_LN2;
+    const float q = __fsqrt_rn(-2.0f * ln);
+    float p = 2.100489240e-07f;
+    p = p * q + -9.117987247e-06f;
+    p = p * q + 1.774382981e-04f;
+    p = p * q + -2.041375730e-03f;
+    p = p * q + 1.541402005e-02f;
+    p = p * q + -8.018484712e-02f;
+    p = p * q + 2.937270701e-01f;
+    p = p * q + -7.639000416e-01f;
+    p = p * q + 2.428994656e+00f;
+    p = p * q + -2.150734663e+00f;
+    return copysignf(p, v);
+}
+
+__device__ __forceinline__ float norm_inv_from_word(uint32_t w) {
+    const float v = word_to_v(w);
+    return fabsf(v) <= MCP_NI_BP ? ni_central(v) : ni_tail(v);
+}
+
+// ---------------------------------------------------------------- sequential per-sim stream (rng.rs:51-128)
+// Counter-addressed view of the sequential stream: word index i lives in Philox block i>>2, lane i&3.
+struct SeqRng {
+    uint32_t k0, k1;
+    uint32_t pos;  // next word index
+    U4 buf;
+    uint32_t buf_block;
+    __device__ void init(uint64_t key) {
+        k0 = (uint32_t)key;
+        k1 = (uint32_t)(key >> 32);
+        pos = 0;
+        buf_block = 0xffffffffu;
+    }
+    __device__ uint32_t word_at(uint32_t i) {
+        const uint32_t blk = i >> 2;
+        if (blk != buf_block) {
+            buf = philox4x32_10(blk, 0u, 0u, 0u, k0, k1);
+            buf_block = blk;
+        }
+        const uint32_t l = i & 3u;
+        return l == 0 ? buf.x : (l == 1 ? buf.y : (l == 2 ? buf.z : buf.w));
+    }
+    __device__ uint32_t next_u32() { return word_at(pos++); }
+    __device__ float next_uniform() { return word_to_unit(next_u32()); }
+    __device__ float next_normal() { return norm_inv_from_word(next_u32()); }
+};
+
+// ---------------------------------------------------------------- owned exp / log (bit-identical twin of the oracle's)
+__device__ __forceinline__ double own_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
+    if (x < -745.1332191019412) return 0.0;
+    const double kf = rint(x * 1.4426950408889634);
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    const double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+    const double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+    return p * s1 * s2;
+}
+
+__device__ __forceinline__ double own_log(double x) {
+    if (x != x) return x;
+    if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+    if (x == 0.0) return __longlong_as_double(0xfff0000000000000LL);
+    if (x == __longlong_as_double(0x7ff0000000000000LL)) return x;
+    int k = 0;
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    if ((b >> 52) == 0) {
+        x *= 18014398509481984.0;
+        b = (unsigned long long)__double_as_longlong(x);
+        k -= 54;
+    }
+    k += (int)(b >> 52) - 1023;
+    const unsigned long long mant = b & 0x000fffffffffffffULL;
+    if (mant >= 0x6a09e667f3bcdULL) {
+        b = mant | 0x3fe0000000000000ULL;
+        k += 1;
+    } else {
+        b = mant | 0x3ff0000000000000ULL;
+    }
+    const double f = __longlong_as_double((long long)b) - 1.0;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+    const double t2 = z * (6.666666666666735130e-01 +
+                           w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
+// distributions.rs:32-56 — A&S 7.1.26
+__device__ __forceinline__ double phi(double z) {
+    const double x = -z * 0.70710678118654752440;
+    const double sign = x < 0.0 ? -1.0 : 1.0;
+    const double ax = fabs(x);
+    const double t = 1.0 / (1.0 + 0.3275911 * ax);
+    const double y =
+        1.0 - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t + 0.254829592) * t * own_exp(-ax * ax);
+    return 0.5 * (1.0 - sign * y);
+}
+
+#define MCP_EXP_CAP 6.95925599364711
+#define MCP_EXP_CENSORED_MEAN 0.9990501970288289
+#define MCP_EXP_CENSORED_STD 0.9933676327697134
+#define MCP_SQRT3 1.7320508075688772
+#define MCP_T3_RES 2048
+#define MCP_T3_PMIN 0.00121
+#define MCP_T3_PMAX 0.99879
+
+// marginals/t3.rs:78-92
+__device__ __forceinline__ double t3_lookup(const double* __restrict__ tab, double percentile) {
+    const double p = percentile < MCP_T3_PMIN ? MCP_T3_PMIN : (percentile > MCP_T3_PMAX ? MCP_T3_PMAX : percentile);
+    const double scale = (double)(MCP_T3_RES - 1) / (MCP_T3_PMAX - MCP_T3_PMIN);
+    const double idx = (p - MCP_T3_PMIN) * scale;
+    const int ii = (int)floor(idx);
+    const double frac = idx - (double)ii;
+    if (ii + 1 >= MCP_T3_RES) return tab[MCP_T3_RES - 1];
+    return tab[ii] * (1.0 - frac) + tab[ii + 1] * frac;
+}
+
+__device__ __forceinline__ double ln_floor(double u) {
+    const double FL = 1.0 / 2048.0;
+    return own_log(u < FL ? FL : u);
+}
+
+// data_gen.rs:1106-1182 (synthetic variants)
+__device__ __noinline__ double apply_marginal(double z, int dist, double param, const double* __restrict__ t3) {
+    switch (dist) {
+        case 1: return phi(z) < 1.0 - param ? 0.0 : 1.0;
+        case 2: {
+            double e = -ln_floor(phi(-z));
+            if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;
+            return (e - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD;
+        }
+        case 3: {
+            double e = -ln_floor(phi(z));
+            if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;
+            return (MCP_EXP_CENSORED_MEAN - e) / MCP_EXP_CENSORED_STD;
+        }
+        case 4: return t3_lookup(t3, phi(z));
+        case 5: return -MCP_SQRT3 + (MCP_SQRT3 - (-MCP_SQRT3)) * phi(z);
+        default: return z;
+    }
+}
+
+// rng.rs:399-419
+__device__ __noinline__ double poisson_quantile(double z, double lambda) {
+    if (!(lambda > 0.0)) return 0.0;
+    if (lambda <= 20.0) {
+        const double u = phi(z);
+        double p = own_exp(-lambda), cdf = p;
+        unsigned k = 0;
+        while (cdf < u && k < 200u) {
+            k++;
+            p *= lambda / (double)k;
+            cdf += p;
+        }
+        return (double)k;
+    }
+    const double v = floor(lambda + z * sqrt(lambda) + 0.5);
+    return v > 0.0 ? v : 0.0;
+}
+
+__device__ __forceinline__ double sigmoid_stable(double e) {
+    if (e >= 0.0) return 1.0 / (1.0 + own_exp(-e));
+    const double ex = own_exp(e);
+    return ex / (1.0 + ex);
+}
+
+}  // namespace mcp

@@ -1,0 +1,805 @@
+// kernels.cuh — the sm_100a hot path: one simulated study per thread, generated and
+// fitted entirely on-chip.
+//
+// Replaces engine_core::batch::run_one_sim (crates/engine-core/src/batch.rs:795-1213, OLS arm)
+// and generate_sim_data (data_gen.rs:87-925).  Mapping:
+//   * thread  = one simulation (global sim id → Philox key, rng.rs:36-69); a warp is 32
+//     independent studies in lock-step, so there is no cross-lane reduction, no idle lane
+//     in the P×P solve, and the integer outputs are independent of launch geometry.
+//   * rows are produced four at a time (one Philox4x32 block per column per 4 rows,
+//     rng.rs:130-137) into a per-thread f32 slab in shared memory — the reference's f32
+//     "generation plane" — then widened to f64 registers row by row (batch.rs:828-851).
+//   * X'X, X'y, y'y, Σy live in registers for the whole study (P(P+1)/2 + P + 2 doubles,
+//     P is a template parameter); nested sample sizes reuse the running sums
+//     (batch.rs:871-917) and re-solve at every grid point.
+//   * the inverse-normal tail branch (4.85 % of draws, rng.rs:354-364) is deferred: the
+//     central polynomial runs branch-free for every draw and tail lanes are patched from a
+//     per-thread bit mask afterwards, so a warp does not pay the tail path for every draw.
+// Generated data never touches HBM; the only global writes are counters (COUNTS mode) or the
+// 0/1 byte tensors of BatchResult (spec.rs:552-600).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_math.cuh"
+#include "plan.h"
+
+namespace mcp {
+
+__constant__ DevicePlan c_plan;
+
+#define MCP_BLOCK 128
+#define MCP_FNZ 1e-30   /* lib.rs:46 FLOAT_NEAR_ZERO */
+#define MCP_EPS_RANK 1e-12 /* batch.rs:41 */
+
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// ------------------------------------------------------------------------------------------
+// Per-fit results shared by the templated (registers) and generic (local memory) solvers.
+struct FitOut {
+    double sigma_sq, sst, rss, df_resid;
+    int converged;
+};
+
+// Cholesky + solves on a packed lower-triangular system held in registers (all indices static).
+// Same operation order as the oracle's ols_solve (oracle/mcp_oracle.c) → bit-identical t².
+template <int PT>
+struct RegSolver {
+    static constexpr int NACC = PT * (PT + 1) / 2;
+    double L[NACC];
+    double inv_d[PT];
+    double beta[PT];
+    FitOut out;
+
+    __device__ __forceinline__ void factor_and_solve(const double (&A)[NACC], const double (&b)[PT], double yty, double sum_y,
+                                                     uint32_t n_rows) {
+        int ok = 1;
+        double dmin = __longlong_as_double(0x7ff0000000000000LL), dmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                double s = A[tri(i, j)];
+#pragma unroll
+                for (int k = 0; k < j; k++) s = fma(-L[tri(i, k)], L[tri(j, k)], s);
+                if (i == j) {
+                    if (!(s > 0.0) || isinf(s)) {
+                        ok = 0;
+                        s = 1.0;
+                    }
+                    const double d = sqrt(s);
+                    L[tri(i, i)] = d;
+                    inv_d[i] = 1.0 / d;
+                    dmin = d < dmin ? d : dmin;
+                    dmax = d > dmax ? d : dmax;
+                } else {
+                    L[tri(i, j)] = s * inv_d[j];
+                }
+            }
+        }
+        if (ok && !(dmin / dmax >= MCP_EPS_RANK)) ok = 0;
+        double w[PT];
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            double s = b[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) s = fma(-L[tri(i, k)], w[k], s);
+            w[i] = s * inv_d[i];
+        }
+#pragma unroll
+        for (int i = PT - 1; i >= 0; i--) {
+            double s = w[i];
+#pragma unroll
+            for (int k = i + 1; k < PT; k++) s = fma(-L[tri(k, i)], beta[k], s);
+            beta[i] = s * inv_d[i];
+        }
+        double rss = yty;
+#pragma unroll
+        for (int i = 0; i < PT; i++) rss = fma(-w[i], w[i], rss);
+        const double n = (double)n_rows;
+        out.converged = ok;
+        out.rss = rss;
+        out.sst = yty - sum_y * sum_y / n;
+        out.df_resid = n - (double)PT;
+        out.sigma_sq = rss / out.df_resid;
+    }
+
+    // t² of c'β for c = e_pos − e_neg (neg < 0 → e_pos): (c'β)² / (σ² ‖L⁻¹c‖²)   (posthoc.rs:3-8)
+    __device__ __forceinline__ double t_sq(int pos, int neg) const {
+        double u[PT];
+        double q = 0.0, est = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            double s = (i == pos ? 1.0 : 0.0) - (i == neg ? 1.0 : 0.0);
+#pragma unroll
+            for (int k = 0; k < i; k++) s = fma(-L[tri(i, k)], u[k], s);
+            u[i] = s * inv_d[i];
+            q = fma(u[i], u[i], q);
+            if (i == pos) est += beta[i];
+        }
+        if (neg >= 0) {
+            double bn = 0.0;
+#pragma unroll
+            for (int i = 0; i < PT; i++)
+                if (i == neg) bn = beta[i];
+            est = est - bn;
+        }
+        const double var = out.sigma_sq * q;
+        if (!(var > MCP_FNZ) || isinf(var)) return __longlong_as_double(0x7ff8000000000000LL);
+        return est * est / var;
+    }
+};
+
+// Generic solver on local-memory arrays (runtime p): sparse-factor-exclusion / test-design
+// reduced fits (batch.rs:970-1013).  Cold path.
+template <int PMAX>
+struct MemSolver {
+    double L[PMAX * (PMAX + 1) / 2];
+    double inv_d[PMAX];
+    double beta[PMAX];
+    double w[PMAX];
+    FitOut out;
+    int p;
+
+    __device__ __noinline__ void factor_and_solve(const double* A, const double* b, int p_, double yty, double sum_y, uint32_t n_rows) {
+        p = p_;
+        int ok = 1;
+        double dmin = __longlong_as_double(0x7ff0000000000000LL), dmax = 0.0;
+        for (int i = 0; i < p; i++) {
+            for (int j = 0; j <= i; j++) {
+                double s = A[tri(i, j)];
+                for (int k = 0; k < j; k++) s = fma(-L[tri(i, k)], L[tri(j, k)], s);
+                if (i == j) {
+                    if (!(s > 0.0) || isinf(s)) {
+                        ok = 0;
+                        s = 1.0;
+                    }
+                    const double d = sqrt(s);
+                    L[tri(i, i)] = d;
+                    inv_d[i] = 1.0 / d;
+                    dmin = d < dmin ? d : dmin;
+                    dmax = d > dmax ? d : dmax;
+                } else {
+                    L[tri(i, j)] = s * inv_d[j];
+                }
+            }
+        }
+        if (ok && !(dmin / dmax >= MCP_EPS_RANK)) ok = 0;
+        for (int i = 0; i < p; i++) {
+            double s = b[i];
+            for (int k = 0; k < i; k++) s = fma(-L[tri(i, k)], w[k], s);
+            w[i] = s * inv_d[i];
+        }
+        for (int i = p - 1; i >= 0; i--) {
+            double s = w[i];
+            for (int k = i + 1; k < p; k++) s = fma(-L[tri(k, i)], beta[k], s);
+            beta[i] = s * inv_d[i];
+        }
+        double rss = yty;
+        for (int i = 0; i < p; i++) rss = fma(-w[i], w[i], rss);
+        const double n = (double)n_rows;
+        out.converged = ok;
+        out.rss = rss;
+        out.sst = yty - sum_y * sum_y / n;
+        out.df_resid = n - (double)p;
+        out.sigma_sq = rss / out.df_resid;
+    }
+
+    __device__ __noinline__ double t_sq(int pos, int neg) {
+        int start = pos;
+        if (neg >= 0 && neg < start) start = neg;
+        double q = 0.0;
+        for (int i = start; i < p; i++) {
+            double s = (i == pos ? 1.0 : 0.0) - (i == neg ? 1.0 : 0.0);
+            for (int k = start; k < i; k++) s = fma(-L[tri(i, k)], w[k], s);  // w reused as u
+            w[i] = s * inv_d[i];
+            q = fma(w[i], w[i], q);
+        }
+        const double est = neg >= 0 ? beta[pos] - beta[neg] : beta[pos];
+        const double var = out.sigma_sq * q;
+        if (!(var > MCP_FNZ) || isinf(var)) return __longlong_as_double(0x7ff8000000000000LL);
+        return est * est / var;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Significance decisions + corrections (batch.rs:1089-1142, correction.rs:16-115) and output.
+// `all_t` lives in local memory (T is a runtime count); executed once per fit.
+__device__ __forceinline__ bool gt_crit(double t, double c) { return !(t != t) && t > c; }
+
+// order[] = indices sorted by t² descending, NaN last, ties by ascending index (stable insertion sort)
+__device__ __noinline__ void sort_desc(const double* t_sq, int n, int8_t* order) {
+    for (int i = 0; i < n; i++) order[i] = (int8_t)i;
+    for (int i = 1; i < n; i++) {
+        const int v = order[i];
+        const double b = t_sq[v];
+        const bool b_nan = b != b;
+        int j = i - 1;
+        while (j >= 0) {
+            const double a = t_sq[order[j]];
+            const bool a_nan = a != a;
+            bool move;
+            if (a_nan && b_nan) move = false;
+            else if (a_nan) move = true;
+            else if (b_nan) move = false;
+            else move = a < b || (a == b && signbit(a) && !signbit(b));
+            if (!move) break;
+            order[j + 1] = order[j];
+            j--;
+        }
+        order[j + 1] = (int8_t)v;
+    }
+}
+
+__device__ __noinline__ void apply_correction(int method, const double* t_sq, int T, double crit_unc, const double* __restrict__ crit_row,
+                                              uint8_t* out) {
+    for (int i = 0; i < T; i++) out[i] = 0;
+    if (method == C_NONE) {
+        for (int i = 0; i < T; i++) out[i] = gt_crit(t_sq[i], crit_unc);
+    } else if (method == C_BONFERRONI || method == C_TUKEY) {
+        for (int i = 0; i < T; i++) out[i] = gt_crit(t_sq[i], crit_row[i]);
+    } else {
+        int8_t order[MCP_MAX_T];
+        sort_desc(t_sq, T, order);
+        if (method == C_HOLM) {
+            for (int k = 0; k < T; k++) {
+                if (gt_crit(t_sq[order[k]], crit_row[k])) out[order[k]] = 1;
+                else break;
+            }
+        } else {
+            int last = -1;
+            for (int k = 0; k < T; k++)
+                if (gt_crit(t_sq[order[k]], crit_row[k])) last = k;
+            for (int k = 0; k <= last; k++) out[order[k]] = 1;
+        }
+    }
+}
+
+// Warp-aggregated counter add: one atomic per warp per flag.
+__device__ __forceinline__ void count_flag(unsigned int* cnt_s, unsigned long long* cnt_g, int idx, bool flag) {
+    const unsigned am = __activemask();
+    const unsigned b = __ballot_sync(am, flag);
+    if (b != 0u && (threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) {
+        if (cnt_s) atomicAdd(&cnt_s[idx], (unsigned)__popc(b));
+        else atomicAdd(&cnt_g[idx], (unsigned long long)__popc(b));
+    }
+}
+
+struct SimOut {
+    unsigned int* cnt_s;  // shared-memory counters or NULL
+    uint64_t sim_local;   // index into the byte tensors
+};
+
+// Emit one fit: decisions, corrections, overall F, counters/bytes.  all_t = T squared statistics (NaN = untestable).
+__device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
+                                      const uint8_t* excl_flags) {
+    const DevicePlan& pl = c_plan;
+    const int T = pl.T;
+    const size_t vrow = (size_t)variant * pl.n_ss + g;
+    const double crit_unc = pl.crit_unc[vrow];
+    uint8_t unc[MCP_MAX_T], cor[MCP_MAX_T];
+    int n_unc = 0, n_cor = 0;
+    if (fit.converged) {
+        for (int t = 0; t < T; t++) {
+            unc[t] = gt_crit(all_t[t], crit_unc);
+            n_unc += unc[t];
+        }
+        apply_correction(pl.correction, all_t, T, crit_unc, pl.crit_corr + vrow * T, cor);
+        for (int t = 0; t < T; t++) n_cor += cor[t];
+    } else {
+        for (int t = 0; t < T; t++) {
+            unc[t] = 0;
+            cor[t] = 0;
+            all_t[t] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+    uint8_t ov = 0;
+    if (pl.report_overall && fit.converged) {
+        const double dfn = (double)(p_red - 1), dfd = fit.df_resid;
+        if (dfn >= 1.0 && fit.sst > 1e-10 && fit.rss > 0.0 && !isinf(fit.rss) && fit.rss == fit.rss && !isinf(fit.sst) &&
+            fit.sst == fit.sst) {
+            const double f = ((fit.sst - fit.rss) / dfn) / (fit.rss / dfd);
+            if (f == f && !isinf(f) && f > pl.crit_overall[vrow]) ov = 1;
+        }
+    }
+    // ---- counters (what aggregate_batch derives, aggregation.rs:91-242)
+    unsigned int* cs = so.cnt_s ? so.cnt_s + (size_t)g * pl.counter_width : nullptr;
+    unsigned long long* cg = pl.counters + (size_t)g * pl.counter_width;
+    for (int t = 0; t < T; t++) {
+        count_flag(cs, cg, t, unc[t] != 0);
+        count_flag(cs, cg, T + t, cor[t] != 0);
+    }
+    count_flag(cs, cg, 2 * T, fit.converged != 0);
+    count_flag(cs, cg, 2 * T + 1, ov != 0);
+    if (cs) {
+        atomicAdd(&cs[2 * T + 2 + n_unc], 1u);
+        atomicAdd(&cs[3 * T + 3 + n_cor], 1u);
+    } else {
+        atomicAdd(&cg[2 * T + 2 + n_unc], 1ull);
+        atomicAdd(&cg[3 * T + 3 + n_cor], 1ull);
+    }
+    for (int f = 0; f < pl.n_factors; f++) count_flag(cs, cg, 4 * T + 4 + f, excl_flags && excl_flags[f] != 0);
+    // ---- BatchResult byte tensors (spec.rs:552-600), sim-major
+    if (pl.out_unc) {
+        const size_t cell = so.sim_local * pl.n_ss + g;
+        for (int t = 0; t < T; t++) {
+            pl.out_unc[cell * T + t] = unc[t];
+            pl.out_cor[cell * T + t] = cor[t];
+        }
+        pl.out_conv[cell] = (uint8_t)fit.converged;
+        if (pl.out_overall) pl.out_overall[cell] = ov;
+        if (pl.out_fx)
+            for (int f = 0; f < pl.n_factors; f++) pl.out_fx[cell * pl.n_factors + f] = excl_flags ? excl_flags[f] : 0;
+    }
+    if (pl.out_tsq) {
+        const size_t cell = so.sim_local * pl.n_ss + g;
+        for (int t = 0; t < T; t++) pl.out_tsq[cell * T + t] = all_t[t];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-sim generation context.
+struct SimCtx {
+    uint32_t k0, k1;       // Philox key words (rng.rs:62-64)
+    SeqRng seq;            // counter-addressed view of the sequential stream
+    double tau;            // sqrt(tau²) of the random intercept
+    uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
+};
+
+// Residual for one row from CLASS_RESID slots (data_gen.rs:412-484).  slot0 = slot-0 normal already generated.
+__device__ __noinline__ float transform_residual(int dist, double df_in, float slot0, uint32_t blk, int lane, uint32_t k0, uint32_t k1) {
+    const double df = df_in > 3.0 ? df_in : 3.0;
+    long long dfi = llround(df);
+    if (dfi < 1) dfi = 1;
+    double chi2 = 0.0;
+    const bool is_t = dist == R_HIGH_KURTOSIS;
+    if (!is_t) {  // right/left skewed: slots 0..df-1, slot 0 is the draw we already have
+        const double gg = (double)slot0;
+        chi2 += gg * gg;
+    }
+    for (long long s = is_t ? 0 : 1; s < dfi; s++) {
+        const U4 w = philox4x32_10(blk, (uint32_t)(is_t ? 1 + s : s), 2u, 0u, k0, k1);
+        const uint32_t ww = lane == 0 ? w.x : (lane == 1 ? w.y : (lane == 2 ? w.z : w.w));
+        const double gg = (double)norm_inv_from_word(ww);
+        chi2 += gg * gg;
+    }
+    if (is_t) {
+        const double scale = 1.0 / sqrt(df / (df - 2.0));
+        const double z = (double)slot0;
+        const double denom = sqrt(chi2 / df);
+        const double t = denom <= 0.0 ? z : z / denom;
+        return (float)(t * scale);
+    }
+    const double scale = 1.0 / sqrt(2.0 * df);
+    const double sign = dist == R_LEFT_SKEWED ? -1.0 : 1.0;
+    return (float)(sign * (chi2 - df) * scale);
+}
+
+// Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
+//   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
+template <int PT>
+__device__ __forceinline__ void gen_block(int b, float* __restrict__ slab, SimCtx& cx) {
+    const DevicePlan& pl = c_plan;
+    const int k = pl.k;
+    const uint32_t k0 = cx.k0, k1 = cx.k1;
+    // ---- A. normals for the continuous block (CLASS_XNORM=1, column j) and residual slot 0 (CLASS_RESID=2)
+    unsigned long long tmask = 0ull;
+#pragma unroll 2
+    for (int j = 0; j < k; j++) {
+        const U4 w = philox4x32_10((uint32_t)b, (uint32_t)j, 1u, 0u, k0, k1);
+        const float v0 = word_to_v(w.x), v1 = word_to_v(w.y), v2 = word_to_v(w.z), v3 = word_to_v(w.w);
+        float4 z;
+        z.x = ni_central(v0);
+        z.y = ni_central(v1);
+        z.z = ni_central(v2);
+        z.w = ni_central(v3);
+        if (j < 15) {
+            unsigned tb = 0u;
+            if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
+            if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
+            if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
+            if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
+            tmask |= (unsigned long long)tb << (4 * j);
+        } else {
+            if (fabsf(v0) > MCP_NI_BP) z.x = ni_tail(v0);
+            if (fabsf(v1) > MCP_NI_BP) z.y = ni_tail(v1);
+            if (fabsf(v2) > MCP_NI_BP) z.z = ni_tail(v2);
+            if (fabsf(v3) > MCP_NI_BP) z.w = ni_tail(v3);
+        }
+        *reinterpret_cast<float4*>(slab + 4 * j) = z;
+    }
+    {
+        const U4 w = philox4x32_10((uint32_t)b, 0u, 2u, 0u, k0, k1);
+        float4 z;
+        const bool uniform_slot0 = (pl.outcome == O_CONTINUOUS && pl.residual_dist == R_UNIFORM) ||
+                                   (pl.outcome == O_BINARY && !pl.link_probit);
+        if (!uniform_slot0) {
+            const float v0 = word_to_v(w.x), v1 = word_to_v(w.y), v2 = word_to_v(w.z), v3 = word_to_v(w.w);
+            z.x = ni_central(v0);
+            z.y = ni_central(v1);
+            z.z = ni_central(v2);
+            z.w = ni_central(v3);
+            unsigned tb = 0u;
+            if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
+            if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
+            if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
+            if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
+            tmask |= (unsigned long long)tb << 60;
+        } else if (pl.outcome == O_CONTINUOUS) {  // Uniform residual: (2u-1)*sqrt(3) (data_gen.rs:485-501)
+            z.x = (float)((2.0 * (double)word_to_unit(w.x) - 1.0) * MCP_SQRT3);
+            z.y = (float)((2.0 * (double)word_to_unit(w.y) - 1.0) * MCP_SQRT3);
+            z.z = (float)((2.0 * (double)word_to_unit(w.z) - 1.0) * MCP_SQRT3);
+            z.w = (float)((2.0 * (double)word_to_unit(w.w) - 1.0) * MCP_SQRT3);
+        } else {  // logit: the raw uniform is compared against sigmoid(eta) (data_gen.rs:390-398)
+            z.x = word_to_unit(w.x);
+            z.y = word_to_unit(w.y);
+            z.z = word_to_unit(w.z);
+            z.w = word_to_unit(w.w);
+        }
+        *reinterpret_cast<float4*>(slab + 4 * (PT - 1)) = z;
+    }
+    // ---- B. deferred tail branch of the inverse-normal kernel
+    while (tmask) {
+        const int bit = __ffsll((long long)tmask) - 1;
+        tmask &= tmask - 1ull;
+        const int c = bit >> 2;
+        const int idx = (c == 15 ? (PT - 1) : c) * 4 + (bit & 3);
+        slab[idx] = ni_tail(slab[idx]);
+    }
+    // ---- B'. t / chi-square residuals need extra CLASS_RESID slots
+    if (pl.outcome == O_CONTINUOUS && pl.residual_dist != R_NORMAL && pl.residual_dist != R_UNIFORM) {
+        for (int r = 0; r < 4; r++)
+            slab[4 * (PT - 1) + r] = transform_residual(pl.residual_dist, pl.residual_df, slab[4 * (PT - 1) + r], (uint32_t)b, r, k0, k1);
+    }
+    // ---- C. Cholesky mix + marginal transforms (data_gen.rs:334-363); skipped when L = I and all Normal
+    if (!(pl.l_identity && pl.all_normal)) {
+        for (int r = 0; r < 4; r++) {
+            double zr[PT];  // zr[j] = z of continuous column j (j < k)
+#pragma unroll
+            for (int j = 0; j < PT - 1; j++) zr[j] = j < k ? (double)slab[4 * j + r] : 0.0;
+#pragma unroll
+            for (int j = PT - 2; j >= 0; j--) {
+                if (j < k) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int m = 0; m <= j; m++) a = a + pl.L[j * MCP_MAX_K + m] * zr[m];
+                    float xf = (float)a;
+                    const int vt = pl.var_type[j];
+                    if (vt != D_NORMAL) xf = (float)apply_marginal((double)xf, vt, pl.var_param[j], pl.t3_table);
+                    slab[4 * j + r] = xf;
+                }
+            }
+        }
+    }
+    // ---- D. factor dummies (data_gen.rs:509-551) and interactions (643-649), in the f32 plane
+    if (pl.n_factors > 0 || pl.n_inter > 0) {
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * b + r;
+            if (row >= pl.max_n) break;
+            int sidx = 0;
+            for (int f = 0; f < pl.n_factors; f++) {
+                const int nl = pl.f_levels[f];
+                int lvl;
+                if (!pl.f_sampled[f]) {
+                    lvl = pl.levels[(size_t)f * pl.max_n + row];
+                } else {  // next_categorical on the sequential stream (rng.rs:112-127), counter-addressed
+                    const uint32_t widx = cx.seq_row_base + (uint32_t)row * (uint32_t)pl.n_sampled_factors + (uint32_t)sidx;
+                    const double u = (double)word_to_unit(cx.seq.word_at(widx));
+                    const double* pr = pl.f_props + pl.f_off[f];
+                    double ca = 0.0;
+                    lvl = nl - 1;
+                    for (int q = 0; q < nl; q++) {
+                        ca += pr[q];
+                        if (u < ca) { lvl = q; break; }
+                    }
+                    sidx++;
+                }
+                const int c0 = pl.f_col[f] - 1;
+                for (int d = 0; d < nl - 1; d++) slab[4 * (c0 + d) + r] = (lvl == d + 1) ? 1.0f : 0.0f;
+            }
+            const int ib = k + pl.n_fd;
+            for (int j = 0; j < pl.n_inter; j++) {
+                double prod = 1.0;
+                for (int q = pl.inter_ptr[j]; q < pl.inter_ptr[j + 1]; q++) prod *= (double)slab[4 * (pl.inter_cols[q] - 1) + r];
+                slab[4 * (ib + j) + r] = (float)prod;
+            }
+        }
+    }
+}
+
+// Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
+template <int PT>
+__device__ __forceinline__ double row_xy(int b, int r, const float* __restrict__ slab, SimCtx& cx, double (&xr)[PT]) {
+    const DevicePlan& pl = c_plan;
+    const int row = 4 * b + r;
+    xr[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j < PT; j++) xr[j] = (double)slab[4 * (j - 1) + r];
+    double lp = 0.0;
+#pragma unroll
+    for (int j = 0; j < PT; j++) lp = lp + xr[j] * pl.beta[j];
+    const float ef = slab[4 * (PT - 1) + r];
+    double u_re = 0.0;
+    if (pl.has_cluster) {  // u_c = f32(normal(word c) * tau), drawn first on the sequential stream (data_gen.rs:146-161)
+        const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+        const uint32_t cid = pl.sizing_fixed_size ? (uint32_t)(row / cs) : (uint32_t)(row % cs);
+        u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
+    }
+    if (pl.outcome == O_CONTINUOUS) return (double)(float)(lp + (double)ef + u_re);
+    const double eta = lp + u_re;
+    if (pl.outcome == O_BINARY) {
+        const double thr = pl.link_probit ? eta : sigmoid_stable(eta);
+        return (double)ef < thr ? 1.0 : 0.0;
+    }
+    return (double)(float)poisson_quantile((double)ef, own_exp(eta));
+}
+
+// ------------------------------------------------------------------------------------------
+// The OLS power kernel.
+//   PT  : total design columns P (compile-time → register-resident sufficient statistics)
+// Dynamic shared memory: [MCP_BLOCK] per-thread slabs of 4*SP floats (SP = P|1 keeps the per-thread
+// LDS.128/STS.128 conflict-free), then the optional block-level counters.
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) ols_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    constexpr int SP = PT | 1;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    float* slab = smem + (size_t)threadIdx.x * (4 * SP);
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    if (sim < n_sims) {
+        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+        SimCtx cx;
+        cx.k0 = (uint32_t)key;
+        cx.k1 = (uint32_t)(key >> 32);
+        cx.seq.init(key);
+        cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
+        cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;  // Normal RE: one word per cluster
+        const int max_n = pl.max_n;
+        SimOut so{cnt_s, (uint64_t)sim};
+
+        double acc[NACC], xty[PT];
+#pragma unroll
+        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) xty[i] = 0.0;
+        double yty = 0.0, sum_y = 0.0;
+        uint32_t n_rows = 0;
+
+        uint32_t lvl_counts[MCP_MAX_LEVELS];
+        uint8_t excl[MCP_MAX_FACTORS];
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        if (track_excl)
+            for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+
+        int g = 0;
+        uint32_t n_next = pl.ss[0];
+        const int n_blocks = (max_n + 3) >> 2;
+
+        for (int b = 0; b < n_blocks; b++) {
+            gen_block<PT>(b, slab, cx);
+            // ---- E. row pass: widen, linear predictor, y, sufficient statistics, fits at grid points
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                const int row = 4 * b + r;
+                if (row >= max_n) break;
+                double xr[PT];
+                const double yd = row_xy<PT>(b, r, slab, cx, xr);
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+#pragma unroll
+                    for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
+                    xty[a] = fma(xr[a], yd, xty[a]);
+                }
+                yty = fma(yd, yd, yty);
+                sum_y += yd;
+                n_rows++;
+                if (track_excl) {  // batch.rs:2451-2496
+                    for (int f = 0; f < pl.n_factors; f++) {
+                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
+                        int lvl = 0;
+                        for (int d = 0; d < nl - 1; d++)
+                            if (slab[4 * (c0 + d) + r] == 1.0f) { lvl = d + 1; break; }
+                        lvl_counts[pl.f_off[f] + lvl]++;
+                    }
+                }
+                if ((uint32_t)(row + 1) == n_next) {
+                    // ---- fit at grid point g
+                    int variant = pl.base_variant;
+                    if (track_excl) {
+                        int maskbits = 0;
+                        for (int f = 0; f < pl.n_factors; f++) {
+                            uint32_t mn = 0xffffffffu;
+                            for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
+                            excl[f] = mn < (uint32_t)pl.min_level_count;
+                            maskbits |= (int)excl[f] << f;
+                        }
+                        variant = maskbits;
+                    }
+                    const McpVariant& vr = pl.variants[variant];
+                    double all_t[MCP_MAX_T];
+                    if (vr.p_red == PT) {
+                        RegSolver<PT> sv;
+                        sv.factor_and_solve(acc, xty, yty, sum_y, n_rows);
+                        for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
+                        for (int t = 0; t < pl.n_contrasts; t++)
+                            all_t[pl.n_marg + t] = sv.t_sq(pl.contrast[2 * t], pl.contrast[2 * t + 1]);
+                        emit_fit(so, g, variant, sv.out, PT, all_t, excl);
+                    } else {
+                        // reduced model: gather kept rows/cols of the sufficient statistics (batch.rs:970-1013)
+                        double Af[NACC], bf[PT];
+#pragma unroll
+                        for (int i = 0; i < NACC; i++) Af[i] = acc[i];
+#pragma unroll
+                        for (int i = 0; i < PT; i++) bf[i] = xty[i];
+                        double Ar[NACC], br[PT];
+                        const int pr = vr.p_red;
+                        for (int ri = 0; ri < pr; ri++) {
+                            br[ri] = bf[vr.kept[ri]];
+                            for (int rj = 0; rj <= ri; rj++) Ar[tri(ri, rj)] = Af[tri(vr.kept[ri], vr.kept[rj])];
+                        }
+                        MemSolver<PT> ms;
+                        ms.factor_and_solve(Ar, br, pr, yty, sum_y, n_rows);
+                        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                        for (int t = 0; t < pl.n_marg; t++) {
+                            const int c = vr.remap[pl.target[t]];
+                            all_t[t] = c >= 0 ? ms.t_sq(c, -1) : nan;
+                        }
+                        for (int t = 0; t < pl.n_contrasts; t++) {
+                            const int pc = vr.remap[pl.contrast[2 * t]], nc = vr.remap[pl.contrast[2 * t + 1]];
+                            all_t[pl.n_marg + t] = (pc >= 0 && nc >= 0) ? ms.t_sq(pc, nc) : nan;
+                        }
+                        emit_fit(so, g, variant, ms.out, pr, all_t, excl);
+                    }
+                    g++;
+                    n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+                }
+            }
+        }
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: dump the generated design of one simulation (introspect::capture_sim0_data, introspect.rs:104-155)
+// through exactly the same generation functions as the power kernel.  One thread; parity/debug only.
+template <int PT>
+__global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __restrict__ x_out /* col-major max_n × P */,
+                                float* __restrict__ y_out) {
+    constexpr int SP = PT | 1;
+    const DevicePlan& pl = c_plan;
+    __shared__ __align__(16) float slab[4 * SP];
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint64_t key = pcg_mix64(base_seed, sim_id);
+    SimCtx cx;
+    cx.k0 = (uint32_t)key;
+    cx.k1 = (uint32_t)(key >> 32);
+    cx.seq.init(key);
+    cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
+    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
+    const int max_n = pl.max_n;
+    for (int b = 0; b < (max_n + 3) / 4; b++) {
+        gen_block<PT>(b, slab, cx);
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * b + r;
+            if (row >= max_n) break;
+            double xr[PT];
+            const double yd = row_xy<PT>(b, r, slab, cx, xr);
+            x_out[row] = 1.0f;
+            for (int j = 1; j < PT; j++) x_out[(size_t)j * max_n + row] = slab[4 * (j - 1) + r];
+            y_out[row] = (float)yd;
+        }
+    }
+}
+
+// K0b: OLS on supplied bytes (introspect::fit_provided_data, introspect.rs:174-293): narrow to f32, widen, same
+// sufficient statistics + solver as the power kernel.  One thread.
+template <int PT>
+__global__ void fit_data_kernel(const double* __restrict__ x /* col-major n × P */, const double* __restrict__ y, int n,
+                                double* __restrict__ out /* beta[P], se[P], t_sq[P], sigma_sq, sst, rss, converged */) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double acc[NACC], xty[PT];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PT; i++) xty[i] = 0.0;
+    double yty = 0.0, sum_y = 0.0;
+    for (int row = 0; row < n; row++) {
+        double xr[PT];
+#pragma unroll
+        for (int j = 0; j < PT; j++) xr[j] = (double)(float)x[(size_t)j * n + row];
+        const double yd = (double)(float)y[row];
+#pragma unroll
+        for (int a = 0; a < PT; a++) {
+#pragma unroll
+            for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
+            xty[a] = fma(xr[a], yd, xty[a]);
+        }
+        yty = fma(yd, yd, yty);
+        sum_y += yd;
+    }
+    RegSolver<PT> sv;
+    sv.factor_and_solve(acc, xty, yty, sum_y, (uint32_t)n);
+    for (int t = 0; t < PT; t++) {
+        const double t2 = sv.t_sq(t, -1);
+        double b = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++)
+            if (i == t) b = sv.beta[i];
+        out[t] = b;
+        out[PT + t] = sqrt(b * b / t2);
+        out[2 * PT + t] = t2;
+    }
+    out[3 * PT] = sv.out.sigma_sq;
+    out[3 * PT + 1] = sv.out.sst;
+    out[3 * PT + 2] = sv.out.rss;
+    out[3 * PT + 3] = (double)sv.out.converged;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pipe micro-benchmarks: measured denominators for the issue/FP64 roofline (SURVEY.md §8d —
+// MEASURED_PEAKS.json has no FP64/FP32/INT peak).  Each thread runs `iters` rounds of 8 independent
+// dependent-chains of one instruction class; the host converts elapsed time to thread-ops/s.
+template <int KIND>
+__global__ void __launch_bounds__(256) pipe_bench_kernel(int iters, double* sink) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (KIND == 0) {  // DFMA
+        double a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+        const double m = 1.0000001, c = 1e-9;
+        for (int i = 0; i < iters; i++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+        if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345) sink[0] = a0;
+    } else if (KIND == 1) {  // FMUL + FADD pairs (the no-FMA Horner step)
+        float a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+        const float m = 0.999f;
+        for (int i = 0; i < iters; i++) {
+            a0 = a0 * m + 1.5f; a1 = a1 * m + 1.5f; a2 = a2 * m + 1.5f; a3 = a3 * m + 1.5f;
+            a4 = a4 * m + 1.5f; a5 = a5 * m + 1.5f; a6 = a6 * m + 1.5f; a7 = a7 * m + 1.5f;
+        }
+        if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345f) sink[0] = a0;
+    } else if (KIND == 2) {  // IMAD.WIDE.U32 + LOP3 (the Philox round)
+        uint32_t c0 = t, c1 = t + 1, c2 = t + 2, c3 = t + 3, d0 = t + 4, d1 = t + 5, d2 = t + 6, d3 = t + 7;
+        for (int i = 0; i < iters; i++) {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+            const uint64_t q0 = (uint64_t)0xD2511F53u * d0, q1 = (uint64_t)0xCD9E8D57u * d2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (uint32_t)i, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (uint32_t)i;
+            const uint32_t m0 = (uint32_t)(q1 >> 32) ^ d1 ^ (uint32_t)i, m2 = (uint32_t)(q0 >> 32) ^ d3 ^ (uint32_t)i;
+            c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+            d1 = (uint32_t)q1; d3 = (uint32_t)q0; d0 = m0; d2 = m2;
+        }
+        if ((c0 ^ c1 ^ c2 ^ c3 ^ d0 ^ d1 ^ d2 ^ d3) == 0x12345u) sink[0] = c0;
+    } else if (KIND == 3) {  // F2F.F64.F32 widen + DADD
+        float f0 = t, f1 = t + 1, f2 = t + 2, f3 = t + 3;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int i = 0; i < iters; i++) {
+            s0 += (double)f0; s1 += (double)f1; s2 += (double)f2; s3 += (double)f3;
+            f0 = __int_as_float(__float_as_int(f0) + 1); f1 = __int_as_float(__float_as_int(f1) + 1);
+            f2 = __int_as_float(__float_as_int(f2) + 1); f3 = __int_as_float(__float_as_int(f3) + 1);
+        }
+        if (s0 + s1 + s2 + s3 == 0.12345) sink[0] = s0;
+    } else if (KIND == 4) {  // DADD only (baseline for KIND 3)
+        double s0 = t, s1 = t + 1, s2 = t + 2, s3 = t + 3, s4 = t + 4, s5 = t + 5, s6 = t + 6, s7 = t + 7;
+        const double c = 1e-9;
+        for (int i = 0; i < iters; i++) {
+            s0 += c; s1 += c; s2 += c; s3 += c; s4 += c; s5 += c; s6 += c; s7 += c;
+        }
+        if (s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7 == 0.12345) sink[0] = s0;
+    }
+}
+
+}  // namespace mcp

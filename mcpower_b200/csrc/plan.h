@@ -1,0 +1,109 @@
+// plan.h — the device-side lowering of one `SimulationSpec` + sample-size grid.
+//
+// Host code (lower.hpp) fills a DevicePlan once per mcp_run_batch call; kernels read it
+// from global/constant memory.  Everything that does not depend on the per-sim RNG
+// (critical values, exclusion-variant tables, exact factor walks, heteroskedasticity
+// moments) is precomputed on the host, mirroring the reference's "host builds the
+// CritValueTable, the loop only compares" split (crates/engine-core/src/critvals.rs:1-9).
+#pragma once
+#include <stdint.h>
+
+#define MCP_MAX_K 24          // continuous (non-factor) predictors
+#define MCP_MAX_P 32          // total design columns incl. intercept
+#define MCP_MAX_T 32          // marginal targets + contrasts
+#define MCP_MAX_FACTORS 6
+#define MCP_MAX_LEVELS 48     // Σ factor_n_levels
+#define MCP_MAX_INTER 16
+#define MCP_MAX_INTER_COMP 48
+#define MCP_MAX_MENU 8
+#define MCP_MAX_TEMPLATE_P 16 // kernels with register-resident X'X exist for P <= this
+
+enum McpDist { D_NORMAL = 0, D_BINARY = 1, D_RIGHT_SKEWED = 2, D_LEFT_SKEWED = 3, D_HIGH_KURTOSIS = 4, D_UNIFORM = 5 };
+enum McpRes { R_NORMAL = 0, R_RIGHT_SKEWED = 1, R_LEFT_SKEWED = 2, R_HIGH_KURTOSIS = 3, R_UNIFORM = 4 };
+enum McpOutcome { O_CONTINUOUS = 0, O_BINARY = 1, O_COUNT = 2 };
+enum McpEstimator { E_OLS = 0, E_GLM = 1, E_MLE = 2 };
+enum McpCorrection { C_NONE = 0, C_BONFERRONI = 1, C_HOLM = 2, C_BH = 3, C_TUKEY = 4 };
+
+// One "fit variant" = the set of kept design columns for a sparse-factor-exclusion mask
+// (batch.rs:2502-2562) intersected with the test design (`fit_columns`).
+struct McpVariant {
+    int32_t p_red;                  // kept column count
+    int32_t valid;                  // 0 → df < 1 for some N or never reachable
+    int8_t kept[MCP_MAX_P];         // kept[r] = full column index
+    int8_t remap[MCP_MAX_P];        // full → reduced index or -1
+};
+
+struct DevicePlan {
+    // ---- shape
+    int32_t k, n_fd, n_factors, n_inter, P, T, n_marg, n_contrasts;
+    int32_t n_ss, max_n;
+    int32_t estimator, outcome, link_probit, correction;
+    int32_t report_overall, min_level_count;
+    // ---- design
+    double L[MCP_MAX_K * MCP_MAX_K];   // optimistic path: lower Cholesky of correlation, row-major L[j][m]
+    double corr[MCP_MAX_K * MCP_MAX_K];// base correlation, column-major (scenario path)
+    int32_t l_identity;                // L == I structurally (skip the mix, bit-exact: adds of ±0)
+    int32_t all_normal;                // every marginal is Normal on the optimistic path
+    int32_t var_type[MCP_MAX_K];
+    uint8_t var_pinned[MCP_MAX_K];
+    double var_param[MCP_MAX_K];
+    int32_t f_levels[MCP_MAX_FACTORS];
+    int32_t f_off[MCP_MAX_FACTORS];    // offset into f_props
+    int32_t f_col[MCP_MAX_FACTORS];    // first dummy column
+    int32_t f_sampled[MCP_MAX_FACTORS];
+    double f_props[MCP_MAX_LEVELS];
+    int32_t n_sampled_factors;         // uniforms consumed per row on the sequential stream
+    int32_t inter_ptr[MCP_MAX_INTER + 1];
+    int32_t inter_cols[MCP_MAX_INTER_COMP];
+    double beta[MCP_MAX_P];
+    int32_t target[MCP_MAX_T];         // marginal target columns
+    int32_t contrast[2 * MCP_MAX_T];   // (pos, neg) pairs
+    // ---- residual / outcome
+    int32_t residual_dist, residual_pinned;
+    double residual_df;
+    // ---- cluster (random intercept only)
+    int32_t has_cluster, sizing_fixed_size, sizing_value, n_clusters;
+    double tau_squared;
+    // ---- scenario knobs (spec.rs:117-176)
+    int32_t optimistic;
+    double heterogeneity, hsk_gamma, corr_noise_sd, dist_change_prob, resid_change_prob;
+    int32_t n_new_dists, new_dists[MCP_MAX_MENU];
+    int32_t n_resid_dists, resid_dists[MCP_MAX_MENU];
+    int32_t has_lme, re_dist;
+    double re_df, icc_noise_sd;
+    int32_t apply_hsk, hsk_driver;     // driver < 0 → linear predictor
+    double hsk_center, hsk_inv_std, hsk_inv_norm;
+    // ---- variants + thresholds
+    int32_t n_variants;                // 1 << n_factors when exclusion is live, else 1
+    int32_t base_variant;              // variant used when no factor is excluded (fit_columns may reduce it)
+    int32_t exact_walk;                // every factor uses the deterministic walk
+    // ---- device pointers (filled by the host before upload)
+    const uint32_t* ss;                // [n_ss]
+    const McpVariant* variants;        // [n_variants]
+    const double* crit_unc;            // [n_variants][n_ss]
+    const double* crit_corr;           // [n_variants][n_ss][T]
+    const double* crit_overall;        // [n_variants][n_ss]
+    const uint8_t* levels;             // [n_factors][max_n] exact-walk levels (NULL if none exact)
+    const double* t3_table;            // [2048] censored t(3) PPF (marginals/t3.rs)
+    // ---- outputs
+    unsigned long long* counters;      // [n_ss][counter_width] (COUNTS)
+    uint8_t* out_unc;                  // [n_sims][n_ss][T]  (BYTES; may be NULL)
+    uint8_t* out_cor;
+    uint8_t* out_conv;                 // [n_sims][n_ss]
+    uint8_t* out_overall;              // [n_sims][n_ss] or NULL
+    uint8_t* out_fx;                   // [n_sims][n_ss][n_factors] or NULL
+    double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
+    int32_t counter_width;             // 2T + 2 + 2(T+1) + n_factors
+    int32_t smem_counters;             // counters staged in shared memory (fits)
+};
+
+// counter row layout (per sample-size index): what aggregate_batch derives
+// (crates/engine-orchestrator/src/aggregation.rs:91-242)
+//   [0,T)            uncorrected successes per target
+//   [T,2T)           corrected successes per target
+//   2T               converged fits
+//   2T+1             overall-test successes
+//   [2T+2, 3T+3)     histogram of #uncorrected-significant targets per sim (T+1 buckets)
+//   [3T+3, 4T+4)     histogram of #corrected-significant targets per sim
+//   [4T+4, 4T+4+F)   sims with factor f excluded
+static inline int mcp_counter_width(int T, int F) { return 4 * T + 4 + F; }

@@ -1,0 +1,301 @@
+// spec.hpp — `SimulationSpec` (crates/engine-core/src/spec.rs:250-417) parsed from its serde JSON
+// shape, plus the spec-level validation run_batch performs (batch.rs:208-330).
+#pragma once
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "json.hpp"
+#include "plan.h"
+
+namespace mcp {
+
+// Error classes mirror EngineError (spec.rs:19-29); codes are the C-ABI return values.
+enum McpStatus { MCP_OK = 0, MCP_INVALID_SPEC = 1, MCP_CORRELATION_NOT_PSD = 2, MCP_RANK_DEFICIENT = 3, MCP_CANCELLED = 4,
+                 MCP_CUDA_ERROR = 5, MCP_UNSUPPORTED = 6 };
+
+struct EngineError : std::runtime_error {
+    int code;
+    EngineError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+[[noreturn]] inline void invalid(const std::string& m) { throw EngineError(MCP_INVALID_SPEC, "invalid spec: " + m); }
+[[noreturn]] inline void unsupported(const std::string& m) { throw EngineError(MCP_UNSUPPORTED, "unsupported by the CUDA backend: " + m); }
+
+struct Spec {
+    int k = 0, n_fd = 0;
+    std::vector<double> correlation;
+    std::vector<int> var_types;
+    std::vector<uint8_t> var_pinned;
+    std::vector<double> var_params;
+    std::vector<int> factor_n_levels;
+    std::vector<double> factor_proportions;
+    std::vector<int> factor_sampled;  // -1 inherit
+    std::vector<double> effect_sizes;
+    std::vector<int> target_indices;
+    std::vector<int> fit_columns;
+    std::vector<std::pair<int, int>> contrast_pairs;
+    std::vector<std::vector<int>> interactions;
+    int correction = C_NONE;
+    double alpha = 0.05;
+    double posthoc_alpha = NAN;
+    int hsk_driver = -1;
+    int residual_dist = R_NORMAL;
+    bool residual_pinned = false;
+    int outcome = O_CONTINUOUS;
+    bool link_probit = false;
+    int estimator = E_OLS;
+    bool report_overall = false;
+    int min_level_count = 0;
+    bool has_posthoc = false;
+    bool has_upload = false;
+    bool has_slopes_or_groupings = false;
+    bool has_between = false;
+    // cluster
+    bool has_cluster = false;
+    bool sizing_fixed_size = false;
+    int sizing_value = 0;
+    double tau_squared = 0.0;
+    // scenario
+    double heterogeneity = 0.0, hsk_ratio = 1.0, corr_noise_sd = 0.0, dist_change_prob = 0.0, resid_change_prob = 0.0;
+    std::vector<int> new_dists, resid_dists;
+    double residual_df = 0.0;
+    bool sampled_factor_proportions = false;
+    bool has_lme = false;
+    int re_dist = R_NORMAL;
+    double re_df = 0.0, icc_noise_sd = 0.0;
+
+    int P() const { return 1 + k + n_fd + (int)interactions.size(); }
+    int T() const { return (int)target_indices.size() + (int)contrast_pairs.size(); }
+    bool is_optimistic() const {  // spec.rs:229-236
+        return heterogeneity == 0.0 && hsk_ratio == 1.0 && corr_noise_sd == 0.0 && dist_change_prob == 0.0 &&
+               resid_change_prob == 0.0 && !has_lme;
+    }
+};
+
+namespace detail {
+inline const JsonValue& req(const JsonValue& o, const char* key) {
+    const JsonValue* v = o.get(key);
+    if (!v) invalid(std::string("missing field `") + key + "`");
+    return *v;
+}
+inline double num(const JsonValue& v, const char* what) {
+    if (v.kind != JsonValue::Number) invalid(std::string("field `") + what + "` must be a number");
+    return v.num;
+}
+inline int to_int(const JsonValue& v, const char* what) {
+    const double d = num(v, what);
+    if (d != std::floor(d) || std::fabs(d) > 2147483647.0) invalid(std::string("field `") + what + "` must be an integer");
+    return (int)d;
+}
+inline bool to_bool(const JsonValue& v, const char* what) {
+    if (v.kind != JsonValue::Bool) invalid(std::string("field `") + what + "` must be a bool");
+    return v.b;
+}
+inline const std::vector<JsonValue>& arr(const JsonValue& v, const char* what) {
+    if (v.kind != JsonValue::Array) invalid(std::string("field `") + what + "` must be an array");
+    return v.arr;
+}
+inline int enum_of(const JsonValue& v, const char* what, std::initializer_list<std::pair<const char*, int>> table) {
+    if (v.kind != JsonValue::String) invalid(std::string("field `") + what + "` must be a string");
+    for (auto& e : table)
+        if (v.str == e.first) return e.second;
+    invalid(std::string("unknown variant `") + v.str + "` for `" + what + "`");
+}
+inline int dist_of(const JsonValue& v, const char* what) {
+    // engine-contract/src/distribution.rs:15-26 (snake_case)
+    const int d = enum_of(v, what, {{"normal", D_NORMAL}, {"binary", D_BINARY}, {"right_skewed", D_RIGHT_SKEWED},
+                                    {"left_skewed", D_LEFT_SKEWED}, {"high_kurtosis", D_HIGH_KURTOSIS}, {"uniform", D_UNIFORM},
+                                    {"uploaded_factor", 100}, {"uploaded_binary", 101}, {"uploaded_data", 102}});
+    return d;
+}
+inline int resid_of(const JsonValue& v, const char* what) {
+    // engine-contract/src/outcome.rs:67-75
+    return enum_of(v, what, {{"normal", R_NORMAL}, {"right_skewed", R_RIGHT_SKEWED}, {"left_skewed", R_LEFT_SKEWED},
+                             {"high_kurtosis", R_HIGH_KURTOSIS}, {"uniform", R_UNIFORM}});
+}
+}  // namespace detail
+
+inline Spec parse_spec(const char* json, size_t len) {
+    using namespace detail;
+    JsonValue root;
+    try {
+        root = JsonParser(json, len).parse();
+    } catch (const std::runtime_error& e) {
+        invalid(e.what());
+    }
+    if (root.kind != JsonValue::Object) invalid("spec must be a JSON object");
+    Spec s;
+    s.k = to_int(req(root, "n_non_factor"), "n_non_factor");
+    s.n_fd = to_int(req(root, "n_factor_dummies"), "n_factor_dummies");
+    if (s.k < 0 || s.n_fd < 0) invalid("negative column count");
+    for (auto& v : arr(req(root, "correlation"), "correlation")) s.correlation.push_back(num(v, "correlation"));
+    for (auto& v : arr(req(root, "var_types"), "var_types")) s.var_types.push_back(dist_of(v, "var_types"));
+    if (auto* p = root.get("var_pinned"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "var_pinned")) s.var_pinned.push_back(to_bool(v, "var_pinned"));
+    if (auto* p = root.get("var_params"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "var_params")) s.var_params.push_back(num(v, "var_params"));
+    auto nonempty = [&](const char* key) {
+        const JsonValue* p = root.get(key);
+        return p && p->kind == JsonValue::Array && !p->arr.empty();
+    };
+    s.has_upload = nonempty("upload_normal") || nonempty("upload_data") || nonempty("bootstrap_frame_map");
+    s.has_between = nonempty("between_var_indices");
+    for (auto& v : arr(req(root, "factor_n_levels"), "factor_n_levels")) s.factor_n_levels.push_back(to_int(v, "factor_n_levels"));
+    for (auto& v : arr(req(root, "factor_proportions"), "factor_proportions")) s.factor_proportions.push_back(num(v, "factor_proportions"));
+    if (auto* p = root.get("factor_sampled"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "factor_sampled")) s.factor_sampled.push_back(v.is_null() ? -1 : (to_bool(v, "factor_sampled") ? 1 : 0));
+    for (auto& v : arr(req(root, "effect_sizes"), "effect_sizes")) s.effect_sizes.push_back(num(v, "effect_sizes"));
+    for (auto& v : arr(req(root, "target_indices"), "target_indices")) s.target_indices.push_back(to_int(v, "target_indices"));
+    if (auto* p = root.get("fit_columns"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "fit_columns")) s.fit_columns.push_back(to_int(v, "fit_columns"));
+    if (auto* p = root.get("contrast_pairs"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "contrast_pairs")) {
+                auto& pr = arr(v, "contrast_pairs");
+                if (pr.size() != 2) invalid("contrast_pairs entries must be (pos, neg) pairs");
+                s.contrast_pairs.push_back({to_int(pr[0], "contrast_pairs"), to_int(pr[1], "contrast_pairs")});
+            }
+    if (auto* p = root.get("interactions"))
+        if (!p->is_null())
+            for (auto& v : arr(*p, "interactions")) {
+                std::vector<int> comp;
+                for (auto& c : arr(v, "interactions")) comp.push_back(to_int(c, "interactions"));
+                s.interactions.push_back(comp);
+            }
+    // engine-contract/src/test_spec.rs:38-47
+    s.correction = enum_of(req(root, "correction_method"), "correction_method",
+                           {{"none", C_NONE}, {"bonferroni", C_BONFERRONI}, {"holm", C_HOLM}, {"benjamini_hochberg", C_BH}, {"tukey_hsd", C_TUKEY}});
+    {
+        const JsonValue& cv = req(root, "crit_values");
+        s.alpha = num(req(cv, "alpha"), "crit_values.alpha");
+        if (auto* pa = cv.get("posthoc_alpha"))
+            if (!pa->is_null()) s.posthoc_alpha = num(*pa, "crit_values.posthoc_alpha");
+    }
+    if (auto* p = root.get("heteroskedasticity_driver"))
+        if (!p->is_null()) s.hsk_driver = to_int(*p, "heteroskedasticity_driver");
+    s.residual_dist = resid_of(req(root, "residual_dist"), "residual_dist");
+    if (auto* p = root.get("residual_pinned")) s.residual_pinned = !p->is_null() && to_bool(*p, "residual_pinned");
+    s.outcome = enum_of(req(root, "outcome_kind"), "outcome_kind", {{"continuous", O_CONTINUOUS}, {"binary", O_BINARY}, {"count", O_COUNT}});
+    if (auto* p = root.get("link"))
+        if (!p->is_null()) s.link_probit = enum_of(*p, "link", {{"probit", 1}}) == 1;
+    s.estimator = enum_of(req(root, "estimator"), "estimator", {{"ols", E_OLS}, {"glm", E_GLM}, {"mle", E_MLE}});
+    if (auto* p = root.get("posthoc")) s.has_posthoc = p->kind == JsonValue::Array && !p->arr.empty();
+    if (auto* p = root.get("report_overall")) s.report_overall = !p->is_null() && to_bool(*p, "report_overall");
+    if (auto* p = root.get("factor_min_level_count"))
+        if (!p->is_null()) s.min_level_count = to_int(*p, "factor_min_level_count");
+    if (auto* p = root.get("cluster_slope_design_cols")) s.has_slopes_or_groupings |= p->kind == JsonValue::Array && !p->arr.empty();
+    if (auto* p = root.get("cluster")) {
+        if (!p->is_null()) {
+            s.has_cluster = true;
+            const JsonValue& sz = req(*p, "sizing");
+            if (auto* fc = sz.get("FixedClusters")) {
+                s.sizing_fixed_size = false;
+                s.sizing_value = to_int(req(*fc, "n_clusters"), "n_clusters");
+            } else if (auto* fs = sz.get("FixedSize")) {
+                s.sizing_fixed_size = true;
+                s.sizing_value = to_int(req(*fs, "cluster_size"), "cluster_size");
+            } else {
+                invalid("cluster.sizing must be FixedClusters or FixedSize");
+            }
+            s.tau_squared = num(req(*p, "tau_squared"), "tau_squared");
+            for (const char* key : {"slopes", "extra_groupings"})
+                if (auto* q = p->get(key)) s.has_slopes_or_groupings |= q->kind == JsonValue::Array && !q->arr.empty();
+        }
+    }
+    {
+        const JsonValue& sc = req(root, "scenario");
+        s.heterogeneity = num(req(sc, "heterogeneity"), "heterogeneity");
+        s.hsk_ratio = num(req(sc, "heteroskedasticity_ratio"), "heteroskedasticity_ratio");
+        s.corr_noise_sd = num(req(sc, "correlation_noise_sd"), "correlation_noise_sd");
+        s.dist_change_prob = num(req(sc, "distribution_change_prob"), "distribution_change_prob");
+        for (auto& v : arr(req(sc, "new_distributions"), "new_distributions")) s.new_dists.push_back(dist_of(v, "new_distributions"));
+        s.resid_change_prob = num(req(sc, "residual_change_prob"), "residual_change_prob");
+        for (auto& v : arr(req(sc, "residual_dists"), "residual_dists")) s.resid_dists.push_back(resid_of(v, "residual_dists"));
+        s.residual_df = num(req(sc, "residual_df"), "residual_df");
+        if (auto* p = sc.get("sampled_factor_proportions")) s.sampled_factor_proportions = !p->is_null() && to_bool(*p, "sampled_factor_proportions");
+        if (auto* p = sc.get("lme"))
+            if (!p->is_null()) {
+                s.has_lme = true;
+                s.re_dist = resid_of(req(*p, "random_effect_dist"), "random_effect_dist");
+                s.re_df = num(req(*p, "random_effect_df"), "random_effect_df");
+                s.icc_noise_sd = num(req(*p, "icc_noise_sd"), "icc_noise_sd");
+            }
+    }
+    return s;
+}
+
+// Lower Cholesky of the k×k correlation (column-major in, row-major L out); left-looking column order
+// of data_gen.rs:55-75 / correlation.rs:48-74.  Returns false on a non-positive pivot.
+inline bool correlation_llt(const std::vector<double>& corr_colmajor, int k, std::vector<double>& L_rowmajor) {
+    std::vector<double> a(corr_colmajor);
+    for (int j = 0; j < k; j++) {
+        double diag = a[j * k + j];
+        for (int m = 0; m < j; m++) diag -= a[m * k + j] * a[m * k + j];
+        if (!(diag > 0.0) || !std::isfinite(diag)) return false;
+        const double ljj = std::sqrt(diag);
+        a[j * k + j] = ljj;
+        for (int i = j + 1; i < k; i++) {
+            double s = a[j * k + i];
+            for (int m = 0; m < j; m++) s -= a[m * k + i] * a[m * k + j];
+            a[j * k + i] = s / ljj;
+        }
+    }
+    L_rowmajor.assign((size_t)k * k, 0.0);
+    for (int j = 0; j < k; j++)
+        for (int i = j; i < k; i++) L_rowmajor[(size_t)i * k + j] = a[j * k + i];
+    return true;
+}
+
+// batch.rs:208-330 — the spec-level checks run_batch owns (contract-level invariants ran upstream).
+inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t n_ss) {
+    if (s.estimator == E_MLE && !s.has_cluster) invalid("estimator Mle requires ClusterSpec");
+    if (s.has_posthoc && s.estimator != E_OLS) invalid("posthoc tests are only supported for estimator=Ols");
+    if (sample_sizes) {
+        if (n_ss == 0) invalid("sample_sizes must be non-empty");
+        for (uint32_t i = 1; i < n_ss; i++)
+            if (sample_sizes[i] <= sample_sizes[i - 1])
+                invalid("sample_sizes must be strictly increasing; got " + std::to_string(sample_sizes[i - 1]) + " then " +
+                        std::to_string(sample_sizes[i]));
+        if (sample_sizes[0] == 0) invalid("sample_sizes[0] must be > 0");
+    }
+    const int P = s.P();
+    if ((int)s.correlation.size() != s.k * s.k)
+        invalid("correlation length " + std::to_string(s.correlation.size()) + " does not match n_non_factor² = " + std::to_string(s.k * s.k));
+    if ((int)s.var_types.size() != s.k)
+        invalid("var_types length " + std::to_string(s.var_types.size()) + " does not match n_non_factor " + std::to_string(s.k));
+    if ((int)s.effect_sizes.size() != P)
+        invalid("effect_sizes length " + std::to_string(s.effect_sizes.size()) + " does not match n_predictors " + std::to_string(P));
+    int expected = 0, dummies = 0;
+    for (int lv : s.factor_n_levels) {
+        if (lv < 2) invalid("factor_n_levels entries must be >= 2; got " + std::to_string(lv));
+        expected += lv;
+        dummies += lv - 1;
+    }
+    if ((int)s.factor_proportions.size() != expected)
+        invalid("factor_proportions length " + std::to_string(s.factor_proportions.size()) + " does not match Σfactor_n_levels " +
+                std::to_string(expected));
+    if (dummies != s.n_fd) invalid("n_factor_dummies does not match Σ(factor_n_levels − 1)");
+    for (int ti : s.target_indices)
+        if (ti < 0 || ti >= P) invalid("target_indices entry " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
+    for (auto& pr : s.contrast_pairs) {
+        if (pr.first < 0 || pr.first >= P) invalid("contrast_pairs positive " + std::to_string(pr.first) + " out of range");
+        if (pr.second < 0 || pr.second >= P) invalid("contrast_pairs negative " + std::to_string(pr.second) + " out of range");
+    }
+    for (auto& comp : s.interactions)
+        for (int c : comp)
+            if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("interaction component out of range");
+    if (s.k > 0) {
+        std::vector<double> L;
+        if (!correlation_llt(s.correlation, s.k, L)) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
+    }
+    if (!std::isfinite(s.alpha) || s.alpha <= 0.0 || s.alpha >= 1.0) invalid("alpha must lie in (0, 1); got " + std::to_string(s.alpha));
+    if (!std::isnan(s.posthoc_alpha) && (!std::isfinite(s.posthoc_alpha) || s.posthoc_alpha <= 0.0 || s.posthoc_alpha >= 1.0))
+        invalid("posthoc_alpha must lie in (0, 1)");
+}
+
+}  // namespace mcp

@@ -1,0 +1,310 @@
+"""Host-side mirror of `engine_core::run_batch` over the C ABI of libmcpower_b200.so.
+
+Reference interface (crates/engine-core/src/batch.rs:130-146, spec.rs:19-52,552-600):
+
+    run_batch(spec, sample_sizes, n_sims, base_seed, sink) -> Result<BatchResult, EngineError>
+
+Same argument meaning, same error classes (InvalidSpec / CorrelationNotPSD / RankDeficient /
+Cancelled), same sim-major integer tensors.  There is no CPU execution path in this package: if the
+shared library is missing or no CUDA device is present the call raises — it never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "libmcpower_b200.so"
+
+MODE_COUNTS, MODE_BYTES, MODE_CAPTURE = 1, 2, 4
+
+
+class EngineError(Exception):
+    """Base of the EngineError family (spec.rs:19-29)."""
+    code = -1
+
+
+class InvalidSpec(EngineError, ValueError):
+    code = 1
+
+
+class CorrelationNotPSD(EngineError, ValueError):
+    code = 2
+
+
+class RankDeficient(EngineError, ValueError):
+    code = 3
+
+
+class Cancelled(EngineError, KeyboardInterrupt):
+    """PyO3 maps EngineError::Cancelled to KeyboardInterrupt (engine-py/src/lib.rs:141-167)."""
+    code = 4
+
+
+class CudaError(EngineError, RuntimeError):
+    code = 5
+
+
+class Unsupported(EngineError, NotImplementedError):
+    code = 6
+
+
+_ERRORS = {c.code: c for c in (InvalidSpec, CorrelationNotPSD, RankDeficient, Cancelled, CudaError, Unsupported)}
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("mode", C.c_uint32), ("sim_begin", C.c_uint64), ("wave_sims", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_sims", C.c_uint32), ("n_sample_sizes", C.c_uint32), ("n_targets", C.c_uint32),
+                ("n_factors", C.c_uint32),
+                ("uncorrected", C.POINTER(C.c_uint8)), ("corrected", C.POINTER(C.c_uint8)),
+                ("converged", C.POINTER(C.c_uint8)), ("overall", C.POINTER(C.c_uint8)),
+                ("factor_excluded", C.POINTER(C.c_uint8)), ("t_sq", C.POINTER(C.c_double)),
+                ("counter_width", C.c_uint32), ("gpu_launches", C.c_uint32),
+                ("counters", C.POINTER(C.c_uint64)), ("kernel_ms", C.c_double)]
+
+
+_PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
+
+EXPORTS = ("mcp_run_batch", "mcp_free_result", "mcp_generate_sim", "mcp_fit_data", "mcp_crit_table", "mcp_splitmix64",
+           "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version")
+
+_lib = None
+
+
+def lib():
+    """Load libmcpower_b200.so (built in-tree by mcpower_b200/build.py). Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _SO.exists():
+        raise CudaError(f"{_SO} is missing — build it with `python -m mcpower_b200.build` "
+                        "(the CUDA backend has no CPU fallback)")
+    L = C.CDLL(str(_SO))
+    L.mcp_run_batch.restype = C.c_int
+    L.mcp_run_batch.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint64,
+                                C.POINTER(_Options), _PROGRESS, C.c_void_p, C.POINTER(C.POINTER(_Result))]
+    L.mcp_free_result.argtypes = [C.POINTER(_Result)]
+    L.mcp_free_result.restype = None
+    L.mcp_generate_sim.restype = C.c_int
+    L.mcp_generate_sim.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int32,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mcp_fit_data.restype = C.c_int
+    L.mcp_fit_data.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32, C.c_uint32, C.c_int32,
+                               C.POINTER(C.c_double)]
+    L.mcp_crit_table.restype = C.c_int
+    L.mcp_crit_table.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double)]
+    L.mcp_splitmix64.restype = C.c_uint64
+    L.mcp_splitmix64.argtypes = [C.c_uint64]
+    L.mcp_pipe_bench.restype = C.c_int
+    L.mcp_pipe_bench.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.mcp_device_count.restype = C.c_int
+    L.mcp_last_error.restype = C.c_char_p
+    L.mcp_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _raise(code: int):
+    msg = lib().mcp_last_error().decode("utf-8", "replace")
+    raise _ERRORS.get(code, EngineError)(msg)
+
+
+def splitmix64(z: int) -> int:
+    """rng::splitmix64_finalize — hosts pass base_seed = splitmix64(user_seed) (find_power.rs:259)."""
+    return int(lib().mcp_splitmix64(z & 0xFFFFFFFFFFFFFFFF))
+
+
+@dataclass
+class BatchResult:
+    """BatchResult (spec.rs:552-600). Byte tensors are None unless MODE_BYTES was requested."""
+    n_sims: int
+    n_sample_sizes: int
+    n_targets: int
+    n_factors: int
+    counters: np.ndarray                       # [n_ss, 4T+4+F] uint64 (layout: include/mcpower_b200.h)
+    uncorrected: Optional[np.ndarray] = None   # [n_sims, n_ss, T] uint8
+    corrected: Optional[np.ndarray] = None
+    converged: Optional[np.ndarray] = None     # [n_sims, n_ss]
+    overall: Optional[np.ndarray] = None
+    factor_excluded: Optional[np.ndarray] = None
+    t_sq: Optional[np.ndarray] = None          # [n_sims, n_ss, T] float64 (MODE_CAPTURE)
+    kernel_ms: float = 0.0
+    gpu_launches: int = 0
+    extras: dict = field(default_factory=dict)
+
+    # ---- views of the counter rows (what aggregate_batch derives, aggregation.rs:91-242)
+    @property
+    def success_uncorrected(self):
+        return self.counters[:, :self.n_targets]
+
+    @property
+    def success_corrected(self):
+        return self.counters[:, self.n_targets:2 * self.n_targets]
+
+    @property
+    def n_converged(self):
+        return self.counters[:, 2 * self.n_targets]
+
+    @property
+    def success_overall(self):
+        return self.counters[:, 2 * self.n_targets + 1]
+
+    @property
+    def hist_uncorrected(self):
+        T = self.n_targets
+        return self.counters[:, 2 * T + 2:3 * T + 3]
+
+    @property
+    def hist_corrected(self):
+        T = self.n_targets
+        return self.counters[:, 3 * T + 3:4 * T + 4]
+
+    @property
+    def n_factor_excluded(self):
+        T = self.n_targets
+        return self.counters[:, 4 * T + 4:4 * T + 4 + self.n_factors]
+
+    def power(self, corrected: bool = False) -> np.ndarray:
+        """successes / n_sims per (sample size, target) — PowerResult.power (aggregation.rs)."""
+        s = self.success_corrected if corrected else self.success_uncorrected
+        return s.astype(np.float64) / max(self.n_sims, 1)
+
+
+def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_excluded=None) -> np.ndarray:
+    """aggregate_batch's integer reductions (aggregation.rs:91-242) over the byte tensors —
+    used to prove COUNTS mode equals BYTES mode + host aggregation."""
+    n_sims, n_ss, T = uncorrected.shape
+    F = 0 if factor_excluded is None else factor_excluded.shape[2]
+    out = np.zeros((n_ss, 4 * T + 4 + F), dtype=np.uint64)
+    out[:, :T] = uncorrected.sum(axis=0)
+    out[:, T:2 * T] = corrected.sum(axis=0)
+    out[:, 2 * T] = converged.sum(axis=0)
+    if overall is not None:
+        out[:, 2 * T + 1] = overall.sum(axis=0)
+    nu = uncorrected.sum(axis=2)
+    nc = corrected.sum(axis=2)
+    for g in range(n_ss):
+        out[g, 2 * T + 2:3 * T + 3] = np.bincount(nu[:, g], minlength=T + 1)
+        out[g, 3 * T + 3:4 * T + 4] = np.bincount(nc[:, g], minlength=T + 1)
+    if F:
+        out[:, 4 * T + 4:] = (factor_excluded != 0).sum(axis=0)
+    return out
+
+
+ProgressSink = Callable[[int, int], bool]
+
+
+def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: int,
+              sink: Optional[ProgressSink] = None, *, mode: int = MODE_COUNTS, device: int = -1, sim_begin: int = 0,
+              wave_sims: int = 0) -> BatchResult:
+    """engine_core::run_batch on the GPU. `sink(current, total) -> bool` mirrors ProgressSink::report
+    (return False to cancel → raises Cancelled, partial results discarded, batch.rs:128-129)."""
+    L = lib()
+    blob = json.dumps(spec).encode()
+    ss = np.ascontiguousarray(np.asarray(list(sample_sizes), dtype=np.int64))
+    if ss.size and (ss.min() < 0 or ss.max() > 0xFFFFFFFF):
+        raise InvalidSpec("invalid spec: sample sizes must fit u32")
+    ss32 = ss.astype(np.uint32)
+    opt = _Options(device, mode, sim_begin, wave_sims, 0)
+    out = C.POINTER(_Result)()
+    cb = _PROGRESS(lambda cur, tot, _u: 1 if sink(int(cur), int(tot)) else 0) if sink else C.cast(None, _PROGRESS)
+    rc = L.mcp_run_batch(blob, len(blob), ss32.ctypes.data_as(C.POINTER(C.c_uint32)), ss32.size, int(n_sims),
+                         base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), cb, None, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    try:
+        r = out.contents
+        n_ss, T, F = r.n_sample_sizes, r.n_targets, r.n_factors
+
+        def take(ptr, shape, dtype):
+            if not ptr:
+                return None
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.zeros(shape, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True).reshape(shape)
+
+        res = BatchResult(
+            n_sims=r.n_sims, n_sample_sizes=n_ss, n_targets=T, n_factors=F,
+            counters=take(r.counters, (n_ss, r.counter_width), np.uint64),
+            uncorrected=take(r.uncorrected, (r.n_sims, n_ss, T), np.uint8),
+            corrected=take(r.corrected, (r.n_sims, n_ss, T), np.uint8),
+            converged=take(r.converged, (r.n_sims, n_ss), np.uint8),
+            overall=take(r.overall, (r.n_sims, n_ss), np.uint8),
+            factor_excluded=take(r.factor_excluded, (r.n_sims, n_ss, F), np.uint8),
+            t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),
+            kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches))
+    finally:
+        L.mcp_free_result(out)
+    return res
+
+
+def generate_sim(spec: dict, base_seed: int, sim_id: int, max_n: int, device: int = -1):
+    """capture_sim0_data twin (introspect.rs:104-155) for any sim id → (X [max_n, P] f32, y [max_n] f32)."""
+    from .spec import n_predictors
+    blob = json.dumps(spec).encode()
+    P = n_predictors(spec)
+    x = np.zeros((P, max_n), dtype=np.float32)
+    y = np.zeros(max_n, dtype=np.float32)
+    rc = lib().mcp_generate_sim(blob, len(blob), max_n, base_seed & 0xFFFFFFFFFFFFFFFF, sim_id, device,
+                                x.ctypes.data_as(C.POINTER(C.c_float)), y.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        _raise(rc)
+    return x.T, y
+
+
+def fit_data(x, y, device: int = -1) -> dict:
+    """fit_provided_data twin (introspect.rs:174-293), OLS: β, SE, t², σ², SST, RSS on supplied bytes."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.zeros(3 * p + 4)
+    rc = lib().mcp_fit_data(xc.ctypes.data_as(C.POINTER(C.c_double)), yv.ctypes.data_as(C.POINTER(C.c_double)), n, p,
+                            device, out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != 0:
+        _raise(rc)
+    return {"betas": out[:p].copy(), "se": out[p:2 * p].copy(), "t_sq": out[2 * p:3 * p].copy(),
+            "sigma_sq": out[3 * p], "sst": out[3 * p + 1], "rss": out[3 * p + 2], "converged": bool(out[3 * p + 3])}
+
+
+def crit_table(spec: dict, sample_sizes: Sequence[int], n_predictors: Optional[int] = None) -> dict:
+    """CritValueTable::build_with_tukey_k twin (host f64; runs without a GPU)."""
+    from .spec import n_predictors as npred
+    blob = json.dumps(spec).encode()
+    ss = np.asarray(list(sample_sizes), dtype=np.uint32)
+    T = len(spec["target_indices"]) + len(spec.get("contrast_pairs", []) or [])
+    P = npred(spec) if n_predictors is None else n_predictors
+    t_unc, corr, post, ov = np.zeros(len(ss)), np.zeros((len(ss), max(T, 1))), np.zeros(len(ss)), np.zeros(len(ss))
+    dp = C.POINTER(C.c_double)
+    rc = lib().mcp_crit_table(blob, len(blob), ss.ctypes.data_as(C.POINTER(C.c_uint32)), len(ss), P,
+                              t_unc.ctypes.data_as(dp), corr.ctypes.data_as(dp), post.ctypes.data_as(dp),
+                              ov.ctypes.data_as(dp))
+    if rc != 0:
+        _raise(rc)
+    return {"t_crit_sq_uncorrected": t_unc, "correction_t_crit_sq": corr[:, :T], "posthoc_t_crit_sq": post,
+            "overall_crit": ov}
+
+
+def pipe_bench(kind: int, device: int = -1) -> float:
+    """Measured thread-operations/s of one instruction class (roofline denominators; see the C header)."""
+    v = C.c_double()
+    rc = lib().mcp_pipe_bench(kind, device, C.byref(v))
+    if rc != 0:
+        _raise(rc)
+    return v.value
+
+
+def device_count() -> int:
+    return int(lib().mcp_device_count())

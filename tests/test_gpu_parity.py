@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, against the committed reference fixtures, and — at full size — through
+size-independent properties.  Bar: bit-exact for every integer/byte output and for the f32 data
+plane; the f64 statistics are computed in the same operation order as the oracle, so they are
+compared bit-for-bit too (tolerance 0), with the 1e-10 relative bar of BASELINE.json's north_star
+checked against the frozen R goldens."""
+import math
+
+import numpy as np
+import pytest
+
+import _cases as CS
+import mcpower_b200 as M
+from mcpower_b200 import spec as S
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x9E3779B97F4A7C15
+
+
+def assert_batch_equal(got: M.BatchResult, want: dict):
+    for key in ("uncorrected", "corrected", "converged"):
+        assert np.array_equal(getattr(got, key), want[key]), key
+    if want["overall"] is not None:
+        assert np.array_equal(got.overall, want["overall"]), "overall"
+    if want["factor_excluded"] is not None:
+        assert np.array_equal(got.factor_excluded, want["factor_excluded"]), "factor_excluded"
+    if want["t_sq"] is not None and got.t_sq is not None:
+        assert np.array_equal(got.t_sq.view(np.uint64), want["t_sq"].view(np.uint64)) or \
+            np.array_equal(got.t_sq, want["t_sq"], equal_nan=True), "t_sq bits"
+    agg = M.counters_from_bytes(got.uncorrected, got.corrected, got.converged, got.overall, got.factor_excluded)
+    assert np.array_equal(agg, got.counters), "COUNTS != aggregate(BYTES)"
+
+
+ALL = M.MODE_COUNTS | M.MODE_BYTES | M.MODE_CAPTURE
+
+
+# ------------------------------------------------------------------ data plane vs the reference's saved datasets
+@pytest.mark.parametrize("name", sorted(CS.validation_cases()))
+def test_generated_design_bit_exact_vs_reference_fixture(name):
+    """sim 0 of base_seed = splitmix64(seed): X and y equal the reference engine's saved bytes."""
+    case = CS.validation_cases()[name]
+    spec = CS.case_spec(case)
+    x, y = M.generate_sim(spec, M.splitmix64(CS.case_seed(case)), 0, case["n"])
+    xr, yr = CS.case_arrays(case)
+    assert np.array_equal(x.view(np.uint32), xr.view(np.uint32)), "design bits"
+    assert np.array_equal(y.view(np.uint32), yr.view(np.uint32)), "outcome bits"
+
+
+@pytest.mark.parametrize("dist", ["binary", "right_skewed", "left_skewed", "high_kurtosis", "uniform"])
+def test_marginal_transforms_bit_exact_vs_oracle(dist):
+    s = S.base_spec(3)
+    s["correlation"] = [1, 0.4, 0.2, 0.4, 1, 0.3, 0.2, 0.3, 1]
+    s["var_types"] = ["normal", dist, dist]
+    s["var_params"] = [0.0, 0.3, 0.7]
+    s["effect_sizes"] = [0.1, 0.2, -0.3, 0.4]
+    for sim in (0, 7):
+        x, y = M.generate_sim(s, SEED, sim, 257)
+        xo, yo, _ = orc.generate_sim(s, SEED, sim, 257)
+        assert np.array_equal(x.view(np.uint32), xo.view(np.uint32))
+        assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+@pytest.mark.parametrize("resid", ["uniform", "high_kurtosis", "right_skewed", "left_skewed"])
+def test_pinned_residual_dists_bit_exact_vs_oracle(resid):
+    s = S.headline_spec()
+    s["residual_dist"], s["residual_pinned"] = resid, True
+    s["scenario"]["residual_df"] = 5.0
+    x, y = M.generate_sim(s, SEED, 11, 130)
+    xo, yo, _ = orc.generate_sim(s, SEED, 11, 130)
+    assert np.array_equal(x.view(np.uint32), xo.view(np.uint32))
+    assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+def test_sampled_factors_and_cluster_intercepts_bit_exact_vs_oracle():
+    s = S.add_factor(S.base_spec(2), [0.2, 0.3, 0.5], [0.3, -0.2])
+    s = S.add_factor(s, [0.6, 0.4], [0.5])
+    s["factor_sampled"] = [True, None]
+    s["effect_sizes"][1] = 0.25
+    s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": 7}}, "tau_squared": 0.3, "slopes": [],
+                    "extra_groupings": []}
+    for sim in (0, 5):
+        x, y = M.generate_sim(s, SEED, sim, 211)
+        xo, yo, _ = orc.generate_sim(s, SEED, sim, 211)
+        assert np.array_equal(x.view(np.uint32), xo.view(np.uint32))
+        assert np.array_equal(y.view(np.uint32), yo.view(np.uint32))
+
+
+def test_prefix_stability_across_max_n():
+    s = CS.case_spec(CS.validation_cases()["ols_cf_a"])
+    x1, y1 = M.generate_sim(s, 99, 5, 61)
+    x2, y2 = M.generate_sim(s, 99, 5, 300)
+    assert np.array_equal(x1, x2[:61]) and np.array_equal(y1, y2[:61])
+
+
+# ------------------------------------------------------------------ solver vs frozen R lm goldens (1e-10, north_star)
+@pytest.mark.parametrize("name", sorted(n for n in CS.validation_cases() if n.startswith("ols_")))
+def test_fit_on_reference_bytes_matches_r_lm(name):
+    case = CS.validation_cases()[name]
+    x, y = CS.case_arrays(case)
+    g = CS.golden_arrays(case)
+    fit = M.fit_data(x.astype(np.float64), y.astype(np.float64))
+    assert fit["converged"]
+    stat = fit["betas"] / fit["se"]
+    for got, want in ((fit["betas"], g["beta"]), (fit["se"], g["se"]), (stat, g["stat"])):
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-10
+    o = orc.fit_ols(x.astype(np.float64), y.astype(np.float64))
+    assert np.array_equal(fit["betas"], o["betas"]) and np.array_equal(fit["t_sq"], o["t_sq"])  # same op order
+
+
+# ------------------------------------------------------------------ run_batch vs oracle: byte tensors identical
+def test_headline_shape_small():
+    s = S.headline_spec()
+    got = M.run_batch(s, [500], 300, M.splitmix64(2137), mode=ALL)
+    want = orc.run_batch(s, [500], 300, M.splitmix64(2137), n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+@pytest.mark.parametrize("method", ["none", "bonferroni", "holm", "benjamini_hochberg"])
+def test_sweep_with_exclusion_and_corrections(method):
+    s = S.sweep_spec()
+    s["correction_method"] = method
+    grid = [20, 24, 40, 100, 333]
+    got = M.run_batch(s, grid, 400, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 400, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert got.factor_excluded[:, 0, 0].all() and not got.factor_excluded[:, 2, 0].any()
+
+
+@pytest.mark.parametrize("name", ["ols_cf_a", "ols_ff_b", "ols_interaction_a", "ols_corr_b", "ols_simple_a"])
+def test_validation_specs_run_batch(name):
+    case = CS.validation_cases()[name]
+    s = CS.case_spec(case)
+    s["report_overall"] = True
+    s["contrast_pairs"] = [[1, 2]] if case["p"] > 2 else []
+    grid = [case["p"] + 2, 50, 200]
+    got = M.run_batch(s, grid, 256, SEED + 1, mode=ALL)
+    want = orc.run_batch(s, grid, 256, SEED + 1, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_sampled_factor_exclusion_varies_per_sim():
+    s = S.add_factor(S.base_spec(2), [0.7, 0.2, 0.1], [0.4, 0.6])
+    s["effect_sizes"][1] = 0.3
+    s["target_indices"] = [1, 3, 4]
+    s["factor_sampled"] = [True]
+    s["factor_min_level_count"] = 5
+    s["correction_method"] = "holm"
+    grid = [30, 45, 90]
+    got = M.run_batch(s, grid, 512, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 512, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    frac = got.factor_excluded[:, 0, 0].mean()
+    assert 0.05 < frac < 0.95  # both the reduced and the full fit were exercised
+
+
+def test_fit_columns_reduced_test_design():
+    s = S.headline_spec()
+    s["fit_columns"] = [0, 1, 2, 5]
+    s["target_indices"] = [1, 2, 7]
+    got = M.run_batch(s, [60, 120], 256, SEED, mode=ALL)
+    want = orc.run_batch(s, [60, 120], 256, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert np.isnan(got.t_sq[:, :, 2]).all()
+
+
+def test_rank_deficient_design_reports_not_converged():
+    s = S.add_factor(S.base_spec(1), [0.5, 0.5], [0.3])
+    s = S.add_interaction(s, [2], 0.0)  # a copy of the dummy column → singular X'X
+    s["target_indices"] = [1]
+    got = M.run_batch(s, [40], 64, SEED, mode=ALL)
+    want = orc.run_batch(s, [40], 64, SEED, capture=True)
+    assert_batch_equal(got, want)
+    assert not got.converged.any() and not got.uncorrected.any()
+
+
+def test_every_template_width():
+    for k in range(0, 16):
+        s = S.base_spec(k)
+        s["target_indices"] = list(range(1, 1 + k))
+        s["effect_sizes"] = [0.0] + [0.2] * k
+        s["report_overall"] = True
+        got = M.run_batch(s, [k + 3, 64], 96, SEED + k, mode=ALL)
+        want = orc.run_batch(s, [k + 3, 64], 96, SEED + k, n_threads=orc.host_threads(), capture=True)
+        assert_batch_equal(got, want)
+
+
+# ------------------------------------------------------------------ determinism contract (batch.rs:2715-2786)
+def test_results_independent_of_wave_size_and_shard_offset():
+    s = S.sweep_spec()
+    grid = [40, 80]
+    a = M.run_batch(s, grid, 1000, SEED, mode=ALL)
+    b = M.run_batch(s, grid, 1000, SEED, mode=ALL, wave_sims=137)
+    assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
+    assert b.gpu_launches == math.ceil(1000 / 137)
+    c1 = M.run_batch(s, grid, 600, SEED, mode=ALL, sim_begin=0)
+    c2 = M.run_batch(s, grid, 400, SEED, mode=ALL, sim_begin=600)
+    assert np.array_equal(np.concatenate([c1.uncorrected, c2.uncorrected]), a.uncorrected)
+    assert np.array_equal(c1.counters + c2.counters, a.counters)
+
+
+def test_progress_and_cancel():
+    s = S.headline_spec()
+    seen = []
+    M.run_batch(s, [100], 5000, SEED, lambda cur, tot: seen.append((cur, tot)) or True)
+    assert seen[-1] == (5000, 5000) and 40 <= len(seen) <= 55
+    with pytest.raises(M.Cancelled):
+        M.run_batch(s, [100], 5000, SEED, lambda cur, tot: cur < 1000)
+
+
+def test_errors_match_reference_classes():
+    s = S.headline_spec()
+    with pytest.raises(M.InvalidSpec):
+        M.run_batch(s, [9], 10, SEED)  # df = N - P < 1 (critvals.rs:874-879)
+    bad = S.base_spec(2)
+    bad["correlation"] = [1.0, 1.2, 1.2, 1.0]
+    with pytest.raises(M.CorrelationNotPSD):
+        M.run_batch(bad, [50], 10, SEED)
+    glm = S.headline_spec()
+    glm["estimator"], glm["outcome_kind"] = "glm", "binary"
+    with pytest.raises(M.Unsupported):
+        M.run_batch(glm, [50], 10, SEED)
+    r = M.run_batch(s, [50], 0, SEED, mode=ALL)  # n_sims == 0 → empty-shaped result (batch.rs:390-421)
+    assert r.uncorrected.shape == (0, 1, 2) and r.counters.sum() == 0
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE.json sizes)
+def test_full_size_counts_are_consistent_and_match_analytic_power():
+    from scipy import stats
+    s = S.headline_spec()
+    n, n_sims = 500, 2_000_000
+    r = M.run_batch(s, [n], n_sims, M.splitmix64(2137))
+    T = 2
+    assert r.n_converged[0] == n_sims
+    assert r.hist_uncorrected[0].sum() == n_sims and r.hist_corrected[0].sum() == n_sims
+    # checksum of checksums: Σ_k k·hist[k] = Σ_t successes[t]
+    assert (np.arange(T + 1) * r.hist_uncorrected[0]).sum() == r.success_uncorrected[0].sum()
+    df, ncp = n - 9, 0.18 * math.sqrt(n)
+    tc = stats.t.ppf(0.975, df)
+    power = 1 - stats.nct.cdf(tc, df, ncp) + stats.nct.cdf(-tc, df, ncp)
+    for t in range(T):
+        emp = r.power()[0, t]
+        assert abs(emp - power) < 4 * math.sqrt(power * (1 - power) / n_sims) + 2e-4, (emp, power)
+    # a shard of the same run reproduces the oracle's counts exactly (same sim ids)
+    sub = M.run_batch(s, [n], 3000, M.splitmix64(2137), sim_begin=1_000_000, mode=M.MODE_COUNTS | M.MODE_BYTES)
+    want = orc.run_batch(s, [n], 3000, M.splitmix64(2137), sim_begin=1_000_000, n_threads=orc.host_threads())
+    assert np.array_equal(sub.uncorrected, want["uncorrected"])
+
+
+def test_power_is_monotone_in_n_full_grid():
+    s = S.sweep_spec()
+    grid = list(range(20, 1001, 20))
+    r = M.run_batch(s, grid, 20000, SEED)
+    p = r.power()[:, 0]
+    assert p[-1] > 0.99 and np.all(np.diff(p) > -0.02)
+    assert np.all(r.hist_uncorrected.sum(axis=1) == 20000)
