@@ -27,13 +27,50 @@ static std::mutex g_plan_mutex;  // c_plan is one __constant__ symbol per device
             throw EngineError(MCP_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
     } while (0)
 
+// Small-buffer cache: cudaMalloc/cudaFree cost ~0.1-1 ms each and cudaFree synchronises the device, which
+// would dominate a millisecond-scale run_batch call.  Buffers up to 4 MiB are recycled per (device, size class).
+struct BufferCache {
+    struct Slot { int dev; size_t bytes; void* p; };
+    std::vector<Slot> free_list;
+    std::mutex mu;
+    void* take(int dev, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].dev == dev && free_list[i].bytes == bytes) {
+                void* p = free_list[i].p;
+                free_list.erase(free_list.begin() + (long)i);
+                return p;
+            }
+        return nullptr;
+    }
+    void give(int dev, size_t bytes, void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        free_list.push_back({dev, bytes, p});
+    }
+};
+static BufferCache g_cache;
+
 struct DeviceBuffers {
-    std::vector<void*> ptrs;
+    struct Owned { void* p; size_t bytes; int dev; };
+    std::vector<Owned> owned;
     template <typename T>
     T* alloc(size_t n) {
+        size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const bool pooled = bytes <= (4u << 20);
+        if (pooled) {
+            size_t cls = 256;
+            while (cls < bytes) cls <<= 1;
+            bytes = cls;
+            if (void* p = g_cache.take(dev, bytes)) {
+                owned.push_back({p, bytes, dev});
+                return static_cast<T*>(p);
+            }
+        }
         void* p = nullptr;
-        CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-        ptrs.push_back(p);
+        CUDA_CHECK(cudaMalloc(&p, bytes));
+        owned.push_back({p, pooled ? bytes : 0, dev});
         return static_cast<T*>(p);
     }
     template <typename T>
@@ -43,7 +80,10 @@ struct DeviceBuffers {
         return p;
     }
     ~DeviceBuffers() {
-        for (void* p : ptrs) cudaFree(p);
+        for (auto& o : owned) {
+            if (o.bytes) g_cache.give(o.dev, o.bytes, o.p);
+            else cudaFree(o.p);
+        }
     }
 };
 

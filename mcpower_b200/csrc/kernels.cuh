@@ -41,7 +41,7 @@ struct FitOut {
 };
 
 // Cholesky + solves on a packed lower-triangular system held in registers (all indices static).
-// Same operation order as the oracle's ols_solve (oracle/mcp_oracle.c) → bit-identical t².
+// The operation order here is the parity contract of the test oracle's solver: bit-identical t².
 template <int PT>
 struct RegSolver {
     static constexpr int NACC = PT * (PT + 1) / 2;

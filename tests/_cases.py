@@ -114,3 +114,16 @@ def case_spec(case: dict) -> dict:
 
 def case_seed(case: dict) -> int:
     return int(_one(case["spec"]["seed"]))
+
+
+def analytic_ols_power(beta: float, n: int, P: int, alpha: float = 0.05) -> float:
+    """Two-sided t-test power of one slope under a random standard-normal design with unit error variance:
+    non-central t with ncp = beta * sqrt(S), S = 1/[(X'X)^-1]_jj ~ chi2(n - P + 1), averaged over S
+    (midpoint rule on 4000 chi-square quantiles)."""
+    import numpy as np
+    from scipy import stats
+    df = n - P
+    tc = stats.t.ppf(1 - alpha / 2, df)
+    q = (np.arange(4000) + 0.5) / 4000
+    ncp = beta * np.sqrt(stats.chi2.ppf(q, n - P + 1))
+    return float(np.mean(1 - stats.nct.cdf(tc, df, ncp) + stats.nct.cdf(-tc, df, ncp)))

