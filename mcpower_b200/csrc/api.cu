@@ -294,7 +294,10 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         for (int c : s.interactions[j]) pl.inter_cols[q++] = c;
     }
     pl.inter_ptr[s.interactions.size()] = q;
-    for (int j = 0; j < P; j++) pl.beta[j] = s.effect_sizes[j];
+    for (int j = 0; j < P; j++) {
+        pl.beta[j] = s.effect_sizes[j];
+        if (s.effect_sizes[j] != 0.0) pl.beta_nonzero_mask |= 1u << j;
+    }
     for (int t = 0; t < pl.n_marg; t++) pl.target[t] = s.target_indices[t];
     for (int t = 0; t < pl.n_contrasts; t++) {
         pl.contrast[2 * t] = s.contrast_pairs[t].first;
@@ -407,7 +410,11 @@ static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_beg
     CUDA_CHECK(cudaGetLastError());
 }
 
+#ifdef MCP_ONLY_P9
+#define MCP_FOR_EACH_P(X) X(9)
+#else
 #define MCP_FOR_EACH_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#endif
 
 static void dispatch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
     switch (lw.P) {

@@ -77,6 +77,49 @@ __device__ __forceinline__ float ni_central(float v) {
     return v * a;
 }
 
+// Packed variant for two draws: FMUL2 (sm_100 f32x2) for the multiplies, scalar FADD for the adds — three
+// instructions per Horner step per pair instead of four.  Bit-identical to ni_central: every product and sum is
+// rounded separately.  (A packed add cannot be used: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// with --fmad=false, which would change the rounding.)
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+#define MCP_H2(c)                 \
+    acc = mul2(acc, r);           \
+    unpack2(acc, x, y);           \
+    x = __fadd_rn(x, c);          \
+    y = __fadd_rn(y, c);          \
+    acc = pack2(x, y);
+__device__ __forceinline__ void ni_central_pair(float v0, float v1, float& z0, float& z1) {
+    const unsigned long long vv = pack2(v0, v1);
+    const unsigned long long r = mul2(vv, vv);
+    unsigned long long acc = pack2(2.401336800e+08f, 2.401336800e+08f);
+    float x, y;
+    MCP_H2(-2.359132160e+08f)
+    MCP_H2(9.886485600e+07f)
+    MCP_H2(-2.294391600e+07f)
+    MCP_H2(3.215264750e+06f)
+    MCP_H2(-2.779154375e+05f)
+    MCP_H2(1.463396387e+04f)
+    MCP_H2(-4.216123047e+02f)
+    MCP_H2(1.238584900e+01f)
+    MCP_H2(2.586458445e+00f)
+    MCP_H2(2.506664753e+00f)
+    acc = mul2(vv, acc);
+    unpack2(acc, z0, z1);
+}
+#undef MCP_H2
+
 // tail branch (|v| > BP): copysign(Pt(sqrt(-2 ln_f32(max(0.5-|v|, 2^-25)))), v)
 __device__ __noinline__ float ni_tail(float v) {
     const float a = fabsf(v);

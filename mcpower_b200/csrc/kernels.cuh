@@ -27,11 +27,20 @@ namespace mcp {
 
 __constant__ DevicePlan c_plan;
 
+#ifndef MCP_BLOCK
 #define MCP_BLOCK 128
+#endif
+#ifndef MCP_MIN_BLOCKS
+#define MCP_MIN_BLOCKS 1
+#endif
+#ifndef MCP_UNROLL_TASKS
+#define MCP_UNROLL_TASKS 1
+#endif
 #define MCP_FNZ 1e-30   /* lib.rs:46 FLOAT_NEAR_ZERO */
 #define MCP_EPS_RANK 1e-12 /* batch.rs:41 */
 
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+constexpr int kUnrollTasks = MCP_UNROLL_TASKS;
 
 // ------------------------------------------------------------------------------------------
 // Per-fit results shared by the templated (registers) and generic (local memory) solvers.
@@ -374,57 +383,61 @@ __device__ __noinline__ float transform_residual(int dist, double df_in, float s
     return (float)(sign * (chi2 - df) * scale);
 }
 
+// Per-thread view of the shared-memory slab.  Element `off` of thread t lives at smem[off * STRIDE + t]:
+// consecutive threads hit consecutive banks, so every per-thread access (static or dynamic offset) is
+// conflict-free (the first version used a 36-float thread stride: 58 % of shared wavefronts were conflicts).
+template <int STRIDE>
+struct Slab {
+    float* p;
+    __device__ __forceinline__ float& operator[](int off) const { return p[off * STRIDE]; }
+};
+
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
-template <int PT>
-__device__ __forceinline__ void gen_block(int b, float* __restrict__ slab, SimCtx& cx) {
+template <int PT, typename SlabT>
+__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx) {
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
     const uint32_t k0 = cx.k0, k1 = cx.k1;
     // ---- A. normals for the continuous block (CLASS_XNORM=1, column j) and residual slot 0 (CLASS_RESID=2)
+    // One "column task" = one Philox block → 4 draws → central polynomial → slab column.  Tasks are independent;
+    // the loop is unrolled by 3 so that three Philox chains and six packed Horner chains are in flight per thread
+    // (the kernel runs at 2 warps per scheduler, so latency must be hidden by ILP inside the thread).
     unsigned long long tmask = 0ull;
-#pragma unroll 2
-    for (int j = 0; j < k; j++) {
-        const U4 w = philox4x32_10((uint32_t)b, (uint32_t)j, 1u, 0u, k0, k1);
+    const bool uniform_slot0 = (pl.outcome == O_CONTINUOUS && pl.residual_dist == R_UNIFORM) ||
+                               (pl.outcome == O_BINARY && !pl.link_probit);
+    const int n_tasks = uniform_slot0 ? k : k + 1;
+#pragma unroll kUnrollTasks
+    for (int t = 0; t < n_tasks; t++) {
+        const bool is_x = t < k;
+        const U4 w = philox4x32_10((uint32_t)b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, k0, k1);
+        const int c = is_x ? t : PT - 1;
         const float v0 = word_to_v(w.x), v1 = word_to_v(w.y), v2 = word_to_v(w.z), v3 = word_to_v(w.w);
         float4 z;
-        z.x = ni_central(v0);
-        z.y = ni_central(v1);
-        z.z = ni_central(v2);
-        z.w = ni_central(v3);
-        if (j < 15) {
+        ni_central_pair(v0, v1, z.x, z.y);
+        ni_central_pair(v2, v3, z.z, z.w);
+        if (t < 15 || !is_x) {
             unsigned tb = 0u;
             if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
             if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
             if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
             if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
-            tmask |= (unsigned long long)tb << (4 * j);
+            tmask |= (unsigned long long)tb << (is_x ? 4 * t : 60);
         } else {
             if (fabsf(v0) > MCP_NI_BP) z.x = ni_tail(v0);
             if (fabsf(v1) > MCP_NI_BP) z.y = ni_tail(v1);
             if (fabsf(v2) > MCP_NI_BP) z.z = ni_tail(v2);
             if (fabsf(v3) > MCP_NI_BP) z.w = ni_tail(v3);
         }
-        *reinterpret_cast<float4*>(slab + 4 * j) = z;
+        slab[4 * c + 0] = z.x;
+        slab[4 * c + 1] = z.y;
+        slab[4 * c + 2] = z.z;
+        slab[4 * c + 3] = z.w;
     }
-    {
+    if (uniform_slot0) {
         const U4 w = philox4x32_10((uint32_t)b, 0u, 2u, 0u, k0, k1);
         float4 z;
-        const bool uniform_slot0 = (pl.outcome == O_CONTINUOUS && pl.residual_dist == R_UNIFORM) ||
-                                   (pl.outcome == O_BINARY && !pl.link_probit);
-        if (!uniform_slot0) {
-            const float v0 = word_to_v(w.x), v1 = word_to_v(w.y), v2 = word_to_v(w.z), v3 = word_to_v(w.w);
-            z.x = ni_central(v0);
-            z.y = ni_central(v1);
-            z.z = ni_central(v2);
-            z.w = ni_central(v3);
-            unsigned tb = 0u;
-            if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
-            if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
-            if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
-            if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
-            tmask |= (unsigned long long)tb << 60;
-        } else if (pl.outcome == O_CONTINUOUS) {  // Uniform residual: (2u-1)*sqrt(3) (data_gen.rs:485-501)
+        if (pl.outcome == O_CONTINUOUS) {  // Uniform residual: (2u-1)*sqrt(3) (data_gen.rs:485-501)
             z.x = (float)((2.0 * (double)word_to_unit(w.x) - 1.0) * MCP_SQRT3);
             z.y = (float)((2.0 * (double)word_to_unit(w.y) - 1.0) * MCP_SQRT3);
             z.z = (float)((2.0 * (double)word_to_unit(w.z) - 1.0) * MCP_SQRT3);
@@ -435,7 +448,10 @@ __device__ __forceinline__ void gen_block(int b, float* __restrict__ slab, SimCt
             z.z = word_to_unit(w.z);
             z.w = word_to_unit(w.w);
         }
-        *reinterpret_cast<float4*>(slab + 4 * (PT - 1)) = z;
+        slab[4 * (PT - 1) + 0] = z.x;
+        slab[4 * (PT - 1) + 1] = z.y;
+        slab[4 * (PT - 1) + 2] = z.z;
+        slab[4 * (PT - 1) + 3] = z.w;
     }
     // ---- B. deferred tail branch of the inverse-normal kernel
     while (tmask) {
@@ -507,16 +523,18 @@ __device__ __forceinline__ void gen_block(int b, float* __restrict__ slab, SimCt
 }
 
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
-template <int PT>
-__device__ __forceinline__ double row_xy(int b, int r, const float* __restrict__ slab, SimCtx& cx, double (&xr)[PT]) {
+template <int PT, typename SlabT>
+__device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx& cx, double (&xr)[PT]) {
     const DevicePlan& pl = c_plan;
     const int row = 4 * b + r;
     xr[0] = 1.0;
 #pragma unroll
     for (int j = 1; j < PT; j++) xr[j] = (double)slab[4 * (j - 1) + r];
     double lp = 0.0;
+    const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum: skipping them is bit-exact
 #pragma unroll
-    for (int j = 0; j < PT; j++) lp = lp + xr[j] * pl.beta[j];
+    for (int j = 0; j < PT; j++)
+        if (bm & (1u << j)) lp = lp + xr[j] * pl.beta[j];
     const float ef = slab[4 * (PT - 1) + r];
     double u_re = 0.0;
     if (pl.has_cluster) {  // u_c = f32(normal(word c) * tau), drawn first on the sequential stream (data_gen.rs:146-161)
@@ -539,12 +557,12 @@ __device__ __forceinline__ double row_xy(int b, int r, const float* __restrict__
 // Dynamic shared memory: [MCP_BLOCK] per-thread slabs of 4*SP floats (SP = P|1 keeps the per-thread
 // LDS.128/STS.128 conflict-free), then the optional block-level counters.
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) ols_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
     const DevicePlan& pl = c_plan;
     extern __shared__ __align__(16) float smem[];
-    float* slab = smem + (size_t)threadIdx.x * (4 * SP);
+    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {
         cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
@@ -680,8 +698,9 @@ __global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __re
                                 float* __restrict__ y_out) {
     constexpr int SP = PT | 1;
     const DevicePlan& pl = c_plan;
-    __shared__ __align__(16) float slab[4 * SP];
+    __shared__ __align__(16) float slab_mem[4 * SP];
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Slab<1> slab{slab_mem};
     const uint64_t key = pcg_mix64(base_seed, sim_id);
     SimCtx cx;
     cx.k0 = (uint32_t)key;

@@ -56,6 +56,7 @@ struct DevicePlan {
     int32_t inter_ptr[MCP_MAX_INTER + 1];
     int32_t inter_cols[MCP_MAX_INTER_COMP];
     double beta[MCP_MAX_P];
+    uint32_t beta_nonzero_mask;        // bit j set ⇔ beta[j] != 0
     int32_t target[MCP_MAX_T];         // marginal target columns
     int32_t contrast[2 * MCP_MAX_T];   // (pos, neg) pairs
     // ---- residual / outcome

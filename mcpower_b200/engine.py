@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Callable, Optional, Sequence
@@ -19,7 +20,7 @@ from typing import Callable, Optional, Sequence
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-_SO = _HERE / "libmcpower_b200.so"
+_SO = Path(os.environ.get("MCPOWER_B200_LIB", _HERE / "libmcpower_b200.so"))
 
 MODE_COUNTS, MODE_BYTES, MODE_CAPTURE = 1, 2, 4
 
