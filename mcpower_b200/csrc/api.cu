@@ -87,6 +87,29 @@ struct DeviceBuffers {
     }
 };
 
+// Host twin of device own_exp (device_math.cuh): same IEEE operations, so constants folded on the host
+// (1/exp(gamma²/2)) carry the bits the kernel would compute.
+static double host_own_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.782712893384) return INFINITY;
+    if (x < -745.1332191019412) return 0.0;
+    const double kf = std::rint(x * 1.4426950408889634);
+    double r = std::fma(-kf, 6.93147180369123816490e-01, x);
+    r = std::fma(-kf, 1.90821492927058770002e-10, r);
+    static const double inv_fact[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                                        1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0,
+                                        0.5,               1.0,              1.0};
+    double p = 1.0 / 6227020800.0;
+    for (double c : inv_fact) p = std::fma(p, r, c);
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
+    double s1, s2;
+    std::memcpy(&s1, &b1, 8);
+    std::memcpy(&s2, &b2, 8);
+    return p * s1 * s2;
+}
+
 // ---- exclusion variants (batch.rs:2502-2562) --------------------------------------------------
 static McpVariant make_variant(const Spec& s, int mask) {
     McpVariant v;
@@ -221,7 +244,10 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     if (s.has_upload) unsupported("uploaded-data marginals / bootstrap");
     if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
     if (s.has_between) unsupported("between_var_indices");
-    if (!s.is_optimistic()) unsupported("scenario perturbations (heterogeneity / heteroskedasticity / correlation noise / swaps)");
+    if (s.has_lme) unsupported("lme scenario knobs (random-effect distribution / ICC jitter)");
+    if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
+    for (int v : s.new_dists)
+        if (v >= 100) unsupported("uploaded_* distributions in the scenario menu");
     for (int v : s.var_types)
         if (v >= 100) unsupported("uploaded_* variable types");
     if (s.k > MCP_MAX_K) unsupported("n_non_factor > " + std::to_string(MCP_MAX_K));
@@ -233,7 +259,6 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     size_t comps = 0;
     for (auto& c : s.interactions) comps += c.size();
     if (comps > MCP_MAX_INTER_COMP) unsupported("interaction components > " + std::to_string(MCP_MAX_INTER_COMP));
-    if (s.has_cluster && s.has_lme) unsupported("lme scenario knobs");
 }
 
 struct Lowered {
@@ -311,6 +336,64 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         pl.n_clusters = s.sizing_fixed_size ? pl.max_n / sv : sv;  // generation.rs n_clusters_at(max_n)
     }
     pl.optimistic = s.is_optimistic();
+    // scenario knobs (spec.rs:117-176)
+    pl.heterogeneity = s.heterogeneity;
+    pl.corr_noise_sd = s.corr_noise_sd;
+    pl.dist_change_prob = s.dist_change_prob;
+    pl.resid_change_prob = s.resid_change_prob;
+    pl.n_new_dists = (int)s.new_dists.size();
+    for (size_t i = 0; i < s.new_dists.size(); i++) pl.new_dists[i] = s.new_dists[i];
+    pl.n_resid_dists = (int)s.resid_dists.size();
+    for (size_t i = 0; i < s.resid_dists.size(); i++) pl.resid_dists[i] = s.resid_dists[i];
+    {
+        // heteroskedasticity: gamma = ln(max(lambda,1))/4, driver moments from the BASE spec (spec.rs:436-515,
+        // data_gen.rs:753-776); 1/exp(gamma²/2) uses the same owned exp as the kernel
+        const double lambda = s.hsk_ratio > 1.0 ? s.hsk_ratio : 1.0;
+        const double gamma = std::log(lambda) / 4.0;
+        const int pf = 1 + s.k + s.n_fd;
+        std::vector<double> mu(pf, 0.0), sd(pf, 0.0);
+        mu[0] = 1.0;
+        for (int j = 0; j < s.k; j++) {
+            if (s.var_types[j] == D_BINARY) {
+                const double pp = pl.var_param[j];
+                mu[1 + j] = pp;
+                sd[1 + j] = std::sqrt(std::max(pp * (1.0 - pp), 0.0));
+            } else {
+                sd[1 + j] = 1.0;
+            }
+        }
+        int c = 1 + s.k, po = 0;
+        for (int nl : s.factor_n_levels) {
+            for (int d = 0; d + 1 < nl; d++) {
+                const double pp = s.factor_proportions[po + d + 1];
+                mu[c + d] = pp;
+                sd[c + d] = std::sqrt(std::max(pp * (1.0 - pp), 0.0));
+            }
+            c += nl - 1;
+            po += nl;
+        }
+        double lp_mean = 0.0, lp_var = 0.0;
+        for (int j = 0; j < pf; j++) lp_mean += s.effect_sizes[j] * mu[j];
+        for (int j = 0; j < pf; j++) lp_var += s.effect_sizes[j] * s.effect_sizes[j] * sd[j] * sd[j];
+        for (int j = 0; j < s.k; j++)
+            for (int m = j + 1; m < s.k; m++)
+                lp_var += 2.0 * s.effect_sizes[1 + j] * s.effect_sizes[1 + m] * s.correlation[(size_t)m * s.k + j] * sd[1 + j] * sd[1 + m];
+        const double lp_std = std::sqrt(std::max(lp_var, 0.0));
+        double center = 0.0, stdv = 0.0;
+        if (s.hsk_driver < 0) {
+            center = lp_mean;
+            stdv = lp_std;
+        } else if (s.hsk_driver < pf) {
+            center = mu[s.hsk_driver];
+            stdv = sd[s.hsk_driver];
+        }
+        pl.hsk_gamma = gamma;
+        pl.hsk_driver = s.hsk_driver;
+        pl.apply_hsk = s.outcome == O_CONTINUOUS && gamma > 1e-30 && stdv > 1e-30;
+        pl.hsk_center = center;
+        pl.hsk_inv_std = pl.apply_hsk ? 1.0 / stdv : 0.0;
+        pl.hsk_inv_norm = host_own_exp(-gamma * gamma / 2.0);
+    }
 
     // variants + thresholds
     const bool track = thresholds && F > 0 && s.min_level_count > 0;
@@ -393,7 +476,7 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
 }
 
 // ---- kernel dispatch by P -----------------------------------------------------------------------
-template <int PT>
+template <int PT, bool SCEN>
 static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
     constexpr int SP = PT | 1;
     size_t smem = (size_t)MCP_BLOCK * 4 * SP * sizeof(float);
@@ -402,11 +485,11 @@ static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_beg
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        CUDA_CHECK(cudaFuncSetAttribute(ols_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(ols_power_kernel<PT, SCEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_done[dev & 63] = true;
     }
     const uint32_t blocks = (n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
-    ols_power_kernel<PT><<<blocks, MCP_BLOCK, smem, st>>>(base_seed, sim_begin, n_sims);
+    ols_power_kernel<PT, SCEN><<<blocks, MCP_BLOCK, smem, st>>>(base_seed, sim_begin, n_sims);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -418,7 +501,11 @@ static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_beg
 
 static void dispatch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
     switch (lw.P) {
-#define X(p) case p: launch_power<p>(lw, base_seed, sim_begin, n_sims, st); break;
+#define X(p)                                                                          \
+    case p:                                                                           \
+        if (lw.plan.optimistic) launch_power<p, false>(lw, base_seed, sim_begin, n_sims, st); \
+        else launch_power<p, true>(lw, base_seed, sim_begin, n_sims, st);             \
+        break;
         MCP_FOR_EACH_P(X)
 #undef X
         default: unsupported("n_predictors = " + std::to_string(lw.P));
@@ -495,6 +582,8 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
         const size_t cells = (size_t)n_sims * n_ss;
         pl.counters = lw.bufs.alloc<unsigned long long>((size_t)n_ss * lw.cw);
         CUDA_CHECK(cudaMemset(pl.counters, 0, (size_t)n_ss * lw.cw * sizeof(unsigned long long)));
+        pl.error_flag = lw.bufs.alloc<int>(1);
+        CUDA_CHECK(cudaMemset(pl.error_flag, 0, sizeof(int)));
         if (bytes) {
             pl.out_unc = lw.bufs.alloc<uint8_t>(cells * T);
             pl.out_cor = lw.bufs.alloc<uint8_t>(cells * T);
@@ -553,6 +642,9 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
         cudaEventDestroy(e1);
         r->kernel_ms = ms;
         if (cancelled) throw EngineError(MCP_CANCELLED, "cancelled by host");  // partial results discarded (batch.rs:128-129)
+        int err_flag = 0;
+        CUDA_CHECK(cudaMemcpy(&err_flag, pl.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err_flag == 2) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
 
         auto fetch = [&](auto*& host, const auto* dev, size_t n) {
             using Elem = std::remove_cv_t<std::remove_pointer_t<decltype(dev)>>;
@@ -589,9 +681,15 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
         const int P = lw.P;
         float* dx = lw.bufs.alloc<float>((size_t)max_n * P);
         float* dy = lw.bufs.alloc<float>(max_n);
+        lw.plan.error_flag = lw.bufs.alloc<int>(1);
+        CUDA_CHECK(cudaMemset(lw.plan.error_flag, 0, sizeof(int)));
         CUDA_CHECK(cudaMemcpyToSymbol(c_plan, &lw.plan, sizeof(DevicePlan)));
         switch (P) {
-#define X(p) case p: dgp_dump_kernel<p><<<1, 32>>>(base_seed, sim_id, dx, dy); break;
+#define X(p)                                                                   \
+    case p:                                                                    \
+        if (lw.plan.optimistic) dgp_dump_kernel<p, false><<<1, 32>>>(base_seed, sim_id, dx, dy); \
+        else dgp_dump_kernel<p, true><<<1, 32>>>(base_seed, sim_id, dx, dy);   \
+        break;
             MCP_FOR_EACH_P(X)
 #undef X
             default: unsupported("n_predictors = " + std::to_string(P));
@@ -600,6 +698,9 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
         CUDA_CHECK(cudaDeviceSynchronize());
         CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * P * sizeof(float), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(y, dy, (size_t)max_n * sizeof(float), cudaMemcpyDeviceToHost));
+        int err_flag = 0;
+        CUDA_CHECK(cudaMemcpy(&err_flag, lw.plan.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err_flag == 2) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
     });
 }
 

@@ -392,19 +392,185 @@ struct Slab {
     __device__ __forceinline__ float& operator[](int off) const { return p[off * STRIDE]; }
 };
 
+// ------------------------------------------------------------------------------------------
+// Scenario (non-optimistic) path: the per-sim design draw of populate_design (data_gen.rs:990-1093):
+// perturbed correlation → PSD repair → Cholesky, marginal swaps, residual swap, per-study β jitter.
+// Lives in local memory (runtime k); only instantiated in the SCEN kernels.
+template <int PT>
+struct ScenDesign {
+    static constexpr int KT = PT > 1 ? PT - 1 : 1;
+    double L[KT * KT];  // row-major lower Cholesky factor of this sim's correlation
+    int vt[KT];         // this sim's marginal types
+    int residual_dist;
+    int use_het;
+    double beta_eff[PT];
+    int ok;
+};
+
+// Column-major LLT, left-looking (same order as the host's correlation_llt / data_gen.rs:55-75).
+__device__ __noinline__ int llt_colmajor(double* a, int n) {
+    for (int j = 0; j < n; j++) {
+        double diag = a[j * n + j];
+        for (int m = 0; m < j; m++) diag -= a[m * n + j] * a[m * n + j];
+        if (!(diag > 0.0) || isinf(diag)) return -1;
+        const double ljj = sqrt(diag);
+        a[j * n + j] = ljj;
+        for (int i = j + 1; i < n; i++) {
+            double s = a[j * n + i];
+            for (int m = 0; m < j; m++) s -= a[m * n + i] * a[m * n + j];
+            a[j * n + i] = s / ljj;
+        }
+    }
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < j; i++) a[j * n + i] = 0.0;
+    return 0;
+}
+
+// Cyclic Jacobi eigen-decomposition (row-major a destroyed; eigenvalues w, eigenvectors = columns of v).
+// Stand-in for faer's self_adjoint_eigen (correlation.rs:120-127); the oracle runs the same rotations.
+__device__ __noinline__ void jacobi_eigh(double* a, int n, double* w, double* v) {
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) v[i * n + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0.0;
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) off += a[i * n + j] * a[i * n + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = a[p * n + q];
+                if (fabs(apq) < 1e-300) continue;
+                const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int kk = 0; kk < n; kk++) {
+                    const double akp = a[kk * n + p], akq = a[kk * n + q];
+                    a[kk * n + p] = c * akp - s * akq;
+                    a[kk * n + q] = s * akp + c * akq;
+                }
+                for (int kk = 0; kk < n; kk++) {
+                    const double apk = a[p * n + kk], aqk = a[q * n + kk];
+                    a[p * n + kk] = c * apk - s * aqk;
+                    a[q * n + kk] = s * apk + c * aqk;
+                }
+                for (int kk = 0; kk < n; kk++) {
+                    const double vkp = v[kk * n + p], vkq = v[kk * n + q];
+                    v[kk * n + p] = c * vkp - s * vkq;
+                    v[kk * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; i++) w[i] = a[i * n + i];
+}
+
+template <int PT>
+__device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t base_seed, uint64_t sim_id) {
+    constexpr int KT = ScenDesign<PT>::KT;
+    const DevicePlan& pl = c_plan;
+    const int k = pl.k;
+    SeqRng sr;
+    sr.init(pcg_mix64(base_seed, sim_id ^ 0x5C5C5C5C5C5C5C5CULL));  // scenarios.rs:19,50
+    double a[KT * KT];  // column-major working matrix
+    // ---- perturb_correlation (scenarios.rs:67-120)
+    if (pl.corr_noise_sd == 0.0) {
+        for (int j = 0; j < k; j++)
+            for (int i = 0; i < k; i++) a[j * k + i] = pl.corr[j * MCP_MAX_K + i];
+    } else {
+        double noise[KT * KT];
+        for (int j = 0; j < k; j++)
+            for (int i = 0; i < k; i++) noise[j * k + i] = (double)sr.next_normal() * pl.corr_noise_sd;
+        for (int j = 0; j < k; j++)
+            for (int i = 0; i < k; i++) {
+                const double sym = 0.5 * (noise[j * k + i] + noise[i * k + j]);
+                const double v = pl.corr[j * MCP_MAX_K + i] + sym;
+                a[j * k + i] = v < -0.8 ? -0.8 : (v > 0.8 ? 0.8 : v);
+            }
+        for (int i = 0; i < k; i++) a[i * k + i] = 1.0;
+    }
+    // ---- psd_repair_and_factor (correlation.rs:82-189)
+    sd.ok = 1;
+    if (k > 0) {
+        double cp[KT * KT];
+        for (int i = 0; i < k * k; i++) cp[i] = a[i];
+        if (llt_colmajor(cp, k) == 0) {
+            for (int i = 0; i < k * k; i++) a[i] = cp[i];
+        } else {
+            double sym[KT * KT], vec[KT * KT], lam[KT], d[KT];
+            for (int j = 0; j < k; j++)
+                for (int i = 0; i < k; i++) sym[i * k + j] = i >= j ? a[j * k + i] : a[i * k + j];
+            jacobi_eigh(sym, k, lam, vec);
+            for (int q = 0; q < k; q++)
+                if (!(lam[q] > 1e-10)) lam[q] = 1e-10;
+            for (int i = 0; i < k; i++)
+                for (int j = 0; j < k; j++) {
+                    double acc = 0.0;
+                    for (int q = 0; q < k; q++) acc += vec[i * k + q] * lam[q] * vec[j * k + q];
+                    cp[i * k + j] = acc;  // repaired, row-major
+                }
+            for (int i = 0; i < k; i++) d[i] = cp[i * k + i] > 0.0 ? sqrt(cp[i * k + i]) : 1.0;
+            for (int j = 0; j < k; j++)
+                for (int i = 0; i < k; i++) a[j * k + i] = cp[i * k + j] / (d[i] * d[j]);
+            for (int i = 0; i < k; i++) a[i * k + i] = 1.0;
+            if (llt_colmajor(a, k) != 0) sd.ok = 0;
+        }
+    }
+    for (int j = 0; j < k; j++)
+        for (int m = 0; m < k; m++) sd.L[j * KT + m] = m <= j ? a[m * k + j] : 0.0;
+    // ---- perturb_var_types (scenarios.rs:127-156)
+    for (int j = 0; j < k; j++) sd.vt[j] = pl.var_type[j];
+    if (pl.dist_change_prob > 0.0 && pl.n_new_dists > 0) {
+        for (int j = 0; j < k; j++) {
+            const double u = (double)sr.next_uniform();
+            if (sd.vt[j] == D_NORMAL && !pl.var_pinned[j] && u < pl.dist_change_prob) {
+                int q = (int)((double)sr.next_uniform() * (double)pl.n_new_dists);
+                if (q > pl.n_new_dists - 1) q = pl.n_new_dists - 1;
+                sd.vt[j] = pl.new_dists[q];
+            }
+        }
+    }
+    // ---- pick_residual (scenarios.rs:163-186)
+    sd.residual_dist = pl.residual_dist;
+    if (pl.resid_change_prob > 0.0 && pl.n_resid_dists > 0) {
+        const double u = (double)sr.next_uniform();
+        if (u < pl.resid_change_prob && pl.residual_dist == R_NORMAL && !pl.residual_pinned) {
+            int q = (int)((double)sr.next_uniform() * (double)pl.n_resid_dists);
+            if (q > pl.n_resid_dists - 1) q = pl.n_resid_dists - 1;
+            sd.residual_dist = pl.resid_dists[q];
+        }
+    }
+    // ---- per-study effect draw (data_gen.rs:709-751), domain-separated stream (scenarios.rs:28)
+    const double het = pl.heterogeneity > 0.0 ? pl.heterogeneity : 0.0;
+    sd.use_het = het > MCP_FNZ;
+    if (sd.use_het) {
+        SeqRng hr;
+        hr.init(pcg_mix64(base_seed, sim_id ^ 0x4848484848484848ULL));
+        const double int_sd = pl.outcome == O_CONTINUOUS ? 0.0 : het;
+        for (int j = 0; j < PT; j++) {
+            const double bj = pl.beta[j];
+            const double sj = j == 0 ? int_sd : het * fabs(bj);
+            const double raw = bj + (double)hr.next_normal() * sj;
+            if (j == 0 || bj == 0.0) sd.beta_eff[j] = raw;
+            else if (bj > 0.0) sd.beta_eff[j] = raw > 0.0 ? raw : 0.0;
+            else sd.beta_eff[j] = raw < 0.0 ? raw : 0.0;
+        }
+    }
+}
+
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
-template <int PT, typename SlabT>
-__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx) {
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
+    constexpr int KT = ScenDesign<PT>::KT;
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
     const uint32_t k0 = cx.k0, k1 = cx.k1;
+    const int residual_dist = SCEN ? sd->residual_dist : pl.residual_dist;
     // ---- A. normals for the continuous block (CLASS_XNORM=1, column j) and residual slot 0 (CLASS_RESID=2)
     // One "column task" = one Philox block → 4 draws → central polynomial → slab column.  Tasks are independent;
     // the loop is unrolled by 3 so that three Philox chains and six packed Horner chains are in flight per thread
     // (the kernel runs at 2 warps per scheduler, so latency must be hidden by ILP inside the thread).
     unsigned long long tmask = 0ull;
-    const bool uniform_slot0 = (pl.outcome == O_CONTINUOUS && pl.residual_dist == R_UNIFORM) ||
+    const bool uniform_slot0 = (pl.outcome == O_CONTINUOUS && residual_dist == R_UNIFORM) ||
                                (pl.outcome == O_BINARY && !pl.link_probit);
     const int n_tasks = uniform_slot0 ? k : k + 1;
 #pragma unroll kUnrollTasks
@@ -462,12 +628,12 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx) {
         slab[idx] = ni_tail(slab[idx]);
     }
     // ---- B'. t / chi-square residuals need extra CLASS_RESID slots
-    if (pl.outcome == O_CONTINUOUS && pl.residual_dist != R_NORMAL && pl.residual_dist != R_UNIFORM) {
+    if (pl.outcome == O_CONTINUOUS && residual_dist != R_NORMAL && residual_dist != R_UNIFORM) {
         for (int r = 0; r < 4; r++)
-            slab[4 * (PT - 1) + r] = transform_residual(pl.residual_dist, pl.residual_df, slab[4 * (PT - 1) + r], (uint32_t)b, r, k0, k1);
+            slab[4 * (PT - 1) + r] = transform_residual(residual_dist, pl.residual_df, slab[4 * (PT - 1) + r], (uint32_t)b, r, k0, k1);
     }
     // ---- C. Cholesky mix + marginal transforms (data_gen.rs:334-363); skipped when L = I and all Normal
-    if (!(pl.l_identity && pl.all_normal)) {
+    if (SCEN || !(pl.l_identity && pl.all_normal)) {
         for (int r = 0; r < 4; r++) {
             double zr[PT];  // zr[j] = z of continuous column j (j < k)
 #pragma unroll
@@ -477,9 +643,9 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx) {
                 if (j < k) {
                     double a = 0.0;
 #pragma unroll
-                    for (int m = 0; m <= j; m++) a = a + pl.L[j * MCP_MAX_K + m] * zr[m];
+                    for (int m = 0; m <= j; m++) a = a + (SCEN ? sd->L[j * KT + m] : pl.L[j * MCP_MAX_K + m]) * zr[m];
                     float xf = (float)a;
-                    const int vt = pl.var_type[j];
+                    const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
                     if (vt != D_NORMAL) xf = (float)apply_marginal((double)xf, vt, pl.var_param[j], pl.t3_table);
                     slab[4 * j + r] = xf;
                 }
@@ -523,8 +689,8 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx) {
 }
 
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
-template <int PT, typename SlabT>
-__device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx& cx, double (&xr)[PT]) {
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx& cx, double (&xr)[PT], const ScenDesign<PT>* sd) {
     const DevicePlan& pl = c_plan;
     const int row = 4 * b + r;
     xr[0] = 1.0;
@@ -535,12 +701,29 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
 #pragma unroll
     for (int j = 0; j < PT; j++)
         if (bm & (1u << j)) lp = lp + xr[j] * pl.beta[j];
-    const float ef = slab[4 * (PT - 1) + r];
+    float ef = slab[4 * (PT - 1) + r];
     double u_re = 0.0;
     if (pl.has_cluster) {  // u_c = f32(normal(word c) * tau), drawn first on the sequential stream (data_gen.rs:146-161)
         const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
         const uint32_t cid = pl.sizing_fixed_size ? (uint32_t)(row / cs) : (uint32_t)(row % cs);
         u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
+    }
+    if (SCEN) {
+        // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)
+        const double lp_clean = lp;
+        if (sd->use_het) {
+            double le = 0.0;
+#pragma unroll
+            for (int j = 0; j < PT; j++) le = le + xr[j] * sd->beta_eff[j];
+            lp = le;
+        }
+        if (pl.apply_hsk) {  // Var(e_i) = exp(gamma z_i) / exp(gamma^2/2) (data_gen.rs:798-809, 876-888)
+            const double drv = pl.hsk_driver < 0 ? lp_clean : (double)slab[4 * (pl.hsk_driver - 1) + r];
+            const double zz = (drv - pl.hsk_center) * pl.hsk_inv_std;
+            const double mult = own_exp(pl.hsk_gamma * zz) * pl.hsk_inv_norm;
+            ef = (float)((double)ef * sqrt(mult));
+            return (double)(float)((lp + u_re) + (double)ef);
+        }
     }
     if (pl.outcome == O_CONTINUOUS) return (double)(float)(lp + (double)ef + u_re);
     const double eta = lp + u_re;
@@ -556,7 +739,7 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
 //   PT  : total design columns P (compile-time → register-resident sufficient statistics)
 // Dynamic shared memory: [MCP_BLOCK] per-thread slabs of 4*SP floats (SP = P|1 keeps the per-thread
 // LDS.128/STS.128 conflict-free), then the optional block-level counters.
-template <int PT>
+template <int PT, bool SCEN>
 __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
@@ -580,6 +763,13 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
         cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;  // Normal RE: one word per cluster
         const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
+        ScenDesign<PT> sdv;
+        ScenDesign<PT>* sd = nullptr;
+        if (SCEN) {
+            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+            sd = &sdv;
+            if (!sdv.ok) atomicExch(pl.error_flag, 2);  // EngineError::CorrelationNotPSD (data_gen.rs:1049)
+        }
 
         double acc[NACC], xty[PT];
 #pragma unroll
@@ -601,14 +791,14 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
         const int n_blocks = (max_n + 3) >> 2;
 
         for (int b = 0; b < n_blocks; b++) {
-            gen_block<PT>(b, slab, cx);
+            gen_block<PT, SCEN>(b, slab, cx, sd);
             // ---- E. row pass: widen, linear predictor, y, sufficient statistics, fits at grid points
 #pragma unroll 1
             for (int r = 0; r < 4; r++) {
                 const int row = 4 * b + r;
                 if (row >= max_n) break;
                 double xr[PT];
-                const double yd = row_xy<PT>(b, r, slab, cx, xr);
+                const double yd = row_xy<PT, SCEN>(b, r, slab, cx, xr, sd);
 #pragma unroll
                 for (int a = 0; a < PT; a++) {
 #pragma unroll
@@ -693,7 +883,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
 // ------------------------------------------------------------------------------------------
 // K0: dump the generated design of one simulation (introspect::capture_sim0_data, introspect.rs:104-155)
 // through exactly the same generation functions as the power kernel.  One thread; parity/debug only.
-template <int PT>
+template <int PT, bool SCEN>
 __global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __restrict__ x_out /* col-major max_n × P */,
                                 float* __restrict__ y_out) {
     constexpr int SP = PT | 1;
@@ -709,13 +899,20 @@ __global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __re
     cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
     cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
     const int max_n = pl.max_n;
+    ScenDesign<PT> sdv;
+    ScenDesign<PT>* sd = nullptr;
+    if (SCEN) {
+        scen_populate<PT>(sdv, base_seed, sim_id);
+        sd = &sdv;
+        if (!sdv.ok) atomicExch(pl.error_flag, 2);
+    }
     for (int b = 0; b < (max_n + 3) / 4; b++) {
-        gen_block<PT>(b, slab, cx);
+        gen_block<PT, SCEN>(b, slab, cx, sd);
         for (int r = 0; r < 4; r++) {
             const int row = 4 * b + r;
             if (row >= max_n) break;
             double xr[PT];
-            const double yd = row_xy<PT>(b, r, slab, cx, xr);
+            const double yd = row_xy<PT, SCEN>(b, r, slab, cx, xr, sd);
             x_out[row] = 1.0f;
             for (int j = 1; j < PT; j++) x_out[(size_t)j * max_n + row] = slab[4 * (j - 1) + r];
             y_out[row] = (float)yd;

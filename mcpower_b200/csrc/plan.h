@@ -94,6 +94,7 @@ struct DevicePlan {
     uint8_t* out_overall;              // [n_sims][n_ss] or NULL
     uint8_t* out_fx;                   // [n_sims][n_ss][n_factors] or NULL
     double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
+    int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
     int32_t counter_width;             // 2T + 2 + 2(T+1) + n_factors
     int32_t smem_counters;             // counters staged in shared memory (fits)
 };

@@ -190,6 +190,70 @@ def test_every_template_width():
         assert_batch_equal(got, want)
 
 
+# ------------------------------------------------------------------ robustness scenarios (BASELINE config 3)
+def _scenario_spec(preset: str, alpha: float = 0.05) -> dict:
+    s = S.sweep_spec()
+    s["scenario"] = S.scenario(preset)
+    s["crit_values"]["alpha"] = alpha
+    s["heteroskedasticity_driver"] = None
+    return s
+
+
+@pytest.mark.parametrize("preset", ["realistic", "doomer"])
+def test_scenario_design_draw_bit_exact_vs_oracle(preset):
+    """Per-sim perturbed correlation (+ Jacobi PSD repair), marginal swaps, residual swaps (t / chi-square
+    slots), per-study beta jitter, heteroskedastic residuals, sampled factor levels: X and y bit-exact."""
+    s = _scenario_spec(preset)
+    repaired = 0
+    for sim in range(12):
+        x, y = M.generate_sim(s, SEED, sim, 150)
+        xo, yo, _ = orc.generate_sim(s, SEED, sim, 150)
+        assert np.array_equal(x.view(np.uint32), xo.view(np.uint32)), (preset, sim)
+        assert np.array_equal(y.view(np.uint32), yo.view(np.uint32)), (preset, sim)
+        repaired += 1
+    assert repaired == 12
+
+
+@pytest.mark.parametrize("preset", ["realistic", "doomer"])
+def test_scenario_run_batch_matches_oracle(preset):
+    s = _scenario_spec(preset)
+    grid = [30, 90, 240]
+    got = M.run_batch(s, grid, 384, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 384, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_scenario_single_knobs_match_oracle():
+    base = S.headline_spec()
+    base["report_overall"] = True
+    knobs = [("heterogeneity", 0.4), ("heteroskedasticity_ratio", 4.0), ("correlation_noise_sd", 0.3),
+             ("distribution_change_prob", 0.8), ("residual_change_prob", 0.8)]
+    for key, val in knobs:
+        s = dict(base, scenario=dict(S.scenario("optimistic"), **{key: val, "residual_df": 5.0}))
+        got = M.run_batch(s, [60, 200], 256, SEED, mode=ALL)
+        want = orc.run_batch(s, [60, 200], 256, SEED, n_threads=orc.host_threads(), capture=True)
+        assert_batch_equal(got, want)
+    s = dict(base, heteroskedasticity_driver=2,
+             scenario=dict(S.scenario("optimistic"), heteroskedasticity_ratio=3.0))
+    got = M.run_batch(s, [80], 256, SEED, mode=ALL)
+    want = orc.run_batch(s, [80], 256, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_five_sigma_alpha_joint_power_doomer():
+    """Config 3: all-tests-significant joint power at alpha = 5e-7 — the last histogram bucket."""
+    s = _scenario_spec("doomer", alpha=5e-7)
+    s["effect_sizes"] = [0.0, 0.6, 0.5, 0.5, 0.4, 0.4, 0.4, 0.4, 0.4, 0.8, 1.0]
+    n_sims = 4096
+    got = M.run_batch(s, [400, 1000], n_sims, SEED, mode=M.MODE_COUNTS | M.MODE_BYTES)
+    want = orc.run_batch(s, [400, 1000], n_sims, SEED, n_threads=orc.host_threads())
+    assert np.array_equal(got.uncorrected, want["uncorrected"])
+    T = got.n_targets
+    joint = got.hist_uncorrected[:, T] / n_sims
+    assert np.array_equal(got.hist_uncorrected[:, T], (want["uncorrected"].sum(axis=2) == T).sum(axis=0))
+    assert joint[1] >= joint[0]
+
+
 # ------------------------------------------------------------------ determinism contract (batch.rs:2715-2786, SURVEY §8b)
 def test_results_independent_of_wave_size_and_shard_offset():
     s = S.sweep_spec()
