@@ -1,5 +1,8 @@
 """Build libmcpower_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo snapshot).
 
+The template-heavy kernels are split over several translation units (kernel_tu.cu compiled with different
+-DMCP_TU_ID / -DMCP_P_LO / -DMCP_P_HI [/-DMCP_TU_GLM]) that build in parallel; api.cu holds the host side.
+
 -fmad=false: the reference's f32 data plane is plain mul/add by contract (rng.rs:199-202); every fused
 operation in the kernels is an explicit fma().  -lineinfo keeps ncu's source page usable.
 """
@@ -9,16 +12,21 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
+OBJ = HERE / "build"
 SO = HERE / "libmcpower_b200.so"
-SOURCES = ["api.cu"]
-DEPS = ["api.cu", "kernels.cuh", "device_math.cuh", "plan.h", "spec.hpp", "critvals.hpp", "json.hpp",
-        "../../include/mcpower_b200.h"]
+DEPS = ["api.cu", "kernel_tu.cu", "kernels.cuh", "kernels_glm.cuh", "device_math.cuh", "pipe_bench.cuh", "launch.h",
+        "plan.h", "spec.hpp", "critvals.hpp", "json.hpp", "../../include/mcpower_b200.h"]
+# (tu id, P_lo, P_hi, glm) — must match MCP_TU_LIST in csrc/launch.h
+TUS = [(0, 1, 6, False), (1, 7, 9, False), (2, 10, 11, False), (3, 12, 13, False), (4, 14, 15, False), (5, 16, 16, False),
+       (6, 1, 8, True), (7, 9, 12, True), (8, 13, 16, True)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
+# the image exports CC=/opt/gcc/bin/gcc (no libgomp spec); nvcc must use the system host compiler (-ccbin)
 
 
 def nvcc() -> str:
@@ -35,20 +43,33 @@ def needs_build() -> bool:
     return any((CSRC / d).resolve().stat().st_mtime > t for d in DEPS) or Path(__file__).stat().st_mtime > t
 
 
-def build(force: bool = False, verbose: bool = False, extra=()) -> Path:
-    if not force and not needs_build():
-        return SO
-    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-o", str(SO), *[str(CSRC / s) for s in SOURCES]]
+def _run(cmd, verbose):
     if verbose:
         print(" ".join(cmd), flush=True)
-    env = dict(os.environ)
-    # the image exports CC=/opt/gcc/bin/gcc (no libgomp spec); nvcc must use the system host compiler
-    res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], capture_output=True, text=True, env=env)
+    res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    return res.stdout + res.stderr
+
+
+def build(force: bool = False, verbose: bool = False, extra=(), only_tus=None) -> Path:
+    if not force and not needs_build():
+        return SO
+    OBJ.mkdir(exist_ok=True)
+    cc = nvcc()
+    jobs = [([cc, *NVCC_FLAGS, *extra, "-c", "-o", str(OBJ / "api.o"), str(CSRC / "api.cu")], OBJ / "api.o")]
+    for tid, lo, hi, glm in TUS:
+        defs = [f"-DMCP_TU_ID={tid}", f"-DMCP_P_LO={lo}", f"-DMCP_P_HI={hi}"] + (["-DMCP_TU_GLM"] if glm else [])
+        obj = OBJ / f"tu{tid}.o"
+        jobs.append(([cc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", str(obj), str(CSRC / "kernel_tu.cu")], obj))
+    logs = []
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        for out in ex.map(lambda j: _run(j[0], verbose), jobs):
+            logs.append(out)
+    _run([cc, "-shared", "-o", str(SO), *[str(j[1]) for j in jobs], "-ccbin", "/usr/bin/g++"], verbose)
     if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        sys.stderr.write("".join(logs))
     return SO
 
 

@@ -12,7 +12,9 @@
 
 #include "../../include/mcpower_b200.h"
 #include "critvals.hpp"
-#include "kernels.cuh"
+#include "device_math.cuh"
+#include "launch.h"
+#include "pipe_bench.cuh"
 #include "spec.hpp"
 
 namespace mcp {
@@ -239,7 +241,12 @@ static std::vector<uint8_t> exact_walk_levels(const double* probs, int nl, int m
 }
 
 static void check_supported(const Spec& s, bool generation_only = false) {
-    if (!generation_only && s.estimator != E_OLS) unsupported("estimator glm/mle (OLS arm only in this build; DESIGN.md §7)");
+    if (!generation_only && s.estimator == E_MLE) unsupported("estimator mle (mixed models; DESIGN.md §7)");
+    if (!generation_only && s.estimator == E_GLM) {
+        if (s.has_cluster) unsupported("clustered GLM (GLMM)");
+        if (!s.contrast_pairs.empty()) unsupported("contrast_pairs with estimator glm (the reference's GLM arm has no contrasts, batch.rs:2060-2062)");
+        if (s.outcome == O_CONTINUOUS) invalid("estimator Glm requires a binary or count outcome");
+    }
     if (!generation_only && s.has_posthoc) unsupported("posthoc blocks");
     if (s.has_upload) unsupported("uploaded-data marginals / bootstrap");
     if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
@@ -417,10 +424,11 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         for (int f = 0; f < F; f++)
             if (!levels[f].empty()) std::copy(levels[f].begin(), levels[f].end(), levels_flat.begin() + (size_t)f * pl.max_n);
     }
-    std::vector<std::vector<char>> needed(nv, std::vector<char>(n_ss, track && !pl.exact_walk ? 1 : 0));
+    const bool all_masks = track && (!pl.exact_walk || s.estimator == E_GLM);  // GLM: the separation fallback can drop any factor
+    std::vector<std::vector<char>> needed(nv, std::vector<char>(n_ss, all_masks ? 1 : 0));
     if (!track) {
         for (uint32_t g = 0; g < n_ss; g++) needed[0][g] = 1;
-    } else if (pl.exact_walk) {
+    } else if (!all_masks) {
         for (uint32_t g = 0; g < n_ss; g++) {
             int mask = 0;
             for (int f = 0; f < F; f++) {
@@ -475,41 +483,15 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
 }
 
-// ---- kernel dispatch by P -----------------------------------------------------------------------
-template <int PT, bool SCEN>
-static void launch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
-    constexpr int SP = PT | 1;
-    size_t smem = (size_t)MCP_BLOCK * 4 * SP * sizeof(float);
-    if (lw.plan.smem_counters) smem += (size_t)lw.n_ss * lw.cw * sizeof(unsigned);
-    static bool attr_done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_done[dev & 63]) {
-        CUDA_CHECK(cudaFuncSetAttribute(ols_power_kernel<PT, SCEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done[dev & 63] = true;
-    }
-    const uint32_t blocks = (n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
-    ols_power_kernel<PT, SCEN><<<blocks, MCP_BLOCK, smem, st>>>(base_seed, sim_begin, n_sims);
-    CUDA_CHECK(cudaGetLastError());
-}
-
-#ifdef MCP_ONLY_P9
-#define MCP_FOR_EACH_P(X) X(9)
-#else
-#define MCP_FOR_EACH_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
-#endif
-
-static void dispatch_power(const Lowered& lw, uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, cudaStream_t st) {
-    switch (lw.P) {
-#define X(p)                                                                          \
-    case p:                                                                           \
-        if (lw.plan.optimistic) launch_power<p, false>(lw, base_seed, sim_begin, n_sims, st); \
-        else launch_power<p, true>(lw, base_seed, sim_begin, n_sims, st);             \
-        break;
-        MCP_FOR_EACH_P(X)
+// ---- kernel dispatch: ask each kernel translation unit in turn (launch.h) -------------------------
+static void dispatch_power(const Lowered& lw, bool glm, const KernelArgs& a) {
+    cudaError_t err = cudaSuccess;
+    bool handled = false;
+#define X(id) if (!handled) handled = tu##id##_launch_power(lw.P, glm, !lw.plan.optimistic, lw.plan, a, &err);
+    MCP_TU_LIST(X)
 #undef X
-        default: unsupported("n_predictors = " + std::to_string(lw.P));
-    }
+    if (!handled) unsupported("n_predictors = " + std::to_string(lw.P));
+    CUDA_CHECK(err);
 }
 
 static void select_device(int device) {
@@ -592,7 +574,7 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             if (F > 0) pl.out_fx = lw.bufs.alloc<uint8_t>(cells * F);
         }
         if (capture) pl.out_tsq = lw.bufs.alloc<double>(cells * T);
-        CUDA_CHECK(cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan)));
+        const bool glm = s.estimator == E_GLM;
 
         McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
         r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
@@ -604,15 +586,25 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
         CUDA_CHECK(cudaEventCreate(&e0));
         CUDA_CHECK(cudaEventCreate(&e1));
         // batch.rs:449-450 — report ~50 times per run; cancellation is polled between waves
-        uint32_t wave = opt.wave_sims ? opt.wave_sims : (progress ? std::max<uint32_t>((n_sims + 49) / 50, MCP_BLOCK) : n_sims);
+        uint32_t wave = opt.wave_sims ? opt.wave_sims : (progress ? std::max<uint32_t>((n_sims + 49) / 50, 128u) : n_sims);
         wave = std::max<uint32_t>(wave, 1);
+        float* glm_scratch = nullptr;
+        if (glm) {
+            // IRLS makes several passes over each study's data: the f32 plane of a wave is kept in HBM as
+            // [row][column][sim] (coalesced across the sims of a warp); the wave is capped at ~6 GiB of scratch
+            const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float);
+            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
+            wave = std::min(wave, cap);
+            wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
+            glm_scratch = lw.bufs.alloc<float>((size_t)wave * pl.max_n * lw.P);
+        }
         CUDA_CHECK(cudaEventRecord(e0, st));
         bool cancelled = false;
         for (uint64_t done = 0; done < n_sims;) {
             const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_sims - done);
             // the byte tensors are indexed by the sim's position in this call, so waves shift the base pointers
+            DevicePlan shifted = pl;
             if (done > 0 && (bytes || capture)) {
-                DevicePlan shifted = pl;
                 if (bytes) {
                     shifted.out_unc = pl.out_unc + done * n_ss * T;
                     shifted.out_cor = pl.out_cor + done * n_ss * T;
@@ -621,9 +613,15 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                     if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
                 }
                 if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
-                CUDA_CHECK(cudaMemcpyToSymbolAsync(c_plan, &shifted, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st));
             }
-            dispatch_power(lw, base_seed, opt.sim_begin + done, cnt, st);
+            {
+                Lowered& lwr = lw;
+                const DevicePlan saved = lwr.plan;
+                lwr.plan = shifted;
+                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch};
+                dispatch_power(lwr, glm, ka);
+                lwr.plan = saved;
+            }
             r->gpu_launches++;
             done += cnt;
             if (progress) {
@@ -683,18 +681,15 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
         float* dy = lw.bufs.alloc<float>(max_n);
         lw.plan.error_flag = lw.bufs.alloc<int>(1);
         CUDA_CHECK(cudaMemset(lw.plan.error_flag, 0, sizeof(int)));
-        CUDA_CHECK(cudaMemcpyToSymbol(c_plan, &lw.plan, sizeof(DevicePlan)));
-        switch (P) {
-#define X(p)                                                                   \
-    case p:                                                                    \
-        if (lw.plan.optimistic) dgp_dump_kernel<p, false><<<1, 32>>>(base_seed, sim_id, dx, dy); \
-        else dgp_dump_kernel<p, true><<<1, 32>>>(base_seed, sim_id, dx, dy);   \
-        break;
-            MCP_FOR_EACH_P(X)
+        {
+            cudaError_t err = cudaSuccess;
+            bool handled = false;
+#define X(id) if (!handled) handled = tu##id##_dump(P, !lw.plan.optimistic, lw.plan, base_seed, sim_id, dx, dy, &err);
+            MCP_TU_LIST(X)
 #undef X
-            default: unsupported("n_predictors = " + std::to_string(P));
+            if (!handled) unsupported("n_predictors = " + std::to_string(P));
+            CUDA_CHECK(err);
         }
-        CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaDeviceSynchronize());
         CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * P * sizeof(float), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(y, dy, (size_t)max_n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -715,12 +710,15 @@ int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t
         double* dout = bufs.alloc<double>(3 * p + 4);
         CUDA_CHECK(cudaMemcpy(dx, x_colmajor, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-        switch ((int)p) {
-#define X(pp) case pp: fit_data_kernel<pp><<<1, 32>>>(dx, dy, (int)n, dout); break;
-            MCP_FOR_EACH_P(X)
+        {
+            cudaError_t err = cudaSuccess;
+            bool handled = false;
+#define X(id) if (!handled) handled = tu##id##_fit_data((int)p, dx, dy, (int)n, dout, &err);
+            MCP_TU_LIST(X)
 #undef X
+            if (!handled) unsupported("p = " + std::to_string(p));
+            CUDA_CHECK(err);
         }
-        CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaDeviceSynchronize());
         CUDA_CHECK(cudaMemcpy(out, dout, (3 * p + 4) * sizeof(double), cudaMemcpyDeviceToHost));
     });

@@ -121,7 +121,7 @@ __device__ __forceinline__ void ni_central_pair(float v0, float v1, float& z0, f
 #undef MCP_H2
 
 // tail branch (|v| > BP): copysign(Pt(sqrt(-2 ln_f32(max(0.5-|v|, 2^-25)))), v)
-__device__ __noinline__ float ni_tail(float v) {
+static __device__ __noinline__ float ni_tail(float v) {
     const float a = fabsf(v);
     float t = 0.5f - a;
     t = fmaxf(t, MCP_NI_FLOOR);
@@ -279,7 +279,7 @@ __device__ __forceinline__ double ln_floor(double u) {
 }
 
 // data_gen.rs:1106-1182 (synthetic variants)
-__device__ __noinline__ double apply_marginal(double z, int dist, double param, const double* __restrict__ t3) {
+static __device__ __noinline__ double apply_marginal(double z, int dist, double param, const double* __restrict__ t3) {
     switch (dist) {
         case 1: return phi(z) < 1.0 - param ? 0.0 : 1.0;
         case 2: {
@@ -299,7 +299,7 @@ __device__ __noinline__ double apply_marginal(double z, int dist, double param, 
 }
 
 // rng.rs:399-419
-__device__ __noinline__ double poisson_quantile(double z, double lambda) {
+static __device__ __noinline__ double poisson_quantile(double z, double lambda) {
     if (!(lambda > 0.0)) return 0.0;
     if (lambda <= 20.0) {
         const double u = phi(z);

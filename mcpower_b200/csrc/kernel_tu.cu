@@ -1,0 +1,137 @@
+// kernel_tu.cu — one kernel translation unit: instantiates the power kernels for P in [MCP_P_LO, MCP_P_HI].
+// Compiled several times in parallel (mcpower_b200/build.py).  MCP_TU_GLM selects the GLM kernels.
+#include "kernels.cuh"
+#ifdef MCP_TU_GLM
+#include "kernels_glm.cuh"
+#endif
+#include "launch.h"
+
+#ifndef MCP_TU_ID
+#error "MCP_TU_ID must be defined"
+#endif
+#define MCP_CAT2(a, b, c) a##b##c
+#define MCP_CAT(a, b, c) MCP_CAT2(a, b, c)
+#define MCP_TU_FN(name) MCP_CAT(tu, MCP_TU_ID, _##name)
+
+namespace mcp {
+
+static size_t power_smem(const DevicePlan& pl, int P) {
+    const int SP = P | 1;
+    size_t smem = (size_t)MCP_BLOCK * 4 * SP * sizeof(float);
+    if (pl.smem_counters) smem += (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned);
+    return smem;
+}
+
+template <int PT>
+static cudaError_t launch_one(bool glm, bool scen, const DevicePlan& pl, const KernelArgs& a) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, a.stream);
+    if (e != cudaSuccess) return e;
+    const size_t smem = power_smem(pl, PT);
+    const uint32_t blocks = (a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
+#ifdef MCP_TU_GLM
+    if (!glm) return cudaErrorInvalidValue;
+    cudaFuncSetAttribute(glm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    glm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+#else
+    if (glm) return cudaErrorInvalidValue;
+    if (scen) {
+        cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        ols_power_kernel<PT, true><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+    } else {
+        cudaFuncSetAttribute(ols_power_kernel<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        ols_power_kernel<PT, false><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+    }
+#endif
+    return cudaGetLastError();
+}
+
+template <int PT>
+static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy) {
+#ifdef MCP_TU_GLM
+    return cudaErrorInvalidValue;
+#else
+    cudaError_t e = cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan));
+    if (e != cudaSuccess) return e;
+    if (scen) dgp_dump_kernel<PT, true><<<1, 32>>>(base_seed, sim_id, dx, dy);
+    else dgp_dump_kernel<PT, false><<<1, 32>>>(base_seed, sim_id, dx, dy);
+    return cudaGetLastError();
+#endif
+}
+
+template <int PT>
+static cudaError_t fit_one(const double* dx, const double* dy, int n, double* dout) {
+#ifdef MCP_TU_GLM
+    return cudaErrorInvalidValue;
+#else
+    fit_data_kernel<PT><<<1, 32>>>(dx, dy, n, dout);
+    return cudaGetLastError();
+#endif
+}
+
+#define MCP_CASE(p, expr) \
+    case p:               \
+        if (p >= MCP_P_LO && p <= MCP_P_HI) { *err = expr; return true; } \
+        return false;
+
+// The switch lists every P; only cases inside [MCP_P_LO, MCP_P_HI] instantiate templates (if constexpr-like via
+// the preprocessor below).
+template <int PT, bool IN = (PT >= MCP_P_LO && PT <= MCP_P_HI)>
+struct Sel {
+    static cudaError_t launch(bool glm, bool scen, const DevicePlan& pl, const KernelArgs& a) { return launch_one<PT>(glm, scen, pl, a); }
+    static cudaError_t dump(bool scen, const DevicePlan& pl, uint64_t s, uint64_t i, float* dx, float* dy) { return dump_one<PT>(scen, pl, s, i, dx, dy); }
+    static cudaError_t fit(const double* dx, const double* dy, int n, double* o) { return fit_one<PT>(dx, dy, n, o); }
+};
+template <int PT>
+struct Sel<PT, false> {
+    static cudaError_t launch(bool, bool, const DevicePlan&, const KernelArgs&) { return cudaErrorInvalidValue; }
+    static cudaError_t dump(bool, const DevicePlan&, uint64_t, uint64_t, float*, float*) { return cudaErrorInvalidValue; }
+    static cudaError_t fit(const double*, const double*, int, double*) { return cudaErrorInvalidValue; }
+};
+
+#define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+bool MCP_TU_FN(launch_power)(int P, bool glm, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err) {
+    if (P < MCP_P_LO || P > MCP_P_HI) return false;
+#ifdef MCP_TU_GLM
+    if (!glm) return false;
+#else
+    if (glm) return false;
+#endif
+    switch (P) {
+#define X(p) case p: *err = Sel<p>::launch(glm, scen, plan, a); return true;
+        MCP_ALL_P(X)
+#undef X
+    }
+    return false;
+}
+
+bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy,
+                     cudaError_t* err) {
+#ifdef MCP_TU_GLM
+    return false;
+#else
+    if (P < MCP_P_LO || P > MCP_P_HI) return false;
+    switch (P) {
+#define X(p) case p: *err = Sel<p>::dump(scen, plan, base_seed, sim_id, dx, dy); return true;
+        MCP_ALL_P(X)
+#undef X
+    }
+    return false;
+#endif
+}
+
+bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, double* dout, cudaError_t* err) {
+#ifdef MCP_TU_GLM
+    return false;
+#else
+    if (P < MCP_P_LO || P > MCP_P_HI) return false;
+    switch (P) {
+#define X(p) case p: *err = Sel<p>::fit(dx, dy, n, dout); return true;
+        MCP_ALL_P(X)
+#undef X
+    }
+    return false;
+#endif
+}
+
+}  // namespace mcp

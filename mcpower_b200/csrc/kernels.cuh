@@ -25,7 +25,9 @@
 
 namespace mcp {
 
-__constant__ DevicePlan c_plan;
+// One copy per translation unit (the kernels are compiled in several TUs to build in parallel); the launch
+// wrappers in kernel_tu.cu upload the plan into their own copy before every launch.
+static __constant__ DevicePlan c_plan;
 
 #ifndef MCP_BLOCK
 #define MCP_BLOCK 128
@@ -216,7 +218,7 @@ struct MemSolver {
 __device__ __forceinline__ bool gt_crit(double t, double c) { return !(t != t) && t > c; }
 
 // order[] = indices sorted by t² descending, NaN last, ties by ascending index (stable insertion sort)
-__device__ __noinline__ void sort_desc(const double* t_sq, int n, int8_t* order) {
+static __device__ __noinline__ void sort_desc(const double* t_sq, int n, int8_t* order) {
     for (int i = 0; i < n; i++) order[i] = (int8_t)i;
     for (int i = 1; i < n; i++) {
         const int v = order[i];
@@ -239,7 +241,7 @@ __device__ __noinline__ void sort_desc(const double* t_sq, int n, int8_t* order)
     }
 }
 
-__device__ __noinline__ void apply_correction(int method, const double* t_sq, int T, double crit_unc, const double* __restrict__ crit_row,
+static __device__ __noinline__ void apply_correction(int method, const double* t_sq, int T, double crit_unc, const double* __restrict__ crit_row,
                                               uint8_t* out) {
     for (int i = 0; i < T; i++) out[i] = 0;
     if (method == C_NONE) {
@@ -279,8 +281,9 @@ struct SimOut {
 };
 
 // Emit one fit: decisions, corrections, overall F, counters/bytes.  all_t = T squared statistics (NaN = untestable).
-__device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
-                                      const uint8_t* excl_flags) {
+// ov_given < 0: compute the overall F test from (sst, rss); otherwise 0/1 decided by the caller (GLM: deviance LRT).
+static __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
+                                      const uint8_t* excl_flags, int ov_given = -1) {
     const DevicePlan& pl = c_plan;
     const int T = pl.T;
     const size_t vrow = (size_t)variant * pl.n_ss + g;
@@ -302,7 +305,9 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
         }
     }
     uint8_t ov = 0;
-    if (pl.report_overall && fit.converged) {
+    if (ov_given >= 0) {
+        ov = (uint8_t)(pl.report_overall ? ov_given : 0);
+    } else if (pl.report_overall && fit.converged) {
         const double dfn = (double)(p_red - 1), dfd = fit.df_resid;
         if (dfn >= 1.0 && fit.sst > 1e-10 && fit.rss > 0.0 && !isinf(fit.rss) && fit.rss == fit.rss && !isinf(fit.sst) &&
             fit.sst == fit.sst) {
@@ -355,7 +360,7 @@ struct SimCtx {
 };
 
 // Residual for one row from CLASS_RESID slots (data_gen.rs:412-484).  slot0 = slot-0 normal already generated.
-__device__ __noinline__ float transform_residual(int dist, double df_in, float slot0, uint32_t blk, int lane, uint32_t k0, uint32_t k1) {
+static __device__ __noinline__ float transform_residual(int dist, double df_in, float slot0, uint32_t blk, int lane, uint32_t k0, uint32_t k1) {
     const double df = df_in > 3.0 ? df_in : 3.0;
     long long dfi = llround(df);
     if (dfi < 1) dfi = 1;
@@ -408,7 +413,7 @@ struct ScenDesign {
 };
 
 // Column-major LLT, left-looking (same order as the host's correlation_llt / data_gen.rs:55-75).
-__device__ __noinline__ int llt_colmajor(double* a, int n) {
+static __device__ __noinline__ int llt_colmajor(double* a, int n) {
     for (int j = 0; j < n; j++) {
         double diag = a[j * n + j];
         for (int m = 0; m < j; m++) diag -= a[m * n + j] * a[m * n + j];
@@ -428,7 +433,7 @@ __device__ __noinline__ int llt_colmajor(double* a, int n) {
 
 // Cyclic Jacobi eigen-decomposition (row-major a destroyed; eigenvalues w, eigenvectors = columns of v).
 // Stand-in for faer's self_adjoint_eigen (correlation.rs:120-127); the oracle runs the same rotations.
-__device__ __noinline__ void jacobi_eigh(double* a, int n, double* w, double* v) {
+static __device__ __noinline__ void jacobi_eigh(double* a, int n, double* w, double* v) {
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) v[i * n + j] = i == j ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 60; sweep++) {
@@ -464,7 +469,7 @@ __device__ __noinline__ void jacobi_eigh(double* a, int n, double* w, double* v)
 }
 
 template <int PT>
-__device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t base_seed, uint64_t sim_id) {
+static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t base_seed, uint64_t sim_id) {
     constexpr int KT = ScenDesign<PT>::KT;
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
@@ -963,59 +968,6 @@ __global__ void fit_data_kernel(const double* __restrict__ x /* col-major n × P
     out[3 * PT + 1] = sv.out.sst;
     out[3 * PT + 2] = sv.out.rss;
     out[3 * PT + 3] = (double)sv.out.converged;
-}
-
-// ------------------------------------------------------------------------------------------
-// Pipe micro-benchmarks: measured denominators for the issue/FP64 roofline (SURVEY.md §8d —
-// MEASURED_PEAKS.json has no FP64/FP32/INT peak).  Each thread runs `iters` rounds of 8 independent
-// dependent-chains of one instruction class; the host converts elapsed time to thread-ops/s.
-template <int KIND>
-__global__ void __launch_bounds__(256) pipe_bench_kernel(int iters, double* sink) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (KIND == 0) {  // DFMA
-        double a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-        const double m = 1.0000001, c = 1e-9;
-        for (int i = 0; i < iters; i++) {
-            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-        }
-        if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345) sink[0] = a0;
-    } else if (KIND == 1) {  // FMUL + FADD pairs (the no-FMA Horner step)
-        float a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-        const float m = 0.999f;
-        for (int i = 0; i < iters; i++) {
-            a0 = a0 * m + 1.5f; a1 = a1 * m + 1.5f; a2 = a2 * m + 1.5f; a3 = a3 * m + 1.5f;
-            a4 = a4 * m + 1.5f; a5 = a5 * m + 1.5f; a6 = a6 * m + 1.5f; a7 = a7 * m + 1.5f;
-        }
-        if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345f) sink[0] = a0;
-    } else if (KIND == 2) {  // IMAD.WIDE.U32 + LOP3 (the Philox round)
-        uint32_t c0 = t, c1 = t + 1, c2 = t + 2, c3 = t + 3, d0 = t + 4, d1 = t + 5, d2 = t + 6, d3 = t + 7;
-        for (int i = 0; i < iters; i++) {
-            const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-            const uint64_t q0 = (uint64_t)0xD2511F53u * d0, q1 = (uint64_t)0xCD9E8D57u * d2;
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (uint32_t)i, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (uint32_t)i;
-            const uint32_t m0 = (uint32_t)(q1 >> 32) ^ d1 ^ (uint32_t)i, m2 = (uint32_t)(q0 >> 32) ^ d3 ^ (uint32_t)i;
-            c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-            d1 = (uint32_t)q1; d3 = (uint32_t)q0; d0 = m0; d2 = m2;
-        }
-        if ((c0 ^ c1 ^ c2 ^ c3 ^ d0 ^ d1 ^ d2 ^ d3) == 0x12345u) sink[0] = c0;
-    } else if (KIND == 3) {  // F2F.F64.F32 widen + DADD
-        float f0 = t, f1 = t + 1, f2 = t + 2, f3 = t + 3;
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int i = 0; i < iters; i++) {
-            s0 += (double)f0; s1 += (double)f1; s2 += (double)f2; s3 += (double)f3;
-            f0 = __int_as_float(__float_as_int(f0) + 1); f1 = __int_as_float(__float_as_int(f1) + 1);
-            f2 = __int_as_float(__float_as_int(f2) + 1); f3 = __int_as_float(__float_as_int(f3) + 1);
-        }
-        if (s0 + s1 + s2 + s3 == 0.12345) sink[0] = s0;
-    } else if (KIND == 4) {  // DADD only (baseline for KIND 3)
-        double s0 = t, s1 = t + 1, s2 = t + 2, s3 = t + 3, s4 = t + 4, s5 = t + 5, s6 = t + 6, s7 = t + 7;
-        const double c = 1e-9;
-        for (int i = 0; i < iters; i++) {
-            s0 += c; s1 += c; s2 += c; s3 += c; s4 += c; s5 += c; s6 += c; s7 += c;
-        }
-        if (s0 + s1 + s2 + s3 + s4 + s5 + s6 + s7 == 0.12345) sink[0] = s0;
-    }
 }
 
 }  // namespace mcp

@@ -1,0 +1,365 @@
+// kernels_glm.cuh — batched IRLS power kernel (logit / probit / Poisson), sm_100a.
+//
+// Replaces the unclustered GLM arm of run_one_sim (crates/engine-core/src/batch.rs:1562-2135) and
+// glmm::glm_irls_fit (call site batch.rs:1969-1981).  One simulated study per thread:
+//   1. the study's max_n rows are generated once (same gen_block/row_xy as the OLS kernel, so the data
+//      plane is bit-identical to the reference fixtures) and parked in an HBM scratch plane laid out
+//      [row][column][sim-in-wave] — the 32 studies of a warp read consecutive floats, so every IRLS pass
+//      is fully coalesced;
+//   2. for every sample size (the reference refits each (sim, N) on the row prefix from the truth start,
+//      batch.rs:1563-1577) IRLS runs with per-lane convergence masks: X'WX / X'Wz / deviance live in
+//      registers (P is a template parameter), one Cholesky per iteration, no step-halving, W clamp,
+//      |beta| > 30 ⇒ not converged (batch.rs:1942-1944, 4550-4555);
+//   3. Wald z², corrections, the deviance LRT against chi2(p-1), sparse-factor exclusion and the separation
+//      fallback (drop the sparsest included factor, cold refit; batch.rs:1994-2028) are decided in-kernel.
+// IRLS constants (25 iterations, |ddev|/(|dev|+0.1) < 1e-8, weight clamp 1e-10) follow R's glm.fit: the crate's
+// own values are not in the reference tree.  Every operation mirrors the test oracle's glm_irls.
+#pragma once
+#include "kernels.cuh"
+
+namespace mcp {
+
+#define MCP_GLM_MAXIT 25
+#define MCP_GLM_TOL 1e-8
+#define MCP_GLM_WCLAMP 1e-10
+#define MCP_GLM_BETA_CAP 30.0
+
+// family 0 logit, 1 probit, 2 poisson(log)
+__device__ __forceinline__ void glm_row(int family, double eta, double y, double& w, double& z, double& dev) {
+    if (family == 0) {
+        const double e = own_exp(-fabs(eta));
+        const double inv = 1.0 / (1.0 + e);
+        const double mu = eta >= 0.0 ? inv : e * inv;
+        w = mu * (1.0 - mu);
+        if (w < MCP_GLM_WCLAMP) w = MCP_GLM_WCLAMP;
+        z = eta + (y - mu) / w;
+        dev = y > 0.5 ? -2.0 * own_log(mu) : -2.0 * own_log(1.0 - mu);
+    } else if (family == 1) {
+        const double mu = phi(eta);
+        double d = own_exp(-0.5 * eta * eta) * 0.3989422804014327;
+        if (d < 1e-300) d = 1e-300;
+        double v = mu * (1.0 - mu);
+        if (v < MCP_GLM_WCLAMP) v = MCP_GLM_WCLAMP;
+        w = d * d / v;
+        z = eta + (y - mu) / d;
+        dev = y > 0.5 ? -2.0 * own_log(mu) : -2.0 * own_log(1.0 - mu);
+    } else {
+        const double mu = own_exp(eta);
+        w = mu;
+        if (w < MCP_GLM_WCLAMP) w = MCP_GLM_WCLAMP;
+        z = eta + (y - mu) / w;
+        dev = y > 0.0 ? 2.0 * (y * own_log(y / mu) - (y - mu)) : 2.0 * mu;
+    }
+}
+
+struct GlmOut {
+    int converged, iters;
+    double deviance, deviance_null;
+};
+
+__device__ __forceinline__ double glm_null_deviance(int family, double s0, double s1, double n) {
+    const double ybar = s0 / n;
+    if (family == 2) return ybar > 0.0 ? 2.0 * (s1 - s0 * own_log(ybar)) : 0.0;
+    const double n1 = s0, n0 = n - s0;
+    double dn = 0.0;
+    if (n1 > 0.0) dn += n1 * own_log(ybar);
+    if (n0 > 0.0) dn += n0 * own_log(1.0 - ybar);
+    return -2.0 * dn;
+}
+
+// Full-model IRLS with register-resident X'WX (all indices static).  `plane` points at this thread's element of
+// row 0 / column 0; element (row, col) is plane[(row * PT + col) * stride]; columns 0..PT-2 = X[:,1..], PT-1 = y.
+template <int PT>
+__device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, size_t stride, int n, int family, bool truth_start,
+                                             RegSolver<PT>& sv, double (&beta)[PT], GlmOut& out) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    const DevicePlan& pl = c_plan;
+#pragma unroll
+    for (int j = 0; j < PT; j++) beta[j] = truth_start ? pl.beta[j] : 0.0;
+    double dev_prev = __longlong_as_double(0x7ff0000000000000LL), dev = dev_prev, s0 = 0.0, s1 = 0.0;
+    int conv = 0, it = 0;
+    bool active = true;  // per-lane convergence mask: finished lanes idle until the warp's slowest study is done
+    for (it = 0; it < MCP_GLM_MAXIT && active; it++) {
+        double A[NACC], b[PT];
+#pragma unroll
+        for (int i = 0; i < NACC; i++) A[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) b[i] = 0.0;
+        dev = 0.0;
+        for (int i = 0; i < n; i++) {
+            const float* rowp = plane + (size_t)i * PT * stride;
+            double xr[PT];
+            xr[0] = 1.0;
+#pragma unroll
+            for (int j = 1; j < PT; j++) xr[j] = (double)rowp[(size_t)(j - 1) * stride];
+            const double yi = (double)rowp[(size_t)(PT - 1) * stride];
+            double eta = 0.0;
+#pragma unroll
+            for (int j = 0; j < PT; j++) eta = fma(xr[j], beta[j], eta);
+            double w, z, di;
+            glm_row(family, eta, yi, w, z, di);
+            dev += di;
+            if (it == 0) {
+                s0 += yi;
+                if (family == 2 && yi > 1.0) s1 += yi * own_log(yi);
+            }
+#pragma unroll
+            for (int a = 0; a < PT; a++) {
+                const double wa = w * xr[a];
+#pragma unroll
+                for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, xr[c], A[tri(a, c)]);
+                b[a] = fma(wa, z, b[a]);
+            }
+        }
+        if (isinf(dev) || dev != dev) {
+            active = false;
+            break;
+        }
+        if (it > 0 && fabs(dev - dev_prev) / (fabs(dev) + 0.1) < MCP_GLM_TOL) {
+            sv.factor_and_solve(A, b, 0.0, 0.0, (uint32_t)n);  // X'WX at the converged beta → Wald covariance
+            conv = sv.out.converged;
+            active = false;
+            break;
+        }
+        dev_prev = dev;
+        sv.factor_and_solve(A, b, 0.0, 0.0, (uint32_t)n);
+        if (!sv.out.converged) {
+            active = false;
+            break;
+        }
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < PT; j++) {
+            beta[j] = sv.beta[j];
+            if (isinf(beta[j]) || beta[j] != beta[j] || fabs(beta[j]) > MCP_GLM_BETA_CAP) bad = true;
+        }
+        if (bad) {
+            active = false;
+            break;
+        }
+    }
+    out.converged = conv;
+    out.iters = it;
+    out.deviance = dev;
+    out.deviance_null = glm_null_deviance(family, s0, s1, (double)n);
+}
+
+// Reduced-model IRLS (exclusion / separation fallback / test design): runtime p on local memory.  Cold path.
+template <int PT>
+static __device__ __noinline__ void glm_irls_mem(const float* __restrict__ plane, size_t stride, int n, int family, bool truth_start,
+                                          const McpVariant& vr, MemSolver<PT>& ms, double* beta, GlmOut& out) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    const DevicePlan& pl = c_plan;
+    const int p = vr.p_red;
+    for (int j = 0; j < p; j++) beta[j] = truth_start ? pl.beta[vr.kept[j]] : 0.0;
+    double dev_prev = __longlong_as_double(0x7ff0000000000000LL), dev = dev_prev, s0 = 0.0, s1 = 0.0;
+    int conv = 0, it = 0;
+    double A[NACC], b[PT], xr[PT], btmp[PT];
+    for (it = 0; it < MCP_GLM_MAXIT; it++) {
+        for (int i = 0; i < p * (p + 1) / 2; i++) A[i] = 0.0;
+        for (int i = 0; i < p; i++) b[i] = 0.0;
+        dev = 0.0;
+        for (int i = 0; i < n; i++) {
+            const float* rowp = plane + (size_t)i * PT * stride;
+            double eta = 0.0;
+            for (int j = 0; j < p; j++) {
+                const int c = vr.kept[j];
+                xr[j] = c == 0 ? 1.0 : (double)rowp[(size_t)(c - 1) * stride];
+                eta = fma(xr[j], beta[j], eta);
+            }
+            const double yi = (double)rowp[(size_t)(PT - 1) * stride];
+            double w, z, di;
+            glm_row(family, eta, yi, w, z, di);
+            dev += di;
+            if (it == 0) {
+                s0 += yi;
+                if (family == 2 && yi > 1.0) s1 += yi * own_log(yi);
+            }
+            for (int a = 0; a < p; a++) {
+                const double wa = w * xr[a];
+                for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, xr[c], A[tri(a, c)]);
+                b[a] = fma(wa, z, b[a]);
+            }
+        }
+        if (isinf(dev) || dev != dev) break;
+        if (it > 0 && fabs(dev - dev_prev) / (fabs(dev) + 0.1) < MCP_GLM_TOL) {
+            for (int j = 0; j < p; j++) btmp[j] = beta[j];
+            ms.factor_and_solve(A, b, p, 0.0, 0.0, (uint32_t)n);
+            for (int j = 0; j < p; j++) ms.beta[j] = btmp[j];
+            conv = ms.out.converged;
+            break;
+        }
+        dev_prev = dev;
+        ms.factor_and_solve(A, b, p, 0.0, 0.0, (uint32_t)n);
+        if (!ms.out.converged) break;
+        bool bad = false;
+        for (int j = 0; j < p; j++) {
+            beta[j] = ms.beta[j];
+            if (isinf(beta[j]) || beta[j] != beta[j] || fabs(beta[j]) > MCP_GLM_BETA_CAP) bad = true;
+        }
+        if (bad) break;
+    }
+    for (int j = 0; j < p; j++) ms.beta[j] = beta[j];
+    out.converged = conv;
+    out.iters = it;
+    out.deviance = dev;
+    out.deviance_null = glm_null_deviance(family, s0, s1, (double)n);
+}
+
+// Decisions for one GLM fit: Wald z² vs the (df-free) normal thresholds, corrections, deviance LRT
+// (dev_null − dev > chi2(p_red − 1), batch.rs:2094-2126).
+static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int variant, const GlmOut& go, double* all_t, const uint8_t* excl_flags) {
+    const DevicePlan& pl = c_plan;
+    FitOut fo;
+    fo.converged = go.converged;
+    fo.df_resid = 1.0;
+    fo.sigma_sq = 1.0;
+    fo.rss = 0.0;
+    fo.sst = 0.0;
+    int ov = 0;
+    const bool finite = !(isinf(go.deviance) || go.deviance != go.deviance || isinf(go.deviance_null) || go.deviance_null != go.deviance_null);
+    if (go.converged && finite) {
+        const double lrt = go.deviance_null - go.deviance;
+        if (!(isinf(lrt) || lrt != lrt) && lrt > pl.crit_overall[(size_t)variant * pl.n_ss + g]) ov = 1;
+    }
+    emit_fit(so, g, variant, fo, pl.variants[variant].p_red, all_t, excl_flags, ov);
+}
+
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) glm_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, float* __restrict__ scratch) {
+    constexpr int SP = PT | 1;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;  // sims per wave, padded to whole blocks
+    if (sim < n_sims) {
+        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+        SimCtx cx;
+        cx.k0 = (uint32_t)key;
+        cx.k1 = (uint32_t)(key >> 32);
+        cx.seq.init(key);
+        cx.tau = 0.0;
+        cx.seq_row_base = 0u;
+        const int max_n = pl.max_n;
+        SimOut so{cnt_s, (uint64_t)sim};
+        float* plane = scratch + sim;
+        const int family = pl.outcome == O_COUNT ? 2 : (pl.link_probit ? 1 : 0);
+        // ---- 1. generate the study once, park the f32 plane in HBM
+        {
+            ScenDesign<PT> sdv;
+            const bool scen = !pl.optimistic;
+            if (scen) {
+                scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+                if (!sdv.ok) atomicExch(pl.error_flag, 2);
+            }
+            for (int b = 0; b < (max_n + 3) >> 2; b++) {
+                if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
+                else gen_block<PT, false>(b, slab, cx, nullptr);
+                for (int r = 0; r < 4; r++) {
+                    const int row = 4 * b + r;
+                    if (row >= max_n) break;
+                    double xr[PT];
+                    const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
+                    float* rowp = plane + (size_t)row * PT * stride;
+#pragma unroll
+                    for (int j = 1; j < PT; j++) rowp[(size_t)(j - 1) * stride] = slab[4 * (j - 1) + r];
+                    rowp[(size_t)(PT - 1) * stride] = (float)yd;
+                }
+            }
+        }
+        // ---- 2. one fit per sample size
+        uint32_t lvl_counts[MCP_MAX_LEVELS];
+        uint8_t excl[MCP_MAX_FACTORS];
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
+        int counted = 0;
+        for (int g = 0; g < pl.n_ss; g++) {
+            const int n = (int)pl.ss[g];
+            for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+            if (track_excl) {  // counts over rows [0, n): cumulative, so only the new rows are scanned (batch.rs:2451-2496)
+                for (int i = counted; i < n; i++) {
+                    const float* rowp = plane + (size_t)i * PT * stride;
+                    for (int f = 0; f < pl.n_factors; f++) {
+                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
+                        int lvl = 0;
+                        for (int d = 0; d < nl - 1; d++)
+                            if (rowp[(size_t)(c0 + d) * stride] == 1.0f) { lvl = d + 1; break; }
+                        lvl_counts[pl.f_off[f] + lvl]++;
+                    }
+                }
+                counted = n;
+                for (int f = 0; f < pl.n_factors; f++) {
+                    uint32_t mn = 0xffffffffu;
+                    for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
+                    excl[f] = mn < (uint32_t)pl.min_level_count;
+                }
+            }
+            GlmOut go;
+            double all_t[MCP_MAX_T];
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            for (int t = 0; t < pl.T; t++) all_t[t] = nan;
+            int variant = 0;
+            for (int attempt = 0; attempt < 2; attempt++) {
+                variant = pl.base_variant;
+                if (track_excl) {
+                    variant = 0;
+                    for (int f = 0; f < pl.n_factors; f++) variant |= (excl[f] != 0 ? 1 : 0) << f;
+                }
+                const McpVariant& vr = pl.variants[variant];
+                if (vr.p_red == PT) {
+                    RegSolver<PT> sv;
+                    double beta[PT];
+                    glm_irls_reg<PT>(plane, stride, n, family, attempt == 0, sv, beta, go);
+                    if (go.converged) {
+#pragma unroll
+                        for (int j = 0; j < PT; j++) sv.beta[j] = beta[j];
+                        sv.out.sigma_sq = 1.0;
+                        for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
+                    }
+                } else {
+                    MemSolver<PT> ms;
+                    double beta[PT];
+                    glm_irls_mem<PT>(plane, stride, n, family, attempt == 0, vr, ms, beta, go);
+                    if (go.converged) {
+                        ms.out.sigma_sq = 1.0;
+                        for (int t = 0; t < pl.n_marg; t++) {
+                            const int c = vr.remap[pl.target[t]];
+                            all_t[t] = c >= 0 ? ms.t_sq(c, -1) : nan;
+                        }
+                    }
+                }
+                if (go.converged || attempt == 1) break;
+                if (pl.min_level_count == 0) break;
+                // separation fallback: drop the included factor with the smallest min level count (batch.rs:2572-2597)
+                int best = -1;
+                uint32_t best_min = 0;
+                for (int f = 0; f < pl.n_factors; f++) {
+                    if (excl[f] == 0) {
+                        uint32_t mn = 0xffffffffu;
+                        for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
+                        if (best < 0 || mn < best_min) { best = f; best_min = mn; }
+                    }
+                }
+                if (best < 0) break;
+                excl[best] = 2;
+            }
+            emit_fit_glm(so, g, variant, go, all_t, excl);
+        }
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace mcp

@@ -1,0 +1,29 @@
+// launch.h — interface between the host API (api.cu) and the kernel translation units (kernel_tu.cu).
+// kernel_tu.cu is compiled several times with different -DMCP_TU_ID / -DMCP_P_LO / -DMCP_P_HI / -DMCP_TU_GLM so
+// the template instantiations build in parallel (see mcpower_b200/build.py for the TU table).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.h"
+
+namespace mcp {
+
+struct KernelArgs {
+    uint64_t base_seed, sim_begin;
+    uint32_t n_sims;
+    cudaStream_t stream;
+    float* scratch;          // GLM: per-wave f32 data plane [row][col][sim]
+};
+
+// Each returns false when P is outside the TU's range; otherwise *err holds the launch status.
+#define MCP_DECLARE_TU(id)                                                                                                 \
+    bool tu##id##_launch_power(int P, bool glm, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err); \
+    bool tu##id##_dump(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy, \
+                       cudaError_t* err);                                                                                  \
+    bool tu##id##_fit_data(int P, const double* dx, const double* dy, int n, double* dout, cudaError_t* err);
+
+#define MCP_TU_LIST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+MCP_TU_LIST(MCP_DECLARE_TU)
+
+}  // namespace mcp

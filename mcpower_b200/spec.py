@@ -145,3 +145,20 @@ def sweep_spec(rho: float = 0.3) -> dict:
 
 def logit_intercept(p: float) -> float:
     return math.log(p / (1.0 - p))
+
+
+def logit_spec(baseline_p: float = 0.3) -> dict:
+    """BASELINE config 4: logistic GLM y ~ treatment*x1 + x2 (treatment = Bernoulli(0.5) marginal),
+    P = 5 columns [1, treatment, x1, x2, treatment:x1], binary outcome, deviance-LRT overall test."""
+    s = base_spec(3)
+    s["var_types"] = ["binary", "normal", "normal"]
+    s["var_params"] = [0.5, 0.0, 0.0]
+    s = add_interaction(s, [1, 2], 0.3)
+    s["intercept"] = logit_intercept(baseline_p)
+    s["effect_sizes"] = [s["intercept"], 0.5, 0.3, 0.2, 0.3]
+    s["target_indices"] = [1, 2, 3, 4]
+    s["outcome_kind"] = "binary"
+    s["estimator"] = "glm"
+    s["report_overall"] = True
+    s["max_failed_fraction"] = 0.25
+    return s

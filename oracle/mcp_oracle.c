@@ -1553,81 +1553,141 @@ int orc_fit_ols(const double* xc, const double* yv, int n, int p, double* betas,
 }
 
 /* ======================================================================= */
-/* GLM IRLS (glmm glm_irls_fit; constants are NOT visible in the reference  */
-/* tree — SURVEY §8c "parity unpinned"; this restatement uses R's rule).    */
+/* GLM IRLS (glmm glm_irls_fit, call site batch.rs:1969-1981).  The crate's  */
+/* constants are NOT visible in the reference tree ("parity      */
+/* unpinned"); what IS visible is restated: truth start, no step-halving,    */
+/* one LLT per iteration, W clamp, |beta| > 30 => not converged              */
+/* (batch.rs:1942-1944,4550-4555, workspace.rs:185-192).  Stopping rule and  */
+/* iteration cap follow R's glm.fit (|ddev|/(|dev|+0.1) < 1e-8, 25 its);     */
+/* value-pinned to the 16 frozen R glm goldens at 1e-4 (tolerances.R:29-31). */
+/* The CUDA kernel mirrors this function operation for operation.            */
 /* ======================================================================= */
 
-static double glm_mu(int family, double eta) {
-    if (family == 0) { if (eta >= 0.0) return 1.0 / (1.0 + orc_exp(-eta)); double e = orc_exp(eta); return e / (1.0 + e); }
-    if (family == 1) return orc_phi(eta);
-    return orc_exp(eta);
-}
-static double glm_dev_i(int family, double y, double mu) {
-    if (family == 2) {
-        double t = y > 0.0 ? y * orc_log(y / mu) : 0.0;
-        return 2.0 * (t - (y - mu));
+#define GLM_MAXIT 25
+#define GLM_TOL 1e-8
+#define GLM_WCLAMP 1e-10
+#define GLM_BETA_CAP 30.0
+
+typedef struct {
+    int converged, iters;
+    double deviance, deviance_null;
+} GlmOut;
+
+/* family 0 logit, 1 probit, 2 poisson(log) */
+static inline void glm_row(int family, double eta, double y, double* w_o, double* z_o, double* dev_o) {
+    double mu, w, z, dev;
+    if (family == 0) {
+        double e = orc_exp(-fabs(eta));
+        double inv = 1.0 / (1.0 + e);
+        mu = eta >= 0.0 ? inv : e * inv;
+        w = mu * (1.0 - mu);
+        if (w < GLM_WCLAMP) w = GLM_WCLAMP;
+        z = eta + (y - mu) / w;
+        dev = y > 0.5 ? -2.0 * orc_log(mu) : -2.0 * orc_log(1.0 - mu);
+    } else if (family == 1) {
+        mu = orc_phi(eta);
+        double d = orc_exp(-0.5 * eta * eta) * 0.3989422804014327;
+        if (d < 1e-300) d = 1e-300;
+        double v = mu * (1.0 - mu);
+        if (v < GLM_WCLAMP) v = GLM_WCLAMP;
+        w = d * d / v;
+        z = eta + (y - mu) / d;
+        dev = y > 0.5 ? -2.0 * orc_log(mu) : -2.0 * orc_log(1.0 - mu);
+    } else {
+        mu = orc_exp(eta);
+        w = mu;
+        if (w < GLM_WCLAMP) w = GLM_WCLAMP;
+        z = eta + (y - mu) / w;
+        dev = y > 0.0 ? 2.0 * (y * orc_log(y / mu) - (y - mu)) : 2.0 * mu;
     }
-    double a = y > 0.0 ? y * orc_log(y / mu) : 0.0;
-    double b = y < 1.0 ? (1.0 - y) * orc_log((1.0 - y) / (1.0 - mu)) : 0.0;
-    return 2.0 * (a + b);
+    *w_o = w; *z_o = z; *dev_o = dev;
+}
+
+/* x: f32 column-major with leading dimension ld; kept = NULL (identity) or p column indices. */
+static void glm_irls(const float* x, const float* y, int ld, int n, int p, const int* kept, int family,
+                     const double* beta_start, double* A, double* b, double* L, double* inv_d, double* wv, double* beta,
+                     GlmOut* out) {
+    size_t nt = (size_t)p * (p + 1) / 2;
+    double beta_tmp[64], xr[64];
+    for (int j = 0; j < p; j++) beta[j] = beta_start ? beta_start[j] : 0.0;
+    double dev_prev = INFINITY, dev = INFINITY, s0 = 0.0, s1 = 0.0;
+    int conv = 0, it;
+    OlsFit f;
+    for (it = 0; it < GLM_MAXIT; it++) {
+        memset(A, 0, sizeof(double) * nt);
+        memset(b, 0, sizeof(double) * (size_t)p);
+        dev = 0.0;
+        for (int i = 0; i < n; i++) {
+            double eta = 0.0;
+            for (int j = 0; j < p; j++) {
+                xr[j] = (double)x[(size_t)(kept ? kept[j] : j) * ld + i];
+                eta = fma(xr[j], beta[j], eta);
+            }
+            double yi = (double)y[i], w, z, di;
+            glm_row(family, eta, yi, &w, &z, &di);
+            dev += di;
+            if (it == 0) {
+                s0 += yi;
+                if (family == 2 && yi > 1.0) s1 += yi * orc_log(yi);
+            }
+            size_t t = 0;
+            for (int a = 0; a < p; a++) {
+                double wa = w * xr[a];
+                for (int c = 0; c <= a; c++) { A[t] = fma(wa, xr[c], A[t]); t++; }
+                b[a] = fma(wa, z, b[a]);
+            }
+        }
+        if (!isfinite(dev)) break;
+        if (it > 0 && fabs(dev - dev_prev) / (fabs(dev) + 0.1) < GLM_TOL) {
+            /* converged at the current beta: factor X'WX(beta) for the Wald covariance, keep beta */
+            ols_solve(A, b, 0.0, 0.0, (uint32_t)n, p, L, inv_d, wv, beta_tmp, &f);
+            conv = f.converged;
+            break;
+        }
+        dev_prev = dev;
+        ols_solve(A, b, 0.0, 0.0, (uint32_t)n, p, L, inv_d, wv, beta_tmp, &f);
+        if (!f.converged) break;
+        int bad = 0;
+        for (int j = 0; j < p; j++) {
+            beta[j] = beta_tmp[j];
+            if (!isfinite(beta[j]) || fabs(beta[j]) > GLM_BETA_CAP) bad = 1;
+        }
+        if (bad) break;
+    }
+    double dn, nn = (double)n, ybar = s0 / nn;
+    if (family == 2) {
+        dn = ybar > 0.0 ? 2.0 * (s1 - s0 * orc_log(ybar)) : 0.0;
+    } else {
+        double n1 = s0, n0 = nn - s0;
+        dn = 0.0;
+        if (n1 > 0.0) dn += n1 * orc_log(ybar);
+        if (n0 > 0.0) dn += n0 * orc_log(1.0 - ybar);
+        dn = -2.0 * dn;
+    }
+    out->converged = conv;
+    out->iters = it;
+    out->deviance = dev;
+    out->deviance_null = dn;
 }
 
 int orc_fit_glm(const double* xc, const double* yv, int n, int p, int family, const double* beta_start, double* betas,
                 double* se, double* deviance, double* deviance_null, int* converged, int* iters) {
     if (p > 64) return fail(ORC_ERR_INVALID_SPEC, "p > 64");
+    float* x = (float*)malloc(sizeof(float) * (size_t)n * p);
+    float* y = (float*)malloc(sizeof(float) * (size_t)n);
+    for (size_t i = 0; i < (size_t)n * p; i++) x[i] = (float)xc[i]; /* introspect.rs:195-203 */
+    for (int i = 0; i < n; i++) y[i] = (float)yv[i];
     size_t nt = (size_t)p * (p + 1) / 2;
-    double* A = (double*)calloc(nt * 2 + (size_t)p * 6, sizeof(double));
+    double* A = (double*)calloc(nt * 2 + (size_t)p * 5, sizeof(double));
     double *L = A + nt, *b = L + nt, *inv_d = b + p, *wv = inv_d + p, *u = wv + p, *beta = u + p;
-    for (int j = 0; j < p; j++) beta[j] = beta_start ? beta_start[j] : 0.0;
-    double dev_prev = INFINITY, dev = INFINITY;
-    int conv = 0, it = 0;
-    const double WCLAMP = 1e-10;
-    for (it = 0; it < 25; it++) {
-        memset(A, 0, sizeof(double) * nt);
-        memset(b, 0, sizeof(double) * (size_t)p);
-        double xr[64];
-        dev = 0.0;
-        for (int i = 0; i < n; i++) {
-            double eta = 0.0;
-            for (int j = 0; j < p; j++) { xr[j] = (double)(float)xc[(size_t)j * n + i]; eta = fma(xr[j], beta[j], eta); }
-            double y = (double)(float)yv[i];
-            double mu = glm_mu(family, eta), wgt, zed;
-            if (family == 0) { wgt = mu * (1.0 - mu); if (wgt < WCLAMP) wgt = WCLAMP; zed = eta + (y - mu) / wgt; }
-            else if (family == 1) {
-                double d = exp(-0.5 * eta * eta) / sqrt(2.0 * M_PI);
-                double v = mu * (1.0 - mu); if (v < WCLAMP) v = WCLAMP;
-                if (d < 1e-300) d = 1e-300;
-                wgt = d * d / v; zed = eta + (y - mu) / d;
-            } else { wgt = mu; if (wgt < WCLAMP) wgt = WCLAMP; zed = eta + (y - mu) / wgt; }
-            dev += glm_dev_i(family, y, mu);
-            size_t t = 0;
-            for (int a = 0; a < p; a++) {
-                double wa = wgt * xr[a];
-                for (int c = 0; c <= a; c++) { A[t] = fma(wa, xr[c], A[t]); t++; }
-                b[a] = fma(wa, zed, b[a]);
-            }
-        }
-        if (it > 0 && fabs(dev - dev_prev) / (fabs(dev) + 0.1) < 1e-8) { conv = 1; break; }
-        dev_prev = dev;
-        OlsFit f;
-        ols_solve(A, b, 0.0, 0.0, (uint32_t)n, p, L, inv_d, wv, beta, &f);
-        if (!f.converged) break;
-        int bad = 0;
-        for (int j = 0; j < p; j++) if (!isfinite(beta[j]) || fabs(beta[j]) > 30.0) bad = 1;
-        if (bad) break;
-    }
-    /* covariance at the converged weights: (X'WX)^-1 from the last factorisation */
+    GlmOut o;
+    glm_irls(x, y, n, n, p, NULL, family, beta_start, A, b, L, inv_d, wv, beta, &o);
     for (int t = 0; t < p; t++) {
         betas[t] = beta[t];
         se[t] = sqrt(linv_norm_sq(L, inv_d, p, t, -1, u));
     }
-    double ybar = 0.0;
-    for (int i = 0; i < n; i++) ybar += (double)(float)yv[i];
-    ybar /= (double)n;
-    double dn = 0.0;
-    for (int i = 0; i < n; i++) dn += glm_dev_i(family, (double)(float)yv[i], ybar);
-    *deviance = dev; *deviance_null = dn; *converged = conv; *iters = it;
-    free(A);
+    *deviance = o.deviance; *deviance_null = o.deviance_null; *converged = o.converged; *iters = o.iters;
+    free(A); free(x); free(y);
     return ORC_OK;
 }
 
@@ -1777,12 +1837,109 @@ static int run_one_sim(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t 
     return ORC_OK;
 }
 
+/* batch.rs:2572-2597 */
+static int included_factor_with_smallest_min_count(const OrcSpec* s, const uint32_t* counts, const uint8_t* flags) {
+    int best = -1, off = 0;
+    uint32_t best_min = 0;
+    for (int f = 0; f < s->n_factors; f++) {
+        int l = s->factor_n_levels[f];
+        if (flags[f] == 0) {
+            uint32_t mn = 0xffffffffu;
+            for (int g = 0; g < l; g++) if (counts[off + g] < mn) mn = counts[off + g];
+            if (best < 0 || mn < best_min) { best = f; best_min = mn; }
+        }
+        off += l;
+    }
+    return best;
+}
+
+/* GLM arm (batch.rs:1562-2135, unclustered): refit per (sim, N) on the row prefix from the truth start;
+ * sparse-factor exclusion recounted from row 0; separation fallback = drop the sparsest included factor, cold start. */
+static int run_one_sim_glm(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t sim_id, uint64_t base_seed, Ws* w,
+                           const double* t_unc, const double* corr, const double* overall_crit, uint8_t* unc, uint8_t* cor,
+                           uint8_t* conv, uint8_t* overall, uint8_t* fx, double* cap) {
+    int rc = gen_sim(s, base_seed, sim_id, w);
+    if (rc) return rc;
+    const int P = w->P, T = s->n_marginal_targets, ld = w->max_n;
+    const int family = s->outcome_kind == ORC_OUT_COUNT ? 2 : (s->link_probit ? 1 : 0);
+    int nprops = 0;
+    for (int f = 0; f < s->n_factors; f++) nprops += s->factor_n_levels[f];
+    int test_reduces = s->n_fit_columns > 0 && s->n_fit_columns < P;
+    double A[64 * 65 / 2], L[64 * 65 / 2], b[64], inv_d[64], wv[64], beta[64], u[64], all_t[256], bstart[64];
+    int kept[64], remap[64];
+    for (int g = 0; g < n_ss; g++) {
+        int n = (int)ss[g];
+        memset(w->prefix_counts, 0, sizeof(uint32_t) * (size_t)(nprops > 0 ? nprops : 1));
+        memset(w->excl_flags, 0, (size_t)(s->n_factors > 0 ? s->n_factors : 1));
+        if (s->n_factors > 0 && s->factor_min_level_count > 0)
+            update_factor_exclusions(s, w->x, ld, 0, n, w->prefix_counts, w->excl_flags);
+        GlmOut go;
+        int p_red = P, reduced = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            int any_excl = 0;
+            for (int f = 0; f < s->n_factors; f++) any_excl |= w->excl_flags[f] != 0;
+            reduced = any_excl || test_reduces;
+            const double* start = NULL;
+            if (!reduced) {
+                p_red = P;
+                if (attempt == 0) start = s->effect_sizes;
+                glm_irls(w->x, w->y, ld, n, P, NULL, family, start, A, b, L, inv_d, wv, beta, &go);
+            } else {
+                p_red = build_exclusion_remap(s, w->excl_flags, kept, remap);
+                for (int j = 0; j < p_red; j++) bstart[j] = s->effect_sizes[kept[j]];
+                if (attempt == 0) start = bstart;
+                glm_irls(w->x, w->y, ld, n, p_red, kept, family, start, A, b, L, inv_d, wv, beta, &go);
+            }
+            if (go.converged || attempt == 1) break;
+            if (s->factor_min_level_count == 0) break;
+            int f = included_factor_with_smallest_min_count(s, w->prefix_counts, w->excl_flags);
+            if (f < 0) break;
+            w->excl_flags[f] = 2;
+        }
+        conv[g] = (uint8_t)go.converged;
+        uint8_t* unc_row = unc + (size_t)g * T;
+        uint8_t* cor_row = cor + (size_t)g * T;
+        memset(unc_row, 0, (size_t)T);
+        memset(cor_row, 0, (size_t)T);
+        for (int t = 0; t < T; t++) all_t[t] = NAN;
+        if (go.converged) {
+            for (int t = 0; t < T; t++) {
+                int c = reduced ? remap[s->target_indices[t]] : s->target_indices[t];
+                if (c >= 0) all_t[t] = target_t_sq(L, inv_d, beta, 1.0, p_red, c, -1, u);
+            }
+            for (int t = 0; t < T; t++) unc_row[t] = !isnan(all_t[t]) && all_t[t] > t_unc[g];
+            orc_apply_correction(s->correction_method, all_t, T, t_unc[g], corr + (size_t)g * T, cor_row);
+        }
+        if (cap) memcpy(cap + (size_t)g * T, all_t, sizeof(double) * (size_t)T);
+        if (overall) {
+            double crit_ov = overall_crit[g];
+            if (reduced) {
+                double r_unc;
+                rc = orc_build_crit_table(s, &ss[g], 1, p_red, &r_unc, NULL, NULL, &crit_ov);
+                if (rc) return rc;
+            }
+            uint8_t sig = 0;
+            if (go.converged && isfinite(go.deviance) && isfinite(go.deviance_null)) {
+                double lrt = go.deviance_null - go.deviance;
+                if (isfinite(lrt) && lrt > crit_ov) sig = 1;
+            }
+            overall[g] = sig;
+        }
+        if (fx && s->n_factors > 0) memcpy(fx + (size_t)g * s->n_factors, w->excl_flags, (size_t)s->n_factors);
+    }
+    return ORC_OK;
+}
+
 int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sims, uint64_t sim_begin, uint64_t base_seed,
                   int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged, uint8_t* overall,
                   uint8_t* factor_excluded, double* t_sq_capture) {
     int rc = validate_spec(s, ss, n_ss);
     if (rc) return rc;
-    if (s->estimator != ORC_EST_OLS) return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: only estimator=ols is restated");
+    if (s->estimator == ORC_EST_MLE) return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: estimator=mle is not restated");
+    if (s->estimator == ORC_EST_GLM && (s->has_cluster || s->n_contrasts > 0))
+        return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: clustered GLM (GLMM) / GLM contrasts are not restated");
+    if (s->estimator == ORC_EST_GLM && s->outcome_kind == ORC_OUT_CONTINUOUS)
+        return fail(ORC_ERR_INVALID_SPEC, "estimator Glm requires a binary or count outcome");
     const int P = 1 + s->n_non_factor + s->n_factor_dummies + s->n_interactions;
     if (P > 64) return fail(ORC_ERR_INVALID_SPEC, "P > 64");
     const int T = s->n_marginal_targets + s->n_contrasts;
@@ -1805,7 +1962,7 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
 #endif
         for (int64_t i = 0; i < (int64_t)n_sims; i++) {
             if (err) continue;
-            int r = run_one_sim(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
+            int r = (s->estimator == ORC_EST_GLM ? run_one_sim_glm : run_one_sim)(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
                                 uncorrected + (size_t)i * n_ss * T, corrected + (size_t)i * n_ss * T,
                                 converged + (size_t)i * n_ss, overall ? overall + (size_t)i * n_ss : NULL,
                                 factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,

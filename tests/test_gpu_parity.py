@@ -254,6 +254,71 @@ def test_five_sigma_alpha_joint_power_doomer():
     assert joint[1] >= joint[0]
 
 
+# ------------------------------------------------------------------ GLM IRLS (BASELINE config 4)
+def test_logit_power_curve_matches_oracle():
+    s = S.logit_spec()
+    grid = [50, 100, 200, 500, 1000, 2000]
+    got = M.run_batch(s, grid, 512, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 512, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    p = got.power()[:, 0]
+    assert p[-1] > 0.95 and np.all(np.diff(p) > -0.05)
+
+
+@pytest.mark.parametrize("family", ["probit", "poisson"])
+def test_probit_and_poisson_match_oracle(family):
+    s = S.logit_spec()
+    if family == "probit":
+        s["link"] = "probit"
+        s["effect_sizes"][0] = -0.5
+    else:
+        s["outcome_kind"] = "count"
+        s["effect_sizes"] = [0.7, 0.3, 0.2, 0.1, 0.1]
+    s["correction_method"] = "holm"
+    got = M.run_batch(s, [60, 150, 400], 384, SEED + 3, mode=ALL)
+    want = orc.run_batch(s, [60, 150, 400], 384, SEED + 3, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_glm_factor_exclusion_and_separation_fallback_match_oracle():
+    """Rare outcome + sparse 4-level factor at small N: sparse-level exclusion (code 1), non-convergence from
+    quasi-separation and the fallback refit without the sparsest factor (code 2), reduced-df LRT."""
+    s = S.add_factor(S.base_spec(1), [0.55, 0.25, 0.12, 0.08], [0.8, 2.5, -2.5])
+    s["effect_sizes"][0] = S.logit_intercept(0.12)
+    s["effect_sizes"][1] = 0.6
+    s["target_indices"] = [1, 2, 3, 4]
+    s["outcome_kind"], s["estimator"] = "binary", "glm"
+    s["report_overall"] = True
+    s["factor_min_level_count"] = 5
+    s["factor_sampled"] = [True]
+    s["correction_method"] = "benjamini_hochberg"
+    grid = [40, 70, 120, 300]
+    got = M.run_batch(s, grid, 768, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 768, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    codes = set(np.unique(got.factor_excluded).tolist())
+    assert {0, 1}.issubset(codes)          # sparse exclusion exercised
+    assert got.converged.mean() < 1.0 or 2 in codes  # fallback / non-convergence exercised
+
+
+def test_glm_fit_columns_and_scenario_match_oracle():
+    s = S.logit_spec()
+    s["fit_columns"] = [0, 1, 2]
+    s["target_indices"] = [1, 2]
+    s["scenario"] = dict(S.scenario("realistic"))
+    got = M.run_batch(s, [120, 360], 256, SEED, mode=ALL)
+    want = orc.run_batch(s, [120, 360], 256, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_glm_wave_split_is_invariant():
+    s = S.logit_spec()
+    a = M.run_batch(s, [100, 300], 700, SEED, mode=ALL)
+    b = M.run_batch(s, [100, 300], 700, SEED, mode=ALL, wave_sims=256)
+    assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
+    assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 3
+
+
 # ------------------------------------------------------------------ determinism contract (batch.rs:2715-2786, SURVEY §8b)
 def test_results_independent_of_wave_size_and_shard_offset():
     s = S.sweep_spec()
@@ -285,10 +350,12 @@ def test_errors_match_reference_classes():
     bad["correlation"] = [1.0, 1.2, 1.2, 1.0]
     with pytest.raises(M.CorrelationNotPSD):
         M.run_batch(bad, [50], 10, SEED)
-    glm = S.headline_spec()
-    glm["estimator"], glm["outcome_kind"] = "glm", "binary"
+    mle = S.headline_spec()
+    mle["estimator"] = "mle"
+    mle["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": 10}}, "tau_squared": 0.25, "slopes": [],
+                      "extra_groupings": []}
     with pytest.raises(M.Unsupported):
-        M.run_batch(glm, [50], 10, SEED)
+        M.run_batch(mle, [50], 10, SEED)
     r = M.run_batch(s, [50], 0, SEED, mode=ALL)  # n_sims == 0 → empty-shaped result (batch.rs:390-421)
     assert r.uncorrected.shape == (0, 1, 2) and r.counters.sum() == 0
 
