@@ -49,18 +49,21 @@ typedef struct McpOptions {
 /* ProgressSink (spec.rs:38-52): report(current, total) ~50×/run; return 0 to request cancellation. */
 typedef int (*McpProgressFn)(uint64_t current, uint64_t total, void* user);
 
-/* Counter row layout per sample-size index (width = 4T + 4 + F):
+/* Counter row layout per sample-size index (width = 4T + 6 + F):
  *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
  *   [2T+2,3T+3) histogram of #uncorrected-significant targets per sim
  *   [3T+3,4T+4) histogram of #corrected-significant targets per sim
- *   [4T+4,4T+4+F) sims with factor f sparse-excluded */
+ *   [4T+4,4T+4+F) sims with factor f excluded (sparse level or GLM separation fallback)
+ *   4T+4+F joint Wald successes (MLE arm)   4T+5+F fits with a variance component on the boundary (MLE arm) */
 typedef struct McpBatchResult {
     uint32_t n_sims, n_sample_sizes, n_targets, n_factors;
     uint8_t* uncorrected;     /* [n_sims][n_ss][T]  or NULL */
     uint8_t* corrected;       /* [n_sims][n_ss][T]  or NULL */
     uint8_t* converged;       /* [n_sims][n_ss]     or NULL */
     uint8_t* overall;         /* [n_sims][n_ss]     or NULL (spec.report_overall) */
-    uint8_t* factor_excluded; /* [n_sims][n_ss][F]  or NULL */
+    uint8_t* factor_excluded; /* [n_sims][n_ss][F]  or NULL; 0 included, 1 sparse-excluded, 2 separation fallback */
+    uint8_t* joint;           /* [n_sims][n_ss]     or NULL (MLE arm: joint_unc == joint_cor, spec.rs:574-582) */
+    uint8_t* boundary_hit;    /* [n_sims][n_ss]     or NULL (MLE arm: 0 none, 1 tau-hat = 0, 2 upper bound) */
     double* t_sq;             /* [n_sims][n_ss][T]  or NULL (CAPTURE) */
     uint32_t counter_width;
     uint32_t gpu_launches;    /* kernels launched for this call */

@@ -17,13 +17,13 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-OBJ = HERE / "build"
+OBJ = Path(os.environ.get("MCPOWER_B200_OBJ_DIR", "/tmp/mcpower_b200_build"))  # objects stay out of the repo snapshot
 SO = HERE / "libmcpower_b200.so"
-DEPS = ["api.cu", "kernel_tu.cu", "kernels.cuh", "kernels_glm.cuh", "device_math.cuh", "pipe_bench.cuh", "launch.h",
+DEPS = ["api.cu", "kernel_tu.cu", "kernels.cuh", "kernels_glm.cuh", "kernels_lmm.cuh", "device_math.cuh", "pipe_bench.cuh", "launch.h",
         "plan.h", "spec.hpp", "critvals.hpp", "json.hpp", "../../include/mcpower_b200.h"]
 # (tu id, P_lo, P_hi, glm) — must match MCP_TU_LIST in csrc/launch.h
 TUS = [(0, 1, 6, False), (1, 7, 9, False), (2, 10, 11, False), (3, 12, 13, False), (4, 14, 15, False), (5, 16, 16, False),
-       (6, 1, 8, True), (7, 9, 12, True), (8, 13, 16, True)]
+       (6, 1, 8, "GLM"), (7, 9, 12, "GLM"), (8, 13, 16, "GLM"), (9, 1, 9, "LMM"), (10, 10, 16, "LMM")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
 # the image exports CC=/opt/gcc/bin/gcc (no libgomp spec); nvcc must use the system host compiler (-ccbin)
@@ -56,11 +56,11 @@ def _run(cmd, verbose):
 def build(force: bool = False, verbose: bool = False, extra=(), only_tus=None) -> Path:
     if not force and not needs_build():
         return SO
-    OBJ.mkdir(exist_ok=True)
+    OBJ.mkdir(parents=True, exist_ok=True)
     cc = nvcc()
     jobs = [([cc, *NVCC_FLAGS, *extra, "-c", "-o", str(OBJ / "api.o"), str(CSRC / "api.cu")], OBJ / "api.o")]
-    for tid, lo, hi, glm in TUS:
-        defs = [f"-DMCP_TU_ID={tid}", f"-DMCP_P_LO={lo}", f"-DMCP_P_HI={hi}"] + (["-DMCP_TU_GLM"] if glm else [])
+    for tid, lo, hi, kind in TUS:
+        defs = [f"-DMCP_TU_ID={tid}", f"-DMCP_P_LO={lo}", f"-DMCP_P_HI={hi}"] + ([f"-DMCP_TU_{kind}"] if kind else [])
         obj = OBJ / f"tu{tid}.o"
         jobs.append(([cc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", str(obj), str(CSRC / "kernel_tu.cu")], obj))
     logs = []

@@ -241,7 +241,10 @@ static std::vector<uint8_t> exact_walk_levels(const double* probs, int nl, int m
 }
 
 static void check_supported(const Spec& s, bool generation_only = false) {
-    if (!generation_only && s.estimator == E_MLE) unsupported("estimator mle (mixed models; DESIGN.md §7)");
+    if (!generation_only && s.estimator == E_MLE) {
+        if (s.outcome != O_CONTINUOUS) unsupported("non-Gaussian mixed models (GLMM)");
+        if (!s.contrast_pairs.empty()) unsupported("contrast_pairs with estimator mle (the reference's MLE arm has no contrasts)");
+    }
     if (!generation_only && s.estimator == E_GLM) {
         if (s.has_cluster) unsupported("clustered GLM (GLMM)");
         if (!s.contrast_pairs.empty()) unsupported("contrast_pairs with estimator glm (the reference's GLM arm has no contrasts, batch.rs:2060-2062)");
@@ -441,6 +444,18 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     }
     const double nan = crit::kNaN;
     std::vector<double> c_unc((size_t)nv * n_ss, nan), c_corr((size_t)nv * n_ss * std::max(T, 1), nan), c_ov((size_t)nv * n_ss, nan);
+    std::vector<double> c_joint((size_t)nv * n_ss, nan);
+    if (s.estimator == E_MLE) {
+        // joint Wald chi-square threshold: chi2(1-alpha, #testable targets) (critvals.rs:962-975, batch.rs:1455-1468)
+        for (int m = 0; m < nv; m++) {
+            int k_red = 0;
+            for (int ti : s.target_indices) k_red += variants[m].remap[ti] >= 0;
+            const bool reduced = variants[m].p_red != P;
+            const double jc = !reduced ? (T > 0 ? crit::chi2_ppf(1.0 - s.alpha, (double)T) : nan)
+                                       : (k_red == 0 ? crit::kInf : crit::chi2_ppf(1.0 - s.alpha, (double)k_red));
+            for (uint32_t g = 0; g < n_ss; g++) c_joint[(size_t)m * n_ss + g] = jc;
+        }
+    }
     // the full-model table is always validated first, like build_crit_tables at batch entry (batch.rs:349-350)
     for (uint32_t g = 0; thresholds && g < n_ss; g++) {
         double dummy;
@@ -474,6 +489,7 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.crit_unc = lw.bufs.upload(c_unc);
     pl.crit_corr = lw.bufs.upload(c_corr);
     pl.crit_overall = lw.bufs.upload(c_ov);
+    pl.crit_joint = lw.bufs.upload(c_joint);
     pl.levels = any_exact ? lw.bufs.upload(levels_flat) : nullptr;
     bool need_t3 = false;
     for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
@@ -484,10 +500,10 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
 }
 
 // ---- kernel dispatch: ask each kernel translation unit in turn (launch.h) -------------------------
-static void dispatch_power(const Lowered& lw, bool glm, const KernelArgs& a) {
+static void dispatch_power(const Lowered& lw, int kind, const KernelArgs& a) {
     cudaError_t err = cudaSuccess;
     bool handled = false;
-#define X(id) if (!handled) handled = tu##id##_launch_power(lw.P, glm, !lw.plan.optimistic, lw.plan, a, &err);
+#define X(id) if (!handled) handled = tu##id##_launch_power(lw.P, kind, !lw.plan.optimistic, lw.plan, a, &err);
     MCP_TU_LIST(X)
 #undef X
     if (!handled) unsupported("n_predictors = " + std::to_string(lw.P));
@@ -538,6 +554,8 @@ void mcp_free_result(McpBatchResult* r) {
     std::free(r->converged);
     std::free(r->overall);
     std::free(r->factor_excluded);
+    std::free(r->joint);
+    std::free(r->boundary_hit);
     std::free(r->t_sq);
     std::free(r->counters);
     std::free(r);
@@ -574,7 +592,12 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             if (F > 0) pl.out_fx = lw.bufs.alloc<uint8_t>(cells * F);
         }
         if (capture) pl.out_tsq = lw.bufs.alloc<double>(cells * T);
-        const bool glm = s.estimator == E_GLM;
+        const bool glm = s.estimator == E_GLM, mle = s.estimator == E_MLE;
+        const int kind = glm ? KIND_GLM : (mle ? KIND_LMM : KIND_OLS);
+        if (mle && bytes) {
+            pl.out_joint = lw.bufs.alloc<uint8_t>(cells);
+            pl.out_bh = lw.bufs.alloc<uint8_t>(cells);
+        }
 
         McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
         r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
@@ -598,6 +621,17 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
             glm_scratch = lw.bufs.alloc<float>((size_t)wave * pl.max_n * lw.P);
         }
+        double* lmm_scratch = nullptr;
+        if (mle) {
+            // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
+            const int cs = std::max(s.sizing_value, 1);
+            const size_t nc_cap = s.sizing_fixed_size ? (size_t)(pl.max_n + cs - 1) / cs : (size_t)cs;
+            const size_t per_sim = nc_cap * (lw.P + 1) * sizeof(double);
+            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
+            wave = std::min(wave, cap);
+            wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
+            lmm_scratch = lw.bufs.alloc<double>((size_t)wave * nc_cap * (lw.P + 1));
+        }
         CUDA_CHECK(cudaEventRecord(e0, st));
         bool cancelled = false;
         for (uint64_t done = 0; done < n_sims;) {
@@ -611,6 +645,8 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                     shifted.out_conv = pl.out_conv + done * n_ss;
                     if (pl.out_overall) shifted.out_overall = pl.out_overall + done * n_ss;
                     if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
+                    if (pl.out_joint) shifted.out_joint = pl.out_joint + done * n_ss;
+                    if (pl.out_bh) shifted.out_bh = pl.out_bh + done * n_ss;
                 }
                 if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
             }
@@ -618,8 +654,8 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                 Lowered& lwr = lw;
                 const DevicePlan saved = lwr.plan;
                 lwr.plan = shifted;
-                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch};
-                dispatch_power(lwr, glm, ka);
+                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch, lmm_scratch};
+                dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }
             r->gpu_launches++;
@@ -658,6 +694,8 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             fetch(r->converged, pl.out_conv, cells);
             if (pl.out_overall) fetch(r->overall, pl.out_overall, cells);
             if (pl.out_fx) fetch(r->factor_excluded, pl.out_fx, cells * F);
+            if (pl.out_joint) fetch(r->joint, pl.out_joint, cells);
+            if (pl.out_bh) fetch(r->boundary_hit, pl.out_bh, cells);
         }
         if (capture) fetch(r->t_sq, pl.out_tsq, cells * T);
         guard.ok = true;

@@ -4,6 +4,9 @@
 #ifdef MCP_TU_GLM
 #include "kernels_glm.cuh"
 #endif
+#ifdef MCP_TU_LMM
+#include "kernels_lmm.cuh"
+#endif
 #include "launch.h"
 
 #ifndef MCP_TU_ID
@@ -22,18 +25,28 @@ static size_t power_smem(const DevicePlan& pl, int P) {
     return smem;
 }
 
+#if defined(MCP_TU_GLM)
+#define MCP_TU_KIND KIND_GLM
+#elif defined(MCP_TU_LMM)
+#define MCP_TU_KIND KIND_LMM
+#else
+#define MCP_TU_KIND KIND_OLS
+#endif
+
 template <int PT>
-static cudaError_t launch_one(bool glm, bool scen, const DevicePlan& pl, const KernelArgs& a) {
+static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, a.stream);
     if (e != cudaSuccess) return e;
     const size_t smem = power_smem(pl, PT);
     const uint32_t blocks = (a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
-#ifdef MCP_TU_GLM
-    if (!glm) return cudaErrorInvalidValue;
+    if (kind != MCP_TU_KIND) return cudaErrorInvalidValue;
+#if defined(MCP_TU_GLM)
     cudaFuncSetAttribute(glm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     glm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+#elif defined(MCP_TU_LMM)
+    cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
 #else
-    if (glm) return cudaErrorInvalidValue;
     if (scen) {
         cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         ols_power_kernel<PT, true><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
@@ -47,7 +60,7 @@ static cudaError_t launch_one(bool glm, bool scen, const DevicePlan& pl, const K
 
 template <int PT>
 static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy) {
-#ifdef MCP_TU_GLM
+#if MCP_TU_KIND != KIND_OLS
     return cudaErrorInvalidValue;
 #else
     cudaError_t e = cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan));
@@ -60,7 +73,7 @@ static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed,
 
 template <int PT>
 static cudaError_t fit_one(const double* dx, const double* dy, int n, double* dout) {
-#ifdef MCP_TU_GLM
+#if MCP_TU_KIND != KIND_OLS
     return cudaErrorInvalidValue;
 #else
     fit_data_kernel<PT><<<1, 32>>>(dx, dy, n, dout);
@@ -77,28 +90,24 @@ static cudaError_t fit_one(const double* dx, const double* dy, int n, double* do
 // the preprocessor below).
 template <int PT, bool IN = (PT >= MCP_P_LO && PT <= MCP_P_HI)>
 struct Sel {
-    static cudaError_t launch(bool glm, bool scen, const DevicePlan& pl, const KernelArgs& a) { return launch_one<PT>(glm, scen, pl, a); }
+    static cudaError_t launch(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) { return launch_one<PT>(kind, scen, pl, a); }
     static cudaError_t dump(bool scen, const DevicePlan& pl, uint64_t s, uint64_t i, float* dx, float* dy) { return dump_one<PT>(scen, pl, s, i, dx, dy); }
     static cudaError_t fit(const double* dx, const double* dy, int n, double* o) { return fit_one<PT>(dx, dy, n, o); }
 };
 template <int PT>
 struct Sel<PT, false> {
-    static cudaError_t launch(bool, bool, const DevicePlan&, const KernelArgs&) { return cudaErrorInvalidValue; }
+    static cudaError_t launch(int, bool, const DevicePlan&, const KernelArgs&) { return cudaErrorInvalidValue; }
     static cudaError_t dump(bool, const DevicePlan&, uint64_t, uint64_t, float*, float*) { return cudaErrorInvalidValue; }
     static cudaError_t fit(const double*, const double*, int, double*) { return cudaErrorInvalidValue; }
 };
 
 #define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
-bool MCP_TU_FN(launch_power)(int P, bool glm, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err) {
+bool MCP_TU_FN(launch_power)(int P, int kind, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err) {
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
-#ifdef MCP_TU_GLM
-    if (!glm) return false;
-#else
-    if (glm) return false;
-#endif
+    if (kind != MCP_TU_KIND) return false;
     switch (P) {
-#define X(p) case p: *err = Sel<p>::launch(glm, scen, plan, a); return true;
+#define X(p) case p: *err = Sel<p>::launch(kind, scen, plan, a); return true;
         MCP_ALL_P(X)
 #undef X
     }
@@ -107,7 +116,7 @@ bool MCP_TU_FN(launch_power)(int P, bool glm, bool scen, const DevicePlan& plan,
 
 bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy,
                      cudaError_t* err) {
-#ifdef MCP_TU_GLM
+#if MCP_TU_KIND != KIND_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
@@ -121,7 +130,7 @@ bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_see
 }
 
 bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, double* dout, cudaError_t* err) {
-#ifdef MCP_TU_GLM
+#if MCP_TU_KIND != KIND_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;

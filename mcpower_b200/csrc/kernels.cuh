@@ -282,8 +282,9 @@ struct SimOut {
 
 // Emit one fit: decisions, corrections, overall F, counters/bytes.  all_t = T squared statistics (NaN = untestable).
 // ov_given < 0: compute the overall F test from (sst, rss); otherwise 0/1 decided by the caller (GLM: deviance LRT).
-static __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
-                                      const uint8_t* excl_flags, int ov_given = -1) {
+static // joint_sig / boundary: MLE arm only (joint Wald chi-square decision, boundary_hit code; spec.rs:562-582).
+__device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
+                                      const uint8_t* excl_flags, int ov_given = -1, int joint_sig = 0, int boundary = 0) {
     const DevicePlan& pl = c_plan;
     const int T = pl.T;
     const size_t vrow = (size_t)variant * pl.n_ss + g;
@@ -332,6 +333,8 @@ static __device__ __noinline__ void emit_fit(const SimOut& so, int g, int varian
         atomicAdd(&cg[3 * T + 3 + n_cor], 1ull);
     }
     for (int f = 0; f < pl.n_factors; f++) count_flag(cs, cg, 4 * T + 4 + f, excl_flags && excl_flags[f] != 0);
+    count_flag(cs, cg, 4 * T + 4 + pl.n_factors, joint_sig != 0);
+    count_flag(cs, cg, 4 * T + 5 + pl.n_factors, boundary != 0);
     // ---- BatchResult byte tensors (spec.rs:552-600), sim-major
     if (pl.out_unc) {
         const size_t cell = so.sim_local * pl.n_ss + g;
@@ -341,6 +344,8 @@ static __device__ __noinline__ void emit_fit(const SimOut& so, int g, int varian
         }
         pl.out_conv[cell] = (uint8_t)fit.converged;
         if (pl.out_overall) pl.out_overall[cell] = ov;
+        if (pl.out_joint) pl.out_joint[cell] = (uint8_t)joint_sig;
+        if (pl.out_bh) pl.out_bh[cell] = (uint8_t)boundary;
         if (pl.out_fx)
             for (int f = 0; f < pl.n_factors; f++) pl.out_fx[cell * pl.n_factors + f] = excl_flags ? excl_flags[f] : 0;
     }
@@ -711,7 +716,8 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
     if (pl.has_cluster) {  // u_c = f32(normal(word c) * tau), drawn first on the sequential stream (data_gen.rs:146-161)
         const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
         const uint32_t cid = pl.sizing_fixed_size ? (uint32_t)(row / cs) : (uint32_t)(row % cs);
-        u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
+        // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
+        if (cid < (uint32_t)pl.n_clusters) u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
     }
     if (SCEN) {
         // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)

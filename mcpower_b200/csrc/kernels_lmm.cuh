@@ -1,0 +1,347 @@
+// kernels_lmm.cuh — random-intercept linear mixed model power kernel (profiled REML), sm_100a.
+//
+// Replaces the MLE arm of run_one_sim (crates/engine-core/src/batch.rs:1214-1561) for the random-intercept case
+// (BASELINE config 5).  The reference fits through glmm::fit_on + BOBYQA over theta (crates not in the tree); for
+// one random intercept the profiled REML deviance is a closed form in theta = tau/sigma over cluster-level
+// sufficient statistics (scripts/lme_handcompute_theta1.py:13-36):
+//     A(theta) = X'X − Σ_c s_c Sx_c Sx_c',  b(theta) = X'y − Σ_c s_c Sx_c Sy_c,  c(theta) = y'y − Σ_c s_c Sy_c²,
+//     s_c = theta² / (1 + theta² n_c),   dev = Σ_c log(1 + theta² n_c) + log|A| + (n − p) log sigma²(theta).
+// One simulated study per thread.  X'X / X'y / y'y stream in registers exactly as in the OLS kernel; the per-cluster
+// sums Sx_c, Sy_c live in an HBM scratch plane [cluster][column][sim] (coalesced across the studies of a warp) and
+// grow with the row prefix (cluster ids are N-independent in both sizing regimes, generation.rs cluster_of_row).
+// Both sizing regimes produce at most two distinct cluster sizes per prefix, so the cluster sums are folded into
+// two groups once per fit and every deviance evaluation is O(p²).  theta is found by Brent's fmin on [0, 30];
+// z-based Wald thresholds, corrections, the joint Wald chi-square and the boundary flag are decided in-kernel.
+// Every operation mirrors the test oracle's lmm_fit.
+#pragma once
+#include "kernels.cuh"
+
+namespace mcp {
+
+#define MCP_LMM_THETA_MAX 30.0
+#define MCP_LMM_TOL 1e-10
+#define MCP_LMM_MAXIT 200
+
+template <int PT>
+struct LmmCtx {
+    static constexpr int NACC = PT * (PT + 1) / 2;
+    int p, ng;
+    uint32_t n_rows;
+    double xtx[NACC], xty[PT], yty;
+    double grp_n[2], grp_m[2];
+    double M[2][NACC], v[2][PT], w[2];
+    double A[NACC], b[PT];
+    MemSolver<PT> ms;
+};
+
+template <int PT>
+static __device__ __noinline__ double lmm_dev(LmmCtx<PT>& c, double theta) {
+    const int p = c.p, nt = p * (p + 1) / 2;
+    const double t2 = theta * theta;
+    double s[2] = {0.0, 0.0};
+    for (int g = 0; g < c.ng; g++) s[g] = t2 / (1.0 + t2 * c.grp_n[g]);
+    for (int e = 0; e < nt; e++) {
+        double a = c.xtx[e];
+        for (int g = 0; g < c.ng; g++) a = fma(-s[g], c.M[g][e], a);
+        c.A[e] = a;
+    }
+    for (int j = 0; j < p; j++) {
+        double a = c.xty[j];
+        for (int g = 0; g < c.ng; g++) a = fma(-s[g], c.v[g][j], a);
+        c.b[j] = a;
+    }
+    double cc = c.yty;
+    for (int g = 0; g < c.ng; g++) cc = fma(-s[g], c.w[g], cc);
+    c.ms.factor_and_solve(c.A, c.b, p, cc, 0.0, c.n_rows);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (!c.ms.out.converged || !(c.ms.out.rss > 0.0) || isinf(c.ms.out.rss)) return inf;
+    double ldv = 0.0;
+    for (int g = 0; g < c.ng; g++) ldv += c.grp_m[g] * own_log(1.0 + t2 * c.grp_n[g]);
+    double lda = 0.0;
+    for (int j = 0; j < p; j++) lda += own_log(c.ms.L[tri(j, j)]);
+    return ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
+}
+
+// Brent's fmin on [a, b] (golden section + parabolic interpolation).
+template <int PT>
+static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out) {
+    const double cgold = 0.3819660112501051, eps = 1.4901161193847656e-08;
+    double v = a + cgold * (b - a), w = v, x = v, e = 0.0, d = 0.0;
+    double fx = lmm_dev<PT>(c, x), fv = fx, fw = fx;
+    for (int it = 0; it < MCP_LMM_MAXIT; it++) {
+        const double xm = 0.5 * (a + b), tol1 = eps * fabs(x) + tol / 3.0, tol2 = 2.0 * tol1;
+        if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) break;
+        bool golden = true;
+        if (fabs(e) > tol1) {
+            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pp = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) pp = -pp;
+            else q = -q;
+            r = e;
+            e = d;
+            if (fabs(pp) < fabs(0.5 * q * r) && pp > q * (a - x) && pp < q * (b - x)) {
+                d = pp / q;
+                const double u = x + d;
+                if (u - a < tol2 || b - u < tol2) d = xm - x >= 0.0 ? tol1 : -tol1;
+                golden = false;
+            }
+        }
+        if (golden) {
+            e = x >= xm ? a - x : b - x;
+            d = cgold * e;
+        }
+        const double u = fabs(d) >= tol1 ? x + d : (d >= 0.0 ? x + tol1 : x - tol1);
+        const double fu = lmm_dev<PT>(c, u);
+        if (fu <= fx) {
+            if (u >= x) a = x;
+            else b = x;
+            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+        } else {
+            if (u < x) a = u;
+            else b = u;
+            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+    }
+    fmin_out = fx;
+    return x;
+}
+
+// rows in cluster k among the first n rows (generation.rs cluster_of_row)
+__device__ __forceinline__ uint32_t lmm_cluster_rows(const DevicePlan& pl, int k, int n) {
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    if (pl.sizing_fixed_size) {
+        const int rem = n - k * cs;
+        return (uint32_t)(rem <= 0 ? 0 : (rem < cs ? rem : cs));
+    }
+    return (uint32_t)(n / cs + (k < n % cs ? 1 : 0));
+}
+
+// Fold the cluster sums into (at most two) size groups and minimise the profiled deviance.
+//   csum element (k, j) = csum[(k * (PT+1) + j) * stride]; kept == nullptr → full model.
+template <int PT>
+static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restrict__ csum, size_t stride, int n, int n_clusters,
+                                            const int8_t* kept, int& converged, int& boundary) {
+    const DevicePlan& pl = c_plan;
+    const int p = c.p, nt = p * (p + 1) / 2;
+    c.ng = 0;
+    for (int g = 0; g < 2; g++) {
+        c.grp_n[g] = 0.0;
+        c.grp_m[g] = 0.0;
+        c.w[g] = 0.0;
+        for (int e = 0; e < nt; e++) c.M[g][e] = 0.0;
+        for (int j = 0; j < p; j++) c.v[g][j] = 0.0;
+    }
+    double sx[PT + 1];
+    for (int k = 0; k < n_clusters; k++) {
+        const uint32_t cnk = lmm_cluster_rows(pl, k, n);
+        if (cnk == 0) continue;
+        int g;
+        if (c.ng == 0) { g = 0; c.ng = 1; c.grp_n[0] = (double)cnk; }
+        else if ((double)cnk == c.grp_n[0]) g = 0;
+        else { g = 1; if (c.ng == 1) { c.ng = 2; c.grp_n[1] = (double)cnk; } }
+        c.grp_m[g] += 1.0;
+        const double* base = csum + (size_t)k * (PT + 1) * stride;
+        for (int j = 0; j < p; j++) sx[j] = base[(size_t)(kept ? kept[j] : j) * stride];
+        sx[p] = base[(size_t)PT * stride];
+        int t = 0;
+        for (int a = 0; a < p; a++) {
+            for (int bb = 0; bb <= a; bb++) { c.M[g][t] = fma(sx[a], sx[bb], c.M[g][t]); t++; }
+            c.v[g][a] = fma(sx[a], sx[p], c.v[g][a]);
+        }
+        c.w[g] = fma(sx[p], sx[p], c.w[g]);
+    }
+    double fbest;
+    double th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest);
+    const double f0 = lmm_dev<PT>(c, 0.0);
+    boundary = 0;
+    converged = 1;
+    if (!(fbest < f0)) { th = 0.0; boundary = 1; }  // tau-hat = 0: OLS fallback (spec.rs:562-565)
+    else if (MCP_LMM_THETA_MAX - th < 1e-6 * MCP_LMM_THETA_MAX) { boundary = 2; converged = 0; }
+    const double f = lmm_dev<PT>(c, th);  // leaves L, beta, sigma² at theta-hat
+    if (isinf(f) || f != f) converged = 0;
+}
+
+// Joint Wald chi-square of the testable targets: beta_T' [Cov_TT]^-1 beta_T, Cov = sigma² A^-1.
+template <int PT>
+static __device__ __noinline__ double lmm_joint_wald(LmmCtx<PT>& c, const int* cols, int k) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (k <= 0 || k > PT) return nan;
+    const int p = c.p;
+    double U[PT][PT], G[PT * (PT + 1) / 2], bt[PT];
+    for (int t = 0; t < k; t++) {
+        c.ms.t_sq(cols[t], -1);  // leaves u = L^-1 e_col in c.ms.w[col..p)
+        for (int i = 0; i < p; i++) U[t][i] = i >= cols[t] ? c.ms.w[i] : 0.0;
+    }
+    for (int a = 0; a < k; a++)
+        for (int bb = 0; bb <= a; bb++) {
+            double sacc = 0.0;
+            for (int i = 0; i < p; i++) sacc = fma(U[a][i], U[bb][i], sacc);
+            G[tri(a, bb)] = sacc;
+        }
+    for (int t = 0; t < k; t++) bt[t] = c.ms.beta[cols[t]];
+    const double sigma_sq = c.ms.out.sigma_sq;
+    MemSolver<PT> gs;
+    gs.factor_and_solve(G, bt, k, 0.0, 0.0, 2u * (uint32_t)k + 2u);
+    if (!gs.out.converged) return nan;
+    double q = 0.0;
+    for (int t = 0; t < k; t++) q = fma(gs.w[t], gs.w[t], q);
+    return q / sigma_sq;
+}
+
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
+                                                              double* __restrict__ scratch) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    constexpr int SP = PT | 1;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
+    if (sim < n_sims) {
+        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+        SimCtx cx;
+        cx.k0 = (uint32_t)key;
+        cx.k1 = (uint32_t)(key >> 32);
+        cx.seq.init(key);
+        cx.tau = sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0);
+        cx.seq_row_base = (uint32_t)pl.n_clusters;
+        const int max_n = pl.max_n;
+        SimOut so{cnt_s, (uint64_t)sim};
+        double* csum = scratch + sim;
+        const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+        const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
+        for (int k = 0; k < nc_cap; k++)
+            for (int j = 0; j <= PT; j++) csum[(size_t)(k * (PT + 1) + j) * stride] = 0.0;
+
+        double acc[NACC], xty[PT];
+#pragma unroll
+        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) xty[i] = 0.0;
+        double yty = 0.0, sum_y = 0.0;
+        uint32_t n_rows = 0;
+        uint32_t lvl_counts[MCP_MAX_LEVELS];
+        uint8_t excl[MCP_MAX_FACTORS];
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+        ScenDesign<PT> sdv;
+        const bool scen = !pl.optimistic;
+        if (scen) {
+            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+            if (!sdv.ok) atomicExch(pl.error_flag, 2);
+        }
+        int g = 0;
+        uint32_t n_next = pl.ss[0];
+        for (int b = 0; b < (max_n + 3) >> 2; b++) {
+            if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
+            else gen_block<PT, false>(b, slab, cx, nullptr);
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                const int row = 4 * b + r;
+                if (row >= max_n) break;
+                double xr[PT];
+                const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+#pragma unroll
+                    for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
+                    xty[a] = fma(xr[a], yd, xty[a]);
+                }
+                yty = fma(yd, yd, yty);
+                sum_y += yd;
+                n_rows++;
+                {  // cluster sums (plain adds in row order, like the host-side restatement)
+                    const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
+                    double* base = csum + (size_t)kc * (PT + 1) * stride;
+#pragma unroll
+                    for (int j = 0; j < PT; j++) base[(size_t)j * stride] += xr[j];
+                    base[(size_t)PT * stride] += yd;
+                }
+                if (track_excl) {
+                    for (int f = 0; f < pl.n_factors; f++) {
+                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
+                        int lvl = 0;
+                        for (int d = 0; d < nl - 1; d++)
+                            if (slab[4 * (c0 + d) + r] == 1.0f) { lvl = d + 1; break; }
+                        lvl_counts[pl.f_off[f] + lvl]++;
+                    }
+                }
+                if ((uint32_t)(row + 1) == n_next) {
+                    const int n = row + 1;
+                    int variant = pl.base_variant;
+                    if (track_excl) {
+                        variant = 0;
+                        for (int f = 0; f < pl.n_factors; f++) {
+                            uint32_t mn = 0xffffffffu;
+                            for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
+                            excl[f] = mn < (uint32_t)pl.min_level_count;
+                            variant |= (int)excl[f] << f;
+                        }
+                    }
+                    const McpVariant& vr = pl.variants[variant];
+                    const bool reduced = vr.p_red != PT;
+                    const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
+                    LmmCtx<PT> c;
+                    c.p = vr.p_red;
+                    c.n_rows = n_rows;
+                    c.yty = yty;
+                    {
+                        double Af[NACC], bf[PT];
+#pragma unroll
+                        for (int i = 0; i < NACC; i++) Af[i] = acc[i];
+#pragma unroll
+                        for (int i = 0; i < PT; i++) bf[i] = xty[i];
+                        for (int ri = 0; ri < vr.p_red; ri++) {
+                            c.xty[ri] = bf[vr.kept[ri]];
+                            for (int rj = 0; rj <= ri; rj++) c.xtx[tri(ri, rj)] = Af[tri(vr.kept[ri], vr.kept[rj])];
+                        }
+                    }
+                    int conv = 0, bnd = 0;
+                    lmm_fit<PT>(c, csum, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd);
+                    double all_t[MCP_MAX_T];
+                    int cols[MCP_MAX_T];
+                    int k_red = 0;
+                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                    for (int t = 0; t < pl.n_marg; t++) {
+                        const int col = vr.remap[pl.target[t]];
+                        all_t[t] = nan;
+                        if (col >= 0) cols[k_red++] = col;
+                    }
+                    int jsig = 0;
+                    if (conv) {
+                        for (int t = 0; t < pl.n_marg; t++) {
+                            const int col = vr.remap[pl.target[t]];
+                            if (col >= 0) all_t[t] = c.ms.t_sq(col, -1);
+                        }
+                        const double jc = pl.crit_joint[(size_t)variant * pl.n_ss + g];
+                        const double jt = lmm_joint_wald<PT>(c, cols, k_red);
+                        jsig = !(isinf(jt) || jt != jt) && jt > jc;
+                    }
+                    FitOut fo = c.ms.out;
+                    fo.converged = conv;
+                    emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
+                    g++;
+                    n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+                }
+            }
+        }
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace mcp

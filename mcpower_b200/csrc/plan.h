@@ -84,6 +84,7 @@ struct DevicePlan {
     const double* crit_unc;            // [n_variants][n_ss]
     const double* crit_corr;           // [n_variants][n_ss][T]
     const double* crit_overall;        // [n_variants][n_ss]
+    const double* crit_joint;          // [n_variants][n_ss] joint Wald chi-square threshold (MLE arm) or NULL
     const uint8_t* levels;             // [n_factors][max_n] exact-walk levels (NULL if none exact)
     const double* t3_table;            // [2048] censored t(3) PPF (marginals/t3.rs)
     // ---- outputs
@@ -93,9 +94,11 @@ struct DevicePlan {
     uint8_t* out_conv;                 // [n_sims][n_ss]
     uint8_t* out_overall;              // [n_sims][n_ss] or NULL
     uint8_t* out_fx;                   // [n_sims][n_ss][n_factors] or NULL
+    uint8_t* out_joint;                // [n_sims][n_ss] joint Wald decision (MLE arm) or NULL
+    uint8_t* out_bh;                   // [n_sims][n_ss] boundary_hit code (MLE arm) or NULL
     double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
     int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
-    int32_t counter_width;             // 2T + 2 + 2(T+1) + n_factors
+    int32_t counter_width;             // 4T + 6 + n_factors
     int32_t smem_counters;             // counters staged in shared memory (fits)
 };
 
@@ -108,4 +111,6 @@ struct DevicePlan {
 //   [2T+2, 3T+3)     histogram of #uncorrected-significant targets per sim (T+1 buckets)
 //   [3T+3, 4T+4)     histogram of #corrected-significant targets per sim
 //   [4T+4, 4T+4+F)   sims with factor f excluded
-static inline int mcp_counter_width(int T, int F) { return 4 * T + 4 + F; }
+//   4T+4+F           joint Wald successes (MLE arm; 0 otherwise)
+//   4T+5+F           fits with a variance component on the boundary (MLE arm; 0 otherwise)
+static inline int mcp_counter_width(int T, int F) { return 4 * T + 6 + F; }

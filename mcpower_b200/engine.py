@@ -68,7 +68,8 @@ class _Result(C.Structure):
                 ("n_factors", C.c_uint32),
                 ("uncorrected", C.POINTER(C.c_uint8)), ("corrected", C.POINTER(C.c_uint8)),
                 ("converged", C.POINTER(C.c_uint8)), ("overall", C.POINTER(C.c_uint8)),
-                ("factor_excluded", C.POINTER(C.c_uint8)), ("t_sq", C.POINTER(C.c_double)),
+                ("factor_excluded", C.POINTER(C.c_uint8)), ("joint", C.POINTER(C.c_uint8)),
+                ("boundary_hit", C.POINTER(C.c_uint8)), ("t_sq", C.POINTER(C.c_double)),
                 ("counter_width", C.c_uint32), ("gpu_launches", C.c_uint32),
                 ("counters", C.POINTER(C.c_uint64)), ("kernel_ms", C.c_double)]
 
@@ -133,12 +134,14 @@ class BatchResult:
     n_sample_sizes: int
     n_targets: int
     n_factors: int
-    counters: np.ndarray                       # [n_ss, 4T+4+F] uint64 (layout: include/mcpower_b200.h)
+    counters: np.ndarray                       # [n_ss, 4T+6+F] uint64 (layout: include/mcpower_b200.h)
     uncorrected: Optional[np.ndarray] = None   # [n_sims, n_ss, T] uint8
     corrected: Optional[np.ndarray] = None
     converged: Optional[np.ndarray] = None     # [n_sims, n_ss]
     overall: Optional[np.ndarray] = None
     factor_excluded: Optional[np.ndarray] = None
+    joint: Optional[np.ndarray] = None         # [n_sims, n_ss] joint Wald decision (estimator mle)
+    boundary_hit: Optional[np.ndarray] = None  # [n_sims, n_ss] 0 none / 1 tau-hat = 0 / 2 upper bound (estimator mle)
     t_sq: Optional[np.ndarray] = None          # [n_sims, n_ss, T] float64 (MODE_CAPTURE)
     kernel_ms: float = 0.0
     gpu_launches: int = 0
@@ -176,18 +179,27 @@ class BatchResult:
         T = self.n_targets
         return self.counters[:, 4 * T + 4:4 * T + 4 + self.n_factors]
 
+    @property
+    def success_joint(self):
+        return self.counters[:, 4 * self.n_targets + 4 + self.n_factors]
+
+    @property
+    def n_boundary(self):
+        return self.counters[:, 4 * self.n_targets + 5 + self.n_factors]
+
     def power(self, corrected: bool = False) -> np.ndarray:
         """successes / n_sims per (sample size, target) — PowerResult.power (aggregation.rs)."""
         s = self.success_corrected if corrected else self.success_uncorrected
         return s.astype(np.float64) / max(self.n_sims, 1)
 
 
-def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_excluded=None) -> np.ndarray:
+def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_excluded=None, joint=None,
+                        boundary_hit=None) -> np.ndarray:
     """aggregate_batch's integer reductions (aggregation.rs:91-242) over the byte tensors —
     used to prove COUNTS mode equals BYTES mode + host aggregation."""
     n_sims, n_ss, T = uncorrected.shape
     F = 0 if factor_excluded is None else factor_excluded.shape[2]
-    out = np.zeros((n_ss, 4 * T + 4 + F), dtype=np.uint64)
+    out = np.zeros((n_ss, 4 * T + 6 + F), dtype=np.uint64)
     out[:, :T] = uncorrected.sum(axis=0)
     out[:, T:2 * T] = corrected.sum(axis=0)
     out[:, 2 * T] = converged.sum(axis=0)
@@ -199,7 +211,11 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
         out[g, 2 * T + 2:3 * T + 3] = np.bincount(nu[:, g], minlength=T + 1)
         out[g, 3 * T + 3:4 * T + 4] = np.bincount(nc[:, g], minlength=T + 1)
     if F:
-        out[:, 4 * T + 4:] = (factor_excluded != 0).sum(axis=0)
+        out[:, 4 * T + 4:4 * T + 4 + F] = (factor_excluded != 0).sum(axis=0)
+    if joint is not None:
+        out[:, 4 * T + 4 + F] = joint.sum(axis=0)
+    if boundary_hit is not None:
+        out[:, 4 * T + 5 + F] = (boundary_hit != 0).sum(axis=0)
     return out
 
 
@@ -244,6 +260,8 @@ def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: i
             converged=take(r.converged, (r.n_sims, n_ss), np.uint8),
             overall=take(r.overall, (r.n_sims, n_ss), np.uint8),
             factor_excluded=take(r.factor_excluded, (r.n_sims, n_ss, F), np.uint8),
+            joint=take(r.joint, (r.n_sims, n_ss), np.uint8),
+            boundary_hit=take(r.boundary_hit, (r.n_sims, n_ss), np.uint8),
             t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),
             kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches))
     finally:

@@ -162,3 +162,16 @@ def logit_spec(baseline_p: float = 0.3) -> dict:
     s["report_overall"] = True
     s["max_failed_fraction"] = 0.25
     return s
+
+
+def lmm_spec(n_clusters: int = 30, icc: float = 0.2) -> dict:
+    """BASELINE config 5: linear mixed model with a random intercept, `n_clusters` clusters (round-robin rows),
+    REML fit, y ~ x1 + x2 + (1 | cluster); tau² = ICC / (1 − ICC) with unit residual variance."""
+    s = base_spec(2)
+    s["effect_sizes"] = [0.0, 0.3, 0.2]
+    s["target_indices"] = [1, 2]
+    s["estimator"] = "mle"
+    s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": n_clusters}}, "tau_squared": icc / (1.0 - icc),
+                    "slopes": [], "extra_groupings": []}
+    s["max_failed_fraction"] = 0.25
+    return s

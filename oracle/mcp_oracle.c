@@ -1692,6 +1692,205 @@ int orc_fit_glm(const double* xc, const double* yv, int n, int p, int family, co
 }
 
 /* ======================================================================= */
+/* Random-intercept LMM by profiled REML (MLE arm, batch.rs:1214-1561).      */
+/* The reference fits through glmm::fit_on + BOBYQA over theta (not in the   */
+/* tree).  For one random intercept the profiled REML deviance is a closed   */
+/* form in theta = tau/sigma over cluster-level sufficient statistics        */
+/* (scripts/lme_handcompute_theta1.py:13-36); this restatement minimises it  */
+/* with Brent's fmin on [0, THETA_MAX].  Value-pinned to the 8 frozen lmer   */
+/* goldens (1e-4 gate, tolerances.R:29-31); optimiser path UNPINNED.         */
+/* ======================================================================= */
+
+#define LMM_THETA_MAX 30.0
+#define LMM_TOL 1e-10
+#define LMM_MAXIT 200
+
+typedef struct {
+    int p, ng;
+    uint32_t n_rows;
+    const double *xtx, *xty;
+    double yty;
+    double grp_n[2], grp_m[2];      /* cluster size / number of clusters of that size */
+    double M[2][64 * 65 / 2], v[2][64], w[2];
+    /* state of the most recent evaluation */
+    double A[64 * 65 / 2], b[64], L[64 * 65 / 2], inv_d[64], wv[64], beta[64];
+    OlsFit fit;
+} LmmCtx;
+
+static double lmm_dev(LmmCtx* c, double theta) {
+    const int p = c->p;
+    const size_t nt = (size_t)p * (p + 1) / 2;
+    double t2 = theta * theta, s[2] = {0.0, 0.0};
+    for (int g = 0; g < c->ng; g++) s[g] = t2 / (1.0 + t2 * c->grp_n[g]);
+    for (size_t e = 0; e < nt; e++) {
+        double a = c->xtx[e];
+        for (int g = 0; g < c->ng; g++) a = fma(-s[g], c->M[g][e], a);
+        c->A[e] = a;
+    }
+    for (int j = 0; j < p; j++) {
+        double a = c->xty[j];
+        for (int g = 0; g < c->ng; g++) a = fma(-s[g], c->v[g][j], a);
+        c->b[j] = a;
+    }
+    double cc = c->yty;
+    for (int g = 0; g < c->ng; g++) cc = fma(-s[g], c->w[g], cc);
+    ols_solve(c->A, c->b, cc, 0.0, c->n_rows, p, c->L, c->inv_d, c->wv, c->beta, &c->fit);
+    if (!c->fit.converged || !(c->fit.rss > 0.0) || !isfinite(c->fit.rss)) return INFINITY;
+    double ldv = 0.0;
+    for (int g = 0; g < c->ng; g++) ldv += c->grp_m[g] * orc_log(1.0 + t2 * c->grp_n[g]);
+    double lda = 0.0;
+    for (int j = 0; j < p; j++) lda += orc_log(c->L[TRI(j, j)]);
+    return ldv + 2.0 * lda + c->fit.df_resid * orc_log(c->fit.sigma_sq);
+}
+
+/* Brent's fmin (golden section + parabolic interpolation) on [a, b]; deterministic, restated in the CUDA kernel. */
+static double lmm_fmin(LmmCtx* c, double a, double b, double tol, double* fmin_out, int* iters) {
+    const double cgold = 0.3819660112501051, eps = 1.4901161193847656e-08;
+    double v = a + cgold * (b - a), w = v, x = v, e = 0.0, d = 0.0;
+    double fx = lmm_dev(c, x), fv = fx, fw = fx;
+    int it;
+    for (it = 0; it < LMM_MAXIT; it++) {
+        double xm = 0.5 * (a + b), tol1 = eps * fabs(x) + tol / 3.0, tol2 = 2.0 * tol1;
+        if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) break;
+        int golden = 1;
+        if (fabs(e) > tol1) {
+            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pp = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) pp = -pp; else q = -q;
+            r = e;
+            e = d;
+            if (fabs(pp) < fabs(0.5 * q * r) && pp > q * (a - x) && pp < q * (b - x)) {
+                d = pp / q;
+                double u = x + d;
+                if (u - a < tol2 || b - u < tol2) d = xm - x >= 0.0 ? tol1 : -tol1;
+                golden = 0;
+            }
+        }
+        if (golden) {
+            e = x >= xm ? a - x : b - x;
+            d = cgold * e;
+        }
+        double u = fabs(d) >= tol1 ? x + d : (d >= 0.0 ? x + tol1 : x - tol1);
+        double fu = lmm_dev(c, u);
+        if (fu <= fx) {
+            if (u >= x) a = x; else b = x;
+            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+        } else {
+            if (u < x) a = u; else b = u;
+            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+    }
+    *fmin_out = fx;
+    *iters = it;
+    return x;
+}
+
+typedef struct {
+    int converged, boundary_hit;
+    double theta, sigma_sq, tau_sq;
+} LmmOut;
+
+/* csum: per-cluster [n_clusters][p+1] = (sum of x_j over the cluster's rows ..., sum of y); cn[c] = rows in cluster c */
+static void lmm_fit(LmmCtx* c, const double* csum, const uint32_t* cn, int n_clusters, int p, LmmOut* out) {
+    const size_t nt = (size_t)p * (p + 1) / 2;
+    c->ng = 0;
+    for (int g = 0; g < 2; g++) {
+        c->grp_n[g] = 0.0; c->grp_m[g] = 0.0; c->w[g] = 0.0;
+        memset(c->M[g], 0, sizeof(double) * nt);
+        memset(c->v[g], 0, sizeof(double) * (size_t)p);
+    }
+    for (int k = 0; k < n_clusters; k++) {
+        if (cn[k] == 0) continue;
+        int g;
+        if (c->ng == 0) { g = 0; c->ng = 1; c->grp_n[0] = (double)cn[k]; }
+        else if ((double)cn[k] == c->grp_n[0]) g = 0;
+        else { g = 1; if (c->ng == 1) { c->ng = 2; c->grp_n[1] = (double)cn[k]; } }
+        c->grp_m[g] += 1.0;
+        const double* sx = csum + (size_t)k * (p + 1);
+        size_t t = 0;
+        for (int a = 0; a < p; a++) {
+            for (int bb = 0; bb <= a; bb++) { c->M[g][t] = fma(sx[a], sx[bb], c->M[g][t]); t++; }
+            c->v[g][a] = fma(sx[a], sx[p], c->v[g][a]);
+        }
+        c->w[g] = fma(sx[p], sx[p], c->w[g]);
+    }
+    double fbest;
+    int iters;
+    double th = lmm_fmin(c, 0.0, LMM_THETA_MAX, LMM_TOL, &fbest, &iters);
+    double f0 = lmm_dev(c, 0.0);
+    out->boundary_hit = 0;
+    out->converged = 1;
+    if (!(fbest < f0)) { th = 0.0; out->boundary_hit = 1; }      /* tau-hat = 0: OLS fallback (spec.rs:562-565) */
+    else if (LMM_THETA_MAX - th < 1e-6 * LMM_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+    double f = lmm_dev(c, th);                                    /* leaves A, L, beta, sigma at theta-hat */
+    if (!isfinite(f)) out->converged = 0;
+    out->theta = th;
+    out->sigma_sq = c->fit.sigma_sq;
+    out->tau_sq = th * th * c->fit.sigma_sq;
+}
+
+/* Joint Wald chi-square of the targets: beta_T' [Cov_TT]^-1 beta_T with Cov = sigma^2 A^-1. */
+static double lmm_joint_wald(const LmmCtx* c, const int* cols, int k) {
+    if (k <= 0 || k > 32) return NAN;
+    const int p = c->p;
+    double U[32][64], G[32 * 33 / 2], Lg[32 * 33 / 2], invd[32], wv[32], u[64];
+    for (int t = 0; t < k; t++) {
+        linv_norm_sq(c->L, c->inv_d, p, cols[t], -1, u);
+        for (int i = 0; i < p; i++) U[t][i] = i >= cols[t] ? u[i] : 0.0;
+    }
+    for (int a = 0; a < k; a++)
+        for (int bb = 0; bb <= a; bb++) {
+            double sacc = 0.0;
+            for (int i = 0; i < p; i++) sacc = fma(U[a][i], U[bb][i], sacc);
+            G[TRI(a, bb)] = sacc;
+        }
+    double bt[32], sol[32];
+    for (int t = 0; t < k; t++) bt[t] = c->beta[cols[t]];
+    OlsFit f;
+    ols_solve(G, bt, 0.0, 0.0, 2u * (uint32_t)k + 2u, k, Lg, invd, wv, sol, &f);
+    if (!f.converged) return NAN;
+    double q = 0.0;
+    for (int t = 0; t < k; t++) q = fma(wv[t], wv[t], q);   /* |Lg^-1 beta_T|^2 = beta_T' G^-1 beta_T */
+    return q / c->fit.sigma_sq;
+}
+
+int orc_fit_lmm(const double* xc, const double* yv, const int32_t* ids, int n, int p, double* betas, double* se,
+                double* theta, double* sigma_sq, int* converged, int* boundary) {
+    if (p > 64) return fail(ORC_ERR_INVALID_SPEC, "p > 64");
+    float* x = (float*)malloc(sizeof(float) * (size_t)n * p);
+    float* y = (float*)malloc(sizeof(float) * (size_t)n);
+    for (size_t i = 0; i < (size_t)n * p; i++) x[i] = (float)xc[i];
+    for (int i = 0; i < n; i++) y[i] = (float)yv[i];
+    int nc = 0;
+    for (int i = 0; i < n; i++) if (ids[i] + 1 > nc) nc = ids[i] + 1;
+    size_t nt = (size_t)p * (p + 1) / 2;
+    double* xtx = (double*)calloc(nt + (size_t)p + (size_t)nc * (p + 1), sizeof(double));
+    double *xty = xtx + nt, *csum = xty + p;
+    uint32_t* cn = (uint32_t*)calloc((size_t)nc, sizeof(uint32_t));
+    SuffScalars sc = {0.0, 0.0, 0};
+    suff_add_rows(x, y, n, p, 0, n, xtx, xty, &sc);
+    for (int i = 0; i < n; i++) {
+        double* sx = csum + (size_t)ids[i] * (p + 1);
+        for (int j = 0; j < p; j++) sx[j] += (double)x[(size_t)j * n + i];
+        sx[p] += (double)y[i];
+        cn[ids[i]]++;
+    }
+    LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
+    c->p = p; c->n_rows = (uint32_t)n; c->xtx = xtx; c->xty = xty; c->yty = sc.yty;
+    LmmOut o;
+    lmm_fit(c, csum, cn, nc, p, &o);
+    double u[64];
+    for (int t = 0; t < p; t++) {
+        betas[t] = c->beta[t];
+        se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
+    }
+    *theta = o.theta; *sigma_sq = o.sigma_sq; *converged = o.converged; *boundary = o.boundary_hit;
+    free(c); free(cn); free(xtx); free(x); free(y);
+    return ORC_OK;
+}
+
+/* ======================================================================= */
 /* Batch driver (batch.rs:199-776, OLS arm 871-1213)                        */
 /* ======================================================================= */
 
@@ -1930,12 +2129,110 @@ static int run_one_sim_glm(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
     return ORC_OK;
 }
 
+/* MLE arm (batch.rs:1214-1561), random intercept only: cluster-level sufficient statistics grow with the row
+ * prefix (cluster ids are N-independent in both sizing regimes, generation.rs cluster_of_row), one profiled-REML
+ * fit per grid point; z-based thresholds; joint Wald chi-square over the testable targets. */
+static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t sim_id, uint64_t base_seed, Ws* w,
+                           const double* t_unc, const double* corr, double joint_crit_full, uint8_t* unc, uint8_t* cor,
+                           uint8_t* conv, uint8_t* overall, uint8_t* fx, double* cap, uint8_t* joint, uint8_t* bh) {
+    int rc = gen_sim(s, base_seed, sim_id, w);
+    if (rc) return rc;
+    const int P = w->P, T = s->n_marginal_targets, ld = w->max_n;
+    const int csz = s->sizing_value > 0 ? s->sizing_value : 1;
+    const int nc_cap = s->sizing_fixed_size ? ld / csz + 1 : csz;
+    size_t nt = (size_t)P * (P + 1) / 2;
+    int nprops = 0;
+    for (int f = 0; f < s->n_factors; f++) nprops += s->factor_n_levels[f];
+    int test_reduces = s->n_fit_columns > 0 && s->n_fit_columns < P;
+    double* csum = (double*)calloc((size_t)nc_cap * (P + 1) * 2, sizeof(double));
+    double* csum_red = csum + (size_t)nc_cap * (P + 1);
+    uint32_t* cn = (uint32_t*)calloc((size_t)nc_cap, sizeof(uint32_t));
+    LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
+    memset(w->xtx, 0, sizeof(double) * nt);
+    memset(w->xty, 0, sizeof(double) * (size_t)P);
+    SuffScalars sc = {0.0, 0.0, 0};
+    double Ared[64 * 65 / 2], bred[64], all_t[256], u[64];
+    int kept[64], remap[64], cols[256];
+    int last = 0;
+    for (int g = 0; g < n_ss; g++) {
+        int n = (int)ss[g];
+        if (n > last) {
+            suff_add_rows(w->x, w->y, ld, P, last, n, w->xtx, w->xty, &sc);
+            for (int i = last; i < n; i++) {
+                int k = w->cluster_ids[i];
+                double* sx = csum + (size_t)k * (P + 1);
+                for (int j = 0; j < P; j++) sx[j] += (double)w->x[(size_t)j * ld + i];
+                sx[P] += (double)w->y[i];
+                cn[k]++;
+            }
+            last = n;
+        }
+        memset(w->prefix_counts, 0, sizeof(uint32_t) * (size_t)(nprops > 0 ? nprops : 1));
+        memset(w->excl_flags, 0, (size_t)(s->n_factors > 0 ? s->n_factors : 1));
+        if (s->n_factors > 0 && s->factor_min_level_count > 0)
+            update_factor_exclusions(s, w->x, ld, 0, n, w->prefix_counts, w->excl_flags);
+        int any_excl = 0;
+        for (int f = 0; f < s->n_factors; f++) any_excl |= w->excl_flags[f] != 0;
+        int reduced = any_excl || test_reduces, p_red = P;
+        int n_clusters = s->sizing_fixed_size ? (n + csz - 1) / csz : csz;
+        LmmOut lo;
+        c->n_rows = sc.n_rows; c->yty = sc.yty;
+        if (!reduced) {
+            c->p = P; c->xtx = w->xtx; c->xty = w->xty;
+            lmm_fit(c, csum, cn, n_clusters, P, &lo);
+        } else {
+            p_red = build_exclusion_remap(s, w->excl_flags, kept, remap);
+            for (int ri = 0; ri < p_red; ri++) {
+                bred[ri] = w->xty[kept[ri]];
+                for (int rj = 0; rj <= ri; rj++) Ared[TRI(ri, rj)] = w->xtx[TRI(kept[ri], kept[rj])];
+            }
+            for (int k = 0; k < n_clusters; k++) {
+                for (int rj = 0; rj < p_red; rj++) csum_red[(size_t)k * (p_red + 1) + rj] = csum[(size_t)k * (P + 1) + kept[rj]];
+                csum_red[(size_t)k * (p_red + 1) + p_red] = csum[(size_t)k * (P + 1) + P];
+            }
+            c->p = p_red; c->xtx = Ared; c->xty = bred;
+            lmm_fit(c, csum_red, cn, n_clusters, p_red, &lo);
+        }
+        conv[g] = (uint8_t)lo.converged;
+        if (bh) bh[g] = (uint8_t)lo.boundary_hit;
+        uint8_t* unc_row = unc + (size_t)g * T;
+        uint8_t* cor_row = cor + (size_t)g * T;
+        memset(unc_row, 0, (size_t)T);
+        memset(cor_row, 0, (size_t)T);
+        for (int t = 0; t < T; t++) all_t[t] = NAN;
+        int k_red = 0;
+        for (int t = 0; t < T; t++) {
+            int col = reduced ? remap[s->target_indices[t]] : s->target_indices[t];
+            if (col >= 0) cols[k_red++] = col;
+        }
+        uint8_t jsig = 0;
+        if (lo.converged) {
+            for (int t = 0; t < T; t++) {
+                int col = reduced ? remap[s->target_indices[t]] : s->target_indices[t];
+                if (col >= 0) all_t[t] = target_t_sq(c->L, c->inv_d, c->beta, c->fit.sigma_sq, p_red, col, -1, u);
+            }
+            for (int t = 0; t < T; t++) unc_row[t] = !isnan(all_t[t]) && all_t[t] > t_unc[g];
+            orc_apply_correction(s->correction_method, all_t, T, t_unc[g], corr + (size_t)g * T, cor_row);
+            double jc = !reduced ? joint_crit_full : (k_red == 0 ? INFINITY : orc_chi2_ppf(1.0 - s->alpha, (double)k_red));
+            double jt = lmm_joint_wald(c, cols, k_red);
+            jsig = isfinite(jt) && jt > jc;
+        }
+        if (joint) joint[g] = jsig;
+        if (cap) memcpy(cap + (size_t)g * T, all_t, sizeof(double) * (size_t)T);
+        if (overall) overall[g] = 0;
+        if (fx && s->n_factors > 0) memcpy(fx + (size_t)g * s->n_factors, w->excl_flags, (size_t)s->n_factors);
+    }
+    free(c); free(cn); free(csum);
+    return ORC_OK;
+}
+
 int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sims, uint64_t sim_begin, uint64_t base_seed,
                   int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged, uint8_t* overall,
-                  uint8_t* factor_excluded, double* t_sq_capture) {
+                  uint8_t* factor_excluded, double* t_sq_capture, uint8_t* joint, uint8_t* boundary_hit) {
     int rc = validate_spec(s, ss, n_ss);
     if (rc) return rc;
-    if (s->estimator == ORC_EST_MLE) return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: estimator=mle is not restated");
+    if (s->estimator == ORC_EST_MLE && (s->n_contrasts > 0 || s->has_lme || s->outcome_kind != ORC_OUT_CONTINUOUS))
+        return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: only the Gaussian random-intercept MLE arm is restated");
     if (s->estimator == ORC_EST_GLM && (s->has_cluster || s->n_contrasts > 0))
         return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: clustered GLM (GLMM) / GLM contrasts are not restated");
     if (s->estimator == ORC_EST_GLM && s->outcome_kind == ORC_OUT_CONTINUOUS)
@@ -1944,6 +2241,7 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
     if (P > 64) return fail(ORC_ERR_INVALID_SPEC, "P > 64");
     const int T = s->n_marginal_targets + s->n_contrasts;
     if (T > 256) return fail(ORC_ERR_INVALID_SPEC, "T > 256");
+    const double joint_crit_full = (s->estimator == ORC_EST_MLE && T > 0) ? orc_chi2_ppf(1.0 - s->alpha, (double)T) : NAN;
     double* t_unc = (double*)malloc(sizeof(double) * (size_t)n_ss * (size_t)(T + 3));
     double *corr = t_unc + n_ss, *ovc = corr + (size_t)n_ss * T, *ph = ovc + n_ss;
     rc = orc_build_crit_table(s, ss, n_ss, P, t_unc, corr, ph, ovc);
@@ -1962,7 +2260,16 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
 #endif
         for (int64_t i = 0; i < (int64_t)n_sims; i++) {
             if (err) continue;
-            int r = (s->estimator == ORC_EST_GLM ? run_one_sim_glm : run_one_sim)(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
+            int r;
+            if (s->estimator == ORC_EST_MLE)
+                r = run_one_sim_mle(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, joint_crit_full,
+                                    uncorrected + (size_t)i * n_ss * T, corrected + (size_t)i * n_ss * T,
+                                    converged + (size_t)i * n_ss, overall ? overall + (size_t)i * n_ss : NULL,
+                                    factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,
+                                    t_sq_capture ? t_sq_capture + (size_t)i * n_ss * T : NULL,
+                                    joint ? joint + (size_t)i * n_ss : NULL, boundary_hit ? boundary_hit + (size_t)i * n_ss : NULL);
+            else
+                r = (s->estimator == ORC_EST_GLM ? run_one_sim_glm : run_one_sim)(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
                                 uncorrected + (size_t)i * n_ss * T, corrected + (size_t)i * n_ss * T,
                                 converged + (size_t)i * n_ss, overall ? overall + (size_t)i * n_ss : NULL,
                                 factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,

@@ -116,6 +116,10 @@ int orc_fit_ols(const double* x_colmajor, const double* y, int n, int p, double*
 int orc_fit_glm(const double* x_colmajor, const double* y, int n, int p, int family, const double* beta_start,
                 double* betas, double* se, double* deviance, double* deviance_null, int* converged, int* iters);
 
+/* ---- random-intercept LMM (profiled REML) on supplied data; ids = 0-based cluster index per row ---- */
+int orc_fit_lmm(const double* x_colmajor, const double* y, const int32_t* ids, int n, int p, double* betas, double* se,
+                double* theta, double* sigma_sq, int* converged, int* boundary);
+
 /* ---- the batch driver (batch.rs:199-776, 795-1213) ----
  * Outputs (caller-allocated, sim-major like spec.rs:552-600):
  *   uncorrected/corrected [n_sims][n_ss][T], converged [n_sims][n_ss],
@@ -124,7 +128,8 @@ int orc_fit_glm(const double* x_colmajor, const double* y, int n, int p, int fam
  * sim ids run over [sim_begin, sim_begin + n_sims).  n_threads<=1 → serial. */
 int orc_run_batch(const OrcSpec* spec, const uint32_t* sample_sizes, int n_ss, uint32_t n_sims, uint64_t sim_begin,
                   uint64_t base_seed, int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged,
-                  uint8_t* overall, uint8_t* factor_excluded, double* t_sq_capture);
+                  uint8_t* overall, uint8_t* factor_excluded, double* t_sq_capture,
+                  uint8_t* joint /* [n_sims][n_ss] or NULL (MLE joint Wald) */, uint8_t* boundary_hit /* or NULL */);
 
 const char* orc_last_error(void);
 

@@ -105,8 +105,10 @@ def lib():
                               P(C.c_int)]
     L.orc_fit_glm.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
                               P(C.c_int), P(C.c_int)]
+    L.orc_fit_lmm.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(C.c_int),
+                              P(C.c_int)]
     L.orc_run_batch.argtypes = [P(OrcSpec), P(u32), C.c_int, u32, u64, u64, C.c_int, P(C.c_uint8), P(C.c_uint8),
-                                P(C.c_uint8), P(C.c_uint8), P(C.c_uint8), P(dbl)]
+                                P(C.c_uint8), P(C.c_uint8), P(C.c_uint8), P(dbl), P(C.c_uint8), P(C.c_uint8)]
     L.orc_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -337,6 +339,22 @@ def fit_glm(x, y, family: str, beta_start=None):
             "iters": it.value}
 
 
+def fit_lmm(x, y, ids):
+    """Random-intercept profiled-REML fit on supplied data → dict(betas, se, theta, sigma_sq, converged, boundary)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    idv = np.ascontiguousarray(ids, dtype=np.int32)
+    b, se = np.zeros(p), np.zeros(p)
+    th, s2 = C.c_double(), C.c_double()
+    conv, bd = C.c_int(), C.c_int()
+    _check(lib().orc_fit_lmm(_ptr(xc, C.c_double), _ptr(yv, C.c_double), _ptr(idv, C.c_int32), n, p, _ptr(b, C.c_double),
+                             _ptr(se, C.c_double), C.byref(th), C.byref(s2), C.byref(conv), C.byref(bd)))
+    return {"betas": b, "se": se, "theta": th.value, "sigma_sq": s2.value, "converged": bool(conv.value),
+            "boundary": bd.value}
+
+
 def run_batch(spec: dict, sample_sizes, n_sims: int, base_seed: int, sim_begin: int = 0, n_threads: int = 1,
               capture: bool = False):
     """CPU restatement of engine_core::run_batch (OLS arm). Returns the BatchResult tensors as numpy arrays."""
@@ -349,13 +367,17 @@ def run_batch(spec: dict, sample_sizes, n_sims: int, base_seed: int, sim_begin: 
     ov = np.zeros((n_sims, n_ss), dtype=np.uint8) if ps.c.report_overall else None
     fx = np.zeros((n_sims, n_ss, F), dtype=np.uint8) if F > 0 else None
     cap = np.full((n_sims, n_ss, T), np.nan) if capture else None
+    mle = ps.c.estimator == EST["mle"]
+    joint = np.zeros((n_sims, n_ss), dtype=np.uint8) if mle else None
+    bh = np.zeros((n_sims, n_ss), dtype=np.uint8) if mle else None
     u8 = C.c_uint8
     _check(lib().orc_run_batch(C.byref(ps.c), _ptr(ss, C.c_uint32), n_ss, n_sims, sim_begin, base_seed, n_threads,
                                _ptr(unc, u8), _ptr(cor, u8), _ptr(conv, u8),
                                None if ov is None else _ptr(ov, u8), None if fx is None else _ptr(fx, u8),
-                               None if cap is None else _ptr(cap, C.c_double)))
+                               None if cap is None else _ptr(cap, C.c_double),
+                               None if joint is None else _ptr(joint, u8), None if bh is None else _ptr(bh, u8)))
     return {"uncorrected": unc, "corrected": cor, "converged": conv, "overall": ov, "factor_excluded": fx,
-            "t_sq": cap}
+            "t_sq": cap, "joint": joint, "boundary_hit": bh}
 
 
 def host_threads() -> int:

@@ -29,7 +29,11 @@ def assert_batch_equal(got: M.BatchResult, want: dict):
     if want["t_sq"] is not None and got.t_sq is not None:
         assert np.array_equal(got.t_sq.view(np.uint64), want["t_sq"].view(np.uint64)) or \
             np.array_equal(got.t_sq, want["t_sq"], equal_nan=True), "t_sq bits"
-    agg = M.counters_from_bytes(got.uncorrected, got.corrected, got.converged, got.overall, got.factor_excluded)
+    if want.get("joint") is not None:
+        assert np.array_equal(got.joint, want["joint"]), "joint"
+        assert np.array_equal(got.boundary_hit, want["boundary_hit"]), "boundary_hit"
+    agg = M.counters_from_bytes(got.uncorrected, got.corrected, got.converged, got.overall, got.factor_excluded,
+                                got.joint, got.boundary_hit)
     assert np.array_equal(agg, got.counters), "COUNTS != aggregate(BYTES)"
 
 
@@ -319,6 +323,44 @@ def test_glm_wave_split_is_invariant():
     assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 3
 
 
+# ------------------------------------------------------------------ random-intercept LMM, REML (BASELINE config 5)
+def test_lmm_random_intercept_matches_oracle():
+    s = S.lmm_spec(30, 0.2)
+    grid = [60, 120, 300, 600]
+    got = M.run_batch(s, grid, 512, SEED, mode=ALL)
+    want = orc.run_batch(s, grid, 512, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert got.boundary_hit[:, 0].mean() > 0.0 and got.success_joint[-1] > 0.95 * 512
+    p = got.power()[:, 0]
+    assert p[-1] > 0.95 and np.all(np.diff(p) > -0.05)
+
+
+def test_lmm_fixed_size_unbalanced_prefixes_match_oracle():
+    """FixedSize sizing with sample sizes that are not multiples of the cluster size: two cluster-size groups."""
+    s = S.lmm_spec(10, 0.3)
+    s["cluster"]["sizing"] = {"FixedSize": {"cluster_size": 8}}
+    s["correction_method"] = "holm"
+    got = M.run_batch(s, [40, 100, 160], 384, SEED + 9, mode=ALL)
+    want = orc.run_batch(s, [40, 100, 160], 384, SEED + 9, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    s2 = S.lmm_spec(7, 0.1)   # FixedClusters with N % n_clusters != 0
+    got = M.run_batch(s2, [30, 95], 384, SEED + 9, mode=ALL)
+    want = orc.run_batch(s2, [30, 95], 384, SEED + 9, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_lmm_with_factor_exclusion_and_interaction_matches_oracle():
+    s = S.add_factor(S.lmm_spec(12, 0.25), [0.6, 0.25, 0.15], [0.4, 0.7])
+    s = S.add_interaction(s, [1, 2], 0.15)
+    s["target_indices"] = [1, 2, 3, 4, 5]
+    s["factor_min_level_count"] = 5
+    s["factor_sampled"] = [True]
+    got = M.run_batch(s, [24, 48, 120], 384, SEED, mode=ALL)
+    want = orc.run_batch(s, [24, 48, 120], 384, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert 0.02 < got.factor_excluded[:, 0, 0].mean() < 0.98
+
+
 # ------------------------------------------------------------------ determinism contract (batch.rs:2715-2786, SURVEY §8b)
 def test_results_independent_of_wave_size_and_shard_offset():
     s = S.sweep_spec()
@@ -350,12 +392,11 @@ def test_errors_match_reference_classes():
     bad["correlation"] = [1.0, 1.2, 1.2, 1.0]
     with pytest.raises(M.CorrelationNotPSD):
         M.run_batch(bad, [50], 10, SEED)
-    mle = S.headline_spec()
-    mle["estimator"] = "mle"
-    mle["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": 10}}, "tau_squared": 0.25, "slopes": [],
-                      "extra_groupings": []}
+    glmm = S.logit_spec()
+    glmm["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": 10}}, "tau_squared": 0.25, "slopes": [],
+                       "extra_groupings": []}
     with pytest.raises(M.Unsupported):
-        M.run_batch(mle, [50], 10, SEED)
+        M.run_batch(glmm, [50], 10, SEED)
     r = M.run_batch(s, [50], 0, SEED, mode=ALL)  # n_sims == 0 → empty-shaped result (batch.rs:390-421)
     assert r.uncorrected.shape == (0, 1, 2) and r.counters.sum() == 0
 
