@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -654,7 +655,11 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                 Lowered& lwr = lw;
                 const DevicePlan saved = lwr.plan;
                 lwr.plan = shifted;
-                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch, lmm_scratch};
+                static const int ols_variant = [] {
+                    const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT");
+                    return e && e[0] == '2' ? 2 : 1;
+                }();
+                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch, lmm_scratch, ols_variant};
                 dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }

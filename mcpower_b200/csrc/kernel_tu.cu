@@ -47,7 +47,16 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
 #else
-    if (scen) {
+    if (a.ols_variant == 2) {
+        const uint32_t blocks2 = (a.n_sims + MCP_BLOCK / 2 - 1) / (MCP_BLOCK / 2);
+        if (scen) {
+            cudaFuncSetAttribute(ols_power_kernel_g2<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_g2<PT, true><<<blocks2, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+        } else {
+            cudaFuncSetAttribute(ols_power_kernel_g2<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_g2<PT, false><<<blocks2, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+        }
+    } else if (scen) {
         cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         ols_power_kernel<PT, true><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
     } else {

@@ -17,6 +17,7 @@ struct KernelArgs {
     cudaStream_t stream;
     float* scratch;          // GLM: per-wave f32 data plane [row][col][sim]
     double* scratch_d;       // LMM: per-wave cluster sums [cluster][col][sim]
+    int ols_variant;         // 1 = one thread per study, 2 = lane pair per study (reflected half-triangles)
 };
 
 // Each returns false when P is outside the TU's range; otherwise *err holds the launch status.
