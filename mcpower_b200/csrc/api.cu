@@ -633,6 +633,28 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
             lmm_scratch = lw.bufs.alloc<double>((size_t)wave * nc_cap * (lw.P + 1));
         }
+        // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
+        //   5 lean path — plain linear models (Normal marginals/residual, no factors/cluster/scenario): lane-quad
+        //     generate+accumulate kernel leaves X'X|X'y|y'y per fit in HBM, a thread-per-fit kernel solves;
+        //   4 general quad kernel — opt-in;  1 thread-per-study kernel — everything else.
+        // MCPOWER_B200_OLS_VARIANT=1|4|5 forces one where eligible (read per call).
+        const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
+                             pl.n_factors == 0 && pl.residual_dist == R_NORMAL && !pl.has_cluster;
+        int ols_variant = lean_ok ? 5 : 1;
+        if (const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT")) {
+            if (e[0] == '1') ols_variant = 1;
+            else if (e[0] == '4') ols_variant = 4;
+            else if (e[0] == '5') ols_variant = lean_ok ? 5 : 4;
+        }
+        if (kind == KIND_OLS && ols_variant == 5) {
+            // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB
+            const size_t E = (size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1;
+            const size_t per_sim = (size_t)n_ss * E * sizeof(double);
+            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / per_sim, 128);
+            wave = std::min(wave, cap);
+            if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
+            lmm_scratch = lw.bufs.alloc<double>((size_t)wave * n_ss * E);
+        }
         CUDA_CHECK(cudaEventRecord(e0, st));
         bool cancelled = false;
         for (uint64_t done = 0; done < n_sims;) {
@@ -655,15 +677,11 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                 Lowered& lwr = lw;
                 const DevicePlan saved = lwr.plan;
                 lwr.plan = shifted;
-                static const int ols_variant = [] {
-                    const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT");
-                    return e && e[0] == '2' ? 2 : 1;
-                }();
                 KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch, lmm_scratch, ols_variant};
                 dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }
-            r->gpu_launches++;
+            r->gpu_launches += (kind == KIND_OLS && ols_variant == 5) ? 2 : 1;
             done += cnt;
             if (progress) {
                 CUDA_CHECK(cudaStreamSynchronize(st));

@@ -121,7 +121,9 @@ __device__ __forceinline__ void ni_central_pair(float v0, float v1, float& z0, f
 #undef MCP_H2
 
 // tail branch (|v| > BP): copysign(Pt(sqrt(-2 ln_f32(max(0.5-|v|, 2^-25)))), v)
-static __device__ __noinline__ float ni_tail(float v) {
+__device__ __forceinline__ float ni_tail_inl(float v);
+static __device__ __noinline__ float ni_tail(float v) { return ni_tail_inl(v); }
+__device__ __forceinline__ float ni_tail_inl(float v) {
     const float a = fabsf(v);
     float t = 0.5f - a;
     t = fmaxf(t, MCP_NI_FLOOR);

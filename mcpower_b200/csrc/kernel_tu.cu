@@ -1,6 +1,10 @@
 // kernel_tu.cu — one kernel translation unit: instantiates the power kernels for P in [MCP_P_LO, MCP_P_HI].
 // Compiled several times in parallel (mcpower_b200/build.py).  MCP_TU_GLM selects the GLM kernels.
 #include "kernels.cuh"
+#if !defined(MCP_TU_GLM) && !defined(MCP_TU_LMM)
+#include "kernels_q4.cuh"
+#include "kernels_lean.cuh"
+#endif
 #ifdef MCP_TU_GLM
 #include "kernels_glm.cuh"
 #endif
@@ -47,14 +51,35 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
 #else
-    if (a.ols_variant == 2) {
-        const uint32_t blocks2 = (a.n_sims + MCP_BLOCK / 2 - 1) / (MCP_BLOCK / 2);
-        if (scen) {
-            cudaFuncSetAttribute(ols_power_kernel_g2<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_power_kernel_g2<PT, true><<<blocks2, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+    if (a.ols_variant == 5) {  // plain-linear-model family: generate + accumulate per lane quad, then one thread per fit
+        using G = LeanGeom<PT>;
+        const size_t smem5 = G::smem_bytes();
+        const uint32_t blocks5 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
+        if (pl.n_inter > 0) {
+            cudaFuncSetAttribute(ols_lean_kernel<PT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_lean_kernel<PT, true, true><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        } else if (!pl.l_identity) {
+            cudaFuncSetAttribute(ols_lean_kernel<PT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_lean_kernel<PT, true, false><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
         } else {
-            cudaFuncSetAttribute(ols_power_kernel_g2<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_power_kernel_g2<PT, false><<<blocks2, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+            cudaFuncSetAttribute(ols_lean_kernel<PT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_lean_kernel<PT, false, false><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
+        const dim3 grid_s((a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK, (unsigned)pl.n_ss);
+        ols_solve_kernel<PT><<<grid_s, MCP_BLOCK, smem_s, a.stream>>>(a.n_sims, a.scratch_d);
+    } else if (a.ols_variant == 4) {  // one study per lane quad (kernels_q4.cuh)
+        using G = Q4Geom<PT>;
+        const size_t smem4 = G::smem_bytes(pl.n_ss, pl.counter_width, pl.smem_counters != 0);
+        const uint32_t blocks4 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
+        if (scen) {
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, true><<<blocks4, MCP_BLOCK, smem4, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+        } else {
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, false><<<blocks4, MCP_BLOCK, smem4, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
         }
     } else if (scen) {
         cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -568,12 +568,9 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
 
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
-// PAIR: the study is shared by a lane pair (ols_power_kernel_g2): lane h generates the column tasks t ≡ h (mod 2) and,
-// after a warp sync, finishes rows 2h and 2h+1 of the per-row phases; PAIR = false → one thread does everything.
-template <int PT, bool SCEN, typename SlabT, bool PAIR = false>
-__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd, int h = 0) {
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
     constexpr int KT = ScenDesign<PT>::KT;
-    const int t0 = PAIR ? h : 0, tstep = PAIR ? 2 : 1, r0 = PAIR ? 2 * h : 0, r1 = PAIR ? 2 * h + 2 : 4;
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
     const uint32_t k0 = cx.k0, k1 = cx.k1;
@@ -587,7 +584,7 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
                                (pl.outcome == O_BINARY && !pl.link_probit);
     const int n_tasks = uniform_slot0 ? k : k + 1;
 #pragma unroll kUnrollTasks
-    for (int t = t0; t < n_tasks; t += tstep) {
+    for (int t = 0; t < n_tasks; t++) {
         const bool is_x = t < k;
         const U4 w = philox4x32_10((uint32_t)b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, k0, k1);
         const int c = is_x ? t : PT - 1;
@@ -613,7 +610,7 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
         slab[4 * c + 2] = z.z;
         slab[4 * c + 3] = z.w;
     }
-    if (uniform_slot0 && (!PAIR || (k & 1) == h)) {
+    if (uniform_slot0) {
         const U4 w = philox4x32_10((uint32_t)b, 0u, 2u, 0u, k0, k1);
         float4 z;
         if (pl.outcome == O_CONTINUOUS) {  // Uniform residual: (2u-1)*sqrt(3) (data_gen.rs:485-501)
@@ -640,15 +637,14 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
         const int idx = (c == 15 ? (PT - 1) : c) * 4 + (bit & 3);
         slab[idx] = ni_tail(slab[idx]);
     }
-    if (PAIR) __syncwarp(3u << ((threadIdx.x & 31u) & ~1u));
     // ---- B'. t / chi-square residuals need extra CLASS_RESID slots
     if (pl.outcome == O_CONTINUOUS && residual_dist != R_NORMAL && residual_dist != R_UNIFORM) {
-        for (int r = r0; r < r1; r++)
+        for (int r = 0; r < 4; r++)
             slab[4 * (PT - 1) + r] = transform_residual(residual_dist, pl.residual_df, slab[4 * (PT - 1) + r], (uint32_t)b, r, k0, k1);
     }
     // ---- C. Cholesky mix + marginal transforms (data_gen.rs:334-363); skipped when L = I and all Normal
     if (SCEN || !(pl.l_identity && pl.all_normal)) {
-        for (int r = r0; r < r1; r++) {
+        for (int r = 0; r < 4; r++) {
             double zr[PT];  // zr[j] = z of continuous column j (j < k)
 #pragma unroll
             for (int j = 0; j < PT - 1; j++) zr[j] = j < k ? (double)slab[4 * j + r] : 0.0;
@@ -668,7 +664,7 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
     }
     // ---- D. factor dummies (data_gen.rs:509-551) and interactions (643-649), in the f32 plane
     if (pl.n_factors > 0 || pl.n_inter > 0) {
-        for (int r = r0; r < r1; r++) {
+        for (int r = 0; r < 4; r++) {
             const int row = 4 * b + r;
             if (row >= pl.max_n) break;
             int sidx = 0;
@@ -898,158 +894,6 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
 #pragma unroll
                     for (int i = 0; i < PT; i++) st[NACC + i] = xty[i];
                     ols_fit_and_emit<PT>(st, yty, sum_y, n_rows, so, g, lvl_counts, excl, track_excl);
-                    g++;
-                    n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
-                }
-            }
-        }
-    }
-    if (cnt_s) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
-            const unsigned v = cnt_s[i];
-            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// The OLS power kernel, lane-pair variant (G2): one simulated study per PAIR of adjacent lanes.
-//
-// Why: with one study per thread the 56 FP64 accumulators (P = 9) pin the kernel at 255 registers → 2 warps per
-// scheduler → ~49 % issue utilisation (profiles/r01b_critical_path.md).  Here lane h ∈ {0,1} of the pair
-//   * generates the column tasks t ≡ h (mod 2) (Philox + inverse normal), then — after a warp sync — finishes rows
-//     2h, 2h+1 of the per-row phases and assembles their y (linear predictor in the canonical order);
-//   * accumulates HALF of the X'X triangle with the reflected-triangle trick: lane 1 loads the row in REVERSED column
-//     order, xq[j] = x[P−1−j], and both lanes run the same instruction stream over local entries (a, c), c ≤ a,
-//     a + c ≤ P−1; for lane 1 that is the true entry (P−1−c, P−1−a), i.e. the other half of the triangle (the
-//     anti-diagonal is computed twice).  X'y is split the same way; y'y and Σy are computed by both.
-// Every accumulator is still one sequential fma chain over the rows, so the results are bit-identical to the
-// one-thread kernel and to the oracle.  At a grid point lane 1 hands its half to lane 0 by shuffle and lane 0 runs
-// the solve.  32 instead of 56 accumulators per thread → ≤128 registers → 4 warps per scheduler.
-
-template <int PT, bool SCEN>
-__global__ void __launch_bounds__(MCP_BLOCK, 4) ols_power_kernel_g2(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
-    constexpr int NACC = PT * (PT + 1) / 2;
-    constexpr int SP = PT | 1;
-    constexpr int HALF = (PT + 1) / 2;  // X'y entries per lane: local a = 0..HALF-1
-    constexpr int PAIRS = MCP_BLOCK / 2;
-    const DevicePlan& pl = c_plan;
-    extern __shared__ __align__(16) float smem[];
-    const int h = threadIdx.x & 1;
-    const Slab<PAIRS> slab{smem + (threadIdx.x >> 1)};
-    unsigned int* cnt_s = nullptr;
-    if (pl.smem_counters) {
-        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)PAIRS * 4 * SP);
-        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
-        __syncthreads();
-    }
-    const uint32_t sim = blockIdx.x * PAIRS + (threadIdx.x >> 1);
-    // pairs never straddle a warp; a pair past the end idles as a whole, so warp-level syncs below see full pairs
-    if (sim < n_sims) {
-        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        SimCtx cx;
-        cx.k0 = (uint32_t)key;
-        cx.k1 = (uint32_t)(key >> 32);
-        cx.seq.init(key);
-        cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
-        cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
-        const int max_n = pl.max_n;
-        SimOut so{cnt_s, (uint64_t)sim};
-        ScenDesign<PT> sdv;
-        ScenDesign<PT>* sd = nullptr;
-        if (SCEN) {
-            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
-            sd = &sdv;
-            if (!sdv.ok) atomicExch(pl.error_flag, 2);
-        }
-        // full-triangle indexing, but only local entries with a + c <= P-1 are ever touched: after unrolling the
-        // untouched elements are dead and take no registers
-        double tri_acc[NACC], xty_acc[PT];
-#pragma unroll
-        for (int i = 0; i < NACC; i++) tri_acc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < PT; i++) xty_acc[i] = 0.0;
-        double yty = 0.0, sum_y = 0.0;
-        uint32_t n_rows = 0;
-        uint32_t lvl_counts[MCP_MAX_LEVELS];
-        uint8_t excl[MCP_MAX_FACTORS];
-        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
-        if (track_excl)
-            for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
-        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
-        int g = 0;
-        uint32_t n_next = pl.ss[0];
-        const int n_blocks = (max_n + 3) >> 2;
-        const unsigned pair_mask = 3u << ((threadIdx.x & 31) & ~1);
-        for (int b = 0; b < n_blocks; b++) {
-            __syncwarp(pair_mask);  // the previous block's row pass has finished reading the slab
-            gen_block<PT, SCEN, Slab<PAIRS>, true>(b, slab, cx, sd, h);
-            // ---- Y. outcome for rows 2h, 2h+1 (canonical column order), parked in the residual slot
-            for (int r = 2 * h; r < 2 * h + 2; r++) {
-                if (4 * b + r >= max_n) break;
-                double xr[PT];
-                const double yd = row_xy<PT, SCEN>(b, r, slab, cx, xr, sd);
-                slab[4 * (PT - 1) + r] = (float)yd;
-            }
-            __syncwarp(pair_mask);
-            // ---- E. row pass on the reflected half-triangle
-#pragma unroll 1
-            for (int r = 0; r < 4; r++) {
-                const int row = 4 * b + r;
-                if (row >= max_n) break;
-                double xq[PT];
-                if (PT == 1) {
-                    xq[0] = 1.0;
-                } else {
-                    const double v_last = (double)slab[4 * (PT - 2) + r];  // design column P-1
-                    xq[0] = h ? v_last : 1.0;
-                    xq[PT - 1] = h ? 1.0 : v_last;
-#pragma unroll
-                    for (int j = 1; j < PT - 1; j++) xq[j] = (double)slab[4 * ((h ? PT - 1 - j : j) - 1) + r];
-                }
-                const double yd = (double)slab[4 * (PT - 1) + r];
-#pragma unroll
-                for (int a = 0; a < PT; a++) {
-#pragma unroll
-                    for (int c = 0; c <= a; c++)
-                        if (a + c <= PT - 1) tri_acc[tri(a, c)] = fma(xq[a], xq[c], tri_acc[tri(a, c)]);
-                    if (a < HALF) xty_acc[a] = fma(xq[a], yd, xty_acc[a]);
-                }
-                yty = fma(yd, yd, yty);
-                sum_y += yd;
-                n_rows++;
-                if (track_excl && h == 0) {
-                    for (int f = 0; f < pl.n_factors; f++) {
-                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
-                        int lvl = 0;
-                        for (int d = 0; d < nl - 1; d++)
-                            if (slab[4 * (c0 + d) + r] == 1.0f) { lvl = d + 1; break; }
-                        lvl_counts[pl.f_off[f] + lvl]++;
-                    }
-                }
-                if ((uint32_t)(row + 1) == n_next) {
-                    // ---- fit at grid point g: lane 1 hands its half over, lane 0 assembles the full system in memory
-                    double st[NACC + PT];
-#pragma unroll
-                    for (int a = 0; a < PT; a++) {
-#pragma unroll
-                        for (int c = 0; c <= a; c++) {
-                            if (a + c <= PT - 1) {
-                                st[tri(a, c)] = tri_acc[tri(a, c)];
-                            } else {  // true (a, c) is lane 1's local (P-1-c, P-1-a)
-                                const double v = tri_acc[tri(PT - 1 - c, PT - 1 - a)];
-                                st[tri(a, c)] = __shfl_down_sync(pair_mask, v, 1);
-                            }
-                        }
-                        if (a < HALF) {
-                            st[NACC + a] = xty_acc[a];
-                        } else {
-                            const double v = xty_acc[PT - 1 - a];
-                            st[NACC + a] = __shfl_down_sync(pair_mask, v, 1);
-                        }
-                    }
-                    if (h == 0) ols_fit_and_emit<PT>(st, yty, sum_y, n_rows, so, g, lvl_counts, excl, track_excl);
                     g++;
                     n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
                 }

@@ -1,0 +1,299 @@
+// kernels_lean.cuh — the headline kernel: OLS power for the "plain linear model" spec family, one simulated study
+// per lane quad, written for a small register footprint (4–5 warps per scheduler) and a short instruction stream.
+//
+// Spec family (host-checked, api.cu lean_eligible()): OLS, continuous outcome, optimistic scenario, Normal
+// marginals, Normal residual, no factors, no cluster; correlated predictors (MIX) and interaction columns (INTER)
+// are compile-time options.  BASELINE.json's metric shape (n = 500, 8 N(0,1) predictors, P = 9) and config 1
+// (y ~ x1 + x2 + x1:x2) are in the family; everything else runs on the general kernels (kernels.cuh /
+// kernels_q4.cuh).  Arithmetic and operation order are those of the general kernels and of the oracle — the data
+// plane follows rng.rs:154-364 / data_gen.rs:334-363,643-649,781-888, the statistics are one sequential fma chain per
+// accumulator — so every output bit is the same whichever kernel runs (tests/test_gpu_parity.py runs all of them on
+// the same inputs).
+//
+// Work split inside a quad (lane q = threadIdx & 3), per "quad step" of 16 rows:
+//   A. lane q generates Philox block 4·sb + q (rows 16·sb + 4q … +3) for every column: one Philox4x32-10 call →
+//      4 words → 4 inverse-normal draws (packed f32x2 Horner: FMUL2 for the product, FFMA2(acc, 1.0, c) for the
+//      separately rounded add — bit-identical to mul + add, half the issue slots) → one STS.128 into the warp's f32
+//      slab.  Tail draws (4.85 %) are flagged in a bit mask and patched afterwards (B).
+//   C. four sub-steps qq = 0..3: lane q finishes row 16·sb + 4·qq + q from lane qq's slab entries — widen to f64
+//      ONCE, Cholesky mix (MIX), interaction products (INTER), linear predictor, y — and stages the row in shared
+//      memory as Z = [1 | x | y] in f64, low half forwards + high half reversed (kernels_q4.cuh explains the
+//      reflected-quarter trick);
+//   D. all four lanes run the same 4-row accumulation pattern on their quarter of Z'Z (M(M+1)/2 accumulators per
+//      lane: 15 at P = 9 instead of 56 per thread).
+// At a grid point the quad hands its entries to lane 0 by shuffle and lane 0 solves (ols_fit_and_emit).
+//
+// Slab layout (per warp, floats): [column c][producer lane qq][slot i ^ 2·qq][row r], i = quad index in the warp.
+// The XOR swizzle makes both the producer's STS.128 (8 lanes of a quarter-warp → 8 distinct 16-byte slots) and the
+// consumer's LDS.32 (32 lanes → 32 distinct banks) conflict-free.
+#pragma once
+#include "kernels_q4.cuh"
+
+namespace mcp {
+
+#ifndef MCP_LEAN_MIN_BLOCKS
+#define MCP_LEAN_MIN_BLOCKS 4
+#endif
+#ifndef MCP_LEAN_UNROLL
+#define MCP_LEAN_UNROLL 2
+#endif
+
+// ---- packed f32x2 helpers.  fma.rn.f32x2 with addend -0.0 is a correctly rounded product (ptxas emits FMUL2);
+// with multiplier 1.0 it is a correctly rounded sum (FFMA2 with a scalar 1.0 and an immediate addend).  Neither can
+// be contracted with its neighbour, unlike mul.rn.f32x2 + add.rn.f32x2 (see device_math.cuh).
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long bcast2(float c) { return pack2(c, c); }
+__device__ __forceinline__ unsigned long long mul2x(unsigned long long a, unsigned long long b) { return fma2(a, b, bcast2(-0.0f)); }
+__device__ __forceinline__ unsigned long long add2c(unsigned long long a, float c) { return fma2(a, bcast2(1.0f), bcast2(c)); }
+
+// Two words → two v = u − ½ (word_to_v) → central polynomial, packed.  Returns z (central value) and v.
+__device__ __forceinline__ void ni_central_pair_packed(uint32_t w0, uint32_t w1, float& z0, float& z1, float& v0, float& v1) {
+    const unsigned long long f = pack2(__uint_as_float(0x3f800000u | (w0 >> 9)), __uint_as_float(0x3f800000u | (w1 >> 9)));
+    const unsigned long long vv = add2c(add2c(f, -1.5f), 5.9604644775390625e-08f);
+    const unsigned long long r = mul2x(vv, vv);
+    unsigned long long a = mul2x(bcast2(2.401336800e+08f), r);
+    a = add2c(a, -2.359132160e+08f);
+#define MCP_HS(c)     \
+    a = mul2x(a, r);  \
+    a = add2c(a, c);
+    MCP_HS(9.886485600e+07f)
+    MCP_HS(-2.294391600e+07f)
+    MCP_HS(3.215264750e+06f)
+    MCP_HS(-2.779154375e+05f)
+    MCP_HS(1.463396387e+04f)
+    MCP_HS(-4.216123047e+02f)
+    MCP_HS(1.238584900e+01f)
+    MCP_HS(2.586458445e+00f)
+    MCP_HS(2.506664753e+00f)
+#undef MCP_HS
+    a = mul2x(vv, a);
+    unpack2(a, z0, z1);
+    unpack2(vv, v0, v1);
+}
+
+// Philox4x32-10 with the 10 round keys precomputed per study (rk[2r] = k0 + r·W0, rk[2r+1] = k1 + r·W1).
+__device__ __forceinline__ U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
+constexpr int kLeanUnroll = MCP_LEAN_UNROLL;
+
+template <int PT>
+struct LeanGeom : Q4Geom<PT> {
+    static constexpr int SLAB_WARP = PT * 128;  // floats per warp: [PT columns][4 producers][8 slots][4 rows]
+    static constexpr int E = PT * (PT + 1) / 2 + PT + 1;  // statistics per fit: X'X (packed lower) | X'y | y'y
+    static size_t smem_bytes() {
+        return (size_t)(MCP_BLOCK / 32) * SLAB_WARP * sizeof(float) + (size_t)Q4Geom<PT>::STUDIES * Q4Geom<PT>::STUDY * sizeof(double);
+    }
+};
+
+template <int PT, bool MIX, bool INTER>
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, double* __restrict__ stats) {
+    using G = LeanGeom<PT>;
+    constexpr int NACC = PT * (PT + 1) / 2;
+    constexpr int N = G::N, M = G::M, MH = G::MH;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    const int q = threadIdx.x & 3;
+    const int qi = (threadIdx.x & 31) >> 2;  // quad index inside the warp
+    float* const wslab = smem + (size_t)(threadIdx.x >> 5) * G::SLAB_WARP;
+    double* const stage_all = reinterpret_cast<double*>(smem + (size_t)(MCP_BLOCK / 32) * G::SLAB_WARP);
+    double* const stage = stage_all + (size_t)(threadIdx.x >> 2) * G::STUDY;
+    const uint32_t sim = blockIdx.x * G::STUDIES + (threadIdx.x >> 2);
+    if (sim < n_sims) {  // quads never straddle a warp; a quad past the end idles as a whole
+        const unsigned qmask = 0xFu << ((threadIdx.x & 31u) & ~3u);
+        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+        uint32_t rk[20];
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            rk[2 * r] = (uint32_t)key + (uint32_t)r * 0x9E3779B9u;
+            rk[2 * r + 1] = (uint32_t)(key >> 32) + (uint32_t)r * 0xBB67AE85u;
+        }
+        const int max_n = pl.max_n;
+        const int k = INTER ? pl.k : PT - 1;  // no factors in this family: P = 1 + k + n_inter
+        double acc[G::NACCQ];
+#pragma unroll
+        for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
+        int g = 0;
+        uint32_t n_next = pl.ss[0];
+        const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
+        const double* const r_base = stage + (q >= 2 ? MH : 0);
+        float* const own = wslab + q * 32 + ((qi ^ (2 * q)) << 2);  // + 128·column: this lane's float4 of 4 rows
+        const int n_qsteps = (max_n + 15) >> 4;
+        for (int sb = 0; sb < n_qsteps; sb++) {
+            // ---- A. generate Philox block 4·sb + q for every column
+            if (16 * sb + 4 * q < max_n) {
+                const uint32_t b = (uint32_t)(4 * sb + q);
+                unsigned long long tmask = 0ull;
+#pragma unroll kLeanUnroll
+                for (int t = 0; t <= k; t++) {
+                    const bool is_x = t < k;
+                    const U4 w = philox4x32_10_rk(b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, rk);
+                    float4 z;
+                    float v0, v1, v2, v3;
+                    ni_central_pair_packed(w.x, w.y, z.x, z.y, v0, v1);
+                    ni_central_pair_packed(w.z, w.w, z.z, z.w, v2, v3);
+                    unsigned tb = 0u;
+                    if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
+                    if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
+                    if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
+                    if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
+                    tmask |= (unsigned long long)tb << (is_x ? 4 * t : 60);
+                    *reinterpret_cast<float4*>(own + 128 * (is_x ? t : PT - 1)) = z;
+                }
+                // ---- B. deferred tail branch of the inverse-normal kernel (rng.rs:354-364)
+                while (tmask) {
+                    const int bit = __ffsll((long long)tmask) - 1;
+                    tmask &= tmask - 1ull;
+                    const int c = bit >> 2;
+                    float* const p = own + 128 * (c == 15 ? PT - 1 : c) + (bit & 3);
+                    *p = ni_tail_inl(*p);
+                }
+            }
+            __syncwarp(qmask);
+#pragma unroll 1
+            for (int qq = 0; qq < 4; qq++) {
+                const int row0 = 16 * sb + 4 * qq;
+                if (row0 >= max_n) break;
+                // ---- C. lane q finishes row row0 + q (generated by lane qq) and stages it in f64
+                if (row0 + q < max_n) {
+                    float* const src = wslab + qq * 32 + ((qi ^ (2 * qq)) << 2) + q;  // + 128·column
+                    double z[PT + 1];
+                    z[0] = 1.0;
+                    if (MIX) {  // x_j = f32(Σ_{m<=j} L[j][m] z_m), f64 accumulator, m ascending, no FMA (data_gen.rs:334-363)
+                        double zr[PT];
+#pragma unroll
+                        for (int j = 0; j < PT - 1; j++) zr[j] = j < k ? (double)src[128 * j] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < PT - 1; j++) {
+                            if (j < k) {
+                                double a = 0.0;
+#pragma unroll
+                                for (int m = 0; m <= j; m++) a = a + pl.L[j * MCP_MAX_K + m] * zr[m];
+                                const float xf = (float)a;
+                                if (INTER) src[128 * j] = xf;
+                                z[j + 1] = (double)xf;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PT - 1; j++)
+                            if (j < k) z[j + 1] = (double)src[128 * j];
+                    }
+                    if (INTER) {  // x = f32(Π f64(components)) (data_gen.rs:643-649); columns k+1.. of the design
+#pragma unroll
+                        for (int j = 0; j < PT - 1; j++) {
+                            if (j >= k) {
+                                double prod = 1.0;
+                                for (int c = pl.inter_ptr[j - k]; c < pl.inter_ptr[j - k + 1]; c++)
+                                    prod *= (double)src[128 * (pl.inter_cols[c] - 1)];
+                                const float xf = (float)prod;
+                                src[128 * j] = xf;
+                                z[j + 1] = (double)xf;
+                            }
+                        }
+                    }
+                    double lp = 0.0;
+                    const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
+#pragma unroll
+                    for (int j = 0; j < PT; j++)
+                        if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
+                    const double ef = (double)src[128 * (PT - 1)];
+                    z[PT] = (double)(float)(lp + ef + 0.0);  // same association as row_xy: (lp + e) + u_re, u_re = +0
+                    double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
+#pragma unroll
+                    for (int j = 0; j < MH / 2; j++) {
+                        const int j0 = 2 * j, j1 = 2 * j + 1;
+                        dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
+                        dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                    }
+                }
+                __syncwarp(qmask);
+                // ---- D. row pass: the same local pattern in every lane
+                const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
+                if (nr == 4 && n_next - (uint32_t)row0 > 4u) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < nr; r++) {
+                        q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                        if ((uint32_t)(row0 + r + 1) == n_next) {
+                            // grid point g: every lane writes its quarter of Z'Z straight to the wave's statistics
+                            // buffer, stats[(g·E + e)·n_sims + sim] (coalesced over the studies of a warp); the
+                            // solve runs in ols_solve_kernel, one thread per fit
+                            double* const out = stats + (size_t)g * G::E * n_sims + sim;
+#pragma unroll
+                            for (int a = 0; a < M; a++) {
+#pragma unroll
+                                for (int c = 0; c <= a; c++) {
+                                    const int i = q == 0 ? a : (q == 1 ? N - a : N - c);
+                                    const int j = q == 0 ? c : (q == 1 ? c : (q == 2 ? N - a : a));
+                                    const int e = i < N ? tri(i, j) : NACC + j;  // X'X | X'y | y'y (j == N)
+                                    out[(size_t)e * n_sims] = acc[tri(a, c)];
+                                }
+                            }
+                            g++;
+                            n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+                        }
+                    }
+                }
+                __syncwarp(qmask);
+            }
+        }
+    }
+}
+
+// One OLS fit per thread from the statistics ols_lean_kernel left in HBM: Cholesky, β, σ², t², decisions,
+// corrections, overall F, counters / byte tensors (ols_fit_and_emit — the same code the thread-per-study kernel runs).
+// grid = (⌈n_sims / MCP_BLOCK⌉, n_ss); Σy is X'y[0] (x_0 ≡ 1).
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) ols_solve_kernel(uint32_t n_sims, const double* __restrict__ stats) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    constexpr int E = LeanGeom<PT>::E;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(smem);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const int g = blockIdx.y;
+    if (sim < n_sims) {
+        const double* const in = stats + (size_t)g * E * n_sims + sim;
+        double st[NACC + PT];
+#pragma unroll
+        for (int e = 0; e < NACC + PT; e++) st[e] = in[(size_t)e * n_sims];
+        const double yty = in[(size_t)(NACC + PT) * n_sims];
+        uint8_t excl[MCP_MAX_FACTORS];
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+        SimOut so{cnt_s, (uint64_t)sim};
+        ols_fit_and_emit<PT>(st, yty, st[NACC], pl.ss[g], so, g, nullptr, excl, false);
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace mcp

@@ -1,0 +1,246 @@
+// kernels_q4.cuh — the OLS power kernel, lane-quad variant (Q4): one simulated study per FOUR adjacent lanes.
+//
+// Why (profiles/r01b_critical_path.md): with one study per thread the P(P+1)/2 + P + 2 FP64 accumulators (56 at P = 9)
+// pin ols_power_kernel at 255 registers → 2 warps per scheduler → ~49 % issue utilisation, and ~88 % of a study's
+// instructions (Philox + inverse normal) run while those 112 registers just sit there.  Here a study's state is spread
+// over a quad, so each thread holds a quarter of the accumulators and the kernel fits 4–5 warps per scheduler:
+//
+//   * generation is split by ROWS, not columns: lane q of the quad runs the unmodified gen_block() for Philox block
+//     4·sb + q (rows 16·sb + 4q … +3) into its own f32 slab — perfectly balanced for any column count;
+//   * rows are then consumed in order, four at a time: in sub-step qq lane q finishes row 16·sb + 4·qq + q from lane
+//     qq's slab (widen to f64 once, linear predictor, outcome — row_xy()) and stages it in shared memory as
+//     Z = [1 | x_1 … x_{P−1} | y] in f64, laid out as [z_0 … z_{M−1} | z_N, z_{N−1}, … z_{N−M+1}] (N = P, M = ⌈(P+1)/2⌉):
+//     the low half forwards and the high half REVERSED;
+//   * every lane accumulates the SAME local pattern acc[a][c] += p[a]·r[c], c ≤ a < M, where p and r are the low
+//     or the reversed-high half depending on the lane:
+//         lane 0: p = lo, r = lo  → Z'Z[a][c]          (top-left triangle)
+//         lane 1: p = hi, r = lo  → Z'Z[N−a][c]        (bottom-left square, on and below its diagonal)
+//         lane 2: p = hi, r = hi  → Z'Z[N−c][N−a]      (bottom-right triangle)
+//         lane 3: p = lo, r = hi  → Z'Z[N−c][a]        (bottom-left square, on and above its diagonal)
+//     one instruction stream, lane-dependent shared-memory base addresses, M(M+1)/2 accumulators per lane (15 at
+//     P = 9).  X'y and y'y are the last row of Z'Z; Σy is its (N, 0) entry (x_0 ≡ 1, so fma(1, y, acc) ≡ acc + y).
+// Every accumulator is still ONE sequential fma chain over the rows, so the statistics are bit-identical to the
+// thread-per-study kernel and to the oracle.  At a grid point the quad hands its entries to lane 0 by shuffle and
+// lane 0 runs the solve (3 of 4 lanes idle there: the host picks this kernel only when fits are rare relative to
+// rows — single-N power runs like the headline shape; dense sample-size sweeps keep the thread-per-study kernel).
+#pragma once
+#include "kernels.cuh"
+
+namespace mcp {
+
+#ifndef MCP_Q4_MIN_BLOCKS
+#define MCP_Q4_MIN_BLOCKS 4
+#endif
+
+template <int PT>
+struct Q4Geom {
+    static constexpr int N = PT;                 // index of y in Z
+    static constexpr int M = (PT + 2) / 2;       // slots per half = ceil((P+1)/2)
+    static constexpr int MH = (M + 1) & ~1;      // padded to an even count (16-byte vector loads)
+    static constexpr int ROW = 2 * MH;           // doubles per staged row
+    static constexpr int STUDY = 4 * ROW + 2;    // doubles per study: 4 staged rows + 16 B, so adjacent quads are 4 banks apart
+    static constexpr int NACCQ = M * (M + 1) / 2;
+    static constexpr int STUDIES = MCP_BLOCK / 4;
+    // owner lane / local (a, c) of the true entry Z'Z[i][j], j <= i <= N
+    __host__ __device__ static constexpr int owner(int i, int j) {
+        return i < M ? 0 : (j >= N - M + 1 ? 2 : (j <= N - i ? 1 : 3));
+    }
+    __host__ __device__ static constexpr int la(int i, int j) {
+        return i < M ? i : (j >= N - M + 1 ? N - j : (j <= N - i ? N - i : j));
+    }
+    __host__ __device__ static constexpr int lc(int i, int j) {
+        return i < M ? j : (j >= N - M + 1 ? N - i : (j <= N - i ? j : N - i));
+    }
+    static size_t smem_bytes(int n_ss, int counter_width, bool smem_counters) {
+        size_t b = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float) + (size_t)STUDIES * STUDY * sizeof(double);
+        if (smem_counters) b += (size_t)n_ss * counter_width * sizeof(unsigned);
+        return b;
+    }
+};
+
+// One staged row into the lane's local pattern: acc[a][c] += p[a]·r[c], c <= a < M.
+template <int PT>
+__device__ __forceinline__ void q4_acc_row(const double* __restrict__ prow, const double* __restrict__ rrow,
+                                           double (&acc)[Q4Geom<PT>::NACCQ]) {
+    constexpr int M = Q4Geom<PT>::M, MH = Q4Geom<PT>::MH;
+    double pv[MH], rv[MH];
+    const double2* const pp = reinterpret_cast<const double2*>(prow);
+    const double2* const rp = reinterpret_cast<const double2*>(rrow);
+#pragma unroll
+    for (int j = 0; j < MH / 2; j++) {
+        const double2 a2 = pp[j], b2 = rp[j];
+        pv[2 * j] = a2.x;
+        pv[2 * j + 1] = a2.y;
+        rv[2 * j] = b2.x;
+        rv[2 * j + 1] = b2.y;
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+#pragma unroll
+        for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(pv[a], rv[c], acc[tri(a, c)]);
+    }
+}
+
+// Hand the quad's accumulators to every lane (lane 0 uses them): loop over the LOCAL pattern (static register
+// indices) and the four owners; the true Z'Z index only addresses the memory-resident st[] array.
+//   owner 0: Z'Z[a][c]   owner 1: Z'Z[N-a][c]   owner 2: Z'Z[N-c][N-a]   owner 3: Z'Z[N-c][a]
+template <int PT>
+__device__ __forceinline__ void q4_gather(const double (&acc)[Q4Geom<PT>::NACCQ], unsigned qmask, double* st, double& yty) {
+    constexpr int N = Q4Geom<PT>::N, M = Q4Geom<PT>::M, NACC = PT * (PT + 1) / 2;
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+#pragma unroll
+        for (int c = 0; c <= a; c++) {
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                const double v = __shfl_sync(qmask, acc[tri(a, c)], o, 4);
+                const int i = o == 0 ? a : (o == 1 ? N - a : N - c);
+                const int j = o == 0 ? c : (o == 1 ? c : (o == 2 ? N - a : a));
+                if (i < N) st[tri(i, j)] = v;
+                else if (j < N) st[NACC + j] = v;
+                else yty = v;
+            }
+        }
+    }
+}
+
+// Per-level counts of slab row r (batch.rs:2451-2496); each lane of the quad counts one row of a sub-step.
+static __device__ __noinline__ void q4_count_levels(const Slab<MCP_BLOCK> ps, int r, uint32_t* lvl_counts) {
+    const DevicePlan& pl = c_plan;
+    for (int f = 0; f < pl.n_factors; f++) {
+        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
+        int lvl = 0;
+        for (int d = 0; d < nl - 1; d++)
+            if (ps[4 * (c0 + d) + r] == 1.0f) { lvl = d + 1; break; }
+        lvl_counts[pl.f_off[f] + lvl]++;
+    }
+}
+
+template <int PT, bool SCEN>
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel_q4(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
+    using G = Q4Geom<PT>;
+    constexpr int NACC = PT * (PT + 1) / 2;
+    constexpr int SP = PT | 1;
+    constexpr int N = G::N, M = G::M, MH = G::MH;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    const int q = threadIdx.x & 3;
+    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    double* const stage = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)(threadIdx.x >> 2) * G::STUDY;
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * G::STUDIES + (threadIdx.x >> 2);
+    // quads never straddle a warp; a quad past the end idles as a whole, so the quad-masked syncs below see full quads
+    if (sim < n_sims) {
+        const unsigned qmask = 0xFu << ((threadIdx.x & 31u) & ~3u);
+        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+        SimCtx cx;
+        cx.k0 = (uint32_t)key;
+        cx.k1 = (uint32_t)(key >> 32);
+        cx.seq.init(key);
+        cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
+        cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
+        const int max_n = pl.max_n;
+        SimOut so{cnt_s, (uint64_t)sim};
+        ScenDesign<PT> sdv;
+        ScenDesign<PT>* sd = nullptr;
+        if (SCEN) {  // every lane of the quad derives the same per-study design (pure function of the sim id)
+            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+            sd = &sdv;
+            if (!sdv.ok) atomicExch(pl.error_flag, 2);
+        }
+        double acc[G::NACCQ];
+#pragma unroll
+        for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
+        uint32_t lvl_counts[MCP_MAX_LEVELS];  // this lane's share (rows with r == q); summed over the quad at a fit
+        uint8_t excl[MCP_MAX_FACTORS];
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        if (track_excl)
+            for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+        int g = 0;
+        uint32_t n_next = pl.ss[0];
+        // lane-dependent halves of the staged row
+        const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
+        const double* const r_base = stage + (q >= 2 ? MH : 0);
+        const int n_qsteps = (max_n + 15) >> 4;
+        for (int sb = 0; sb < n_qsteps; sb++) {
+            if (16 * sb + 4 * q < max_n) gen_block<PT, SCEN>(4 * sb + q, slab, cx, sd);
+            __syncwarp(qmask);
+#pragma unroll 1
+            for (int qq = 0; qq < 4; qq++) {
+                const int row0 = 16 * sb + 4 * qq;
+                if (row0 >= max_n) break;
+                const Slab<MCP_BLOCK> ps{smem + (threadIdx.x & ~3u) + qq};  // slab of the lane that generated these rows
+                // ---- Y. lane q finishes row row0 + q and stages it in f64
+                if (row0 + q < max_n) {
+                    double z[PT + 1];
+                    {
+                        double xr[PT];
+                        const double yd = row_xy<PT, SCEN>(4 * sb + qq, q, ps, cx, xr, sd);
+#pragma unroll
+                        for (int j = 0; j < PT; j++) z[j] = xr[j];
+                        z[PT] = yd;
+                    }
+                    double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
+#pragma unroll
+                    for (int j = 0; j < MH / 2; j++) {
+                        const int j0 = 2 * j, j1 = 2 * j + 1;
+                        dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
+                        dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                    }
+                }
+                __syncwarp(qmask);
+                // ---- E. row pass: the same local pattern in every lane
+                const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
+                if (nr == 4 && n_next - (uint32_t)row0 > 4u) {
+                    // fast path: four rows, no grid point inside
+#pragma unroll
+                    for (int r = 0; r < 4; r++) q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                    if (track_excl) q4_count_levels(ps, q, lvl_counts);
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < nr; r++) {
+                        q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                        if (track_excl && r == q) q4_count_levels(ps, r, lvl_counts);
+                        if ((uint32_t)(row0 + r + 1) == n_next) {
+                            // ---- fit at grid point g: the quad hands its entries to lane 0, which solves through memory
+                            double st[NACC + PT];
+                            double yty = 0.0;
+                            q4_gather<PT>(acc, qmask, st, yty);
+                            uint32_t lc_tot[MCP_MAX_LEVELS];
+                            if (track_excl) {
+                                int n_lv = 0;
+                                for (int f = 0; f < pl.n_factors; f++) n_lv += pl.f_levels[f];
+                                for (int i = 0; i < n_lv; i++) {
+                                    uint32_t v = lvl_counts[i];
+                                    v += __shfl_xor_sync(qmask, v, 1);
+                                    v += __shfl_xor_sync(qmask, v, 2);
+                                    lc_tot[i] = v;
+                                }
+                            }
+                            if (q == 0) ols_fit_and_emit<PT>(st, yty, st[NACC], (uint32_t)(row0 + r + 1), so, g, lc_tot, excl, track_excl);
+                            __syncwarp(qmask);
+                            g++;
+                            n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+                        }
+                    }
+                }
+                __syncwarp(qmask);
+            }
+        }
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace mcp

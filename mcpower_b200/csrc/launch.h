@@ -16,8 +16,8 @@ struct KernelArgs {
     uint32_t n_sims;
     cudaStream_t stream;
     float* scratch;          // GLM: per-wave f32 data plane [row][col][sim]
-    double* scratch_d;       // LMM: per-wave cluster sums [cluster][col][sim]
-    int ols_variant;         // 1 = one thread per study, 2 = lane pair per study (reflected half-triangles)
+    double* scratch_d;       // LMM: per-wave cluster sums [cluster][col][sim]; lean OLS: statistics [grid point][entry][sim]
+    int ols_variant;         // 1 = thread per study (kernels.cuh), 4 = lane quad per study (kernels_q4.cuh), 5 = lean quad (kernels_lean.cuh)
 };
 
 // Each returns false when P is outside the TU's range; otherwise *err holds the launch status.

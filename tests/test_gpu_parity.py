@@ -18,6 +18,21 @@ pytestmark = pytest.mark.gpu
 
 SEED = 0x9E3779B97F4A7C15
 
+# All OLS power kernels (one thread per study / one lane quad per study / the lean quad + solve pair for plain linear
+# models, which falls back to the general quad kernel where a spec is outside its family) must produce the same bits
+# on the same inputs: every run_batch test below runs once per forced kernel choice.  Tests that never reach the OLS power
+# kernel (generated-design dumps, supplied-bytes fits, GLM / LMM arms, host-side errors) run once.
+_NOT_OLS_POWER = ("generated_design", "marginal_transforms", "pinned_residual", "sampled_factors_and_cluster",
+                  "prefix_stability", "fit_on_reference", "design_draw", "logit", "probit", "glm", "lmm", "errors")
+
+
+@pytest.fixture(autouse=True, params=["thread", "quad", "lean"])
+def ols_kernel_choice(request, monkeypatch):
+    if request.param != "thread" and any(t in request.node.name for t in _NOT_OLS_POWER):
+        pytest.skip("does not reach the OLS power kernel")
+    monkeypatch.setenv("MCPOWER_B200_OLS_VARIANT", {"thread": "1", "quad": "4", "lean": "5"}[request.param])
+    return request.param
+
 
 def assert_batch_equal(got: M.BatchResult, want: dict):
     for key in ("uncorrected", "corrected", "converged"):
