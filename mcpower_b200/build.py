@@ -63,9 +63,11 @@ def build(force: bool = False, verbose: bool = False, extra=(), only_tus=None) -
         defs = [f"-DMCP_TU_ID={tid}", f"-DMCP_P_LO={lo}", f"-DMCP_P_HI={hi}"] + ([f"-DMCP_TU_{kind}"] if kind else [])
         obj = OBJ / f"tu{tid}.o"
         jobs.append(([cc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", str(obj), str(CSRC / "kernel_tu.cu")], obj))
+    # only_tus (developer iteration): recompile just these objects ("api" or a TU id) and relink with the cached rest
+    todo = [j for j in jobs if only_tus is None or j[1].stem.replace("tu", "") in only_tus or not j[1].exists()]
     logs = []
-    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-        for out in ex.map(lambda j: _run(j[0], verbose), jobs):
+    with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+        for out in ex.map(lambda j: _run(j[0], verbose), todo):
             logs.append(out)
     _run([cc, "-shared", "-o", str(SO), *[str(j[1]) for j in jobs], "-ccbin", "/usr/bin/g++"], verbose)
     if verbose:
@@ -74,5 +76,10 @@ def build(force: bool = False, verbose: bool = False, extra=(), only_tus=None) -
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ())
+    only = None
+    if "--tus" in sys.argv:
+        only = sys.argv[sys.argv.index("--tus") + 1].split(",")
+    extra = ["-Xptxas", "-v"] if "--ptxas" in sys.argv else []
+    extra += [a for a in sys.argv[1:] if a.startswith("-D")]
+    build(force="--force" in sys.argv or only is not None, verbose=True, extra=extra, only_tus=only)
     print(SO)

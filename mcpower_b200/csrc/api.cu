@@ -817,6 +817,14 @@ int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s) {
                 case 2: pipe_bench_kernel<2><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
                 case 3: pipe_bench_kernel<3><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
                 case 4: pipe_bench_kernel<4><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;
+                case 5: pipe_bench_kernel<5><<<blocks, threads>>>(it, sink); ops_per_iter = 16; break;  // packed instructions
+                case 6: pipe_bench_kernel<6><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;   // IMAD.WIDE (+ IADD)
+                case 7: pipe_bench_kernel<7><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;   // LOP3
+                case 8: pipe_bench_kernel<8><<<blocks, threads>>>(it, sink); ops_per_iter = 16; break;  // packed (+ 16 LOP3)
+                case 10: pipe_bench_kernel<10><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // DFMA (+ LOP3)
+                case 11: pipe_bench_kernel<11><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // DFMA (+ packed FP32)
+                case 12: pipe_bench_kernel<12><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // DFMA (+ IMAD.WIDE, LOP3)
+                case 9: pipe_bench_kernel<9><<<blocks, threads>>>(it, sink); ops_per_iter = 4; break;   // normal draws
                 default: invalid("unknown pipe_bench kind");
             }
         };

@@ -12,6 +12,8 @@
 #include "kernels_lmm.cuh"
 #endif
 #include "launch.h"
+#include <algorithm>
+#include <cstdlib>
 
 #ifndef MCP_TU_ID
 #error "MCP_TU_ID must be defined"
@@ -51,20 +53,29 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
 #else
-    if (a.ols_variant == 5) {  // plain-linear-model family: generate + accumulate per lane quad, then one thread per fit
+    if (a.ols_variant == 5) {  // plain-linear-model family: lane-quad generate + accumulate kernel, then one thread per fit
         using G = LeanGeom<PT>;
         const size_t smem5 = G::smem_bytes();
         const uint32_t blocks5 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
-        if (pl.n_inter > 0) {
-            cudaFuncSetAttribute(ols_lean_kernel<PT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_lean_kernel<PT, true, true><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
-        } else if (!pl.l_identity) {
-            cudaFuncSetAttribute(ols_lean_kernel<PT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_lean_kernel<PT, true, false><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
-        } else {
-            cudaFuncSetAttribute(ols_lean_kernel<PT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_lean_kernel<PT, false, false><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+#define MCP_LAUNCH_LEAN(...)                                                                                              \
+    do {                                                                                                                  \
+        cudaFuncSetAttribute(ols_lean_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5);      \
+        ols_lean_kernel<__VA_ARGS__><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims,        \
+                                                                              a.scratch_d);                               \
+    } while (0)
+        if (pl.n_inter > 0) MCP_LAUNCH_LEAN(PT, true, true);
+        else if (!pl.l_identity) MCP_LAUNCH_LEAN(PT, true, false);
+        else {
+#ifdef MCP_LEAN_TUNE  // tuning build only: MCPOWER_B200_LEAN_TUNE=u<unroll> picks an instantiation at P = 9
+            const char* tune = getenv("MCPOWER_B200_LEAN_TUNE");
+            if (PT == 9 && tune && tune[0] == 'u' && tune[1] == '1') MCP_LAUNCH_LEAN(PT, false, false, 1);
+            else if (PT == 9 && tune && tune[0] == 'u' && tune[1] == '2') MCP_LAUNCH_LEAN(PT, false, false, 2);
+            else if (PT == 9 && tune && tune[0] == 'u' && tune[1] == '4') MCP_LAUNCH_LEAN(PT, false, false, 4);
+            else
+#endif
+                MCP_LAUNCH_LEAN(PT, false, false);
         }
+#undef MCP_LAUNCH_LEAN
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;

@@ -27,7 +27,7 @@
 // The XOR swizzle makes both the producer's STS.128 (8 lanes of a quarter-warp → 8 distinct 16-byte slots) and the
 // consumer's LDS.32 (32 lanes → 32 distinct banks) conflict-free.
 #pragma once
-#include "kernels_q4.cuh"
+#include "kernels.cuh"
 
 namespace mcp {
 
@@ -35,8 +35,9 @@ namespace mcp {
 #define MCP_LEAN_MIN_BLOCKS 4
 #endif
 #ifndef MCP_LEAN_UNROLL
-#define MCP_LEAN_UNROLL 2
+#define MCP_LEAN_UNROLL 3
 #endif
+
 
 // ---- packed f32x2 helpers.  fma.rn.f32x2 with addend -0.0 is a correctly rounded product (ptxas emits FMUL2);
 // with multiplier 1.0 it is a correctly rounded sum (FFMA2 with a scalar 1.0 and an immediate addend).  Neither can
@@ -91,152 +92,218 @@ __device__ __forceinline__ U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_
     return U4{c0, c1, c2, c3};
 }
 
-constexpr int kLeanUnroll = MCP_LEAN_UNROLL;
-
 template <int PT>
-struct LeanGeom : Q4Geom<PT> {
-    static constexpr int SLAB_WARP = PT * 128;  // floats per warp: [PT columns][4 producers][8 slots][4 rows]
+struct LeanGeom {
+    static constexpr int N = PT;                  // index of y in Z = [1 | x_1 .. x_{P-1} | y]
+    static constexpr int M = (PT + 2) / 2;        // slots per half = ceil((P+1)/2)
+    static constexpr int NACCQ = M * (M + 1) / 2; // accumulators per lane
+    static constexpr int MH = (M + 1) & ~1;       // half padded to an even count (16-byte vector loads)
+    static constexpr int ROW = 2 * MH;            // doubles per staged row: [z_0..z_{M-1} pad | z_N, z_{N-1} .. z_{N-M+1} pad]
+    static constexpr int STUDY = 4 * ROW + 2;     // 4 staged rows per study + 16 B: adjacent studies are 4 banks apart
+    static constexpr int STUDIES = MCP_BLOCK / 4; // studies per CTA
+    static constexpr int WARPS = MCP_BLOCK / 32;
+    static constexpr int SLAB_WARP = PT * 128;    // floats per warp: [PT columns][4 producers][8 slots][4 rows]
     static constexpr int E = PT * (PT + 1) / 2 + PT + 1;  // statistics per fit: X'X (packed lower) | X'y | y'y
-    static size_t smem_bytes() {
-        return (size_t)(MCP_BLOCK / 32) * SLAB_WARP * sizeof(float) + (size_t)Q4Geom<PT>::STUDIES * Q4Geom<PT>::STUDY * sizeof(double);
+    static size_t smem_bytes() {  // slabs | staged rows (aliased by the tail queues) | one tail-queue counter per warp
+        return (size_t)WARPS * SLAB_WARP * sizeof(float) + (size_t)STUDIES * STUDY * sizeof(double) + WARPS * sizeof(unsigned);
     }
+    static_assert(8 * STUDY * sizeof(double) >= (size_t)SLAB_WARP * sizeof(unsigned short), "tail queue must fit the staged rows");
 };
 
-template <int PT, bool MIX, bool INTER>
-__global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, double* __restrict__ stats) {
+// One staged row into the lane's local pattern: acc[a][c] += p[a]·r[c], c <= a < M; p and r are the low or the
+// reversed-high half of the row depending on the lane.
+template <int PT>
+__device__ __forceinline__ void lean_acc_row(const double* __restrict__ prow, const double* __restrict__ rrow,
+                                             double (&acc)[LeanGeom<PT>::NACCQ]) {
+    constexpr int M = LeanGeom<PT>::M, MH = LeanGeom<PT>::MH;
+    double pv[MH], rv[MH];
+    const double2* const pp = reinterpret_cast<const double2*>(prow);
+    const double2* const rp = reinterpret_cast<const double2*>(rrow);
+#pragma unroll
+    for (int j = 0; j < MH / 2; j++) {
+        const double2 a2 = pp[j], b2 = rp[j];
+        pv[2 * j] = a2.x;
+        pv[2 * j + 1] = a2.y;
+        rv[2 * j] = b2.x;
+        rv[2 * j + 1] = b2.y;
+    }
+#pragma unroll
+    for (int a = 0; a < M; a++) {
+#pragma unroll
+        for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(pv[a], rv[c], acc[tri(a, c)]);
+    }
+}
+
+// One column task of the generation phase: Philox block b of column t (t == k: the residual) -> 4 packed draws ->
+// the lane's float4 in the slab; tail draws keep v and are flagged in tmask (bits 4t.., residual at 60..).
+template <int PT>
+__device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const uint32_t (&rk)[20], float* own, unsigned long long& tmask) {
+    const bool is_x = t < k;
+    const U4 w = philox4x32_10_rk(b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, rk);
+    float4 z;
+    float v0, v1, v2, v3;
+    ni_central_pair_packed(w.x, w.y, z.x, z.y, v0, v1);
+    ni_central_pair_packed(w.z, w.w, z.z, z.w, v2, v3);
+    unsigned tb = 0u;
+    if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
+    if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
+    if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
+    if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
+    tmask |= (unsigned long long)tb << (is_x ? 4 * t : 60);
+    *reinterpret_cast<float4*>(own + 128 * (is_x ? t : PT - 1)) = z;
+}
+
+// grid = ⌈n_sims / 32⌉ CTAs of MCP_BLOCK threads (32 studies each), 4 CTAs per SM.  All cooperation is inside a warp
+// (8 studies): full-mask warp syncs only, no block-level barrier.
+// Measured alternatives that were slower on B200 (tools/tune_lean.sh, gpurun_out/tune_lean*.log): 3 or 5-6 CTAs per SM;
+// a persistent one-CTA-per-SM variant with staggered warp starts; f32 staging (4x the F2F.F64.F32 count: the FP64
+// pipe is the shared one); 16-row staging with the accumulation fused into the next step's generation code.
+template <int PT, bool MIX, bool INTER, int UNR = MCP_LEAN_UNROLL>
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
+                                                                                  double* __restrict__ stats) {
     using G = LeanGeom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int N = G::N, M = G::M, MH = G::MH;
     const DevicePlan& pl = c_plan;
     extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5;
     const int q = threadIdx.x & 3;
-    const int qi = (threadIdx.x & 31) >> 2;  // quad index inside the warp
-    float* const wslab = smem + (size_t)(threadIdx.x >> 5) * G::SLAB_WARP;
-    double* const stage_all = reinterpret_cast<double*>(smem + (size_t)(MCP_BLOCK / 32) * G::SLAB_WARP);
-    double* const stage = stage_all + (size_t)(threadIdx.x >> 2) * G::STUDY;
-    const uint32_t sim = blockIdx.x * G::STUDIES + (threadIdx.x >> 2);
-    if (sim < n_sims) {  // quads never straddle a warp; a quad past the end idles as a whole
-        const unsigned qmask = 0xFu << ((threadIdx.x & 31u) & ~3u);
-        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        uint32_t rk[20];
+    const int qi = (threadIdx.x & 31) >> 2;  // quad (study) index inside the warp
+    float* const wslab = smem + (size_t)warp * G::SLAB_WARP;
+    double* const stage_all = reinterpret_cast<double*>(smem + (size_t)G::WARPS * G::SLAB_WARP);
+    double* const stage = stage_all + (size_t)(threadIdx.x >> 2) * G::STUDY;  // this study's 4 staged rows
+    unsigned short* const wq = reinterpret_cast<unsigned short*>(stage_all + (size_t)warp * 8 * G::STUDY);
+    unsigned* const wq_cnt = reinterpret_cast<unsigned*>(stage_all + (size_t)G::STUDIES * G::STUDY) + warp;
+    if ((threadIdx.x & 31u) == 0u) *wq_cnt = 0u;
+    __syncwarp();
+    // Every warp runs with all 32 lanes in lock-step (full-mask warp syncs, warp-cooperative tail queue): a quad past
+    // the end of the wave recomputes the last study and simply does not write statistics.
+    const uint32_t sim_raw = blockIdx.x * G::STUDIES + (threadIdx.x >> 2);
+    const bool valid = sim_raw < n_sims;
+    const uint32_t sim = valid ? sim_raw : n_sims - 1;
+    const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+    uint32_t rk[20];
 #pragma unroll
-        for (int r = 0; r < 10; r++) {
-            rk[2 * r] = (uint32_t)key + (uint32_t)r * 0x9E3779B9u;
-            rk[2 * r + 1] = (uint32_t)(key >> 32) + (uint32_t)r * 0xBB67AE85u;
+    for (int r = 0; r < 10; r++) {
+        rk[2 * r] = (uint32_t)key + (uint32_t)r * 0x9E3779B9u;
+        rk[2 * r + 1] = (uint32_t)(key >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+    const int max_n = pl.max_n;
+    const int k = INTER ? pl.k : PT - 1;  // no factors in this family: P = 1 + k + n_inter
+    double acc[G::NACCQ];
+#pragma unroll
+    for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
+    int g = 0;
+    uint32_t n_next = pl.ss[0];
+    const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
+    const double* const r_base = stage + (q >= 2 ? MH : 0);
+    const int own_off = q * 32 + ((qi ^ (2 * q)) << 2);
+    float* const own = wslab + own_off;  // + 128·column: this lane's float4 of 4 rows
+    const int n_qsteps = (max_n + 15) >> 4;
+    for (int sb = 0; sb < n_qsteps; sb++) {
+        // ---- A. generate Philox block 4·sb + q (rows 16·sb + 4q .. +3) for every column
+        unsigned long long tmask = 0ull;
+        if (16 * sb + 4 * q < max_n) {
+            const uint32_t b = (uint32_t)(4 * sb + q);
+#pragma unroll UNR
+            for (int t = 0; t <= k; t++) lean_gen_task<PT>(t, k, b, rk, own, tmask);
         }
-        const int max_n = pl.max_n;
-        const int k = INTER ? pl.k : PT - 1;  // no factors in this family: P = 1 + k + n_inter
-        double acc[G::NACCQ];
+        // ---- B. deferred tail branch of the inverse-normal kernel (rng.rs:354-364), warp-cooperative: a lane sees
+        // Binomial(4(k+1), 0.0485) tail draws per block, so a per-lane loop runs max-over-32-lanes (~5 at k = 8)
+        // iterations of the ~45-instruction tail path with most lanes idle.  Instead every lane queues the slab
+        // offsets of its tail draws (the queue aliases the staged rows, dead in this phase) and the warp drains the
+        // queue 32 entries at a time (~2 iterations).
+        {
+            const int cnt = __popcll(tmask);
+            unsigned slot = cnt ? atomicAdd(wq_cnt, (unsigned)cnt) : 0u;
+            while (tmask) {
+                const int bit = __ffsll((long long)tmask) - 1;
+                tmask &= tmask - 1ull;
+                const int c = bit >> 2;
+                wq[slot++] = (unsigned short)(own_off + 128 * (c == 15 ? PT - 1 : c) + (bit & 3));
+            }
+            __syncwarp();
+            const unsigned total = *(volatile unsigned*)wq_cnt;
+            for (unsigned e = threadIdx.x & 31u; e < total; e += 32u) {
+                float* const p = wslab + wq[e];
+                *p = ni_tail_inl(*p);
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0u) *wq_cnt = 0u;
+        }
+#pragma unroll 1
+        for (int qq = 0; qq < 4; qq++) {
+            const int row0 = 16 * sb + 4 * qq;
+            if (row0 >= max_n) break;
+            // ---- C. lane q finishes row row0 + q (generated by lane qq) — Cholesky mix (MIX), interaction products
+            // (INTER), linear predictor, y — and stages it in f64 (widened ONCE) as [z_0..z_{M-1} | z_N .. z_{N-M+1}]
+            if (row0 + q < max_n) {
+                float* const src = wslab + qq * 32 + ((qi ^ (2 * qq)) << 2) + q;  // + 128·column
+                double z[PT + 1];
+                z[0] = 1.0;
+                if (MIX) {  // x_j = f32(Σ_{m<=j} L[j][m] z_m), f64 accumulator, m ascending, no FMA (data_gen.rs:334-363)
+                    double zr[PT];
 #pragma unroll
-        for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
-        int g = 0;
-        uint32_t n_next = pl.ss[0];
-        const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
-        const double* const r_base = stage + (q >= 2 ? MH : 0);
-        float* const own = wslab + q * 32 + ((qi ^ (2 * q)) << 2);  // + 128·column: this lane's float4 of 4 rows
-        const int n_qsteps = (max_n + 15) >> 4;
-        for (int sb = 0; sb < n_qsteps; sb++) {
-            // ---- A. generate Philox block 4·sb + q for every column
-            if (16 * sb + 4 * q < max_n) {
-                const uint32_t b = (uint32_t)(4 * sb + q);
-                unsigned long long tmask = 0ull;
-#pragma unroll kLeanUnroll
-                for (int t = 0; t <= k; t++) {
-                    const bool is_x = t < k;
-                    const U4 w = philox4x32_10_rk(b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, rk);
-                    float4 z;
-                    float v0, v1, v2, v3;
-                    ni_central_pair_packed(w.x, w.y, z.x, z.y, v0, v1);
-                    ni_central_pair_packed(w.z, w.w, z.z, z.w, v2, v3);
-                    unsigned tb = 0u;
-                    if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
-                    if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
-                    if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
-                    if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
-                    tmask |= (unsigned long long)tb << (is_x ? 4 * t : 60);
-                    *reinterpret_cast<float4*>(own + 128 * (is_x ? t : PT - 1)) = z;
+                    for (int j = 0; j < PT - 1; j++) zr[j] = j < k ? (double)src[128 * j] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < PT - 1; j++) {
+                        if (j < k) {
+                            double a = 0.0;
+#pragma unroll
+                            for (int m = 0; m <= j; m++) a = a + pl.L[j * MCP_MAX_K + m] * zr[m];
+                            const float xf = (float)a;
+                            if (INTER) src[128 * j] = xf;
+                            z[j + 1] = (double)xf;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PT - 1; j++)
+                        if (j < k) z[j + 1] = (double)src[128 * j];
                 }
-                // ---- B. deferred tail branch of the inverse-normal kernel (rng.rs:354-364)
-                while (tmask) {
-                    const int bit = __ffsll((long long)tmask) - 1;
-                    tmask &= tmask - 1ull;
-                    const int c = bit >> 2;
-                    float* const p = own + 128 * (c == 15 ? PT - 1 : c) + (bit & 3);
-                    *p = ni_tail_inl(*p);
+                if (INTER) {  // x = f32(Π f64(components)) (data_gen.rs:643-649); columns k+1.. of the design
+#pragma unroll
+                    for (int j = 0; j < PT - 1; j++) {
+                        if (j >= k) {
+                            double prod = 1.0;
+                            for (int c = pl.inter_ptr[j - k]; c < pl.inter_ptr[j - k + 1]; c++)
+                                prod *= (double)src[128 * (pl.inter_cols[c] - 1)];
+                            const float xf = (float)prod;
+                            src[128 * j] = xf;
+                            z[j + 1] = (double)xf;
+                        }
+                    }
+                }
+                double lp = 0.0;
+                const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
+#pragma unroll
+                for (int j = 0; j < PT; j++)
+                    if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
+                const double ef = (double)src[128 * (PT - 1)];
+                z[PT] = (double)(float)(lp + ef + 0.0);  // same association as row_xy: (lp + e) + u_re, u_re = +0
+                double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
+#pragma unroll
+                for (int j = 0; j < MH / 2; j++) {
+                    const int j0 = 2 * j, j1 = 2 * j + 1;
+                    dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
+                    dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
                 }
             }
-            __syncwarp(qmask);
+            __syncwarp();
+            // ---- D. row pass: the same local pattern in every lane
+            const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
+            if (nr == 4 && n_next - (uint32_t)row0 > 4u) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) lean_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+            } else {
 #pragma unroll 1
-            for (int qq = 0; qq < 4; qq++) {
-                const int row0 = 16 * sb + 4 * qq;
-                if (row0 >= max_n) break;
-                // ---- C. lane q finishes row row0 + q (generated by lane qq) and stages it in f64
-                if (row0 + q < max_n) {
-                    float* const src = wslab + qq * 32 + ((qi ^ (2 * qq)) << 2) + q;  // + 128·column
-                    double z[PT + 1];
-                    z[0] = 1.0;
-                    if (MIX) {  // x_j = f32(Σ_{m<=j} L[j][m] z_m), f64 accumulator, m ascending, no FMA (data_gen.rs:334-363)
-                        double zr[PT];
-#pragma unroll
-                        for (int j = 0; j < PT - 1; j++) zr[j] = j < k ? (double)src[128 * j] : 0.0;
-#pragma unroll
-                        for (int j = 0; j < PT - 1; j++) {
-                            if (j < k) {
-                                double a = 0.0;
-#pragma unroll
-                                for (int m = 0; m <= j; m++) a = a + pl.L[j * MCP_MAX_K + m] * zr[m];
-                                const float xf = (float)a;
-                                if (INTER) src[128 * j] = xf;
-                                z[j + 1] = (double)xf;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < PT - 1; j++)
-                            if (j < k) z[j + 1] = (double)src[128 * j];
-                    }
-                    if (INTER) {  // x = f32(Π f64(components)) (data_gen.rs:643-649); columns k+1.. of the design
-#pragma unroll
-                        for (int j = 0; j < PT - 1; j++) {
-                            if (j >= k) {
-                                double prod = 1.0;
-                                for (int c = pl.inter_ptr[j - k]; c < pl.inter_ptr[j - k + 1]; c++)
-                                    prod *= (double)src[128 * (pl.inter_cols[c] - 1)];
-                                const float xf = (float)prod;
-                                src[128 * j] = xf;
-                                z[j + 1] = (double)xf;
-                            }
-                        }
-                    }
-                    double lp = 0.0;
-                    const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
-#pragma unroll
-                    for (int j = 0; j < PT; j++)
-                        if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
-                    const double ef = (double)src[128 * (PT - 1)];
-                    z[PT] = (double)(float)(lp + ef + 0.0);  // same association as row_xy: (lp + e) + u_re, u_re = +0
-                    double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
-#pragma unroll
-                    for (int j = 0; j < MH / 2; j++) {
-                        const int j0 = 2 * j, j1 = 2 * j + 1;
-                        dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
-                        dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
-                    }
-                }
-                __syncwarp(qmask);
-                // ---- D. row pass: the same local pattern in every lane
-                const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
-                if (nr == 4 && n_next - (uint32_t)row0 > 4u) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
-                } else {
-#pragma unroll 1
-                    for (int r = 0; r < nr; r++) {
-                        q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
-                        if ((uint32_t)(row0 + r + 1) == n_next) {
-                            // grid point g: every lane writes its quarter of Z'Z straight to the wave's statistics
-                            // buffer, stats[(g·E + e)·n_sims + sim] (coalesced over the studies of a warp); the
-                            // solve runs in ols_solve_kernel, one thread per fit
+                for (int r = 0; r < nr; r++) {
+                    lean_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                    if ((uint32_t)(row0 + r + 1) == n_next) {
+                        // grid point g: every lane writes its quarter of Z'Z straight to the wave's statistics buffer,
+                        // stats[(g·E + e)·n_sims + sim] (coalesced over the studies of a warp); the solve runs in
+                        // ols_solve_kernel, one thread per fit
+                        if (valid) {
                             double* const out = stats + (size_t)g * G::E * n_sims + sim;
 #pragma unroll
                             for (int a = 0; a < M; a++) {
@@ -248,13 +315,13 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                                     out[(size_t)e * n_sims] = acc[tri(a, c)];
                                 }
                             }
-                            g++;
-                            n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
                         }
+                        g++;
+                        n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
                     }
                 }
-                __syncwarp(qmask);
             }
+            __syncwarp();
         }
     }
 }

@@ -25,3 +25,19 @@ for k, r in enumerate(ins):
 print("top stall-sample instructions:")
 for k, r in sorted(enumerate(ins), key=lambda kr: -int(kr[1][isamp]))[:int(sys.argv[2]) if len(sys.argv) > 2 else 25]:
     print(f"  #{k:6d} {r[isrc][:70]:70s} exec {int(r[iex]):12d} samples {r[isamp]}")
+
+# stall reasons aggregated by opcode (all samples)
+stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+by_op = {}
+for r in ins:
+    t = r[isrc].split()
+    op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
+    d = by_op.setdefault(op, Counter())
+    for i in stall_cols:
+        v = int(r[i] or 0)
+        if v:
+            d[hdr[i]] += v
+print("stall samples by opcode (top reasons):")
+for op, d in sorted(by_op.items(), key=lambda kv: -sum(kv[1].values()))[:14]:
+    tot_s = sum(d.values())
+    print(f"  {op:10s} {tot_s:8d}  " + "  ".join(f"{k[6:]}={v}" for k, v in d.most_common(5)))
