@@ -9,8 +9,9 @@ collective; the only exchange is one all-reduce of the per-cell integer counters
   value : fits/s from device time (CUDA events on the launch stream, max over ranks)
   e2e   : fits/s through the public API (mcpower_b200.run_batch → C ABI) with host buffers: spec JSON
           parse + lowering + H2D of the plan/tables + kernel + D2H of the counters, wall clock
-  roofline      : FP64-pipe view — algorithmic FP64 flop per fit ÷ measured DFMA peak
-  roofline_issue: instruction-issue view (the real bound) when profiles/inst_per_fit.json exists
+  roofline      : instruction-issue view (the real bound): algorithmic warp-instructions/s ÷ issue peak
+  roofline_fp64 : FP64-pipe view — algorithmic FP64 flop per fit ÷ measured DFMA peak
+  secondary     : BASELINE configs[1] (sample-size sweep, correlated predictors + factor, Bonferroni) fits/s
   cpu_baseline  : the oracle (CPU restatement of the reference algorithm) on all host threads, bounded sample
 
 `--impl reference` times the oracle alone (the Rust engine cannot be built here: no cargo/rustc).
@@ -33,6 +34,7 @@ sys.path.insert(0, str(ROOT))
 N_ROWS = 500
 SIMS_PER_STEP = 1 << 22          # per GPU per step
 FLOP64_PER_FIT = 6.6e4           # 3.3e4 DFMA at n=500, P=9 (identity mix skipped: structural zeros)
+DRAM_BYTES_PER_FIT = 390.0       # ncu dram__bytes_read+write of ols_lean_kernel / studies (profiles/r01c_ncu_summary.md)
 USER_SEED = 2137                 # configs/config.json default seed; base_seed = splitmix64(seed) (find_power.rs:259)
 
 
@@ -103,6 +105,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sims-per-step", type=int, default=SIMS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -212,6 +215,14 @@ def main():
         dfma = M.pipe_bench(0, local_rank)
         peak_tf = 2.0 * dfma / 1e12
         ach_tf = (value / world) * FLOP64_PER_FIT / 1e12
+        # The path is bound by instruction issue / datapath cycles, not by HBM (generated data never leaves the SM) and
+        # not by tensor cores: the headline roofline is the issue roofline,
+        # ALGORITHMIC warp-instructions per fit (2.6e5 thread-instructions) x fits/s against one issue per
+        # scheduler per clock at the SM clock sampled during the timed region.
+        prof = json.loads((ROOT / "profiles" / "inst_per_fit.json").read_text())
+        sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        peak_issue = 148 * 4 * sm_clock_hz
+        ach_issue = (value / world) * prof["algorithmic_thread_inst_per_fit"] / 32.0
         line = {"metric": "ols_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -219,23 +230,30 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_wall / args.steps},
                 "gpu_launches": launches,
-                "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": ach_tf / peak_tf, "traffic": None,
-                             "note": "per GPU; peak = measured DFMA throughput (mcp_pipe_bench kind 0) on this device, "
-                                     "not MEASURED_PEAKS.json (which has no FP64 entry); algorithmic 6.6e4 FP64 flop/fit"},
+                "roofline": {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "Gwarp-inst/s",
+                             "frac": ach_issue / peak_issue,
+                             "traffic": DRAM_BYTES_PER_FIT * per,
+                             "note": "per GPU, dominant kernel ols_lean_kernel (98 % of the step); achieved = algorithmic "
+                                     "2.6e5 thread-instructions per fit (SURVEY 8d) / 32 x fits/s; peak = 148 SMs x 4 schedulers x "
+                                     "SM clock; executed instructions per fit and ncu issue utilisation in profiles/r01c_ncu_summary.md; "
+                                     "traffic = ncu dram bytes (the 448 B of sufficient statistics per fit) x fits per launch",
+                             "executed_warp_inst_per_fit": prof["warp_inst_per_fit"]},
+                "roofline_fp64": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                                  "frac": ach_tf / peak_tf,
+                                  "note": "algorithmic 6.6e4 FP64 flop per fit against the DFMA rate measured on this device "
+                                          "(mcp_pipe_bench kind 0); MEASURED_PEAKS.json has no FP64 entry"},
                 "power_x1_x2": [float(p) for p in power],
                 "wall_ms_per_step": 1e3 * wall / args.steps}
-        ipf = ROOT / "profiles" / "inst_per_fit.json"
-        if ipf.exists():
-            d = json.loads(ipf.read_text())
-            fmul = M.pipe_bench(1, local_rank)
-            sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-            peak_issue = 148 * 4 * sm_clock_hz  # warp-instructions/s at one issue per SMSP per clock
-            ach_issue = (value / world) * d["warp_inst_per_fit"]
-            line["roofline_issue"] = {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
-                                      "unit": "Gwarp-inst/s", "frac": ach_issue / peak_issue,
-                                      "warp_inst_per_fit": d["warp_inst_per_fit"], "source": d.get("source"),
-                                      "fp32_pair_thread_ops_per_s": fmul}
+        if not args.no_secondary:
+            # second headline: BASELINE configs[1] — sample-size sweep 20..1000 step 20, 8 correlated
+            # predictors + 3-level factor, Bonferroni; fits/s = n_sims x n_ss / device time
+            sweep = S.sweep_spec()
+            grid = list(range(20, 1001, 20))
+            M.run_batch(sweep, grid, 4096, seed, device=local_rank)
+            rs = M.run_batch(sweep, grid, 1 << 18, seed, device=local_rank)
+            line["secondary"] = {"workload": "c2_sweep_p11_grid50_bonferroni", "n_sims": 1 << 18, "n_sample_sizes": len(grid),
+                                 "fits_per_s": (1 << 18) * len(grid) / (rs.kernel_ms * 1e-3),
+                                 "sims_per_s": (1 << 18) / (rs.kernel_ms * 1e-3), "n_gpus": 1}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import orc
             v, cores, n_big, dt = cpu_reference(spec, N_ROWS, seed, 12.0, orc)
