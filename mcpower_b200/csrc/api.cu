@@ -53,6 +53,28 @@ struct BufferCache {
 };
 static BufferCache g_cache;
 
+// Wave scratch (GLM data plane, LMM cluster sums, lean-path sufficient statistics): gigabytes per call, so one
+// grow-only arena per device is kept across calls (cudaMalloc/cudaFree of a 2 GB buffer costs milliseconds and
+// synchronises the device).  Batches are serialised by g_plan_mutex, so one arena per device is enough.
+struct ScratchArena {
+    void* p[64] = {};
+    size_t bytes[64] = {};
+    void* get(size_t need) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) throw EngineError(MCP_CUDA_ERROR, "device index out of range");
+        if (bytes[dev] < need) {
+            if (p[dev]) cudaFree(p[dev]);
+            p[dev] = nullptr;
+            bytes[dev] = 0;
+            CUDA_CHECK(cudaMalloc(&p[dev], need));
+            bytes[dev] = need;
+        }
+        return p[dev];
+    }
+};
+static ScratchArena g_scratch;
+
 struct DeviceBuffers {
     struct Owned { void* p; size_t bytes; int dev; };
     std::vector<Owned> owned;
@@ -310,6 +332,7 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     }
     int off = 0, col = 1 + s.k;
     pl.exact_walk = 1;
+    for (int j = 0; j < MCP_MAX_P; j++) pl.col_factor[j] = -1;
     for (int f = 0; f < F; f++) {
         pl.f_levels[f] = s.factor_n_levels[f];
         pl.f_off[f] = off;
@@ -321,6 +344,10 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
             pl.n_sampled_factors++;
         }
         for (int g = 0; g < s.factor_n_levels[f]; g++) pl.f_props[off + g] = s.factor_proportions[off + g];
+        for (int d = 0; d < s.factor_n_levels[f] - 1 && col + d < MCP_MAX_P; d++) {
+            pl.col_factor[col + d] = (int8_t)f;
+            pl.col_level[col + d] = (int8_t)(d + 1);
+        }
         off += s.factor_n_levels[f];
         col += s.factor_n_levels[f] - 1;
     }
@@ -492,6 +519,14 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.crit_overall = lw.bufs.upload(c_ov);
     pl.crit_joint = lw.bufs.upload(c_joint);
     pl.levels = any_exact ? lw.bufs.upload(levels_flat) : nullptr;
+    pl.exact_counts = nullptr;
+    if (F > 0 && pl.exact_walk) {  // exact walks are sim-invariant: the per-level prefix counts at every grid point too
+        std::vector<uint32_t> ec((size_t)n_ss * MCP_MAX_LEVELS, 0);
+        for (uint32_t g = 0; g < n_ss; g++)
+            for (int f = 0; f < F; f++)
+                for (uint32_t i = 0; i < ss[g]; i++) ec[(size_t)g * MCP_MAX_LEVELS + pl.f_off[f] + levels[f][i]]++;
+        pl.exact_counts = lw.bufs.upload(ec);
+    }
     bool need_t3 = false;
     for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
     if (need_t3) pl.t3_table = lw.bufs.upload(crit::build_t3_table());
@@ -620,7 +655,7 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
             wave = std::min(wave, cap);
             wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            glm_scratch = lw.bufs.alloc<float>((size_t)wave * pl.max_n * lw.P);
+            glm_scratch = static_cast<float*>(g_scratch.get((size_t)wave * pl.max_n * lw.P * sizeof(float)));
         }
         double* lmm_scratch = nullptr;
         if (mle) {
@@ -631,15 +666,15 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
             wave = std::min(wave, cap);
             wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            lmm_scratch = lw.bufs.alloc<double>((size_t)wave * nc_cap * (lw.P + 1));
+            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * nc_cap * (lw.P + 1) * sizeof(double)));
         }
         // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
-        //   5 lean path — plain linear models (Normal marginals/residual, no factors/cluster/scenario): lane-quad
+        //   5 lean path — plain linear models (Normal marginals/residual, exact-walk factors, no cluster/scenario): lane-quad
         //     generate+accumulate kernel leaves X'X|X'y|y'y per fit in HBM, a thread-per-fit kernel solves;
         //   4 general quad kernel — opt-in;  1 thread-per-study kernel — everything else.
         // MCPOWER_B200_OLS_VARIANT=1|4|5 forces one where eligible (read per call).
         const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
-                             pl.n_factors == 0 && pl.residual_dist == R_NORMAL && !pl.has_cluster;
+                             (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster;
         int ols_variant = lean_ok ? 5 : 1;
         if (const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT")) {
             if (e[0] == '1') ols_variant = 1;
@@ -653,7 +688,7 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / per_sim, 128);
             wave = std::min(wave, cap);
             if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            lmm_scratch = lw.bufs.alloc<double>((size_t)wave * n_ss * E);
+            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * n_ss * E * sizeof(double)));
         }
         CUDA_CHECK(cudaEventRecord(e0, st));
         bool cancelled = false;

@@ -747,13 +747,13 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
 
 // ------------------------------------------------------------------------------------------
 // One OLS fit at a grid point, from sufficient statistics handed over THROUGH MEMORY (st = X'X packed lower
-// triangle [NACC], X'y [PT]).  Deliberately not inlined: the solver needs ~2x the registers of the streaming loops,
+// triangle [NACC], X'y [PT], element i at st[i * stride]: a local array, or the [entry][sim] buffer in HBM).  Deliberately not inlined: the solver needs ~2x the registers of the streaming loops,
 // and inlining it makes ptxas spill the live accumulators inside the hot row loop (measured: +70 % instructions,
 // 1.6 GB of local-memory write-back per 0.5 M studies).  As a call, the spill happens once per fit at the call site.
 template <int PT>
 static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ st, double yty, double sum_y, uint32_t n_rows,
                                                      const SimOut& so, int g, const uint32_t* lvl_counts, uint8_t* excl,
-                                                     bool track_excl) {
+                                                     bool track_excl, size_t stride = 1) {
     constexpr int NACC = PT * (PT + 1) / 2;
     const DevicePlan& pl = c_plan;
     int variant = pl.base_variant;
@@ -772,9 +772,9 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
     if (vr.p_red == PT) {
         double acc[NACC], xty[PT];
 #pragma unroll
-        for (int i = 0; i < NACC; i++) acc[i] = st[i];
+        for (int i = 0; i < NACC; i++) acc[i] = st[i * stride];
 #pragma unroll
-        for (int i = 0; i < PT; i++) xty[i] = st[NACC + i];
+        for (int i = 0; i < PT; i++) xty[i] = st[(NACC + i) * stride];
         RegSolver<PT> sv;
         sv.factor_and_solve(acc, xty, yty, sum_y, n_rows);
         for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
@@ -785,8 +785,8 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
         double Ar[NACC], br[PT];
         const int pr = vr.p_red;
         for (int ri = 0; ri < pr; ri++) {
-            br[ri] = st[NACC + vr.kept[ri]];
-            for (int rj = 0; rj <= ri; rj++) Ar[tri(ri, rj)] = st[tri(vr.kept[ri], vr.kept[rj])];
+            br[ri] = st[(NACC + vr.kept[ri]) * stride];
+            for (int rj = 0; rj <= ri; rj++) Ar[tri(ri, rj)] = st[tri(vr.kept[ri], vr.kept[rj]) * stride];
         }
         MemSolver<PT> ms;
         ms.factor_and_solve(Ar, br, pr, yty, sum_y, n_rows);

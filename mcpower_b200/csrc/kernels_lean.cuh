@@ -1,11 +1,12 @@
 // kernels_lean.cuh — the headline kernel: OLS power for the "plain linear model" spec family, one simulated study
 // per lane quad, written for a small register footprint (4–5 warps per scheduler) and a short instruction stream.
 //
-// Spec family (host-checked, api.cu lean_eligible()): OLS, continuous outcome, optimistic scenario, Normal
-// marginals, Normal residual, no factors, no cluster; correlated predictors (MIX) and interaction columns (INTER)
-// are compile-time options.  BASELINE.json's metric shape (n = 500, 8 N(0,1) predictors, P = 9) and config 1
-// (y ~ x1 + x2 + x1:x2) are in the family; everything else runs on the general kernels (kernels.cuh /
-// kernels_q4.cuh).  Arithmetic and operation order are those of the general kernels and of the oracle — the data
+// Spec family (host-checked, api.cu lean_ok): OLS, continuous outcome, optimistic scenario, Normal marginals, Normal
+// residual, no cluster, factors only with the exact (sim-invariant) level walk; correlated predictors (MIX), factor
+// dummies (FACT) and interaction columns (INTER) are compile-time options.  BASELINE.json's metric shape (n = 500,
+// 8 N(0,1) predictors, P = 9), config 1 (y ~ x1 + x2 + x1:x2) and config 2 (sample-size sweep, 8 correlated
+// predictors + 3-level factor, Bonferroni / BH) are in the family; everything else runs on the general kernels
+// (kernels.cuh / kernels_q4.cuh).  Arithmetic and operation order are those of the general kernels and of the oracle — the data
 // plane follows rng.rs:154-364 / data_gen.rs:334-363,643-649,781-888, the statistics are one sequential fma chain per
 // accumulator — so every output bit is the same whichever kernel runs (tests/test_gpu_parity.py runs all of them on
 // the same inputs).
@@ -158,7 +159,7 @@ __device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const ui
 // Measured alternatives that were slower on B200 (tools/tune_lean.sh, gpurun_out/tune_lean*.log): 3 or 5-6 CTAs per SM;
 // a persistent one-CTA-per-SM variant with staggered warp starts; f32 staging (4x the F2F.F64.F32 count: the FP64
 // pipe is the shared one); 16-row staging with the accumulation fused into the next step's generation code.
-template <int PT, bool MIX, bool INTER, int UNR = MCP_LEAN_UNROLL>
+template <int PT, bool MIX, bool INTER, int UNR = MCP_LEAN_UNROLL, bool FACT = INTER>
 __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
                                                                                   double* __restrict__ stats) {
     using G = LeanGeom<PT>;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
         rk[2 * r + 1] = (uint32_t)(key >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
     const int max_n = pl.max_n;
-    const int k = INTER ? pl.k : PT - 1;  // no factors in this family: P = 1 + k + n_inter
+    const int k = (INTER || FACT) ? pl.k : PT - 1;  // P = 1 + k + factor dummies + interactions
     double acc[G::NACCQ];
 #pragma unroll
     for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
@@ -261,12 +262,24 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                     for (int j = 0; j < PT - 1; j++)
                         if (j < k) z[j + 1] = (double)src[128 * j];
                 }
-                if (INTER) {  // x = f32(Π f64(components)) (data_gen.rs:643-649); columns k+1.. of the design
+                if (FACT) {  // factor dummies from the exact largest-remainder walk (data_gen.rs:509-551, no RNG): the
+                             // host-built level table is sim-invariant
 #pragma unroll
                     for (int j = 0; j < PT - 1; j++) {
-                        if (j >= k) {
+                        const int f = pl.col_factor[j + 1];
+                        if (j >= k && f >= 0) {
+                            const float xf = pl.levels[(size_t)f * max_n + (row0 + q)] == (uint8_t)pl.col_level[j + 1] ? 1.0f : 0.0f;
+                            if (INTER) src[128 * j] = xf;
+                            z[j + 1] = (double)xf;
+                        }
+                    }
+                }
+                if (INTER) {  // x = f32(Π f64(components)) (data_gen.rs:643-649); columns after the dummies
+#pragma unroll
+                    for (int j = 0; j < PT - 1; j++) {
+                        if (j >= k + pl.n_fd) {
                             double prod = 1.0;
-                            for (int c = pl.inter_ptr[j - k]; c < pl.inter_ptr[j - k + 1]; c++)
+                            for (int c = pl.inter_ptr[j - k - pl.n_fd]; c < pl.inter_ptr[j - k - pl.n_fd + 1]; c++)
                                 prod *= (double)src[128 * (pl.inter_cols[c] - 1)];
                             const float xf = (float)prod;
                             src[128 * j] = xf;
@@ -344,15 +357,17 @@ __global__ void __launch_bounds__(MCP_BLOCK) ols_solve_kernel(uint32_t n_sims, c
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
     const int g = blockIdx.y;
     if (sim < n_sims) {
-        const double* const in = stats + (size_t)g * E * n_sims + sim;
-        double st[NACC + PT];
-#pragma unroll
-        for (int e = 0; e < NACC + PT; e++) st[e] = in[(size_t)e * n_sims];
+        const double* const in = stats + (size_t)g * E * n_sims + sim;  // entry e at in[e * n_sims]: coalesced over the warp
         const double yty = in[(size_t)(NACC + PT) * n_sims];
+        const double sum_y = in[(size_t)NACC * n_sims];
         uint8_t excl[MCP_MAX_FACTORS];
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
         SimOut so{cnt_s, (uint64_t)sim};
-        ols_fit_and_emit<PT>(st, yty, st[NACC], pl.ss[g], so, g, nullptr, excl, false);
+        // sparse-factor exclusion (batch.rs:2451-2562): with exact walks the per-level counts at a grid point are the
+        // same for every study, so the host tabulates them once
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        ols_fit_and_emit<PT>(in, yty, sum_y, pl.ss[g], so, g, track_excl ? pl.exact_counts + (size_t)g * MCP_MAX_LEVELS : nullptr, excl,
+                             track_excl, (size_t)n_sims);
     }
     if (cnt_s) {
         __syncthreads();

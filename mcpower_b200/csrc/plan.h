@@ -53,6 +53,8 @@ struct DevicePlan {
     int32_t f_sampled[MCP_MAX_FACTORS];
     double f_props[MCP_MAX_LEVELS];
     int32_t n_sampled_factors;         // uniforms consumed per row on the sequential stream
+    int8_t col_factor[MCP_MAX_P];      // design column j is a dummy of factor col_factor[j] (−1: not a dummy) ...
+    int8_t col_level[MCP_MAX_P];       // ... and indicates level col_level[j] (1..levels−1)
     int32_t inter_ptr[MCP_MAX_INTER + 1];
     int32_t inter_cols[MCP_MAX_INTER_COMP];
     double beta[MCP_MAX_P];
@@ -86,6 +88,8 @@ struct DevicePlan {
     const double* crit_overall;        // [n_variants][n_ss]
     const double* crit_joint;          // [n_variants][n_ss] joint Wald chi-square threshold (MLE arm) or NULL
     const uint8_t* levels;             // [n_factors][max_n] exact-walk levels (NULL if none exact)
+    const uint32_t* exact_counts;      // [n_ss][MCP_MAX_LEVELS] per-level counts of the first ss[g] rows when every factor
+                                       // uses the exact walk (sim-invariant; consumed by ols_solve_kernel) or NULL
     const double* t3_table;            // [2048] censored t(3) PPF (marginals/t3.rs)
     // ---- outputs
     unsigned long long* counters;      // [n_ss][counter_width] (COUNTS)
