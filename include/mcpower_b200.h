@@ -49,12 +49,13 @@ typedef struct McpOptions {
 /* ProgressSink (spec.rs:38-52): report(current, total) ~50×/run; return 0 to request cancellation. */
 typedef int (*McpProgressFn)(uint64_t current, uint64_t total, void* user);
 
-/* Counter row layout per sample-size index (width = 4T + 6 + F):
+/* Counter row layout per sample-size index (width = 4T + 6 + F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
  *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
- *   [2T+2,3T+3) histogram of #uncorrected-significant targets per sim
- *   [3T+3,4T+4) histogram of #corrected-significant targets per sim
- *   [4T+4,4T+4+F) sims with factor f excluded (sparse level or GLM separation fallback)
- *   4T+4+F joint Wald successes (MLE arm)   4T+5+F fits with a variance component on the boundary (MLE arm) */
+ *   [2T+2, +J+1) histogram of #uncorrected-significant tests per sim (targets AND posthoc contrasts)
+ *   [2T+3+J, +J+1) histogram of #corrected-significant tests per sim
+ *   then F: sims with factor f excluded (sparse level or GLM separation fallback)
+ *   then joint Wald successes (MLE arm), fits with a variance component on the boundary (MLE arm)
+ *   then C posthoc uncorrected successes, C posthoc corrected successes.  C = 0 gives the 4T + 6 + F layout. */
 typedef struct McpBatchResult {
     uint32_t n_sims, n_sample_sizes, n_targets, n_factors;
     uint8_t* uncorrected;     /* [n_sims][n_ss][T]  or NULL */
@@ -69,6 +70,10 @@ typedef struct McpBatchResult {
     uint32_t gpu_launches;    /* kernels launched for this call */
     uint64_t* counters;       /* [n_ss][counter_width] */
     double kernel_ms;         /* device time of the power kernel(s), CUDA events on the launch stream */
+    uint32_t n_posthoc;       /* C = total pairwise posthoc contrasts over all blocks (spec.posthoc, batch.rs:2183-2227) */
+    uint32_t reserved;
+    uint8_t* posthoc_unc;     /* [n_sims][n_ss][C] or NULL (BatchResult::posthoc_unc, spec.rs:557-559) */
+    uint8_t* posthoc_cor;     /* [n_sims][n_ss][C] or NULL */
 } McpBatchResult;
 
 /* run_batch twin. spec_json = serde JSON of SimulationSpec (same field names / enum spellings). */

@@ -213,14 +213,26 @@ static void crit_row(const Spec& s, uint32_t n, int n_predictors, double* t_unc_
                     corr[i] = t * t;
                 }
                 break;
-            case C_TUKEY:
+            case C_TUKEY: {  // the studentized-range quantile costs ~0.2 s: one evaluation per distinct k in the row
+                double qk[MCP_MAX_LEVELS + 2];
+                for (double& v : qk) v = -1.0;
                 for (int i = 0; i < m; i++) {
                     const int nm = (int)s.target_indices.size();
                     const int col = i < nm ? s.target_indices[i] : s.contrast_pairs[i - nm].first;
-                    const double t = crit::q_tukey_ppf(1.0 - alpha, tukey_k_for_col(s, col), df) / crit::kSqrt2;
+                    const double kk = tukey_k_for_col(s, col);
+                    double q;
+                    if (kk == kk && kk >= 0.0 && kk <= MCP_MAX_LEVELS) {
+                        double& slot = qk[(int)kk];
+                        if (slot == -1.0) slot = crit::q_tukey_ppf(1.0 - alpha, kk, df);
+                        q = slot;
+                    } else {
+                        q = crit::q_tukey_ppf(1.0 - alpha, kk, df);
+                    }
+                    const double t = q / crit::kSqrt2;
                     corr[i] = t * t;
                 }
                 break;
+            }
         }
     }
     if (posthoc_sq) {
@@ -234,6 +246,42 @@ static void crit_row(const Spec& s, uint32_t n, int n_predictors, double* t_unc_
         else if (s.estimator == E_OLS) *overall = crit::f_ppf(1.0 - alpha, npni, df);
         else if (s.estimator == E_GLM) *overall = crit::chi2_ppf(1.0 - alpha, npni);
         else *overall = crit::kInf;
+    }
+}
+
+// Posthoc correction thresholds for sample size n and `n_predictors` fitted columns: one CritValueTable per block
+// (alpha = posthoc_alpha, family = the block's C(k,2) contrasts, Tukey k = the block's level count), concatenated
+// in block order (build_posthoc_correction_crit_with_levels + build_crit_tables, batch.rs:2252-2405).
+static void posthoc_corr_row(const Spec& s, uint32_t n, int n_predictors, double* out /*n_ph*/) {
+    const long df_signed = (long)n - (long)n_predictors;
+    if (df_signed < 1) invalid("df = N - P = " + std::to_string(n) + " - " + std::to_string(n_predictors) + " < 1");
+    const double df = (double)df_signed;
+    const double pa = std::isnan(s.posthoc_alpha) ? s.alpha : s.posthoc_alpha;
+    const bool use_t = s.estimator == E_OLS;
+    auto quant = [&](double p) { return use_t ? crit::t_ppf(p, df) : crit::norm_ppf(p); };
+    size_t o = 0;
+    for (size_t b = 0; b < s.posthoc_block_ncontrasts.size(); b++) {
+        const int m = s.posthoc_block_ncontrasts[b];
+        const double t_tukey = s.correction == C_TUKEY ? crit::q_tukey_ppf(1.0 - pa, (double)s.posthoc_block_levels[b], df) / crit::kSqrt2 : 0.0;
+        for (int i = 0; i < m; i++) {
+            double t = 0.0;
+            switch (s.correction) {
+                case C_NONE: t = quant(1.0 - pa / 2.0); break;
+                case C_BONFERRONI: t = quant(1.0 - pa / (2.0 * (double)m)); break;
+                case C_HOLM: {
+                    const double eff = pa / (2.0 * (double)(m - i));
+                    t = eff < 1e-12 ? crit::kInf : quant(1.0 - eff);
+                    break;
+                }
+                case C_BH: {
+                    const double eff = (double)(i + 1) / (double)m * pa / 2.0;
+                    t = eff < 1e-12 ? crit::kInf : quant(1.0 - eff);
+                    break;
+                }
+                case C_TUKEY: t = t_tukey; break;
+            }
+            out[o++] = t * t;
+        }
     }
 }
 
@@ -273,7 +321,7 @@ static void check_supported(const Spec& s, bool generation_only = false) {
         if (!s.contrast_pairs.empty()) unsupported("contrast_pairs with estimator glm (the reference's GLM arm has no contrasts, batch.rs:2060-2062)");
         if (s.outcome == O_CONTINUOUS) invalid("estimator Glm requires a binary or count outcome");
     }
-    if (!generation_only && s.has_posthoc) unsupported("posthoc blocks");
+    if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
     if (s.has_upload) unsupported("uploaded-data marginals / bootstrap");
     if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
     if (s.has_between) unsupported("between_var_indices");
@@ -360,6 +408,11 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     for (int j = 0; j < P; j++) {
         pl.beta[j] = s.effect_sizes[j];
         if (s.effect_sizes[j] != 0.0) pl.beta_nonzero_mask |= 1u << j;
+    }
+    pl.n_ph = (int)s.posthoc_contrasts.size();
+    for (int c = 0; c < pl.n_ph; c++) {
+        pl.ph_contrast[2 * c] = s.posthoc_contrasts[c].first;
+        pl.ph_contrast[2 * c + 1] = s.posthoc_contrasts[c].second;
     }
     for (int t = 0; t < pl.n_marg; t++) pl.target[t] = s.target_indices[t];
     for (int t = 0; t < pl.n_contrasts; t++) {
@@ -490,7 +543,9 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         crit_row(s, ss[g], P, &dummy, nullptr, nullptr, nullptr);
     }
     // thresholds depend on (N, p_red) only — memoise like reduced_crit_entry (batch.rs:2418-2437)
-    struct Memo { uint32_t n; int p; double unc, ov; std::vector<double> corr; };
+    const int NPH = (int)s.posthoc_contrasts.size();
+    std::vector<double> c_phu((size_t)nv * n_ss, nan), c_phc((size_t)nv * n_ss * std::max(NPH, 1), nan);
+    struct Memo { uint32_t n; int p; double unc, ov, phu; std::vector<double> corr, phc; };
     std::vector<Memo> memo;
     for (int m = 0; m < nv; m++)
         for (uint32_t g = 0; g < n_ss; g++) {
@@ -501,8 +556,9 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
             for (auto& e : memo)
                 if (e.n == ss[g] && e.p == pr) hit = &e;
             if (!hit) {
-                Memo e{ss[g], pr, 0, 0, std::vector<double>(std::max(T, 1))};
-                crit_row(s, ss[g], pr, &e.unc, e.corr.data(), nullptr, &e.ov);
+                Memo e{ss[g], pr, 0, 0, 0, std::vector<double>(std::max(T, 1)), std::vector<double>(std::max(NPH, 1))};
+                crit_row(s, ss[g], pr, &e.unc, e.corr.data(), &e.phu, &e.ov);
+                if (NPH > 0) posthoc_corr_row(s, ss[g], pr, e.phc.data());
                 memo.push_back(e);
                 hit = &memo.back();
             }
@@ -510,6 +566,8 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
             c_unc[r] = hit->unc;
             c_ov[r] = hit->ov;
             for (int t = 0; t < T; t++) c_corr[r * T + t] = hit->corr[t];
+            c_phu[r] = hit->phu;
+            for (int c = 0; c < NPH; c++) c_phc[r * NPH + c] = hit->phc[c];
         }
     std::vector<uint32_t> ssv(ss, ss + n_ss);
     pl.ss = lw.bufs.upload(ssv);
@@ -518,6 +576,8 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.crit_corr = lw.bufs.upload(c_corr);
     pl.crit_overall = lw.bufs.upload(c_ov);
     pl.crit_joint = lw.bufs.upload(c_joint);
+    pl.crit_ph_unc = NPH > 0 ? lw.bufs.upload(c_phu) : nullptr;
+    pl.crit_ph_corr = NPH > 0 ? lw.bufs.upload(c_phc) : nullptr;
     pl.levels = any_exact ? lw.bufs.upload(levels_flat) : nullptr;
     pl.exact_counts = nullptr;
     if (F > 0 && pl.exact_walk) {  // exact walks are sim-invariant: the per-level prefix counts at every grid point too
@@ -530,7 +590,13 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     bool need_t3 = false;
     for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
     if (need_t3) pl.t3_table = lw.bufs.upload(crit::build_t3_table());
-    pl.counter_width = mcp_counter_width(T, F);
+    pl.counter_width = mcp_counter_width(T, F, NPH);
+    pl.off_hist_cor = 2 * T + 3 + (T + NPH);
+    pl.off_fx = pl.off_hist_cor + (T + NPH) + 1;
+    pl.off_joint = pl.off_fx + F;
+    pl.off_bh = pl.off_joint + 1;
+    pl.off_ph_unc = pl.off_bh + 1;
+    pl.off_ph_cor = pl.off_ph_unc + NPH;
     lw.cw = pl.counter_width;
     pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
 }
@@ -593,6 +659,8 @@ void mcp_free_result(McpBatchResult* r) {
     std::free(r->joint);
     std::free(r->boundary_hit);
     std::free(r->t_sq);
+    std::free(r->posthoc_unc);
+    std::free(r->posthoc_cor);
     std::free(r->counters);
     std::free(r);
 }
@@ -626,6 +694,10 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             pl.out_conv = lw.bufs.alloc<uint8_t>(cells);
             if (s.report_overall) pl.out_overall = lw.bufs.alloc<uint8_t>(cells);
             if (F > 0) pl.out_fx = lw.bufs.alloc<uint8_t>(cells * F);
+            if (pl.n_ph > 0) {
+                pl.out_ph_unc = lw.bufs.alloc<uint8_t>(cells * pl.n_ph);
+                pl.out_ph_cor = lw.bufs.alloc<uint8_t>(cells * pl.n_ph);
+            }
         }
         if (capture) pl.out_tsq = lw.bufs.alloc<double>(cells * T);
         const bool glm = s.estimator == E_GLM, mle = s.estimator == E_MLE;
@@ -638,6 +710,7 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
         McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
         r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
         r->counter_width = (uint32_t)lw.cw;
+        r->n_posthoc = (uint32_t)pl.n_ph;
         struct Guard { McpBatchResult* r; bool ok = false; ~Guard() { if (!ok) mcp_free_result(r); } } guard{r};
 
         cudaStream_t st = 0;
@@ -705,6 +778,10 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                     if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
                     if (pl.out_joint) shifted.out_joint = pl.out_joint + done * n_ss;
                     if (pl.out_bh) shifted.out_bh = pl.out_bh + done * n_ss;
+                    if (pl.out_ph_unc) {
+                        shifted.out_ph_unc = pl.out_ph_unc + done * n_ss * pl.n_ph;
+                        shifted.out_ph_cor = pl.out_ph_cor + done * n_ss * pl.n_ph;
+                    }
                 }
                 if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
             }
@@ -754,6 +831,10 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
             if (pl.out_fx) fetch(r->factor_excluded, pl.out_fx, cells * F);
             if (pl.out_joint) fetch(r->joint, pl.out_joint, cells);
             if (pl.out_bh) fetch(r->boundary_hit, pl.out_bh, cells);
+            if (pl.out_ph_unc) {
+                fetch(r->posthoc_unc, pl.out_ph_unc, cells * pl.n_ph);
+                fetch(r->posthoc_cor, pl.out_ph_cor, cells * pl.n_ph);
+            }
         }
         if (capture) fetch(r->t_sq, pl.out_tsq, cells * T);
         guard.ok = true;

@@ -284,7 +284,8 @@ struct SimOut {
 // ov_given < 0: compute the overall F test from (sst, rss); otherwise 0/1 decided by the caller (GLM: deviance LRT).
 static // joint_sig / boundary: MLE arm only (joint Wald chi-square decision, boundary_hit code; spec.rs:562-582).
 __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, const FitOut& fit, int p_red, double* all_t,
-                                      const uint8_t* excl_flags, int ov_given = -1, int joint_sig = 0, int boundary = 0) {
+                                      const uint8_t* excl_flags, int ov_given = -1, int joint_sig = 0, int boundary = 0,
+                                      const double* ph_t = nullptr) {
     const DevicePlan& pl = c_plan;
     const int T = pl.T;
     const size_t vrow = (size_t)variant * pl.n_ss + g;
@@ -303,6 +304,22 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
             unc[t] = 0;
             cor[t] = 0;
             all_t[t] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+    // ---- posthoc pairwise contrasts (evaluate_posthoc, posthoc.rs:40-148): uncorrected at the posthoc-alpha threshold,
+    // corrected with the main correction method over the flat contrast set and the per-block threshold rows
+    const int NPH = ph_t ? pl.n_ph : 0;
+    uint8_t ph_unc[MCP_MAX_PH], ph_cor[MCP_MAX_PH];
+    if (NPH > 0) {
+        for (int c = 0; c < NPH; c++) ph_unc[c] = ph_cor[c] = 0;
+        if (fit.converged) {
+            const double ph_crit = pl.crit_ph_unc[vrow];
+            for (int c = 0; c < NPH; c++) ph_unc[c] = gt_crit(ph_t[c], ph_crit);
+            apply_correction(pl.correction, ph_t, NPH, ph_crit, pl.crit_ph_corr + vrow * NPH, ph_cor);
+        }
+        for (int c = 0; c < NPH; c++) {
+            n_unc += ph_unc[c];
+            n_cor += ph_cor[c];
         }
     }
     uint8_t ov = 0;
@@ -325,16 +342,20 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
     }
     count_flag(cs, cg, 2 * T, fit.converged != 0);
     count_flag(cs, cg, 2 * T + 1, ov != 0);
-    if (cs) {
+    if (cs) {  // joint histograms pool the targets and the posthoc contrasts (aggregation.rs:186-217)
         atomicAdd(&cs[2 * T + 2 + n_unc], 1u);
-        atomicAdd(&cs[3 * T + 3 + n_cor], 1u);
+        atomicAdd(&cs[pl.off_hist_cor + n_cor], 1u);
     } else {
         atomicAdd(&cg[2 * T + 2 + n_unc], 1ull);
-        atomicAdd(&cg[3 * T + 3 + n_cor], 1ull);
+        atomicAdd(&cg[pl.off_hist_cor + n_cor], 1ull);
     }
-    for (int f = 0; f < pl.n_factors; f++) count_flag(cs, cg, 4 * T + 4 + f, excl_flags && excl_flags[f] != 0);
-    count_flag(cs, cg, 4 * T + 4 + pl.n_factors, joint_sig != 0);
-    count_flag(cs, cg, 4 * T + 5 + pl.n_factors, boundary != 0);
+    for (int f = 0; f < pl.n_factors; f++) count_flag(cs, cg, pl.off_fx + f, excl_flags && excl_flags[f] != 0);
+    count_flag(cs, cg, pl.off_joint, joint_sig != 0);
+    count_flag(cs, cg, pl.off_bh, boundary != 0);
+    for (int c = 0; c < NPH; c++) {
+        count_flag(cs, cg, pl.off_ph_unc + c, ph_unc[c] != 0);
+        count_flag(cs, cg, pl.off_ph_cor + c, ph_cor[c] != 0);
+    }
     // ---- BatchResult byte tensors (spec.rs:552-600), sim-major
     if (pl.out_unc) {
         const size_t cell = so.sim_local * pl.n_ss + g;
@@ -348,6 +369,13 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
         if (pl.out_bh) pl.out_bh[cell] = (uint8_t)boundary;
         if (pl.out_fx)
             for (int f = 0; f < pl.n_factors; f++) pl.out_fx[cell * pl.n_factors + f] = excl_flags ? excl_flags[f] : 0;
+    }
+    if (pl.out_ph_unc && NPH > 0) {
+        const size_t cell = so.sim_local * pl.n_ss + g;
+        for (int c = 0; c < NPH; c++) {
+            pl.out_ph_unc[cell * NPH + c] = ph_unc[c];
+            pl.out_ph_cor[cell * NPH + c] = ph_cor[c];
+        }
     }
     if (pl.out_tsq) {
         const size_t cell = so.sim_local * pl.n_ss + g;
@@ -779,7 +807,9 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
         sv.factor_and_solve(acc, xty, yty, sum_y, n_rows);
         for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
         for (int t = 0; t < pl.n_contrasts; t++) all_t[pl.n_marg + t] = sv.t_sq(pl.contrast[2 * t], pl.contrast[2 * t + 1]);
-        emit_fit(so, g, variant, sv.out, PT, all_t, excl);
+        double ph_t[MCP_MAX_PH];
+        for (int c = 0; c < pl.n_ph; c++) ph_t[c] = sv.t_sq(pl.ph_contrast[2 * c], pl.ph_contrast[2 * c + 1]);
+        emit_fit(so, g, variant, sv.out, PT, all_t, excl, -1, 0, 0, pl.n_ph > 0 ? ph_t : nullptr);
     } else {
         // reduced model: gather kept rows/cols of the sufficient statistics (batch.rs:970-1013)
         double Ar[NACC], br[PT];
@@ -799,7 +829,15 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
             const int pc = vr.remap[pl.contrast[2 * t]], nc = vr.remap[pl.contrast[2 * t + 1]];
             all_t[pl.n_marg + t] = (pc >= 0 && nc >= 0) ? ms.t_sq(pc, nc) : nan;
         }
-        emit_fit(so, g, variant, ms.out, pr, all_t, excl);
+        // posthoc under exclusion (batch.rs:1163-1203): a contrast touching a dropped column becomes the zero contrast,
+        // whose se² fails the > 1e-30 guard — never significant
+        double ph_t[MCP_MAX_PH];
+        for (int c = 0; c < pl.n_ph; c++) {
+            const int pos = pl.ph_contrast[2 * c], neg = pl.ph_contrast[2 * c + 1];
+            const int pc = vr.remap[pos], nc = neg >= 0 ? vr.remap[neg] : -1;
+            ph_t[c] = (pc >= 0 && (neg < 0 || nc >= 0)) ? ms.t_sq(pc, nc) : nan;
+        }
+        emit_fit(so, g, variant, ms.out, pr, all_t, excl, -1, 0, 0, pl.n_ph > 0 ? ph_t : nullptr);
     }
 }
 

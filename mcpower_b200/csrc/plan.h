@@ -11,6 +11,7 @@
 #define MCP_MAX_K 24          // continuous (non-factor) predictors
 #define MCP_MAX_P 32          // total design columns incl. intercept
 #define MCP_MAX_T 32          // marginal targets + contrasts
+#define MCP_MAX_PH 32         // posthoc pairwise contrasts (all blocks)
 #define MCP_MAX_FACTORS 6
 #define MCP_MAX_LEVELS 48     // Σ factor_n_levels
 #define MCP_MAX_INTER 16
@@ -61,6 +62,8 @@ struct DevicePlan {
     uint32_t beta_nonzero_mask;        // bit j set ⇔ beta[j] != 0
     int32_t target[MCP_MAX_T];         // marginal target columns
     int32_t contrast[2 * MCP_MAX_T];   // (pos, neg) pairs
+    int32_t n_ph;                      // posthoc pairwise contrasts, flat over blocks (posthoc.rs:40-148)
+    int32_t ph_contrast[2 * MCP_MAX_PH]; // (pos, neg) columns, neg < 0 → the factor's reference level
     // ---- residual / outcome
     int32_t residual_dist, residual_pinned;
     double residual_df;
@@ -87,6 +90,8 @@ struct DevicePlan {
     const double* crit_corr;           // [n_variants][n_ss][T]
     const double* crit_overall;        // [n_variants][n_ss]
     const double* crit_joint;          // [n_variants][n_ss] joint Wald chi-square threshold (MLE arm) or NULL
+    const double* crit_ph_unc;         // [n_variants][n_ss] posthoc-alpha threshold or NULL
+    const double* crit_ph_corr;        // [n_variants][n_ss][n_ph] per-block correction rows, concatenated
     const uint8_t* levels;             // [n_factors][max_n] exact-walk levels (NULL if none exact)
     const uint32_t* exact_counts;      // [n_ss][MCP_MAX_LEVELS] per-level counts of the first ss[g] rows when every factor
                                        // uses the exact walk (sim-invariant; consumed by ols_solve_kernel) or NULL
@@ -100,21 +105,27 @@ struct DevicePlan {
     uint8_t* out_fx;                   // [n_sims][n_ss][n_factors] or NULL
     uint8_t* out_joint;                // [n_sims][n_ss] joint Wald decision (MLE arm) or NULL
     uint8_t* out_bh;                   // [n_sims][n_ss] boundary_hit code (MLE arm) or NULL
+    uint8_t* out_ph_unc;               // [n_sims][n_ss][n_ph] or NULL
+    uint8_t* out_ph_cor;
     double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
     int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
-    int32_t counter_width;             // 4T + 6 + n_factors
+    int32_t counter_width;             // 4T + 6 + n_factors + 4 n_ph
+    int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor;  // counter-row offsets (below)
     int32_t smem_counters;             // counters staged in shared memory (fits)
 };
 
 // counter row layout (per sample-size index): what aggregate_batch derives
-// (crates/engine-orchestrator/src/aggregation.rs:91-242)
-//   [0,T)            uncorrected successes per target
-//   [T,2T)           corrected successes per target
-//   2T               converged fits
-//   2T+1             overall-test successes
-//   [2T+2, 3T+3)     histogram of #uncorrected-significant targets per sim (T+1 buckets)
-//   [3T+3, 4T+4)     histogram of #corrected-significant targets per sim
-//   [4T+4, 4T+4+F)   sims with factor f excluded
-//   4T+4+F           joint Wald successes (MLE arm; 0 otherwise)
-//   4T+5+F           fits with a variance component on the boundary (MLE arm; 0 otherwise)
-static inline int mcp_counter_width(int T, int F) { return 4 * T + 6 + F; }
+// (crates/engine-orchestrator/src/aggregation.rs:91-242); J = T + n_ph tests enter the joint histograms
+//   [0,T)                    uncorrected successes per target
+//   [T,2T)                   corrected successes per target
+//   2T                       converged fits
+//   2T+1                     overall-test successes
+//   [2T+2, 2T+3+J)           histogram of #uncorrected-significant tests per sim (targets + posthoc contrasts, J+1 buckets)
+//   [off_hist_cor, +J+1)     histogram of #corrected-significant tests per sim
+//   [off_fx, +F)             sims with factor f excluded
+//   off_joint                joint Wald successes (MLE arm; 0 otherwise)
+//   off_bh                   fits with a variance component on the boundary (MLE arm; 0 otherwise)
+//   [off_ph_unc, +n_ph)      posthoc uncorrected successes per contrast
+//   [off_ph_cor, +n_ph)      posthoc corrected successes per contrast
+// With n_ph = 0 this is the 4T + 6 + F layout of round 1.
+static inline int mcp_counter_width(int T, int F, int n_ph) { return 4 * T + 6 + F + 4 * n_ph; }

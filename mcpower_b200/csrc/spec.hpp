@@ -48,6 +48,11 @@ struct Spec {
     bool report_overall = false;
     int min_level_count = 0;
     bool has_posthoc = false;
+    // posthoc blocks (spec.rs:90-103): per factor the target (dummy) columns; the pairwise contrasts of all blocks,
+    // flat in block order (build_posthoc_contrasts, batch.rs:2183-2227): c = e_pos − e_neg, neg < 0 → reference level
+    std::vector<std::vector<int>> posthoc_blocks;
+    std::vector<std::pair<int, int>> posthoc_contrasts;
+    std::vector<int> posthoc_block_levels, posthoc_block_ncontrasts;
     bool has_upload = false;
     bool has_slopes_or_groupings = false;
     bool has_between = false;
@@ -184,7 +189,21 @@ inline Spec parse_spec(const char* json, size_t len) {
     if (auto* p = root.get("link"))
         if (!p->is_null()) s.link_probit = enum_of(*p, "link", {{"probit", 1}}) == 1;
     s.estimator = enum_of(req(root, "estimator"), "estimator", {{"ols", E_OLS}, {"glm", E_GLM}, {"mle", E_MLE}});
-    if (auto* p = root.get("posthoc")) s.has_posthoc = p->kind == JsonValue::Array && !p->arr.empty();
+    if (auto* p = root.get("posthoc")) {
+        s.has_posthoc = p->kind == JsonValue::Array && !p->arr.empty();
+        if (s.has_posthoc)
+            for (auto& blk : arr(*p, "posthoc")) {
+                std::vector<int> tis;
+                for (auto& v : arr(req(blk, "target_indices"), "posthoc.target_indices")) tis.push_back(to_int(v, "posthoc.target_indices"));
+                s.posthoc_blocks.push_back(tis);
+                // batch.rs:2196-2225: canonical order a < b over the levels, level 0 = the reference level
+                const int kl = (int)tis.size() + 1;
+                for (int a = 0; a < kl; a++)
+                    for (int b = a + 1; b < kl; b++) s.posthoc_contrasts.push_back({tis[b - 1], a > 0 ? tis[a - 1] : -1});
+                s.posthoc_block_levels.push_back(kl);
+                s.posthoc_block_ncontrasts.push_back(kl * (kl - 1) / 2);
+            }
+    }
     if (auto* p = root.get("report_overall")) s.report_overall = !p->is_null() && to_bool(*p, "report_overall");
     if (auto* p = root.get("factor_min_level_count"))
         if (!p->is_null()) s.min_level_count = to_int(*p, "factor_min_level_count");
@@ -289,6 +308,9 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
     for (auto& comp : s.interactions)
         for (int c : comp)
             if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("interaction component out of range");
+    for (auto& dummies : s.posthoc_blocks)
+        for (int ti : dummies)
+            if (ti < 0 || ti >= P) invalid("posthoc target index " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
     if (s.k > 0) {
         std::vector<double> L;
         if (!correlation_llt(s.correlation, s.k, L)) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");

@@ -71,7 +71,9 @@ class _Result(C.Structure):
                 ("factor_excluded", C.POINTER(C.c_uint8)), ("joint", C.POINTER(C.c_uint8)),
                 ("boundary_hit", C.POINTER(C.c_uint8)), ("t_sq", C.POINTER(C.c_double)),
                 ("counter_width", C.c_uint32), ("gpu_launches", C.c_uint32),
-                ("counters", C.POINTER(C.c_uint64)), ("kernel_ms", C.c_double)]
+                ("counters", C.POINTER(C.c_uint64)), ("kernel_ms", C.c_double),
+                ("n_posthoc", C.c_uint32), ("reserved", C.c_uint32),
+                ("posthoc_unc", C.POINTER(C.c_uint8)), ("posthoc_cor", C.POINTER(C.c_uint8))]
 
 
 _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
@@ -134,7 +136,7 @@ class BatchResult:
     n_sample_sizes: int
     n_targets: int
     n_factors: int
-    counters: np.ndarray                       # [n_ss, 4T+6+F] uint64 (layout: include/mcpower_b200.h)
+    counters: np.ndarray                       # [n_ss, 4T+6+F+4C] uint64 (layout: include/mcpower_b200.h)
     uncorrected: Optional[np.ndarray] = None   # [n_sims, n_ss, T] uint8
     corrected: Optional[np.ndarray] = None
     converged: Optional[np.ndarray] = None     # [n_sims, n_ss]
@@ -143,6 +145,9 @@ class BatchResult:
     joint: Optional[np.ndarray] = None         # [n_sims, n_ss] joint Wald decision (estimator mle)
     boundary_hit: Optional[np.ndarray] = None  # [n_sims, n_ss] 0 none / 1 tau-hat = 0 / 2 upper bound (estimator mle)
     t_sq: Optional[np.ndarray] = None          # [n_sims, n_ss, T] float64 (MODE_CAPTURE)
+    n_posthoc: int = 0                         # C = pairwise posthoc contrasts over all blocks
+    posthoc_unc: Optional[np.ndarray] = None   # [n_sims, n_ss, C] uint8 (BatchResult::posthoc_unc, spec.rs:557-559)
+    posthoc_cor: Optional[np.ndarray] = None
     kernel_ms: float = 0.0
     gpu_launches: int = 0
     extras: dict = field(default_factory=dict)
@@ -165,27 +170,44 @@ class BatchResult:
         return self.counters[:, 2 * self.n_targets + 1]
 
     @property
+    def _j(self):
+        return self.n_targets + self.n_posthoc  # tests pooled in the joint histograms (aggregation.rs:186-217)
+
+    @property
     def hist_uncorrected(self):
         T = self.n_targets
-        return self.counters[:, 2 * T + 2:3 * T + 3]
+        return self.counters[:, 2 * T + 2:2 * T + 3 + self._j]
 
     @property
     def hist_corrected(self):
-        T = self.n_targets
-        return self.counters[:, 3 * T + 3:4 * T + 4]
+        o = 2 * self.n_targets + 3 + self._j
+        return self.counters[:, o:o + self._j + 1]
+
+    @property
+    def _off_fx(self):
+        return 2 * self.n_targets + 4 + 2 * self._j
 
     @property
     def n_factor_excluded(self):
-        T = self.n_targets
-        return self.counters[:, 4 * T + 4:4 * T + 4 + self.n_factors]
+        return self.counters[:, self._off_fx:self._off_fx + self.n_factors]
 
     @property
     def success_joint(self):
-        return self.counters[:, 4 * self.n_targets + 4 + self.n_factors]
+        return self.counters[:, self._off_fx + self.n_factors]
 
     @property
     def n_boundary(self):
-        return self.counters[:, 4 * self.n_targets + 5 + self.n_factors]
+        return self.counters[:, self._off_fx + self.n_factors + 1]
+
+    @property
+    def success_posthoc_uncorrected(self):
+        o = self._off_fx + self.n_factors + 2
+        return self.counters[:, o:o + self.n_posthoc]
+
+    @property
+    def success_posthoc_corrected(self):
+        o = self._off_fx + self.n_factors + 2 + self.n_posthoc
+        return self.counters[:, o:o + self.n_posthoc]
 
     def power(self, corrected: bool = False) -> np.ndarray:
         """successes / n_sims per (sample size, target) — PowerResult.power (aggregation.rs)."""
@@ -194,28 +216,38 @@ class BatchResult:
 
 
 def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_excluded=None, joint=None,
-                        boundary_hit=None) -> np.ndarray:
+                        boundary_hit=None, posthoc_unc=None, posthoc_cor=None) -> np.ndarray:
     """aggregate_batch's integer reductions (aggregation.rs:91-242) over the byte tensors —
     used to prove COUNTS mode equals BYTES mode + host aggregation."""
     n_sims, n_ss, T = uncorrected.shape
     F = 0 if factor_excluded is None else factor_excluded.shape[2]
-    out = np.zeros((n_ss, 4 * T + 6 + F), dtype=np.uint64)
+    Cph = 0 if posthoc_unc is None else posthoc_unc.shape[2]
+    J = T + Cph
+    out = np.zeros((n_ss, 4 * T + 6 + F + 4 * Cph), dtype=np.uint64)
     out[:, :T] = uncorrected.sum(axis=0)
     out[:, T:2 * T] = corrected.sum(axis=0)
     out[:, 2 * T] = converged.sum(axis=0)
     if overall is not None:
         out[:, 2 * T + 1] = overall.sum(axis=0)
-    nu = uncorrected.sum(axis=2)
-    nc = corrected.sum(axis=2)
+    nu = uncorrected.sum(axis=2, dtype=np.int64)
+    nc = corrected.sum(axis=2, dtype=np.int64)
+    if Cph:
+        nu = nu + posthoc_unc.sum(axis=2, dtype=np.int64)
+        nc = nc + posthoc_cor.sum(axis=2, dtype=np.int64)
+    o_hc = 2 * T + 3 + J
+    o_fx = o_hc + J + 1
     for g in range(n_ss):
-        out[g, 2 * T + 2:3 * T + 3] = np.bincount(nu[:, g], minlength=T + 1)
-        out[g, 3 * T + 3:4 * T + 4] = np.bincount(nc[:, g], minlength=T + 1)
+        out[g, 2 * T + 2:2 * T + 3 + J] = np.bincount(nu[:, g], minlength=J + 1)
+        out[g, o_hc:o_hc + J + 1] = np.bincount(nc[:, g], minlength=J + 1)
     if F:
-        out[:, 4 * T + 4:4 * T + 4 + F] = (factor_excluded != 0).sum(axis=0)
+        out[:, o_fx:o_fx + F] = (factor_excluded != 0).sum(axis=0)
     if joint is not None:
-        out[:, 4 * T + 4 + F] = joint.sum(axis=0)
+        out[:, o_fx + F] = joint.sum(axis=0)
     if boundary_hit is not None:
-        out[:, 4 * T + 5 + F] = (boundary_hit != 0).sum(axis=0)
+        out[:, o_fx + F + 1] = (boundary_hit != 0).sum(axis=0)
+    if Cph:
+        out[:, o_fx + F + 2:o_fx + F + 2 + Cph] = posthoc_unc.sum(axis=0)
+        out[:, o_fx + F + 2 + Cph:o_fx + F + 2 + 2 * Cph] = posthoc_cor.sum(axis=0)
     return out
 
 
@@ -260,6 +292,9 @@ def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: i
             converged=take(r.converged, (r.n_sims, n_ss), np.uint8),
             overall=take(r.overall, (r.n_sims, n_ss), np.uint8),
             factor_excluded=take(r.factor_excluded, (r.n_sims, n_ss, F), np.uint8),
+            n_posthoc=r.n_posthoc,
+            posthoc_unc=take(r.posthoc_unc, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
+            posthoc_cor=take(r.posthoc_cor, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
             joint=take(r.joint, (r.n_sims, n_ss), np.uint8),
             boundary_hit=take(r.boundary_hit, (r.n_sims, n_ss), np.uint8),
             t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),

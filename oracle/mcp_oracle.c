@@ -808,15 +808,18 @@ int orc_build_crit_table(const OrcSpec* s, const uint32_t* sample_sizes, int n_s
                         row[k] = t * t;
                     }
                     break;
-                case ORC_CORR_TUKEY:
+                case ORC_CORR_TUKEY: {  /* one studentized-range quantile per distinct k in the row (~0.2 s each) */
+                    double last_k = -1.0, last_q = NAN;
                     for (int k = 0; k < m; k++) {
                         int col = k < s->n_marginal_targets ? s->target_indices[k]
                                                             : s->contrast_pairs[2 * (k - s->n_marginal_targets)];
-                        double q = orc_q_tukey_ppf(1.0 - alpha, tukey_k_for_col(s, col), df);
-                        double t = q / M_SQRT2;
+                        double kk = tukey_k_for_col(s, col);
+                        if (!(kk == last_k)) { last_q = orc_q_tukey_ppf(1.0 - alpha, kk, df); last_k = kk; }
+                        double t = last_q / M_SQRT2;
                         row[k] = t * t;
                     }
                     break;
+                }
                 default: return fail(ORC_ERR_INVALID_SPEC, "unknown correction method");
             }
         }
@@ -832,6 +835,47 @@ int orc_build_crit_table(const OrcSpec* s, const uint32_t* sample_sizes, int n_s
             else if (s->estimator == ORC_EST_GLM) overall[i] = orc_chi2_ppf(1.0 - alpha, npni);
             else overall[i] = INFINITY;
         }
+    }
+    return ORC_OK;
+}
+
+int orc_posthoc_corr_rows(const OrcSpec* s, const uint32_t* sample_sizes, int n_ss, int n_predictors, double* out) {
+    double pa = isnan(s->posthoc_alpha) ? s->alpha : s->posthoc_alpha;
+    if (!isfinite(pa) || pa <= 0.0 || pa >= 1.0) return fail(ORC_ERR_INVALID_SPEC, "posthoc_alpha must lie in (0, 1)");
+    int use_t = s->estimator == ORC_EST_OLS;
+    for (int i = 0; i < n_ss; i++) {
+        long df_signed = (long)sample_sizes[i] - (long)n_predictors;
+        if (df_signed < 1) return fail(ORC_ERR_INVALID_SPEC, "df = N - P < 1");
+        double df = (double)df_signed;
+        double* row = out + (size_t)i * s->n_posthoc;
+        int o = 0;
+#define QUANT(p) (use_t ? orc_t_ppf((p), df) : orc_norm_ppf((p)))
+        for (int b = 0; b < s->n_posthoc_blocks; b++) {
+            int m = s->posthoc_block_ncontrasts[b];
+            double t_tukey = s->correction_method == ORC_CORR_TUKEY
+                                 ? orc_q_tukey_ppf(1.0 - pa, (double)s->posthoc_block_levels[b], df) / M_SQRT2 : 0.0;
+            for (int k = 0; k < m; k++) {
+                double t;
+                switch (s->correction_method) {
+                    case ORC_CORR_NONE: t = QUANT(1.0 - pa / 2.0); break;
+                    case ORC_CORR_BONFERRONI: t = QUANT(1.0 - pa / (2.0 * (double)m)); break;
+                    case ORC_CORR_HOLM: {
+                        double eff = pa / (2.0 * (double)(m - k));
+                        t = eff < 1e-12 ? INFINITY : QUANT(1.0 - eff);
+                        break;
+                    }
+                    case ORC_CORR_BH: {
+                        double eff = (double)(k + 1) / (double)m * pa / 2.0;
+                        t = eff < 1e-12 ? INFINITY : QUANT(1.0 - eff);
+                        break;
+                    }
+                    case ORC_CORR_TUKEY: t = t_tukey; break;
+                    default: return fail(ORC_ERR_INVALID_SPEC, "unknown correction method");
+                }
+                row[o++] = t * t;
+            }
+        }
+#undef QUANT
     }
     return ORC_OK;
 }
@@ -1021,6 +1065,9 @@ typedef struct {
     double* xty;
     uint32_t* prefix_counts;
     uint8_t* excl_flags;
+    /* reduced-model thresholds memoised per (N, p_red) like reduced_crit_entry (batch.rs:2418-2437) */
+    struct RedCrit { uint32_t n; int p_red; double unc, ov, ph; double corr[256], phc[64]; } * red_memo;
+    int n_red_memo;
 } Ws;
 
 static Ws* ws_new(const OrcSpec* s, int max_n) {
@@ -1062,7 +1109,7 @@ static void ws_free(Ws* w) {
     free(w->x); free(w->y); free(w->z_planar); free(w->residuals); free(w->resid_g); free(w->words);
     free(w->mix_acc); free(w->eta_acc); free(w->l_design); free(w->var_types_design); free(w->alloc_counts);
     free(w->prefix_counts); free(w->excl_flags); free(w->beta_eff); free(w->xtx); free(w->xty);
-    free(w->cluster_u); free(w->cluster_ids);
+    free(w->cluster_u); free(w->cluster_ids); free(w->red_memo);
     free(w);
 }
 
@@ -1953,7 +2000,8 @@ static int build_exclusion_remap(const OrcSpec* s, const uint8_t* flags, int* ke
 
 static int run_one_sim(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t sim_id, uint64_t base_seed, Ws* w,
                        const double* t_unc, const double* corr, const double* overall_crit, uint8_t* unc, uint8_t* cor,
-                       uint8_t* conv, uint8_t* overall, uint8_t* fx, double* cap) {
+                       uint8_t* conv, uint8_t* overall, uint8_t* fx, double* cap, const double* ph_unc_crit,
+                       const double* ph_corr, uint8_t* ph_unc, uint8_t* ph_cor) {
     int rc = gen_sim(s, base_seed, sim_id, w);
     if (rc) return rc;
     const int P = w->P, T = s->n_marginal_targets + s->n_contrasts, ld = w->max_n;
@@ -1984,7 +2032,10 @@ static int run_one_sim(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t 
         int p_red = P;
         OlsFit fit;
         const double *crit_unc_p = &t_unc[g], *corr_row = corr + (size_t)g * T, *ov_p = &overall_crit[g];
-        double r_unc, r_corr[256], r_ov;
+        double r_unc, r_corr[256], r_ov, r_ph, r_phc[64];
+        const int NPH = ph_unc ? s->n_posthoc : 0;
+        const double* ph_crit_p = NPH ? &ph_unc_crit[g] : NULL;
+        const double* ph_corr_row = NPH ? ph_corr + (size_t)g * NPH : NULL;
         if (!reduced) {
             ols_solve(w->xtx, w->xty, sc.yty, sc.sum_y, sc.n_rows, P, L, inv_d, wv, beta, &fit);
         } else {
@@ -1995,9 +2046,24 @@ static int run_one_sim(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t 
             }
             ols_solve(Ared, bred, sc.yty, sc.sum_y, sc.n_rows, p_red, L, inv_d, wv, beta, &fit);
             /* reduced-df thresholds (batch.rs:2418-2437) */
-            rc = orc_build_crit_table(s, &ss[g], 1, p_red, &r_unc, r_corr, NULL, &r_ov);
-            if (rc) return rc;
-            crit_unc_p = &r_unc; corr_row = r_corr; ov_p = &r_ov;
+            struct RedCrit* hit = NULL;
+            for (int m = 0; m < w->n_red_memo; m++)
+                if (w->red_memo[m].n == ss[g] && w->red_memo[m].p_red == p_red) hit = &w->red_memo[m];
+            if (!hit) {
+                w->red_memo = (struct RedCrit*)realloc(w->red_memo, sizeof(struct RedCrit) * (size_t)(w->n_red_memo + 1));
+                hit = &w->red_memo[w->n_red_memo];
+                hit->n = ss[g]; hit->p_red = p_red;
+                rc = orc_build_crit_table(s, &ss[g], 1, p_red, &hit->unc, hit->corr, &hit->ph, &hit->ov);
+                if (rc) return rc;
+                if (s->n_posthoc > 0) {  /* crit_src carries the reduced-df post-hoc crits (batch.rs:1190-1203) */
+                    rc = orc_posthoc_corr_rows(s, &ss[g], 1, p_red, hit->phc);
+                    if (rc) return rc;
+                }
+                w->n_red_memo++;
+            }
+            (void)r_unc; (void)r_corr; (void)r_ov; (void)r_ph; (void)r_phc;
+            crit_unc_p = &hit->unc; corr_row = hit->corr; ov_p = &hit->ov;
+            if (NPH) { ph_crit_p = &hit->ph; ph_corr_row = hit->phc; }
         }
         conv[g] = (uint8_t)fit.converged;
         uint8_t* unc_row = unc + (size_t)g * T;
@@ -2020,6 +2086,22 @@ static int run_one_sim(const OrcSpec* s, const uint32_t* ss, int n_ss, uint64_t 
             memset(cor_row, 0, (size_t)T);
         }
         if (cap) memcpy(cap + (size_t)g * T, all_t, sizeof(double) * (size_t)T);
+        if (NPH) {  /* evaluate_posthoc (posthoc.rs:40-148); under exclusion a contrast touching a dropped column is zeroed */
+            uint8_t* pu = ph_unc + (size_t)g * NPH;
+            uint8_t* pc_out = ph_cor + (size_t)g * NPH;
+            double ph_t[64];
+            memset(pu, 0, (size_t)NPH);
+            memset(pc_out, 0, (size_t)NPH);
+            if (fit.converged) {
+                for (int c = 0; c < NPH; c++) {
+                    int pos = s->posthoc_pairs[2 * c], neg = s->posthoc_pairs[2 * c + 1];
+                    int pc = reduced ? remap[pos] : pos, nc = neg >= 0 ? (reduced ? remap[neg] : neg) : -1;
+                    ph_t[c] = (pc >= 0 && (neg < 0 || nc >= 0)) ? target_t_sq(L, inv_d, beta, fit.sigma_sq, p_red, pc, nc, u) : NAN;
+                    pu[c] = !isnan(ph_t[c]) && ph_t[c] > *ph_crit_p;
+                }
+                orc_apply_correction(s->correction_method, ph_t, NPH, *ph_crit_p, ph_corr_row, pc_out);
+            }
+        }
         if (overall) {
             uint8_t sig = 0;
             if (fit.converged) {
@@ -2228,9 +2310,13 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
 
 int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sims, uint64_t sim_begin, uint64_t base_seed,
                   int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged, uint8_t* overall,
-                  uint8_t* factor_excluded, double* t_sq_capture, uint8_t* joint, uint8_t* boundary_hit) {
+                  uint8_t* factor_excluded, double* t_sq_capture, uint8_t* joint, uint8_t* boundary_hit,
+                  uint8_t* posthoc_unc, uint8_t* posthoc_cor) {
     int rc = validate_spec(s, ss, n_ss);
     if (rc) return rc;
+    if (s->n_posthoc > 0 && s->estimator != ORC_EST_OLS)
+        return fail(ORC_ERR_INVALID_SPEC, "posthoc tests are only supported for estimator=Ols");
+    if (s->n_posthoc > 64) return fail(ORC_ERR_INVALID_SPEC, "posthoc contrasts > 64");
     if (s->estimator == ORC_EST_MLE && (s->n_contrasts > 0 || s->has_lme || s->outcome_kind != ORC_OUT_CONTINUOUS))
         return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: only the Gaussian random-intercept MLE arm is restated");
     if (s->estimator == ORC_EST_GLM && (s->has_cluster || s->n_contrasts > 0))
@@ -2246,6 +2332,13 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
     double *corr = t_unc + n_ss, *ovc = corr + (size_t)n_ss * T, *ph = ovc + n_ss;
     rc = orc_build_crit_table(s, ss, n_ss, P, t_unc, corr, ph, ovc);
     if (rc) { free(t_unc); return rc; }
+    const int NPH = (posthoc_unc && posthoc_cor) ? s->n_posthoc : 0;
+    double* ph_corr = NULL;
+    if (NPH) {
+        ph_corr = (double*)malloc(sizeof(double) * (size_t)n_ss * (size_t)NPH);
+        rc = orc_posthoc_corr_rows(s, ss, n_ss, P, ph_corr);
+        if (rc) { free(t_unc); free(ph_corr); return rc; }
+    }
     if (!g_t3_ready) t3_build();
     const int max_n = (int)ss[n_ss - 1];
     int err = 0;
@@ -2268,12 +2361,19 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
                                     factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,
                                     t_sq_capture ? t_sq_capture + (size_t)i * n_ss * T : NULL,
                                     joint ? joint + (size_t)i * n_ss : NULL, boundary_hit ? boundary_hit + (size_t)i * n_ss : NULL);
+            else if (s->estimator == ORC_EST_GLM)
+                r = run_one_sim_glm(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
+                                    uncorrected + (size_t)i * n_ss * T, corrected + (size_t)i * n_ss * T,
+                                    converged + (size_t)i * n_ss, overall ? overall + (size_t)i * n_ss : NULL,
+                                    factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,
+                                    t_sq_capture ? t_sq_capture + (size_t)i * n_ss * T : NULL);
             else
-                r = (s->estimator == ORC_EST_GLM ? run_one_sim_glm : run_one_sim)(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
+                r = run_one_sim(s, ss, n_ss, sim_begin + (uint64_t)i, base_seed, w, t_unc, corr, ovc,
                                 uncorrected + (size_t)i * n_ss * T, corrected + (size_t)i * n_ss * T,
                                 converged + (size_t)i * n_ss, overall ? overall + (size_t)i * n_ss : NULL,
                                 factor_excluded ? factor_excluded + (size_t)i * n_ss * s->n_factors : NULL,
-                                t_sq_capture ? t_sq_capture + (size_t)i * n_ss * T : NULL);
+                                t_sq_capture ? t_sq_capture + (size_t)i * n_ss * T : NULL, ph, ph_corr,
+                                NPH ? posthoc_unc + (size_t)i * n_ss * NPH : NULL, NPH ? posthoc_cor + (size_t)i * n_ss * NPH : NULL);
             if (r) {
 #ifdef _OPENMP
 #pragma omp critical(orc_err)
@@ -2284,5 +2384,6 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
         ws_free(w);
     }
     free(t_unc);
+    free(ph_corr);
     return err;
 }

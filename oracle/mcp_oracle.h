@@ -68,6 +68,13 @@ typedef struct {
     int32_t sampled_factor_proportions;
     int32_t has_lme, re_dist;
     double re_df, icc_noise_sd;
+    /* posthoc blocks (spec.rs:90-103, batch.rs:2183-2227): pairwise contrasts of all blocks, flat in block order,
+     * c = e_pos - e_neg (neg < 0: the factor's reference level); per block its level count and C(k,2) */
+    int32_t n_posthoc;
+    const int32_t* posthoc_pairs;           /* 2*n_posthoc (pos, neg) */
+    int32_t n_posthoc_blocks;
+    const int32_t* posthoc_block_levels;    /* n_posthoc_blocks */
+    const int32_t* posthoc_block_ncontrasts;
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
@@ -129,7 +136,11 @@ int orc_fit_lmm(const double* x_colmajor, const double* y, const int32_t* ids, i
 int orc_run_batch(const OrcSpec* spec, const uint32_t* sample_sizes, int n_ss, uint32_t n_sims, uint64_t sim_begin,
                   uint64_t base_seed, int n_threads, uint8_t* uncorrected, uint8_t* corrected, uint8_t* converged,
                   uint8_t* overall, uint8_t* factor_excluded, double* t_sq_capture,
-                  uint8_t* joint /* [n_sims][n_ss] or NULL (MLE joint Wald) */, uint8_t* boundary_hit /* or NULL */);
+                  uint8_t* joint /* [n_sims][n_ss] or NULL (MLE joint Wald) */, uint8_t* boundary_hit /* or NULL */,
+                  uint8_t* posthoc_unc /* [n_sims][n_ss][n_posthoc] or NULL */, uint8_t* posthoc_cor);
+/* per-N posthoc correction rows, [n_ss][n_posthoc]: one table per block (alpha = posthoc alpha, family = the block's
+ * contrasts, Tukey k = the block's levels), concatenated (batch.rs:2252-2405) */
+int orc_posthoc_corr_rows(const OrcSpec* spec, const uint32_t* sample_sizes, int n_ss, int n_predictors, double* out);
 
 const char* orc_last_error(void);
 

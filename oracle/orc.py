@@ -53,6 +53,9 @@ class OrcSpec(C.Structure):
         ("sampled_factor_proportions", C.c_int32),
         ("has_lme", C.c_int32), ("re_dist", C.c_int32),
         ("re_df", C.c_double), ("icc_noise_sd", C.c_double),
+        ("n_posthoc", C.c_int32), ("posthoc_pairs", C.POINTER(C.c_int32)),
+        ("n_posthoc_blocks", C.c_int32), ("posthoc_block_levels", C.POINTER(C.c_int32)),
+        ("posthoc_block_ncontrasts", C.POINTER(C.c_int32)),
     ]
 
 
@@ -171,6 +174,21 @@ class PackedSpec:
         cp = list(spec.get("contrast_pairs", []) or [])
         s.n_contrasts = len(cp)
         s.contrast_pairs = _ptr(arr([v for pr in cp for v in pr], np.int32), C.c_int32)
+        # posthoc blocks → flat pairwise contrasts in canonical order (build_posthoc_contrasts, batch.rs:2183-2227)
+        pairs, levels, ncs = [], [], []
+        for blk in list(spec.get("posthoc", []) or []):
+            d = [int(v) for v in blk["target_indices"]]
+            kl = len(d) + 1
+            for a in range(kl):
+                for b in range(a + 1, kl):
+                    pairs += [d[b - 1], d[a - 1] if a > 0 else -1]
+            levels.append(kl)
+            ncs.append(kl * (kl - 1) // 2)
+        s.n_posthoc = len(pairs) // 2
+        s.posthoc_pairs = _ptr(arr(pairs, np.int32), C.c_int32)
+        s.n_posthoc_blocks = len(levels)
+        s.posthoc_block_levels = _ptr(arr(levels, np.int32), C.c_int32)
+        s.posthoc_block_ncontrasts = _ptr(arr(ncs, np.int32), C.c_int32)
         fc = list(spec.get("fit_columns", []) or [])
         s.n_fit_columns = len(fc)
         s.fit_columns = _ptr(arr(fc, np.int32), C.c_int32)
@@ -370,14 +388,18 @@ def run_batch(spec: dict, sample_sizes, n_sims: int, base_seed: int, sim_begin: 
     mle = ps.c.estimator == EST["mle"]
     joint = np.zeros((n_sims, n_ss), dtype=np.uint8) if mle else None
     bh = np.zeros((n_sims, n_ss), dtype=np.uint8) if mle else None
+    nph = int(ps.c.n_posthoc)
+    phu = np.zeros((n_sims, n_ss, nph), dtype=np.uint8) if nph else None
+    phc = np.zeros((n_sims, n_ss, nph), dtype=np.uint8) if nph else None
     u8 = C.c_uint8
     _check(lib().orc_run_batch(C.byref(ps.c), _ptr(ss, C.c_uint32), n_ss, n_sims, sim_begin, base_seed, n_threads,
                                _ptr(unc, u8), _ptr(cor, u8), _ptr(conv, u8),
                                None if ov is None else _ptr(ov, u8), None if fx is None else _ptr(fx, u8),
                                None if cap is None else _ptr(cap, C.c_double),
-                               None if joint is None else _ptr(joint, u8), None if bh is None else _ptr(bh, u8)))
+                               None if joint is None else _ptr(joint, u8), None if bh is None else _ptr(bh, u8),
+                               None if phu is None else _ptr(phu, u8), None if phc is None else _ptr(phc, u8)))
     return {"uncorrected": unc, "corrected": cor, "converged": conv, "overall": ov, "factor_excluded": fx,
-            "t_sq": cap, "joint": joint, "boundary_hit": bh}
+            "t_sq": cap, "joint": joint, "boundary_hit": bh, "posthoc_unc": phu, "posthoc_cor": phc}
 
 
 def host_threads() -> int:

@@ -127,3 +127,23 @@ def analytic_ols_power(beta: float, n: int, P: int, alpha: float = 0.05) -> floa
     q = (np.arange(4000) + 0.5) / 4000
     ncp = beta * np.sqrt(stats.chi2.ppf(q, n - P + 1))
     return float(np.mean(1 - stats.nct.cdf(tc, df, ncp) + stats.nct.cdf(-tc, df, ncp)))
+
+
+def posthoc_spec(method: str = "none") -> dict:
+    """2 correlated continuous predictors + a 3-level and a 4-level factor (exact walk), every dummy a target, one
+    posthoc block per factor (all pairwise level comparisons), posthoc alpha 0.01."""
+    from mcpower_b200 import spec as S
+    s = S.base_spec(2)
+    s["correlation"] = [1.0, 0.3, 0.3, 1.0]
+    s["n_factor_dummies"] = 2 + 3
+    s["factor_n_levels"] = [3, 4]
+    s["factor_proportions"] = [0.5, 0.3, 0.2, 0.4, 0.3, 0.2, 0.1]
+    s["effect_sizes"] = [0.0, 0.25, 0.1, 0.5, -0.4, 0.3, 0.0, 0.6]
+    s["target_indices"] = [1, 3, 4, 5, 6, 7]
+    s["contrast_pairs"] = [[4, 3]]
+    s["correction_method"] = method
+    s["crit_values"] = {"alpha": 0.05, "posthoc_alpha": 0.01}
+    s["posthoc"] = [{"factor_index": 0, "target_indices": [3, 4]}, {"factor_index": 1, "target_indices": [5, 6, 7]}]
+    s["factor_min_level_count"] = 5
+    s["report_overall"] = True
+    return s

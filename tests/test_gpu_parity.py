@@ -47,12 +47,24 @@ def assert_batch_equal(got: M.BatchResult, want: dict):
     if want.get("joint") is not None:
         assert np.array_equal(got.joint, want["joint"]), "joint"
         assert np.array_equal(got.boundary_hit, want["boundary_hit"]), "boundary_hit"
+    if want.get("posthoc_unc") is not None:
+        assert np.array_equal(got.posthoc_unc, want["posthoc_unc"]), "posthoc_unc"
+        assert np.array_equal(got.posthoc_cor, want["posthoc_cor"]), "posthoc_cor"
     agg = M.counters_from_bytes(got.uncorrected, got.corrected, got.converged, got.overall, got.factor_excluded,
-                                got.joint, got.boundary_hit)
+                                got.joint, got.boundary_hit, got.posthoc_unc, got.posthoc_cor)
     assert np.array_equal(agg, got.counters), "COUNTS != aggregate(BYTES)"
 
 
 ALL = M.MODE_COUNTS | M.MODE_BYTES | M.MODE_CAPTURE
+
+_ORACLE_CACHE = {}
+
+
+def oracle_once(key, fn):
+    """The oracle result of a case does not depend on which GPU kernel is under test: compute it once per session."""
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = fn()
+    return _ORACLE_CACHE[key]
 
 
 # ------------------------------------------------------------------ data plane vs the reference's saved datasets
@@ -145,6 +157,20 @@ def test_sweep_with_exclusion_and_corrections(method):
     want = orc.run_batch(s, grid, 400, SEED, n_threads=orc.host_threads(), capture=True)
     assert_batch_equal(got, want)
     assert got.factor_excluded[:, 0, 0].all() and not got.factor_excluded[:, 2, 0].any()
+
+
+@pytest.mark.parametrize("method", ["none", "bonferroni", "holm", "benjamini_hochberg", "tukey_hsd"])
+def test_posthoc_blocks_match_oracle(method):
+    """Posthoc pairwise contrasts (evaluate_posthoc, posthoc.rs:40-148): two factor blocks (3 and 4 levels), posthoc
+    alpha != alpha, every correction method, sparse-factor exclusion live at the small sample sizes."""
+    s = CS.posthoc_spec(method)
+    grid = [24, 40, 60, 150]
+    got = M.run_batch(s, grid, 500, SEED, mode=ALL)
+    want = oracle_once(("posthoc", method), lambda: orc.run_batch(s, grid, 500, SEED, n_threads=orc.host_threads(), capture=True))
+    assert got.n_posthoc == 3 + 6
+    assert_batch_equal(got, want)
+    assert got.posthoc_unc[:, -1].any() and got.factor_excluded[:, 0].any()
+    assert np.array_equal(got.success_posthoc_uncorrected, want["posthoc_unc"].sum(axis=0))
 
 
 @pytest.mark.parametrize("name", ["ols_cf_a", "ols_ff_b", "ols_interaction_a", "ols_corr_b", "ols_simple_a"])

@@ -251,6 +251,47 @@ def test_posthoc_contrast_golden():  # posthoc.rs:283-437 (R lm contrast t², ±
     assert abs(fit["t_sq"][3] / f["tsq_c"] - 1) < 1e-5
 
 
+def test_posthoc_contrasts_reduce_to_target_and_contrast_tests():
+    """build_posthoc_contrasts (batch.rs:2183-2227): level-vs-reference is the unit contrast on the dummy, level-vs-level
+    is e_b - e_a.  With posthoc_alpha = alpha and equal family sizes the posthoc decisions must therefore equal the
+    marginal-target / contrast_pairs decisions on the same columns (same t², same thresholds)."""
+    s = CS.posthoc_spec("bonferroni")
+    s["factor_n_levels"], s["factor_proportions"], s["n_factor_dummies"] = [3], [0.5, 0.3, 0.2], 2
+    s["effect_sizes"] = [0.0, 0.25, 0.1, 0.5, -0.4]
+    s["target_indices"], s["contrast_pairs"] = [3, 4], [[4, 3]]
+    s["posthoc"] = [{"factor_index": 0, "target_indices": [3, 4]}]
+    s["crit_values"] = {"alpha": 0.05, "posthoc_alpha": None}
+    r = orc.run_batch(s, [30, 90], 400, 0x1234, n_threads=orc.host_threads())
+    assert r["posthoc_unc"].shape == (400, 2, 3)
+    assert np.array_equal(r["posthoc_unc"], r["uncorrected"]) and np.array_equal(r["posthoc_cor"], r["corrected"])
+    assert r["posthoc_unc"].any() and not r["posthoc_unc"].all()
+
+
+def test_posthoc_correction_rows_per_block():
+    """build_posthoc_correction_crit_with_levels (batch.rs:2252-2310): one table per block at posthoc alpha, family =
+    the block's C(k,2) contrasts, Tukey k = the block's level count; rows concatenated in block order."""
+    import ctypes as C
+    for method in ("bonferroni", "holm", "benjamini_hochberg", "tukey_hsd"):
+        ps = orc.PackedSpec(CS.posthoc_spec(method))
+        ss = np.array([40, 200], dtype=np.uint32)
+        out = np.zeros((2, 9))
+        assert orc.lib().orc_posthoc_corr_rows(C.byref(ps.c), ss.ctypes.data_as(C.POINTER(C.c_uint32)), 2, ps.P,
+                                               out.ctypes.data_as(C.POINTER(C.c_double))) == 0
+        for i, n in enumerate((40, 200)):
+            df = n - ps.P
+            for off, m, k in ((0, 3, 3), (3, 6, 4)):
+                row = out[i, off:off + m]
+                if method == "bonferroni":
+                    want = [orc.lib().orc_t_ppf(1 - 0.01 / (2 * m), df) ** 2] * m
+                elif method == "holm":
+                    want = [orc.lib().orc_t_ppf(1 - 0.01 / (2 * (m - j)), df) ** 2 for j in range(m)]
+                elif method == "benjamini_hochberg":
+                    want = [orc.lib().orc_t_ppf(1 - (j + 1) / m * 0.01 / 2, df) ** 2 for j in range(m)]
+                else:
+                    want = [(orc.lib().orc_q_tukey_ppf(1 - 0.01, k, df) / math.sqrt(2)) ** 2] * m
+                assert np.allclose(row, want, rtol=1e-13), (method, n, off)
+
+
 # ---------------------------------------------------------------- GLM IRLS vs frozen R glm (1e-4 gate, tolerances.R:29-31)
 @pytest.mark.parametrize("name", sorted(n for n in CS.validation_cases()
                                         if n.startswith(("glm_", "probit_", "poisson_"))))
