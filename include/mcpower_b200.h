@@ -49,13 +49,15 @@ typedef struct McpOptions {
 /* ProgressSink (spec.rs:38-52): report(current, total) ~50×/run; return 0 to request cancellation. */
 typedef int (*McpProgressFn)(uint64_t current, uint64_t total, void* user);
 
-/* Counter row layout per sample-size index (width = 4T + 6 + F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
+/* Counter row layout per sample-size index (width = 4T + 7 + 2F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
  *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
  *   [2T+2, +J+1) histogram of #uncorrected-significant tests per sim (targets AND posthoc contrasts)
  *   [2T+3+J, +J+1) histogram of #corrected-significant tests per sim
- *   then F: sims with factor f excluded (sparse level or GLM separation fallback)
- *   then joint Wald successes (MLE arm), fits with a variance component on the boundary (MLE arm)
- *   then C posthoc uncorrected successes, C posthoc corrected successes.  C = 0 gives the 4T + 6 + F layout. */
+ *   then F: sims with factor f sparse-excluded (factor_excluded code 1)
+ *   then joint Wald successes (MLE arm), fits with boundary_hit != 0 (MLE arm)
+ *   then C posthoc uncorrected successes, C posthoc corrected successes
+ *   then converged fits with boundary_hit == 1 (singular fits), then F: sims where the GLM separation fallback
+ *   dropped factor f (factor_excluded code 2). */
 typedef struct McpBatchResult {
     uint32_t n_sims, n_sample_sizes, n_targets, n_factors;
     uint8_t* uncorrected;     /* [n_sims][n_ss][T]  or NULL */
@@ -81,6 +83,43 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
                   uint32_t n_sims, uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user,
                   McpBatchResult** out);
 void mcp_free_result(McpBatchResult* result);
+
+/* ---- Orchestrator entry points for ONE lowered scenario -------------------------
+ * find_power (engine-orchestrator/src/find_power.rs:337 + aggregation.rs:61-271): run_batch + the per-N PowerResult
+ * fold.  *json_out = JSON array of PowerResult (serde field names: n, n_sims, target_indices, contrast_pairs,
+ * power_uncorrected, power_corrected, ci_uncorrected, ci_corrected, convergence_rate, boundary_hit, estimator_extras,
+ * overall_significant_rate, success_counts_*, convergence_count, overall_significant_count, overall_significant_ci,
+ * success_count_histogram_*, grid_warnings, posthoc, factor_exclusion_counts, factor_separation_counts); free with
+ * mcp_free_string.  boundary_hit (per sim) is filled only when options->mode includes MCP_MODE_BYTES. */
+int mcp_find_power(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_sample_sizes,
+                   uint32_t n_sims, uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user,
+                   char** json_out);
+
+/* find_sample_size (find_sample_size.rs:83-257, grid.rs:37-330, fit.rs:45-246): cluster-aware grid over
+ * [from_size, to_size] (by = fixed step, or point count when by_auto != 0; log_grid != 0 = log-spaced), one run_batch
+ * over the grid, per-N fold, first-N lookups and model-based crossing fits.  *json_out = SampleSizeResult object
+ * (grid_or_trace, first_achieved, first_joint_achieved, fitted, fitted_joint, first_overall_achieved, fitted_overall,
+ * cluster_atom, target_power, grid_warnings). */
+int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_size, uint64_t to_size, uint64_t by,
+                         int32_t by_auto, int32_t log_grid, double target_power, uint32_t n_sims, uint64_t base_seed,
+                         const McpOptions* options, McpProgressFn progress, void* user, char** json_out);
+void mcp_free_string(char* s);
+
+/* CrossingFit (result.rs:416-450); status: 0 fitted, 1 at_or_below_min, 2 not_reached, 3 non_monotone. */
+typedef struct McpCrossingFit {
+    int32_t status;
+    int32_t has_ci_lo, has_ci_hi, has_n_approx;
+    double n_star, ci_lo, ci_hi, max_violation;
+    uint64_t n_achievable, n_min, n_approx;
+} McpCrossingFit;
+/* fit_crossing (fit.rs:45-120): monotonicity gate, PAVA, interpolated crossing, Wilson band inversion, probit hint. */
+int mcp_fit_crossing(const uint64_t* grid, const uint64_t* counts, uint32_t n_points, uint64_t n_sims, double target_power,
+                     uint64_t atom, McpCrossingFit* out);
+/* build_grid (grid.rs:37-147). */
+int mcp_build_grid(uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto, int32_t log_grid, uint64_t atom,
+                   uint64_t hard_min, uint64_t* grid_out, uint32_t capacity, uint32_t* n_out, uint32_t* n_warnings);
+/* wilson_ci (aggregation.rs:18-33). */
+void mcp_wilson_ci(uint64_t k, uint64_t n, double* lo, double* hi);
 
 /* introspect::capture_sim0_data twin (introspect.rs:104-155) for ANY sim id: the f32 design matrix
  * (column-major, max_n × P) and outcome the power kernel generates for (base_seed, sim_id). */

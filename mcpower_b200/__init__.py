@@ -7,4 +7,5 @@ libmcpower_b200.so (include/mcpower_b200.h).  There is no CPU fallback.
 from . import spec  # noqa: F401
 from .engine import (MODE_BYTES, MODE_CAPTURE, MODE_COUNTS, BatchResult, Cancelled, CorrelationNotPSD,  # noqa: F401
                      CudaError, EngineError, InvalidSpec, RankDeficient, Unsupported, counters_from_bytes, crit_table,
-                     device_count, fit_data, generate_sim, pipe_bench, run_batch, splitmix64)
+                     build_grid, device_count, find_power, find_sample_size, fit_crossing, fit_data, generate_sim,
+                     pipe_bench, run_batch, splitmix64, wilson_ci)

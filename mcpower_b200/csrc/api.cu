@@ -15,6 +15,7 @@
 #include "critvals.hpp"
 #include "device_math.cuh"
 #include "launch.h"
+#include "orchestrator.hpp"
 #include "pipe_bench.cuh"
 #include "spec.hpp"
 
@@ -597,6 +598,8 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.off_bh = pl.off_joint + 1;
     pl.off_ph_unc = pl.off_bh + 1;
     pl.off_ph_cor = pl.off_ph_unc + NPH;
+    pl.off_sing = pl.off_ph_cor + NPH;
+    pl.off_fsep = pl.off_sing + 1;
     lw.cw = pl.counter_width;
     pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
 }
@@ -665,15 +668,15 @@ void mcp_free_result(McpBatchResult* r) {
     std::free(r);
 }
 
-int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
-                  uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user, McpBatchResult** out) {
-    return guarded([&] {
-        if (!out) invalid("out pointer is NULL");
-        *out = nullptr;
+// run_batch on a parsed spec: validation, lowering, waves of kernel launches, result fetch.  Shared by mcp_run_batch and
+// the orchestrator entry points (mcp_find_power / mcp_find_sample_size).
+static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims, uint64_t base_seed,
+                                      const McpOptions* options, McpProgressFn progress, void* user) {
+    McpBatchResult* result_out = nullptr;
+    {
         McpOptions opt{-1, MCP_MODE_COUNTS, 0, 0, 0};
         if (options) opt = *options;
         if (opt.mode == 0) opt.mode = MCP_MODE_COUNTS;
-        Spec s = parse_spec(spec_json, spec_len);
         validate_spec(s, sample_sizes, n_ss);
         check_supported(s);
         select_device(opt.device);
@@ -838,8 +841,200 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
         }
         if (capture) fetch(r->t_sq, pl.out_tsq, cells * T);
         guard.ok = true;
-        *out = r;
+        result_out = r;
+    }
+    return result_out;
+}
+
+int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
+                  uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user, McpBatchResult** out) {
+    return guarded([&] {
+        if (!out) invalid("out pointer is NULL");
+        *out = nullptr;
+        Spec s = parse_spec(spec_json, spec_len);
+        *out = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user);
     });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Orchestrator entry points: the callers of run_batch, for ONE lowered scenario.
+
+// aggregate_batch (aggregation.rs:61-271) from the per-cell counters the kernels reduced (identical integers to the
+// fold over the byte tensors: tests prove COUNTS == aggregate(BYTES)).
+static std::vector<orch::PowerResult> power_results_from(const Spec& s, const McpBatchResult* r, const uint32_t* ss) {
+    const int T = (int)r->n_targets, F = (int)r->n_factors, C = (int)r->n_posthoc, J = T + C;
+    const int off_hc = 2 * T + 3 + J, off_fx = off_hc + J + 1, off_joint = off_fx + F, off_bh = off_joint + 1;
+    const int off_pu = off_bh + 1, off_pc = off_pu + C, off_sing = off_pc + C, off_fsep = off_sing + 1;
+    std::vector<orch::PowerResult> out(r->n_sample_sizes);
+    for (uint32_t g = 0; g < r->n_sample_sizes; g++) {
+        const uint64_t* row = r->counters + (size_t)g * r->counter_width;
+        orch::PowerResult& pr = out[g];
+        pr.n = ss[g];
+        pr.n_sims = r->n_sims;
+        pr.target_indices = s.target_indices;
+        pr.contrast_pairs = s.contrast_pairs;
+        pr.k_unc.assign(row, row + T);
+        pr.k_cor.assign(row + T, row + 2 * T);
+        pr.conv_count = row[2 * T];
+        pr.overall_count = row[2 * T + 1];
+        pr.has_overall = s.report_overall;
+        pr.hist_unc.assign(row + 2 * T + 2, row + 2 * T + 3 + J);
+        pr.hist_cor.assign(row + off_hc, row + off_hc + J + 1);
+        pr.excl_sparse.assign(row + off_fx, row + off_fx + F);
+        pr.excl_sep.assign(row + off_fsep, row + off_fsep + F);
+        pr.estimator = s.estimator == E_OLS ? 0 : (s.estimator == E_GLM ? 1 : 2);
+        pr.joint_count = row[off_joint];
+        pr.boundary_hits = row[off_bh];
+        pr.singular_count = row[off_sing];
+        size_t o = 0;
+        for (size_t b = 0; b < s.posthoc_block_ncontrasts.size(); b++) {
+            orch::PosthocPower ph;
+            ph.n_levels = (uint64_t)s.posthoc_block_levels[b];
+            const int m = s.posthoc_block_ncontrasts[b];
+            ph.k_unc.assign(row + off_pu + o, row + off_pu + o + m);
+            ph.k_cor.assign(row + off_pc + o, row + off_pc + o + m);
+            o += (size_t)m;
+            pr.posthoc.push_back(ph);
+        }
+        if (r->boundary_hit)
+            for (uint32_t i = 0; i < r->n_sims; i++) pr.boundary_hit.push_back(r->boundary_hit[(size_t)i * r->n_sample_sizes + g]);
+    }
+    return out;
+}
+
+static char* dup_json(const std::string& s) {
+    char* p = static_cast<char*>(std::malloc(s.size() + 1));
+    std::memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+
+// find_power for one scenario (find_power.rs:337 + aggregate_batch): JSON array of PowerResult, one per sample size.
+int mcp_find_power(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
+                   uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user, char** json_out) {
+    return guarded([&] {
+        if (!json_out) invalid("json_out pointer is NULL");
+        *json_out = nullptr;
+        Spec s = parse_spec(spec_json, spec_len);
+        McpBatchResult* r = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user);
+        struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
+        const std::vector<orch::PowerResult> per_n = power_results_from(s, r, sample_sizes);
+        std::string o = "[";
+        for (size_t i = 0; i < per_n.size(); i++) {
+            if (i) o += ',';
+            orch::power_result_json(o, per_n[i]);
+        }
+        o += ']';
+        *json_out = dup_json(o);
+    });
+}
+
+// find_sample_size for one scenario (find_sample_size.rs:83-257): cluster-aware grid, one run_batch over the whole
+// grid (nested row prefixes of the same studies), per-N PowerResult fold, grid-empirical first-N and model-based
+// crossing fits per target / per joint count / for the overall test.  JSON object = SampleSizeResult.
+int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto,
+                         int32_t log_grid, double target_power, uint32_t n_sims, uint64_t base_seed, const McpOptions* options,
+                         McpProgressFn progress, void* user, char** json_out) {
+    return guarded([&] {
+        if (!json_out) invalid("json_out pointer is NULL");
+        *json_out = nullptr;
+        Spec s = parse_spec(spec_json, spec_len);
+        // resolve_cluster_grid_params (find_sample_size.rs:24-79); limits from configs/config.json:27-28
+        const uint64_t min_rows = 2, min_clusters = 5;
+        uint64_t atom = 1, hard_min = 1;
+        std::vector<std::string> warnings;
+        if (s.has_cluster) {
+            const uint64_t v = (uint64_t)std::max(s.sizing_value, 1);
+            atom = v;
+            if (!s.sizing_fixed_size) {
+                if (v < min_clusters) warnings.push_back("only " + std::to_string(v) + " clusters (< " + std::to_string(min_clusters) + "); τ² estimates may be unstable");
+                hard_min = v * min_rows;
+            } else {
+                if (v < min_rows) invalid("cluster_size " + std::to_string(v) + " is below the minimum rows per cluster " + std::to_string(min_rows));
+                hard_min = min_clusters * v;
+            }
+        }
+        std::vector<uint64_t> grid;
+        const orch::GridError ge = orch::build_grid(from_size, to_size, by, by_auto != 0, log_grid != 0, atom, hard_min, grid, warnings);
+        if (ge == orch::GRID_INVALID_BOUNDS) invalid("sample-size bounds: need 1 <= from <= to");
+        if (ge == orch::GRID_EMPTY) invalid("no multiple of the cluster atom lies inside the sample-size bounds");
+        if (ge == orch::GRID_SINGLE_POINT) invalid("the sample-size bounds leave a single grid point after cluster snapping");
+        if (ge != orch::GRID_OK) invalid("cluster atom must be positive");
+        std::vector<uint32_t> ss(grid.begin(), grid.end());
+        McpBatchResult* r = run_batch_core(s, ss.data(), (uint32_t)ss.size(), n_sims, base_seed, options, progress, user);
+        struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
+        const std::vector<orch::PowerResult> per_n = power_results_from(s, r, ss.data());
+        const orch::SampleSizeDerivations d = orch::derive_sample_size_outputs(per_n, grid, target_power, atom);
+        std::string o = "{\"grid_or_trace\":[";
+        for (size_t i = 0; i < per_n.size(); i++) {
+            if (i) o += ',';
+            orch::power_result_json(o, per_n[i]);
+        }
+        o += "],\"first_achieved\":";
+        orch::jarr(o, d.first_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
+        o += ",\"first_joint_achieved\":";
+        orch::jarr(o, d.first_joint_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
+        o += ",\"fitted\":";
+        orch::jarr(o, d.fitted, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
+        o += ",\"fitted_joint\":";
+        orch::jarr(o, d.fitted_joint, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
+        o += ",\"first_overall_achieved\":";
+        orch::jopt(o, d.has_overall ? d.first_overall_achieved : -1);
+        o += ",\"fitted_overall\":";
+        if (d.has_overall) orch::crossing_fit_json(o, d.fitted_overall);
+        else o += "null";
+        o += ",\"cluster_atom\":" + std::to_string(atom) + ",\"target_power\":";
+        orch::jnum(o, target_power);
+        o += ",\"grid_warnings\":";
+        orch::jarr(o, warnings, [](std::string& t, const std::string& w) { orch::jstr(t, w); });
+        o += ",\"kernel_ms\":";
+        orch::jnum(o, r->kernel_ms);
+        o += '}';
+        *json_out = dup_json(o);
+    });
+}
+
+void mcp_free_string(char* s) { std::free(s); }
+
+// Pure helpers, exported so the reference's known-answer tests (fit.rs:262-491, grid.rs:393-638, aggregation.rs)
+// run against this implementation.
+int mcp_fit_crossing(const uint64_t* grid, const uint64_t* counts, uint32_t n_points, uint64_t n_sims, double target_power,
+                     uint64_t atom, McpCrossingFit* out) {
+    return guarded([&] {
+        if (!out) invalid("out pointer is NULL");
+        const orch::CrossingFit f = orch::fit_crossing(std::vector<uint64_t>(grid, grid + n_points),
+                                                       std::vector<uint64_t>(counts, counts + n_points), n_sims, target_power, atom);
+        out->status = f.status;
+        out->n_star = f.n_star;
+        out->n_achievable = f.n_achievable;
+        out->has_ci_lo = f.has_ci_lo;
+        out->has_ci_hi = f.has_ci_hi;
+        out->ci_lo = f.ci_lo;
+        out->ci_hi = f.ci_hi;
+        out->n_min = f.n_min;
+        out->has_n_approx = f.has_n_approx;
+        out->n_approx = f.n_approx;
+        out->max_violation = f.max_violation;
+    });
+}
+
+int mcp_build_grid(uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto, int32_t log_grid, uint64_t atom,
+                   uint64_t hard_min, uint64_t* grid_out, uint32_t capacity, uint32_t* n_out, uint32_t* n_warnings) {
+    return guarded([&] {
+        std::vector<uint64_t> grid;
+        std::vector<std::string> warnings;
+        const orch::GridError ge = orch::build_grid(from_size, to_size, by, by_auto != 0, log_grid != 0, atom, hard_min, grid, warnings);
+        if (ge != orch::GRID_OK) invalid("build_grid: error " + std::to_string((int)ge));
+        if (grid.size() > capacity) invalid("build_grid: capacity too small");
+        std::copy(grid.begin(), grid.end(), grid_out);
+        if (n_out) *n_out = (uint32_t)grid.size();
+        if (n_warnings) *n_warnings = (uint32_t)warnings.size();
+    });
+}
+
+void mcp_wilson_ci(uint64_t k, uint64_t n, double* lo, double* hi) {
+    const orch::Ci c = orch::wilson_ci(k, n);
+    *lo = c.lo;
+    *hi = c.hi;
 }
 
 int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uint64_t base_seed, uint64_t sim_id, int32_t device,

@@ -349,9 +349,13 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
         atomicAdd(&cg[2 * T + 2 + n_unc], 1ull);
         atomicAdd(&cg[pl.off_hist_cor + n_cor], 1ull);
     }
-    for (int f = 0; f < pl.n_factors; f++) count_flag(cs, cg, pl.off_fx + f, excl_flags && excl_flags[f] != 0);
+    for (int f = 0; f < pl.n_factors; f++) {
+        count_flag(cs, cg, pl.off_fx + f, excl_flags && excl_flags[f] == 1);
+        count_flag(cs, cg, pl.off_fsep + f, excl_flags && excl_flags[f] == 2);
+    }
     count_flag(cs, cg, pl.off_joint, joint_sig != 0);
     count_flag(cs, cg, pl.off_bh, boundary != 0);
+    count_flag(cs, cg, pl.off_sing, fit.converged && boundary == 1);
     for (int c = 0; c < NPH; c++) {
         count_flag(cs, cg, pl.off_ph_unc + c, ph_unc[c] != 0);
         count_flag(cs, cg, pl.off_ph_cor + c, ph_cor[c] != 0);

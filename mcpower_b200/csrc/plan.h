@@ -110,7 +110,7 @@ struct DevicePlan {
     double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
     int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
     int32_t counter_width;             // 4T + 6 + n_factors + 4 n_ph
-    int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor;  // counter-row offsets (below)
+    int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor, off_sing, off_fsep;  // counter-row offsets (below)
     int32_t smem_counters;             // counters staged in shared memory (fits)
 };
 
@@ -122,10 +122,11 @@ struct DevicePlan {
 //   2T+1                     overall-test successes
 //   [2T+2, 2T+3+J)           histogram of #uncorrected-significant tests per sim (targets + posthoc contrasts, J+1 buckets)
 //   [off_hist_cor, +J+1)     histogram of #corrected-significant tests per sim
-//   [off_fx, +F)             sims with factor f excluded
+//   [off_fx, +F)             sims with factor f sparse-excluded (factor_excluded code 1: factor_exclusion_counts)
 //   off_joint                joint Wald successes (MLE arm; 0 otherwise)
-//   off_bh                   fits with a variance component on the boundary (MLE arm; 0 otherwise)
+//   off_bh                   fits with boundary_hit != 0 (MLE arm; 0 otherwise)
 //   [off_ph_unc, +n_ph)      posthoc uncorrected successes per contrast
 //   [off_ph_cor, +n_ph)      posthoc corrected successes per contrast
-// With n_ph = 0 this is the 4T + 6 + F layout of round 1.
-static inline int mcp_counter_width(int T, int F, int n_ph) { return 4 * T + 6 + F + 4 * n_ph; }
+//   off_sing                 converged fits pinned at the variance boundary (boundary_hit == 1: singular_count)
+//   [off_fsep, +F)           sims where the GLM separation fallback dropped factor f (code 2: factor_separation_counts)
+static inline int mcp_counter_width(int T, int F, int n_ph) { return 4 * T + 7 + 2 * F + 4 * n_ph; }

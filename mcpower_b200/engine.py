@@ -79,7 +79,14 @@ class _Result(C.Structure):
 _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
 
 EXPORTS = ("mcp_run_batch", "mcp_free_result", "mcp_generate_sim", "mcp_fit_data", "mcp_crit_table", "mcp_splitmix64",
-           "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version")
+           "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version", "mcp_find_power", "mcp_find_sample_size",
+           "mcp_free_string", "mcp_fit_crossing", "mcp_build_grid", "mcp_wilson_ci")
+
+
+class _CrossingFit(C.Structure):
+    _fields_ = [("status", C.c_int32), ("has_ci_lo", C.c_int32), ("has_ci_hi", C.c_int32), ("has_n_approx", C.c_int32),
+                ("n_star", C.c_double), ("ci_lo", C.c_double), ("ci_hi", C.c_double), ("max_violation", C.c_double),
+                ("n_achievable", C.c_uint64), ("n_min", C.c_uint64), ("n_approx", C.c_uint64)]
 
 _lib = None
 
@@ -112,6 +119,23 @@ def lib():
     L.mcp_splitmix64.argtypes = [C.c_uint64]
     L.mcp_pipe_bench.restype = C.c_int
     L.mcp_pipe_bench.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.mcp_find_power.restype = C.c_int
+    L.mcp_find_power.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint64,
+                                 C.POINTER(_Options), _PROGRESS, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mcp_find_sample_size.restype = C.c_int
+    L.mcp_find_sample_size.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
+                                       C.c_double, C.c_uint32, C.c_uint64, C.POINTER(_Options), _PROGRESS, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]
+    L.mcp_free_string.restype = None
+    L.mcp_free_string.argtypes = [C.c_void_p]
+    L.mcp_fit_crossing.restype = C.c_int
+    L.mcp_fit_crossing.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32, C.c_uint64, C.c_double,
+                                   C.c_uint64, C.POINTER(_CrossingFit)]
+    L.mcp_build_grid.restype = C.c_int
+    L.mcp_build_grid.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64,
+                                 C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.mcp_wilson_ci.restype = None
+    L.mcp_wilson_ci.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mcp_device_count.restype = C.c_int
     L.mcp_last_error.restype = C.c_char_p
     L.mcp_version.restype = C.c_char_p
@@ -136,7 +160,7 @@ class BatchResult:
     n_sample_sizes: int
     n_targets: int
     n_factors: int
-    counters: np.ndarray                       # [n_ss, 4T+6+F+4C] uint64 (layout: include/mcpower_b200.h)
+    counters: np.ndarray                       # [n_ss, 4T+7+2F+4C] uint64 (layout: include/mcpower_b200.h)
     uncorrected: Optional[np.ndarray] = None   # [n_sims, n_ss, T] uint8
     corrected: Optional[np.ndarray] = None
     converged: Optional[np.ndarray] = None     # [n_sims, n_ss]
@@ -209,6 +233,15 @@ class BatchResult:
         o = self._off_fx + self.n_factors + 2 + self.n_posthoc
         return self.counters[:, o:o + self.n_posthoc]
 
+    @property
+    def n_singular(self):
+        return self.counters[:, self._off_fx + self.n_factors + 2 + 2 * self.n_posthoc]
+
+    @property
+    def n_factor_separation(self):
+        o = self._off_fx + self.n_factors + 3 + 2 * self.n_posthoc
+        return self.counters[:, o:o + self.n_factors]
+
     def power(self, corrected: bool = False) -> np.ndarray:
         """successes / n_sims per (sample size, target) — PowerResult.power (aggregation.rs)."""
         s = self.success_corrected if corrected else self.success_uncorrected
@@ -223,7 +256,7 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
     F = 0 if factor_excluded is None else factor_excluded.shape[2]
     Cph = 0 if posthoc_unc is None else posthoc_unc.shape[2]
     J = T + Cph
-    out = np.zeros((n_ss, 4 * T + 6 + F + 4 * Cph), dtype=np.uint64)
+    out = np.zeros((n_ss, 4 * T + 7 + 2 * F + 4 * Cph), dtype=np.uint64)
     out[:, :T] = uncorrected.sum(axis=0)
     out[:, T:2 * T] = corrected.sum(axis=0)
     out[:, 2 * T] = converged.sum(axis=0)
@@ -240,11 +273,13 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
         out[g, 2 * T + 2:2 * T + 3 + J] = np.bincount(nu[:, g], minlength=J + 1)
         out[g, o_hc:o_hc + J + 1] = np.bincount(nc[:, g], minlength=J + 1)
     if F:
-        out[:, o_fx:o_fx + F] = (factor_excluded != 0).sum(axis=0)
+        out[:, o_fx:o_fx + F] = (factor_excluded == 1).sum(axis=0)
+        out[:, o_fx + F + 3 + 2 * Cph:o_fx + 2 * F + 3 + 2 * Cph] = (factor_excluded == 2).sum(axis=0)
     if joint is not None:
         out[:, o_fx + F] = joint.sum(axis=0)
     if boundary_hit is not None:
         out[:, o_fx + F + 1] = (boundary_hit != 0).sum(axis=0)
+        out[:, o_fx + F + 2 + 2 * Cph] = ((boundary_hit == 1) & (converged != 0)).sum(axis=0)
     if Cph:
         out[:, o_fx + F + 2:o_fx + F + 2 + Cph] = posthoc_unc.sum(axis=0)
         out[:, o_fx + F + 2 + Cph:o_fx + F + 2 + 2 * Cph] = posthoc_cor.sum(axis=0)
@@ -362,3 +397,84 @@ def pipe_bench(kind: int, device: int = -1) -> float:
 
 def device_count() -> int:
     return int(lib().mcp_device_count())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Orchestrator entry points for one lowered scenario (engine-orchestrator: find_power / find_sample_size)
+def _take_json(ptr) -> object:
+    try:
+        return json.loads(C.string_at(ptr).decode("utf-8"))
+    finally:
+        lib().mcp_free_string(ptr)
+
+
+def find_power(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: int, *, mode: int = MODE_COUNTS,
+               device: int = -1, sim_begin: int = 0) -> list:
+    """find_power for one scenario: run_batch + aggregate_batch → one PowerResult dict per sample size
+    (field names of engine-orchestrator/src/result.rs:54-144)."""
+    blob = json.dumps(spec).encode()
+    ss32 = np.ascontiguousarray(np.asarray(list(sample_sizes), dtype=np.uint32))
+    opt = _Options(device, mode, sim_begin, 0, 0)
+    out = C.c_void_p()
+    rc = lib().mcp_find_power(blob, len(blob), ss32.ctypes.data_as(C.POINTER(C.c_uint32)), ss32.size, int(n_sims),
+                              base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    return _take_json(out)
+
+
+def find_sample_size(spec: dict, from_size: int, to_size: int, n_sims: int, base_seed: int, *, by: Optional[int] = None,
+                     count: int = 12, log_grid: bool = False, target_power: float = 80.0, device: int = -1) -> dict:
+    """find_sample_size for one scenario (find_sample_size.rs:83-257): `by` = fixed step (linear) / point count (log);
+    by=None → ~`count` auto-placed points.  Returns the SampleSizeResult dict."""
+    blob = json.dumps(spec).encode()
+    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    out = C.c_void_p()
+    rc = lib().mcp_find_sample_size(blob, len(blob), int(from_size), int(to_size), int(count if by is None else by),
+                                    1 if by is None else 0, 1 if log_grid else 0, float(target_power), int(n_sims),
+                                    base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    return _take_json(out)
+
+
+_FIT_STATUS = ("fitted", "at_or_below_min", "not_reached", "non_monotone")
+
+
+def fit_crossing(grid: Sequence[int], counts: Sequence[int], n_sims: int, target_power: float, atom: int = 1) -> dict:
+    """fit_crossing (fit.rs:45-120) → CrossingFit as a dict tagged by `status`."""
+    g = np.ascontiguousarray(np.asarray(list(grid), dtype=np.uint64))
+    k = np.ascontiguousarray(np.asarray(list(counts), dtype=np.uint64))
+    f = _CrossingFit()
+    rc = lib().mcp_fit_crossing(g.ctypes.data_as(C.POINTER(C.c_uint64)), k.ctypes.data_as(C.POINTER(C.c_uint64)), g.size,
+                                int(n_sims), float(target_power), int(atom), C.byref(f))
+    if rc != 0:
+        _raise(rc)
+    st = _FIT_STATUS[f.status]
+    if st == "fitted":
+        return {"status": st, "n_star": f.n_star, "n_achievable": int(f.n_achievable),
+                "ci_lo": f.ci_lo if f.has_ci_lo else None, "ci_hi": f.ci_hi if f.has_ci_hi else None}
+    if st == "at_or_below_min":
+        return {"status": st, "n_min": int(f.n_min)}
+    if st == "not_reached":
+        return {"status": st, "n_approx": int(f.n_approx) if f.has_n_approx else None}
+    return {"status": st, "max_violation": f.max_violation}
+
+
+def build_grid(from_size: int, to_size: int, *, by: Optional[int] = None, count: int = 12, log_grid: bool = False,
+               atom: int = 1, hard_min: int = 1):
+    """build_grid (grid.rs:37-147) → (grid list, number of advisory warnings)."""
+    buf = np.zeros(1 << 16, dtype=np.uint64)
+    n, w = C.c_uint32(), C.c_uint32()
+    rc = lib().mcp_build_grid(int(from_size), int(to_size), int(count if by is None else by), 1 if by is None else 0,
+                              1 if log_grid else 0, int(atom), int(hard_min), buf.ctypes.data_as(C.POINTER(C.c_uint64)),
+                              buf.size, C.byref(n), C.byref(w))
+    if rc != 0:
+        _raise(rc)
+    return [int(v) for v in buf[:n.value]], int(w.value)
+
+
+def wilson_ci(k: int, n: int):
+    lo, hi = C.c_double(), C.c_double()
+    lib().mcp_wilson_ci(int(k), int(n), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
