@@ -147,3 +147,32 @@ def posthoc_spec(method: str = "none") -> dict:
     s["factor_min_level_count"] = 5
     s["report_overall"] = True
     return s
+
+
+def crossing_goldens() -> dict:
+    """End-to-end goldens of the shipped engine (validation/data/cross_*.golden.rds via tests/golden/make_crossing_goldens.py)."""
+    return json.loads((GOLDEN / "crossing_goldens.json").read_text())
+
+
+def crossing_spec(case: dict) -> dict:
+    """Lowered SimulationSpec of a CROSS_CASES entry as the public API builds it (validation/common.R:60-72): standardized
+    Normal predictors, every effect a target, alpha 0.05, no correction, optimistic scenario, overall test reported."""
+    from mcpower_b200 import spec as S
+    effects = list(case["effects"].values())
+    s = S.base_spec(len(effects))
+    s["effect_sizes"] = [0.0] + [float(e) for e in effects]
+    s["target_indices"] = list(range(1, len(effects) + 1))
+    s["report_overall"] = True
+    if case["family"] == "logit":
+        s["effect_sizes"][0] = S.logit_intercept(case["baseline_probability"])
+        s["outcome_kind"] = "binary"
+        s["estimator"] = "glm"
+        s["max_failed_fraction"] = 0.25
+    elif case["family"] == "lme":
+        icc = case["cluster"]["ICC"]
+        s["estimator"] = "mle"
+        s["report_overall"] = False
+        s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": case["cluster"]["n_clusters"]}},
+                        "tau_squared": icc / (1.0 - icc), "slopes": [], "extra_groupings": []}
+        s["max_failed_fraction"] = 0.25
+    return s

@@ -22,7 +22,7 @@ SEED = 0x9E3779B97F4A7C15
 # models, which falls back to the general quad kernel where a spec is outside its family) must produce the same bits
 # on the same inputs: every run_batch test below runs once per forced kernel choice.  Tests that never reach the OLS power
 # kernel (generated-design dumps, supplied-bytes fits, GLM / LMM arms, host-side errors) run once.
-_NOT_OLS_POWER = ("generated_design", "marginal_transforms", "pinned_residual", "sampled_factors_and_cluster",
+_NOT_OLS_POWER = ("cross_lme", "cross_glm", "generated_design", "marginal_transforms", "pinned_residual", "sampled_factors_and_cluster",
                   "prefix_stability", "fit_on_reference", "design_draw", "logit", "probit", "glm", "lmm", "errors")
 
 
@@ -470,3 +470,23 @@ def test_power_is_monotone_in_n_full_grid():
     p = r.power()[:, 0]
     assert p[-1] > 0.99 and np.all(np.diff(p) > -0.02)
     assert np.all(r.hist_uncorrected.sum(axis=1) == 20000)
+
+
+# ------------------------------------------------------------------ end-to-end vs the SHIPPED ENGINE's own outputs
+@pytest.mark.parametrize("name", ["cross_ols", "cross_partial", "cross_lme", "cross_glm"])
+def test_find_sample_size_reproduces_the_engines_frozen_required_n(name):
+    """The reference engine's own find_sample_size results (validation/data/cross_*.golden.rds: 20..300 by 2, 100000 sims per
+    cell, seed 2137, public API) reproduced through mcp_find_sample_size: OLS (lean quad + solve kernels), logistic GLM
+    (IRLS kernel), random-intercept LMM (REML kernel, cluster atom 10) and the not-reached case."""
+    g = CS.crossing_goldens()[name]
+    r = M.find_sample_size(CS.crossing_spec(g["case"]), g["from_size"], g["to_size"], g["n_sims"], M.splitmix64(g["seed"]),
+                           by=g["by"])
+    assert r["cluster_atom"] == g["case"].get("cluster", {}).get("n_clusters", 1)
+    for fit, want in zip(r["fitted"], g["dense"].values()):
+        assert fit["status"] == want["status"], (name, fit)
+        if want["status"] == "fitted":
+            assert fit["n_achievable"] == want["n_achievable"], (name, fit)
+    pr = r["grid_or_trace"][-1]
+    assert pr["n"] == 300 and pr["n_sims"] == g["n_sims"] and sum(pr["success_count_histogram_corrected"]) == g["n_sims"]
+    lo, hi = M.wilson_ci(pr["success_counts_corrected"][0], pr["n_sims"])
+    assert pr["ci_corrected"][0] == {"lo": lo, "hi": hi}

@@ -348,3 +348,25 @@ def test_power_matches_noncentral_t():
     power = CS.analytic_ols_power(0.18, n, 9)
     emp = r["uncorrected"][:, 0, 0].mean()
     assert abs(emp - power) < 4 * math.sqrt(power * (1 - power) / n_sims) + 1e-4, (emp, power)
+
+
+# ---------------------------------------------------------------- end-to-end vs the SHIPPED ENGINE's own outputs
+@pytest.mark.parametrize("name", ["cross_ols", "cross_partial", "cross_lme", "cross_glm"])
+def test_oracle_reproduces_the_engines_frozen_required_n(name):
+    """validation/data/cross_*.golden.rds: `find_sample_size(20..300 by 2, 100000 sims, seed 2137)` run by the reference
+    engine through its public API (validation_crossing.rmd:112-135).  The oracle's per-cell corrected counts, folded by the
+    product's host-side crossing fit (fit.rs twin, itself pinned by the reference's KATs in test_orchestrator_host.py),
+    must give the same status and required N for every target — RNG, data generation, OLS / IRLS / REML fits, decisions,
+    aggregation, grid snapping and crossing fit, end to end."""
+    import mcpower_b200 as M
+    g = CS.crossing_goldens()[name]
+    s = CS.crossing_spec(g["case"])
+    atom = g["case"].get("cluster", {}).get("n_clusters", 1)
+    grid, _ = M.build_grid(g["from_size"], g["to_size"], by=g["by"], atom=atom, hard_min=2 * atom if atom > 1 else 1)
+    r = orc.run_batch(s, grid, g["n_sims"], orc.splitmix64(g["seed"]), n_threads=orc.host_threads())
+    counts = r["corrected"].sum(axis=0)
+    for t, want in enumerate(g["dense"].values()):
+        fit = M.fit_crossing(grid, counts[:, t], g["n_sims"], 80.0, atom)
+        assert fit["status"] == want["status"], (name, t, fit)
+        if want["status"] == "fitted":
+            assert fit["n_achievable"] == want["n_achievable"], (name, t, fit)
