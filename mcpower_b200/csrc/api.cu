@@ -590,6 +590,7 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     }
     bool need_t3 = false;
     for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
+    for (int v : s.new_dists) need_t3 |= v == D_HIGH_KURTOSIS;  // a scenario swap can introduce the t(3) marginal
     if (need_t3) pl.t3_table = lw.bufs.upload(crit::build_t3_table());
     pl.counter_width = mcp_counter_width(T, F, NPH);
     pl.off_hist_cor = 2 * T + 3 + (T + NPH);

@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Extract the reference's frozen scenario-perturbation goldens (validation/data/scenario_golden.rds) into a fixture.
+
+Each value is a statistic the SHIPPED engine's generated data produced in validation_scenarios.rmd (K draws, draw k = sim 0
+of base_seed = splitmix64(seed + k) under a one-knob custom scenario; case list validation/formulas.R:705-830, probes
+validation/common.R:895-1075), frozen with `golden_abs = 1e-9` (tolerances.R:146).  Run HERE (needs /root/reference).
+"""
+import json
+from pathlib import Path
+
+import make_fixtures as mf
+
+CASES = {  # validation/formulas.R:708-806
+    "scen_he": {"effects": [0.40, 0.25], "knobs": {"heterogeneity": 0.4}, "n": 4000, "K": 200, "seed": 31000},
+    "scen_hs": {"effects": [0.25], "knobs": {"heteroskedasticity_ratio": 4.0}, "n": 4000, "K": 200, "seed": 32000},
+    "scen_co_low": {"effects": [0.25, 0.25], "corr": 0.3, "knobs": {"correlation_noise_sd": 0.15}, "n": 4000, "K": 400, "seed": 33000},
+    "scen_co_high": {"effects": [0.25, 0.25], "corr": 0.75, "knobs": {"correlation_noise_sd": 0.15}, "n": 2000, "K": 800, "seed": 34000},
+    "scen_co_psd": {"effects": [0.25, 0.25, 0.25], "corr": 0.6, "knobs": {"correlation_noise_sd": 0.3}, "n": 2000, "K": 400, "seed": 35000},
+    "scen_px": {"effects": [0.25, 0.25], "knobs": {"distribution_change_prob": 0.5}, "n": 4000, "K": 400, "seed": 36000},
+    "scen_px_t3": {"effects": [0.25], "knobs": {"distribution_change_prob": 1.0, "new_distributions": ["high_kurtosis"]},
+                   "n": 4000, "K": 200, "seed": 37000},
+    "scen_re": {"effects": [0.25], "knobs": {"residual_change_prob": 0.5, "residual_df": 10.0}, "n": 4000, "K": 400, "seed": 38000},
+    "scen_re_replace": {"effects": [0.25], "residual": "high_kurtosis",
+                        "knobs": {"residual_change_prob": 1.0, "residual_dists": ["right_skewed"], "residual_df": 6.0},
+                        "n": 4000, "K": 200, "seed": 39000},
+}
+
+
+def main():
+    g = mf.plain(mf.read_rds(Path("/root/reference/validation/data/scenario_golden.rds")))
+    out = {}
+    for name, case in CASES.items():
+        vals = {k: (v[0] if isinstance(v, list) else v) for k, v in g[name].items()}
+        out[name] = {"case": case, "golden": vals}
+    path = Path(__file__).resolve().parent / "scenario_goldens.json"
+    path.write_text(json.dumps(out, indent=1, ensure_ascii=False))
+    print(path, len(out))
+
+
+if __name__ == "__main__":
+    main()
