@@ -18,6 +18,8 @@ def spec_of(case: dict) -> dict:
     s = S.base_spec(k)
     s["effect_sizes"] = [0.0] + [float(e) for e in case["effects"]]
     s["target_indices"] = list(range(1, k + 1))
+    if "factor" in case:
+        s = S.add_factor(s, case["factor"]["proportions"], case["factor"]["effects"])
     if "corr" in case:
         s["correlation"] = [1.0 if i == j else case["corr"] for j in range(k) for i in range(k)]
     if "residual" in case:  # set_residual_distribution PINS the residual (scenarios.rs:163-186)
@@ -75,6 +77,20 @@ def statistics(name: str, draw) -> dict:
     K, seed = case["K"], case["seed"]
     tb = np.array([0.0] + case["effects"])
     draws = (draw(seed + k) for k in range(1, K + 1))
+    if name == "scen_fa_ols":  # run_fa: draw(seed, sampled) here; level counts from the dummy columns
+        props, n = np.array(case["factor"]["proportions"]), case["n"]
+
+        def counts(X):
+            d = X[:, 2:2 + len(props) - 1].sum(axis=0)
+            return np.concatenate([[n - d.sum()], d])
+
+        c_fix = np.array([counts(draw(seed + k, False)[0]) for k in range(1, 21)])
+        c_smp = np.array([counts(draw(seed + 500 + k, True)[0]) for k in range(1, K + 1)])
+        out = {"fixed: counts identical across draws (no RNG)": float((c_fix == c_fix[0]).all()),
+               "fixed: max |count − n·p| ≤ 1 (largest remainder)": float(np.abs(c_fix - n * props).max())}
+        for g in range(len(props)):
+            out[f"sampled: Var(count) level {g + 1} = n·p(1−p)"] = float(((c_smp[:, g] - n * props[g]) ** 2).mean())
+        return out
     if name == "scen_he":  # run_he: slope of squared true-beta residuals on the squared predictors
         sl = []
         for X, y in draws:

@@ -23,6 +23,10 @@ CASES = {  # validation/formulas.R:708-806
     "scen_re_replace": {"effects": [0.25], "residual": "high_kurtosis",
                         "knobs": {"residual_change_prob": 1.0, "residual_dists": ["right_skewed"], "residual_df": 6.0},
                         "n": 4000, "K": 200, "seed": 39000},
+    # g = (factor, 0.5, 0.3, 0.2); fixed walk under the optimistic scenario (20 draws, seed + k), sampled levels under
+    # sampled_factor_proportions (K draws, seed + 500 + k): run_fa, validation_scenarios.rmd:262-283
+    "scen_fa_ols": {"effects": [0.25], "factor": {"proportions": [0.5, 0.3, 0.2], "effects": [0.50, 0.80]},
+                    "knobs": {"sampled_factor_proportions": True}, "n": 1000, "K": 400, "seed": 40000},
 }
 
 

@@ -11,6 +11,12 @@ import _scenario_probes as SP
 TOL = 1e-9  # SCENARIO_TOL$golden_abs
 
 
+def _with_sampling(spec, sampled):
+    sp = dict(spec)
+    sp["scenario"] = dict(spec["scenario"], sampled_factor_proportions=bool(sampled))
+    return sp
+
+
 def _check(name, draw):
     got = SP.statistics(name, draw)
     for key, want in SP.GOLDEN[name]["golden"].items():
@@ -23,8 +29,9 @@ def test_oracle_reproduces_engine_scenario_goldens(name):
     case = SP.GOLDEN[name]["case"]
     spec = SP.spec_of(case)
 
-    def draw(seed):
-        x, y, _ = orc.generate_sim(spec, orc.splitmix64(seed), 0, case["n"])
+    def draw(seed, sampled=None):
+        sp = spec if sampled is None else _with_sampling(spec, sampled)
+        x, y, _ = orc.generate_sim(sp, orc.splitmix64(seed), 0, case["n"])
         return x.astype(np.float64), y.astype(np.float64)
 
     _check(name, draw)
@@ -37,8 +44,9 @@ def test_cuda_data_plane_reproduces_engine_scenario_goldens(name):
     case = SP.GOLDEN[name]["case"]
     spec = SP.spec_of(case)
 
-    def draw(seed):
-        x, y = M.generate_sim(spec, M.splitmix64(seed), 0, case["n"])
+    def draw(seed, sampled=None):
+        sp = spec if sampled is None else _with_sampling(spec, sampled)
+        x, y = M.generate_sim(sp, M.splitmix64(seed), 0, case["n"])
         return x.astype(np.float64), y.astype(np.float64)
 
     _check(name, draw)
