@@ -86,13 +86,24 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
 #pragma unroll
         for (int i = 0; i < PT; i++) b[i] = 0.0;
         dev = 0.0;
+        // software pipeline: row i + 1 is fetched (coalesced, L2/HBM) while row i's ~300 instructions run
+        float nxt[PT];
+#pragma unroll
+        for (int j = 0; j < PT; j++) nxt[j] = n > 0 ? plane[(size_t)j * stride] : 0.0f;
         for (int i = 0; i < n; i++) {
-            const float* rowp = plane + (size_t)i * PT * stride;
+            float cur[PT];
+#pragma unroll
+            for (int j = 0; j < PT; j++) cur[j] = nxt[j];
+            if (i + 1 < n) {
+                const float* rowp = plane + (size_t)(i + 1) * PT * stride;
+#pragma unroll
+                for (int j = 0; j < PT; j++) nxt[j] = rowp[(size_t)j * stride];
+            }
             double xr[PT];
             xr[0] = 1.0;
 #pragma unroll
-            for (int j = 1; j < PT; j++) xr[j] = (double)rowp[(size_t)(j - 1) * stride];
-            const double yi = (double)rowp[(size_t)(PT - 1) * stride];
+            for (int j = 1; j < PT; j++) xr[j] = (double)cur[j - 1];
+            const double yi = (double)cur[PT - 1];
             double eta = 0.0;
 #pragma unroll
             for (int j = 0; j < PT; j++) eta = fma(xr[j], beta[j], eta);

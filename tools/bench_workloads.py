@@ -23,11 +23,11 @@ def workloads():
     return [
         ("c1_ols_interaction_n100", c1, [100], 1600, 1600),
         ("headline_ols_n500_p9", S.headline_spec(), [500], 1 << 21, 20000),
-        ("c2_sweep_p11_grid50_bonferroni", sweep, grid50, 1 << 18, 2000),
-        ("c2_sweep_p11_grid50_bh", bh, grid50, 1 << 18, 2000),
-        ("c3_doomer_alpha5e-7_grid50", doomer, grid50, 1 << 17, 1000),
-        ("c4_logit_n50_2000", S.logit_spec(), [50, 100, 200, 500, 1000, 2000], 1 << 16, 1000),
-        ("c5_lmm_30clusters_grid", S.lmm_spec(30, 0.2), [60, 120, 300, 600, 900], 1 << 18, 2000),
+        ("c2_sweep_p11_grid50_bonferroni", sweep, grid50, 1 << 19, 2000),
+        ("c2_sweep_p11_grid50_bh", bh, grid50, 1 << 19, 2000),
+        ("c3_doomer_alpha5e-7_grid50", doomer, grid50, 1 << 19, 1000),
+        ("c4_logit_n50_2000", S.logit_spec(), [50, 100, 200, 500, 1000, 2000], 1 << 19, 1000),
+        ("c5_lmm_30clusters_grid", S.lmm_spec(30, 0.2), [60, 120, 300, 600, 900], 1 << 20, 2000),
     ]
 
 
