@@ -280,24 +280,22 @@ __device__ __forceinline__ double ln_floor(double u) {
     return own_log(u < FL ? FL : u);
 }
 
-// data_gen.rs:1106-1182 (synthetic variants)
+// data_gen.rs:1106-1182 (synthetic variants).  Every non-Normal marginal starts from Φ(±z): the lanes of a warp hold
+// different studies, which under scenario swaps carry DIFFERENT marginals for the same column, so the expensive common
+// part (Φ, then −ln for the two skewed kinds) is evaluated once for all lanes and only the cheap tails branch.  The
+// arithmetic per kind is unchanged (bit-identical to the per-kind formulas of the oracle).
 static __device__ __noinline__ double apply_marginal(double z, int dist, double param, const double* __restrict__ t3) {
-    switch (dist) {
-        case 1: return phi(z) < 1.0 - param ? 0.0 : 1.0;
-        case 2: {
-            double e = -ln_floor(phi(-z));
-            if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;
-            return (e - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD;
-        }
-        case 3: {
-            double e = -ln_floor(phi(z));
-            if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;
-            return (MCP_EXP_CENSORED_MEAN - e) / MCP_EXP_CENSORED_STD;
-        }
-        case 4: return t3_lookup(t3, phi(z));
-        case 5: return -MCP_SQRT3 + (MCP_SQRT3 - (-MCP_SQRT3)) * phi(z);
-        default: return z;
+    if (dist == 0) return z;
+    const double u = phi(dist == 2 ? -z : z);
+    if (dist == 2 || dist == 3) {
+        double e = -ln_floor(u);
+        if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;
+        return dist == 2 ? (e - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD : (MCP_EXP_CENSORED_MEAN - e) / MCP_EXP_CENSORED_STD;
     }
+    if (dist == 1) return u < 1.0 - param ? 0.0 : 1.0;
+    if (dist == 4) return t3_lookup(t3, u);
+    if (dist == 5) return -MCP_SQRT3 + (MCP_SQRT3 - (-MCP_SQRT3)) * u;
+    return z;
 }
 
 // rng.rs:399-419

@@ -13,6 +13,7 @@
 #endif
 #include "launch.h"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #ifndef MCP_TU_ID
@@ -37,7 +38,12 @@ static size_t power_smem(const DevicePlan& pl, int P) {
 #define MCP_TU_KIND KIND_LMM
 #else
 #define MCP_TU_KIND KIND_OLS
+#define MCP_TU_IS_OLS 1
 #endif
+// NOTE: KIND_* are enum constants, invisible to the preprocessor — the former `#if MCP_TU_KIND != KIND_OLS` was always false, so the
+// GLM / LMM translation units also instantiated the dump / fit kernels.  The duplicate (weak) host stubs were merged by
+// the linker and registered by several modules: a launch could run another module's copy of the kernel, reading THAT
+// module's __constant__ plan (stale).  Guard with a real macro.
 
 template <int PT>
 static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) {
@@ -105,7 +111,7 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
 
 template <int PT>
 static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy) {
-#if MCP_TU_KIND != KIND_OLS
+#ifndef MCP_TU_IS_OLS
     return cudaErrorInvalidValue;
 #else
     cudaError_t e = cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan));
@@ -118,7 +124,7 @@ static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed,
 
 template <int PT>
 static cudaError_t fit_one(const double* dx, const double* dy, int n, double* dout) {
-#if MCP_TU_KIND != KIND_OLS
+#ifndef MCP_TU_IS_OLS
     return cudaErrorInvalidValue;
 #else
     fit_data_kernel<PT><<<1, 32>>>(dx, dy, n, dout);
@@ -161,7 +167,7 @@ bool MCP_TU_FN(launch_power)(int P, int kind, bool scen, const DevicePlan& plan,
 
 bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy,
                      cudaError_t* err) {
-#if MCP_TU_KIND != KIND_OLS
+#ifndef MCP_TU_IS_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
@@ -175,7 +181,7 @@ bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_see
 }
 
 bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, double* dout, cudaError_t* err) {
-#if MCP_TU_KIND != KIND_OLS
+#ifndef MCP_TU_IS_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
