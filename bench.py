@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -58,9 +58,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")) -> dict:
+        """Summarise the samples taken inside [t_begin, t_end] (the timed region); the sampler itself is started before
+        the warm-up because nvidia-smi needs a few hundred ms to produce its first line."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -69,7 +71,11 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (ts, r) in self.rows if t_begin <= ts <= t_end + 0.15]
+        window = "timed region"
+        if not inside:  # timed region shorter than the sampling period: use the samples under load (warm-up + timed)
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region"
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -79,7 +85,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference(spec, n_rows, seed, target_seconds, orc):
@@ -173,12 +179,13 @@ def main():
         begin = (i * world + rank) * per
         return M.run_batch(spec, [N_ROWS], per, seed, mode=mode, device=local_rank, sim_begin=begin)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     # ---- timed region 1: device time (value)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t_begin = time.time()
     t0 = time.perf_counter()
     dev_ms, total_counters = 0.0, None
     for i in range(args.steps):
@@ -188,7 +195,6 @@ def main():
         total_counters = r.counters.copy() if total_counters is None else total_counters + r.counters
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     # ---- timed region 2: end-to-end through the public API (host buffers in, host counters out)
     barrier()
     t1 = time.perf_counter()
@@ -196,6 +202,7 @@ def main():
         r = step(args.warmup + args.steps + i)
     barrier()
     e2e_wall = time.perf_counter() - t1
+    clocks = sampler.stop(t_begin, time.time())  # both timed regions (device-timed steps, then the e2e steps)
 
     t = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
     cnt = torch.from_numpy(total_counters.astype(np.int64)).cuda()
