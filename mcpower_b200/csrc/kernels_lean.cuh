@@ -342,8 +342,11 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
 // One OLS fit per thread from the statistics ols_lean_kernel left in HBM: Cholesky, β, σ², t², decisions,
 // corrections, overall F, counters / byte tensors (ols_fit_and_emit — the same code the thread-per-study kernel runs).
 // grid = (⌈n_sims / MCP_BLOCK⌉, n_ss); Σy is X'y[0] (x_0 ≡ 1).
+#ifndef MCP_SOLVE_MIN_BLOCKS
+#define MCP_SOLVE_MIN_BLOCKS 2
+#endif
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) ols_solve_kernel(uint32_t n_sims, const double* __restrict__ stats) {
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_SOLVE_MIN_BLOCKS) ols_solve_kernel(uint32_t n_sims, const double* __restrict__ stats) {
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int E = LeanGeom<PT>::E;
     const DevicePlan& pl = c_plan;

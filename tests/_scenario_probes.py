@@ -18,6 +18,13 @@ def spec_of(case: dict) -> dict:
     s = S.base_spec(k)
     s["effect_sizes"] = [0.0] + [float(e) for e in case["effects"]]
     s["target_indices"] = list(range(1, k + 1))
+    if case.get("family") == "probit":
+        from statistics import NormalDist
+        s["effect_sizes"][0] = NormalDist().inv_cdf(case["baseline_probability"])
+        s["outcome_kind"], s["link"], s["estimator"] = "binary", "probit", "glm"
+    elif case.get("family") == "poisson":
+        s["effect_sizes"][0] = math.log(case["baseline_rate"])
+        s["outcome_kind"], s["estimator"] = "count", "glm"
     if "factor" in case:
         s = S.add_factor(s, case["factor"]["proportions"], case["factor"]["effects"])
     if "corr" in case:
@@ -91,6 +98,12 @@ def statistics(name: str, draw) -> dict:
         for g in range(len(props)):
             out[f"sampled: Var(count) level {g + 1} = n·p(1−p)"] = float(((c_smp[:, g] - n * props[g]) ** 2).mean())
         return out
+    if name in ("scen_he_probit", "scen_he_poisson"):  # run_he_glm: mean fitted slope (oracle IRLS from the truth start)
+        from oracle import orc
+        fam = case["family"]
+        b_true = np.array(spec_of(case)["effect_sizes"])
+        B = np.array([orc.fit_glm(X, y, fam, beta_start=b_true)["betas"] for X, y in draws])
+        return {"β̂[x1] = per-study pseudo-true (h=0.4)": B[:, 1].mean(), "β̂[x2] = per-study pseudo-true (h=0.4)": B[:, 2].mean()}
     if name == "scen_he":  # run_he: slope of squared true-beta residuals on the squared predictors
         sl = []
         for X, y in draws:

@@ -25,6 +25,12 @@ CASES = {  # validation/formulas.R:708-806
                         "n": 4000, "K": 200, "seed": 39000},
     # g = (factor, 0.5, 0.3, 0.2); fixed walk under the optimistic scenario (20 draws, seed + k), sampled levels under
     # sampled_factor_proportions (K draws, seed + 500 + k): run_fa, validation_scenarios.rmd:262-283
+    # GLM families under heterogeneity: mean fitted slope over K studies (run_he_glm, validation_scenarios.rmd:64-85; the
+    # fit there is R glm — the tests use the oracle's IRLS from the truth start, see TOL_GLM in test_scenario_goldens.py)
+    "scen_he_probit": {"effects": [0.5, 0.3], "family": "probit", "baseline_probability": 0.4, "knobs": {"heterogeneity": 0.4},
+                       "n": 2000, "K": 300, "seed": 60000},
+    "scen_he_poisson": {"effects": [0.5, 0.3], "family": "poisson", "baseline_rate": 2.0, "knobs": {"heterogeneity": 0.4},
+                        "n": 2000, "K": 300, "seed": 61000},
     "scen_fa_ols": {"effects": [0.25], "factor": {"proportions": [0.5, 0.3, 0.2], "effects": [0.50, 0.80]},
                     "knobs": {"sampled_factor_proportions": True}, "n": 1000, "K": 400, "seed": 40000},
 }

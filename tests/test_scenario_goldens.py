@@ -9,6 +9,10 @@ import pytest
 import _scenario_probes as SP
 
 TOL = 1e-9  # SCENARIO_TOL$golden_abs
+# The two GLM cases freeze the mean of R `glm` slopes; the tests refit with the oracle's IRLS (R's stopping rule, truth
+# start), so the comparison carries R's own convergence tolerance (|ddev|/(|dev|+0.1) < 1e-8 ⇒ ~1e-7 on a probit slope).
+# Measured: Poisson 5e-11, probit 1.4e-7.
+TOL_GLM = {"scen_he_probit": 1e-6, "scen_he_poisson": 1e-8}
 
 
 def _with_sampling(spec, sampled):
@@ -20,7 +24,7 @@ def _with_sampling(spec, sampled):
 def _check(name, draw):
     got = SP.statistics(name, draw)
     for key, want in SP.GOLDEN[name]["golden"].items():
-        assert abs(got[key] - want) <= TOL, (name, key, got[key], want)
+        assert abs(got[key] - want) <= TOL_GLM.get(name, TOL), (name, key, got[key], want)
 
 
 @pytest.mark.parametrize("name", sorted(SP.GOLDEN))
