@@ -120,6 +120,43 @@ __device__ __forceinline__ void ni_central_pair(float v0, float v1, float& z0, f
 }
 #undef MCP_H2
 
+// ---- packed f32x2 helpers.  fma.rn.f32x2 with addend -0.0 is a correctly rounded product (ptxas emits FMUL2);
+// with multiplier 1.0 it is a correctly rounded sum (FFMA2 with a scalar 1.0 and an immediate addend).  Neither can
+// be contracted with its neighbour, unlike mul.rn.f32x2 + add.rn.f32x2 (see device_math.cuh).
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long bcast2(float c) { return pack2(c, c); }
+__device__ __forceinline__ unsigned long long mul2x(unsigned long long a, unsigned long long b) { return fma2(a, b, bcast2(-0.0f)); }
+__device__ __forceinline__ unsigned long long add2c(unsigned long long a, float c) { return fma2(a, bcast2(1.0f), bcast2(c)); }
+
+// Two words → two v = u − ½ (word_to_v) → central polynomial, packed.  Returns z (central value) and v.
+__device__ __forceinline__ void ni_central_pair_packed(uint32_t w0, uint32_t w1, float& z0, float& z1, float& v0, float& v1) {
+    const unsigned long long f = pack2(__uint_as_float(0x3f800000u | (w0 >> 9)), __uint_as_float(0x3f800000u | (w1 >> 9)));
+    const unsigned long long vv = add2c(add2c(f, -1.5f), 5.9604644775390625e-08f);
+    const unsigned long long r = mul2x(vv, vv);
+    unsigned long long a = mul2x(bcast2(2.401336800e+08f), r);
+    a = add2c(a, -2.359132160e+08f);
+#define MCP_HS(c)     \
+    a = mul2x(a, r);  \
+    a = add2c(a, c);
+    MCP_HS(9.886485600e+07f)
+    MCP_HS(-2.294391600e+07f)
+    MCP_HS(3.215264750e+06f)
+    MCP_HS(-2.779154375e+05f)
+    MCP_HS(1.463396387e+04f)
+    MCP_HS(-4.216123047e+02f)
+    MCP_HS(1.238584900e+01f)
+    MCP_HS(2.586458445e+00f)
+    MCP_HS(2.506664753e+00f)
+#undef MCP_HS
+    a = mul2x(vv, a);
+    unpack2(a, z0, z1);
+    unpack2(vv, v0, v1);
+}
+
 // tail branch (|v| > BP): copysign(Pt(sqrt(-2 ln_f32(max(0.5-|v|, 2^-25)))), v)
 __device__ __forceinline__ float ni_tail_inl(float v);
 static __device__ __noinline__ float ni_tail(float v) { return ni_tail_inl(v); }

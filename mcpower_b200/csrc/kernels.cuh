@@ -620,10 +620,10 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
         const bool is_x = t < k;
         const U4 w = philox4x32_10((uint32_t)b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, k0, k1);
         const int c = is_x ? t : PT - 1;
-        const float v0 = word_to_v(w.x), v1 = word_to_v(w.y), v2 = word_to_v(w.z), v3 = word_to_v(w.w);
         float4 z;
-        ni_central_pair(v0, v1, z.x, z.y);
-        ni_central_pair(v2, v3, z.z, z.w);
+        float v0, v1, v2, v3;  // packed f32x2 polynomial: FMUL2 + FFMA2(acc, 1, c), bit-identical to mul + add (device_math.cuh)
+        ni_central_pair_packed(w.x, w.y, z.x, z.y, v0, v1);
+        ni_central_pair_packed(w.z, w.w, z.z, z.w, v2, v3);
         if (t < 15 || !is_x) {
             unsigned tb = 0u;
             if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
