@@ -105,6 +105,25 @@ int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_s
                          const McpOptions* options, McpProgressFn progress, void* user, char** json_out);
 void mcp_free_string(char* s);
 
+/* ---- Contract entry points -------------------------------------------------------------
+ * The hosts' own payload: the `Vec<SimulationContract>` blob engine-py / engine-r forward verbatim
+ * (engine-py/src/orchestrator_bridge.rs:23-30 — msgpack, `rmp_serde::to_vec_named`; format 0) or the same tree as serde
+ * JSON (format 1).  Each contract is validated (engine-contract/src/validate.rs:22-50) and lowered like
+ * `contract_to_simulation_spec` (engine-core/src/contract_adapter.rs:74-230) + `lower_contracts`
+ * (engine-orchestrator/src/find_power.rs:251-288: factor_min_level_count forced to the configured 5, every scenario run
+ * with the call seed splitmix64(user_seed), results labelled with the design_test term positions).
+ * mcp_lower_contracts: *json_out = [{"label", "spec" (SimulationSpec JSON, ready for mcp_run_batch),
+ * "report_target_indices", "report_contrast_pairs"}, ...].  The two runners return ScenarioResult<T>
+ * (result.rs:581-584): {"scenarios": [[label, PowerResult | SampleSizeResult], ...]}.  Errors: MCP_INVALID_SPEC with
+ * "invalid scenarios input: contract <i> (<label>): ..." (OrchestratorError::InvalidScenarios). */
+int mcp_lower_contracts(const uint8_t* contracts, size_t len, int32_t format, char** json_out);
+int mcp_find_power_contracts(const uint8_t* contracts, size_t len, int32_t format, uint64_t sample_size, uint32_t n_sims,
+                             uint64_t user_seed, const McpOptions* options, McpProgressFn progress, void* user, char** json_out);
+int mcp_find_sample_size_contracts(const uint8_t* contracts, size_t len, int32_t format, uint64_t from_size, uint64_t to_size,
+                                   uint64_t by, int32_t by_auto, int32_t log_grid, double target_power, uint32_t n_sims,
+                                   uint64_t user_seed, const McpOptions* options, McpProgressFn progress, void* user,
+                                   char** json_out);
+
 /* CrossingFit (result.rs:416-450); status: 0 fitted, 1 at_or_below_min, 2 not_reached, 3 non_monotone. */
 typedef struct McpCrossingFit {
     int32_t status;

@@ -7,5 +7,6 @@ libmcpower_b200.so (include/mcpower_b200.h).  There is no CPU fallback.
 from . import spec  # noqa: F401
 from .engine import (MODE_BYTES, MODE_CAPTURE, MODE_COUNTS, BatchResult, Cancelled, CorrelationNotPSD,  # noqa: F401
                      CudaError, EngineError, InvalidSpec, RankDeficient, Unsupported, counters_from_bytes, crit_table,
-                     build_grid, device_count, find_power, find_sample_size, fit_crossing, fit_data, generate_sim,
+                     build_grid, device_count, find_power, find_power_contracts, find_sample_size,
+                     find_sample_size_contracts, fit_crossing, fit_data, generate_sim, lower_contracts,
                      pipe_bench, run_batch, splitmix64, wilson_ci)

@@ -20,7 +20,7 @@ CSRC = HERE / "csrc"
 OBJ = Path(os.environ.get("MCPOWER_B200_OBJ_DIR", "/tmp/mcpower_b200_build"))  # objects stay out of the repo snapshot
 SO = HERE / "libmcpower_b200.so"
 DEPS = ["api.cu", "kernel_tu.cu", "kernels.cuh", "kernels_q4.cuh", "kernels_lean.cuh", "kernels_glm.cuh", "kernels_lmm.cuh", "device_math.cuh", "pipe_bench.cuh", "launch.h",
-        "plan.h", "spec.hpp", "critvals.hpp", "json.hpp", "../../include/mcpower_b200.h"]
+        "plan.h", "spec.hpp", "contract.hpp", "orchestrator.hpp", "critvals.hpp", "json.hpp", "../../include/mcpower_b200.h"]
 # (tu id, P_lo, P_hi, glm) — must match MCP_TU_LIST in csrc/launch.h
 TUS = [(0, 1, 6, False), (1, 7, 9, False), (2, 10, 11, False), (3, 12, 13, False), (4, 14, 15, False), (5, 16, 16, False),
        (6, 1, 8, "GLM"), (7, 9, 12, "GLM"), (8, 13, 16, "GLM"), (9, 1, 9, "LMM"), (10, 10, 16, "LMM")]

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/mcpower_b200.h"
+#include "contract.hpp"
 #include "critvals.hpp"
 #include "device_math.cuh"
 #include "launch.h"
@@ -323,15 +324,12 @@ static void check_supported(const Spec& s, bool generation_only = false) {
         if (s.outcome == O_CONTINUOUS) invalid("estimator Glm requires a binary or count outcome");
     }
     if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
-    if (s.has_upload) unsupported("uploaded-data marginals / bootstrap");
     if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
     if (s.has_between) unsupported("between_var_indices");
     if (s.has_lme) unsupported("lme scenario knobs (random-effect distribution / ICC jitter)");
     if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
     for (int v : s.new_dists)
-        if (v >= 100) unsupported("uploaded_* distributions in the scenario menu");
-    for (int v : s.var_types)
-        if (v >= 100) unsupported("uploaded_* variable types");
+        if (v >= D_UPLOADED_FACTOR) unsupported("uploaded_* distributions in the scenario menu");
     if (s.k > MCP_MAX_K) unsupported("n_non_factor > " + std::to_string(MCP_MAX_K));
     if (s.P() > MCP_MAX_TEMPLATE_P) unsupported("n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
     if (s.T() > MCP_MAX_T) unsupported("targets > " + std::to_string(MCP_MAX_T));
@@ -400,6 +398,16 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         off += s.factor_n_levels[f];
         col += s.factor_n_levels[f] - 1;
     }
+    // uploaded-data arms: NORTA table / strict-bootstrap frame + column map
+    pl.bootstrap = s.frame_map.empty() ? 0 : 1;
+    pl.seq_per_row = pl.n_sampled_factors + pl.bootstrap;
+    pl.un_rows = s.un_rows; pl.un_cols = s.un_cols; pl.ud_rows = s.ud_rows; pl.ud_cols = s.ud_cols;
+    for (int c = 0; c < MCP_MAX_K + MCP_MAX_FACTORS; c++) pl.frame_map[c] = -1;
+    for (int c = 0; c < (int)s.frame_map.size(); c++) pl.frame_map[c < s.k ? c : MCP_MAX_K + (c - s.k)] = s.frame_map[c];
+    for (int j = 0; j < s.k; j++) pl.var_param_bs[j] = j < (int)s.var_params.size() ? s.var_params[j] : 0.0;
+    pl.upload_normal = s.upload_normal.empty() ? nullptr : lw.bufs.upload(s.upload_normal);
+    pl.upload_data = s.upload_data.empty() || !pl.bootstrap ? nullptr : lw.bufs.upload(s.upload_data);
+    if (pl.bootstrap) pl.exact_walk = 0;  // copied factor levels differ per study: per-study level counts, every exclusion mask
     int q = 0;
     for (size_t j = 0; j < s.interactions.size(); j++) {
         pl.inter_ptr[j] = q;
@@ -751,7 +759,7 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
         //   4 general quad kernel — opt-in;  1 thread-per-study kernel — everything else.
         // MCPOWER_B200_OLS_VARIANT=1|4|5 forces one where eligible (read per call).
         const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
-                             (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster;
+                             (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster && !pl.bootstrap;
         int ols_variant = lean_ok ? 5 : 1;
         if (const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT")) {
             if (e[0] == '1') ols_variant = 1;
@@ -909,29 +917,100 @@ static char* dup_json(const std::string& s) {
     return p;
 }
 
-// find_power for one scenario (find_power.rs:337 + aggregate_batch): JSON array of PowerResult, one per sample size.
+// find_power for one lowered scenario: run_batch + aggregate_batch → JSON array of PowerResult, one per sample size.
+// `report` carries the target / contrast indices the results are labelled with (the design_test term space when the
+// scenario came from a contract, find_power.rs:353-358; the spec's own indices otherwise).
+static std::string find_power_json(const Spec& s, const Spec& report, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
+                                   uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user,
+                                   const std::vector<std::string>& warnings = {}) {
+    McpBatchResult* r = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user);
+    struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
+    std::vector<orch::PowerResult> per_n = power_results_from(report, r, sample_sizes);
+    std::string o = "[";
+    for (size_t i = 0; i < per_n.size(); i++) {
+        if (i) o += ',';
+        per_n[i].grid_warnings.insert(per_n[i].grid_warnings.end(), warnings.begin(), warnings.end());
+        orch::power_result_json(o, per_n[i]);
+    }
+    o += ']';
+    return o;
+}
+
 int mcp_find_power(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
                    uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user, char** json_out) {
     return guarded([&] {
         if (!json_out) invalid("json_out pointer is NULL");
         *json_out = nullptr;
         Spec s = parse_spec(spec_json, spec_len);
-        McpBatchResult* r = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user);
-        struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
-        const std::vector<orch::PowerResult> per_n = power_results_from(s, r, sample_sizes);
-        std::string o = "[";
-        for (size_t i = 0; i < per_n.size(); i++) {
-            if (i) o += ',';
-            orch::power_result_json(o, per_n[i]);
-        }
-        o += ']';
-        *json_out = dup_json(o);
+        *json_out = dup_json(find_power_json(s, s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user));
     });
 }
 
-// find_sample_size for one scenario (find_sample_size.rs:83-257): cluster-aware grid, one run_batch over the whole
+// resolve_cluster_grid_params (find_sample_size.rs:24-79); limits from configs/config.json:27-28
+static void cluster_grid_params(const Spec& s, uint64_t& atom, uint64_t& hard_min, std::vector<std::string>& warnings) {
+    const uint64_t min_rows = 2, min_clusters = 5;
+    atom = 1;
+    hard_min = 1;
+    if (!s.has_cluster) return;
+    const uint64_t v = (uint64_t)std::max(s.sizing_value, 1);
+    atom = v;
+    if (!s.sizing_fixed_size) {
+        if (v < min_clusters) warnings.push_back("only " + std::to_string(v) + " clusters (< " + std::to_string(min_clusters) + "); τ² estimates may be unstable");
+        hard_min = v * min_rows;
+    } else {
+        if (v < min_rows) invalid("cluster_size " + std::to_string(v) + " is below the minimum rows per cluster " + std::to_string(min_rows));
+        hard_min = min_clusters * v;
+    }
+}
+
+// find_sample_size for one lowered scenario (find_sample_size.rs:83-257): cluster-aware grid, one run_batch over the whole
 // grid (nested row prefixes of the same studies), per-N PowerResult fold, grid-empirical first-N and model-based
 // crossing fits per target / per joint count / for the overall test.  JSON object = SampleSizeResult.
+static std::string find_sample_size_json(const Spec& s, const Spec& report, uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto,
+                                         int32_t log_grid, double target_power, uint32_t n_sims, uint64_t base_seed,
+                                         const McpOptions* options, McpProgressFn progress, void* user) {
+    uint64_t atom = 1, hard_min = 1;
+    std::vector<std::string> warnings;
+    cluster_grid_params(s, atom, hard_min, warnings);
+    std::vector<uint64_t> grid;
+    const orch::GridError ge = orch::build_grid(from_size, to_size, by, by_auto != 0, log_grid != 0, atom, hard_min, grid, warnings);
+    if (ge == orch::GRID_INVALID_BOUNDS) invalid("sample-size bounds: need 1 <= from <= to");
+    if (ge == orch::GRID_EMPTY) invalid("no multiple of the cluster atom lies inside the sample-size bounds");
+    if (ge == orch::GRID_SINGLE_POINT) invalid("the sample-size bounds leave a single grid point after cluster snapping");
+    if (ge != orch::GRID_OK) invalid("cluster atom must be positive");
+    std::vector<uint32_t> ss(grid.begin(), grid.end());
+    McpBatchResult* r = run_batch_core(s, ss.data(), (uint32_t)ss.size(), n_sims, base_seed, options, progress, user);
+    struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
+    const std::vector<orch::PowerResult> per_n = power_results_from(report, r, ss.data());
+    const orch::SampleSizeDerivations d = orch::derive_sample_size_outputs(per_n, grid, target_power, atom);
+    std::string o = "{\"grid_or_trace\":[";
+    for (size_t i = 0; i < per_n.size(); i++) {
+        if (i) o += ',';
+        orch::power_result_json(o, per_n[i]);
+    }
+    o += "],\"first_achieved\":";
+    orch::jarr(o, d.first_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
+    o += ",\"first_joint_achieved\":";
+    orch::jarr(o, d.first_joint_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
+    o += ",\"fitted\":";
+    orch::jarr(o, d.fitted, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
+    o += ",\"fitted_joint\":";
+    orch::jarr(o, d.fitted_joint, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
+    o += ",\"first_overall_achieved\":";
+    orch::jopt(o, d.has_overall ? d.first_overall_achieved : -1);
+    o += ",\"fitted_overall\":";
+    if (d.has_overall) orch::crossing_fit_json(o, d.fitted_overall);
+    else o += "null";
+    o += ",\"cluster_atom\":" + std::to_string(atom) + ",\"target_power\":";
+    orch::jnum(o, target_power);
+    o += ",\"grid_warnings\":";
+    orch::jarr(o, warnings, [](std::string& t, const std::string& w) { orch::jstr(t, w); });
+    o += ",\"kernel_ms\":";
+    orch::jnum(o, r->kernel_ms);
+    o += '}';
+    return o;
+}
+
 int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto,
                          int32_t log_grid, double target_power, uint32_t n_sims, uint64_t base_seed, const McpOptions* options,
                          McpProgressFn progress, void* user, char** json_out) {
@@ -939,57 +1018,133 @@ int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_s
         if (!json_out) invalid("json_out pointer is NULL");
         *json_out = nullptr;
         Spec s = parse_spec(spec_json, spec_len);
-        // resolve_cluster_grid_params (find_sample_size.rs:24-79); limits from configs/config.json:27-28
-        const uint64_t min_rows = 2, min_clusters = 5;
-        uint64_t atom = 1, hard_min = 1;
-        std::vector<std::string> warnings;
-        if (s.has_cluster) {
-            const uint64_t v = (uint64_t)std::max(s.sizing_value, 1);
-            atom = v;
-            if (!s.sizing_fixed_size) {
-                if (v < min_clusters) warnings.push_back("only " + std::to_string(v) + " clusters (< " + std::to_string(min_clusters) + "); τ² estimates may be unstable");
-                hard_min = v * min_rows;
-            } else {
-                if (v < min_rows) invalid("cluster_size " + std::to_string(v) + " is below the minimum rows per cluster " + std::to_string(min_rows));
-                hard_min = min_clusters * v;
-            }
+        *json_out = dup_json(find_sample_size_json(s, s, from_size, to_size, by, by_auto, log_grid, target_power, n_sims, base_seed, options,
+                                                   progress, user));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Contract entry points: the hosts' own payload — the `Vec<SimulationContract>` blob
+// engine-py / engine-r forward verbatim — lowered by contract.hpp and run through the same paths as above.
+
+struct LoweredScenario {
+    std::string label;
+    std::string spec_json;
+    Spec spec, report;  // report = spec with the host-report (design_test term) target / contrast indices
+    contract::Lowering low;
+};
+
+// lower_contracts (find_power.rs:251-288): validate + lower every contract, force factor_min_level_count to the
+// configured limit (configs/config.json:31), keep the report-space twins of the target indices.
+static std::vector<LoweredScenario> lower_contracts(const uint8_t* bytes, size_t len, int32_t format) {
+    if (!bytes) invalid("contracts pointer is NULL");
+    const std::vector<JsonValue> raw = contract::decode_contracts(bytes, len, format);
+    std::vector<LoweredScenario> out;
+    for (size_t idx = 0; idx < raw.size(); idx++) {
+        LoweredScenario sc;
+        try {
+            const contract::Contract c = contract::parse_contract(raw[idx]);
+            if (const JsonValue* nm = c.scenario.get("name")) sc.label = nm->str;
+            sc.low = contract::lower_contract(c);
+        } catch (const EngineError& e) {
+            throw EngineError(e.code, "invalid scenarios input: contract " + std::to_string(idx) + " (\"" + sc.label + "\"): " + e.what());
         }
-        std::vector<uint64_t> grid;
-        const orch::GridError ge = orch::build_grid(from_size, to_size, by, by_auto != 0, log_grid != 0, atom, hard_min, grid, warnings);
-        if (ge == orch::GRID_INVALID_BOUNDS) invalid("sample-size bounds: need 1 <= from <= to");
-        if (ge == orch::GRID_EMPTY) invalid("no multiple of the cluster atom lies inside the sample-size bounds");
-        if (ge == orch::GRID_SINGLE_POINT) invalid("the sample-size bounds leave a single grid point after cluster snapping");
-        if (ge != orch::GRID_OK) invalid("cluster atom must be positive");
-        std::vector<uint32_t> ss(grid.begin(), grid.end());
-        McpBatchResult* r = run_batch_core(s, ss.data(), (uint32_t)ss.size(), n_sims, base_seed, options, progress, user);
-        struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
-        const std::vector<orch::PowerResult> per_n = power_results_from(s, r, ss.data());
-        const orch::SampleSizeDerivations d = orch::derive_sample_size_outputs(per_n, grid, target_power, atom);
-        std::string o = "{\"grid_or_trace\":[";
-        for (size_t i = 0; i < per_n.size(); i++) {
+        // single source: limits.factor_min_level_count
+        const std::string key = "\"factor_min_level_count\":0}";
+        sc.spec_json = sc.low.spec_json.substr(0, sc.low.spec_json.size() - key.size()) + "\"factor_min_level_count\":5}";
+        sc.spec = parse_spec(sc.spec_json.c_str(), sc.spec_json.size());
+        sc.report = sc.spec;
+        sc.report.target_indices.assign(sc.low.report_targets.begin(), sc.low.report_targets.end());
+        sc.report.contrast_pairs.clear();
+        for (auto& p : sc.low.report_contrasts) sc.report.contrast_pairs.push_back({(int)p.first, (int)p.second});
+        out.push_back(std::move(sc));
+    }
+    return out;
+}
+
+int mcp_lower_contracts(const uint8_t* contracts, size_t len, int32_t format, char** json_out) {
+    return guarded([&] {
+        if (!json_out) invalid("json_out pointer is NULL");
+        *json_out = nullptr;
+        const std::vector<LoweredScenario> scs = lower_contracts(contracts, len, format);
+        std::string o = "[";
+        for (size_t i = 0; i < scs.size(); i++) {
             if (i) o += ',';
-            orch::power_result_json(o, per_n[i]);
+            o += "{\"label\":";
+            orch::jstr(o, scs[i].label);
+            o += ",\"spec\":" + scs[i].spec_json + ",\"report_target_indices\":";
+            orch::jarr(o, scs[i].low.report_targets, [](std::string& t, uint32_t v) { t += std::to_string(v); });
+            o += ",\"report_contrast_pairs\":";
+            orch::jarr(o, scs[i].low.report_contrasts,
+                       [](std::string& t, const std::pair<uint32_t, uint32_t>& p) { t += "[" + std::to_string(p.first) + "," + std::to_string(p.second) + "]"; });
+            o += '}';
         }
-        o += "],\"first_achieved\":";
-        orch::jarr(o, d.first_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
-        o += ",\"first_joint_achieved\":";
-        orch::jarr(o, d.first_joint_achieved, [](std::string& t, int64_t v) { orch::jopt(t, v); });
-        o += ",\"fitted\":";
-        orch::jarr(o, d.fitted, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
-        o += ",\"fitted_joint\":";
-        orch::jarr(o, d.fitted_joint, [](std::string& t, const orch::CrossingFit& f) { orch::crossing_fit_json(t, f); });
-        o += ",\"first_overall_achieved\":";
-        orch::jopt(o, d.has_overall ? d.first_overall_achieved : -1);
-        o += ",\"fitted_overall\":";
-        if (d.has_overall) orch::crossing_fit_json(o, d.fitted_overall);
-        else o += "null";
-        o += ",\"cluster_atom\":" + std::to_string(atom) + ",\"target_power\":";
-        orch::jnum(o, target_power);
-        o += ",\"grid_warnings\":";
-        orch::jarr(o, warnings, [](std::string& t, const std::string& w) { orch::jstr(t, w); });
-        o += ",\"kernel_ms\":";
-        orch::jnum(o, r->kernel_ms);
-        o += '}';
+        o += ']';
+        *json_out = dup_json(o);
+    });
+}
+
+// find_power over contracts (find_power.rs:301-392): N snapped to the cluster atom (snap_single_n, find_power.rs:25-58),
+// every scenario run with the same call seed splitmix64(user_seed) — scenarios of one call are paired runs — and the
+// results labelled in report space.  JSON = ScenarioResult<PowerResult>: {"scenarios": [[label, PowerResult], ...]}.
+int mcp_find_power_contracts(const uint8_t* contracts, size_t len, int32_t format, uint64_t sample_size, uint32_t n_sims, uint64_t user_seed,
+                             const McpOptions* options, McpProgressFn progress, void* user, char** json_out) {
+    return guarded([&] {
+        if (!json_out) invalid("json_out pointer is NULL");
+        *json_out = nullptr;
+        const std::vector<LoweredScenario> scs = lower_contracts(contracts, len, format);
+        uint64_t n = sample_size;
+        std::vector<std::string> warnings;
+        for (auto& sc : scs)
+            if (sc.spec.has_cluster) {
+                const uint64_t a = (uint64_t)std::max(sc.spec.sizing_value, 1);
+                if (a > 1) {
+                    uint64_t snapped = (n / a) * a;
+                    if (snapped == 0) snapped = a;
+                    if (sc.spec.sizing_fixed_size && snapped / a < 5)
+                        invalid("sample size " + std::to_string(snapped) + " gives " + std::to_string(snapped / a) + " clusters of size " + std::to_string(a) +
+                                " (minimum 5)");
+                    if (snapped != n)
+                        warnings.push_back("sample_size " + std::to_string(n) + " not a multiple of the cluster atom " + std::to_string(a) + "; using " +
+                                           std::to_string(snapped));
+                    n = snapped;
+                }
+                break;
+            }
+        if (n == 0 || n > 0xffffffffull) invalid("sample_size out of range");
+        const uint32_t n32 = (uint32_t)n;
+        const uint64_t call_seed = mcp_splitmix64(user_seed);
+        std::string o = "{\"scenarios\":[";
+        for (size_t i = 0; i < scs.size(); i++) {
+            if (i) o += ',';
+            o += '[';
+            orch::jstr(o, scs[i].label);
+            const std::string arr = find_power_json(scs[i].spec, scs[i].report, &n32, 1, n_sims, call_seed, options, progress, user, warnings);
+            o += ',' + arr.substr(1, arr.size() - 2) + ']';
+        }
+        o += "]}";
+        *json_out = dup_json(o);
+    });
+}
+
+// find_sample_size over contracts (find_sample_size.rs:83-257): {"scenarios": [[label, SampleSizeResult], ...]}.
+int mcp_find_sample_size_contracts(const uint8_t* contracts, size_t len, int32_t format, uint64_t from_size, uint64_t to_size, uint64_t by,
+                                   int32_t by_auto, int32_t log_grid, double target_power, uint32_t n_sims, uint64_t user_seed,
+                                   const McpOptions* options, McpProgressFn progress, void* user, char** json_out) {
+    return guarded([&] {
+        if (!json_out) invalid("json_out pointer is NULL");
+        *json_out = nullptr;
+        const std::vector<LoweredScenario> scs = lower_contracts(contracts, len, format);
+        const uint64_t call_seed = mcp_splitmix64(user_seed);
+        std::string o = "{\"scenarios\":[";
+        for (size_t i = 0; i < scs.size(); i++) {
+            if (i) o += ',';
+            o += '[';
+            orch::jstr(o, scs[i].label);
+            o += ',' + find_sample_size_json(scs[i].spec, scs[i].report, from_size, to_size, by, by_auto, log_grid, target_power, n_sims, call_seed,
+                                             options, progress, user) + ']';
+        }
+        o += "]}";
         *json_out = dup_json(o);
     });
 }

@@ -8,6 +8,14 @@
 #include <stdint.h>
 #include <math.h>
 
+#include "plan.h"
+
+namespace mcp {
+// The lowered study plan.  One copy per translation unit (the kernels are compiled in several TUs to build in parallel);
+// the launch wrappers in kernel_tu.cu upload the plan into their own copy before every launch.
+static __constant__ DevicePlan c_plan;
+}  // namespace mcp
+
 namespace mcp {
 
 // ---------------------------------------------------------------- seeds / Philox
@@ -321,9 +329,28 @@ __device__ __forceinline__ double ln_floor(double u) {
 // different studies, which under scenario swaps carry DIFFERENT marginals for the same column, so the expensive common
 // part (Φ, then −ln for the two skewed kinds) is evaluated once for all lanes and only the cheap tails branch.  The
 // arithmetic per kind is unchanged (bit-identical to the per-kind formulas of the oracle).
-static __device__ __noinline__ double apply_marginal(double z, int dist, double param, const double* __restrict__ t3) {
-    if (dist == 0) return z;
+//
+// `dist_col` = dist | column << 8.  Uploaded kinds (data_gen.rs:1156-1180): uploaded_binary thresholds like binary;
+// uploaded_data maps clamp(Φ(z), 0, 1) through the type-7 empirical quantile of column `col` of the sorted
+// (un_rows × un_cols) table in the plan (data_gen.rs:1262-1277); uploaded_factor is the identity.  The table is read
+// from c_plan rather than passed in, so the call site of the synthetic path is unchanged.
+static __device__ __noinline__ double apply_marginal(double z, int dist_col, double param, const double* __restrict__ t3) {
+    const int dist = dist_col & 0xff;
+    if (dist == 0 || dist == D_UPLOADED_FACTOR) return z;
     const double u = phi(dist == 2 ? -z : z);
+    if (dist >= D_UPLOADED_BINARY) {
+        if (dist == D_UPLOADED_BINARY) return u < 1.0 - param ? 0.0 : 1.0;
+        const int un_rows = c_plan.un_rows, un_cols = c_plan.un_cols, col = dist_col >> 8;
+        if (un_rows <= 0) return 0.0;
+        const double* __restrict__ un = c_plan.upload_normal;
+        const double uc = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        const double pos = uc * (double)(un_rows - 1);
+        const int lo = (int)floor(pos);
+        const int hi = lo + 1 < un_rows - 1 ? lo + 1 : un_rows - 1;
+        const double frac = pos - (double)lo;
+        const double val_lo = un[(size_t)lo * un_cols + col], val_hi = un[(size_t)hi * un_cols + col];
+        return val_lo + frac * (val_hi - val_lo);
+    }
     if (dist == 2 || dist == 3) {
         double e = -ln_floor(u);
         if (e > MCP_EXP_CAP) e = MCP_EXP_CAP;

@@ -25,9 +25,7 @@
 
 namespace mcp {
 
-// One copy per translation unit (the kernels are compiled in several TUs to build in parallel); the launch
-// wrappers in kernel_tu.cu upload the plan into their own copy before every launch.
-static __constant__ DevicePlan c_plan;
+// c_plan (the __constant__ DevicePlan, one copy per translation unit) is declared in device_math.cuh.
 
 #ifndef MCP_BLOCK
 #define MCP_BLOCK 128
@@ -598,6 +596,45 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
     }
 }
 
+// Strict bootstrap (data_gen.rs:553-604) for rows 4b..4b+3: ONE source row per design row — picked by the sequential-stream
+// word after the row's factor draws — is copied into every mapped column (the values generated before are discarded) and
+// the mapped factors are re-expanded to reference-coded dummies.  Out of line and self-contained (its own view of the
+// sequential stream), so that the synthetic path keeps its register footprint.
+template <typename SlabT>
+static __device__ __noinline__ void bootstrap_block(const SlabT slab, int b, uint32_t k0, uint32_t k1, uint32_t seq_row_base) {
+    const DevicePlan& pl = c_plan;
+    SeqRng seq;
+    seq.k0 = k0;
+    seq.k1 = k1;
+    seq.pos = 0;
+    seq.buf_block = 0xffffffffu;
+    for (int r = 0; r < 4; r++) {
+        const int row = 4 * b + r;
+        if (row >= pl.max_n) break;
+        const uint32_t word = seq.word_at(seq_row_base + (uint32_t)row * (uint32_t)pl.seq_per_row + (uint32_t)pl.n_sampled_factors);
+        const double pick = (double)word_to_unit(word) * (double)pl.ud_rows;
+        int src = (int)pick;  // pick ∈ [0, ud_rows): truncation = Rust's `as usize`
+        if (src > pl.ud_rows - 1) src = pl.ud_rows - 1;
+        const double* __restrict__ fr = pl.upload_data + (size_t)src * pl.ud_cols;
+        for (int j = 0; j < pl.k; j++) {
+            const int fc = pl.frame_map[j];
+            if (fc < 0) continue;
+            double v = fr[fc];
+            // the ORIGINAL contract type decides, not the scenario-perturbed one (data_gen.rs:570-573)
+            if (pl.var_type[j] == D_UPLOADED_BINARY) v = v + pl.var_param_bs[j] >= 0.5 ? 1.0 : 0.0;
+            slab[4 * j + r] = (float)v;
+        }
+        for (int f = 0; f < pl.n_factors; f++) {
+            const int fc = pl.frame_map[MCP_MAX_K + f];
+            if (fc < 0) continue;
+            const double lv = round(fr[fc]);
+            const int level = !(lv > 0.0) ? 0 : (lv > 1e9 ? 1000000000 : (int)lv);  // saturating `as usize`, NaN → 0
+            const int c0 = pl.f_col[f] - 1, nd = pl.f_levels[f] - 1;
+            for (int d = 0; d < nd; d++) slab[4 * (c0 + d) + r] = (level == d + 1) ? 1.0f : 0.0f;
+        }
+    }
+}
+
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
 template <int PT, bool SCEN, typename SlabT>
@@ -688,14 +725,14 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
                     for (int m = 0; m <= j; m++) a = a + (SCEN ? sd->L[j * KT + m] : pl.L[j * MCP_MAX_K + m]) * zr[m];
                     float xf = (float)a;
                     const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
-                    if (vt != D_NORMAL) xf = (float)apply_marginal((double)xf, vt, pl.var_param[j], pl.t3_table);
+                    if (vt != D_NORMAL) xf = (float)apply_marginal((double)xf, vt | (j << 8), pl.var_param[j], pl.t3_table);
                     slab[4 * j + r] = xf;
                 }
             }
         }
     }
     // ---- D. factor dummies (data_gen.rs:509-551) and interactions (643-649), in the f32 plane
-    if (pl.n_factors > 0 || pl.n_inter > 0) {
+    if (pl.n_factors > 0) {
         for (int r = 0; r < 4; r++) {
             const int row = 4 * b + r;
             if (row >= pl.max_n) break;
@@ -706,7 +743,7 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
                 if (!pl.f_sampled[f]) {
                     lvl = pl.levels[(size_t)f * pl.max_n + row];
                 } else {  // next_categorical on the sequential stream (rng.rs:112-127), counter-addressed
-                    const uint32_t widx = cx.seq_row_base + (uint32_t)row * (uint32_t)pl.n_sampled_factors + (uint32_t)sidx;
+                    const uint32_t widx = cx.seq_row_base + (uint32_t)row * (uint32_t)pl.seq_per_row + (uint32_t)sidx;
                     const double u = (double)word_to_unit(cx.seq.word_at(widx));
                     const double* pr = pl.f_props + pl.f_off[f];
                     double ca = 0.0;
@@ -720,6 +757,13 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
                 const int c0 = pl.f_col[f] - 1;
                 for (int d = 0; d < nl - 1; d++) slab[4 * (c0 + d) + r] = (lvl == d + 1) ? 1.0f : 0.0f;
             }
+        }
+    }
+    // strict bootstrap: after the factor block, before the interactions (data_gen.rs:553-604)
+    if (pl.bootstrap) bootstrap_block(slab, b, cx.seq.k0, cx.seq.k1, cx.seq_row_base);
+    if (pl.n_inter > 0) {
+        for (int r = 0; r < 4; r++) {
+            if (4 * b + r >= pl.max_n) break;
             const int ib = k + pl.n_fd;
             for (int j = 0; j < pl.n_inter; j++) {
                 double prod = 1.0;

@@ -19,7 +19,8 @@
 #define MCP_MAX_MENU 8
 #define MCP_MAX_TEMPLATE_P 16 // kernels with register-resident X'X exist for P <= this
 
-enum McpDist { D_NORMAL = 0, D_BINARY = 1, D_RIGHT_SKEWED = 2, D_LEFT_SKEWED = 3, D_HIGH_KURTOSIS = 4, D_UNIFORM = 5 };
+enum McpDist { D_NORMAL = 0, D_BINARY = 1, D_RIGHT_SKEWED = 2, D_LEFT_SKEWED = 3, D_HIGH_KURTOSIS = 4, D_UNIFORM = 5,
+               D_UPLOADED_FACTOR = 6, D_UPLOADED_BINARY = 7, D_UPLOADED_DATA = 8 };  // engine-contract/src/distribution.rs:23-25
 enum McpRes { R_NORMAL = 0, R_RIGHT_SKEWED = 1, R_LEFT_SKEWED = 2, R_HIGH_KURTOSIS = 3, R_UNIFORM = 4 };
 enum McpOutcome { O_CONTINUOUS = 0, O_BINARY = 1, O_COUNT = 2 };
 enum McpEstimator { E_OLS = 0, E_GLM = 1, E_MLE = 2 };
@@ -53,7 +54,16 @@ struct DevicePlan {
     int32_t f_col[MCP_MAX_FACTORS];    // first dummy column
     int32_t f_sampled[MCP_MAX_FACTORS];
     double f_props[MCP_MAX_LEVELS];
-    int32_t n_sampled_factors;         // uniforms consumed per row on the sequential stream
+    int32_t n_sampled_factors;         // sampled-factor uniforms consumed per row on the sequential stream
+    int32_t seq_per_row;               // all per-row words of the sequential stream: n_sampled_factors + bootstrap
+    // ---- uploaded-data arms (data_gen.rs:553-604 strict bootstrap, 1156-1175 / 1262-1277 NORTA)
+    int32_t bootstrap;                 // bootstrap_frame_map non-empty: one source-row pick per design row
+    int32_t un_rows, un_cols;          // upload_normal shape (sorted standardised values, column j = non-factor column j)
+    int32_t ud_rows, ud_cols;          // upload_data shape (the raw frame)
+    int32_t frame_map[MCP_MAX_K + MCP_MAX_FACTORS];  // frame column copied into non-factor column c / factor c − k, −1 = none
+    double var_param_bs[MCP_MAX_K];    // var_params with the bootstrap arm's unwrap_or(0.0) default (data_gen.rs:577)
+    const double* upload_normal;       // [un_rows][un_cols]
+    const double* upload_data;         // [ud_rows][ud_cols]
     int8_t col_factor[MCP_MAX_P];      // design column j is a dummy of factor col_factor[j] (−1: not a dummy) ...
     int8_t col_level[MCP_MAX_P];       // ... and indicates level col_level[j] (1..levels−1)
     int32_t inter_ptr[MCP_MAX_INTER + 1];

@@ -53,7 +53,10 @@ struct Spec {
     std::vector<std::vector<int>> posthoc_blocks;
     std::vector<std::pair<int, int>> posthoc_contrasts;
     std::vector<int> posthoc_block_levels, posthoc_block_ncontrasts;
-    bool has_upload = false;
+    // uploaded-data arms (spec.rs upload_* fields; contract_adapter.rs:359-455)
+    std::vector<double> upload_normal, upload_data;
+    int un_rows = 0, un_cols = 0, ud_rows = 0, ud_cols = 0;
+    std::vector<int> frame_map;  // bootstrap_frame_map, −1 = None; empty = not bootstrap
     bool has_slopes_or_groupings = false;
     bool has_between = false;
     // cluster
@@ -111,7 +114,8 @@ inline int dist_of(const JsonValue& v, const char* what) {
     // engine-contract/src/distribution.rs:15-26 (snake_case)
     const int d = enum_of(v, what, {{"normal", D_NORMAL}, {"binary", D_BINARY}, {"right_skewed", D_RIGHT_SKEWED},
                                     {"left_skewed", D_LEFT_SKEWED}, {"high_kurtosis", D_HIGH_KURTOSIS}, {"uniform", D_UNIFORM},
-                                    {"uploaded_factor", 100}, {"uploaded_binary", 101}, {"uploaded_data", 102}});
+                                    {"uploaded_factor", D_UPLOADED_FACTOR}, {"uploaded_binary", D_UPLOADED_BINARY},
+                                    {"uploaded_data", D_UPLOADED_DATA}});
     return d;
 }
 inline int resid_of(const JsonValue& v, const char* what) {
@@ -146,7 +150,24 @@ inline Spec parse_spec(const char* json, size_t len) {
         const JsonValue* p = root.get(key);
         return p && p->kind == JsonValue::Array && !p->arr.empty();
     };
-    s.has_upload = nonempty("upload_normal") || nonempty("upload_data") || nonempty("bootstrap_frame_map");
+    auto table = [&](const char* key, const char* shape_key, std::vector<double>& out, int& rows, int& cols) {
+        if (nonempty(key))
+            for (auto& v : arr(*root.get(key), key)) out.push_back(num(v, key));
+        if (const JsonValue* p = root.get(shape_key))
+            if (!p->is_null()) {
+                auto& sh = arr(*p, shape_key);
+                if (sh.size() != 2) invalid(std::string("`") + shape_key + "` must be a (rows, cols) pair");
+                rows = to_int(sh[0], shape_key);
+                cols = to_int(sh[1], shape_key);
+            }
+        if (rows < 0 || cols < 0 || (size_t)rows * (size_t)cols != out.size())
+            invalid(std::string("`") + key + "` length does not match `" + shape_key + "`");
+    };
+    table("upload_normal", "upload_normal_shape", s.upload_normal, s.un_rows, s.un_cols);
+    table("upload_data", "upload_data_shape", s.upload_data, s.ud_rows, s.ud_cols);
+    if (nonempty("bootstrap_frame_map"))
+        for (auto& v : arr(*root.get("bootstrap_frame_map"), "bootstrap_frame_map"))
+            s.frame_map.push_back(v.is_null() ? -1 : to_int(v, "bootstrap_frame_map"));
     s.has_between = nonempty("between_var_indices");
     for (auto& v : arr(req(root, "factor_n_levels"), "factor_n_levels")) s.factor_n_levels.push_back(to_int(v, "factor_n_levels"));
     for (auto& v : arr(req(root, "factor_proportions"), "factor_proportions")) s.factor_proportions.push_back(num(v, "factor_proportions"));
@@ -311,6 +332,17 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
     for (auto& dummies : s.posthoc_blocks)
         for (int ti : dummies)
             if (ti < 0 || ti >= P) invalid("posthoc target index " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
+    // uploaded-data tables: the reference indexes them unchecked (a malformed spec panics → RuntimeError); reject instead
+    if (!s.frame_map.empty()) {
+        if ((int)s.frame_map.size() != s.k + (int)s.factor_n_levels.size())
+            invalid("bootstrap_frame_map length must equal n_non_factor + n_factors");  // data_gen.rs:117-121
+        if (s.ud_rows <= 0 || s.ud_cols <= 0) invalid("bootstrap mode requires a non-empty frame");  // data_gen.rs:563
+        for (int fc : s.frame_map)
+            if (fc >= s.ud_cols) invalid("bootstrap_frame_map entry " + std::to_string(fc) + " out of range");
+    }
+    for (int j = 0; j < s.k; j++)
+        if (s.var_types[j] == D_UPLOADED_DATA && s.un_rows > 0 && j >= s.un_cols)
+            invalid("upload_normal has no column for uploaded_data variable " + std::to_string(j));
     if (s.k > 0) {
         std::vector<double> L;
         if (!correlation_llt(s.correlation, s.k, L)) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");

@@ -80,7 +80,8 @@ _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
 
 EXPORTS = ("mcp_run_batch", "mcp_free_result", "mcp_generate_sim", "mcp_fit_data", "mcp_crit_table", "mcp_splitmix64",
            "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version", "mcp_find_power", "mcp_find_sample_size",
-           "mcp_free_string", "mcp_fit_crossing", "mcp_build_grid", "mcp_wilson_ci")
+           "mcp_free_string", "mcp_fit_crossing", "mcp_build_grid", "mcp_wilson_ci", "mcp_lower_contracts",
+           "mcp_find_power_contracts", "mcp_find_sample_size_contracts")
 
 
 class _CrossingFit(C.Structure):
@@ -126,6 +127,15 @@ def lib():
     L.mcp_find_sample_size.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
                                        C.c_double, C.c_uint32, C.c_uint64, C.POINTER(_Options), _PROGRESS, C.c_void_p,
                                        C.POINTER(C.c_void_p)]
+    L.mcp_lower_contracts.restype = C.c_int
+    L.mcp_lower_contracts.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]
+    L.mcp_find_power_contracts.restype = C.c_int
+    L.mcp_find_power_contracts.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64,
+                                           C.POINTER(_Options), _PROGRESS, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mcp_find_sample_size_contracts.restype = C.c_int
+    L.mcp_find_sample_size_contracts.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32,
+                                                 C.c_int32, C.c_double, C.c_uint32, C.c_uint64, C.POINTER(_Options), _PROGRESS,
+                                                 C.c_void_p, C.POINTER(C.c_void_p)]
     L.mcp_free_string.restype = None
     L.mcp_free_string.argtypes = [C.c_void_p]
     L.mcp_fit_crossing.restype = C.c_int
@@ -433,6 +443,54 @@ def find_sample_size(spec: dict, from_size: int, to_size: int, n_sims: int, base
     rc = lib().mcp_find_sample_size(blob, len(blob), int(from_size), int(to_size), int(count if by is None else by),
                                     1 if by is None else 0, 1 if log_grid else 0, float(target_power), int(n_sims),
                                     base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    return _take_json(out)
+
+
+def _contract_payload(contracts) -> tuple:
+    """bytes → the msgpack `Vec<SimulationContract>` blob the reference hosts forward (format 0); a dict / list of dicts →
+    the same tree as serde JSON (format 1)."""
+    if isinstance(contracts, (bytes, bytearray, memoryview)):
+        return bytes(contracts), 0
+    return json.dumps(contracts if isinstance(contracts, list) else [contracts]).encode(), 1
+
+
+def lower_contracts(contracts) -> list:
+    """`lower_contracts` (find_power.rs:251-288) over `contract_to_simulation_spec` (contract_adapter.rs:74-230): one
+    {"label", "spec", "report_target_indices", "report_contrast_pairs"} dict per contract."""
+    blob, fmt = _contract_payload(contracts)
+    out = C.c_void_p()
+    rc = lib().mcp_lower_contracts(blob, len(blob), fmt, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    return _take_json(out)
+
+
+def find_power_contracts(contracts, sample_size: int, n_sims: int, user_seed: int = 2137, *, device: int = -1) -> dict:
+    """find_power (find_power.rs:301-392) on the hosts' contract payload → {"scenarios": [[label, PowerResult], ...]}."""
+    blob, fmt = _contract_payload(contracts)
+    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    out = C.c_void_p()
+    rc = lib().mcp_find_power_contracts(blob, len(blob), fmt, int(sample_size), int(n_sims), user_seed & 0xFFFFFFFFFFFFFFFF,
+                                        C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
+    if rc != 0:
+        _raise(rc)
+    return _take_json(out)
+
+
+def find_sample_size_contracts(contracts, from_size: int, to_size: int, n_sims: int, user_seed: int = 2137, *,
+                               by: Optional[int] = None, count: int = 12, log_grid: bool = False, target_power: float = 80.0,
+                               device: int = -1) -> dict:
+    """find_sample_size (find_sample_size.rs:83-257) on the hosts' contract payload →
+    {"scenarios": [[label, SampleSizeResult], ...]}."""
+    blob, fmt = _contract_payload(contracts)
+    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    out = C.c_void_p()
+    rc = lib().mcp_find_sample_size_contracts(blob, len(blob), fmt, int(from_size), int(to_size), int(count if by is None else by),
+                                              1 if by is None else 0, 1 if log_grid else 0, float(target_power), int(n_sims),
+                                              user_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), C.cast(None, _PROGRESS), None,
+                                              C.byref(out))
     if rc != 0:
         _raise(rc)
     return _take_json(out)

@@ -175,3 +175,43 @@ def lmm_spec(n_clusters: int = 30, icc: float = 0.2) -> dict:
                     "slopes": [], "extra_groupings": []}
     s["max_failed_fraction"] = 0.25
     return s
+
+
+def with_uploaded_frame(spec: dict, frame, columns: dict, factors: dict | None = None, bootstrap: bool = False) -> dict:
+    """Attach an uploaded frame the way `translate_uploaded_frame` lowers it (contract_adapter.rs:359-455).
+
+    `frame`: rows × frame-columns (standardised values; factor columns hold level codes).
+    `columns`: {non-factor index j: frame column}  → `uploaded_data`, or {j: (frame column, proportion)} →
+    `uploaded_binary`.  `factors`: {factor index f: frame column} (FactorFromFrame; strict mode copies the code).
+    NORTA (`bootstrap=False`): `upload_normal[r][j]` = r-th order statistic of the mapped frame column.
+    Strict (`bootstrap=True`): the raw frame + `bootstrap_frame_map` (non-factor columns first, then factors)."""
+    s = copy.deepcopy(spec)
+    rows = [[float(v) for v in row] for row in frame]
+    u, nc = len(rows), len(rows[0]) if rows else 0
+    k, nf = s["n_non_factor"], len(s["factor_n_levels"])
+    s["var_params"] = (list(s.get("var_params") or []) + [0.0] * k)[:k]
+    for j, m in columns.items():
+        if isinstance(m, tuple):
+            s["var_types"][j], s["var_params"][j] = "uploaded_binary", float(m[1])
+        else:
+            s["var_types"][j], s["var_params"][j] = "uploaded_data", 0.0
+    s["upload_data"] = [v for row in rows for v in row]
+    s["upload_data_shape"] = [u, nc]
+    if bootstrap:
+        fmap = [None] * (k + nf)
+        for j, m in columns.items():
+            fmap[j] = int(m[0] if isinstance(m, tuple) else m)
+        for f, fc in (factors or {}).items():
+            fmap[k + f] = int(fc)
+        s["bootstrap_frame_map"] = fmap
+        s["upload_normal"], s["upload_normal_shape"] = [], [0, 0]
+    else:
+        table = [[0.0] * k for _ in range(u)]
+        for j, m in columns.items():
+            fc = int(m[0] if isinstance(m, tuple) else m)
+            for r, v in enumerate(sorted(row[fc] for row in rows)):
+                table[r][j] = v
+        s["upload_normal"] = [v for row in table for v in row]
+        s["upload_normal_shape"] = [u, k]
+        s["bootstrap_frame_map"] = []
+    return s

@@ -677,8 +677,28 @@ double orc_apply_marginal(double z, int dist, double param) {
         }
         case ORC_DIST_HIGH_KURTOSIS: return orc_t3_lookup(orc_phi(z));
         case ORC_DIST_UNIFORM: return -SQRT3 + (SQRT3 - (-SQRT3)) * orc_phi(z);
+        case ORC_DIST_UPLOADED_BINARY: return orc_phi(z) < 1.0 - param ? 0.0 : 1.0; /* data_gen.rs:1162-1175 */
         default: return z;
     }
+}
+
+/* data_gen.rs:1262-1277 — type-7 linear-interpolation quantile of column `col` of the sorted (rows x cols) table */
+static double empirical_quantile(const double* table, int rows, int cols, int col, double u) {
+    if (rows <= 0) return 0.0;
+    const double pos = u * (double)(rows - 1);
+    const long lo = (long)floor(pos);
+    const long hi = lo + 1 < rows - 1 ? lo + 1 : rows - 1;
+    const double frac = pos - (double)lo;
+    const double val_lo = table[(size_t)lo * cols + col], val_hi = table[(size_t)hi * cols + col];
+    return val_lo + frac * (val_hi - val_lo);
+}
+double orc_apply_marginal_upload(double z, int dist, double param, const double* table, int rows, int cols, int col) {
+    if (dist == ORC_DIST_UPLOADED_DATA) { /* data_gen.rs:1156-1161: u = clamp(phi(z), 0, 1) */
+        double u = orc_phi(z);
+        u = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        return empirical_quantile(table, rows, cols, col, u);
+    }
+    return orc_apply_marginal(z, dist, param);
 }
 
 /* rng.rs:399-419 */
@@ -1280,7 +1300,8 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
             for (int i = 0; i < max_n; i++) xc[i] = (float)w->mix_acc[i];
         } else {
             double param = s->var_params[j];
-            for (int i = 0; i < max_n; i++) xc[i] = (float)orc_apply_marginal((double)(float)w->mix_acc[i], vt, param);
+            for (int i = 0; i < max_n; i++)
+                xc[i] = (float)orc_apply_marginal_upload((double)(float)w->mix_acc[i], vt, param, s->upload_normal, s->un_rows, s->un_cols, j);
         }
     }
 
@@ -1348,6 +1369,35 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
             if (lvl > 0 && lvl - 1 < nl - 1) w->x[(size_t)(col + lvl - 1) * max_n + i] = 1.0f;
             off += nl;
             col += nl - 1;
+        }
+        /* (b.4) strict bootstrap (data_gen.rs:553-604): ONE source row per design row, drawn after the factor draws */
+        if (s->n_frame_map > 0) {
+            const int u_rows = s->ud_rows, nc = s->ud_cols;
+            size_t r = (size_t)((double)seq_uniform(&rng) * (double)u_rows);
+            if (r > (size_t)(u_rows > 0 ? u_rows - 1 : 0)) r = (size_t)(u_rows > 0 ? u_rows - 1 : 0);
+            for (int j = 0; j < k; j++) {
+                const int fc = s->frame_map[j];
+                if (fc < 0) continue;
+                const double v = s->upload_data[r * (size_t)nc + fc];
+                double xv = v;
+                if (s->var_types[j] == ORC_DIST_UPLOADED_BINARY) { /* the ORIGINAL type, not the scenario-perturbed one */
+                    const double p = j < s->n_var_params ? s->var_params[j] : 0.0;
+                    xv = v + p >= 0.5 ? 1.0 : 0.0;
+                }
+                w->x[(size_t)(1 + j) * max_n + i] = (float)xv;
+            }
+            int start = 1 + k;
+            for (int f = 0; f < s->n_factors; f++) {
+                const int nd = s->factor_n_levels[f] > 1 ? s->factor_n_levels[f] - 1 : 0;
+                const int fc = s->frame_map[k + f];
+                if (fc >= 0) {
+                    const double lv = round(s->upload_data[r * (size_t)nc + fc]); /* f64::round, then a saturating `as usize` */
+                    const long level = lv != lv || lv <= 0.0 ? 0 : (lv > 1e9 ? 1000000000L : (long)lv);
+                    for (int d = 0; d < nd; d++) w->x[(size_t)(start + d) * max_n + i] = 0.0f;
+                    if (level > 0 && level - 1 < nd) w->x[(size_t)(start + level - 1) * max_n + i] = 1.0f;
+                }
+                start += nd;
+            }
         }
         for (int j = 0; j < s->n_interactions; j++) {
             double prod = 1.0;
@@ -1448,6 +1498,16 @@ static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* ba
     for (int c = 0; c < 2 * s->n_contrasts; c++)
         if (s->contrast_pairs[c] < 0 || s->contrast_pairs[c] >= P) return fail(ORC_ERR_INVALID_SPEC, "contrast_pairs entry out of range");
     int k = s->n_non_factor;
+    /* uploaded-data tables: the reference indexes them unchecked (a malformed spec panics); the backends reject it */
+    if (s->n_frame_map > 0) {
+        if (s->n_frame_map != k + s->n_factors) return fail(ORC_ERR_INVALID_SPEC, "bootstrap_frame_map length must equal n_non_factor + n_factors");
+        if (s->ud_rows <= 0 || s->ud_cols <= 0) return fail(ORC_ERR_INVALID_SPEC, "bootstrap mode requires a non-empty frame");
+        for (int c = 0; c < s->n_frame_map; c++)
+            if (s->frame_map[c] >= s->ud_cols) return fail(ORC_ERR_INVALID_SPEC, "bootstrap_frame_map entry out of range");
+    }
+    for (int j = 0; j < k; j++)
+        if (s->var_types[j] == ORC_DIST_UPLOADED_DATA && s->un_rows > 0 && j >= s->un_cols)
+            return fail(ORC_ERR_INVALID_SPEC, "upload_normal has no column for an uploaded_data variable");
     if (k > 0) {
         double* tmp = (double*)malloc(sizeof(double) * (size_t)k * k);
         memcpy(tmp, s->correlation, sizeof(double) * (size_t)k * k);

@@ -23,7 +23,9 @@ extern "C" {
 
 /* enum codes shared with the Python test harness (tests/orc.py) */
 enum { ORC_DIST_NORMAL = 0, ORC_DIST_BINARY = 1, ORC_DIST_RIGHT_SKEWED = 2, ORC_DIST_LEFT_SKEWED = 3,
-       ORC_DIST_HIGH_KURTOSIS = 4, ORC_DIST_UNIFORM = 5 };
+       ORC_DIST_HIGH_KURTOSIS = 4, ORC_DIST_UNIFORM = 5,
+       /* engine-contract/src/distribution.rs:23-25 */
+       ORC_DIST_UPLOADED_FACTOR = 6, ORC_DIST_UPLOADED_BINARY = 7, ORC_DIST_UPLOADED_DATA = 8 };
 enum { ORC_RES_NORMAL = 0, ORC_RES_RIGHT_SKEWED = 1, ORC_RES_LEFT_SKEWED = 2, ORC_RES_HIGH_KURTOSIS = 3,
        ORC_RES_UNIFORM = 4 };
 enum { ORC_OUT_CONTINUOUS = 0, ORC_OUT_BINARY = 1, ORC_OUT_COUNT = 2 };
@@ -75,6 +77,18 @@ typedef struct {
     int32_t n_posthoc_blocks;
     const int32_t* posthoc_block_levels;    /* n_posthoc_blocks */
     const int32_t* posthoc_block_ncontrasts;
+    /* uploaded-data arms (spec.rs upload_* fields; contract_adapter.rs:359-455).  NORTA: upload_normal is the
+     * row-major (un_rows, un_cols) table whose column j holds the sorted standardised values of non-factor
+     * column j.  Strict bootstrap: upload_data is the row-major (ud_rows, ud_cols) frame and frame_map[c]
+     * (c < k: non-factor column c; c >= k: factor c-k) the frame column copied into it, -1 = none;
+     * n_frame_map == 0 means "not bootstrap". */
+    const double* upload_normal;
+    int32_t un_rows, un_cols;
+    const double* upload_data;
+    int32_t ud_rows, ud_cols;
+    int32_t n_frame_map;
+    const int32_t* frame_map;
+    int32_t n_var_params;                   /* entries of var_params the spec really carried (bootstrap binary: unwrap_or(0.0)) */
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
@@ -95,6 +109,8 @@ double orc_exp(double x);
 double orc_log(double x);
 double orc_phi(double z);
 double orc_apply_marginal(double z, int dist, double param);
+/* the uploaded-data marginals as well (data_gen.rs:1156-1180): `table` = upload_normal (rows x cols, row-major), column `col` */
+double orc_apply_marginal_upload(double z, int dist, double param, const double* table, int rows, int cols, int col);
 double orc_t3_lookup(double percentile);
 double orc_poisson_quantile(double z, double lambda);
 

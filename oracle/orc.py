@@ -18,7 +18,8 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _SO = _HERE / "_ref" / "libmcp_oracle.so"
 
-DIST = {"normal": 0, "binary": 1, "right_skewed": 2, "left_skewed": 3, "high_kurtosis": 4, "uniform": 5}
+DIST = {"normal": 0, "binary": 1, "right_skewed": 2, "left_skewed": 3, "high_kurtosis": 4, "uniform": 5,
+        "uploaded_factor": 6, "uploaded_binary": 7, "uploaded_data": 8}
 RES = {"normal": 0, "right_skewed": 1, "left_skewed": 2, "high_kurtosis": 3, "uniform": 4}
 OUT = {"continuous": 0, "binary": 1, "count": 2}
 EST = {"ols": 0, "glm": 1, "mle": 2}
@@ -56,6 +57,10 @@ class OrcSpec(C.Structure):
         ("n_posthoc", C.c_int32), ("posthoc_pairs", C.POINTER(C.c_int32)),
         ("n_posthoc_blocks", C.c_int32), ("posthoc_block_levels", C.POINTER(C.c_int32)),
         ("posthoc_block_ncontrasts", C.POINTER(C.c_int32)),
+        ("upload_normal", C.POINTER(C.c_double)), ("un_rows", C.c_int32), ("un_cols", C.c_int32),
+        ("upload_data", C.POINTER(C.c_double)), ("ud_rows", C.c_int32), ("ud_cols", C.c_int32),
+        ("n_frame_map", C.c_int32), ("frame_map", C.POINTER(C.c_int32)),
+        ("n_var_params", C.c_int32),
     ]
 
 
@@ -101,6 +106,8 @@ def lib():
         f.argtypes = [dbl] * n
     L.orc_apply_marginal.restype = dbl
     L.orc_apply_marginal.argtypes = [dbl, C.c_int, dbl]
+    L.orc_apply_marginal_upload.restype = dbl
+    L.orc_apply_marginal_upload.argtypes = [dbl, C.c_int, dbl, P(dbl), C.c_int, C.c_int, C.c_int]
     L.orc_build_crit_table.argtypes = [P(OrcSpec), P(u32), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl)]
     L.orc_apply_correction.argtypes = [C.c_int, P(dbl), C.c_int, dbl, P(dbl), P(C.c_uint8)]
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
@@ -153,8 +160,23 @@ class PackedSpec:
         pinned = list(spec.get("var_pinned", []) or [])
         pinned = (pinned + [False] * k)[:k]
         s.var_pinned = _ptr(arr([1 if v else 0 for v in pinned], np.uint8), C.c_uint8)
-        vp = list(spec.get("var_params", []))
+        vp = list(spec.get("var_params", []) or [])
+        s.n_var_params = min(len(vp), k)
         vp = (vp + [0.5] * k)[:k]  # data_gen.rs:347 unwrap_or(0.5)
+        # uploaded-data arms (spec.rs upload_* fields): NORTA table, raw frame, strict-bootstrap column map
+        un = list(spec.get("upload_normal", []) or [])
+        uns = list(spec.get("upload_normal_shape", [0, 0]) or [0, 0])
+        ud = list(spec.get("upload_data", []) or [])
+        uds = list(spec.get("upload_data_shape", [0, 0]) or [0, 0])
+        fm = list(spec.get("bootstrap_frame_map", []) or [])
+        if len(un) != int(uns[0]) * int(uns[1]) or len(ud) != int(uds[0]) * int(uds[1]):
+            raise ValueError("invalid spec: upload table length does not match its shape")
+        s.upload_normal = _ptr(arr(un, np.float64), C.c_double)
+        s.un_rows, s.un_cols = int(uns[0]), int(uns[1])
+        s.upload_data = _ptr(arr(ud, np.float64), C.c_double)
+        s.ud_rows, s.ud_cols = int(uds[0]), int(uds[1])
+        s.n_frame_map = len(fm)
+        s.frame_map = _ptr(arr([-1 if v is None else int(v) for v in fm], np.int32), C.c_int32)
         s.var_params = _ptr(arr(vp, np.float64), C.c_double)
         s.factor_n_levels = _ptr(arr(levels, np.int32), C.c_int32)
         s.factor_proportions = _ptr(arr(spec.get("factor_proportions", []), np.float64), C.c_double)

@@ -23,7 +23,7 @@ SEED = 0x9E3779B97F4A7C15
 # on the same inputs: every run_batch test below runs once per forced kernel choice.  Tests that never reach the OLS power
 # kernel (generated-design dumps, supplied-bytes fits, GLM / LMM arms, host-side errors) run once.
 _NOT_OLS_POWER = ("cross_lme", "cross_glm", "generated_design", "marginal_transforms", "pinned_residual", "sampled_factors_and_cluster",
-                  "prefix_stability", "fit_on_reference", "design_draw", "logit", "probit", "glm", "lmm", "errors")
+                  "prefix_stability", "fit_on_reference", "design_draw", "logit", "probit", "glm", "lmm", "errors", "contract")  # substrings of test names
 
 
 @pytest.fixture(autouse=True, params=["thread", "quad", "lean"])
@@ -441,6 +441,141 @@ def test_errors_match_reference_classes():
         M.run_batch(glmm, [50], 10, SEED)
     r = M.run_batch(s, [50], 0, SEED, mode=ALL)  # n_sims == 0 → empty-shaped result (batch.rs:390-421)
     assert r.uncorrected.shape == (0, 1, 2) and r.counters.sum() == 0
+
+
+# ------------------------------------------------------------------ uploaded-data arms
+def _upload_frame(n=60):
+    rng = np.random.default_rng(17)
+    x = rng.exponential(size=n)
+    x = (x - x.mean()) / x.std()
+    return [[float(x[i]), float(x[i] ** 2 - 1.0), (1.0 if rng.random() < 0.35 else 0.0) - 0.35, float(rng.integers(0, 3))] for i in range(n)]
+
+
+def _upload_spec(kind: str) -> dict:
+    """NORTA (Gaussian-copula marginal through the sorted table) and strict bootstrap (whole-row copies) specs:
+    correlated block, uploaded continuous + binary columns, a frame factor next to a sampled synthetic factor
+    (so the bootstrap pick is the THIRD sequential-stream word of a row), an interaction on copied columns."""
+    s = S.base_spec(3)
+    s["correlation"] = [1, 0.4, 0.2, 0.4, 1, 0.3, 0.2, 0.3, 1]
+    s["effect_sizes"] = [0.1, 0.3, 0.25, 0.4]
+    s = S.add_factor(s, [0.5, 0.3, 0.2], [0.3, -0.4])
+    s = S.add_factor(s, [0.6, 0.4], [0.2])
+    s["factor_sampled"] = [None, True]
+    s = S.add_interaction(s, [1, 3], 0.2)
+    s["target_indices"] = [1, 2, 3, 4, 7]
+    s["correction_method"] = "holm"
+    s["report_overall"] = True
+    s["factor_min_level_count"] = 5
+    frame = _upload_frame()
+    if kind.startswith("norta"):
+        s = S.with_uploaded_frame(s, frame, {0: 0, 2: (2, 0.35)})
+    else:
+        s = S.with_uploaded_frame(s, frame, {0: 0, 1: 1, 2: (2, 0.35)}, factors={0: 3}, bootstrap=True)
+    if kind.endswith("doomer"):
+        s["scenario"] = S.scenario("doomer")
+    if kind.endswith("cluster"):
+        s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": 6}}, "tau_squared": 0.2, "slopes": [], "extra_groupings": []}
+    return s
+
+
+_UPLOAD_KINDS = ["norta", "norta_doomer", "strict", "strict_doomer", "strict_cluster"]
+
+
+@pytest.mark.parametrize("kind", _UPLOAD_KINDS)
+def test_uploaded_generated_design_bit_exact_vs_oracle(kind):
+    s = _upload_spec(kind)
+    for sim in (0, 3, 11):
+        x, y = M.generate_sim(s, SEED, sim, 203)
+        xo, yo, _ = orc.generate_sim(s, SEED, sim, 203)
+        assert np.array_equal(x.view(np.uint32), xo.view(np.uint32)), (kind, sim)
+        assert np.array_equal(y.view(np.uint32), yo.view(np.uint32)), (kind, sim)
+    if kind.startswith("strict"):  # every generated row is one whole frame row (test_upload_bootstrap.rs:104-131)
+        fr = np.asarray(_upload_frame())
+        src = {(np.float32(r[0]).item(), np.float32(r[1]).item(), 1.0 if r[2] + 0.35 >= 0.5 else 0.0, int(r[3])) for r in fr}
+        for i in range(203):
+            lvl = 1 if x[i, 4] == 1.0 else 2 if x[i, 5] == 1.0 else 0
+            assert (float(x[i, 1]), float(x[i, 2]), float(x[i, 3]), lvl) in src, i
+
+
+@pytest.mark.parametrize("kind", _UPLOAD_KINDS)
+def test_uploaded_run_batch_matches_oracle(kind):
+    s = _upload_spec(kind)
+    grid = [24, 48, 150]
+    got = M.run_batch(s, grid, 384, SEED, mode=ALL)
+    want = oracle_once(("upload", kind), lambda: orc.run_batch(s, grid, 384, SEED, n_threads=orc.host_threads(), capture=True))
+    assert_batch_equal(got, want)
+    if kind.startswith("strict"):  # the copied factor's level counts differ per study: both fits were exercised at n = 24
+        assert 0.0 < got.factor_excluded[:, 0, 0].mean() < 1.0
+
+
+def test_uploaded_logit_and_lmm_match_oracle():
+    g = S.logit_spec()
+    g = S.with_uploaded_frame(g, _upload_frame(), {1: 0, 0: (2, 0.35)}, bootstrap=True)
+    got = M.run_batch(g, [80, 200], 256, SEED, mode=ALL)
+    want = orc.run_batch(g, [80, 200], 256, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    m = S.with_uploaded_frame(S.lmm_spec(10, 0.2), _upload_frame(), {0: 0})
+    got = M.run_batch(m, [60, 120], 256, SEED, mode=ALL)
+    want = orc.run_batch(m, [60, 120], 256, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+
+
+def test_uploaded_errors():
+    s = _upload_spec("strict")
+    s["bootstrap_frame_map"][1] = 9
+    with pytest.raises(M.InvalidSpec):
+        M.run_batch(s, [50], 10, SEED)
+    s = _upload_spec("norta")
+    s["upload_normal"] = s["upload_normal"][:-1]
+    with pytest.raises(M.InvalidSpec):
+        M.run_batch(s, [50], 10, SEED)
+
+
+# ------------------------------------------------------------------ contract entry points (SURVEY §8f-3)
+def test_contract_entry_points_match_spec_entry_points():
+    """The hosts' payload (msgpack `Vec<SimulationContract>`) through mcp_find_power_contracts / mcp_find_sample_size_contracts
+    gives exactly what the lowered spec gives through the spec entry points with base_seed = splitmix64(user_seed)
+    (find_power.rs:251-288), labelled in report space; scenarios of one call are paired runs (same seed)."""
+    import msgpack
+    import test_contract_lowering as TC
+    terms = [TC.CONST, TC.direct(0), TC.direct(1), TC.dummy(2, 1), TC.dummy(2, 2)]
+    base = TC.contract([TC.normal(), TC.normal(), TC.factor(3, [0.5, 0.3, 0.2])], terms, [0.0, 0.4, 0.25, 0.3, 0.5],
+                       [TC.marginal(2), TC.marginal(3), TC.marginal(4), {"kind": "joint", "terms": [1, 2, 3]}],
+                       design_test=[TC.CONST, TC.direct(1), TC.dummy(2, 1), TC.dummy(2, 2)], correction="holm",
+                       correlations={"Matrix": {"continuous_columns": [0, 1], "values": [1.0, 0.3, 0.3, 1.0]}})
+    base["test"]["targets"][0] = TC.marginal(1)  # design_test term positions: 1 = x2, 2/3 = the dummies
+    base["test"]["targets"][1] = TC.marginal(2)
+    base["test"]["targets"][2] = TC.marginal(3)
+    base["scenario"]["name"] = "optimistic"
+    rough = __import__("copy").deepcopy(base)
+    rough["scenario"] = TC.scenario(name="realistic", heterogeneity=0.2, heteroskedasticity_ratio=2.0, correlation_noise_sd=0.15,
+                                    distribution_change_prob=0.5, new_distributions=["RightSkewed", "LeftSkewed", "Uniform"],
+                                    residual_change_prob=0.5, residual_dists=["high_kurtosis", "right_skewed"], residual_df=8.0,
+                                    sampled_factor_proportions=True)
+    blob = msgpack.packb([base, rough], use_bin_type=True)
+    lowered = M.lower_contracts(blob)
+    assert [sc["label"] for sc in lowered] == ["optimistic", "realistic"]
+    assert lowered[0]["spec"]["target_indices"] == [2, 3, 4] and lowered[0]["report_target_indices"] == [1, 2, 3]
+    assert lowered[0]["spec"]["fit_columns"] == [0, 2, 3, 4] and lowered[0]["spec"]["report_overall"] is True
+    got = M.find_power_contracts(blob, 60, 2048, 2137)
+    assert [label for label, _ in got["scenarios"]] == ["optimistic", "realistic"]
+    for (label, pr), sc in zip(got["scenarios"], lowered):
+        want = M.find_power(sc["spec"], [60], 2048, M.splitmix64(2137))[0]
+        assert pr["target_indices"] == sc["report_target_indices"]
+        for key in ("n", "n_sims", "success_counts_uncorrected", "success_counts_corrected", "convergence_count",
+                    "overall_significant_count", "success_count_histogram_uncorrected", "factor_exclusion_counts"):
+            assert pr[key] == want[key], (label, key)
+    assert got["scenarios"][0][1]["success_counts_uncorrected"] != got["scenarios"][1][1]["success_counts_uncorrected"]
+    ss = M.find_sample_size_contracts(blob, 20, 200, 1024, 2137, by=20)
+    for (label, res), sc in zip(ss["scenarios"], lowered):
+        want = M.find_sample_size(sc["spec"], 20, 200, 1024, M.splitmix64(2137), by=20)
+        assert res["first_achieved"] == want["first_achieved"] and res["fitted"] == want["fitted"], label
+        assert [p["success_counts_uncorrected"] for p in res["grid_or_trace"]] == [p["success_counts_uncorrected"] for p in want["grid_or_trace"]]
+        assert res["grid_or_trace"][0]["target_indices"] == sc["report_target_indices"]
+    with pytest.raises(M.InvalidSpec, match="contract 1"):
+        bad = __import__("copy").deepcopy(rough)
+        bad["test"]["alpha"] = 2.0
+        M.find_power_contracts(msgpack.packb([base, bad]), 60, 16)
 
 
 # ------------------------------------------------------------------ full-size properties (BASELINE.json sizes)

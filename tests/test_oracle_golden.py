@@ -8,6 +8,7 @@ validation/tolerances.R:24-28), R contrast t² (posthoc.rs:300-317), quantile go
 (critvals.rs:1807-1925), phi-composed transforms (≤2 ULP — the reference's exp kernel
 lives in the un-vendored glmm crate and is only specified to "≤1 ULP of libm").
 """
+import ctypes as C
 import json
 import math
 
@@ -100,22 +101,24 @@ def test_golden_marginal_uniform_within_2ulp():  # tests/golden_rng.rs:214-223
 
 def test_golden_apply_marginal():  # data_gen.rs:2282-2400
     names = {"Normal": "normal", "Binary": "binary", "RightSkewed": "right_skewed", "LeftSkewed": "left_skewed",
-             "HighKurtosis": "high_kurtosis", "Uniform": "uniform"}
+             "HighKurtosis": "high_kurtosis", "Uniform": "uniform", "UploadedData": "uploaded_data",
+             "UploadedBinary": "uploaded_binary", "UploadedFactor": "uploaded_factor"}
     zs = G["apply_marginal"]["z_grid"]
+    # the fabricated sorted upload table of the reference test, shape (5, 2); var_idx = 1 reads [-2, -1, 0, 1, 2]
+    table = np.array([-1.5, -2.0, -0.5, -1.0, 0.0, 0.0, 0.5, 1.0, 1.5, 2.0])
+    tp = table.ctypes.data_as(C.POINTER(C.c_double))
     seen = 0
     for row in G["apply_marginal"]["rows"]:
-        if row["dist"] not in names:
-            continue  # uploaded-data marginals: out of scope
         seen += 1
         for z, bits in zip(zs, row["bits"]):
-            got = orc.lib().orc_apply_marginal(z, orc.DIST[names[row["dist"]]], row["param"])
+            got = orc.lib().orc_apply_marginal_upload(z, orc.DIST[names[row["dist"]]], row["param"], tp, 5, 2, 1)
             want = float(np.uint64(bits).view(np.float64))
-            if row["dist"] in ("Normal", "Binary"):
+            if row["dist"] in ("Normal", "Binary", "UploadedBinary", "UploadedFactor"):
                 assert int(np.float64(got).view(np.uint64)) == bits or got == want
             else:
                 # phi/ln-composed: value-pinned; |z|=8 rows sit in phi's cancellation region
                 assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), (row["dist"], z, got, want)
-    assert seen == 6
+    assert seen == 9
 
 
 def test_own_exp_log_accuracy():
@@ -370,3 +373,89 @@ def test_oracle_reproduces_the_engines_frozen_required_n(name):
         assert fit["status"] == want["status"], (name, t, fit)
         if want["status"] == "fitted":
             assert fit["n_achievable"] == want["n_achievable"], (name, t, fit)
+
+
+# ---------------------------------------------------------------- uploaded-data arms
+def _nonlinear_frame():  # tests/test_upload_bootstrap.rs:88-96 — x2 = x1², impossible under a Gaussian copula
+    return [[-2.0 + 4.0 * i / 39.0, (-2.0 + 4.0 * i / 39.0) ** 2] for i in range(40)]
+
+
+def _strict_2cont_spec(frame):  # tests/test_upload_bootstrap.rs:29-83
+    from mcpower_b200 import spec as S
+    s = S.base_spec(2)
+    s["effect_sizes"] = [0.0, 0.5, 0.3]
+    return S.with_uploaded_frame(s, frame, {0: 0, 1: 1}, bootstrap=True)
+
+
+def test_strict_bootstrap_copies_whole_rows():  # tests/test_upload_bootstrap.rs:104-131
+    frame = _nonlinear_frame()
+    x, _, _ = orc.generate_sim(_strict_2cont_spec(frame), 2137, 0, 500)
+    f32 = np.asarray(frame, dtype=np.float64).astype(np.float32)
+    for i in range(500):
+        assert np.any((f32[:, 0] == x[i, 1]) & (f32[:, 1] == x[i, 2])), i
+    assert len({float(v) for v in x[:, 1]}) > 20  # rows are picked all over the frame, not one row repeated
+
+
+def test_strict_bootstrap_is_row_stable():  # tests/test_upload_bootstrap.rs:136-160
+    s = _strict_2cont_spec(_nonlinear_frame())
+    xs, ys, _ = orc.generate_sim(s, 2137, 5, 100)
+    xb, yb, _ = orc.generate_sim(s, 2137, 5, 1000)
+    assert np.array_equal(xs, xb[:100]) and np.array_equal(ys, yb[:100])
+
+
+def test_strict_bootstrap_factor_reexpands_level():  # tests/test_upload_bootstrap.rs:229-300
+    from mcpower_b200 import spec as S
+    frame = [[i * 0.1 - 1.5, float(i % 3)] for i in range(30)]
+    s = S.add_factor(S.base_spec(1), [0.5, 0.3, 0.2], [0.0, 0.0])
+    s["effect_sizes"][1], s["target_indices"] = 0.5, [1]
+    s = S.with_uploaded_frame(s, frame, {0: 0}, factors={0: 1}, bootstrap=True)
+    x, _, _ = orc.generate_sim(s, 2137, 0, 500)
+    src = {(np.float32(r[0]).item(), int(r[1])) for r in frame}
+    for i in range(500):
+        d0, d1 = float(x[i, 2]), float(x[i, 3])
+        assert (d0, d1) in ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0))
+        assert (float(x[i, 1]), 1 if d0 == 1.0 else 2 if d1 == 1.0 else 0) in src, i  # both from the SAME source row
+
+
+def test_strict_bootstrap_binary_copies_joint_with_continuous():  # tests/test_upload_bootstrap.rs:308-444
+    from mcpower_b200 import spec as S
+    p = 0.4
+    frame = [[-1.0 + 0.05 * i, (1.0 if i % 5 < 2 else 0.0) - p] for i in range(40)]  # binary stored centred: x − p
+    s = S.base_spec(2)
+    s["effect_sizes"] = [0.0, 0.4, 0.3]
+    s = S.with_uploaded_frame(s, frame, {0: 0, 1: (1, p)}, bootstrap=True)
+    x, _, _ = orc.generate_sim(s, 2137, 3, 400)
+    src = {(np.float32(r[0]).item(), 1.0 if r[1] + p >= 0.5 else 0.0) for r in frame}
+    assert set(np.unique(x[:, 2])) == {0.0, 1.0}
+    for i in range(400):
+        assert (float(x[i, 1]), float(x[i, 2])) in src, i
+
+
+def test_norta_uploaded_marginal_reproduces_the_empirical_distribution():  # data_gen.rs:1156-1175, 1262-1277
+    from mcpower_b200 import spec as S
+    rng = np.random.default_rng(5)
+    col = rng.exponential(size=200)
+    col = (col - col.mean()) / col.std()
+    frame = [[float(v), float(i % 2) - 0.5] for i, v in enumerate(col)]
+    s = S.base_spec(3)
+    s["correlation"] = [1, 0.5, 0, 0.5, 1, 0, 0, 0, 1]
+    s["effect_sizes"] = [0.0, 0.2, 0.2, 0.1]
+    s = S.with_uploaded_frame(s, frame, {1: 0, 2: (1, 0.5)})
+    x, _, _ = orc.generate_sim(s, 2137, 0, 20000)
+    z = x[:, 2].astype(np.float64)
+    assert col.min() - 1e-6 <= z.min() and z.max() <= col.max() + 1e-6
+    for q in (0.1, 0.5, 0.9):
+        assert abs(np.quantile(z, q) - np.quantile(col, q)) < 0.06
+    assert abs(np.corrcoef(x[:, 1], x[:, 2])[0, 1] - 0.5) < 0.06  # the Gaussian copula carries the correlation (attenuated)
+    assert set(np.unique(x[:, 3])) == {0.0, 1.0} and abs(x[:, 3].mean() - 0.5) < 0.02
+
+
+def test_uploaded_tables_are_validated():
+    from mcpower_b200 import spec as S
+    s = _strict_2cont_spec(_nonlinear_frame())
+    s["bootstrap_frame_map"] = [0, 5]
+    with pytest.raises(orc.OracleError):
+        orc.generate_sim(s, 1, 0, 10)
+    s["bootstrap_frame_map"] = [0]
+    with pytest.raises(orc.OracleError):
+        orc.generate_sim(s, 1, 0, 10)
