@@ -756,24 +756,29 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
         // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
         //   5 lean path — plain linear models (Normal marginals/residual, exact-walk factors, no cluster/scenario): lane-quad
         //     generate+accumulate kernel leaves X'X|X'y|y'y per fit in HBM, a thread-per-fit kernel solves;
-        //   4 general quad kernel — opt-in;  1 thread-per-study kernel — everything else.
-        // MCPOWER_B200_OLS_VARIANT=1|4|5 forces one where eligible (read per call).
+        //   6 split path — everything else on the OLS arm: the general lane-quad kernel in generate+accumulate form
+        //     (scenario designs from their own one-thread-per-study kernel), same statistics buffer, same solve kernel;
+        //   4 general quad kernel solving by call, 1 thread-per-study kernel — kept for cross-checks.
+        // MCPOWER_B200_OLS_VARIANT=1|4|5|6 forces one where eligible (read per call).
         const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
                              (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster && !pl.bootstrap;
-        int ols_variant = lean_ok ? 5 : 1;
+        int ols_variant = lean_ok ? 5 : 6;
         if (const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT")) {
             if (e[0] == '1') ols_variant = 1;
             else if (e[0] == '4') ols_variant = 4;
             else if (e[0] == '5') ols_variant = lean_ok ? 5 : 4;
+            else if (e[0] == '6') ols_variant = 6;
         }
-        if (kind == KIND_OLS && ols_variant == 5) {
+        if (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) {
             // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB
             const size_t E = (size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1;
             const size_t per_sim = (size_t)n_ss * E * sizeof(double);
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / per_sim, 128);
             wave = std::min(wave, cap);
             if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * n_ss * E * sizeof(double)));
+            // variant 6 on the scenario path keeps the per-study scenario designs behind the statistics (sized for the widest template)
+            const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>) : 0;
+            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * (n_ss * E * sizeof(double) + design_bytes)));
         }
         CUDA_CHECK(cudaEventRecord(e0, st));
         bool cancelled = false;
@@ -805,7 +810,7 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
                 dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }
-            r->gpu_launches += (kind == KIND_OLS && ols_variant == 5) ? 2 : 1;
+            r->gpu_launches += (kind == KIND_OLS && ols_variant == 6 && !pl.optimistic) ? 3 : (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) ? 2 : 1;
             done += cnt;
             if (progress) {
                 CUDA_CHECK(cudaStreamSynchronize(st));

@@ -87,6 +87,27 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
         const dim3 grid_s((a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK, (unsigned)pl.n_ss);
         ols_solve_kernel<PT><<<grid_s, MCP_BLOCK, smem_s, a.stream>>>(a.n_sims, a.scratch_d);
+    } else if (a.ols_variant == 6) {  // general quad generate + accumulate kernel, then one thread per fit (kernels_q4.cuh, SPLIT)
+        using G = Q4Geom<PT>;
+        const size_t smem6 = G::smem_bytes(0, 0, false);
+        const uint32_t blocks6 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
+        if (scen) {
+            // per-study scenario designs behind this wave's statistics (api.cu sizes the scratch for both)
+            ScenDesign<PT>* designs = reinterpret_cast<ScenDesign<PT>*>(a.scratch_d + (size_t)pl.n_ss * (PT * (PT + 1) / 2 + PT + 1) * a.n_sims);
+            scen_design_kernel<PT><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, true, true><<<blocks6, MCP_BLOCK, smem6, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d, designs);
+        } else {
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, false, true><<<blocks6, MCP_BLOCK, smem6, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
+        const dim3 grid_s((a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK, (unsigned)pl.n_ss);
+        ols_solve_kernel<PT><<<grid_s, MCP_BLOCK, smem_s, a.stream>>>(a.n_sims, a.scratch_d);
     } else if (a.ols_variant == 4) {  // one study per lane quad (kernels_q4.cuh)
         using G = Q4Geom<PT>;
         const size_t smem4 = G::smem_bytes(pl.n_ss, pl.counter_width, pl.smem_counters != 0);

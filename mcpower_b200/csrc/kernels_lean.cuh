@@ -330,10 +330,30 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_SOLVE_MIN_BLOCKS) ols_solve_ker
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
         SimOut so{cnt_s, (uint64_t)sim};
         // sparse-factor exclusion (batch.rs:2451-2562): with exact walks the per-level counts at a grid point are the
-        // same for every study, so the host tabulates them once
+        // same for every study, so the host tabulates them once; otherwise (sampled / bootstrapped factors) they are read
+        // off the statistics — a reference-coded dummy is exactly 0 / 1, so the count of level l >= 1 is the column sum
+        // X'X[dummy_l][0] (an exact integer in f64) and level 0 takes the remaining rows
         const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
-        ols_fit_and_emit<PT>(in, yty, sum_y, pl.ss[g], so, g, track_excl ? pl.exact_counts + (size_t)g * MCP_MAX_LEVELS : nullptr, excl,
-                             track_excl, (size_t)n_sims);
+        uint32_t lc[MCP_MAX_LEVELS];
+        const uint32_t* counts = nullptr;
+        if (track_excl) {
+            if (pl.exact_counts) {
+                counts = pl.exact_counts + (size_t)g * MCP_MAX_LEVELS;
+            } else {
+                for (int f = 0; f < pl.n_factors; f++) {
+                    uint32_t rest = pl.ss[g];
+                    for (int l = 1; l < pl.f_levels[f]; l++) {
+                        const int col = pl.f_col[f] + l - 1;
+                        const uint32_t c = (uint32_t)in[(size_t)tri(col, 0) * n_sims];
+                        lc[pl.f_off[f] + l] = c;
+                        rest -= c;
+                    }
+                    lc[pl.f_off[f]] = rest;
+                }
+                counts = lc;
+            }
+        }
+        ols_fit_and_emit<PT>(in, yty, sum_y, pl.ss[g], so, g, counts, excl, track_excl, (size_t)n_sims);
     }
     if (cnt_s) {
         __syncthreads();

@@ -116,8 +116,30 @@ static __device__ __noinline__ void q4_count_levels(const Slab<MCP_BLOCK> ps, in
     }
 }
 
-template <int PT, bool SCEN>
-__global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel_q4(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims) {
+// SPLIT = true: generate + accumulate only.  At a grid point every lane writes its quarter of Z'Z straight to the wave's
+// statistics buffer stats[(g·E + e)·n_sims + sim] (the lean path's layout, coalesced over the studies of a warp) and
+// ols_solve_kernel (kernels_lean.cuh) fits from there, one thread per fit.  No solver call in the streaming kernel, so
+// ptxas does not park the accumulators in local memory around it, and no per-level counting either: the dummies are exact
+// 0 / 1 (data_gen.rs:545-549), so the per-level counts of batch.rs:2451-2496 ARE the dummy column sums X'X[dummy][0]
+// (exact integers in f64), and the solve kernel reads them from the statistics.
+// The SPLIT scenario path also takes the per-study scenario design (perturbed correlation → PSD repair → Cholesky, marginal
+// and residual swaps, jittered effects) from scen_design_kernel below instead of deriving it in every lane of the quad: the
+// Jacobi repair runs once per study, in its own kernel, and the streaming kernel reads the factor through the caches.
+// One thread per study: the per-study scenario design of populate_design (data_gen.rs:990-1093) into HBM.
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) scen_design_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, ScenDesign<PT>* __restrict__ out) {
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    if (sim >= n_sims) return;
+    ScenDesign<PT> sd;
+    scen_populate<PT>(sd, base_seed, sim_begin + sim);
+    if (!sd.ok) atomicExch(c_plan.error_flag, 2);  // EngineError::CorrelationNotPSD (data_gen.rs:1049)
+    out[sim] = sd;
+}
+
+template <int PT, bool SCEN, bool SPLIT = false>
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel_q4(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
+                                                                                    double* __restrict__ stats = nullptr,
+                                                                                    const ScenDesign<PT>* __restrict__ designs = nullptr) {
     using G = Q4Geom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
@@ -128,7 +150,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
     double* const stage = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)(threadIdx.x >> 2) * G::STUDY;
     unsigned int* cnt_s = nullptr;
-    if (pl.smem_counters) {
+    if (!SPLIT && pl.smem_counters) {  // SPLIT emits nothing: the solve kernel owns the counters
         cnt_s = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY);
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
         __syncthreads();
@@ -147,18 +169,22 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
         ScenDesign<PT> sdv;
-        ScenDesign<PT>* sd = nullptr;
-        if (SCEN) {  // every lane of the quad derives the same per-study design (pure function of the sim id)
-            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
-            sd = &sdv;
-            if (!sdv.ok) atomicExch(pl.error_flag, 2);
+        const ScenDesign<PT>* sd = nullptr;
+        if (SCEN) {
+            if (SPLIT) {
+                sd = designs + sim;  // scen_design_kernel ran first
+            } else {  // every lane of the quad derives the same per-study design (pure function of the sim id)
+                scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+                sd = &sdv;
+                if (!sdv.ok) atomicExch(pl.error_flag, 2);
+            }
         }
         double acc[G::NACCQ];
 #pragma unroll
         for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
         uint32_t lvl_counts[MCP_MAX_LEVELS];  // this lane's share (rows with r == q); summed over the quad at a fit
         uint8_t excl[MCP_MAX_FACTORS];
-        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        const bool track_excl = !SPLIT && pl.n_factors > 0 && pl.min_level_count > 0;
         if (track_excl)
             for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
@@ -207,7 +233,23 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                     for (int r = 0; r < nr; r++) {
                         q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
                         if (track_excl && r == q) q4_count_levels(ps, r, lvl_counts);
-                        if ((uint32_t)(row0 + r + 1) == n_next) {
+                        if (SPLIT && (uint32_t)(row0 + r + 1) == n_next) {
+                            // ---- grid point g: this lane's quarter of Z'Z → the statistics buffer (entry e = X'X packed lower
+                            // | X'y | y'y, as LeanGeom<PT>::E)
+                            double* const out = stats + (size_t)g * (NACC + PT + 1) * n_sims + sim;
+#pragma unroll
+                            for (int a = 0; a < M; a++) {
+#pragma unroll
+                                for (int c = 0; c <= a; c++) {
+                                    const int i = q == 0 ? a : (q == 1 ? N - a : N - c);
+                                    const int j = q == 0 ? c : (q == 1 ? c : (q == 2 ? N - a : a));
+                                    const int e = i < N ? tri(i, j) : NACC + j;  // j == N: y'y
+                                    out[(size_t)e * n_sims] = acc[tri(a, c)];
+                                }
+                            }
+                            g++;
+                            n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+                        } else if ((uint32_t)(row0 + r + 1) == n_next) {
                             // ---- fit at grid point g: the quad hands its entries to lane 0, which solves through memory
                             double st[NACC + PT];
                             double yty = 0.0;

@@ -19,18 +19,19 @@ pytestmark = pytest.mark.gpu
 SEED = 0x9E3779B97F4A7C15
 
 # All OLS power kernels (one thread per study / one lane quad per study / the lean quad + solve pair for plain linear
-# models, which falls back to the general quad kernel where a spec is outside its family) must produce the same bits
+# models, which falls back to the general quad kernel where a spec is outside its family / the general quad
+# generate + accumulate kernel with the separate solve kernel) must produce the same bits
 # on the same inputs: every run_batch test below runs once per forced kernel choice.  Tests that never reach the OLS power
 # kernel (generated-design dumps, supplied-bytes fits, GLM / LMM arms, host-side errors) run once.
 _NOT_OLS_POWER = ("cross_lme", "cross_glm", "generated_design", "marginal_transforms", "pinned_residual", "sampled_factors_and_cluster",
                   "prefix_stability", "fit_on_reference", "design_draw", "logit", "probit", "glm", "lmm", "errors", "contract")  # substrings of test names
 
 
-@pytest.fixture(autouse=True, params=["thread", "quad", "lean"])
+@pytest.fixture(autouse=True, params=["thread", "quad", "lean", "split"])
 def ols_kernel_choice(request, monkeypatch):
     if request.param != "thread" and any(t in request.node.name for t in _NOT_OLS_POWER):
         pytest.skip("does not reach the OLS power kernel")
-    monkeypatch.setenv("MCPOWER_B200_OLS_VARIANT", {"thread": "1", "quad": "4", "lean": "5"}[request.param])
+    monkeypatch.setenv("MCPOWER_B200_OLS_VARIANT", {"thread": "1", "quad": "4", "lean": "5", "split": "6"}[request.param])
     return request.param
 
 
@@ -409,8 +410,8 @@ def test_results_independent_of_wave_size_and_shard_offset(ols_kernel_choice):
     a = M.run_batch(s, grid, 1000, SEED, mode=ALL)
     b = M.run_batch(s, grid, 1000, SEED, mode=ALL, wave_sims=137)
     assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
-    # the lean path rounds a wave down to whole 128-study groups and launches two kernels per wave (accumulate, solve)
-    assert b.gpu_launches == (2 * math.ceil(1000 / 128) if ols_kernel_choice == "lean" else math.ceil(1000 / 137))
+    # the lean and split paths round a wave down to whole 128-study groups and launch two kernels per wave (accumulate, solve)
+    assert b.gpu_launches == (2 * math.ceil(1000 / 128) if ols_kernel_choice in ("lean", "split") else math.ceil(1000 / 137))  # optimistic spec
     c1 = M.run_batch(s, grid, 600, SEED, mode=ALL, sim_begin=0)
     c2 = M.run_batch(s, grid, 400, SEED, mode=ALL, sim_begin=600)
     assert np.array_equal(np.concatenate([c1.uncorrected, c2.uncorrected]), a.uncorrected)
