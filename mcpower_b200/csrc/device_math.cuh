@@ -229,27 +229,44 @@ struct SeqRng {
 };
 
 // ---------------------------------------------------------------- owned exp / log (bit-identical twin of the oracle's)
+// The FP64 coefficients live in a __constant__ table: a literal becomes two UMOVs feeding a uniform-register operand
+// (a quarter of the instructions of the marginal transforms, profiles/r01k), a table entry is a constant-bank operand of
+// the DFMA / DMUL / DADD itself.  Same doubles as the literals they replace (compile-time IEEE folding).
+enum {
+    KM_LOG2E, KM_LN2_HI, KM_LN2_LO, KM_E13, KM_E12, KM_E11, KM_E10, KM_E9, KM_E8, KM_E7, KM_E6, KM_E5, KM_E4, KM_E3, KM_HALF, KM_ONE,
+    KM_EXP_HI, KM_EXP_LO, KM_TWO54, KM_TWO, KM_LG1, KM_LG2, KM_LG3, KM_LG4, KM_LG5, KM_LG6, KM_LG7,
+    KM_RSQRT2, KM_AS_P, KM_AS_A1, KM_AS_A2, KM_AS_A3, KM_AS_A4, KM_AS_A5, KM_COUNT
+};
+static __constant__ double c_km[KM_COUNT] = {
+    1.4426950408889634, 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,
+    709.782712893384, -745.1332191019412, 18014398509481984.0, 2.0,
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01, 1.818357216161805012e-01,
+    1.531383769920937332e-01, 1.479819860511658591e-01,
+    0.70710678118654752440, 0.3275911, 0.254829592, -0.284496736, 1.421413741, -1.453152027, 1.061405429};
+
 __device__ __forceinline__ double own_exp(double x) {
     if (x != x) return x;
-    if (x > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
-    if (x < -745.1332191019412) return 0.0;
-    const double kf = rint(x * 1.4426950408889634);
-    double r = fma(-kf, 6.93147180369123816490e-01, x);
-    r = fma(-kf, 1.90821492927058770002e-10, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    if (x > c_km[KM_EXP_HI]) return __longlong_as_double(0x7ff0000000000000LL);
+    if (x < c_km[KM_EXP_LO]) return 0.0;
+    const double kf = rint(x * c_km[KM_LOG2E]);
+    double r = fma(-kf, c_km[KM_LN2_HI], x);
+    r = fma(-kf, c_km[KM_LN2_LO], r);
+    double p = c_km[KM_E13];
+    p = fma(p, r, c_km[KM_E12]);
+    p = fma(p, r, c_km[KM_E11]);
+    p = fma(p, r, c_km[KM_E10]);
+    p = fma(p, r, c_km[KM_E9]);
+    p = fma(p, r, c_km[KM_E8]);
+    p = fma(p, r, c_km[KM_E7]);
+    p = fma(p, r, c_km[KM_E6]);
+    p = fma(p, r, c_km[KM_E5]);
+    p = fma(p, r, c_km[KM_E4]);
+    p = fma(p, r, c_km[KM_E3]);
+    p = fma(p, r, c_km[KM_HALF]);
+    p = fma(p, r, c_km[KM_ONE]);
+    p = fma(p, r, c_km[KM_ONE]);
     const int k = (int)kf;
     const int k1 = k / 2, k2 = k - k1;
     const double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
@@ -265,7 +282,7 @@ __device__ __forceinline__ double own_log(double x) {
     int k = 0;
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
     if ((b >> 52) == 0) {
-        x *= 18014398509481984.0;
+        x *= c_km[KM_TWO54];
         b = (unsigned long long)__double_as_longlong(x);
         k -= 54;
     }
@@ -277,28 +294,27 @@ __device__ __forceinline__ double own_log(double x) {
     } else {
         b = mant | 0x3ff0000000000000ULL;
     }
-    const double f = __longlong_as_double((long long)b) - 1.0;
-    const double s = f / (2.0 + f);
+    const double f = __longlong_as_double((long long)b) - c_km[KM_ONE];
+    const double s = f / (c_km[KM_TWO] + f);
     const double z = s * s;
     const double w = z * z;
-    const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
-    const double t2 = z * (6.666666666666735130e-01 +
-                           w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+    const double t1 = w * (c_km[KM_LG2] + w * (c_km[KM_LG4] + w * c_km[KM_LG6]));
+    const double t2 = z * (c_km[KM_LG1] + w * (c_km[KM_LG3] + w * (c_km[KM_LG5] + w * c_km[KM_LG7])));
     const double R = t2 + t1;
-    const double hfsq = 0.5 * f * f;
+    const double hfsq = c_km[KM_HALF] * f * f;
     const double dk = (double)k;
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+    return dk * c_km[KM_LN2_HI] - ((hfsq - (s * (hfsq + R) + dk * c_km[KM_LN2_LO])) - f);
 }
 
 // distributions.rs:32-56 — A&S 7.1.26
 __device__ __forceinline__ double phi(double z) {
-    const double x = -z * 0.70710678118654752440;
+    const double x = -z * c_km[KM_RSQRT2];
     const double sign = x < 0.0 ? -1.0 : 1.0;
     const double ax = fabs(x);
-    const double t = 1.0 / (1.0 + 0.3275911 * ax);
-    const double y =
-        1.0 - (((((1.061405429 * t + -1.453152027) * t) + 1.421413741) * t + -0.284496736) * t + 0.254829592) * t * own_exp(-ax * ax);
-    return 0.5 * (1.0 - sign * y);
+    const double t = c_km[KM_ONE] / (c_km[KM_ONE] + c_km[KM_AS_P] * ax);
+    const double y = c_km[KM_ONE] - (((((c_km[KM_AS_A5] * t + c_km[KM_AS_A4]) * t) + c_km[KM_AS_A3]) * t + c_km[KM_AS_A2]) * t + c_km[KM_AS_A1]) * t *
+                                        own_exp(-ax * ax);
+    return c_km[KM_HALF] * (c_km[KM_ONE] - sign * y);
 }
 
 #define MCP_EXP_CAP 6.95925599364711
