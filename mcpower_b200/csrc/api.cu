@@ -810,7 +810,8 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
                 dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }
-            r->gpu_launches += (kind == KIND_OLS && ols_variant == 6 && !pl.optimistic) ? 3 : (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) ? 2 : 1;
+            r->gpu_launches += (kind == KIND_OLS && ols_variant == 6 && !pl.optimistic) ? 3
+                               : ((kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) || kind == KIND_GLM) ? 2 : 1;
             done += cnt;
             if (progress) {
                 CUDA_CHECK(cudaStreamSynchronize(st));

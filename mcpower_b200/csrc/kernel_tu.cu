@@ -53,8 +53,19 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     const uint32_t blocks = (a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK;
     if (kind != MCP_TU_KIND) return cudaErrorInvalidValue;
 #if defined(MCP_TU_GLM)
-    cudaFuncSetAttribute(glm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    glm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+    {
+        const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
+        cudaFuncSetAttribute(glm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        glm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
+        const dim3 grid_fit(blocks, (unsigned)pl.n_ss);
+        // resident CTAs per SM the fit kernel is compiled for: the IRLS accumulators (P(P+1)/2 + P doubles) set the register
+        // floor; measured at P = 5 (config 4): 2 → 1.21e7, 4 → 1.71e7, 5 → 1.75e7, 6 → 1.57e7, 8 → 1.58e7 fits/s
+        constexpr int MINB = PT <= 5 ? 5 : (PT <= 6 ? 4 : (PT <= 8 ? 3 : 2));
+        glm_fit_kernel<PT, MINB><<<grid_fit, MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch);
+    }
 #elif defined(MCP_TU_LMM)
     cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);

@@ -1,7 +1,8 @@
 // kernels_glm.cuh — batched IRLS power kernel (logit / probit / Poisson), sm_100a.
 //
 // Replaces the unclustered GLM arm of run_one_sim (crates/engine-core/src/batch.rs:1562-2135) and
-// glmm::glm_irls_fit (call site batch.rs:1969-1981).  One simulated study per thread:
+// glmm::glm_irls_fit (call site batch.rs:1969-1981).  Two kernels per wave (glm_gen_kernel: one study per thread;
+// glm_fit_kernel: one (study, sample size) fit per thread):
 //   1. the study's max_n rows are generated once (same gen_block/row_xy as the OLS kernel, so the data
 //      plane is bit-identical to the reference fixtures) and parked in an HBM scratch plane laid out
 //      [row][column][sim-in-wave] — the 32 studies of a warp read consecutive floats, so every IRLS pass
@@ -236,133 +237,141 @@ static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int va
     emit_fit(so, g, variant, fo, pl.variants[variant].p_red, all_t, excl_flags, ov);
 }
 
+// Stage 1 — one study per thread: generate the max_n rows once (same gen_block / row_xy as the OLS kernels, so the data plane
+// is bit-identical to the reference fixtures) and park the f32 plane in HBM, [row][column][sim-in-wave].
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) glm_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, float* __restrict__ scratch) {
-    constexpr int SP = PT | 1;
+__global__ void __launch_bounds__(MCP_BLOCK) glm_gen_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, float* __restrict__ scratch) {
     const DevicePlan& pl = c_plan;
     extern __shared__ __align__(16) float smem[];
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;  // sims per wave, padded to whole blocks
+    if (sim >= n_sims) return;
+    const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+    SimCtx cx;
+    cx.k0 = (uint32_t)key;
+    cx.k1 = (uint32_t)(key >> 32);
+    cx.seq.init(key);
+    cx.tau = 0.0;
+    cx.seq_row_base = 0u;
+    const int max_n = pl.max_n;
+    float* plane = scratch + sim;
+    ScenDesign<PT> sdv;
+    const bool scen = !pl.optimistic;
+    if (scen) {
+        scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+        if (!sdv.ok) atomicExch(pl.error_flag, 2);
+    }
+    for (int b = 0; b < (max_n + 3) >> 2; b++) {
+        if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
+        else gen_block<PT, false>(b, slab, cx, nullptr);
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * b + r;
+            if (row >= max_n) break;
+            double xr[PT];
+            const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
+            float* rowp = plane + (size_t)row * PT * stride;
+#pragma unroll
+            for (int j = 1; j < PT; j++) rowp[(size_t)(j - 1) * stride] = slab[4 * (j - 1) + r];
+            rowp[(size_t)(PT - 1) * stride] = (float)yd;
+        }
+    }
+}
+
+// Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): the fits of one study at its different
+// sample sizes are independent (each restarts from the truth start on its own row prefix, batch.rs:1563-1577), so they run
+// concurrently, the threads of a warp all fit the same n (same row-loop trip count), and this kernel carries no generation
+// code.  blockIdx.y counts DOWN the grid so the longest fits are scheduled first.
+template <int PT, int MINB>
+__global__ void __launch_bounds__(MCP_BLOCK, MINB) glm_fit_kernel(uint32_t n_sims, const float* __restrict__ scratch) {
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {
-        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
+        cnt_s = reinterpret_cast<unsigned int*>(smem);
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
         __syncthreads();
     }
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;  // sims per wave, padded to whole blocks
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
+    const int g = pl.n_ss - 1 - (int)blockIdx.y;
     if (sim < n_sims) {
-        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        SimCtx cx;
-        cx.k0 = (uint32_t)key;
-        cx.k1 = (uint32_t)(key >> 32);
-        cx.seq.init(key);
-        cx.tau = 0.0;
-        cx.seq_row_base = 0u;
-        const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
-        float* plane = scratch + sim;
+        const float* plane = scratch + sim;
         const int family = pl.outcome == O_COUNT ? 2 : (pl.link_probit ? 1 : 0);
-        // ---- 1. generate the study once, park the f32 plane in HBM
-        {
-            ScenDesign<PT> sdv;
-            const bool scen = !pl.optimistic;
-            if (scen) {
-                scen_populate<PT>(sdv, base_seed, sim_begin + sim);
-                if (!sdv.ok) atomicExch(pl.error_flag, 2);
-            }
-            for (int b = 0; b < (max_n + 3) >> 2; b++) {
-                if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
-                else gen_block<PT, false>(b, slab, cx, nullptr);
-                for (int r = 0; r < 4; r++) {
-                    const int row = 4 * b + r;
-                    if (row >= max_n) break;
-                    double xr[PT];
-                    const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
-                    float* rowp = plane + (size_t)row * PT * stride;
-#pragma unroll
-                    for (int j = 1; j < PT; j++) rowp[(size_t)(j - 1) * stride] = slab[4 * (j - 1) + r];
-                    rowp[(size_t)(PT - 1) * stride] = (float)yd;
-                }
-            }
-        }
-        // ---- 2. one fit per sample size
         uint32_t lvl_counts[MCP_MAX_LEVELS];
         uint8_t excl[MCP_MAX_FACTORS];
         const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
         for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
-        int counted = 0;
-        for (int g = 0; g < pl.n_ss; g++) {
-            const int n = (int)pl.ss[g];
-            for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
-            if (track_excl) {  // counts over rows [0, n): cumulative, so only the new rows are scanned (batch.rs:2451-2496)
-                for (int i = counted; i < n; i++) {
-                    const float* rowp = plane + (size_t)i * PT * stride;
-                    for (int f = 0; f < pl.n_factors; f++) {
-                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
-                        int lvl = 0;
-                        for (int d = 0; d < nl - 1; d++)
-                            if (rowp[(size_t)(c0 + d) * stride] == 1.0f) { lvl = d + 1; break; }
-                        lvl_counts[pl.f_off[f] + lvl]++;
+        const int n = (int)pl.ss[g];
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+        if (track_excl) {  // per-level counts over rows [0, n) (batch.rs:2451-2496)
+            for (int i = 0; i < n; i++) {
+                const float* rowp = plane + (size_t)i * PT * stride;
+                for (int f = 0; f < pl.n_factors; f++) {
+                    const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
+                    int lvl = 0;
+                    for (int d = 0; d < nl - 1; d++)
+                        if (rowp[(size_t)(c0 + d) * stride] == 1.0f) { lvl = d + 1; break; }
+                    lvl_counts[pl.f_off[f] + lvl]++;
+                }
+            }
+            for (int f = 0; f < pl.n_factors; f++) {
+                uint32_t mn = 0xffffffffu;
+                for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
+                excl[f] = mn < (uint32_t)pl.min_level_count;
+            }
+        }
+        GlmOut go;
+        double all_t[MCP_MAX_T];
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int t = 0; t < pl.T; t++) all_t[t] = nan;
+        int variant = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            variant = pl.base_variant;
+            if (track_excl) {
+                variant = 0;
+                for (int f = 0; f < pl.n_factors; f++) variant |= (excl[f] != 0 ? 1 : 0) << f;
+            }
+            const McpVariant& vr = pl.variants[variant];
+            if (vr.p_red == PT) {
+                RegSolver<PT> sv;
+                double beta[PT];
+                glm_irls_reg<PT>(plane, stride, n, family, attempt == 0, sv, beta, go);
+                if (go.converged) {
+#pragma unroll
+                    for (int j = 0; j < PT; j++) sv.beta[j] = beta[j];
+                    sv.out.sigma_sq = 1.0;
+                    for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
+                }
+            } else {
+                MemSolver<PT> ms;
+                double beta[PT];
+                glm_irls_mem<PT>(plane, stride, n, family, attempt == 0, vr, ms, beta, go);
+                if (go.converged) {
+                    ms.out.sigma_sq = 1.0;
+                    for (int t = 0; t < pl.n_marg; t++) {
+                        const int c = vr.remap[pl.target[t]];
+                        all_t[t] = c >= 0 ? ms.t_sq(c, -1) : nan;
                     }
                 }
-                counted = n;
-                for (int f = 0; f < pl.n_factors; f++) {
+            }
+            if (go.converged || attempt == 1) break;
+            if (pl.min_level_count == 0) break;
+            // separation fallback: drop the included factor with the smallest min level count (batch.rs:2572-2597)
+            int best = -1;
+            uint32_t best_min = 0;
+            for (int f = 0; f < pl.n_factors; f++) {
+                if (excl[f] == 0) {
                     uint32_t mn = 0xffffffffu;
                     for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
-                    excl[f] = mn < (uint32_t)pl.min_level_count;
+                    if (best < 0 || mn < best_min) { best = f; best_min = mn; }
                 }
             }
-            GlmOut go;
-            double all_t[MCP_MAX_T];
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            for (int t = 0; t < pl.T; t++) all_t[t] = nan;
-            int variant = 0;
-            for (int attempt = 0; attempt < 2; attempt++) {
-                variant = pl.base_variant;
-                if (track_excl) {
-                    variant = 0;
-                    for (int f = 0; f < pl.n_factors; f++) variant |= (excl[f] != 0 ? 1 : 0) << f;
-                }
-                const McpVariant& vr = pl.variants[variant];
-                if (vr.p_red == PT) {
-                    RegSolver<PT> sv;
-                    double beta[PT];
-                    glm_irls_reg<PT>(plane, stride, n, family, attempt == 0, sv, beta, go);
-                    if (go.converged) {
-#pragma unroll
-                        for (int j = 0; j < PT; j++) sv.beta[j] = beta[j];
-                        sv.out.sigma_sq = 1.0;
-                        for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
-                    }
-                } else {
-                    MemSolver<PT> ms;
-                    double beta[PT];
-                    glm_irls_mem<PT>(plane, stride, n, family, attempt == 0, vr, ms, beta, go);
-                    if (go.converged) {
-                        ms.out.sigma_sq = 1.0;
-                        for (int t = 0; t < pl.n_marg; t++) {
-                            const int c = vr.remap[pl.target[t]];
-                            all_t[t] = c >= 0 ? ms.t_sq(c, -1) : nan;
-                        }
-                    }
-                }
-                if (go.converged || attempt == 1) break;
-                if (pl.min_level_count == 0) break;
-                // separation fallback: drop the included factor with the smallest min level count (batch.rs:2572-2597)
-                int best = -1;
-                uint32_t best_min = 0;
-                for (int f = 0; f < pl.n_factors; f++) {
-                    if (excl[f] == 0) {
-                        uint32_t mn = 0xffffffffu;
-                        for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
-                        if (best < 0 || mn < best_min) { best = f; best_min = mn; }
-                    }
-                }
-                if (best < 0) break;
-                excl[best] = 2;
-            }
-            emit_fit_glm(so, g, variant, go, all_t, excl);
+            if (best < 0) break;
+            excl[best] = 2;
         }
+        emit_fit_glm(so, g, variant, go, all_t, excl);
     }
     if (cnt_s) {
         __syncthreads();

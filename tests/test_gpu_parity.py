@@ -362,7 +362,7 @@ def test_glm_wave_split_is_invariant():
     a = M.run_batch(s, [100, 300], 700, SEED, mode=ALL)
     b = M.run_batch(s, [100, 300], 700, SEED, mode=ALL, wave_sims=256)
     assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
-    assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 3
+    assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 6  # 3 waves x (generate, fit)
 
 
 # ------------------------------------------------------------------ random-intercept LMM, REML (BASELINE config 5)
