@@ -747,11 +747,13 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
             // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
             const int cs = std::max(s.sizing_value, 1);
             const size_t nc_cap = s.sizing_fixed_size ? (size_t)(pl.max_n + cs - 1) / cs : (size_t)cs;
-            const size_t per_sim = nc_cap * (lw.P + 1) * sizeof(double);
+            // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
+            const size_t per_sim = (nc_cap * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double);
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
             wave = std::min(wave, cap);
-            wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * nc_cap * (lw.P + 1) * sizeof(double)));
+            wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs
+            if (wave > cap) wave = std::max<uint32_t>((cap / 128u) * 128u, 128u);
+            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * per_sim));
         }
         // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
         //   5 lean path — plain linear models (Normal marginals/residual, exact-walk factors, no cluster/scenario): lane-quad
@@ -811,7 +813,7 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
                 lwr.plan = saved;
             }
             r->gpu_launches += (kind == KIND_OLS && ols_variant == 6 && !pl.optimistic) ? 3
-                               : ((kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) || kind == KIND_GLM) ? 2 : 1;
+                               : ((kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) || kind == KIND_GLM || kind == KIND_LMM) ? 2 : 1;
             done += cnt;
             if (progress) {
                 CUDA_CHECK(cudaStreamSynchronize(st));

@@ -67,8 +67,15 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         glm_fit_kernel<PT, MINB><<<grid_fit, MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch);
     }
 #elif defined(MCP_TU_LMM)
-    cudaFuncSetAttribute(lmm_power_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    lmm_power_kernel<PT><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+    {
+        const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
+        cudaFuncSetAttribute(lmm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        lmm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
+        lmm_fit_kernel<PT><<<dim3(blocks, (unsigned)pl.n_ss), MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch_d);
+    }
 #else
     if (a.ols_variant == 5) {  // plain-linear-model family: lane-quad generate + accumulate kernel, then one thread per fit
         using G = LeanGeom<PT>;

@@ -189,151 +189,183 @@ static __device__ __noinline__ double lmm_joint_wald(LmmCtx<PT>& c, const int* c
     return q / sigma_sq;
 }
 
+// Scratch of one wave (stride = studies per wave, padded to whole CTAs; everything [..][study] so that the studies of a warp
+// read and write consecutive doubles):
+//   running cluster sums  csum[k][j]          k < nc_cap, j <= PT (x_0..x_{P-1}, y)
+//   snapshots             snap[g][k][j]       the cluster sums after the first ss[g] rows
+//   statistics            stat[g][e]          X'X packed lower | X'y | y'y after the first ss[g] rows
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) lmm_power_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
-                                                              double* __restrict__ scratch) {
-    constexpr int NACC = PT * (PT + 1) / 2;
-    constexpr int SP = PT | 1;
+struct LmmLayout {
+    static constexpr int NACC = PT * (PT + 1) / 2;
+    static constexpr int E = NACC + PT + 1;
+    static __host__ __device__ size_t csum_doubles(int nc_cap) { return (size_t)nc_cap * (PT + 1); }
+    static __host__ __device__ size_t per_study_doubles(int nc_cap, int n_ss) {
+        return csum_doubles(nc_cap) * (size_t)(1 + n_ss) + (size_t)n_ss * E;
+    }
+};
+
+// Stage 1 — one study per thread: generate, accumulate X'X / X'y / y'y in registers and the cluster sums in HBM; at every
+// grid point leave the statistics and a snapshot of the cluster sums for the fit kernel.
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
+                                                            double* __restrict__ scratch) {
+    using LY = LmmLayout<PT>;
+    constexpr int NACC = LY::NACC;
     const DevicePlan& pl = c_plan;
     extern __shared__ __align__(16) float smem[];
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
+    if (sim >= n_sims) return;
+    const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+    SimCtx cx;
+    cx.k0 = (uint32_t)key;
+    cx.k1 = (uint32_t)(key >> 32);
+    cx.seq.init(key);
+    cx.tau = sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0);
+    cx.seq_row_base = (uint32_t)pl.n_clusters;
+    const int max_n = pl.max_n;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
+    double* const csum = scratch + sim;
+    double* const snap = csum + LY::csum_doubles(nc_cap) * stride;
+    double* const stat = snap + LY::csum_doubles(nc_cap) * (size_t)pl.n_ss * stride;
+    for (int k = 0; k < nc_cap; k++)
+        for (int j = 0; j <= PT; j++) csum[(size_t)(k * (PT + 1) + j) * stride] = 0.0;
+
+    double acc[NACC], xty[PT];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PT; i++) xty[i] = 0.0;
+    double yty = 0.0;
+    ScenDesign<PT> sdv;
+    const bool scen = !pl.optimistic;
+    if (scen) {
+        scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+        if (!sdv.ok) atomicExch(pl.error_flag, 2);
+    }
+    int g = 0;
+    uint32_t n_next = pl.ss[0];
+    for (int b = 0; b < (max_n + 3) >> 2; b++) {
+        if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
+        else gen_block<PT, false>(b, slab, cx, nullptr);
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * b + r;
+            if (row >= max_n) break;
+            double xr[PT];
+            const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
+#pragma unroll
+            for (int a = 0; a < PT; a++) {
+#pragma unroll
+                for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
+                xty[a] = fma(xr[a], yd, xty[a]);
+            }
+            yty = fma(yd, yd, yty);
+            {  // cluster sums (plain adds in row order, like the host-side restatement)
+                const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
+                double* base = csum + (size_t)kc * (PT + 1) * stride;
+#pragma unroll
+                for (int j = 0; j < PT; j++) base[(size_t)j * stride] += xr[j];
+                base[(size_t)PT * stride] += yd;
+            }
+            if ((uint32_t)(row + 1) == n_next) {
+                double* const so = stat + (size_t)g * LY::E * stride;
+#pragma unroll
+                for (int i = 0; i < NACC; i++) so[(size_t)i * stride] = acc[i];
+#pragma unroll
+                for (int i = 0; i < PT; i++) so[(size_t)(NACC + i) * stride] = xty[i];
+                so[(size_t)(NACC + PT) * stride] = yty;
+                const int n_clusters = pl.sizing_fixed_size ? (row + 1 + cs - 1) / cs : cs;
+                double* const sn = snap + (size_t)g * LY::csum_doubles(nc_cap) * stride;
+                for (int e = 0; e < n_clusters * (PT + 1); e++) sn[(size_t)e * stride] = csum[(size_t)e * stride];
+                g++;
+                n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
+            }
+        }
+    }
+}
+
+// Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): profiled REML by Brent over the cluster
+// sufficient statistics of that prefix, Wald tests, joint Wald, boundary flag, counters / byte tensors.  The per-level counts of
+// the sparse-factor exclusion are the dummy column sums X'X[dummy][0] (a reference-coded dummy is exactly 0 / 1).
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_fit_kernel(uint32_t n_sims, const double* __restrict__ scratch) {
+    using LY = LmmLayout<PT>;
+    constexpr int NACC = LY::NACC;
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {
-        cnt_s = reinterpret_cast<unsigned int*>(smem + (size_t)MCP_BLOCK * 4 * SP);
+        cnt_s = reinterpret_cast<unsigned int*>(smem);
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
         __syncthreads();
     }
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
+    const int g = pl.n_ss - 1 - (int)blockIdx.y;  // longest fits first
     if (sim < n_sims) {
-        const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        SimCtx cx;
-        cx.k0 = (uint32_t)key;
-        cx.k1 = (uint32_t)(key >> 32);
-        cx.seq.init(key);
-        cx.tau = sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0);
-        cx.seq_row_base = (uint32_t)pl.n_clusters;
-        const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
-        double* csum = scratch + sim;
+        const int max_n = pl.max_n;
         const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
         const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
-        for (int k = 0; k < nc_cap; k++)
-            for (int j = 0; j <= PT; j++) csum[(size_t)(k * (PT + 1) + j) * stride] = 0.0;
-
-        double acc[NACC], xty[PT];
-#pragma unroll
-        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < PT; i++) xty[i] = 0.0;
-        double yty = 0.0, sum_y = 0.0;
-        uint32_t n_rows = 0;
-        uint32_t lvl_counts[MCP_MAX_LEVELS];
+        const double* const snap = scratch + sim + LY::csum_doubles(nc_cap) * stride + (size_t)g * LY::csum_doubles(nc_cap) * stride;
+        const double* const st = scratch + sim + LY::csum_doubles(nc_cap) * (size_t)(1 + pl.n_ss) * stride + (size_t)g * LY::E * stride;
+        const int n = (int)pl.ss[g];
         uint8_t excl[MCP_MAX_FACTORS];
-        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
-        for (int i = 0; i < MCP_MAX_LEVELS; i++) lvl_counts[i] = 0;
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
-        ScenDesign<PT> sdv;
-        const bool scen = !pl.optimistic;
-        if (scen) {
-            scen_populate<PT>(sdv, base_seed, sim_begin + sim);
-            if (!sdv.ok) atomicExch(pl.error_flag, 2);
-        }
-        int g = 0;
-        uint32_t n_next = pl.ss[0];
-        for (int b = 0; b < (max_n + 3) >> 2; b++) {
-            if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
-            else gen_block<PT, false>(b, slab, cx, nullptr);
-#pragma unroll 1
-            for (int r = 0; r < 4; r++) {
-                const int row = 4 * b + r;
-                if (row >= max_n) break;
-                double xr[PT];
-                const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
-#pragma unroll
-                for (int a = 0; a < PT; a++) {
-#pragma unroll
-                    for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
-                    xty[a] = fma(xr[a], yd, xty[a]);
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        int variant = pl.base_variant;
+        if (track_excl) {
+            variant = 0;
+            for (int f = 0; f < pl.n_factors; f++) {
+                uint32_t rest = (uint32_t)n, mn = 0xffffffffu;
+                for (int l = 1; l < pl.f_levels[f]; l++) {
+                    const uint32_t cnt = (uint32_t)st[(size_t)tri(pl.f_col[f] + l - 1, 0) * stride];
+                    mn = min(mn, cnt);
+                    rest -= cnt;
                 }
-                yty = fma(yd, yd, yty);
-                sum_y += yd;
-                n_rows++;
-                {  // cluster sums (plain adds in row order, like the host-side restatement)
-                    const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
-                    double* base = csum + (size_t)kc * (PT + 1) * stride;
-#pragma unroll
-                    for (int j = 0; j < PT; j++) base[(size_t)j * stride] += xr[j];
-                    base[(size_t)PT * stride] += yd;
-                }
-                if (track_excl) {
-                    for (int f = 0; f < pl.n_factors; f++) {
-                        const int c0 = pl.f_col[f] - 1, nl = pl.f_levels[f];
-                        int lvl = 0;
-                        for (int d = 0; d < nl - 1; d++)
-                            if (slab[4 * (c0 + d) + r] == 1.0f) { lvl = d + 1; break; }
-                        lvl_counts[pl.f_off[f] + lvl]++;
-                    }
-                }
-                if ((uint32_t)(row + 1) == n_next) {
-                    const int n = row + 1;
-                    int variant = pl.base_variant;
-                    if (track_excl) {
-                        variant = 0;
-                        for (int f = 0; f < pl.n_factors; f++) {
-                            uint32_t mn = 0xffffffffu;
-                            for (int q = 0; q < pl.f_levels[f]; q++) mn = min(mn, lvl_counts[pl.f_off[f] + q]);
-                            excl[f] = mn < (uint32_t)pl.min_level_count;
-                            variant |= (int)excl[f] << f;
-                        }
-                    }
-                    const McpVariant& vr = pl.variants[variant];
-                    const bool reduced = vr.p_red != PT;
-                    const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
-                    LmmCtx<PT> c;
-                    c.p = vr.p_red;
-                    c.n_rows = n_rows;
-                    c.yty = yty;
-                    {
-                        double Af[NACC], bf[PT];
-#pragma unroll
-                        for (int i = 0; i < NACC; i++) Af[i] = acc[i];
-#pragma unroll
-                        for (int i = 0; i < PT; i++) bf[i] = xty[i];
-                        for (int ri = 0; ri < vr.p_red; ri++) {
-                            c.xty[ri] = bf[vr.kept[ri]];
-                            for (int rj = 0; rj <= ri; rj++) c.xtx[tri(ri, rj)] = Af[tri(vr.kept[ri], vr.kept[rj])];
-                        }
-                    }
-                    int conv = 0, bnd = 0;
-                    lmm_fit<PT>(c, csum, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd);
-                    double all_t[MCP_MAX_T];
-                    int cols[MCP_MAX_T];
-                    int k_red = 0;
-                    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                    for (int t = 0; t < pl.n_marg; t++) {
-                        const int col = vr.remap[pl.target[t]];
-                        all_t[t] = nan;
-                        if (col >= 0) cols[k_red++] = col;
-                    }
-                    int jsig = 0;
-                    if (conv) {
-                        for (int t = 0; t < pl.n_marg; t++) {
-                            const int col = vr.remap[pl.target[t]];
-                            if (col >= 0) all_t[t] = c.ms.t_sq(col, -1);
-                        }
-                        const double jc = pl.crit_joint[(size_t)variant * pl.n_ss + g];
-                        const double jt = lmm_joint_wald<PT>(c, cols, k_red);
-                        jsig = !(isinf(jt) || jt != jt) && jt > jc;
-                    }
-                    FitOut fo = c.ms.out;
-                    fo.converged = conv;
-                    emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
-                    g++;
-                    n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
-                }
+                mn = min(mn, rest);
+                excl[f] = mn < (uint32_t)pl.min_level_count;
+                variant |= (int)excl[f] << f;
             }
         }
+        const McpVariant& vr = pl.variants[variant];
+        const bool reduced = vr.p_red != PT;
+        const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
+        LmmCtx<PT> c;
+        c.p = vr.p_red;
+        c.n_rows = (uint32_t)n;
+        c.yty = st[(size_t)(NACC + PT) * stride];
+        for (int ri = 0; ri < vr.p_red; ri++) {
+            c.xty[ri] = st[(size_t)(NACC + vr.kept[ri]) * stride];
+            for (int rj = 0; rj <= ri; rj++) c.xtx[tri(ri, rj)] = st[(size_t)tri(vr.kept[ri], vr.kept[rj]) * stride];
+        }
+        int conv = 0, bnd = 0;
+        lmm_fit<PT>(c, snap, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd);
+        double all_t[MCP_MAX_T];
+        int cols[MCP_MAX_T];
+        int k_red = 0;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int t = 0; t < pl.n_marg; t++) {
+            const int col = vr.remap[pl.target[t]];
+            all_t[t] = nan;
+            if (col >= 0) cols[k_red++] = col;
+        }
+        int jsig = 0;
+        if (conv) {
+            for (int t = 0; t < pl.n_marg; t++) {
+                const int col = vr.remap[pl.target[t]];
+                if (col >= 0) all_t[t] = c.ms.t_sq(col, -1);
+            }
+            const double jc = pl.crit_joint[(size_t)variant * pl.n_ss + g];
+            const double jt = lmm_joint_wald<PT>(c, cols, k_red);
+            jsig = !(isinf(jt) || jt != jt) && jt > jc;
+        }
+        FitOut fo = c.ms.out;
+        fo.converged = conv;
+        emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
     }
     if (cnt_s) {
         __syncthreads();
