@@ -68,13 +68,30 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     }
 #elif defined(MCP_TU_LMM)
     {
-        const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
-        cudaFuncSetAttribute(lmm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        lmm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        using LY = LmmLayout<PT>;
+        using G = Q4Geom<PT>;
+        const size_t stride = (size_t)blocks * MCP_BLOCK;
+        const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+        const int nc_cap = pl.sizing_fixed_size ? (pl.max_n + cs - 1) / cs : cs;
+        const int clus_doubles = (int)LY::csum_doubles(nc_cap);
+        const size_t smem_q = G::smem_bytes(0, 0, false) + (size_t)G::STUDIES * (size_t)((clus_doubles | 1) + (nc_cap | 1)) * sizeof(double);
+        if (!scen && smem_q <= 56 * 1024) {
+            // generator on the lane-quad kernel: cluster sums in shared memory (4 CTAs per SM fit), no read-modify-write of HBM per row
+            double* snap = a.scratch_d + LY::csum_doubles(nc_cap) * stride;
+            double* stat = snap + LY::csum_doubles(nc_cap) * (size_t)pl.n_ss * stride;
+            const uint32_t blocks_q = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, false, true, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, stat, nullptr,
+                                                                                                 stride, snap, clus_doubles);
+        } else {
+            const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
+            cudaFuncSetAttribute(lmm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            lmm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
-        lmm_fit_kernel<PT><<<dim3(blocks, (unsigned)pl.n_ss), MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch_d);
+        lmm_fit_kernel<PT><<<dim3(blocks, (unsigned)pl.n_ss), MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch_d, stride);
     }
 #else
     if (a.ols_variant == 5) {  // plain-linear-model family: lane-quad generate + accumulate kernel, then one thread per fit

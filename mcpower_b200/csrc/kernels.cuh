@@ -392,6 +392,7 @@ struct SimCtx {
     SeqRng seq;            // counter-addressed view of the sequential stream
     double tau;            // sqrt(tau²) of the random intercept
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
+    const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
 };
 
 // Residual for one row from CLASS_RESID slots (data_gen.rs:412-484).  slot0 = slot-0 normal already generated.
@@ -793,7 +794,8 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
         const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
         const uint32_t cid = pl.sizing_fixed_size ? (uint32_t)(row / cs) : (uint32_t)(row % cs);
         // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
-        if (cid < (uint32_t)pl.n_clusters) u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
+        if (cx.utab) u_re = cx.utab[cid];
+        else if (cid < (uint32_t)pl.n_clusters) u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
     }
     if (SCEN) {
         // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)

@@ -15,6 +15,7 @@
 // Every operation mirrors the test oracle's lmm_fit.
 #pragma once
 #include "kernels.cuh"
+#include "kernels_q4.cuh"
 
 namespace mcp {
 
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
 // sufficient statistics of that prefix, Wald tests, joint Wald, boundary flag, counters / byte tensors.  The per-level counts of
 // the sparse-factor exclusion are the dummy column sums X'X[dummy][0] (a reference-coded dummy is exactly 0 / 1).
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) lmm_fit_kernel(uint32_t n_sims, const double* __restrict__ scratch) {
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_fit_kernel(uint32_t n_sims, const double* __restrict__ scratch, size_t stride) {
     using LY = LmmLayout<PT>;
     constexpr int NACC = LY::NACC;
     const DevicePlan& pl = c_plan;
@@ -303,7 +304,6 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_fit_kernel(uint32_t n_sims, con
         __syncthreads();
     }
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
     const int g = pl.n_ss - 1 - (int)blockIdx.y;  // longest fits first
     if (sim < n_sims) {
         SimOut so{cnt_s, (uint64_t)sim};

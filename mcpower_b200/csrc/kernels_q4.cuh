@@ -136,10 +136,19 @@ __global__ void __launch_bounds__(MCP_BLOCK) scen_design_kernel(uint64_t base_se
     out[sim] = sd;
 }
 
-template <int PT, bool SCEN, bool SPLIT = false>
+//
+// CLUS = true (with SPLIT; the mixed-model arm's generator): the study's per-cluster sums of [1 | x | y] also live in shared
+// memory, csm[cluster][column].  After a sub-step's four rows are staged, lane q adds them — rows in order, so every sum is
+// the same sequential chain as in the oracle — into the columns j ≡ q (mod 4); at a grid point the quad copies the sums of
+// the clusters seen so far to clus_snap[(g · clus_doubles + e) · stride + study] for lmm_fit_kernel.  `stat_stride` is the
+// study stride of both buffers (0 → n_sims, the OLS layout).
+template <int PT, bool SCEN, bool SPLIT = false, bool CLUS = false>
 __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel_q4(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
                                                                                     double* __restrict__ stats = nullptr,
-                                                                                    const ScenDesign<PT>* __restrict__ designs = nullptr) {
+                                                                                    const ScenDesign<PT>* __restrict__ designs = nullptr,
+                                                                                    size_t stat_stride = 0, double* __restrict__ clus_snap = nullptr,
+                                                                                    int clus_doubles = 0) {
+    static_assert(!CLUS || SPLIT, "cluster sums are only kept on the split path");
     using G = Q4Geom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
@@ -149,6 +158,10 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
     const int q = threadIdx.x & 3;
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
     double* const stage = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)(threadIdx.x >> 2) * G::STUDY;
+    // odd study stride: the eight quads of a warp hit eight different bank pairs
+    double* const csm = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY +
+                        (size_t)(threadIdx.x >> 2) * (size_t)(clus_doubles | 1);
+    const size_t sstride = stat_stride ? stat_stride : (size_t)n_sims;
     unsigned int* cnt_s = nullptr;
     if (!SPLIT && pl.smem_counters) {  // SPLIT emits nothing: the solve kernel owns the counters
         cnt_s = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY);
@@ -182,6 +195,25 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         double acc[G::NACCQ];
 #pragma unroll
         for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
+        const int clus_cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+        if (CLUS) {
+            for (int e = q; e < clus_doubles; e += 4) csm[e] = 0.0;
+            // the study's cluster effects u_c = f32(normal(word c) · tau) (data_gen.rs:146-161), tabulated once instead of one
+            // Philox block + inverse normal per row; clusters that were never drawn (trailing partial cluster) have none
+            const int nc_cap = clus_doubles / (PT + 1);
+            double* const utab = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY +
+                                 (size_t)G::STUDIES * (size_t)(clus_doubles | 1) + (size_t)(threadIdx.x >> 2) * (size_t)(nc_cap | 1);
+            for (int c = q; c < nc_cap; c += 4)
+                utab[c] = c < pl.n_clusters ? (double)(float)((double)norm_inv_from_word(cx.seq.word_at((uint32_t)c)) * cx.tau) : 0.0;
+            cx.utab = utab;
+            __syncwarp(qmask);
+        }
+        // cluster sums of staged row r (row index row0 + r): this lane's columns, plain adds (data_gen.rs cluster_of_row)
+        auto clus_add = [&](int row, const double* zr) {
+            const int kc = pl.sizing_fixed_size ? row / clus_cs : row % clus_cs;
+            double* const base = csm + kc * (PT + 1);
+            for (int j = q; j <= PT; j += 4) base[j] += j < M ? zr[j] : zr[MH + (N - j)];
+        };
         uint32_t lvl_counts[MCP_MAX_LEVELS];  // this lane's share (rows with r == q); summed over the quad at a fit
         uint8_t excl[MCP_MAX_FACTORS];
         const bool track_excl = !SPLIT && pl.n_factors > 0 && pl.min_level_count > 0;
@@ -227,16 +259,21 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                     // fast path: four rows, no grid point inside
 #pragma unroll
                     for (int r = 0; r < 4; r++) q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                    if (CLUS) {
+#pragma unroll 1
+                        for (int r = 0; r < 4; r++) clus_add(row0 + r, stage + r * G::ROW);
+                    }
                     if (track_excl) q4_count_levels(ps, q, lvl_counts);
                 } else {
 #pragma unroll 1
                     for (int r = 0; r < nr; r++) {
                         q4_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                        if (CLUS) clus_add(row0 + r, stage + r * G::ROW);
                         if (track_excl && r == q) q4_count_levels(ps, r, lvl_counts);
                         if (SPLIT && (uint32_t)(row0 + r + 1) == n_next) {
                             // ---- grid point g: this lane's quarter of Z'Z → the statistics buffer (entry e = X'X packed lower
                             // | X'y | y'y, as LeanGeom<PT>::E)
-                            double* const out = stats + (size_t)g * (NACC + PT + 1) * n_sims + sim;
+                            double* const out = stats + (size_t)g * (NACC + PT + 1) * sstride + sim;
 #pragma unroll
                             for (int a = 0; a < M; a++) {
 #pragma unroll
@@ -244,8 +281,16 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                                     const int i = q == 0 ? a : (q == 1 ? N - a : N - c);
                                     const int j = q == 0 ? c : (q == 1 ? c : (q == 2 ? N - a : a));
                                     const int e = i < N ? tri(i, j) : NACC + j;  // j == N: y'y
-                                    out[(size_t)e * n_sims] = acc[tri(a, c)];
+                                    out[(size_t)e * sstride] = acc[tri(a, c)];
                                 }
+                            }
+                            if (CLUS) {  // snapshot of the cluster sums after the first row0 + r + 1 rows
+                                const int n_now = row0 + r + 1;
+                                const int ncl = pl.sizing_fixed_size ? (n_now + clus_cs - 1) / clus_cs : clus_cs;
+                                __syncwarp(qmask);
+                                double* const sn = clus_snap + (size_t)g * clus_doubles * sstride + sim;
+                                for (int e = q; e < ncl * (PT + 1); e += 4) sn[(size_t)e * sstride] = csm[e];
+                                __syncwarp(qmask);
                             }
                             g++;
                             n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
