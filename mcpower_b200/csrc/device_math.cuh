@@ -306,6 +306,63 @@ __device__ __forceinline__ double own_log(double x) {
     return dk * c_km[KM_LN2_HI] - ((hfsq - (s * (hfsq + R) + dk * c_km[KM_LN2_LO])) - f);
 }
 
+// Branch-free twins of own_exp / own_log: the special cases are selected at the end instead of returned early, so two
+// independent evaluations placed back to back form one basic block and ptxas interleaves their dependent FP64 chains
+// (the IRLS row loop evaluates two rows at a time).  Bit-identical to the originals for every input.
+__device__ __forceinline__ double own_exp_sel(double x) {
+    const double kf = rint(x * c_km[KM_LOG2E]);
+    double r = fma(-kf, c_km[KM_LN2_HI], x);
+    r = fma(-kf, c_km[KM_LN2_LO], r);
+    double p = c_km[KM_E13];
+    p = fma(p, r, c_km[KM_E12]);
+    p = fma(p, r, c_km[KM_E11]);
+    p = fma(p, r, c_km[KM_E10]);
+    p = fma(p, r, c_km[KM_E9]);
+    p = fma(p, r, c_km[KM_E8]);
+    p = fma(p, r, c_km[KM_E7]);
+    p = fma(p, r, c_km[KM_E6]);
+    p = fma(p, r, c_km[KM_E5]);
+    p = fma(p, r, c_km[KM_E4]);
+    p = fma(p, r, c_km[KM_E3]);
+    p = fma(p, r, c_km[KM_HALF]);
+    p = fma(p, r, c_km[KM_ONE]);
+    p = fma(p, r, c_km[KM_ONE]);
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    const double s1 = __longlong_as_double((long long)(k1 + 1023) << 52);
+    const double s2 = __longlong_as_double((long long)(k2 + 1023) << 52);
+    double res = p * s1 * s2;
+    res = x < c_km[KM_EXP_LO] ? 0.0 : res;
+    res = x > c_km[KM_EXP_HI] ? __longlong_as_double(0x7ff0000000000000LL) : res;
+    return x != x ? x : res;
+}
+
+__device__ __forceinline__ double own_log_sel(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    const bool sub = (b >> 52) == 0;
+    const double xs = sub ? x * c_km[KM_TWO54] : x;
+    b = (unsigned long long)__double_as_longlong(xs);
+    int k = (sub ? -54 : 0) + (int)(b >> 52) - 1023;
+    const unsigned long long mant = b & 0x000fffffffffffffULL;
+    const bool hi = mant >= 0x6a09e667f3bcdULL;
+    b = mant | (hi ? 0x3fe0000000000000ULL : 0x3ff0000000000000ULL);
+    k += hi ? 1 : 0;
+    const double f = __longlong_as_double((long long)b) - c_km[KM_ONE];
+    const double s = f / (c_km[KM_TWO] + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (c_km[KM_LG2] + w * (c_km[KM_LG4] + w * c_km[KM_LG6]));
+    const double t2 = z * (c_km[KM_LG1] + w * (c_km[KM_LG3] + w * (c_km[KM_LG5] + w * c_km[KM_LG7])));
+    const double R = t2 + t1;
+    const double hfsq = c_km[KM_HALF] * f * f;
+    const double dk = (double)k;
+    double res = dk * c_km[KM_LN2_HI] - ((hfsq - (s * (hfsq + R) + dk * c_km[KM_LN2_LO])) - f);
+    res = x == __longlong_as_double(0x7ff0000000000000LL) ? x : res;
+    res = x == 0.0 ? __longlong_as_double(0xfff0000000000000LL) : res;
+    res = x < 0.0 ? __longlong_as_double(0x7ff8000000000000LL) : res;
+    return x != x ? x : res;
+}
+
 // distributions.rs:32-56 — A&S 7.1.26
 __device__ __forceinline__ double phi(double z) {
     const double x = -z * c_km[KM_RSQRT2];

@@ -61,9 +61,9 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         if (e != cudaSuccess) return e;
         const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
         const dim3 grid_fit(blocks, (unsigned)pl.n_ss);
-        // resident CTAs per SM the fit kernel is compiled for: the IRLS accumulators (P(P+1)/2 + P doubles) set the register
-        // floor; measured at P = 5 (config 4): 2 → 1.21e7, 4 → 1.71e7, 5 → 1.75e7, 6 → 1.57e7, 8 → 1.58e7 fits/s
-        constexpr int MINB = PT <= 5 ? 5 : (PT <= 6 ? 4 : (PT <= 8 ? 3 : 2));
+        // resident CTAs per SM the fit kernel is compiled for: the IRLS accumulators (P(P+1)/2 + P doubles) and the two rows
+        // in flight set the register floor; measured at P = 5 (config 4, two-row loop): 5 → 1.86e7, 4 → 2.30e7, 3 → 2.17e7 fits/s
+        constexpr int MINB = PT <= 6 ? 4 : (PT <= 8 ? 3 : 2);
         glm_fit_kernel<PT, MINB><<<grid_fit, MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch);
     }
 #elif defined(MCP_TU_LMM)

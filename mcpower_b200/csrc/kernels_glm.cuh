@@ -53,6 +53,19 @@ __device__ __forceinline__ void glm_row(int family, double eta, double y, double
     }
 }
 
+// Logit row, branch-free (selects only): the same arithmetic as glm_row(family 0), so that two rows evaluated back to back
+// interleave their exp / division / log chains.
+__device__ __forceinline__ void glm_row_logit_sel(double eta, double y, double& w, double& z, double& dev) {
+    const double e = own_exp_sel(-fabs(eta));
+    const double inv = 1.0 / (1.0 + e);
+    const double mu = eta >= 0.0 ? inv : e * inv;
+    double ww = mu * (1.0 - mu);
+    ww = ww < MCP_GLM_WCLAMP ? MCP_GLM_WCLAMP : ww;
+    w = ww;
+    z = eta + (y - mu) / ww;
+    dev = -2.0 * own_log_sel(y > 0.5 ? mu : 1.0 - mu);
+}
+
 struct GlmOut {
     int converged, iters;
     double deviance, deviance_null;
@@ -87,6 +100,95 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
 #pragma unroll
         for (int i = 0; i < PT; i++) b[i] = 0.0;
         dev = 0.0;
+        if (family == 0) {
+            // logit: two rows per iteration.  Every accumulator still sees the rows in order (row i, then row i + 1), so the
+            // sums are bit-identical to the one-row loop; the two rows' exp / division / log chains are independent and
+            // interleave.  Rows i + 2 / i + 3 are fetched (coalesced, L2 / HBM) while rows i / i + 1 are processed.
+            float nx0[PT], nx1[PT];
+#pragma unroll
+            for (int j = 0; j < PT; j++) {
+                nx0[j] = n > 0 ? plane[(size_t)j * stride] : 0.0f;
+                nx1[j] = n > 1 ? plane[(size_t)(PT + j) * stride] : 0.0f;
+            }
+            int i = 0;
+            for (; i + 1 < n; i += 2) {
+                float c0[PT], c1[PT];
+#pragma unroll
+                for (int j = 0; j < PT; j++) {
+                    c0[j] = nx0[j];
+                    c1[j] = nx1[j];
+                }
+                if (i + 2 < n) {
+                    const float* rowp = plane + (size_t)(i + 2) * PT * stride;
+#pragma unroll
+                    for (int j = 0; j < PT; j++) nx0[j] = rowp[(size_t)j * stride];
+                }
+                if (i + 3 < n) {
+                    const float* rowp = plane + (size_t)(i + 3) * PT * stride;
+#pragma unroll
+                    for (int j = 0; j < PT; j++) nx1[j] = rowp[(size_t)j * stride];
+                }
+                double x0[PT], x1[PT];
+                x0[0] = 1.0;
+                x1[0] = 1.0;
+#pragma unroll
+                for (int j = 1; j < PT; j++) {
+                    x0[j] = (double)c0[j - 1];
+                    x1[j] = (double)c1[j - 1];
+                }
+                const double y0 = (double)c0[PT - 1], y1 = (double)c1[PT - 1];
+                double eta0 = 0.0, eta1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < PT; j++) {
+                    eta0 = fma(x0[j], beta[j], eta0);
+                    eta1 = fma(x1[j], beta[j], eta1);
+                }
+                double w0, z0, d0, w1, z1, d1;
+                glm_row_logit_sel(eta0, y0, w0, z0, d0);
+                glm_row_logit_sel(eta1, y1, w1, z1, d1);
+                dev += d0;
+                dev += d1;
+                if (it == 0) {
+                    s0 += y0;
+                    s0 += y1;
+                }
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+                    const double wa = w0 * x0[a];
+#pragma unroll
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x0[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z0, b[a]);
+                }
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+                    const double wa = w1 * x1[a];
+#pragma unroll
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x1[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z1, b[a]);
+                }
+            }
+            if (i < n) {  // odd row count: the last row alone (it sits in nx0)
+                double x0[PT];
+                x0[0] = 1.0;
+#pragma unroll
+                for (int j = 1; j < PT; j++) x0[j] = (double)nx0[j - 1];
+                const double y0 = (double)nx0[PT - 1];
+                double eta0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < PT; j++) eta0 = fma(x0[j], beta[j], eta0);
+                double w0, z0, d0;
+                glm_row_logit_sel(eta0, y0, w0, z0, d0);
+                dev += d0;
+                if (it == 0) s0 += y0;
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+                    const double wa = w0 * x0[a];
+#pragma unroll
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x0[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z0, b[a]);
+                }
+            }
+        } else {
         // software pipeline: row i + 1 is fetched (coalesced, L2/HBM) while row i's ~300 instructions run
         float nxt[PT];
 #pragma unroll
@@ -122,6 +224,7 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
                 for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, xr[c], A[tri(a, c)]);
                 b[a] = fma(wa, z, b[a]);
             }
+        }
         }
         if (isinf(dev) || dev != dev) {
             active = false;
