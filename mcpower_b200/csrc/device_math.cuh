@@ -435,6 +435,39 @@ static __device__ __noinline__ double apply_marginal(double z, int dist_col, dou
     return z;
 }
 
+// Two elements of one column at a time (rows r and r + 1 carry the same marginal kind): the same arithmetic as
+// apply_marginal, with the branch-free exp / log twins, so that the two elements' Φ → (−ln) chains interleave.  Inputs and
+// results are the f32 plane values (the caller casts apply_marginal's result to f32 anyway).
+__device__ __forceinline__ double phi_sel(double z) {
+    const double x = -z * c_km[KM_RSQRT2];
+    const double sign = x < 0.0 ? -1.0 : 1.0;
+    const double ax = fabs(x);
+    const double t = c_km[KM_ONE] / (c_km[KM_ONE] + c_km[KM_AS_P] * ax);
+    const double y = c_km[KM_ONE] - (((((c_km[KM_AS_A5] * t + c_km[KM_AS_A4]) * t) + c_km[KM_AS_A3]) * t + c_km[KM_AS_A2]) * t + c_km[KM_AS_A1]) * t *
+                                        own_exp_sel(-ax * ax);
+    return c_km[KM_HALF] * (c_km[KM_ONE] - sign * y);
+}
+static __device__ __noinline__ float2 apply_marginal2(float x0, float x1, int dist_col, double param, const double* __restrict__ t3) {
+    const int dist = dist_col & 0xff;
+    if (dist == 0 || dist >= D_UPLOADED_FACTOR)  // identity / uploaded kinds: the one-element path
+        return make_float2((float)apply_marginal((double)x0, dist_col, param, t3), (float)apply_marginal((double)x1, dist_col, param, t3));
+    const double z0 = (double)x0, z1 = (double)x1;
+    const double u0 = phi_sel(dist == 2 ? -z0 : z0);
+    const double u1 = phi_sel(dist == 2 ? -z1 : z1);
+    if (dist == 2 || dist == 3) {
+        const double FL = 1.0 / 2048.0;
+        double e0 = -own_log_sel(u0 < FL ? FL : u0);
+        double e1 = -own_log_sel(u1 < FL ? FL : u1);
+        e0 = e0 > MCP_EXP_CAP ? MCP_EXP_CAP : e0;
+        e1 = e1 > MCP_EXP_CAP ? MCP_EXP_CAP : e1;
+        if (dist == 2) return make_float2((float)((e0 - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD), (float)((e1 - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD));
+        return make_float2((float)((MCP_EXP_CENSORED_MEAN - e0) / MCP_EXP_CENSORED_STD), (float)((MCP_EXP_CENSORED_MEAN - e1) / MCP_EXP_CENSORED_STD));
+    }
+    if (dist == 1) return make_float2(u0 < 1.0 - param ? 0.0f : 1.0f, u1 < 1.0 - param ? 0.0f : 1.0f);
+    if (dist == 4) return make_float2((float)t3_lookup(t3, u0), (float)t3_lookup(t3, u1));
+    return make_float2((float)(-MCP_SQRT3 + (MCP_SQRT3 - (-MCP_SQRT3)) * u0), (float)(-MCP_SQRT3 + (MCP_SQRT3 - (-MCP_SQRT3)) * u1));  // dist == 5
+}
+
 // rng.rs:399-419
 static __device__ __noinline__ double poisson_quantile(double z, double lambda) {
     if (!(lambda > 0.0)) return 0.0;

@@ -724,11 +724,22 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
                     double a = 0.0;
 #pragma unroll
                     for (int m = 0; m <= j; m++) a = a + (SCEN ? sd->L[j * KT + m] : pl.L[j * MCP_MAX_K + m]) * zr[m];
-                    float xf = (float)a;
-                    const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
-                    if (vt != D_NORMAL) xf = (float)apply_marginal((double)xf, vt | (j << 8), pl.var_param[j], pl.t3_table);
-                    slab[4 * j + r] = xf;
+                    slab[4 * j + r] = (float)a;
                 }
+            }
+        }
+        // marginal transforms on the mixed f32 values, two rows of a column per call (same kind: their chains interleave)
+        if (SCEN || !pl.all_normal) {
+#pragma unroll 1
+            for (int j = 0; j < k; j++) {
+                const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
+                if (vt == D_NORMAL) continue;
+                const float2 lo = apply_marginal2(slab[4 * j + 0], slab[4 * j + 1], vt | (j << 8), pl.var_param[j], pl.t3_table);
+                const float2 hi = apply_marginal2(slab[4 * j + 2], slab[4 * j + 3], vt | (j << 8), pl.var_param[j], pl.t3_table);
+                slab[4 * j + 0] = lo.x;
+                slab[4 * j + 1] = lo.y;
+                slab[4 * j + 2] = hi.x;
+                slab[4 * j + 3] = hi.y;
             }
         }
     }
