@@ -12,6 +12,7 @@ collective; the only exchange is one all-reduce of the per-cell integer counters
   roofline      : instruction-issue view (the real bound): algorithmic warp-instructions/s ÷ issue peak
   roofline_fp64 : FP64-pipe view — algorithmic FP64 flop per fit ÷ measured DFMA peak
   secondary     : BASELINE configs[1] (sample-size sweep, correlated predictors + factor, Bonferroni) fits/s
+  workloads     : BASELINE configs[2..4] (doomer scenario sweep, logistic GLM, random-intercept LMM) fits/s, device time
   cpu_baseline  : the oracle (CPU restatement of the reference algorithm) on all host threads, bounded sample
 
 `--impl reference` times the oracle alone (the Rust engine cannot be built here: no cargo/rustc).
@@ -261,6 +262,18 @@ def main():
             line["secondary"] = {"workload": "c2_sweep_p11_grid50_bonferroni", "n_sims": 1 << 18, "n_sample_sizes": len(grid),
                                  "fits_per_s": (1 << 18) * len(grid) / (rs.kernel_ms * 1e-3),
                                  "sims_per_s": (1 << 18) / (rs.kernel_ms * 1e-3), "n_gpus": 1}
+            # the other BASELINE configs (device time, one GPU): robustness scenario sweep, logistic GLM power curve,
+            # random-intercept mixed model — the split path's kernels
+            doomer = dict(sweep, scenario=S.scenario("doomer"), crit_values={"alpha": 5e-7, "posthoc_alpha": None})
+            others = {}
+            for name, wspec, wgrid, wn in (("c3_doomer_alpha5e-7_grid50", doomer, grid, 1 << 18),
+                                           ("c4_logit_n50_2000", S.logit_spec(), [50, 100, 200, 500, 1000, 2000], 1 << 17),
+                                           ("c5_lmm_30clusters_grid", S.lmm_spec(30, 0.2), [60, 120, 300, 600, 900], 1 << 19)):
+                M.run_batch(wspec, wgrid, 4096, seed, device=local_rank)
+                rw = M.run_batch(wspec, wgrid, wn, seed, device=local_rank)
+                others[name] = {"n_sims": wn, "n_sample_sizes": len(wgrid), "fits_per_s": wn * len(wgrid) / (rw.kernel_ms * 1e-3),
+                                "gpu_launches": int(rw.gpu_launches)}
+            line["workloads"] = others
         if world == 1 and not args.no_cpu_baseline:
             from oracle import orc
             v, cores, n_big, dt = cpu_reference(spec, N_ROWS, seed, 12.0, orc)

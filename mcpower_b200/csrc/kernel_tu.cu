@@ -54,9 +54,19 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     if (kind != MCP_TU_KIND) return cudaErrorInvalidValue;
 #if defined(MCP_TU_GLM)
     {
-        const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
-        cudaFuncSetAttribute(glm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        glm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+        if (!scen) {
+            // generator on the lane-quad kernel (PLANE mode): four rows of a study in flight per quad, 4 CTAs per SM
+            using G = Q4Geom<PT>;
+            const size_t smem_q = G::smem_bytes(0, 0, false);
+            const uint32_t blocks_q = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
+            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel_q4<PT, false, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
+                a.base_seed, a.sim_begin, a.n_sims, nullptr, nullptr, (size_t)blocks * MCP_BLOCK, nullptr, 0, a.scratch);
+        } else {
+            const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
+            cudaFuncSetAttribute(glm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            glm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;

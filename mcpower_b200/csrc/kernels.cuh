@@ -395,33 +395,42 @@ struct SimCtx {
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
 };
 
-// Residual for one row from CLASS_RESID slots (data_gen.rs:412-484).  slot0 = slot-0 normal already generated.
-static __device__ __noinline__ float transform_residual(int dist, double df_in, float slot0, uint32_t blk, int lane, uint32_t k0, uint32_t k1) {
+// Residuals of the four rows of Philox block `blk` from the CLASS_RESID slots (data_gen.rs:412-484); slot0 = the slot-0
+// normals already generated.  ONE Philox call per extra slot serves all four rows and the four inverse-normal chains
+// interleave; each row's chi-square is accumulated in slot order, as in the oracle.
+static __device__ __noinline__ float4 transform_residual4(int dist, double df_in, float4 slot0, uint32_t blk, uint32_t k0, uint32_t k1) {
     const double df = df_in > 3.0 ? df_in : 3.0;
     long long dfi = llround(df);
     if (dfi < 1) dfi = 1;
-    double chi2 = 0.0;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
     const bool is_t = dist == R_HIGH_KURTOSIS;
     if (!is_t) {  // right/left skewed: slots 0..df-1, slot 0 is the draw we already have
-        const double gg = (double)slot0;
-        chi2 += gg * gg;
+        const double g0 = (double)slot0.x, g1 = (double)slot0.y, g2 = (double)slot0.z, g3 = (double)slot0.w;
+        c0 += g0 * g0;
+        c1 += g1 * g1;
+        c2 += g2 * g2;
+        c3 += g3 * g3;
     }
     for (long long s = is_t ? 0 : 1; s < dfi; s++) {
         const U4 w = philox4x32_10(blk, (uint32_t)(is_t ? 1 + s : s), 2u, 0u, k0, k1);
-        const uint32_t ww = lane == 0 ? w.x : (lane == 1 ? w.y : (lane == 2 ? w.z : w.w));
-        const double gg = (double)norm_inv_from_word(ww);
-        chi2 += gg * gg;
+        const double g0 = (double)norm_inv_from_word(w.x), g1 = (double)norm_inv_from_word(w.y);
+        const double g2 = (double)norm_inv_from_word(w.z), g3 = (double)norm_inv_from_word(w.w);
+        c0 += g0 * g0;
+        c1 += g1 * g1;
+        c2 += g2 * g2;
+        c3 += g3 * g3;
     }
     if (is_t) {
         const double scale = 1.0 / sqrt(df / (df - 2.0));
-        const double z = (double)slot0;
-        const double denom = sqrt(chi2 / df);
-        const double t = denom <= 0.0 ? z : z / denom;
-        return (float)(t * scale);
+        const double d0 = sqrt(c0 / df), d1 = sqrt(c1 / df), d2 = sqrt(c2 / df), d3 = sqrt(c3 / df);
+        const double z0 = (double)slot0.x, z1 = (double)slot0.y, z2 = (double)slot0.z, z3 = (double)slot0.w;
+        return make_float4((float)((d0 <= 0.0 ? z0 : z0 / d0) * scale), (float)((d1 <= 0.0 ? z1 : z1 / d1) * scale),
+                           (float)((d2 <= 0.0 ? z2 : z2 / d2) * scale), (float)((d3 <= 0.0 ? z3 : z3 / d3) * scale));
     }
     const double scale = 1.0 / sqrt(2.0 * df);
     const double sign = dist == R_LEFT_SKEWED ? -1.0 : 1.0;
-    return (float)(sign * (chi2 - df) * scale);
+    return make_float4((float)(sign * (c0 - df) * scale), (float)(sign * (c1 - df) * scale), (float)(sign * (c2 - df) * scale),
+                       (float)(sign * (c3 - df) * scale));
 }
 
 // Per-thread view of the shared-memory slab.  Element `off` of thread t lives at smem[off * STRIDE + t]:
@@ -709,8 +718,13 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
     }
     // ---- B'. t / chi-square residuals need extra CLASS_RESID slots
     if (pl.outcome == O_CONTINUOUS && residual_dist != R_NORMAL && residual_dist != R_UNIFORM) {
-        for (int r = 0; r < 4; r++)
-            slab[4 * (PT - 1) + r] = transform_residual(residual_dist, pl.residual_df, slab[4 * (PT - 1) + r], (uint32_t)b, r, k0, k1);
+        const float4 e4 = transform_residual4(residual_dist, pl.residual_df,
+                                              make_float4(slab[4 * (PT - 1) + 0], slab[4 * (PT - 1) + 1], slab[4 * (PT - 1) + 2], slab[4 * (PT - 1) + 3]),
+                                              (uint32_t)b, k0, k1);
+        slab[4 * (PT - 1) + 0] = e4.x;
+        slab[4 * (PT - 1) + 1] = e4.y;
+        slab[4 * (PT - 1) + 2] = e4.z;
+        slab[4 * (PT - 1) + 3] = e4.w;
     }
     // ---- C. Cholesky mix + marginal transforms (data_gen.rs:334-363); skipped when L = I and all Normal
     if (SCEN || !(pl.l_identity && pl.all_normal)) {

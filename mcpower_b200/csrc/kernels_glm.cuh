@@ -17,6 +17,7 @@
 // own values are not in the reference tree.  Every operation mirrors the test oracle's glm_irls.
 #pragma once
 #include "kernels.cuh"
+#include "kernels_q4.cuh"
 
 namespace mcp {
 

@@ -142,13 +142,18 @@ __global__ void __launch_bounds__(MCP_BLOCK) scen_design_kernel(uint64_t base_se
 // the same sequential chain as in the oracle — into the columns j ≡ q (mod 4); at a grid point the quad copies the sums of
 // the clusters seen so far to clus_snap[(g · clus_doubles + e) · stride + study] for lmm_fit_kernel.  `stat_stride` is the
 // study stride of both buffers (0 → n_sims, the OLS layout).
-template <int PT, bool SCEN, bool SPLIT = false, bool CLUS = false>
+//
+// PLANE = true (with SPLIT; the GLM arm's generator): nothing is accumulated — lane q writes the finished row row0 + q
+// (x_1 … x_{P−1}, y as f32) to the data plane plane[(row · PT + column) · stride + study] that glm_fit_kernel re-reads on
+// every IRLS pass.
+template <int PT, bool SCEN, bool SPLIT = false, bool CLUS = false, bool PLANE = false>
 __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel_q4(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims,
                                                                                     double* __restrict__ stats = nullptr,
                                                                                     const ScenDesign<PT>* __restrict__ designs = nullptr,
                                                                                     size_t stat_stride = 0, double* __restrict__ clus_snap = nullptr,
-                                                                                    int clus_doubles = 0) {
+                                                                                    int clus_doubles = 0, float* __restrict__ plane = nullptr) {
     static_assert(!CLUS || SPLIT, "cluster sums are only kept on the split path");
+    static_assert(!PLANE || (SPLIT && !CLUS), "the data plane is written on the split path");
     using G = Q4Geom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
@@ -244,15 +249,22 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                         for (int j = 0; j < PT; j++) z[j] = xr[j];
                         z[PT] = yd;
                     }
-                    double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
+                    if (PLANE) {
+                        float* const rowp = plane + (size_t)(row0 + q) * PT * sstride + sim;
 #pragma unroll
-                    for (int j = 0; j < MH / 2; j++) {
-                        const int j0 = 2 * j, j1 = 2 * j + 1;
-                        dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
-                        dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                        for (int j = 1; j <= PT; j++) rowp[(size_t)(j - 1) * sstride] = (float)z[j];
+                    } else {
+                        double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
+#pragma unroll
+                        for (int j = 0; j < MH / 2; j++) {
+                            const int j0 = 2 * j, j1 = 2 * j + 1;
+                            dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
+                            dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                        }
                     }
                 }
                 __syncwarp(qmask);
+                if (PLANE) continue;
                 // ---- E. row pass: the same local pattern in every lane
                 const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
                 if (nr == 4 && n_next - (uint32_t)row0 > 4u) {
