@@ -22,6 +22,10 @@ namespace mcp {
 #define MCP_LMM_THETA_MAX 30.0
 #define MCP_LMM_TOL 1e-10
 #define MCP_LMM_MAXIT 200
+// resident CTAs per SM the fit kernel is compiled for.  The REML search is latency-bound (serial Brent steps, six logs per
+// evaluation), so occupancy pays until the spills bite; measured at P = 3 (config 5): unbounded (168 registers) 1.15e8,
+// 4 → 1.21e8, 6 → 1.27e8, 8 → 1.32e8, 10 → 1.37e8, 12 → 1.33e8 fits/s
+#define MCP_LMM_FIT_MINB(PT) ((PT) <= 3 ? 10 : ((PT) <= 4 ? 8 : ((PT) <= 6 ? 6 : 4)))
 
 template <int PT>
 struct LmmCtx {
@@ -63,12 +67,126 @@ static __device__ __noinline__ double lmm_dev(LmmCtx<PT>& c, double theta) {
     return ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
 }
 
-// Brent's fmin on [a, b] (golden section + parabolic interpolation).
+// The same profiled deviance for the FULL model (p == PT), value only, on register copies of the sufficient statistics:
+// every loop has static bounds, nothing goes through local memory, and the solve stops at what the deviance needs (Cholesky,
+// forward substitution, rss).  Operation for operation the arithmetic of lmm_dev + MemSolver::factor_and_solve, so the Brent
+// search sees bit-identical values; the final evaluation at theta-hat still runs lmm_dev, which leaves L / beta / sigma².
 template <int PT>
-static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out) {
+struct LmmRegStats {
+    static constexpr int NACC = PT * (PT + 1) / 2;
+    int ng;
+    double n_rows;
+    double xtx[NACC], xty[PT], yty;
+    double grp_n[2], grp_m[2];
+    double M[2][NACC], v[2][PT], w[2];
+    __device__ __forceinline__ void load(const LmmCtx<PT>& c) {
+        ng = c.ng;
+        n_rows = (double)c.n_rows;
+        yty = c.yty;
+#pragma unroll
+        for (int e = 0; e < NACC; e++) {
+            xtx[e] = c.xtx[e];
+            M[0][e] = c.M[0][e];
+            M[1][e] = c.M[1][e];
+        }
+#pragma unroll
+        for (int j = 0; j < PT; j++) {
+            xty[j] = c.xty[j];
+            v[0][j] = c.v[0][j];
+            v[1][j] = c.v[1][j];
+        }
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            grp_n[g] = c.grp_n[g];
+            grp_m[g] = c.grp_m[g];
+            w[g] = c.w[g];
+        }
+    }
+    __device__ __forceinline__ double dev(double theta) const {
+        const double t2 = theta * theta;
+        double s[2] = {0.0, 0.0};
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+            if (g < ng) s[g] = t2 / (1.0 + t2 * grp_n[g]);
+        double A[NACC], b[PT];
+#pragma unroll
+        for (int e = 0; e < NACC; e++) {
+            double a = xtx[e];
+#pragma unroll
+            for (int g = 0; g < 2; g++)
+                if (g < ng) a = fma(-s[g], M[g][e], a);
+            A[e] = a;
+        }
+#pragma unroll
+        for (int j = 0; j < PT; j++) {
+            double a = xty[j];
+#pragma unroll
+            for (int g = 0; g < 2; g++)
+                if (g < ng) a = fma(-s[g], v[g][j], a);
+            b[j] = a;
+        }
+        double cc = yty;
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+            if (g < ng) cc = fma(-s[g], w[g], cc);
+        // MemSolver::factor_and_solve, p = PT: Cholesky–Banachiewicz, forward substitution, rss
+        double L[NACC], inv_d[PT], wv[PT];
+        int ok = 1;
+        double dmin = __longlong_as_double(0x7ff0000000000000LL), dmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+                double sacc = A[tri(i, j)];
+#pragma unroll
+                for (int k = 0; k < j; k++) sacc = fma(-L[tri(i, k)], L[tri(j, k)], sacc);
+                if (i == j) {
+                    if (!(sacc > 0.0) || isinf(sacc)) {
+                        ok = 0;
+                        sacc = 1.0;
+                    }
+                    const double d = sqrt(sacc);
+                    L[tri(i, i)] = d;
+                    inv_d[i] = 1.0 / d;
+                    dmin = d < dmin ? d : dmin;
+                    dmax = d > dmax ? d : dmax;
+                } else {
+                    L[tri(i, j)] = sacc * inv_d[j];
+                }
+            }
+        }
+        if (ok && !(dmin / dmax >= MCP_EPS_RANK)) ok = 0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            double sacc = b[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) sacc = fma(-L[tri(i, k)], wv[k], sacc);
+            wv[i] = sacc * inv_d[i];
+        }
+        double rss = cc;
+#pragma unroll
+        for (int i = 0; i < PT; i++) rss = fma(-wv[i], wv[i], rss);
+        const double df_resid = n_rows - (double)PT;
+        const double sigma_sq = rss / df_resid;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        if (!ok || !(rss > 0.0) || isinf(rss)) return inf;
+        double ldv = 0.0;
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+            if (g < ng) ldv += grp_m[g] * own_log(1.0 + t2 * grp_n[g]);
+        double lda = 0.0;
+#pragma unroll
+        for (int j = 0; j < PT; j++) lda += own_log(L[tri(j, j)]);
+        return ldv + 2.0 * lda + df_resid * own_log(sigma_sq);
+    }
+};
+
+// Brent's fmin on [a, b] (golden section + parabolic interpolation) over any deviance evaluator.
+template <typename F>
+__device__ __forceinline__ double lmm_fmin_over(F&& dev_at, double a, double b, double tol, double& fmin_out) {
     const double cgold = 0.3819660112501051, eps = 1.4901161193847656e-08;
     double v = a + cgold * (b - a), w = v, x = v, e = 0.0, d = 0.0;
-    double fx = lmm_dev<PT>(c, x), fv = fx, fw = fx;
+    double fx = dev_at(x), fv = fx, fw = fx;
     for (int it = 0; it < MCP_LMM_MAXIT; it++) {
         const double xm = 0.5 * (a + b), tol1 = eps * fabs(x) + tol / 3.0, tol2 = 2.0 * tol1;
         if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) break;
@@ -92,7 +210,7 @@ static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b
             d = cgold * e;
         }
         const double u = fabs(d) >= tol1 ? x + d : (d >= 0.0 ? x + tol1 : x - tol1);
-        const double fu = lmm_dev<PT>(c, u);
+        const double fu = dev_at(u);
         if (fu <= fx) {
             if (u >= x) a = x;
             else b = x;
@@ -106,6 +224,20 @@ static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b
     }
     fmin_out = fx;
     return x;
+}
+
+template <int PT>
+static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out) {
+    return lmm_fmin_over([&](double th) { return lmm_dev<PT>(c, th); }, a, b, tol, fmin_out);
+}
+// full model, small P: the search runs on registers (see LmmRegStats); also returns the deviance at theta = 0
+template <int PT>
+static __device__ __noinline__ double lmm_fmin_full(const LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out, double& f0_out) {
+    LmmRegStats<PT> rs;
+    rs.load(c);
+    const double th = lmm_fmin_over([&](double t) { return rs.dev(t); }, a, b, tol, fmin_out);
+    f0_out = rs.dev(0.0);
+    return th;
 }
 
 // rows in cluster k among the first n rows (generation.rs cluster_of_row)
@@ -152,9 +284,19 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
         }
         c.w[g] = fma(sx[p], sx[p], c.w[g]);
     }
-    double fbest;
-    double th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest);
-    const double f0 = lmm_dev<PT>(c, 0.0);
+    double fbest, f0;
+    double th;
+    bool searched = false;
+    if constexpr (PT <= 6) {  // register-resident search (bit-identical values); wider models keep the generic evaluator
+        if (p == PT) {
+            th = lmm_fmin_full<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest, f0);
+            searched = true;
+        }
+    }
+    if (!searched) {
+        th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest);
+        f0 = lmm_dev<PT>(c, 0.0);
+    }
     boundary = 0;
     converged = 1;
     if (!(fbest < f0)) { th = 0.0; boundary = 1; }  // tau-hat = 0: OLS fallback (spec.rs:562-565)
@@ -292,7 +434,7 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
 // sufficient statistics of that prefix, Wald tests, joint Wald, boundary flag, counters / byte tensors.  The per-level counts of
 // the sparse-factor exclusion are the dummy column sums X'X[dummy][0] (a reference-coded dummy is exactly 0 / 1).
 template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) lmm_fit_kernel(uint32_t n_sims, const double* __restrict__ scratch, size_t stride) {
+__global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kernel(uint32_t n_sims, const double* __restrict__ scratch, size_t stride) {
     using LY = LmmLayout<PT>;
     constexpr int NACC = LY::NACC;
     const DevicePlan& pl = c_plan;
