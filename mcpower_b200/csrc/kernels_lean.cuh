@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
 // corrections, overall F, counters / byte tensors (ols_fit_and_emit — the same code the thread-per-study kernel runs).
 // grid = (⌈n_sims / MCP_BLOCK⌉, n_ss); Σy is X'y[0] (x_0 ≡ 1).
 #ifndef MCP_SOLVE_MIN_BLOCKS
-#define MCP_SOLVE_MIN_BLOCKS 2
+#define MCP_SOLVE_MIN_BLOCKS 3  // measured on the 50-point sweep (P = 11): 2 → 6.13e8, 3 → 6.25e8, 4 → 5.69e8 fits/s
 #endif
 template <int PT>
 __global__ void __launch_bounds__(MCP_BLOCK, MCP_SOLVE_MIN_BLOCKS) ols_solve_kernel(uint32_t n_sims, const double* __restrict__ stats) {
