@@ -80,6 +80,40 @@ def test_validation_errors_without_a_gpu():  # batch.rs:208-330 run before any d
         M.run_batch(mle, [50], 4, 1)
 
 
+def test_uploaded_table_validation_without_a_gpu():
+    """The uploaded-data tables are checked with the rest of the spec, before any device work (the reference indexes them
+    unchecked and would panic; data_gen.rs:117-121, 563)."""
+    frame = [[0.1 * i - 1.0, float(i % 3)] for i in range(20)]
+    strict = S.with_uploaded_frame(S.add_factor(S.base_spec(1), [0.5, 0.3, 0.2], [0.1, 0.2]), frame, {0: 0}, factors={0: 1}, bootstrap=True)
+    bad = dict(strict, bootstrap_frame_map=[0, 7])
+    with pytest.raises(M.InvalidSpec, match="bootstrap_frame_map entry 7 out of range"):
+        M.run_batch(bad, [50], 4, 1)
+    bad = dict(strict, bootstrap_frame_map=[0])
+    with pytest.raises(M.InvalidSpec, match="n_non_factor \\+ n_factors"):
+        M.run_batch(bad, [50], 4, 1)
+    bad = dict(strict, upload_data_shape=[19, 2])
+    with pytest.raises(M.InvalidSpec, match="does not match `upload_data_shape`"):
+        M.run_batch(bad, [50], 4, 1)
+    norta = S.with_uploaded_frame(S.base_spec(2), frame, {1: 0})
+    assert norta["upload_normal_shape"] == [20, 2] and norta["upload_normal"][1::2] == sorted(r[0] for r in frame)
+    bad = dict(norta, upload_normal=norta["upload_normal"][:-2], upload_normal_shape=[19, 2])
+    bad["upload_normal_shape"] = [19, 1]
+    with pytest.raises(M.InvalidSpec):
+        M.run_batch(bad, [50], 4, 1)
+    menu = dict(S.base_spec(2), scenario=dict(S.scenario("realistic"), new_distributions=["uploaded_data"]))
+    with pytest.raises(M.Unsupported, match="scenario menu"):
+        M.run_batch(menu, [50], 4, 1)
+
+
+def test_contract_runners_report_lowering_errors_without_a_gpu():
+    """mcp_find_power_contracts / mcp_find_sample_size_contracts lower every contract first (find_power.rs:251-288)."""
+    bad = {"generation": {"columns": [], "correlations": "Identity", "cluster": None, "uploaded_frame": None}}
+    with pytest.raises(M.InvalidSpec, match=r"contract 0 .*missing field"):
+        M.find_power_contracts([bad], 100, 16)
+    with pytest.raises(M.InvalidSpec, match="cannot be empty"):
+        M.find_sample_size_contracts([], 20, 100, 16)
+
+
 def test_no_cpu_fallback():
     """Without a device the product must fail loudly, never compute on the host."""
     if M.device_count() > 0:
