@@ -772,10 +772,13 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
             else if (e[0] == '6') ols_variant = 6;
         }
         if (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) {
-            // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB
+            // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB of scratch, ~12 GiB
+            // on the scenario path: its one-thread-per-study design kernel is latency-bound (Jacobi repair in local memory)
+            // and wants as many studies in flight as the 180 GB part allows
             const size_t E = (size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1;
             const size_t per_sim = (size_t)n_ss * E * sizeof(double);
-            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / per_sim, 128);
+            const size_t cap_bytes = (ols_variant == 6 && !pl.optimistic) ? (size_t)12 << 30 : (size_t)4 << 30;
+            const uint32_t cap = (uint32_t)std::max<size_t>(cap_bytes / per_sim, 128);
             wave = std::min(wave, cap);
             if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
             // variant 6 on the scenario path keeps the per-study scenario designs behind the statistics (sized for the widest template)

@@ -181,15 +181,45 @@ struct LmmRegStats {
     }
 };
 
-// Brent's fmin on [a, b] (golden section + parabolic interpolation) over any deviance evaluator.
+// Brent's fmin on [a, b] (golden section + parabolic interpolation) over any deviance evaluator, followed by the evaluation
+// at theta = 0 that decides the boundary case.  Written as a small state machine around ONE call site of the evaluator: the
+// register-resident evaluator is inlined, and three copies of it (first point, search loop, theta = 0) in divergent warps were
+// the kernel's top stall (instruction fetch).  Same evaluations in the same order as the textbook loop.
 template <typename F>
-__device__ __forceinline__ double lmm_fmin_over(F&& dev_at, double a, double b, double tol, double& fmin_out) {
+__device__ __forceinline__ double lmm_fmin_over(F&& dev_at, double a, double b, double tol, double& fmin_out, double& f0_out) {
     const double cgold = 0.3819660112501051, eps = 1.4901161193847656e-08;
     double v = a + cgold * (b - a), w = v, x = v, e = 0.0, d = 0.0;
-    double fx = dev_at(x), fv = fx, fw = fx;
-    for (int it = 0; it < MCP_LMM_MAXIT; it++) {
+    double fx = 0.0, fv = 0.0, fw = 0.0;
+    double u = x;
+    int phase = 0, it = 0;  // phase 0: first point, 1: search, 2: theta = 0
+    for (;;) {
+        const double fu = dev_at(u);
+        if (phase == 2) {
+            f0_out = fu;
+            break;
+        }
+        if (phase == 0) {
+            fx = fv = fw = fu;
+            phase = 1;
+        } else {
+            if (fu <= fx) {
+                if (u >= x) a = x;
+                else b = x;
+                v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+            } else {
+                if (u < x) a = u;
+                else b = u;
+                if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+                else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+            }
+            it++;
+        }
         const double xm = 0.5 * (a + b), tol1 = eps * fabs(x) + tol / 3.0, tol2 = 2.0 * tol1;
-        if (fabs(x - xm) <= tol2 - 0.5 * (b - a)) break;
+        if (it >= MCP_LMM_MAXIT || fabs(x - xm) <= tol2 - 0.5 * (b - a)) {
+            phase = 2;
+            u = 0.0;
+            continue;
+        }
         bool golden = true;
         if (fabs(e) > tol1) {
             double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pp = (x - v) * q - (x - w) * r;
@@ -200,8 +230,8 @@ __device__ __forceinline__ double lmm_fmin_over(F&& dev_at, double a, double b, 
             e = d;
             if (fabs(pp) < fabs(0.5 * q * r) && pp > q * (a - x) && pp < q * (b - x)) {
                 d = pp / q;
-                const double u = x + d;
-                if (u - a < tol2 || b - u < tol2) d = xm - x >= 0.0 ? tol1 : -tol1;
+                const double uu = x + d;
+                if (uu - a < tol2 || b - uu < tol2) d = xm - x >= 0.0 ? tol1 : -tol1;
                 golden = false;
             }
         }
@@ -209,35 +239,22 @@ __device__ __forceinline__ double lmm_fmin_over(F&& dev_at, double a, double b, 
             e = x >= xm ? a - x : b - x;
             d = cgold * e;
         }
-        const double u = fabs(d) >= tol1 ? x + d : (d >= 0.0 ? x + tol1 : x - tol1);
-        const double fu = dev_at(u);
-        if (fu <= fx) {
-            if (u >= x) a = x;
-            else b = x;
-            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
-        } else {
-            if (u < x) a = u;
-            else b = u;
-            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
-            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
-        }
+        u = fabs(d) >= tol1 ? x + d : (d >= 0.0 ? x + tol1 : x - tol1);
     }
     fmin_out = fx;
     return x;
 }
 
 template <int PT>
-static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out) {
-    return lmm_fmin_over([&](double th) { return lmm_dev<PT>(c, th); }, a, b, tol, fmin_out);
+static __device__ __noinline__ double lmm_fmin(LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out, double& f0_out) {
+    return lmm_fmin_over([&](double th) { return lmm_dev<PT>(c, th); }, a, b, tol, fmin_out, f0_out);
 }
-// full model, small P: the search runs on registers (see LmmRegStats); also returns the deviance at theta = 0
+// full model, small P: the search runs on registers (see LmmRegStats)
 template <int PT>
 static __device__ __noinline__ double lmm_fmin_full(const LmmCtx<PT>& c, double a, double b, double tol, double& fmin_out, double& f0_out) {
     LmmRegStats<PT> rs;
     rs.load(c);
-    const double th = lmm_fmin_over([&](double t) { return rs.dev(t); }, a, b, tol, fmin_out);
-    f0_out = rs.dev(0.0);
-    return th;
+    return lmm_fmin_over([&](double t) { return rs.dev(t); }, a, b, tol, fmin_out, f0_out);
 }
 
 // rows in cluster k among the first n rows (generation.rs cluster_of_row)
@@ -293,10 +310,7 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
             searched = true;
         }
     }
-    if (!searched) {
-        th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest);
-        f0 = lmm_dev<PT>(c, 0.0);
-    }
+    if (!searched) th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest, f0);
     boundary = 0;
     converged = 1;
     if (!(fbest < f0)) { th = 0.0; boundary = 1; }  // tau-hat = 0: OLS fallback (spec.rs:562-565)
