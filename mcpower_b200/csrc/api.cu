@@ -736,19 +736,28 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
         if (glm) {
             // IRLS makes several passes over each study's data: the f32 plane of a wave is kept in HBM as
             // [row][column][sim] (coalesced across the sims of a warp); the wave is capped at ~6 GiB of scratch
-            const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float);
+            // (+ the per-study scenario designs behind the plane on the scenario path, sized for the widest template)
+            const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
             wave = std::min(wave, cap);
             wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            glm_scratch = static_cast<float*>(g_scratch.get((size_t)wave * pl.max_n * lw.P * sizeof(float)));
+            glm_scratch = static_cast<float*>(g_scratch.get((size_t)wave * per_sim));
         }
         double* lmm_scratch = nullptr;
+        bool lmm_quad = false;  // mixed-model generator on the quad kernel (cluster sums fit in shared memory; kernel_tu.cu decides the same way)
         if (mle) {
+            const int P_ = lw.P, M_ = (P_ + 2) / 2, MH_ = (M_ + 1) & ~1, STUDY_ = 4 * (2 * MH_) + 2;
+            const int cs_ = std::max(s.sizing_value, 1);
+            const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
+            const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
+                                  (size_t)(MCP_BLOCK / 4) * (((nc_ * (P_ + 1)) | 1) + (nc_ | 1)) * sizeof(double);
+            lmm_quad = smem_q <= 56 * 1024;
             // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
             const int cs = std::max(s.sizing_value, 1);
             const size_t nc_cap = s.sizing_fixed_size ? (size_t)(pl.max_n + cs - 1) / cs : (size_t)cs;
             // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
-            const size_t per_sim = (nc_cap * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double);
+            const size_t per_sim = (nc_cap * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
+                                   (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));  // + scenario designs behind the layout
             const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
             wave = std::min(wave, cap);
             wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs
@@ -815,8 +824,10 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
                 dispatch_power(lwr, kind, ka);
                 lwr.plan = saved;
             }
-            r->gpu_launches += (kind == KIND_OLS && ols_variant == 6 && !pl.optimistic) ? 3
-                               : ((kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) || kind == KIND_GLM || kind == KIND_LMM) ? 2 : 1;
+            // accumulate / generate + solve / fit per wave, + the scenario-design kernel on the scenario path (the thread-per-study
+            // cross-check kernels, variants 1 and 4, are single launches)
+            const bool two_stage = kind != KIND_OLS || ols_variant == 5 || ols_variant == 6;
+            r->gpu_launches += two_stage ? ((pl.optimistic || (mle && !lmm_quad)) ? 2 : 3) : 1;
             done += cnt;
             if (progress) {
                 CUDA_CHECK(cudaStreamSynchronize(st));

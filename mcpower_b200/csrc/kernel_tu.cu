@@ -54,18 +54,26 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
     if (kind != MCP_TU_KIND) return cudaErrorInvalidValue;
 #if defined(MCP_TU_GLM)
     {
-        if (!scen) {
-            // generator on the lane-quad kernel (PLANE mode): four rows of a study in flight per quad, 4 CTAs per SM
+        {
+            // generator on the lane-quad kernel (PLANE mode): four rows of a study in flight per quad; on the scenario path the
+            // per-study designs come from scen_design_kernel and sit behind the plane (api.cu sizes the scratch for both)
             using G = Q4Geom<PT>;
             const size_t smem_q = G::smem_bytes(0, 0, false);
             const uint32_t blocks_q = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
-            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_power_kernel_q4<PT, false, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
-                a.base_seed, a.sim_begin, a.n_sims, nullptr, nullptr, (size_t)blocks * MCP_BLOCK, nullptr, 0, a.scratch);
-        } else {
-            const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
-            cudaFuncSetAttribute(glm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            glm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch);
+            const size_t stride = (size_t)blocks * MCP_BLOCK;
+            if (scen) {
+                ScenDesign<PT>* designs = reinterpret_cast<ScenDesign<PT>*>(a.scratch + stride * (size_t)pl.max_n * PT);
+                scen_design_kernel<PT, MCP_TU_KIND><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+                cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                ols_power_kernel_q4<PT, true, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
+                    a.base_seed, a.sim_begin, a.n_sims, nullptr, designs, stride, nullptr, 0, a.scratch);
+            } else {
+                cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                ols_power_kernel_q4<PT, false, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
+                    a.base_seed, a.sim_begin, a.n_sims, nullptr, nullptr, stride, nullptr, 0, a.scratch);
+            }
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -85,14 +93,25 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const int nc_cap = pl.sizing_fixed_size ? (pl.max_n + cs - 1) / cs : cs;
         const int clus_doubles = (int)LY::csum_doubles(nc_cap);
         const size_t smem_q = G::smem_bytes(0, 0, false) + (size_t)G::STUDIES * (size_t)((clus_doubles | 1) + (nc_cap | 1)) * sizeof(double);
-        if (!scen && smem_q <= 56 * 1024) {
-            // generator on the lane-quad kernel: cluster sums in shared memory (4 CTAs per SM fit), no read-modify-write of HBM per row
+        if (smem_q <= 56 * 1024) {
+            // generator on the lane-quad kernel: cluster sums in shared memory (4 CTAs per SM fit), no read-modify-write of HBM per
+            // row; on the scenario path the per-study designs come from scen_design_kernel and sit behind the layout
             double* snap = a.scratch_d + LY::csum_doubles(nc_cap) * stride;
             double* stat = snap + LY::csum_doubles(nc_cap) * (size_t)pl.n_ss * stride;
             const uint32_t blocks_q = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
-            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-            ols_power_kernel_q4<PT, false, true, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, stat, nullptr,
-                                                                                                 stride, snap, clus_doubles);
+            if (scen) {
+                ScenDesign<PT>* designs = reinterpret_cast<ScenDesign<PT>*>(a.scratch_d + LY::per_study_doubles(nc_cap, pl.n_ss) * stride);
+                scen_design_kernel<PT, MCP_TU_KIND><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+                cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                ols_power_kernel_q4<PT, true, true, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, stat, designs,
+                                                                                                    stride, snap, clus_doubles);
+            } else {
+                cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                ols_power_kernel_q4<PT, false, true, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, stat, nullptr,
+                                                                                                     stride, snap, clus_doubles);
+            }
         } else {
             const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
             cudaFuncSetAttribute(lmm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -139,7 +158,7 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         if (scen) {
             // per-study scenario designs behind this wave's statistics (api.cu sizes the scratch for both)
             ScenDesign<PT>* designs = reinterpret_cast<ScenDesign<PT>*>(a.scratch_d + (size_t)pl.n_ss * (PT * (PT + 1) / 2 + PT + 1) * a.n_sims);
-            scen_design_kernel<PT><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
+            scen_design_kernel<PT, MCP_TU_KIND><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -1,7 +1,7 @@
 // kernels_glm.cuh — batched IRLS power kernel (logit / probit / Poisson), sm_100a.
 //
 // Replaces the unclustered GLM arm of run_one_sim (crates/engine-core/src/batch.rs:1562-2135) and
-// glmm::glm_irls_fit (call site batch.rs:1969-1981).  Two kernels per wave (glm_gen_kernel: one study per thread;
+// glmm::glm_irls_fit (call site batch.rs:1969-1981).  Two kernels per wave (the quad kernel in PLANE mode: one study per lane quad;
 // glm_fit_kernel: one (study, sample size) fit per thread):
 //   1. the study's max_n rows are generated once (same gen_block/row_xy as the OLS kernel, so the data
 //      plane is bit-identical to the reference fixtures) and parked in an HBM scratch plane laid out
@@ -341,46 +341,9 @@ static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int va
     emit_fit(so, g, variant, fo, pl.variants[variant].p_red, all_t, excl_flags, ov);
 }
 
-// Stage 1 — one study per thread: generate the max_n rows once (same gen_block / row_xy as the OLS kernels, so the data plane
-// is bit-identical to the reference fixtures) and park the f32 plane in HBM, [row][column][sim-in-wave].
-template <int PT>
-__global__ void __launch_bounds__(MCP_BLOCK) glm_gen_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, float* __restrict__ scratch) {
-    const DevicePlan& pl = c_plan;
-    extern __shared__ __align__(16) float smem[];
-    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
-    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;  // sims per wave, padded to whole blocks
-    if (sim >= n_sims) return;
-    const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-    SimCtx cx;
-    cx.k0 = (uint32_t)key;
-    cx.k1 = (uint32_t)(key >> 32);
-    cx.seq.init(key);
-    cx.tau = 0.0;
-    cx.seq_row_base = 0u;
-    const int max_n = pl.max_n;
-    float* plane = scratch + sim;
-    ScenDesign<PT> sdv;
-    const bool scen = !pl.optimistic;
-    if (scen) {
-        scen_populate<PT>(sdv, base_seed, sim_begin + sim);
-        if (!sdv.ok) atomicExch(pl.error_flag, 2);
-    }
-    for (int b = 0; b < (max_n + 3) >> 2; b++) {
-        if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
-        else gen_block<PT, false>(b, slab, cx, nullptr);
-        for (int r = 0; r < 4; r++) {
-            const int row = 4 * b + r;
-            if (row >= max_n) break;
-            double xr[PT];
-            const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
-            float* rowp = plane + (size_t)row * PT * stride;
-#pragma unroll
-            for (int j = 1; j < PT; j++) rowp[(size_t)(j - 1) * stride] = slab[4 * (j - 1) + r];
-            rowp[(size_t)(PT - 1) * stride] = (float)yd;
-        }
-    }
-}
+// Stage 1 is the lane-quad kernel in PLANE mode (kernels_q4.cuh): it generates the study's max_n rows once — the same gen_block /
+// row_xy as the OLS kernels, so the data plane is bit-identical to the reference fixtures — and parks the f32 plane in HBM,
+// [row][column][study-in-wave].
 
 // Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): the fits of one study at its different
 // sample sizes are independent (each restarts from the truth start on its own row prefix, batch.rs:1563-1577), so they run

@@ -126,7 +126,10 @@ static __device__ __noinline__ void q4_count_levels(const Slab<MCP_BLOCK> ps, in
 // and residual swaps, jittered effects) from scen_design_kernel below instead of deriving it in every lane of the quad: the
 // Jacobi repair runs once per study, in its own kernel, and the streaming kernel reads the factor through the caches.
 // One thread per study: the per-study scenario design of populate_design (data_gen.rs:990-1093) into HBM.
-template <int PT>
+// TAG = the translation unit's kernel family (OLS / GLM / LMM): every family launches this kernel for the same P, and identical
+// template instantiations in two translation units are merged by the linker — the launch could then run the other module's copy,
+// which reads THAT module's __constant__ plan (see the note in kernel_tu.cu).  The tag keeps the instantiations distinct.
+template <int PT, int TAG>
 __global__ void __launch_bounds__(MCP_BLOCK) scen_design_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, ScenDesign<PT>* __restrict__ out) {
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
     if (sim >= n_sims) return;

@@ -377,6 +377,25 @@ def test_lmm_random_intercept_matches_oracle():
     assert p[-1] > 0.95 and np.all(np.diff(p) > -0.05)
 
 
+def test_lmm_and_glm_under_scenarios_match_oracle():
+    """Robustness scenarios on the mixed-model and GLM arms: the per-study designs come from scen_design_kernel and the
+    quad generators read them (correlated predictors + doomer noise → the Jacobi PSD repair runs for most studies)."""
+    m = S.lmm_spec(12, 0.2)
+    m["correlation"] = [1.0, 0.5, 0.5, 1.0]
+    m["scenario"] = dict(S.scenario("doomer"), sampled_factor_proportions=False)
+    got = M.run_batch(m, [48, 96, 240], 384, SEED, mode=ALL)
+    want = orc.run_batch(m, [48, 96, 240], 384, SEED, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert got.gpu_launches == 3  # designs, generate, fit
+    g = S.logit_spec()
+    g["correlation"] = [1, 0.4, 0.2, 0.4, 1, 0.3, 0.2, 0.3, 1]
+    g["scenario"] = S.scenario("doomer")
+    got = M.run_batch(g, [80, 200, 500], 384, SEED + 1, mode=ALL)
+    want = orc.run_batch(g, [80, 200, 500], 384, SEED + 1, n_threads=orc.host_threads(), capture=True)
+    assert_batch_equal(got, want)
+    assert got.gpu_launches == 3
+
+
 def test_lmm_fixed_size_unbalanced_prefixes_match_oracle():
     """FixedSize sizing with sample sizes that are not multiples of the cluster size: two cluster-size groups."""
     s = S.lmm_spec(10, 0.3)
