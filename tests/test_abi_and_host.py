@@ -114,6 +114,23 @@ def test_contract_runners_report_lowering_errors_without_a_gpu():
         M.find_sample_size_contracts([], 20, 100, 16)
 
 
+def test_no_kernel_is_instantiated_in_two_translation_units():
+    """Every translation unit carries its own __constant__ plan; a template kernel instantiated with the same arguments in two
+    of them is merged by the linker, and a launch may then run the other module's copy against ITS (stale) plan.  So each
+    kernel symbol must live in exactly one cubin of the library."""
+    import shutil
+    import subprocess
+    from collections import Counter
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(tool).exists():
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", str(ROOT / "mcpower_b200" / "libmcpower_b200.so")], capture_output=True, text=True).stdout
+    names = [ln.split("Function", 1)[1].strip().rstrip(":") for ln in out.splitlines() if ln.lstrip().startswith("Function ")]
+    assert len(names) > 100, "cuobjdump listed no kernels"
+    dupes = [n for n, c in Counter(names).items() if c > 1]
+    assert not dupes, dupes[:5]
+
+
 def test_no_cpu_fallback():
     """Without a device the product must fail loudly, never compute on the host."""
     if M.device_count() > 0:
