@@ -18,6 +18,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "kernels_q4.cuh"
+#include <type_traits>
 
 namespace mcp {
 
@@ -54,17 +55,37 @@ __device__ __forceinline__ void glm_row(int family, double eta, double y, double
     }
 }
 
-// Logit row, branch-free (selects only): the same arithmetic as glm_row(family 0), so that two rows evaluated back to back
-// interleave their exp / division / log chains.
-__device__ __forceinline__ void glm_row_logit_sel(double eta, double y, double& w, double& z, double& dev) {
-    const double e = own_exp_sel(-fabs(eta));
-    const double inv = 1.0 / (1.0 + e);
-    const double mu = eta >= 0.0 ? inv : e * inv;
-    double ww = mu * (1.0 - mu);
-    ww = ww < MCP_GLM_WCLAMP ? MCP_GLM_WCLAMP : ww;
-    w = ww;
-    z = eta + (y - mu) / ww;
-    dev = -2.0 * own_log_sel(y > 0.5 ? mu : 1.0 - mu);
+// One IRLS row, branch-free (selects only), per family: the same arithmetic as glm_row, so that two rows evaluated back to
+// back form one basic block and their exp / division / log chains interleave.
+template <int FAM>
+__device__ __forceinline__ void glm_row_sel(double eta, double y, double& w, double& z, double& dev) {
+    if (FAM == 0) {
+        const double e = own_exp_sel(-fabs(eta));
+        const double inv = 1.0 / (1.0 + e);
+        const double mu = eta >= 0.0 ? inv : e * inv;
+        double ww = mu * (1.0 - mu);
+        ww = ww < MCP_GLM_WCLAMP ? MCP_GLM_WCLAMP : ww;
+        w = ww;
+        z = eta + (y - mu) / ww;
+        dev = -2.0 * own_log_sel(y > 0.5 ? mu : 1.0 - mu);
+    } else if (FAM == 1) {
+        const double mu = phi_sel(eta);
+        double d = own_exp_sel(-0.5 * eta * eta) * 0.3989422804014327;
+        d = d < 1e-300 ? 1e-300 : d;
+        double v = mu * (1.0 - mu);
+        v = v < MCP_GLM_WCLAMP ? MCP_GLM_WCLAMP : v;
+        w = d * d / v;
+        z = eta + (y - mu) / d;
+        dev = -2.0 * own_log_sel(y > 0.5 ? mu : 1.0 - mu);
+    } else {
+        const double mu = own_exp_sel(eta);
+        double ww = mu;
+        ww = ww < MCP_GLM_WCLAMP ? MCP_GLM_WCLAMP : ww;
+        w = ww;
+        z = eta + (y - mu) / ww;
+        const double dpos = 2.0 * (y * own_log_sel(y / mu) - (y - mu));  // selected away for y == 0 (log 0 → −inf, no trap)
+        dev = y > 0.0 ? dpos : 2.0 * mu;
+    }
 }
 
 struct GlmOut {
@@ -101,10 +122,12 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
 #pragma unroll
         for (int i = 0; i < PT; i++) b[i] = 0.0;
         dev = 0.0;
-        if (family == 0) {
-            // logit: two rows per iteration.  Every accumulator still sees the rows in order (row i, then row i + 1), so the
-            // sums are bit-identical to the one-row loop; the two rows' exp / division / log chains are independent and
-            // interleave.  Rows i + 2 / i + 3 are fetched (coalesced, L2 / HBM) while rows i / i + 1 are processed.
+        // Two rows per iteration.  Every accumulator still sees the rows in order (row i, then row i + 1), so the sums are
+        // bit-identical to a one-row loop; the two rows' exp / division / log chains are independent and interleave.  Rows
+        // i + 2 / i + 3 are fetched (coalesced, L2 / HBM) while rows i / i + 1 are processed.  The family is uniform over the
+        // launch: one of the three instantiations runs.
+        auto pass = [&](auto fam_tag) {
+            constexpr int FAM = decltype(fam_tag)::value;
             float nx0[PT], nx1[PT];
 #pragma unroll
             for (int j = 0; j < PT; j++) {
@@ -145,13 +168,15 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
                     eta1 = fma(x1[j], beta[j], eta1);
                 }
                 double w0, z0, d0, w1, z1, d1;
-                glm_row_logit_sel(eta0, y0, w0, z0, d0);
-                glm_row_logit_sel(eta1, y1, w1, z1, d1);
+                glm_row_sel<FAM>(eta0, y0, w0, z0, d0);
+                glm_row_sel<FAM>(eta1, y1, w1, z1, d1);
                 dev += d0;
                 dev += d1;
                 if (it == 0) {
                     s0 += y0;
+                    if (FAM == 2 && y0 > 1.0) s1 += y0 * own_log(y0);
                     s0 += y1;
+                    if (FAM == 2 && y1 > 1.0) s1 += y1 * own_log(y1);
                 }
 #pragma unroll
                 for (int a = 0; a < PT; a++) {
@@ -178,9 +203,12 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
 #pragma unroll
                 for (int j = 0; j < PT; j++) eta0 = fma(x0[j], beta[j], eta0);
                 double w0, z0, d0;
-                glm_row_logit_sel(eta0, y0, w0, z0, d0);
+                glm_row_sel<FAM>(eta0, y0, w0, z0, d0);
                 dev += d0;
-                if (it == 0) s0 += y0;
+                if (it == 0) {
+                    s0 += y0;
+                    if (FAM == 2 && y0 > 1.0) s1 += y0 * own_log(y0);
+                }
 #pragma unroll
                 for (int a = 0; a < PT; a++) {
                     const double wa = w0 * x0[a];
@@ -189,44 +217,10 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
                     b[a] = fma(wa, z0, b[a]);
                 }
             }
-        } else {
-        // software pipeline: row i + 1 is fetched (coalesced, L2/HBM) while row i's ~300 instructions run
-        float nxt[PT];
-#pragma unroll
-        for (int j = 0; j < PT; j++) nxt[j] = n > 0 ? plane[(size_t)j * stride] : 0.0f;
-        for (int i = 0; i < n; i++) {
-            float cur[PT];
-#pragma unroll
-            for (int j = 0; j < PT; j++) cur[j] = nxt[j];
-            if (i + 1 < n) {
-                const float* rowp = plane + (size_t)(i + 1) * PT * stride;
-#pragma unroll
-                for (int j = 0; j < PT; j++) nxt[j] = rowp[(size_t)j * stride];
-            }
-            double xr[PT];
-            xr[0] = 1.0;
-#pragma unroll
-            for (int j = 1; j < PT; j++) xr[j] = (double)cur[j - 1];
-            const double yi = (double)cur[PT - 1];
-            double eta = 0.0;
-#pragma unroll
-            for (int j = 0; j < PT; j++) eta = fma(xr[j], beta[j], eta);
-            double w, z, di;
-            glm_row(family, eta, yi, w, z, di);
-            dev += di;
-            if (it == 0) {
-                s0 += yi;
-                if (family == 2 && yi > 1.0) s1 += yi * own_log(yi);
-            }
-#pragma unroll
-            for (int a = 0; a < PT; a++) {
-                const double wa = w * xr[a];
-#pragma unroll
-                for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, xr[c], A[tri(a, c)]);
-                b[a] = fma(wa, z, b[a]);
-            }
-        }
-        }
+        };
+        if (family == 0) pass(std::integral_constant<int, 0>{});
+        else if (family == 1) pass(std::integral_constant<int, 1>{});
+        else pass(std::integral_constant<int, 2>{});
         if (isinf(dev) || dev != dev) {
             active = false;
             break;
