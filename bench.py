@@ -35,7 +35,6 @@ sys.path.insert(0, str(ROOT))
 N_ROWS = 500
 SIMS_PER_STEP = 1 << 22          # per GPU per step
 FLOP64_PER_FIT = 6.6e4           # 3.3e4 DFMA at n=500, P=9 (identity mix skipped: structural zeros)
-DRAM_BYTES_PER_FIT = 390.0       # ncu dram__bytes_read+write of ols_lean_kernel / studies (profiles/r01c_ncu_summary.md)
 USER_SEED = 2137                 # configs/config.json default seed; base_seed = splitmix64(seed) (find_power.rs:259)
 
 
@@ -174,11 +173,31 @@ def main():
     seed = M.splitmix64(USER_SEED)
     per = args.sims_per_step
     launches = 0
+    E_STATS = 9 * 10 // 2 + 9 + 1  # doubles of sufficient statistics per fit at P = 9 (X'X packed | X'y | y'y)
 
-    def step(i, mode=M.MODE_COUNTS):
+    def step(i, mode=M.MODE_COUNTS, sink=None):
         # global sim ids: step-major, rank-minor — the union over ranks is one contiguous id range
         begin = (i * world + rank) * per
-        return M.run_batch(spec, [N_ROWS], per, seed, mode=mode, device=local_rank, sim_begin=begin)
+        return M.run_batch(spec, [N_ROWS], per, seed, sink, mode=mode, device=local_rank, sim_begin=begin)
+
+    def reduce_counters(r):
+        """The path's only collective: one all-reduce of the integer counters per (sample size, test)."""
+        if dist is None:
+            return r.counters
+        c = torch.from_numpy(r.counters.astype(np.int64)).cuda()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return c.cpu().numpy()
+
+    def timed(n_steps, first, **kw):
+        """Wall clock over n_steps public-API calls (host spec in, host result out, counters all-reduced), barrier on both sides."""
+        barrier()
+        t = time.perf_counter()
+        last = None
+        for i in range(n_steps):
+            last = step(first + i, **kw)
+            reduce_counters(last)
+        barrier()
+        return time.perf_counter() - t, last
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -189,28 +208,40 @@ def main():
     t_begin = time.time()
     t0 = time.perf_counter()
     dev_ms, total_counters = 0.0, None
+    h2d = d2h = 0
     for i in range(args.steps):
         r = step(args.warmup + i)
         dev_ms += r.kernel_ms
         launches += r.gpu_launches
+        h2d, d2h = r.h2d_bytes, r.d2h_bytes
         total_counters = r.counters.copy() if total_counters is None else total_counters + r.counters
     barrier()
     wall = time.perf_counter() - t0
-    # ---- timed region 2: end-to-end through the public API (host buffers in, host counters out)
-    barrier()
-    t1 = time.perf_counter()
-    for i in range(args.steps):
-        r = step(args.warmup + args.steps + i)
-    barrier()
-    e2e_wall = time.perf_counter() - t1
-    clocks = sampler.stop(t_begin, time.time())  # both timed regions (device-timed steps, then the e2e steps)
+    # ---- timed region 2: end-to-end through the public API (host buffers in, host counters out, the all-reduce inside)
+    base = args.warmup + args.steps
+    e2e_wall, r_e2e = timed(args.steps, base)
+    # ---- the reference's real host path: a ProgressSink is always attached (engine-py/src/lib.rs:57-71) ...
+    n_reports = [0]
 
-    t = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
+    def sink(cur, tot):
+        n_reports[0] += 1
+        return True
+
+    step(base + args.steps, sink=sink)
+    n_reports[0] = 0
+    prog_wall, r_prog = timed(args.steps, base + args.steps + 1, sink=sink)
+    reports_per_call = n_reports[0] / max(args.steps, 1)
+    # ---- ... and the orchestrator folds the sim-major byte tensors (BYTES | COUNTS, sink attached)
+    step(base + 2 * args.steps + 1, mode=M.MODE_COUNTS | M.MODE_BYTES, sink=sink)
+    bytes_wall, r_bytes = timed(args.steps, base + 2 * args.steps + 2, mode=M.MODE_COUNTS | M.MODE_BYTES, sink=sink)
+    clocks = sampler.stop(t_begin, time.time())  # every timed region
+
+    t = torch.tensor([dev_ms, wall, e2e_wall, prog_wall, bytes_wall], dtype=torch.float64, device="cuda")
     cnt = torch.from_numpy(total_counters.astype(np.int64)).cuda()
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)   # the path's only collective: integer counters per cell
-    dev_ms, wall, e2e_wall = (float(v) for v in t.tolist())
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall, e2e_wall, prog_wall, bytes_wall = (float(v) for v in t.tolist())
     counters = cnt.cpu().numpy()
     total_fits = per * args.steps * world
     value = total_fits / (dev_ms * 1e-3)
@@ -218,33 +249,50 @@ def main():
 
     if rank == 0:
         power = counters[0, :2] / total_fits
-        plan_bytes = 20_000  # DevicePlan (~13 KB) + sample sizes + variant/threshold tables, per run_batch call
-        d2h = int(r.counters.nbytes)
         dfma = M.pipe_bench(0, local_rank)
         peak_tf = 2.0 * dfma / 1e12
         ach_tf = (value / world) * FLOP64_PER_FIT / 1e12
         # The path is bound by instruction issue / datapath cycles, not by HBM (generated data never leaves the SM) and
         # not by tensor cores: the headline roofline is the issue roofline,
         # ALGORITHMIC warp-instructions per fit (2.6e5 thread-instructions) x fits/s against one issue per
-        # scheduler per clock at the SM clock sampled during the timed region.
+        # scheduler per clock at the SM clock sampled during the timed region.  frac_essential uses the instruction count
+        # derived in DESIGN.md section 3.3 (Philox + packed Horner + DFMA + widening + tails: what no implementation of
+        # this arithmetic can avoid) instead of SURVEY's estimate, which is close to what the kernel executes.
         prof = json.loads((ROOT / "profiles" / "inst_per_fit.json").read_text())
         sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         peak_issue = 148 * 4 * sm_clock_hz
         ach_issue = (value / world) * prof["algorithmic_thread_inst_per_fit"] / 32.0
+        ess_issue = (value / world) * prof["essential_thread_inst_per_fit"] / 32.0
         line = {"metric": "ols_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": plan_bytes, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_wall / args.steps},
+                "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": int(r_e2e.h2d_bytes),
+                        "d2h_bytes_per_step": int(r_e2e.d2h_bytes), "ms_per_step": 1e3 * e2e_wall / args.steps,
+                        "note": "public API, host spec in / host counters out, the counter all-reduce inside the timed region; "
+                                "byte counts are what the library copied (plan + tables up, counters down)"},
+                "e2e_progress": {"value": total_fits / prog_wall, "unit": "fits/s", "ms_per_step": 1e3 * prog_wall / args.steps,
+                                 "reports_per_call": reports_per_call, "gpu_launches_per_call": int(r_prog.gpu_launches),
+                                 "waves_per_call": int(r_prog.n_waves),
+                                 "note": "the same with a ProgressSink attached (the reference's hosts always pass one): progress "
+                                         "comes from a device counter published to mapped host memory, the batch is not split"},
+                "e2e_bytes": {"value": total_fits / bytes_wall, "unit": "fits/s", "ms_per_step": 1e3 * bytes_wall / args.steps,
+                              "h2d_bytes_per_step": int(r_bytes.h2d_bytes), "d2h_bytes_per_step": int(r_bytes.d2h_bytes),
+                              "waves_per_call": int(r_bytes.n_waves),
+                              "note": "BYTES | COUNTS with the sink attached: the sim-major BatchResult tensors land in page-locked "
+                                      "host memory, each wave's copy overlapping the next wave's kernels"},
+                "host_ms_per_call": {"lower": r_e2e.lower_ms, "enqueue": r_e2e.enqueue_ms, "wait": r_e2e.wait_ms},
                 "gpu_launches": launches,
                 "roofline": {"bound": "issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9, "unit": "Gwarp-inst/s",
-                             "frac": ach_issue / peak_issue,
-                             "traffic": DRAM_BYTES_PER_FIT * per,
+                             "frac": ach_issue / peak_issue, "frac_essential": ess_issue / peak_issue,
+                             "frac_executed": (value / world) * prof["warp_inst_per_fit"] / peak_issue,
+                             "traffic": float(E_STATS * 8 * per),
                              "note": "per GPU, dominant kernel ols_lean_kernel (98 % of the step); achieved = algorithmic "
-                                     "2.6e5 thread-instructions per fit (SURVEY 8d) / 32 x fits/s; peak = 148 SMs x 4 schedulers x "
-                                     "SM clock; executed instructions per fit and ncu issue utilisation in profiles/r01c_ncu_summary.md; "
-                                     "traffic = ncu dram bytes (the 448 B of sufficient statistics per fit) x fits per launch",
+                                     "2.6e5 thread-instructions per fit (SURVEY 8d) / 32 x fits/s; frac_essential = the irreducible "
+                                     "instruction count of DESIGN.md 3.3 (" + str(int(prof["essential_thread_inst_per_fit"])) +
+                                     " thread-instructions per fit); frac_executed = what ncu counted at HEAD (" + prof["source"] +
+                                     "); peak = 148 SMs x 4 schedulers x SM clock; traffic = the statistics hand-off the kernel "
+                                     "writes, E x 8 B x fits per launch (E = 55 entries at P = 9), computed from the plan",
                              "executed_warp_inst_per_fit": prof["warp_inst_per_fit"]},
                 "roofline_fp64": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                                   "frac": ach_tf / peak_tf,
@@ -252,16 +300,39 @@ def main():
                                           "(mcp_pipe_bench kind 0); MEASURED_PEAKS.json has no FP64 entry"},
                 "power_x1_x2": [float(p) for p in power],
                 "wall_ms_per_step": 1e3 * wall / args.steps}
+        if world == 1 and M.device_count() > 1 and not args.no_secondary:
+            # the same batch sharded over every visible GPU INSIDE one library call (McpOptions.n_devices): strong scaling of
+            # one run_batch, counters summed by the library
+            nd = M.device_count()
+            M.run_batch(spec, [N_ROWS], per, seed, device=0, n_devices=nd)
+            tt = time.perf_counter()
+            rm = M.run_batch(spec, [N_ROWS], per * nd, seed, device=0, n_devices=nd)
+            tw = time.perf_counter() - tt
+            line["in_library_multi_gpu"] = {"n_devices": nd, "sims": per * nd, "value": per * nd / (rm.kernel_ms * 1e-3),
+                                            "e2e": per * nd / tw, "lower_ms": rm.lower_ms, "enqueue_ms": rm.enqueue_ms,
+                                            "wait_ms": rm.wait_ms}
         if not args.no_secondary:
             # second headline: BASELINE configs[1] — sample-size sweep 20..1000 step 20, 8 correlated
-            # predictors + 3-level factor, Bonferroni; fits/s = n_sims x n_ss / device time
+            # predictors + 3-level factor, Bonferroni, at the BASELINE size of 1e6 sims per cell; fits/s = n_sims x n_ss / time
             sweep = S.sweep_spec()
             grid = list(range(20, 1001, 20))
+            n2 = 1_000_000
             M.run_batch(sweep, grid, 4096, seed, device=local_rank)
-            rs = M.run_batch(sweep, grid, 1 << 18, seed, device=local_rank)
-            line["secondary"] = {"workload": "c2_sweep_p11_grid50_bonferroni", "n_sims": 1 << 18, "n_sample_sizes": len(grid),
-                                 "fits_per_s": (1 << 18) * len(grid) / (rs.kernel_ms * 1e-3),
-                                 "sims_per_s": (1 << 18) / (rs.kernel_ms * 1e-3), "n_gpus": 1}
+            rs = M.run_batch(sweep, grid, n2, seed, device=local_rank)
+            tt = time.perf_counter()
+            rs = M.run_batch(sweep, grid, n2, seed, sink, device=local_rank)
+            c2_wall = time.perf_counter() - tt
+            M.run_batch(sweep, grid, n2, seed, sink, mode=M.MODE_COUNTS | M.MODE_BYTES, device=local_rank)  # pins the result pool
+            tt = time.perf_counter()
+            rb = M.run_batch(sweep, grid, n2, seed, sink, mode=M.MODE_COUNTS | M.MODE_BYTES, device=local_rank)
+            c2_bytes_wall = time.perf_counter() - tt
+            line["secondary"] = {"workload": "c2_sweep_p11_grid50_bonferroni", "n_sims": n2, "n_sample_sizes": len(grid),
+                                 "fits_per_s": n2 * len(grid) / (rs.kernel_ms * 1e-3),
+                                 "sims_per_s": n2 / (rs.kernel_ms * 1e-3), "n_gpus": 1,
+                                 "e2e_progress_fits_per_s": n2 * len(grid) / c2_wall, "e2e_progress_ms": 1e3 * c2_wall,
+                                 "e2e_bytes_fits_per_s": n2 * len(grid) / c2_bytes_wall, "e2e_bytes_ms": 1e3 * c2_bytes_wall,
+                                 "bytes_d2h": int(rb.d2h_bytes), "bytes_waves": int(rb.n_waves), "kernel_ms": rs.kernel_ms,
+                                 "lower_ms": rs.lower_ms}
             # the other BASELINE configs (device time, one GPU): robustness scenario sweep, logistic GLM power curve,
             # random-intercept mixed model — the split path's kernels
             doomer = dict(sweep, scenario=S.scenario("doomer"), crit_values={"alpha": 5e-7, "posthoc_alpha": None})

@@ -38,16 +38,25 @@ enum {
  * batch.rs:175-197, extended to every sample-size index). */
 enum { MCP_MODE_COUNTS = 1, MCP_MODE_BYTES = 2, MCP_MODE_CAPTURE = 4 };
 
-typedef struct McpOptions {
-    int32_t device;      /* CUDA ordinal; -1 = current device */
-    uint32_t mode;       /* MCP_MODE_*; 0 = COUNTS */
-    uint64_t sim_begin;  /* first GLOBAL sim id of this shard (multi-GPU: same base_seed, disjoint id ranges) */
-    uint32_t wave_sims;  /* sims per kernel launch; 0 = auto. Progress/cancel are polled between waves */
-    uint32_t reserved;
-} McpOptions;
-
-/* ProgressSink (spec.rs:38-52): report(current, total) ~50×/run; return 0 to request cancellation. */
+/* ProgressSink (spec.rs:38-52): report(current, total) ~50x per run, called on the thread that made the library call, while
+ * the kernels run (the batch is NOT cut into small launches for it: the kernels publish their progress through a mapped
+ * host word the waiting thread polls); return 0 to request cancellation.  is_cancelled: the trait's cheap poll, asked every
+ * ~100 us by the same waiting thread; return nonzero to cancel.  On cancellation CTAs that have not started exit at once,
+ * the partial result is discarded and the call returns MCP_STATUS_CANCELLED (batch.rs:128-129).  Neither callback may call
+ * back into the library for a device the call is using (the per-device lock is held). */
 typedef int (*McpProgressFn)(uint64_t current, uint64_t total, void* user);
+typedef int (*McpCancelFn)(void* user);
+
+typedef struct McpOptions {
+    int32_t device;      /* first CUDA ordinal; -1 = the calling thread's current device */
+    uint32_t mode;       /* MCP_MODE_*; 0 = COUNTS */
+    uint64_t sim_begin;  /* first GLOBAL sim id of this call (same base_seed, disjoint id ranges = one bigger batch) */
+    uint32_t wave_sims;  /* sims per kernel launch; 0 = auto (as many as the scratch arena allows) */
+    int32_t n_devices;   /* 0 or 1: one device; N > 1: the call shards its sims over ordinals device .. device+N-1 (contiguous
+                            global sim-id ranges, same base_seed: every output bit equals the one-device result; counters are
+                            summed, byte tensors land in sim order); -1: every visible device from `device` on */
+    McpCancelFn is_cancelled; /* may be NULL */
+} McpOptions;
 
 /* Counter row layout per sample-size index (width = 4T + 7 + 2F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
  *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
@@ -76,6 +85,13 @@ typedef struct McpBatchResult {
     uint32_t reserved;
     uint8_t* posthoc_unc;     /* [n_sims][n_ss][C] or NULL (BatchResult::posthoc_unc, spec.rs:557-559) */
     uint8_t* posthoc_cor;     /* [n_sims][n_ss][C] or NULL */
+    uint64_t h2d_bytes;       /* bytes this call copied host -> device (plan + tables, every device) */
+    uint64_t d2h_bytes;       /* bytes this call copied device -> host (counters, byte tensors, capture) */
+    uint32_t n_devices;       /* devices that ran a shard of the call */
+    uint32_t n_waves;         /* kernel waves over all devices (1 per device unless the scratch arena or BYTES pipelining split it) */
+    double lower_ms;          /* host: validation + lowering (critical-value tables, exact factor walks) */
+    double enqueue_ms;        /* host: result allocation + enqueueing every device's uploads, launches and copies */
+    double wait_ms;           /* host: from the last enqueue until every device finished (kernels + copies) */
 } McpBatchResult;
 
 /* run_batch twin. spec_json = serde JSON of SimulationSpec (same field names / enum spellings). */
@@ -161,6 +177,11 @@ uint64_t mcp_splitmix64(uint64_t z);
  * kind 0 = DFMA, 1 = FMUL+FADD pair (counts 2 ops), 2 = Philox round mix (2 IMAD.WIDE + 2 LOP3 → counts 4 ops),
  * 3 = F2F.F64.F32 + DADD (counts 2 ops), 4 = DADD. */
 int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s);
+
+/* Test hook (not part of the reference seam): pin the OLS power kernel — 1 one thread per study, 4 lane quad solving by
+ * call, 5 lean generate+accumulate / solve pair, 6 general split pair; 0 = the library's own choice.  Every variant computes
+ * the same bits; the parity tests run each OLS case under all of them.  Process-wide; returns the previous setting. */
+int mcp_test_force_ols_variant(int variant);
 
 int mcp_device_count(void);
 const char* mcp_last_error(void);

@@ -4,11 +4,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mcpower_b200.h"
@@ -23,7 +28,7 @@
 namespace mcp {
 
 static thread_local std::string g_last_error;
-static std::mutex g_plan_mutex;  // c_plan is one __constant__ symbol per device → one batch at a time per process
+static std::atomic<int> g_force_ols_variant{0};  // test hook (mcp_test_force_ols_variant): 0 = the product's own choice
 
 #define CUDA_CHECK(expr)                                                                                      \
     do {                                                                                                      \
@@ -32,85 +37,198 @@ static std::mutex g_plan_mutex;  // c_plan is one __constant__ symbol per device
             throw EngineError(MCP_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
     } while (0)
 
-// Small-buffer cache: cudaMalloc/cudaFree cost ~0.1-1 ms each and cudaFree synchronises the device, which
-// would dominate a millisecond-scale run_batch call.  Buffers up to 4 MiB are recycled per (device, size class).
-struct BufferCache {
-    struct Slot { int dev; size_t bytes; void* p; };
-    std::vector<Slot> free_list;
+// ---- pinned host memory for everything the device writes back ------------------------------------------------------
+// A device→host copy into pageable memory is synchronous and staged through the driver's bounce buffers (~10 GB/s); the
+// BatchResult byte tensors of a large call are gigabytes.  Result buffers therefore come from a process-wide pool of
+// page-locked, portable blocks (cudaHostAlloc costs ~0.3 ms per MiB the first time, nothing when a freed block is reused);
+// mcp_free_result hands them back.  At most kKeepBytes stay cached.
+struct PinnedPool {
+    struct Blk { void* p; size_t bytes; };
     std::mutex mu;
-    void* take(int dev, size_t bytes) {
-        std::lock_guard<std::mutex> g(mu);
-        for (size_t i = 0; i < free_list.size(); i++)
-            if (free_list[i].dev == dev && free_list[i].bytes == bytes) {
-                void* p = free_list[i].p;
-                free_list.erase(free_list.begin() + (long)i);
-                return p;
-            }
-        return nullptr;
-    }
-    void give(int dev, size_t bytes, void* p) {
-        std::lock_guard<std::mutex> g(mu);
-        free_list.push_back({dev, bytes, p});
-    }
-};
-static BufferCache g_cache;
-
-// Wave scratch (GLM data plane, LMM cluster sums, lean-path sufficient statistics): gigabytes per call, so one
-// grow-only arena per device is kept across calls (cudaMalloc/cudaFree of a 2 GB buffer costs milliseconds and
-// synchronises the device).  Batches are serialised by g_plan_mutex, so one arena per device is enough.
-struct ScratchArena {
-    void* p[64] = {};
-    size_t bytes[64] = {};
-    void* get(size_t need) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64) throw EngineError(MCP_CUDA_ERROR, "device index out of range");
-        if (bytes[dev] < need) {
-            if (p[dev]) cudaFree(p[dev]);
-            p[dev] = nullptr;
-            bytes[dev] = 0;
-            CUDA_CHECK(cudaMalloc(&p[dev], need));
-            bytes[dev] = need;
-        }
-        return p[dev];
-    }
-};
-static ScratchArena g_scratch;
-
-struct DeviceBuffers {
-    struct Owned { void* p; size_t bytes; int dev; };
-    std::vector<Owned> owned;
-    template <typename T>
-    T* alloc(size_t n) {
-        size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const bool pooled = bytes <= (4u << 20);
-        if (pooled) {
-            size_t cls = 256;
-            while (cls < bytes) cls <<= 1;
-            bytes = cls;
-            if (void* p = g_cache.take(dev, bytes)) {
-                owned.push_back({p, bytes, dev});
-                return static_cast<T*>(p);
+    std::vector<Blk> idle;
+    std::map<void*, size_t> live;
+    size_t cached = 0;
+    static constexpr size_t kKeepBytes = (size_t)8 << 30, kGrain = (size_t)64 << 10;
+    void* take(size_t need) {
+        const size_t bytes = ((std::max<size_t>(need, 1) + kGrain - 1) / kGrain) * kGrain;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = idle.size();
+            for (size_t i = 0; i < idle.size(); i++)
+                if (idle[i].bytes >= bytes && idle[i].bytes <= 2 * bytes && (best == idle.size() || idle[i].bytes < idle[best].bytes)) best = i;
+            if (best != idle.size()) {
+                Blk b = idle[best];
+                idle.erase(idle.begin() + (long)best);
+                cached -= b.bytes;
+                live[b.p] = b.bytes;
+                return b.p;
             }
         }
         void* p = nullptr;
-        CUDA_CHECK(cudaMalloc(&p, bytes));
-        owned.push_back({p, pooled ? bytes : 0, dev});
-        return static_cast<T*>(p);
-    }
-    template <typename T>
-    T* upload(const std::vector<T>& v) {
-        T* p = alloc<T>(v.size());
-        if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) {  // out of lockable memory: drop the cache and retry once
+            trim(0);
+            cudaGetLastError();
+            e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        }
+        if (e != cudaSuccess) throw EngineError(MCP_CUDA_ERROR, std::string("CUDA error: ") + cudaGetErrorString(e) + " at cudaHostAlloc(result buffer)");
+        std::lock_guard<std::mutex> g(mu);
+        live[p] = bytes;
         return p;
     }
-    ~DeviceBuffers() {
-        for (auto& o : owned) {
-            if (o.bytes) g_cache.give(o.dev, o.bytes, o.p);
-            else cudaFree(o.p);
+    bool give(void* p) {  // false: not one of ours (plain malloc)
+        Blk b{p, 0};
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = live.find(p);
+            if (it == live.end()) return false;
+            b.bytes = it->second;
+            live.erase(it);
+            if (cached + b.bytes <= kKeepBytes) {
+                idle.push_back(b);
+                cached += b.bytes;
+                return true;
+            }
         }
+        cudaFreeHost(p);
+        return true;
+    }
+    void trim(size_t keep) {
+        std::vector<Blk> drop;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            while (cached > keep && !idle.empty()) {
+                drop.push_back(idle.back());
+                cached -= idle.back().bytes;
+                idle.pop_back();
+            }
+        }
+        for (auto& b : drop) cudaFreeHost(b.p);
+    }
+};
+static PinnedPool g_pinned;
+
+// ---- one context per CUDA device ------------------------------------------------------------------------------------
+// c_plan is a __constant__ symbol, i.e. one copy per device: batches on the same device are serialised by the context's
+// mutex, batches on different devices run concurrently (also from one call: n_devices > 1).  The context owns two
+// non-blocking streams (kernels; device→host copies of finished waves), a control stream for the cancel flag, grow-only
+// device arenas (cudaMalloc / cudaFree of gigabytes cost milliseconds and synchronise the device) and a small page-locked
+// mailbox: progress word written by the kernels, staging for the counters.
+struct Arena {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void* get(size_t need) {
+        if (bytes < need) {
+            if (p) cudaFree(p);
+            p = nullptr;
+            bytes = 0;
+            CUDA_CHECK(cudaMalloc(&p, need));
+            bytes = need;
+        }
+        return p;
+    }
+};
+
+struct Mailbox {
+    volatile unsigned int progress;  // written by the kernels (mapped), read by the polling host thread
+    int one;                         // source of the cancel-flag copy
+    int error_flag;                  // device error flag, copied back with the counters
+    int pad;
+};
+
+struct DeviceCtx {
+    int dev = -1;
+    std::mutex mu;
+    cudaStream_t compute = nullptr, copy = nullptr, ctl = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, done_compute = nullptr, done_copy = nullptr;
+    std::vector<cudaEvent_t> wave_events;
+    Arena scratch, tables, outputs, small, between;
+    Mailbox* mail = nullptr;            // page-locked, mapped
+    unsigned long long* h_counters = nullptr;  // page-locked staging, grow-only
+    size_t h_counters_cap = 0;
+    unsigned int* d_prog = nullptr;     // device progress counter
+    int* d_cancel = nullptr;            // device cancel flag
+    int* d_error = nullptr;             // device error flag (2 = CorrelationNotPSD raised by a study)
+    cudaEvent_t wave_event(size_t i) {
+        while (wave_events.size() <= i) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            wave_events.push_back(e);
+        }
+        return wave_events[i];
+    }
+    unsigned long long* counters_staging(size_t n) {
+        if (h_counters_cap < n) {
+            if (h_counters) cudaFreeHost(h_counters);
+            h_counters = nullptr;
+            h_counters_cap = 0;
+            CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_counters), std::max<size_t>(n, 4096) * sizeof(unsigned long long), cudaHostAllocPortable));
+            h_counters_cap = std::max<size_t>(n, 4096);
+        }
+        return h_counters;
+    }
+};
+
+static std::mutex g_ctx_mu;
+static DeviceCtx* g_ctx[64] = {};
+
+static int device_count_checked() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        throw EngineError(MCP_CUDA_ERROR, "no CUDA device available — the CUDA backend has no CPU fallback");
+    return n;
+}
+
+// The context of device `dev` (−1: the calling thread's current device), created on first use.  Leaves `dev` current.
+static DeviceCtx& ctx_for(int dev) {
+    const int n = device_count_checked();
+    if (dev < 0) CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= n || dev >= 64) throw EngineError(MCP_CUDA_ERROR, "CUDA device ordinal " + std::to_string(dev) + " out of range (" + std::to_string(n) + " visible)");
+    CUDA_CHECK(cudaSetDevice(dev));
+    std::lock_guard<std::mutex> g(g_ctx_mu);
+    if (!g_ctx[dev]) {
+        std::unique_ptr<DeviceCtx> cx(new DeviceCtx);
+        cx->dev = dev;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&cx->compute, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&cx->copy, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&cx->ctl, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreate(&cx->e0));
+        CUDA_CHECK(cudaEventCreate(&cx->e1));
+        CUDA_CHECK(cudaEventCreateWithFlags(&cx->done_compute, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&cx->done_copy, cudaEventDisableTiming));
+        CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&cx->mail), sizeof(Mailbox), cudaHostAllocPortable | cudaHostAllocMapped));
+        std::memset(cx->mail, 0, sizeof(Mailbox));
+        cx->mail->one = 1;
+        void* d = nullptr;
+        CUDA_CHECK(cudaMalloc(&d, 256));
+        CUDA_CHECK(cudaMemset(d, 0, 256));
+        cx->d_prog = static_cast<unsigned int*>(d);
+        cx->d_cancel = reinterpret_cast<int*>(static_cast<char*>(d) + 64);
+        cx->d_error = reinterpret_cast<int*>(static_cast<char*>(d) + 128);
+        g_ctx[dev] = cx.release();
+    }
+    return *g_ctx[dev];
+}
+
+// Device pointer of the mapped progress word (UVA: identical to the host pointer on every 64-bit platform CUDA supports;
+// asked for anyway).
+static volatile unsigned int* mapped_progress_word(DeviceCtx& cx) {
+    void* d = nullptr;
+    CUDA_CHECK(cudaHostGetDevicePointer(&d, cx.mail, 0));
+    return &static_cast<Mailbox*>(d)->progress;
+}
+
+// Carves sub-buffers out of one arena block (256-byte aligned).
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+    static size_t pad(size_t n) { return (n + 255) & ~(size_t)255; }
+    template <typename T>
+    T* take(size_t n) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += pad(std::max<size_t>(n, 1) * sizeof(T));
+        return p;
     }
 };
 
@@ -323,10 +441,9 @@ static void check_supported(const Spec& s, bool generation_only = false) {
         if (!s.contrast_pairs.empty()) unsupported("contrast_pairs with estimator glm (the reference's GLM arm has no contrasts, batch.rs:2060-2062)");
         if (s.outcome == O_CONTINUOUS) invalid("estimator Glm requires a binary or count outcome");
     }
+    if (s.between_cols.size() > MCP_MAX_P) unsupported("between_var_indices > " + std::to_string(MCP_MAX_P));
     if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
     if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
-    if (s.has_between) unsupported("between_var_indices");
-    if (s.has_lme) unsupported("lme scenario knobs (random-effect distribution / ICC jitter)");
     if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
     for (int v : s.new_dists)
         if (v >= D_UPLOADED_FACTOR) unsupported("uploaded_* distributions in the scenario menu");
@@ -341,13 +458,45 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     if (comps > MCP_MAX_INTER_COMP) unsupported("interaction components > " + std::to_string(MCP_MAX_INTER_COMP));
 }
 
+// The lowered call, host side: the scalar part of the DevicePlan and ONE blob holding every device-side table (256-byte
+// aligned sections).  Built once per call — the critical-value rows can cost milliseconds (Tukey quantiles) — and bound to
+// each device the call drives with a single asynchronous upload.
 struct Lowered {
     DevicePlan plan;
-    DeviceBuffers bufs;
     int P = 0, T = 0, F = 0, n_ss = 0, cw = 0;
+    static constexpr size_t NPOS = ~(size_t)0;
+    std::vector<uint8_t> blob;
+    size_t o_ss = NPOS, o_variants = NPOS, o_unc = NPOS, o_corr = NPOS, o_ov = NPOS, o_joint = NPOS, o_phu = NPOS, o_phc = NPOS,
+           o_levels = NPOS, o_ec = NPOS, o_t3 = NPOS, o_un = NPOS, o_ud = NPOS;
+    template <typename T_>
+    size_t add(const std::vector<T_>& v) {
+        const size_t off = (blob.size() + 255) & ~(size_t)255;
+        blob.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T_));
+        if (!v.empty()) std::memcpy(blob.data() + off, v.data(), v.size() * sizeof(T_));
+        return off;
+    }
 };
 
-// SimulationSpec → DevicePlan (+ device-side tables).  Output pointers are filled by the caller.
+// Point the plan's table pointers at a device copy of the blob.
+static void bind_tables(const Lowered& lw, DevicePlan& pl, const void* dev_blob) {
+    const char* base = static_cast<const char*>(dev_blob);
+    auto at = [&](size_t off) -> const void* { return off == Lowered::NPOS ? nullptr : base + off; };
+    pl.ss = static_cast<const uint32_t*>(at(lw.o_ss));
+    pl.variants = static_cast<const McpVariant*>(at(lw.o_variants));
+    pl.crit_unc = static_cast<const double*>(at(lw.o_unc));
+    pl.crit_corr = static_cast<const double*>(at(lw.o_corr));
+    pl.crit_overall = static_cast<const double*>(at(lw.o_ov));
+    pl.crit_joint = static_cast<const double*>(at(lw.o_joint));
+    pl.crit_ph_unc = static_cast<const double*>(at(lw.o_phu));
+    pl.crit_ph_corr = static_cast<const double*>(at(lw.o_phc));
+    pl.levels = static_cast<const uint8_t*>(at(lw.o_levels));
+    pl.exact_counts = static_cast<const uint32_t*>(at(lw.o_ec));
+    pl.t3_table = static_cast<const double*>(at(lw.o_t3));
+    pl.upload_normal = static_cast<const double*>(at(lw.o_un));
+    pl.upload_data = static_cast<const double*>(at(lw.o_ud));
+}
+
+// SimulationSpec → DevicePlan scalars + the table blob (host only; no CUDA call).  Output pointers are filled by the caller.
 static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw, bool thresholds = true) {
     DevicePlan& pl = lw.plan;
     std::memset(&pl, 0, sizeof pl);
@@ -405,8 +554,8 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     for (int c = 0; c < MCP_MAX_K + MCP_MAX_FACTORS; c++) pl.frame_map[c] = -1;
     for (int c = 0; c < (int)s.frame_map.size(); c++) pl.frame_map[c < s.k ? c : MCP_MAX_K + (c - s.k)] = s.frame_map[c];
     for (int j = 0; j < s.k; j++) pl.var_param_bs[j] = j < (int)s.var_params.size() ? s.var_params[j] : 0.0;
-    pl.upload_normal = s.upload_normal.empty() ? nullptr : lw.bufs.upload(s.upload_normal);
-    pl.upload_data = s.upload_data.empty() || !pl.bootstrap ? nullptr : lw.bufs.upload(s.upload_data);
+    if (!s.upload_normal.empty()) lw.o_un = lw.add(s.upload_normal);
+    if (!s.upload_data.empty() && pl.bootstrap) lw.o_ud = lw.add(s.upload_data);
     if (pl.bootstrap) pl.exact_walk = 0;  // copied factor levels differ per study: per-study level counts, every exclusion mask
     int q = 0;
     for (size_t j = 0; j < s.interactions.size(); j++) {
@@ -434,6 +583,23 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     if (s.has_cluster) {
         const int sv = std::max(s.sizing_value, 1);
         pl.n_clusters = s.sizing_fixed_size ? pl.max_n / sv : sv;  // generation.rs n_clusters_at(max_n)
+    }
+    // scenario.lme: random-effect distribution through draw_residual (data_gen.rs:146-161, 1289-1320), per-study ICC jitter
+    pl.has_lme = s.has_lme;
+    pl.re_dist = s.has_lme ? s.re_dist : R_NORMAL;
+    pl.re_df = s.re_df;
+    pl.icc_noise_sd = s.icc_noise_sd;
+    {
+        const double df = s.re_df > 3.0 ? s.re_df : 3.0;
+        const long long dfi = std::max<long long>(std::llround(df), 1);
+        pl.re_words = pl.re_dist == R_HIGH_KURTOSIS ? (int)(1 + dfi) : ((pl.re_dist == R_RIGHT_SKEWED || pl.re_dist == R_LEFT_SKEWED) ? (int)dfi : 1);
+    }
+    // cluster-level predictors: only with a cluster (data_gen.rs:619-620).  A broadcast factor no longer follows the exact walk
+    // row by row, so its per-level counts are read off the statistics like a sampled factor's.
+    pl.n_between = s.has_cluster ? (int)s.between_cols.size() : 0;
+    for (int b = 0; b < pl.n_between; b++) {
+        pl.between_cols[b] = (int8_t)s.between_cols[b];
+        if (s.between_cols[b] >= 1 + s.k) pl.exact_walk = 0;
     }
     pl.optimistic = s.is_optimistic();
     // scenario knobs (spec.rs:117-176)
@@ -579,27 +745,36 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
             for (int c = 0; c < NPH; c++) c_phc[r * NPH + c] = hit->phc[c];
         }
     std::vector<uint32_t> ssv(ss, ss + n_ss);
-    pl.ss = lw.bufs.upload(ssv);
-    pl.variants = lw.bufs.upload(variants);
-    pl.crit_unc = lw.bufs.upload(c_unc);
-    pl.crit_corr = lw.bufs.upload(c_corr);
-    pl.crit_overall = lw.bufs.upload(c_ov);
-    pl.crit_joint = lw.bufs.upload(c_joint);
-    pl.crit_ph_unc = NPH > 0 ? lw.bufs.upload(c_phu) : nullptr;
-    pl.crit_ph_corr = NPH > 0 ? lw.bufs.upload(c_phc) : nullptr;
-    pl.levels = any_exact ? lw.bufs.upload(levels_flat) : nullptr;
-    pl.exact_counts = nullptr;
+    lw.o_ss = lw.add(ssv);
+    lw.o_variants = lw.add(variants);
+    lw.o_unc = lw.add(c_unc);
+    lw.o_corr = lw.add(c_corr);
+    lw.o_ov = lw.add(c_ov);
+    lw.o_joint = lw.add(c_joint);
+    if (NPH > 0) {
+        lw.o_phu = lw.add(c_phu);
+        lw.o_phc = lw.add(c_phc);
+    }
+    if (any_exact) lw.o_levels = lw.add(levels_flat);
     if (F > 0 && pl.exact_walk) {  // exact walks are sim-invariant: the per-level prefix counts at every grid point too
         std::vector<uint32_t> ec((size_t)n_ss * MCP_MAX_LEVELS, 0);
-        for (uint32_t g = 0; g < n_ss; g++)
-            for (int f = 0; f < F; f++)
-                for (uint32_t i = 0; i < ss[g]; i++) ec[(size_t)g * MCP_MAX_LEVELS + pl.f_off[f] + levels[f][i]]++;
-        pl.exact_counts = lw.bufs.upload(ec);
+        for (int f = 0; f < F; f++) {  // one pass over the walk per factor: running counts snapshotted at the grid points
+            std::vector<uint32_t> run(s.factor_n_levels[f], 0);
+            uint32_t g = 0;
+            for (uint32_t i = 0; i < ss[n_ss - 1]; i++) {
+                run[levels[f][i]]++;
+                while (g < n_ss && ss[g] == i + 1) {
+                    for (int l = 0; l < s.factor_n_levels[f]; l++) ec[(size_t)g * MCP_MAX_LEVELS + pl.f_off[f] + l] = run[l];
+                    g++;
+                }
+            }
+        }
+        lw.o_ec = lw.add(ec);
     }
     bool need_t3 = false;
     for (int v : s.var_types) need_t3 |= v == D_HIGH_KURTOSIS;
     for (int v : s.new_dists) need_t3 |= v == D_HIGH_KURTOSIS;  // a scenario swap can introduce the t(3) marginal
-    if (need_t3) pl.t3_table = lw.bufs.upload(crit::build_t3_table());
+    if (need_t3) lw.o_t3 = lw.add(crit::build_t3_table());
     pl.counter_width = mcp_counter_width(T, F, NPH);
     pl.off_hist_cor = 2 * T + 3 + (T + NPH);
     pl.off_fx = pl.off_hist_cor + (T + NPH) + 1;
@@ -614,21 +789,14 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
 }
 
 // ---- kernel dispatch: ask each kernel translation unit in turn (launch.h) -------------------------
-static void dispatch_power(const Lowered& lw, int kind, const KernelArgs& a) {
+static void dispatch_power(int P, int kind, const DevicePlan& plan, const KernelArgs& a) {
     cudaError_t err = cudaSuccess;
     bool handled = false;
-#define X(id) if (!handled) handled = tu##id##_launch_power(lw.P, kind, !lw.plan.optimistic, lw.plan, a, &err);
+#define X(id) if (!handled) handled = tu##id##_launch_power(P, kind, !plan.optimistic, plan, a, &err);
     MCP_TU_LIST(X)
 #undef X
-    if (!handled) unsupported("n_predictors = " + std::to_string(lw.P));
+    if (!handled) unsupported("n_predictors = " + std::to_string(P));
     CUDA_CHECK(err);
-}
-
-static void select_device(int device) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
-        throw EngineError(MCP_CUDA_ERROR, "no CUDA device available — the CUDA backend has no CPU fallback");
-    if (device >= 0) CUDA_CHECK(cudaSetDevice(device));
 }
 
 template <typename F>
@@ -645,6 +813,265 @@ static int guarded(F&& body) {
     }
 }
 
+// The devices one call drives (McpOptions.device / n_devices), ascending — also the lock order.
+static std::vector<int> resolve_devices(const McpOptions& opt) {
+    const int visible = device_count_checked();
+    int first = opt.device;
+    if (first < 0) CUDA_CHECK(cudaGetDevice(&first));
+    int n = opt.n_devices == 0 ? 1 : opt.n_devices;
+    if (n < 0) n = visible - first;
+    if (first >= visible || n < 1 || first + n > visible)
+        throw EngineError(MCP_CUDA_ERROR, "devices " + std::to_string(first) + ".." + std::to_string(first + n - 1) + " requested, " +
+                                              std::to_string(visible) + " visible");
+    std::vector<int> out(n);
+    for (int i = 0; i < n; i++) out[i] = first + i;
+    return out;
+}
+
+// One device's share of a call: a contiguous range of the call's sims.
+struct Shard {
+    DeviceCtx* cx = nullptr;
+    uint64_t begin = 0;  // first sim of the shard, relative to the call
+    uint32_t count = 0;
+    DevicePlan pl;
+    unsigned launches = 0, waves = 0;
+    uint64_t h2d = 0, d2h = 0;
+    uint32_t units_per_sim = 1;  // progress units the kernels count per sim (OLS: 1 study; GLM / MLE: n_ss fits)
+    bool copies = false, done = false;
+    float ms = 0.f;
+};
+
+// Host views of the call-wide result tensors (element sizes per cell follow BatchResult, spec.rs:552-600).
+struct HostOut {
+    uint8_t *unc = nullptr, *cor = nullptr, *conv = nullptr, *overall = nullptr, *fx = nullptr, *joint = nullptr, *bh = nullptr, *ph_unc = nullptr,
+            *ph_cor = nullptr;
+    double* tsq = nullptr;
+};
+
+// Everything one device has to do for its shard, enqueued without a single host-side wait: table upload, waves of kernel
+// launches on the compute stream, device→host copies of each finished wave on the copy stream (BYTES / CAPTURE: wave w travels
+// while wave w + 1 computes), counters into the page-locked staging buffer.
+static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t n_ss, uint64_t base_seed, uint64_t call_sim_begin,
+                          const McpOptions& opt, const HostOut& ho, bool sink) {
+    DeviceCtx& cx = *sh.cx;
+    CUDA_CHECK(cudaSetDevice(cx.dev));
+    const cudaStream_t st = cx.compute;
+    DevicePlan& pl = sh.pl;
+    pl = lw.plan;
+    const int T = lw.T, F = lw.F;
+    const uint32_t n_sims = sh.count;
+    const bool bytes = opt.mode & MCP_MODE_BYTES, capture = opt.mode & MCP_MODE_CAPTURE;
+    const bool glm = s.estimator == E_GLM, mle = s.estimator == E_MLE;
+    const int kind = glm ? KIND_GLM : (mle ? KIND_LMM : KIND_OLS);
+    sh.copies = bytes || capture;
+    // ---- tables: one blob, one upload
+    void* dblob = cx.tables.get(lw.blob.size());
+    CUDA_CHECK(cudaMemcpyAsync(dblob, lw.blob.data(), lw.blob.size(), cudaMemcpyHostToDevice, st));
+    sh.h2d += lw.blob.size();
+    bind_tables(lw, pl, dblob);
+    // ---- per-call device state: counters, progress counter / cancel flag / error flag (one 256-byte block)
+    const size_t ncnt = (size_t)n_ss * lw.cw;
+    pl.counters = static_cast<unsigned long long*>(cx.small.get(Carver::pad(ncnt * sizeof(unsigned long long))));
+    CUDA_CHECK(cudaMemsetAsync(pl.counters, 0, ncnt * sizeof(unsigned long long), st));
+    CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
+    pl.error_flag = cx.d_error;
+    sh.units_per_sim = kind == KIND_OLS ? 1u : n_ss;
+    if (sink) {
+        const uint64_t units = (uint64_t)n_sims * sh.units_per_sim;
+        if (units > 0xffffffffull) unsupported("progress reporting for more than 2^32 fits per device and call");
+        pl.prog_counter = cx.d_prog;
+        pl.prog_host = mapped_progress_word(cx);
+        pl.prog_step = (uint32_t)std::max<uint64_t>(units / 50, 1);  // batch.rs:449-450
+        pl.cancel_flag = cx.d_cancel;
+        cx.mail->progress = 0;
+    }
+    // ---- device-side result tensors of the shard
+    const size_t cells = (size_t)n_sims * n_ss;
+    {
+        size_t total = 0;
+        if (bytes) {
+            total += 2 * Carver::pad(cells * T) + Carver::pad(cells);
+            if (s.report_overall) total += Carver::pad(cells);
+            if (F > 0) total += Carver::pad(cells * F);
+            if (pl.n_ph > 0) total += 2 * Carver::pad(cells * pl.n_ph);
+            if (mle) total += 2 * Carver::pad(cells);
+        }
+        if (capture) total += Carver::pad(cells * T * sizeof(double));
+        Carver oc(total ? cx.outputs.get(total) : nullptr);
+        if (bytes) {
+            pl.out_unc = oc.take<uint8_t>(cells * T);
+            pl.out_cor = oc.take<uint8_t>(cells * T);
+            pl.out_conv = oc.take<uint8_t>(cells);
+            if (s.report_overall) pl.out_overall = oc.take<uint8_t>(cells);
+            if (F > 0) pl.out_fx = oc.take<uint8_t>(cells * F);
+            if (pl.n_ph > 0) {
+                pl.out_ph_unc = oc.take<uint8_t>(cells * pl.n_ph);
+                pl.out_ph_cor = oc.take<uint8_t>(cells * pl.n_ph);
+            }
+            if (mle) {
+                pl.out_joint = oc.take<uint8_t>(cells);
+                pl.out_bh = oc.take<uint8_t>(cells);
+            }
+        }
+        if (capture) pl.out_tsq = oc.take<double>(cells * T);
+    }
+    // ---- wave size.  The batch is never cut for progress reporting (the kernels publish it); waves exist only where the scratch
+    // arena bounds the studies in flight, and — BYTES / CAPTURE — so that the copy of one wave overlaps the next wave's kernels.
+    uint32_t wave = opt.wave_sims ? opt.wave_sims : n_sims;
+    wave = std::max<uint32_t>(wave, 1);
+    if (!opt.wave_sims && sh.copies) {
+        size_t per_sim = 0;
+        if (bytes) per_sim += (size_t)n_ss * (2 * T + 1 + (s.report_overall ? 1 : 0) + F + 2 * pl.n_ph + (mle ? 2 : 0));
+        if (capture) per_sim += (size_t)n_ss * T * sizeof(double);
+        const size_t out_bytes = per_sim * n_sims;
+        const uint32_t pieces = (uint32_t)std::min<size_t>(std::max<size_t>(out_bytes >> 25, 1), 16);  // ~32 MiB per piece, at most 16
+        if (pieces > 1) wave = std::max<uint32_t>((((n_sims + pieces - 1) / pieces + 127u) / 128u) * 128u, 1u << 15);
+    }
+    float* glm_scratch = nullptr;
+    if (glm) {
+        // IRLS makes several passes over each study's data: the f32 plane of a wave is kept in HBM as
+        // [row][column][sim] (coalesced across the sims of a warp); the wave is capped at ~6 GiB of scratch
+        // (+ the per-study scenario designs behind the plane on the scenario path, sized for the widest template)
+        const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));
+        const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
+        wave = std::min(wave, cap);
+        wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
+        glm_scratch = static_cast<float*>(cx.scratch.get((size_t)wave * per_sim));
+    }
+    double* lmm_scratch = nullptr;
+    bool lmm_quad = false;  // mixed-model generator on the quad kernel (cluster sums fit in shared memory; kernel_tu.cu decides the same way)
+    if (mle) {
+        const int P_ = lw.P, M_ = (P_ + 2) / 2, MH_ = (M_ + 1) & ~1, STUDY_ = 4 * (2 * MH_) + 2;
+        const int cs_ = std::max(s.sizing_value, 1);
+        const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
+        const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
+                              (size_t)(MCP_BLOCK / 4) * (((nc_ * (P_ + 1)) | 1) + (nc_ | 1)) * sizeof(double);
+        lmm_quad = smem_q <= 56 * 1024;
+        // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
+        // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
+        const size_t per_sim = (nc_ * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
+                               (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));  // + scenario designs behind the layout
+        const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
+        wave = std::min(wave, cap);
+        wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs
+        if (wave > cap) wave = std::max<uint32_t>((cap / 128u) * 128u, 128u);
+        lmm_scratch = static_cast<double*>(cx.scratch.get((size_t)wave * per_sim));
+    }
+    // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
+    //   5 lean path — plain linear models (Normal marginals/residual, exact-walk factors, no cluster/scenario): lane-quad
+    //     generate+accumulate kernel leaves X'X|X'y|y'y per fit in HBM, a thread-per-fit kernel solves;
+    //   6 split path — everything else on the OLS arm: the general lane-quad kernel in generate+accumulate form
+    //     (scenario designs from their own one-thread-per-study kernel), same statistics buffer, same solve kernel;
+    //   4 general quad kernel solving by call, 1 thread-per-study kernel — kept for cross-checks (tests select them through
+    //     the process-wide test hook mcp_test_force_ols_variant; the product path never reads the environment).
+    const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
+                         (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster && !pl.bootstrap;
+    int ols_variant = lean_ok ? 5 : 6;
+    switch (g_force_ols_variant.load(std::memory_order_relaxed)) {
+        case 1: ols_variant = 1; break;
+        case 4: ols_variant = 4; break;
+        case 5: ols_variant = lean_ok ? 5 : 4; break;
+        case 6: ols_variant = 6; break;
+        default: break;
+    }
+    if (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) {
+        // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB of scratch, ~12 GiB
+        // on the scenario path: its one-thread-per-study design kernel is latency-bound (Jacobi repair in local memory)
+        // and wants as many studies in flight as the 180 GB part allows
+        const size_t E = (size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1;
+        const size_t per_sim = (size_t)n_ss * E * sizeof(double);
+        const size_t cap_bytes = (ols_variant == 6 && !pl.optimistic) ? (size_t)12 << 30 : (size_t)4 << 30;
+        const uint32_t cap = (uint32_t)std::max<size_t>(cap_bytes / per_sim, 128);
+        wave = std::min(wave, cap);
+        if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
+        // variant 6 on the scenario path keeps the per-study scenario designs behind the statistics (sized for the widest template)
+        const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>) : 0;
+        lmm_scratch = static_cast<double*>(cx.scratch.get((size_t)wave * (n_ss * E * sizeof(double) + design_bytes)));
+    }
+    if (pl.n_between > 0) {  // representative-row values of the cluster-level predictors, [cluster][column][study in wave]
+        const size_t cs = (size_t)std::max(s.sizing_value, 1);
+        const size_t n_rep = s.sizing_fixed_size ? ((size_t)pl.max_n + cs - 1) / cs : std::min<size_t>(cs, (size_t)pl.max_n);
+        pl.between_stride = wave;
+        pl.between_tab = static_cast<float*>(cx.between.get(n_rep * pl.n_between * (size_t)wave * sizeof(float)));
+    }
+    // accumulate / generate + solve / fit per wave, + the scenario-design kernel on the scenario path (the thread-per-study
+    // cross-check kernels, variants 1 and 4, are single launches)
+    const bool two_stage = kind != KIND_OLS || ols_variant == 5 || ols_variant == 6;
+    const unsigned launches_per_wave = two_stage ? ((pl.optimistic || (mle && !lmm_quad)) ? 2 : 3) : 1;
+    CUDA_CHECK(cudaEventRecord(cx.e0, st));
+    for (uint64_t done = 0; done < n_sims;) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_sims - done);
+        // the byte tensors are indexed by the sim's position in the shard, so waves shift the base pointers
+        DevicePlan shifted = pl;
+        if (done > 0 && sh.copies) {
+            if (bytes) {
+                shifted.out_unc = pl.out_unc + done * n_ss * T;
+                shifted.out_cor = pl.out_cor + done * n_ss * T;
+                shifted.out_conv = pl.out_conv + done * n_ss;
+                if (pl.out_overall) shifted.out_overall = pl.out_overall + done * n_ss;
+                if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
+                if (pl.out_joint) shifted.out_joint = pl.out_joint + done * n_ss;
+                if (pl.out_bh) shifted.out_bh = pl.out_bh + done * n_ss;
+                if (pl.out_ph_unc) {
+                    shifted.out_ph_unc = pl.out_ph_unc + done * n_ss * pl.n_ph;
+                    shifted.out_ph_cor = pl.out_ph_cor + done * n_ss * pl.n_ph;
+                }
+            }
+            if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
+        }
+        KernelArgs ka{base_seed, call_sim_begin + sh.begin + done, cnt, st, glm_scratch, lmm_scratch, ols_variant};
+        dispatch_power(lw.P, kind, shifted, ka);
+        sh.h2d += sizeof(DevicePlan);
+        sh.launches += launches_per_wave;
+        if (sh.copies) {  // this wave's slices travel on the copy stream while the next wave computes
+            cudaEvent_t ev = cx.wave_event(sh.waves);
+            CUDA_CHECK(cudaEventRecord(ev, st));
+            CUDA_CHECK(cudaStreamWaitEvent(cx.copy, ev, 0));
+            const uint64_t at = sh.begin + done;  // position in the call-wide host tensors
+            auto fetch = [&](auto* host, const auto* dev, size_t row) {
+                if (!host || !dev || row == 0) return;
+                using Elem = std::remove_cv_t<std::remove_pointer_t<decltype(dev)>>;
+                const size_t nb = (size_t)cnt * row * sizeof(Elem);
+                CUDA_CHECK(cudaMemcpyAsync(host + at * row, dev + done * row, nb, cudaMemcpyDeviceToHost, cx.copy));
+                sh.d2h += nb;
+            };
+            fetch(ho.unc, pl.out_unc, (size_t)n_ss * T);
+            fetch(ho.cor, pl.out_cor, (size_t)n_ss * T);
+            fetch(ho.conv, pl.out_conv, (size_t)n_ss);
+            fetch(ho.overall, pl.out_overall, (size_t)n_ss);
+            fetch(ho.fx, pl.out_fx, (size_t)n_ss * F);
+            fetch(ho.joint, pl.out_joint, (size_t)n_ss);
+            fetch(ho.bh, pl.out_bh, (size_t)n_ss);
+            fetch(ho.ph_unc, pl.out_ph_unc, (size_t)n_ss * pl.n_ph);
+            fetch(ho.ph_cor, pl.out_ph_cor, (size_t)n_ss * pl.n_ph);
+            fetch(ho.tsq, pl.out_tsq, (size_t)n_ss * T);
+        }
+        sh.waves++;
+        done += cnt;
+    }
+    CUDA_CHECK(cudaEventRecord(cx.e1, st));
+    unsigned long long* hc = cx.counters_staging(ncnt);
+    CUDA_CHECK(cudaMemcpyAsync(hc, pl.counters, ncnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&cx.mail->error_flag, cx.d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+    sh.d2h += ncnt * sizeof(unsigned long long) + sizeof(int);
+    CUDA_CHECK(cudaEventRecord(cx.done_compute, st));
+    if (sh.copies) CUDA_CHECK(cudaEventRecord(cx.done_copy, cx.copy));
+}
+
+static bool shard_finished(Shard& sh) {
+    if (sh.done) return true;
+    cudaError_t e = cudaEventQuery(sh.cx->done_compute);
+    if (e == cudaErrorNotReady) return false;
+    CUDA_CHECK(e);
+    if (sh.copies) {
+        e = cudaEventQuery(sh.cx->done_copy);
+        if (e == cudaErrorNotReady) return false;
+        CUDA_CHECK(e);
+    }
+    sh.done = true;
+    return true;
+}
+
 }  // namespace mcp
 
 using namespace mcp;
@@ -652,7 +1079,7 @@ using namespace mcp;
 extern "C" {
 
 const char* mcp_last_error(void) { return g_last_error.c_str(); }
-const char* mcp_version(void) { return "mcpower_b200 0.1.0 (sm_100a)"; }
+const char* mcp_version(void) { return "mcpower_b200 0.2.0 (sm_100a)"; }
 uint64_t mcp_splitmix64(uint64_t z) { return splitmix64(z); }
 
 int mcp_device_count(void) {
@@ -661,220 +1088,189 @@ int mcp_device_count(void) {
     return n;
 }
 
+int mcp_test_force_ols_variant(int variant) {
+    return g_force_ols_variant.exchange(variant, std::memory_order_relaxed);
+}
+
 void mcp_free_result(McpBatchResult* r) {
     if (!r) return;
-    std::free(r->uncorrected);
-    std::free(r->corrected);
-    std::free(r->converged);
-    std::free(r->overall);
-    std::free(r->factor_excluded);
-    std::free(r->joint);
-    std::free(r->boundary_hit);
-    std::free(r->t_sq);
-    std::free(r->posthoc_unc);
-    std::free(r->posthoc_cor);
-    std::free(r->counters);
+    void* owned[] = {r->uncorrected, r->corrected, r->converged, r->overall, r->factor_excluded, r->joint, r->boundary_hit,
+                     r->t_sq, r->posthoc_unc, r->posthoc_cor, r->counters};
+    for (void* p : owned)
+        if (p && !g_pinned.give(p)) std::free(p);
     std::free(r);
 }
 
-// run_batch on a parsed spec: validation, lowering, waves of kernel launches, result fetch.  Shared by mcp_run_batch and
-// the orchestrator entry points (mcp_find_power / mcp_find_sample_size).
+// run_batch on a parsed spec: validation, lowering (once), one shard per device — everything enqueued asynchronously —, then
+// the calling thread waits: it polls the devices' progress words and events, serves the ProgressSink, raises the cancel flag.
+// Shared by mcp_run_batch and the orchestrator entry points (mcp_find_power / mcp_find_sample_size).
+// progress_offset / progress_total: the (current, total) the sink sees are offset + done and total (a multi-scenario call
+// reports one range over all scenarios, find_power.rs:337-380); total 0 = this batch alone.
 static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims, uint64_t base_seed,
-                                      const McpOptions* options, McpProgressFn progress, void* user) {
-    McpBatchResult* result_out = nullptr;
+                                      const McpOptions* options, McpProgressFn progress, void* user, uint64_t progress_offset = 0,
+                                      uint64_t progress_total = 0) {
+    McpOptions opt{-1, MCP_MODE_COUNTS, 0, 0, 0, nullptr};
+    if (options) opt = *options;
+    if (opt.mode == 0) opt.mode = MCP_MODE_COUNTS;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (!sample_sizes) invalid("sample_sizes pointer is NULL");
+    validate_spec(s, sample_sizes, n_ss);
+    if (n_ss > 65535u) invalid("more than 65535 sample sizes in one batch");  // grid.y of the fit kernels
+    check_supported(s);
+    Lowered lw;
+    lower(s, sample_sizes, n_ss, lw);  // host only: every spec-level error surfaces before a device is touched
+    const double lower_ms = ms_since(t_start);
+    const auto t_enqueue = std::chrono::steady_clock::now();
+    const std::vector<int> devices = resolve_devices(opt);
+    const int T = lw.T, F = lw.F;
+    const bool bytes = opt.mode & MCP_MODE_BYTES, capture = opt.mode & MCP_MODE_CAPTURE;
+    const bool mle = s.estimator == E_MLE;
+    const bool sink = progress != nullptr || opt.is_cancelled != nullptr;
+
+    // ---- shards: contiguous sim-id ranges, device g takes [g·ceil(S/G), ...); empty shards are dropped
+    std::vector<Shard> shards;
     {
-        McpOptions opt{-1, MCP_MODE_COUNTS, 0, 0, 0};
-        if (options) opt = *options;
-        if (opt.mode == 0) opt.mode = MCP_MODE_COUNTS;
-        validate_spec(s, sample_sizes, n_ss);
-        check_supported(s);
-        select_device(opt.device);
-        std::lock_guard<std::mutex> lock(g_plan_mutex);
-        Lowered lw;
-        lower(s, sample_sizes, n_ss, lw);
-        DevicePlan& pl = lw.plan;
-        const int T = lw.T, F = lw.F;
-        const bool bytes = opt.mode & MCP_MODE_BYTES, capture = opt.mode & MCP_MODE_CAPTURE;
-        const size_t cells = (size_t)n_sims * n_ss;
-        pl.counters = lw.bufs.alloc<unsigned long long>((size_t)n_ss * lw.cw);
-        CUDA_CHECK(cudaMemset(pl.counters, 0, (size_t)n_ss * lw.cw * sizeof(unsigned long long)));
-        pl.error_flag = lw.bufs.alloc<int>(1);
-        CUDA_CHECK(cudaMemset(pl.error_flag, 0, sizeof(int)));
-        if (bytes) {
-            pl.out_unc = lw.bufs.alloc<uint8_t>(cells * T);
-            pl.out_cor = lw.bufs.alloc<uint8_t>(cells * T);
-            pl.out_conv = lw.bufs.alloc<uint8_t>(cells);
-            if (s.report_overall) pl.out_overall = lw.bufs.alloc<uint8_t>(cells);
-            if (F > 0) pl.out_fx = lw.bufs.alloc<uint8_t>(cells * F);
-            if (pl.n_ph > 0) {
-                pl.out_ph_unc = lw.bufs.alloc<uint8_t>(cells * pl.n_ph);
-                pl.out_ph_cor = lw.bufs.alloc<uint8_t>(cells * pl.n_ph);
+        const uint64_t G = devices.size(), per = (n_sims + G - 1) / G;
+        for (uint64_t g = 0; g < G; g++) {
+            const uint64_t b = std::min<uint64_t>(g * per, n_sims), e = std::min<uint64_t>(b + per, n_sims);
+            if (e > b || (g == 0 && n_sims == 0)) {
+                Shard sh;
+                sh.cx = &ctx_for(devices[g]);
+                sh.begin = b;
+                sh.count = (uint32_t)(e - b);
+                shards.push_back(sh);
             }
         }
-        if (capture) pl.out_tsq = lw.bufs.alloc<double>(cells * T);
-        const bool glm = s.estimator == E_GLM, mle = s.estimator == E_MLE;
-        const int kind = glm ? KIND_GLM : (mle ? KIND_LMM : KIND_OLS);
-        if (mle && bytes) {
-            pl.out_joint = lw.bufs.alloc<uint8_t>(cells);
-            pl.out_bh = lw.bufs.alloc<uint8_t>(cells);
-        }
+    }
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto& sh : shards) locks.emplace_back(sh.cx->mu);  // ascending ordinals: no lock-order inversion between calls
 
-        McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
-        r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
-        r->counter_width = (uint32_t)lw.cw;
-        r->n_posthoc = (uint32_t)pl.n_ph;
-        struct Guard { McpBatchResult* r; bool ok = false; ~Guard() { if (!ok) mcp_free_result(r); } } guard{r};
-
-        cudaStream_t st = 0;
-        cudaEvent_t e0, e1;
-        CUDA_CHECK(cudaEventCreate(&e0));
-        CUDA_CHECK(cudaEventCreate(&e1));
-        // batch.rs:449-450 — report ~50 times per run; cancellation is polled between waves
-        uint32_t wave = opt.wave_sims ? opt.wave_sims : (progress ? std::max<uint32_t>((n_sims + 49) / 50, 128u) : n_sims);
-        wave = std::max<uint32_t>(wave, 1);
-        float* glm_scratch = nullptr;
-        if (glm) {
-            // IRLS makes several passes over each study's data: the f32 plane of a wave is kept in HBM as
-            // [row][column][sim] (coalesced across the sims of a warp); the wave is capped at ~6 GiB of scratch
-            // (+ the per-study scenario designs behind the plane on the scenario path, sized for the widest template)
-            const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));
-            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
-            wave = std::min(wave, cap);
-            wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            glm_scratch = static_cast<float*>(g_scratch.get((size_t)wave * per_sim));
+    // ---- the call-wide result (host)
+    McpBatchResult* r = static_cast<McpBatchResult*>(std::calloc(1, sizeof(McpBatchResult)));
+    if (!r) throw EngineError(MCP_CUDA_ERROR, "out of host memory");
+    r->n_sims = n_sims; r->n_sample_sizes = n_ss; r->n_targets = (uint32_t)T; r->n_factors = (uint32_t)F;
+    r->counter_width = (uint32_t)lw.cw;
+    r->n_posthoc = (uint32_t)lw.plan.n_ph;
+    r->n_devices = (uint32_t)shards.size();
+    bool enqueued = false;
+    struct Guard {  // on any failure: let the devices drain (they may still write into the result buffers), then free
+        McpBatchResult* r; std::vector<Shard>* shards; bool* enqueued; bool ok = false;
+        ~Guard() {
+            if (ok) return;
+            if (*enqueued)
+                for (auto& sh : *shards) {
+                    cudaSetDevice(sh.cx->dev);
+                    cudaDeviceSynchronize();
+                }
+            mcp_free_result(r);
         }
-        double* lmm_scratch = nullptr;
-        bool lmm_quad = false;  // mixed-model generator on the quad kernel (cluster sums fit in shared memory; kernel_tu.cu decides the same way)
+    } guard{r, &shards, &enqueued};
+    const size_t cells = (size_t)n_sims * n_ss, ncnt = (size_t)n_ss * lw.cw;
+    r->counters = static_cast<uint64_t*>(std::calloc(std::max<size_t>(ncnt, 1), sizeof(uint64_t)));
+    HostOut ho;
+    CUDA_CHECK(cudaSetDevice(shards[0].cx->dev));
+    if (bytes) {
+        auto take = [&](size_t n) { return static_cast<uint8_t*>(g_pinned.take(n)); };
+        ho.unc = r->uncorrected = take(cells * T);
+        ho.cor = r->corrected = take(cells * T);
+        ho.conv = r->converged = take(cells);
+        if (s.report_overall) ho.overall = r->overall = take(cells);
+        if (F > 0) ho.fx = r->factor_excluded = take(cells * F);
+        if (lw.plan.n_ph > 0) {
+            ho.ph_unc = r->posthoc_unc = take(cells * lw.plan.n_ph);
+            ho.ph_cor = r->posthoc_cor = take(cells * lw.plan.n_ph);
+        }
         if (mle) {
-            const int P_ = lw.P, M_ = (P_ + 2) / 2, MH_ = (M_ + 1) & ~1, STUDY_ = 4 * (2 * MH_) + 2;
-            const int cs_ = std::max(s.sizing_value, 1);
-            const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
-            const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
-                                  (size_t)(MCP_BLOCK / 4) * (((nc_ * (P_ + 1)) | 1) + (nc_ | 1)) * sizeof(double);
-            lmm_quad = smem_q <= 56 * 1024;
-            // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
-            const int cs = std::max(s.sizing_value, 1);
-            const size_t nc_cap = s.sizing_fixed_size ? (size_t)(pl.max_n + cs - 1) / cs : (size_t)cs;
-            // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
-            const size_t per_sim = (nc_cap * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
-                                   (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));  // + scenario designs behind the layout
-            const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
-            wave = std::min(wave, cap);
-            wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs
-            if (wave > cap) wave = std::max<uint32_t>((cap / 128u) * 128u, 128u);
-            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * per_sim));
+            ho.joint = r->joint = take(cells);
+            ho.bh = r->boundary_hit = take(cells);
         }
-        // OLS kernel choice (results are bit-identical whichever runs; tests/test_gpu_parity.py checks that):
-        //   5 lean path — plain linear models (Normal marginals/residual, exact-walk factors, no cluster/scenario): lane-quad
-        //     generate+accumulate kernel leaves X'X|X'y|y'y per fit in HBM, a thread-per-fit kernel solves;
-        //   6 split path — everything else on the OLS arm: the general lane-quad kernel in generate+accumulate form
-        //     (scenario designs from their own one-thread-per-study kernel), same statistics buffer, same solve kernel;
-        //   4 general quad kernel solving by call, 1 thread-per-study kernel — kept for cross-checks.
-        // MCPOWER_B200_OLS_VARIANT=1|4|5|6 forces one where eligible (read per call).
-        const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
-                             (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster && !pl.bootstrap;
-        int ols_variant = lean_ok ? 5 : 6;
-        if (const char* e = std::getenv("MCPOWER_B200_OLS_VARIANT")) {
-            if (e[0] == '1') ols_variant = 1;
-            else if (e[0] == '4') ols_variant = 4;
-            else if (e[0] == '5') ols_variant = lean_ok ? 5 : 4;
-            else if (e[0] == '6') ols_variant = 6;
-        }
-        if (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) {
-            // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB of scratch, ~12 GiB
-            // on the scenario path: its one-thread-per-study design kernel is latency-bound (Jacobi repair in local memory)
-            // and wants as many studies in flight as the 180 GB part allows
-            const size_t E = (size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1;
-            const size_t per_sim = (size_t)n_ss * E * sizeof(double);
-            const size_t cap_bytes = (ols_variant == 6 && !pl.optimistic) ? (size_t)12 << 30 : (size_t)4 << 30;
-            const uint32_t cap = (uint32_t)std::max<size_t>(cap_bytes / per_sim, 128);
-            wave = std::min(wave, cap);
-            if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
-            // variant 6 on the scenario path keeps the per-study scenario designs behind the statistics (sized for the widest template)
-            const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>) : 0;
-            lmm_scratch = static_cast<double*>(g_scratch.get((size_t)wave * (n_ss * E * sizeof(double) + design_bytes)));
-        }
-        CUDA_CHECK(cudaEventRecord(e0, st));
-        bool cancelled = false;
-        for (uint64_t done = 0; done < n_sims;) {
-            const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_sims - done);
-            // the byte tensors are indexed by the sim's position in this call, so waves shift the base pointers
-            DevicePlan shifted = pl;
-            if (done > 0 && (bytes || capture)) {
-                if (bytes) {
-                    shifted.out_unc = pl.out_unc + done * n_ss * T;
-                    shifted.out_cor = pl.out_cor + done * n_ss * T;
-                    shifted.out_conv = pl.out_conv + done * n_ss;
-                    if (pl.out_overall) shifted.out_overall = pl.out_overall + done * n_ss;
-                    if (pl.out_fx) shifted.out_fx = pl.out_fx + done * n_ss * F;
-                    if (pl.out_joint) shifted.out_joint = pl.out_joint + done * n_ss;
-                    if (pl.out_bh) shifted.out_bh = pl.out_bh + done * n_ss;
-                    if (pl.out_ph_unc) {
-                        shifted.out_ph_unc = pl.out_ph_unc + done * n_ss * pl.n_ph;
-                        shifted.out_ph_cor = pl.out_ph_cor + done * n_ss * pl.n_ph;
+    }
+    if (capture) ho.tsq = r->t_sq = static_cast<double*>(g_pinned.take(cells * T * sizeof(double)));
+
+    // ---- enqueue every device's work, then wait
+    enqueued = true;
+    for (auto& sh : shards) enqueue_shard(sh, lw, s, n_ss, base_seed, opt.sim_begin, opt, ho, sink);
+    r->lower_ms = lower_ms;
+    r->enqueue_ms = ms_since(t_enqueue);
+    const auto t_wait = std::chrono::steady_clock::now();
+    bool cancelled = false;
+    if (sink) {
+        const uint64_t total = progress_total ? progress_total : n_sims;
+        const uint64_t step = std::max<uint64_t>(n_sims / 50, 1);  // batch.rs:449-450
+        uint64_t reported = 0;
+        auto t_last = std::chrono::steady_clock::now();
+        int spins = 0;
+        for (;;) {
+            bool all = true;
+            for (auto& sh : shards) all = shard_finished(sh) && all;
+            if (all) break;
+            if (!cancelled) {
+                uint64_t done_sims = 0;
+                for (auto& sh : shards) done_sims += std::min<uint64_t>(sh.cx->mail->progress / sh.units_per_sim, sh.count);
+                if (n_sims > 0) done_sims = std::min<uint64_t>(done_sims, n_sims - 1);  // the last report follows the last kernel
+                bool stop = false;
+                if (progress && done_sims >= reported + step) {
+                    reported = done_sims - done_sims % step;
+                    stop = !progress(progress_offset + reported, total, user);
+                }
+                if (!stop && opt.is_cancelled) {
+                    const auto now = std::chrono::steady_clock::now();
+                    if (now - t_last >= std::chrono::microseconds(100)) {
+                        t_last = now;
+                        stop = opt.is_cancelled(user) != 0;
                     }
                 }
-                if (capture) shifted.out_tsq = pl.out_tsq + done * n_ss * T;
-            }
-            {
-                Lowered& lwr = lw;
-                const DevicePlan saved = lwr.plan;
-                lwr.plan = shifted;
-                KernelArgs ka{base_seed, opt.sim_begin + done, cnt, st, glm_scratch, lmm_scratch, ols_variant};
-                dispatch_power(lwr, kind, ka);
-                lwr.plan = saved;
-            }
-            // accumulate / generate + solve / fit per wave, + the scenario-design kernel on the scenario path (the thread-per-study
-            // cross-check kernels, variants 1 and 4, are single launches)
-            const bool two_stage = kind != KIND_OLS || ols_variant == 5 || ols_variant == 6;
-            r->gpu_launches += two_stage ? ((pl.optimistic || (mle && !lmm_quad)) ? 2 : 3) : 1;
-            done += cnt;
-            if (progress) {
-                CUDA_CHECK(cudaStreamSynchronize(st));
-                if (!progress(done, n_sims, user)) {
+                if (stop) {  // CTAs that have not started yet see the flag and exit; running ones finish their studies
                     cancelled = true;
-                    break;
+                    for (auto& sh : shards) {
+                        CUDA_CHECK(cudaSetDevice(sh.cx->dev));
+                        CUDA_CHECK(cudaMemcpyAsync(sh.cx->d_cancel, &sh.cx->mail->one, sizeof(int), cudaMemcpyHostToDevice, sh.cx->ctl));
+                    }
                 }
             }
+            if (++spins < 64) std::this_thread::yield();
+            else std::this_thread::sleep_for(std::chrono::microseconds(50));
         }
-        CUDA_CHECK(cudaEventRecord(e1, st));
-        CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        r->kernel_ms = ms;
-        if (cancelled) throw EngineError(MCP_CANCELLED, "cancelled by host");  // partial results discarded (batch.rs:128-129)
-        int err_flag = 0;
-        CUDA_CHECK(cudaMemcpy(&err_flag, pl.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err_flag == 2) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
-
-        auto fetch = [&](auto*& host, const auto* dev, size_t n) {
-            using Elem = std::remove_cv_t<std::remove_pointer_t<decltype(dev)>>;
-            host = static_cast<Elem*>(std::malloc(std::max<size_t>(n, 1) * sizeof(Elem)));
-            if (n) CUDA_CHECK(cudaMemcpy(host, dev, n * sizeof(Elem), cudaMemcpyDeviceToHost));
-        };
-        unsigned long long* cnt_host = nullptr;
-        fetch(cnt_host, pl.counters, (size_t)n_ss * lw.cw);
-        r->counters = reinterpret_cast<uint64_t*>(cnt_host);
-        if (bytes) {
-            fetch(r->uncorrected, pl.out_unc, cells * T);
-            fetch(r->corrected, pl.out_cor, cells * T);
-            fetch(r->converged, pl.out_conv, cells);
-            if (pl.out_overall) fetch(r->overall, pl.out_overall, cells);
-            if (pl.out_fx) fetch(r->factor_excluded, pl.out_fx, cells * F);
-            if (pl.out_joint) fetch(r->joint, pl.out_joint, cells);
-            if (pl.out_bh) fetch(r->boundary_hit, pl.out_bh, cells);
-            if (pl.out_ph_unc) {
-                fetch(r->posthoc_unc, pl.out_ph_unc, cells * pl.n_ph);
-                fetch(r->posthoc_cor, pl.out_ph_cor, cells * pl.n_ph);
+        if (cancelled)
+            for (auto& sh : shards) {
+                CUDA_CHECK(cudaSetDevice(sh.cx->dev));
+                CUDA_CHECK(cudaStreamSynchronize(sh.cx->ctl));
             }
+    } else {
+        for (auto& sh : shards) {
+            CUDA_CHECK(cudaSetDevice(sh.cx->dev));
+            CUDA_CHECK(cudaEventSynchronize(sh.cx->done_compute));
+            if (sh.copies) CUDA_CHECK(cudaEventSynchronize(sh.cx->done_copy));
+            sh.done = true;
         }
-        if (capture) fetch(r->t_sq, pl.out_tsq, cells * T);
-        guard.ok = true;
-        result_out = r;
     }
-    return result_out;
+    enqueued = false;  // drained
+    r->wait_ms = ms_since(t_wait);
+    if (cancelled) throw EngineError(MCP_CANCELLED, "cancelled by host");  // partial results discarded (batch.rs:128-129)
+    bool not_psd = false;
+    for (auto& sh : shards) {
+        CUDA_CHECK(cudaSetDevice(sh.cx->dev));
+        CUDA_CHECK(cudaEventElapsedTime(&sh.ms, sh.cx->e0, sh.cx->e1));
+        r->kernel_ms = std::max<double>(r->kernel_ms, sh.ms);  // the devices run concurrently
+        r->gpu_launches += sh.launches;
+        r->n_waves += sh.waves;
+        r->h2d_bytes += sh.h2d;
+        r->d2h_bytes += sh.d2h;
+        not_psd = not_psd || sh.cx->mail->error_flag == 2;
+        // the path's only reduction: integer counters per (sample size, test).  The partial sums must reach the host anyway
+        // (they ARE the result), one page-locked row block per device, so they are added here rather than by an NCCL
+        // all-reduce that would then be followed by the same device→host copy.
+        const unsigned long long* hc = sh.cx->h_counters;
+        for (size_t i = 0; i < ncnt; i++) r->counters[i] += hc[i];
+    }
+    if (not_psd) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
+    if (progress && !progress(progress_offset + n_sims, progress_total ? progress_total : n_sims, user))
+        throw EngineError(MCP_CANCELLED, "cancelled by host");
+    guard.ok = true;
+    return r;
 }
 
 int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
@@ -1222,29 +1618,39 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
         validate_spec(s, nullptr, 0);
         check_supported(s, /*generation_only=*/true);
         if (max_n == 0) invalid("max_n must be > 0");
-        select_device(device);
-        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        DeviceCtx& cx = ctx_for(device);
+        std::lock_guard<std::mutex> lock(cx.mu);
+        const cudaStream_t st = cx.compute;
         Lowered lw;
         lower(s, &max_n, 1, lw, /*thresholds=*/false);
         const int P = lw.P;
-        float* dx = lw.bufs.alloc<float>((size_t)max_n * P);
-        float* dy = lw.bufs.alloc<float>(max_n);
-        lw.plan.error_flag = lw.bufs.alloc<int>(1);
-        CUDA_CHECK(cudaMemset(lw.plan.error_flag, 0, sizeof(int)));
+        void* dblob = cx.tables.get(lw.blob.size());
+        CUDA_CHECK(cudaMemcpyAsync(dblob, lw.blob.data(), lw.blob.size(), cudaMemcpyHostToDevice, st));
+        bind_tables(lw, lw.plan, dblob);
+        Carver oc(cx.outputs.get(Carver::pad((size_t)max_n * P * sizeof(float)) + Carver::pad((size_t)max_n * sizeof(float))));
+        float* dx = oc.take<float>((size_t)max_n * P);
+        float* dy = oc.take<float>(max_n);
+        CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
+        lw.plan.error_flag = cx.d_error;
+        if (lw.plan.n_between > 0) {
+            lw.plan.between_stride = 1;
+            lw.plan.between_tab = static_cast<float*>(cx.between.get((size_t)max_n * lw.plan.n_between * sizeof(float)));
+        }
         {
             cudaError_t err = cudaSuccess;
             bool handled = false;
-#define X(id) if (!handled) handled = tu##id##_dump(P, !lw.plan.optimistic, lw.plan, base_seed, sim_id, dx, dy, &err);
+#define X(id) if (!handled) handled = tu##id##_dump(P, !lw.plan.optimistic, lw.plan, base_seed, sim_id, dx, dy, st, &err);
             MCP_TU_LIST(X)
 #undef X
             if (!handled) unsupported("n_predictors = " + std::to_string(P));
             CUDA_CHECK(err);
         }
-        CUDA_CHECK(cudaDeviceSynchronize());
+        // the caller's buffers are pageable: synchronous copies, ordered behind the kernel by the stream synchronisation
+        CUDA_CHECK(cudaStreamSynchronize(st));
         CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * P * sizeof(float), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaMemcpy(y, dy, (size_t)max_n * sizeof(float), cudaMemcpyDeviceToHost));
         int err_flag = 0;
-        CUDA_CHECK(cudaMemcpy(&err_flag, lw.plan.error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(&err_flag, cx.d_error, sizeof(int), cudaMemcpyDeviceToHost));
         if (err_flag == 2) throw EngineError(MCP_CORRELATION_NOT_PSD, "correlation matrix is not positive semi-definite");
     });
 }
@@ -1253,23 +1659,25 @@ int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t
     return guarded([&] {
         if (p < 1 || p > MCP_MAX_TEMPLATE_P) unsupported("p outside [1, " + std::to_string(MCP_MAX_TEMPLATE_P) + "]");
         if (n <= p) invalid("df = N - P < 1");
-        select_device(device);
-        DeviceBuffers bufs;
-        double* dx = bufs.alloc<double>((size_t)n * p);
-        double* dy = bufs.alloc<double>(n);
-        double* dout = bufs.alloc<double>(3 * p + 4);
-        CUDA_CHECK(cudaMemcpy(dx, x_colmajor, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        DeviceCtx& cx = ctx_for(device);
+        std::lock_guard<std::mutex> lock(cx.mu);
+        const cudaStream_t st = cx.compute;
+        Carver oc(cx.outputs.get(Carver::pad((size_t)n * p * sizeof(double)) + Carver::pad((size_t)n * sizeof(double)) + Carver::pad((3 * p + 4) * sizeof(double))));
+        double* dx = oc.take<double>((size_t)n * p);
+        double* dy = oc.take<double>(n);
+        double* dout = oc.take<double>(3 * p + 4);
+        CUDA_CHECK(cudaMemcpyAsync(dx, x_colmajor, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
         {
             cudaError_t err = cudaSuccess;
             bool handled = false;
-#define X(id) if (!handled) handled = tu##id##_fit_data((int)p, dx, dy, (int)n, dout, &err);
+#define X(id) if (!handled) handled = tu##id##_fit_data((int)p, dx, dy, (int)n, dout, st, &err);
             MCP_TU_LIST(X)
 #undef X
             if (!handled) unsupported("p = " + std::to_string(p));
             CUDA_CHECK(err);
         }
-        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaStreamSynchronize(st));
         CUDA_CHECK(cudaMemcpy(out, dout, (3 * p + 4) * sizeof(double), cudaMemcpyDeviceToHost));
     });
 }
@@ -1287,13 +1695,11 @@ int mcp_crit_table(const char* spec_json, size_t spec_len, const uint32_t* sampl
 
 int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s) {
     return guarded([&] {
-        select_device(device);
+        DeviceCtx& cx = ctx_for(device);
+        std::lock_guard<std::mutex> lock(cx.mu);
         cudaDeviceProp prop;
-        int dev = 0;
-        CUDA_CHECK(cudaGetDevice(&dev));
-        CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-        DeviceBuffers bufs;
-        double* sink = bufs.alloc<double>(1);
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, cx.dev));
+        double* sink = static_cast<double*>(cx.small.get(256));
         const int iters = 1 << 14, blocks = prop.multiProcessorCount * 8, threads = 256;
         cudaEvent_t e0, e1;
         CUDA_CHECK(cudaEventCreate(&e0));
@@ -1314,6 +1720,13 @@ int mcp_pipe_bench(int32_t kind, int32_t device, double* thread_ops_per_s) {
                 case 11: pipe_bench_kernel<11><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // DFMA (+ packed FP32)
                 case 12: pipe_bench_kernel<12><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // DFMA (+ IMAD.WIDE, LOP3)
                 case 9: pipe_bench_kernel<9><<<blocks, threads>>>(it, sink); ops_per_iter = 4; break;   // normal draws
+                case 13: pipe_bench_kernel<13><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // mul.hi.u32
+                case 14: pipe_bench_kernel<14><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // mul.lo.u32
+                case 15: pipe_bench_kernel<15><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // mul.hi + mul.lo pairs (counted per pair)
+                case 16: pipe_bench_kernel<16><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // FFMA, register addend
+                case 17: pipe_bench_kernel<17><<<blocks, threads>>>(it, sink); ops_per_iter = 8; break;  // FFMA, immediate addend
+                case 18: pipe_bench_kernel<18><<<blocks, threads>>>(it, sink); ops_per_iter = 4; break;  // integer widen + DADD
+                case 19: pipe_bench_kernel<19><<<blocks, threads, 2048 * sizeof(double2)>>>(it, sink); ops_per_iter = 8; break;  // LDS.128
                 default: invalid("unknown pipe_bench kind");
             }
         };

@@ -195,24 +195,24 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
 }
 
 template <int PT>
-static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy) {
+static cudaError_t dump_one(bool scen, const DevicePlan& pl, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy, cudaStream_t st) {
 #ifndef MCP_TU_IS_OLS
     return cudaErrorInvalidValue;
 #else
-    cudaError_t e = cudaMemcpyToSymbol(c_plan, &pl, sizeof(DevicePlan));
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    if (scen) dgp_dump_kernel<PT, true><<<1, 32>>>(base_seed, sim_id, dx, dy);
-    else dgp_dump_kernel<PT, false><<<1, 32>>>(base_seed, sim_id, dx, dy);
+    if (scen) dgp_dump_kernel<PT, true><<<1, 32, 0, st>>>(base_seed, sim_id, dx, dy);
+    else dgp_dump_kernel<PT, false><<<1, 32, 0, st>>>(base_seed, sim_id, dx, dy);
     return cudaGetLastError();
 #endif
 }
 
 template <int PT>
-static cudaError_t fit_one(const double* dx, const double* dy, int n, double* dout) {
+static cudaError_t fit_one(const double* dx, const double* dy, int n, double* dout, cudaStream_t st) {
 #ifndef MCP_TU_IS_OLS
     return cudaErrorInvalidValue;
 #else
-    fit_data_kernel<PT><<<1, 32>>>(dx, dy, n, dout);
+    fit_data_kernel<PT><<<1, 32, 0, st>>>(dx, dy, n, dout);
     return cudaGetLastError();
 #endif
 }
@@ -227,14 +227,14 @@ static cudaError_t fit_one(const double* dx, const double* dy, int n, double* do
 template <int PT, bool IN = (PT >= MCP_P_LO && PT <= MCP_P_HI)>
 struct Sel {
     static cudaError_t launch(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) { return launch_one<PT>(kind, scen, pl, a); }
-    static cudaError_t dump(bool scen, const DevicePlan& pl, uint64_t s, uint64_t i, float* dx, float* dy) { return dump_one<PT>(scen, pl, s, i, dx, dy); }
-    static cudaError_t fit(const double* dx, const double* dy, int n, double* o) { return fit_one<PT>(dx, dy, n, o); }
+    static cudaError_t dump(bool scen, const DevicePlan& pl, uint64_t s, uint64_t i, float* dx, float* dy, cudaStream_t st) { return dump_one<PT>(scen, pl, s, i, dx, dy, st); }
+    static cudaError_t fit(const double* dx, const double* dy, int n, double* o, cudaStream_t st) { return fit_one<PT>(dx, dy, n, o, st); }
 };
 template <int PT>
 struct Sel<PT, false> {
     static cudaError_t launch(int, bool, const DevicePlan&, const KernelArgs&) { return cudaErrorInvalidValue; }
-    static cudaError_t dump(bool, const DevicePlan&, uint64_t, uint64_t, float*, float*) { return cudaErrorInvalidValue; }
-    static cudaError_t fit(const double*, const double*, int, double*) { return cudaErrorInvalidValue; }
+    static cudaError_t dump(bool, const DevicePlan&, uint64_t, uint64_t, float*, float*, cudaStream_t) { return cudaErrorInvalidValue; }
+    static cudaError_t fit(const double*, const double*, int, double*, cudaStream_t) { return cudaErrorInvalidValue; }
 };
 
 #define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
@@ -251,13 +251,13 @@ bool MCP_TU_FN(launch_power)(int P, int kind, bool scen, const DevicePlan& plan,
 }
 
 bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy,
-                     cudaError_t* err) {
+                     cudaStream_t st, cudaError_t* err) {
 #ifndef MCP_TU_IS_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
     switch (P) {
-#define X(p) case p: *err = Sel<p>::dump(scen, plan, base_seed, sim_id, dx, dy); return true;
+#define X(p) case p: *err = Sel<p>::dump(scen, plan, base_seed, sim_id, dx, dy, st); return true;
         MCP_ALL_P(X)
 #undef X
     }
@@ -265,13 +265,13 @@ bool MCP_TU_FN(dump)(int P, bool scen, const DevicePlan& plan, uint64_t base_see
 #endif
 }
 
-bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, double* dout, cudaError_t* err) {
+bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, double* dout, cudaStream_t st, cudaError_t* err) {
 #ifndef MCP_TU_IS_OLS
     return false;
 #else
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
     switch (P) {
-#define X(p) case p: *err = Sel<p>::fit(dx, dy, n, dout); return true;
+#define X(p) case p: *err = Sel<p>::fit(dx, dy, n, dout, st); return true;
         MCP_ALL_P(X)
 #undef X
     }

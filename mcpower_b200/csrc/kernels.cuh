@@ -263,6 +263,29 @@ static __device__ __noinline__ void apply_correction(int method, const double* t
     }
 }
 
+// ProgressSink plumbing (spec.rs:38-52, batch.rs:2149-2177).  The host never cuts a batch into small launches to report
+// progress: one lane per warp adds its finished work units to a device counter, and the warp whose add crosses a multiple of
+// prog_step publishes the new value to a mapped pinned host word that the waiting host thread polls (~50 stores per call
+// travel over PCIe).  Cancellation is the reverse direction: the host sets a device flag, CTAs that have not started exit.
+__device__ __forceinline__ bool mcp_cancelled() {
+    const int* f = c_plan.cancel_flag;
+    return f != nullptr && *reinterpret_cast<const volatile int*>(f) != 0;
+}
+__device__ __forceinline__ void mcp_report_units(unsigned int units) {  // call from ONE lane per warp
+    unsigned int* ctr = c_plan.prog_counter;
+    if (ctr == nullptr || units == 0u) return;
+    const unsigned int old = atomicAdd(ctr, units), now = old + units, step = c_plan.prog_step;
+    if (now / step != old / step) {
+        *c_plan.prog_host = now;
+        __threadfence_system();
+    }
+}
+// units finished by the warp whose first unit has index `first`, `per_warp` units per warp, `total` units in the launch
+__device__ __forceinline__ void mcp_report_warp(uint32_t first, uint32_t per_warp, uint32_t total) {
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0u && first < total) mcp_report_units(total - first < per_warp ? total - first : per_warp);
+}
+
 // Warp-aggregated counter add: one atomic per warp per flag.
 __device__ __forceinline__ void count_flag(unsigned int* cnt_s, unsigned long long* cnt_g, int idx, bool flag) {
     const unsigned am = __activemask();
@@ -393,6 +416,7 @@ struct SimCtx {
     double tau;            // sqrt(tau²) of the random intercept
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
+    uint32_t sim_local = 0;        // the study's index inside the launch (addresses per-wave scratch)
 };
 
 // Residuals of the four rows of Philox block `blk` from the CLASS_RESID slots (data_gen.rs:412-484); slot0 = the slot-0
@@ -454,6 +478,7 @@ struct ScenDesign {
     int residual_dist;
     int use_het;
     double beta_eff[PT];
+    double tau;         // sqrt of this study's effective tau² (base + ICC jitter, clamped at 0; data_gen.rs:1065-1075)
     int ok;
 };
 
@@ -610,6 +635,17 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
             sd.residual_dist = pl.resid_dists[q];
         }
     }
+    // ---- effective tau² of the study (data_gen.rs:1065-1075): base + N(0, icc_noise_sd²) drawn from the scenario stream AFTER
+    // the design draws above, clamped at 0
+    {
+        double tsq = pl.has_cluster ? pl.tau_squared : 0.0;
+        if (pl.has_lme && pl.icc_noise_sd > 0.0) {
+            const double jitter = (double)sr.next_normal() * pl.icc_noise_sd;
+            tsq = tsq + jitter;
+            tsq = tsq > 0.0 ? tsq : 0.0;
+        }
+        sd.tau = sqrt(tsq > 0.0 ? tsq : 0.0);
+    }
     // ---- per-study effect draw (data_gen.rs:709-751), domain-separated stream (scenarios.rs:28)
     const double het = pl.heterogeneity > 0.0 ? pl.heterogeneity : 0.0;
     sd.use_het = het > MCP_FNZ;
@@ -625,6 +661,74 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
             else if (bj > 0.0) sd.beta_eff[j] = raw > 0.0 ? raw : 0.0;
             else sd.beta_eff[j] = raw < 0.0 ? raw : 0.0;
         }
+    }
+}
+
+// Random effect of cluster c: u_c = f32(draw_residual(re_dist, re_df) · tau) (data_gen.rs:146-161, 1289-1320).  The draws sit
+// at the head of the study's sequential stream, re_words words each, so cluster c's draw is counter-addressed at c · re_words.
+static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
+    const DevicePlan& pl = c_plan;
+    const uint32_t w0 = c * (uint32_t)pl.re_words;
+    const int dist = pl.has_lme ? pl.re_dist : R_NORMAL;
+    double d;
+    if (dist == R_NORMAL) {
+        d = (double)norm_inv_from_word(cx.seq.word_at(w0));
+    } else if (dist == R_UNIFORM) {
+        d = (2.0 * (double)word_to_unit(cx.seq.word_at(w0)) - 1.0) * MCP_SQRT3;
+    } else {
+        const double df = pl.re_df > 3.0 ? pl.re_df : 3.0;
+        long long dfi = llround(df);
+        if (dfi < 1) dfi = 1;
+        const bool is_t = dist == R_HIGH_KURTOSIS;
+        const double z = is_t ? (double)norm_inv_from_word(cx.seq.word_at(w0)) : 0.0;  // sample_t draws z first (distributions.rs:78-97)
+        double chi2 = 0.0;
+        for (long long i = 0; i < dfi; i++) {
+            const double g = (double)norm_inv_from_word(cx.seq.word_at(w0 + (is_t ? 1u : 0u) + (uint32_t)i));
+            chi2 += g * g;
+        }
+        if (is_t) {
+            const double scale = 1.0 / sqrt(df / (df - 2.0));
+            const double denom = sqrt(chi2 / df);
+            d = (denom <= 0.0 ? z : z / denom) * scale;
+        } else {
+            const double centered = (chi2 - df) * (1.0 / sqrt(2.0 * df));
+            d = dist == R_LEFT_SKEWED ? -centered : centered;
+        }
+    }
+    return (double)(float)(d * cx.tau);
+}
+
+// Cluster-level predictors (data_gen.rs:605-640): on every non-representative row the marked columns take the value of the
+// cluster's representative row (FixedClusters: row i mod n_clusters; FixedSize: the cluster's first row).  The representative
+// values of a study are parked in a per-wave table in HBM; rows are generated four at a time — and by four lanes at once in the
+// quad kernels — so the stores of a block's representative rows (between_store) and the loads of its other rows (between_load)
+// are separate passes with a quad barrier between them.
+template <typename SlabT>
+static __device__ __noinline__ void between_store(const SlabT slab, int b, uint32_t sim_local) {
+    const DevicePlan& pl = c_plan;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    for (int r = 0; r < 4; r++) {
+        const int row = 4 * b + r;
+        if (row >= pl.max_n) break;
+        const int rep = pl.sizing_fixed_size ? row - row % cs : row % cs;
+        if (row != rep) continue;
+        const int c = pl.sizing_fixed_size ? row / cs : row;
+        for (int q = 0; q < pl.n_between; q++)
+            pl.between_tab[((size_t)c * pl.n_between + q) * pl.between_stride + sim_local] = slab[4 * (pl.between_cols[q] - 1) + r];
+    }
+}
+template <typename SlabT>
+static __device__ __noinline__ void between_load(const SlabT slab, int b, uint32_t sim_local) {
+    const DevicePlan& pl = c_plan;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    for (int r = 0; r < 4; r++) {
+        const int row = 4 * b + r;
+        if (row >= pl.max_n) break;
+        const int rep = pl.sizing_fixed_size ? row - row % cs : row % cs;
+        if (row == rep) continue;
+        const int c = pl.sizing_fixed_size ? row / cs : rep;
+        for (int q = 0; q < pl.n_between; q++)
+            slab[4 * (pl.between_cols[q] - 1) + r] = __ldcg(&pl.between_tab[((size_t)c * pl.n_between + q) * pl.between_stride + sim_local]);
     }
 }
 
@@ -669,8 +773,10 @@ static __device__ __noinline__ void bootstrap_block(const SlabT slab, int b, uin
 
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
+// gen_block_pre: everything up to and including the factor / bootstrap block (+ the stores of cluster-level predictors);
+// gen_block_post: the loads of cluster-level predictors and the interaction columns.  gen_block = both, for one thread per study.
 template <int PT, bool SCEN, typename SlabT>
-__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
+__device__ __forceinline__ void gen_block_pre(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
     constexpr int KT = ScenDesign<PT>::KT;
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
@@ -809,6 +915,14 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
     }
     // strict bootstrap: after the factor block, before the interactions (data_gen.rs:553-604)
     if (pl.bootstrap) bootstrap_block(slab, b, cx.seq.k0, cx.seq.k1, cx.seq_row_base);
+    if (pl.n_between > 0) between_store(slab, b, cx.sim_local);
+}
+
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ void gen_block_post(int b, const SlabT slab, SimCtx& cx) {
+    const DevicePlan& pl = c_plan;
+    const int k = pl.k;
+    if (pl.n_between > 0) between_load(slab, b, cx.sim_local);
     if (pl.n_inter > 0) {
         for (int r = 0; r < 4; r++) {
             if (4 * b + r >= pl.max_n) break;
@@ -820,6 +934,25 @@ __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, c
             }
         }
     }
+}
+
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
+    gen_block_pre<PT, SCEN>(b, slab, cx, sd);
+    gen_block_post<PT, SCEN>(b, slab, cx);
+}
+
+// Per-study generation context: Philox key, sequential stream, tau (the scenario design's when there is one), and where
+// the per-row words of the sequential stream start (behind the cluster draws).
+template <int PT>
+__device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t sim_local, const ScenDesign<PT>* sd) {
+    const DevicePlan& pl = c_plan;
+    cx.k0 = (uint32_t)key;
+    cx.k1 = (uint32_t)(key >> 32);
+    cx.seq.init(key);
+    cx.tau = !pl.has_cluster ? 0.0 : (sd ? sd->tau : sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0));
+    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words : 0u;
+    cx.sim_local = sim_local;
 }
 
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
@@ -842,7 +975,7 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
         const uint32_t cid = pl.sizing_fixed_size ? (uint32_t)(row / cs) : (uint32_t)(row % cs);
         // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
         if (cx.utab) u_re = cx.utab[cid];
-        else if (cid < (uint32_t)pl.n_clusters) u_re = (double)(float)((double)norm_inv_from_word(cx.seq.word_at(cid)) * cx.tau);
+        else if (cid < (uint32_t)pl.n_clusters) u_re = cluster_effect(cx, cid);
     }
     if (SCEN) {
         // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)
@@ -948,6 +1081,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
     unsigned int* cnt_s = nullptr;
@@ -959,12 +1093,6 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
     if (sim < n_sims) {
         const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        SimCtx cx;
-        cx.k0 = (uint32_t)key;
-        cx.k1 = (uint32_t)(key >> 32);
-        cx.seq.init(key);
-        cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
-        cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;  // Normal RE: one word per cluster
         const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
         ScenDesign<PT> sdv;
@@ -974,6 +1102,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
             sd = &sdv;
             if (!sdv.ok) atomicExch(pl.error_flag, 2);  // EngineError::CorrelationNotPSD (data_gen.rs:1049)
         }
+        SimCtx cx;
+        init_sim_ctx<PT>(cx, key, sim, sd);
 
         double acc[NACC], xty[PT];
 #pragma unroll
@@ -1035,6 +1165,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_MIN_BLOCKS) ols_power_kernel(ui
             }
         }
     }
+    mcp_report_warp((blockIdx.x * MCP_BLOCK + threadIdx.x) & ~31u, 32u, n_sims);
     if (cnt_s) {
         __syncthreads();
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
@@ -1056,12 +1187,6 @@ __global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __re
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const Slab<1> slab{slab_mem};
     const uint64_t key = pcg_mix64(base_seed, sim_id);
-    SimCtx cx;
-    cx.k0 = (uint32_t)key;
-    cx.k1 = (uint32_t)(key >> 32);
-    cx.seq.init(key);
-    cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
-    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
     const int max_n = pl.max_n;
     ScenDesign<PT> sdv;
     ScenDesign<PT>* sd = nullptr;
@@ -1070,6 +1195,8 @@ __global__ void dgp_dump_kernel(uint64_t base_seed, uint64_t sim_id, float* __re
         sd = &sdv;
         if (!sdv.ok) atomicExch(pl.error_flag, 2);
     }
+    SimCtx cx;
+    init_sim_ctx<PT>(cx, key, 0u, sd);
     for (int b = 0; b < (max_n + 3) / 4; b++) {
         gen_block<PT, SCEN>(b, slab, cx, sd);
         for (int r = 0; r < 4; r++) {

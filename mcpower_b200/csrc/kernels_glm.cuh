@@ -346,6 +346,7 @@ static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int va
 template <int PT, int MINB>
 __global__ void __launch_bounds__(MCP_BLOCK, MINB) glm_fit_kernel(uint32_t n_sims, const float* __restrict__ scratch) {
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MINB) glm_fit_kernel(uint32_t n_sim
         }
         emit_fit_glm(so, g, variant, go, all_t, excl);
     }
+    mcp_report_warp((blockIdx.x * MCP_BLOCK + threadIdx.x) & ~31u, 32u, n_sims);  // unit = one fit; the host divides by n_ss
     if (cnt_s) {
         __syncthreads();
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int N = G::N, M = G::M, MH = G::MH;
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5;
     const int q = threadIdx.x & 3;
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
             __syncwarp();
         }
     }
+    mcp_report_warp(blockIdx.x * G::STUDIES + (uint32_t)warp * 8u, 8u, n_sims);
 }
 
 // One OLS fit per thread from the statistics ols_lean_kernel left in HBM: Cholesky, β, σ², t², decisions,
@@ -313,6 +315,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_SOLVE_MIN_BLOCKS) ols_solve_ker
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int E = LeanGeom<PT>::E;
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {

@@ -373,14 +373,8 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
-    if (sim >= n_sims) return;
+    if (sim >= n_sims || mcp_cancelled()) return;
     const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-    SimCtx cx;
-    cx.k0 = (uint32_t)key;
-    cx.k1 = (uint32_t)(key >> 32);
-    cx.seq.init(key);
-    cx.tau = sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0);
-    cx.seq_row_base = (uint32_t)pl.n_clusters;
     const int max_n = pl.max_n;
     const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
     const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
@@ -402,6 +396,8 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
         scen_populate<PT>(sdv, base_seed, sim_begin + sim);
         if (!sdv.ok) atomicExch(pl.error_flag, 2);
     }
+    SimCtx cx;
+    init_sim_ctx<PT>(cx, key, sim, scen ? &sdv : nullptr);
     int g = 0;
     uint32_t n_next = pl.ss[0];
     for (int b = 0; b < (max_n + 3) >> 2; b++) {
@@ -452,6 +448,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
     using LY = LmmLayout<PT>;
     constexpr int NACC = LY::NACC;
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     unsigned int* cnt_s = nullptr;
     if (pl.smem_counters) {
@@ -523,6 +520,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
         fo.converged = conv;
         emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
     }
+    mcp_report_warp((blockIdx.x * MCP_BLOCK + threadIdx.x) & ~31u, 32u, n_sims);  // unit = one fit; the host divides by n_ss
     if (cnt_s) {
         __syncthreads();
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {

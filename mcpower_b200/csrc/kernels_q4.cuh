@@ -132,7 +132,7 @@ static __device__ __noinline__ void q4_count_levels(const Slab<MCP_BLOCK> ps, in
 template <int PT, int TAG>
 __global__ void __launch_bounds__(MCP_BLOCK) scen_design_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, ScenDesign<PT>* __restrict__ out) {
     const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
-    if (sim >= n_sims) return;
+    if (sim >= n_sims || mcp_cancelled()) return;
     ScenDesign<PT> sd;
     scen_populate<PT>(sd, base_seed, sim_begin + sim);
     if (!sd.ok) atomicExch(c_plan.error_flag, 2);  // EngineError::CorrelationNotPSD (data_gen.rs:1049)
@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
     constexpr int SP = PT | 1;
     constexpr int N = G::N, M = G::M, MH = G::MH;
     const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
     const int q = threadIdx.x & 3;
     const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
@@ -181,12 +182,6 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
     if (sim < n_sims) {
         const unsigned qmask = 0xFu << ((threadIdx.x & 31u) & ~3u);
         const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
-        SimCtx cx;
-        cx.k0 = (uint32_t)key;
-        cx.k1 = (uint32_t)(key >> 32);
-        cx.seq.init(key);
-        cx.tau = pl.has_cluster ? sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0) : 0.0;
-        cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters : 0u;
         const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
         ScenDesign<PT> sdv;
@@ -200,6 +195,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                 if (!sdv.ok) atomicExch(pl.error_flag, 2);
             }
         }
+        SimCtx cx;
+        init_sim_ctx<PT>(cx, key, sim, sd);
         double acc[G::NACCQ];
 #pragma unroll
         for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
@@ -211,8 +208,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
             const int nc_cap = clus_doubles / (PT + 1);
             double* const utab = reinterpret_cast<double*>(smem + (size_t)MCP_BLOCK * 4 * SP) + (size_t)G::STUDIES * G::STUDY +
                                  (size_t)G::STUDIES * (size_t)(clus_doubles | 1) + (size_t)(threadIdx.x >> 2) * (size_t)(nc_cap | 1);
-            for (int c = q; c < nc_cap; c += 4)
-                utab[c] = c < pl.n_clusters ? (double)(float)((double)norm_inv_from_word(cx.seq.word_at((uint32_t)c)) * cx.tau) : 0.0;
+            for (int c = q; c < nc_cap; c += 4) utab[c] = c < pl.n_clusters ? cluster_effect(cx, (uint32_t)c) : 0.0;
             cx.utab = utab;
             __syncwarp(qmask);
         }
@@ -235,7 +231,16 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         const double* const r_base = stage + (q >= 2 ? MH : 0);
         const int n_qsteps = (max_n + 15) >> 4;
         for (int sb = 0; sb < n_qsteps; sb++) {
-            if (16 * sb + 4 * q < max_n) gen_block<PT, SCEN>(4 * sb + q, slab, cx, sd);
+            {
+                const bool mine = 16 * sb + 4 * q < max_n;
+                if (pl.n_between == 0) {
+                    if (mine) gen_block<PT, SCEN>(4 * sb + q, slab, cx, sd);
+                } else {  // cluster-level predictors: the step's representative rows are stored before any lane loads one
+                    if (mine) gen_block_pre<PT, SCEN>(4 * sb + q, slab, cx, sd);
+                    __syncwarp(qmask);
+                    if (mine) gen_block_post<PT, SCEN>(4 * sb + q, slab, cx);
+                }
+            }
             __syncwarp(qmask);
 #pragma unroll 1
             for (int qq = 0; qq < 4; qq++) {
@@ -336,6 +341,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
             }
         }
     }
+    // progress is counted where the OLS arm spends its time; the GLM / mixed-model arms count finished fits in their fit kernels
+    if (!CLUS && !PLANE) mcp_report_warp(blockIdx.x * G::STUDIES + ((threadIdx.x & ~31u) >> 2), 8u, n_sims);
     if (cnt_s) {
         __syncthreads();
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {

@@ -133,6 +133,56 @@ __global__ void __launch_bounds__(256) pipe_bench_kernel(int iters, double* sink
         if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345 || (c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7) == 0x12345u ||
             (p0 ^ p1 ^ p2 ^ p3 ^ p4 ^ p5 ^ p6 ^ p7) == 0x12345ull)
             sink[0] = a0;
+    } else if (KIND == 13 || KIND == 14 || KIND == 15) {  // 13: mul.hi.u32 only, 14: mul.lo.u32 only, 15: the pair (a Philox half-round without IMAD.WIDE)
+        uint32_t c0 = t, c1 = t + 1, c2 = t + 2, c3 = t + 3, c4 = t + 4, c5 = t + 5, c6 = t + 6, c7 = t + 7;
+        for (int i = 0; i < iters; i++) {
+#define MCP_PB(c)                                                                                  \
+    {                                                                                              \
+        uint32_t h = 0u, l = 0u;                                                                   \
+        if (KIND != 14) asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(c), "r"(0xD2511F53u)); \
+        if (KIND != 13) asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(l) : "r"(c), "r"(0xD2511F53u)); \
+        c = h + l + (uint32_t)i;                                                                   \
+    }
+            MCP_PB(c0) MCP_PB(c1) MCP_PB(c2) MCP_PB(c3) MCP_PB(c4) MCP_PB(c5) MCP_PB(c6) MCP_PB(c7)
+#undef MCP_PB
+        }
+        if ((c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7) == 0x12345u) sink[0] = c0;
+    } else if (KIND == 16 || KIND == 17) {  // scalar FFMA: 16 = three register operands, 17 = immediate addend (guide: imm form issues every cycle)
+        float a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+        const float m = 0.999f;
+        float cc = KIND == 16 ? (float)(iters & 7) * 0.25f + 1.5f : 1.5f;
+        for (int i = 0; i < iters; i++) {
+            a0 = fmaf(a0, m, cc); a1 = fmaf(a1, m, cc); a2 = fmaf(a2, m, cc); a3 = fmaf(a3, m, cc);
+            a4 = fmaf(a4, m, cc); a5 = fmaf(a5, m, cc); a6 = fmaf(a6, m, cc); a7 = fmaf(a7, m, cc);
+        }
+        if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 0.12345f) sink[0] = a0;
+    } else if (KIND == 18) {  // f32 -> f64 widening with integer ops (ALU pipe) instead of F2F (XU), + DADD as in kind 3
+        float f0 = t, f1 = t + 1, f2 = t + 2, f3 = t + 3;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int i = 0; i < iters; i++) {
+#define MCP_W(f) __hiloint2double((int)(((__float_as_uint(f) >> 3) & 0x0fffffffu) + 0x38000000u) | (int)(__float_as_uint(f) & 0x80000000u), (int)(__float_as_uint(f) << 29))
+            s0 += MCP_W(f0); s1 += MCP_W(f1); s2 += MCP_W(f2); s3 += MCP_W(f3);
+#undef MCP_W
+            f0 = __int_as_float(__float_as_int(f0) + 1); f1 = __int_as_float(__float_as_int(f1) + 1);
+            f2 = __int_as_float(__float_as_int(f2) + 1); f3 = __int_as_float(__float_as_int(f3) + 1);
+        }
+        if (s0 + s1 + s2 + s3 == 0.12345) sink[0] = s0;
+    } else if (KIND == 19) {  // shared-memory pipe: LDS.128 per thread (conflict-free), 8 per iteration
+        extern __shared__ double2 pbs[];
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) pbs[i] = make_double2((double)i, 1.0);
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+        int idx = threadIdx.x;
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double2 v = pbs[(idx + 256 * u) & 2047];
+                s0 += v.x;
+                s1 += v.y;
+            }
+            idx = (idx + 1) & 2047;
+        }
+        if (s0 + s1 == 0.12345) sink[0] = s0;
     } else if (KIND == 4) {  // DADD only (baseline for KIND 3)
         double s0 = t, s1 = t + 1, s2 = t + 2, s3 = t + 3, s4 = t + 4, s5 = t + 5, s6 = t + 6, s7 = t + 7;
         const double c = 1e-9;

@@ -85,8 +85,14 @@ struct DevicePlan {
     double heterogeneity, hsk_gamma, corr_noise_sd, dist_change_prob, resid_change_prob;
     int32_t n_new_dists, new_dists[MCP_MAX_MENU];
     int32_t n_resid_dists, resid_dists[MCP_MAX_MENU];
-    int32_t has_lme, re_dist;
-    double re_df, icc_noise_sd;
+    int32_t has_lme, re_dist;          // scenario.lme (spec.rs:175): random-effect distribution (a McpRes code), ...
+    double re_df, icc_noise_sd;        // ... its df, and the sd of the per-study jitter added to tau² (data_gen.rs:1065-1075)
+    int32_t re_words;                  // sequential-stream words one random-effect draw consumes (draw_residual, data_gen.rs:1289-1320)
+    // ---- cluster-level predictors (spec.between_var_indices, data_gen.rs:605-640)
+    int32_t n_between;                 // 0 unless the spec has a cluster
+    int8_t between_cols[MCP_MAX_P];    // design columns (>= 1) broadcast from the cluster's representative row
+    float* between_tab;                // wave scratch [cluster][between column][study in wave]
+    uint32_t between_stride;           // studies per wave (the table's innermost extent)
     int32_t apply_hsk, hsk_driver;     // driver < 0 → linear predictor
     double hsk_center, hsk_inv_std, hsk_inv_norm;
     // ---- variants + thresholds
@@ -122,6 +128,11 @@ struct DevicePlan {
     int32_t counter_width;             // 4T + 6 + n_factors + 4 n_ph
     int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor, off_sing, off_fsep;  // counter-row offsets (below)
     int32_t smem_counters;             // counters staged in shared memory (fits)
+    // ---- progress / cancellation mailbox (ProgressSink, spec.rs:38-52); all NULL / 0 when no sink is attached
+    unsigned int* prog_counter;        // device counter of finished work units (OLS: studies generated; GLM / MLE: fits)
+    volatile unsigned int* prog_host;  // mapped pinned host word: the counter's value whenever it crosses a multiple of prog_step
+    uint32_t prog_step;                // work units between two published values (~1/50 of the call)
+    const int* cancel_flag;            // device int set by the host on cancellation: CTAs that have not started yet exit at once
 };
 
 // counter row layout (per sample-size index): what aggregate_batch derives

@@ -58,7 +58,7 @@ struct Spec {
     int un_rows = 0, un_cols = 0, ud_rows = 0, ud_cols = 0;
     std::vector<int> frame_map;  // bootstrap_frame_map, −1 = None; empty = not bootstrap
     bool has_slopes_or_groupings = false;
-    bool has_between = false;
+    std::vector<int> between_cols;  // between_var_indices (spec.rs:279): design columns broadcast within a cluster
     // cluster
     bool has_cluster = false;
     bool sizing_fixed_size = false;
@@ -168,7 +168,8 @@ inline Spec parse_spec(const char* json, size_t len) {
     if (nonempty("bootstrap_frame_map"))
         for (auto& v : arr(*root.get("bootstrap_frame_map"), "bootstrap_frame_map"))
             s.frame_map.push_back(v.is_null() ? -1 : to_int(v, "bootstrap_frame_map"));
-    s.has_between = nonempty("between_var_indices");
+    if (nonempty("between_var_indices"))
+        for (auto& v : arr(*root.get("between_var_indices"), "between_var_indices")) s.between_cols.push_back(to_int(v, "between_var_indices"));
     for (auto& v : arr(req(root, "factor_n_levels"), "factor_n_levels")) s.factor_n_levels.push_back(to_int(v, "factor_n_levels"));
     for (auto& v : arr(req(root, "factor_proportions"), "factor_proportions")) s.factor_proportions.push_back(num(v, "factor_proportions"));
     if (auto* p = root.get("factor_sampled"))
@@ -332,6 +333,8 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
     for (auto& dummies : s.posthoc_blocks)
         for (int ti : dummies)
             if (ti < 0 || ti >= P) invalid("posthoc target index " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
+    for (int c : s.between_cols)  // the reference indexes x_full unchecked (data_gen.rs:631-633); reject instead
+        if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("between_var_indices entry " + std::to_string(c) + " out of range");
     // uploaded-data tables: the reference indexes them unchecked (a malformed spec panics → RuntimeError); reject instead
     if (!s.frame_map.empty()) {
         if ((int)s.frame_map.size() != s.k + (int)s.factor_n_levels.size())

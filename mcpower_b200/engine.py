@@ -58,9 +58,17 @@ class Unsupported(EngineError, NotImplementedError):
 _ERRORS = {c.code: c for c in (InvalidSpec, CorrelationNotPSD, RankDeficient, Cancelled, CudaError, Unsupported)}
 
 
+_CANCEL = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
 class _Options(C.Structure):
+    """McpOptions (include/mcpower_b200.h)."""
     _fields_ = [("device", C.c_int32), ("mode", C.c_uint32), ("sim_begin", C.c_uint64), ("wave_sims", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("n_devices", C.c_int32), ("is_cancelled", _CANCEL)]
+
+
+def _options(device=-1, mode=1, sim_begin=0, wave_sims=0, n_devices=0, is_cancelled=None) -> "_Options":
+    return _Options(device, mode, sim_begin, wave_sims, n_devices, is_cancelled if is_cancelled is not None else C.cast(None, _CANCEL))
 
 
 class _Result(C.Structure):
@@ -73,7 +81,9 @@ class _Result(C.Structure):
                 ("counter_width", C.c_uint32), ("gpu_launches", C.c_uint32),
                 ("counters", C.POINTER(C.c_uint64)), ("kernel_ms", C.c_double),
                 ("n_posthoc", C.c_uint32), ("reserved", C.c_uint32),
-                ("posthoc_unc", C.POINTER(C.c_uint8)), ("posthoc_cor", C.POINTER(C.c_uint8))]
+                ("posthoc_unc", C.POINTER(C.c_uint8)), ("posthoc_cor", C.POINTER(C.c_uint8)),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_devices", C.c_uint32), ("n_waves", C.c_uint32),
+                ("lower_ms", C.c_double), ("enqueue_ms", C.c_double), ("wait_ms", C.c_double)]
 
 
 _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
@@ -81,7 +91,7 @@ _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
 EXPORTS = ("mcp_run_batch", "mcp_free_result", "mcp_generate_sim", "mcp_fit_data", "mcp_crit_table", "mcp_splitmix64",
            "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version", "mcp_find_power", "mcp_find_sample_size",
            "mcp_free_string", "mcp_fit_crossing", "mcp_build_grid", "mcp_wilson_ci", "mcp_lower_contracts",
-           "mcp_find_power_contracts", "mcp_find_sample_size_contracts")
+           "mcp_find_power_contracts", "mcp_find_sample_size_contracts", "mcp_test_force_ols_variant")
 
 
 class _CrossingFit(C.Structure):
@@ -147,6 +157,8 @@ def lib():
     L.mcp_wilson_ci.restype = None
     L.mcp_wilson_ci.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mcp_device_count.restype = C.c_int
+    L.mcp_test_force_ols_variant.restype = C.c_int
+    L.mcp_test_force_ols_variant.argtypes = [C.c_int]
     L.mcp_last_error.restype = C.c_char_p
     L.mcp_version.restype = C.c_char_p
     _lib = L
@@ -184,6 +196,13 @@ class BatchResult:
     posthoc_cor: Optional[np.ndarray] = None
     kernel_ms: float = 0.0
     gpu_launches: int = 0
+    h2d_bytes: int = 0                         # bytes the call copied host → device (plan + tables, every device)
+    d2h_bytes: int = 0                         # bytes the call copied device → host (counters, byte tensors, capture)
+    n_devices: int = 1
+    n_waves: int = 1
+    lower_ms: float = 0.0                      # host: validation + lowering
+    enqueue_ms: float = 0.0                    # host: allocation + enqueueing uploads / launches / copies on every device
+    wait_ms: float = 0.0                       # host: waiting for the devices (kernels + copies)
     extras: dict = field(default_factory=dict)
 
     # ---- views of the counter rows (what aggregate_batch derives, aggregation.rs:91-242)
@@ -299,18 +318,27 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
 ProgressSink = Callable[[int, int], bool]
 
 
+def force_ols_variant(variant: int) -> int:
+    """Test hook: pin the OLS power kernel (1 thread per study, 4 lane quad solving by call, 5 lean pair, 6 split pair;
+    0 = the library's own choice).  Process-wide; returns the previous setting.  The cross-check kernels compute the
+    same bits — tests/test_gpu_parity.py runs every OLS case under each."""
+    return int(lib().mcp_test_force_ols_variant(int(variant)))
+
+
 def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: int,
               sink: Optional[ProgressSink] = None, *, mode: int = MODE_COUNTS, device: int = -1, sim_begin: int = 0,
-              wave_sims: int = 0) -> BatchResult:
+              wave_sims: int = 0, n_devices: int = 0, is_cancelled: Optional[Callable[[], bool]] = None) -> BatchResult:
     """engine_core::run_batch on the GPU. `sink(current, total) -> bool` mirrors ProgressSink::report
-    (return False to cancel → raises Cancelled, partial results discarded, batch.rs:128-129)."""
+    (return False to cancel → raises Cancelled, partial results discarded, batch.rs:128-129); `is_cancelled() -> bool`
+    mirrors ProgressSink::is_cancelled.  n_devices > 1 (or -1 = all) shards the sims over several GPUs inside the call."""
     L = lib()
     blob = json.dumps(spec).encode()
     ss = np.ascontiguousarray(np.asarray(list(sample_sizes), dtype=np.int64))
     if ss.size and (ss.min() < 0 or ss.max() > 0xFFFFFFFF):
         raise InvalidSpec("invalid spec: sample sizes must fit u32")
     ss32 = ss.astype(np.uint32)
-    opt = _Options(device, mode, sim_begin, wave_sims, 0)
+    ccb = _CANCEL(lambda _u: 1 if is_cancelled() else 0) if is_cancelled else None
+    opt = _options(device, mode, sim_begin, wave_sims, n_devices, ccb)
     out = C.POINTER(_Result)()
     cb = _PROGRESS(lambda cur, tot, _u: 1 if sink(int(cur), int(tot)) else 0) if sink else C.cast(None, _PROGRESS)
     rc = L.mcp_run_batch(blob, len(blob), ss32.ctypes.data_as(C.POINTER(C.c_uint32)), ss32.size, int(n_sims),
@@ -343,7 +371,9 @@ def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: i
             joint=take(r.joint, (r.n_sims, n_ss), np.uint8),
             boundary_hit=take(r.boundary_hit, (r.n_sims, n_ss), np.uint8),
             t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),
-            kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches))
+            kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches), h2d_bytes=int(r.h2d_bytes),
+            d2h_bytes=int(r.d2h_bytes), n_devices=int(r.n_devices), n_waves=int(r.n_waves), lower_ms=float(r.lower_ms),
+            enqueue_ms=float(r.enqueue_ms), wait_ms=float(r.wait_ms))
     finally:
         L.mcp_free_result(out)
     return res
@@ -424,7 +454,7 @@ def find_power(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: 
     (field names of engine-orchestrator/src/result.rs:54-144)."""
     blob = json.dumps(spec).encode()
     ss32 = np.ascontiguousarray(np.asarray(list(sample_sizes), dtype=np.uint32))
-    opt = _Options(device, mode, sim_begin, 0, 0)
+    opt = _options(device, mode, sim_begin)
     out = C.c_void_p()
     rc = lib().mcp_find_power(blob, len(blob), ss32.ctypes.data_as(C.POINTER(C.c_uint32)), ss32.size, int(n_sims),
                               base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
@@ -438,7 +468,7 @@ def find_sample_size(spec: dict, from_size: int, to_size: int, n_sims: int, base
     """find_sample_size for one scenario (find_sample_size.rs:83-257): `by` = fixed step (linear) / point count (log);
     by=None → ~`count` auto-placed points.  Returns the SampleSizeResult dict."""
     blob = json.dumps(spec).encode()
-    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    opt = _options(device, MODE_COUNTS)
     out = C.c_void_p()
     rc = lib().mcp_find_sample_size(blob, len(blob), int(from_size), int(to_size), int(count if by is None else by),
                                     1 if by is None else 0, 1 if log_grid else 0, float(target_power), int(n_sims),
@@ -470,7 +500,7 @@ def lower_contracts(contracts) -> list:
 def find_power_contracts(contracts, sample_size: int, n_sims: int, user_seed: int = 2137, *, device: int = -1) -> dict:
     """find_power (find_power.rs:301-392) on the hosts' contract payload → {"scenarios": [[label, PowerResult], ...]}."""
     blob, fmt = _contract_payload(contracts)
-    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    opt = _options(device, MODE_COUNTS)
     out = C.c_void_p()
     rc = lib().mcp_find_power_contracts(blob, len(blob), fmt, int(sample_size), int(n_sims), user_seed & 0xFFFFFFFFFFFFFFFF,
                                         C.byref(opt), C.cast(None, _PROGRESS), None, C.byref(out))
@@ -485,7 +515,7 @@ def find_sample_size_contracts(contracts, from_size: int, to_size: int, n_sims: 
     """find_sample_size (find_sample_size.rs:83-257) on the hosts' contract payload →
     {"scenarios": [[label, SampleSizeResult], ...]}."""
     blob, fmt = _contract_payload(contracts)
-    opt = _Options(device, MODE_COUNTS, 0, 0, 0)
+    opt = _options(device, MODE_COUNTS)
     out = C.c_void_p()
     rc = lib().mcp_find_sample_size_contracts(blob, len(blob), fmt, int(from_size), int(to_size), int(count if by is None else by),
                                               1 if by is None else 0, 1 if log_grid else 0, float(target_power), int(n_sims),

@@ -13,8 +13,10 @@ import math
 _MENUS = (["right_skewed", "left_skewed", "uniform"], ["high_kurtosis", "right_skewed"])
 
 
-def scenario(name: str = "optimistic") -> dict:
-    """Scenario presets (configs/scenarios.json as frozen in throughput.rs:77-133)."""
+def scenario(name: str = "optimistic", mixed: bool = False) -> dict:
+    """Scenario presets (configs/scenarios.json; frozen copies in throughput.rs:77-133).  `mixed=True` is a model with random
+    effects: the hosts then carry the preset's random-effect knobs as the `lme` block (heavy-tailed = the t kernel,
+    project_contract.rs:922-980); for every other model they zero them, so `lme` stays None (spec_builder.py:246-253)."""
     base = {
         "name": name,
         "heterogeneity": 0.0,
@@ -35,11 +37,15 @@ def scenario(name: str = "optimistic") -> dict:
         base.update(heterogeneity=0.2, heteroskedasticity_ratio=2.0, correlation_noise_sd=0.15,
                     distribution_change_prob=0.5, residual_change_prob=0.5, residual_df=8.0,
                     sampled_factor_proportions=True, truth_start=False)
+        if mixed:
+            base["lme"] = {"random_effect_dist": "high_kurtosis", "random_effect_df": 10.0, "icc_noise_sd": 0.15}
         return base
     if name == "doomer":
         base.update(heterogeneity=0.4, heteroskedasticity_ratio=4.0, correlation_noise_sd=0.3,
                     distribution_change_prob=0.8, residual_change_prob=0.8, residual_df=5.0,
                     sampled_factor_proportions=True, truth_start=False)
+        if mixed:
+            base["lme"] = {"random_effect_dist": "high_kurtosis", "random_effect_df": 5.0, "icc_noise_sd": 0.3}
         return base
     raise ValueError(f"unknown scenario preset {name!r}")
 
@@ -164,10 +170,12 @@ def logit_spec(baseline_p: float = 0.3) -> dict:
     return s
 
 
-def lmm_spec(n_clusters: int = 30, icc: float = 0.2) -> dict:
+def lmm_spec(n_clusters: int = 30, icc: float = 0.2, preset: str = "optimistic") -> dict:
     """BASELINE config 5: linear mixed model with a random intercept, `n_clusters` clusters (round-robin rows),
-    REML fit, y ~ x1 + x2 + (1 | cluster); tau² = ICC / (1 − ICC) with unit residual variance."""
+    REML fit, y ~ x1 + x2 + (1 | cluster); tau² = ICC / (1 − ICC) with unit residual variance.  `preset` = the scenario
+    preset with the mixed-model knobs (heavy-tailed random effects, ICC jitter) attached."""
     s = base_spec(2)
+    s["scenario"] = scenario(preset, mixed=True)
     s["effect_sizes"] = [0.0, 0.3, 0.2]
     s["target_indices"] = [1, 2]
     s["estimator"] = "mle"

@@ -1399,6 +1399,15 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
                 start += nd;
             }
         }
+        /* (b.45) cluster-level broadcast (data_gen.rs:605-640): after the factor / bootstrap block, before the interactions;
+         * the representative row precedes row i in both layouts, so its value is final and resident */
+        if (s->n_between > 0 && s->has_cluster) {
+            const int sv = s->sizing_value > 0 ? s->sizing_value : 1;
+            const int rep = s->sizing_fixed_size ? i - (i % sv) : i % sv;
+            if (i != rep)
+                for (int b = 0; b < s->n_between; b++)
+                    w->x[(size_t)s->between_cols[b] * max_n + i] = w->x[(size_t)s->between_cols[b] * max_n + rep];
+        }
         for (int j = 0; j < s->n_interactions; j++) {
             double prod = 1.0;
             for (int c = s->inter_ptr[j]; c < s->inter_ptr[j + 1]; c++) prod *= (double)w->x[(size_t)s->inter_cols[c] * max_n + i];
@@ -1498,6 +1507,9 @@ static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* ba
     for (int c = 0; c < 2 * s->n_contrasts; c++)
         if (s->contrast_pairs[c] < 0 || s->contrast_pairs[c] >= P) return fail(ORC_ERR_INVALID_SPEC, "contrast_pairs entry out of range");
     int k = s->n_non_factor;
+    for (int b = 0; b < s->n_between; b++) /* the reference indexes x_full unchecked (a malformed spec panics); the backends reject it */
+        if (s->between_cols[b] < 1 || s->between_cols[b] >= 1 + s->n_non_factor + s->n_factor_dummies)
+            return fail(ORC_ERR_INVALID_SPEC, "between_var_indices entry out of range");
     /* uploaded-data tables: the reference indexes them unchecked (a malformed spec panics); the backends reject it */
     if (s->n_frame_map > 0) {
         if (s->n_frame_map != k + s->n_factors) return fail(ORC_ERR_INVALID_SPEC, "bootstrap_frame_map length must equal n_non_factor + n_factors");

@@ -89,6 +89,10 @@ typedef struct {
     int32_t n_frame_map;
     const int32_t* frame_map;
     int32_t n_var_params;                   /* entries of var_params the spec really carried (bootstrap binary: unwrap_or(0.0)) */
+    /* cluster-level predictors (spec.between_var_indices, data_gen.rs:605-640): design columns whose value on every row of a
+     * cluster is the value on the cluster's representative (first) row */
+    int32_t n_between;
+    const int32_t* between_cols;
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */

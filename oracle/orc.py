@@ -61,6 +61,7 @@ class OrcSpec(C.Structure):
         ("upload_data", C.POINTER(C.c_double)), ("ud_rows", C.c_int32), ("ud_cols", C.c_int32),
         ("n_frame_map", C.c_int32), ("frame_map", C.POINTER(C.c_int32)),
         ("n_var_params", C.c_int32),
+        ("n_between", C.c_int32), ("between_cols", C.POINTER(C.c_int32)),
     ]
 
 
@@ -178,6 +179,9 @@ class PackedSpec:
         s.n_frame_map = len(fm)
         s.frame_map = _ptr(arr([-1 if v is None else int(v) for v in fm], np.int32), C.c_int32)
         s.var_params = _ptr(arr(vp, np.float64), C.c_double)
+        bv = [int(v) for v in (spec.get("between_var_indices", []) or [])]
+        s.n_between = len(bv)
+        s.between_cols = _ptr(arr(bv, np.int32), C.c_int32)
         s.factor_n_levels = _ptr(arr(levels, np.int32), C.c_int32)
         s.factor_proportions = _ptr(arr(spec.get("factor_proportions", []), np.float64), C.c_double)
         fs = list(spec.get("factor_sampled", []) or [])

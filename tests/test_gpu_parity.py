@@ -28,11 +28,12 @@ _NOT_OLS_POWER = ("cross_lme", "cross_glm", "generated_design", "marginal_transf
 
 
 @pytest.fixture(autouse=True, params=["thread", "quad", "lean", "split"])
-def ols_kernel_choice(request, monkeypatch):
+def ols_kernel_choice(request):
     if request.param != "thread" and any(t in request.node.name for t in _NOT_OLS_POWER):
         pytest.skip("does not reach the OLS power kernel")
-    monkeypatch.setenv("MCPOWER_B200_OLS_VARIANT", {"thread": "1", "quad": "4", "lean": "5", "split": "6"}[request.param])
-    return request.param
+    previous = M.force_ols_variant({"thread": 1, "quad": 4, "lean": 5, "split": 6}[request.param])
+    yield request.param
+    M.force_ols_variant(previous)
 
 
 def assert_batch_equal(got: M.BatchResult, want: dict):
@@ -441,7 +442,10 @@ def test_progress_and_cancel():
     s = S.headline_spec()
     seen = []
     M.run_batch(s, [100], 5000, SEED, lambda cur, tot: seen.append((cur, tot)) or True)
-    assert seen[-1] == (5000, 5000) and 40 <= len(seen) <= 55
+    # the kernels publish ~50 progress values per call; the waiting host thread reports the ones it sees (a 0.1 ms batch is
+    # over before most of them), always ending with (n, n) — tests/test_gpu_hostpath.py covers the long-running case
+    assert seen[-1] == (5000, 5000) and 1 <= len(seen) <= 51
+    assert [c for c, _ in seen] == sorted({c for c, _ in seen})
     with pytest.raises(M.Cancelled):
         M.run_batch(s, [100], 5000, SEED, lambda cur, tot: cur < 1000)
 

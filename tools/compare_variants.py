@@ -1,7 +1,6 @@
 #!/usr/bin/env python3
-"""Device-time fits/s of one OLS workload under each forced kernel variant (MCPOWER_B200_OLS_VARIANT):
+"""Device-time fits/s of one OLS workload under each forced kernel variant (mcpower_b200.force_ols_variant):
 usage compare_variants.py c1|c2|c3|c3r|hl [n_sims] [variants, e.g. 1,4,6]."""
-import os
 import sys
 from pathlib import Path
 
@@ -29,7 +28,7 @@ else:
     spec, grid = S.headline_spec(), [500]
 ref = None
 for v in variants:
-    os.environ["MCPOWER_B200_OLS_VARIANT"] = v
+    M.force_ols_variant(int(v))
     M.run_batch(spec, grid, 4096, seed)
     best = None
     for _ in range(3):

@@ -8,7 +8,12 @@ from collections import Counter
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
 ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-ins = rows[2:]
+ins = []
+for r in rows[2:]:  # a multi-launch export repeats the header rows: keep the first launch
+    if r and r[0] == "Kernel Name":
+        break
+    if len(r) == len(hdr):
+        ins.append(r)
 tot = sum(int(r[iex]) for r in ins)
 ops = Counter()
 for r in ins:
