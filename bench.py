@@ -278,7 +278,7 @@ def main():
                                          "comes from a device counter published to mapped host memory, the batch is not split"},
                 "e2e_bytes": {"value": total_fits / bytes_wall, "unit": "fits/s", "ms_per_step": 1e3 * bytes_wall / args.steps,
                               "h2d_bytes_per_step": int(r_bytes.h2d_bytes), "d2h_bytes_per_step": int(r_bytes.d2h_bytes),
-                              "waves_per_call": int(r_bytes.n_waves),
+                              "waves_per_call": int(r_bytes.n_waves), "kernel_ms_per_call": r_bytes.kernel_ms,
                               "note": "BYTES | COUNTS with the sink attached: the sim-major BatchResult tensors land in page-locked "
                                       "host memory, each wave's copy overlapping the next wave's kernels"},
                 "host_ms_per_call": {"lower": r_e2e.lower_ms, "enqueue": r_e2e.enqueue_ms, "wait": r_e2e.wait_ms},
@@ -304,7 +304,7 @@ def main():
             # the same batch sharded over every visible GPU INSIDE one library call (McpOptions.n_devices): strong scaling of
             # one run_batch, counters summed by the library
             nd = M.device_count()
-            M.run_batch(spec, [N_ROWS], per, seed, device=0, n_devices=nd)
+            M.run_batch(spec, [N_ROWS], per * nd, seed, device=0, n_devices=nd)
             tt = time.perf_counter()
             rm = M.run_batch(spec, [N_ROWS], per * nd, seed, device=0, n_devices=nd)
             tw = time.perf_counter() - tt
@@ -332,6 +332,7 @@ def main():
                                  "e2e_progress_fits_per_s": n2 * len(grid) / c2_wall, "e2e_progress_ms": 1e3 * c2_wall,
                                  "e2e_bytes_fits_per_s": n2 * len(grid) / c2_bytes_wall, "e2e_bytes_ms": 1e3 * c2_bytes_wall,
                                  "bytes_d2h": int(rb.d2h_bytes), "bytes_waves": int(rb.n_waves), "kernel_ms": rs.kernel_ms,
+                                 "bytes_kernel_ms": rb.kernel_ms,
                                  "lower_ms": rs.lower_ms}
             # the other BASELINE configs (device time, one GPU): robustness scenario sweep, logistic GLM power curve,
             # random-intercept mixed model — the split path's kernels

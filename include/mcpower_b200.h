@@ -165,6 +165,28 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
  * f32 first, like the reference), n × p.  out = beta[p], se[p], t_sq[p], sigma_sq, sst, rss, converged. */
 int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t p, int32_t device, double* out);
 
+/* introspect::fit_provided_data twin WITH the spec (introspect.rs:174-562): the supplied dataset goes through the shipped fit
+ * code of spec.estimator — OLS (sufficient statistics + Cholesky), unclustered GLM (the IRLS of the power kernel, truth start
+ * beta0 = effect_sizes), Gaussian random-intercept MLE (cluster sufficient statistics + profiled REML) — and comes back as
+ * IntrospectResults: betas per design column, se and the natural (unsquared) statistic per target (spec.target_indices), the
+ * squared uncorrected threshold and df_resid = N - n_predictors.  design = column-major f64 nrow x ncol (narrowed to the f32
+ * data plane first, like the reference); cluster_ids may be NULL (= the spec's sizing) and must otherwise equal it. */
+typedef struct McpFitInfo {
+    int32_t converged;
+    int32_t boundary_hit;        /* MLE: 0 none, 1 tau-hat = 0, 2 upper bound; else 0 */
+    int32_t iterations;          /* GLM: IRLS passes; else 0 */
+    int32_t n_targets;
+    double crit_sq_uncorrected;  /* t_crit_sq_uncorrected[0] (t for OLS, z for GLM / MLE) */
+    double df_resid;
+    double sigma_sq_hat;         /* OLS: residual variance; MLE: sigma²-hat at theta-hat; GLM: NaN */
+    double tau_sq_hat;           /* MLE: the variance component theta² sigma²; else NaN */
+    double deviance;             /* GLM; else NaN */
+    double deviance_null;        /* GLM; else NaN */
+} McpFitInfo;
+int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* design_colmajor, uint32_t nrow, uint32_t ncol,
+                          const double* outcome, const uint32_t* cluster_ids, int32_t device, double* betas /* [ncol] */,
+                          double* se /* [n_targets] */, double* statistic /* [n_targets] */, McpFitInfo* info);
+
 /* CritValueTable::build_with_tukey_k twin (critvals.rs:827-1012; host f64).
  * t_unc_sq[n_ss], corr_sq[n_ss*T], posthoc_sq[n_ss], overall[n_ss]; any pointer may be NULL. */
 int mcp_crit_table(const char* spec_json, size_t spec_len, const uint32_t* sample_sizes, uint32_t n_sample_sizes,

@@ -8,5 +8,5 @@ from . import spec  # noqa: F401
 from .engine import (MODE_BYTES, MODE_CAPTURE, MODE_COUNTS, BatchResult, Cancelled, CorrelationNotPSD,  # noqa: F401
                      CudaError, EngineError, InvalidSpec, RankDeficient, Unsupported, counters_from_bytes, crit_table,
                      build_grid, device_count, find_power, find_power_contracts, find_sample_size,
-                     find_sample_size_contracts, fit_crossing, fit_data, force_ols_variant, generate_sim, lower_contracts,
+                     find_sample_size_contracts, fit_crossing, fit_data, fit_provided_data, force_ols_variant, generate_sim, lower_contracts,
                      pipe_bench, run_batch, splitmix64, wilson_ci)

@@ -1329,6 +1329,8 @@ static std::vector<orch::PowerResult> power_results_from(const Spec& s, const Mc
     return out;
 }
 
+static std::vector<std::string> factor_preflight_warnings(const Spec& s, uint64_t n);
+
 static char* dup_json(const std::string& s) {
     char* p = static_cast<char*>(std::malloc(s.size() + 1));
     std::memcpy(p, s.c_str(), s.size() + 1);
@@ -1340,14 +1342,16 @@ static char* dup_json(const std::string& s) {
 // scenario came from a contract, find_power.rs:353-358; the spec's own indices otherwise).
 static std::string find_power_json(const Spec& s, const Spec& report, const uint32_t* sample_sizes, uint32_t n_ss, uint32_t n_sims,
                                    uint64_t base_seed, const McpOptions* options, McpProgressFn progress, void* user,
-                                   const std::vector<std::string>& warnings = {}) {
-    McpBatchResult* r = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user);
+                                   const std::vector<std::string>& warnings = {}, uint64_t progress_offset = 0, uint64_t progress_total = 0) {
+    McpBatchResult* r = run_batch_core(s, sample_sizes, n_ss, n_sims, base_seed, options, progress, user, progress_offset, progress_total);
     struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
     std::vector<orch::PowerResult> per_n = power_results_from(report, r, sample_sizes);
     std::string o = "[";
     for (size_t i = 0; i < per_n.size(); i++) {
         if (i) o += ',';
         per_n[i].grid_warnings.insert(per_n[i].grid_warnings.end(), warnings.begin(), warnings.end());
+        // pre-run sparse-factor advisory (find_power.rs:364-368; fixed-allocation factors only)
+        for (auto& w : factor_preflight_warnings(s, sample_sizes[i])) per_n[i].grid_warnings.push_back(w);
         orch::power_result_json(o, per_n[i]);
     }
     o += ']';
@@ -1364,40 +1368,136 @@ int mcp_find_power(const char* spec_json, size_t spec_len, const uint32_t* sampl
     });
 }
 
-// resolve_cluster_grid_params (find_sample_size.rs:24-79); limits from configs/config.json:27-28
-static void cluster_grid_params(const Spec& s, uint64_t& atom, uint64_t& hard_min, std::vector<std::string>& warnings) {
+// resolve_cluster_grid_params (find_sample_size.rs:24-79) over ALL scenarios of a call: one shared atom (scenarios that
+// disagree are an error, OrchestratorError::MixedClusterAtoms), grid floor and pre-grid warnings from the first clustered
+// scenario; limits from configs/config.json:27-28.
+static void cluster_grid_params(const std::vector<const Spec*>& specs, uint64_t& atom, uint64_t& hard_min, std::vector<std::string>& warnings) {
     const uint64_t min_rows = 2, min_clusters = 5;
     atom = 1;
     hard_min = 1;
-    if (!s.has_cluster) return;
-    const uint64_t v = (uint64_t)std::max(s.sizing_value, 1);
+    const Spec* cl = nullptr;
+    for (const Spec* s : specs) {
+        if (!s->has_cluster) continue;
+        const uint64_t a = (uint64_t)std::max(s->sizing_value, 1);
+        if (!cl) cl = s;
+        else if ((uint64_t)std::max(cl->sizing_value, 1) != a)
+            invalid("scenarios in this call disagree on the cluster atom (" + std::to_string(std::max(cl->sizing_value, 1)) + " vs " + std::to_string(a) +
+                    "); a single shared grid cannot be a multiple of every atom");
+    }
+    if (!cl) return;
+    const uint64_t v = (uint64_t)std::max(cl->sizing_value, 1);
     atom = v;
-    if (!s.sizing_fixed_size) {
+    if (!cl->sizing_fixed_size) {
         if (v < min_clusters) warnings.push_back("only " + std::to_string(v) + " clusters (< " + std::to_string(min_clusters) + "); τ² estimates may be unstable");
         hard_min = v * min_rows;
     } else {
-        if (v < min_rows) invalid("cluster_size " + std::to_string(v) + " is below the minimum rows per cluster " + std::to_string(min_rows));
+        if (v < min_rows)
+            invalid("FixedSize cluster regime needs cluster_size >= " + std::to_string(min_rows) + " (no within-cluster information below that); got " +
+                    std::to_string(v));
         hard_min = min_clusters * v;
     }
 }
 
-// find_sample_size for one lowered scenario (find_sample_size.rs:83-257): cluster-aware grid, one run_batch over the whole
-// grid (nested row prefixes of the same studies), per-N PowerResult fold, grid-empirical first-N and model-based
-// crossing fits per target / per joint count / for the overall test.  JSON object = SampleSizeResult.
-static std::string find_sample_size_json(const Spec& s, const Spec& report, uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto,
-                                         int32_t log_grid, double target_power, uint32_t n_sims, uint64_t base_seed,
-                                         const McpOptions* options, McpProgressFn progress, void* user) {
-    uint64_t atom = 1, hard_min = 1;
-    std::vector<std::string> warnings;
-    cluster_grid_params(s, atom, hard_min, warnings);
+// Level counts of the deterministic largest-remainder walk after n rows (fixed_allocation_counts, data_gen.rs:966-972).
+static std::vector<uint32_t> fixed_allocation_counts(const double* probs, int nl, uint64_t n) {
+    std::vector<uint32_t> counts(nl, 0);
+    if (n == 0) return counts;
+    const std::vector<uint8_t> lv = exact_walk_levels(probs, nl, (int)std::min<uint64_t>(n, 0x7fffffffu));
+    for (uint8_t l : lv) counts[l]++;
+    return counts;
+}
+
+static bool factor_is_sampled(const Spec& s, size_t f) {
+    const int fs = f < s.factor_sampled.size() ? s.factor_sampled[f] : -1;
+    return fs < 0 ? s.sampled_factor_proportions : fs != 0;
+}
+
+// factor_preflight_warnings (find_power.rs:67-116): fixed-allocation factors whose sparsest level stays under the minimum at n.
+static std::vector<std::string> factor_preflight_warnings(const Spec& s, uint64_t n) {
+    std::vector<std::string> out;
+    const uint32_t k_min = (uint32_t)std::max(s.min_level_count, 0);
+    if (k_min == 0 || !s.upload_data.empty()) return out;
+    size_t off = 0;
+    for (size_t f = 0; f < s.factor_n_levels.size(); f++) {
+        const int l = std::max(s.factor_n_levels[f], 0);
+        if (!factor_is_sampled(s, f) && l > 0) {
+            const std::vector<uint32_t> counts = fixed_allocation_counts(s.factor_proportions.data() + off, l, n);
+            size_t lvl = 0;
+            for (size_t i = 1; i < counts.size(); i++)
+                if (counts[i] < counts[lvl]) lvl = i;  // min_by_key: the first minimum
+            if (counts[lvl] < k_min)
+                out.push_back("factor " + std::to_string(f + 1) + ": level " + std::to_string(lvl + 1) + " receives " + std::to_string(counts[lvl]) + " of " +
+                              std::to_string(n) + " observations (minimum " + std::to_string(k_min) + "); the factor is excluded from every simulation at N=" +
+                              std::to_string(n) + " and its effects report power 0 — increase N or this level's proportion");
+        }
+        off += (size_t)l;
+    }
+    return out;
+}
+
+// factor_preflight_sample_size (find_power.rs:122-170): factors sparse at the grid's lower bound, and the N at which they clear it.
+static std::vector<std::string> factor_preflight_sample_size(const Spec& s, const std::vector<uint64_t>& grid) {
+    std::vector<std::string> out;
+    const uint32_t k_min = (uint32_t)std::max(s.min_level_count, 0);
+    if (grid.empty() || k_min == 0 || !s.upload_data.empty()) return out;
+    const uint64_t lo = grid.front(), hi = grid.back();
+    size_t off = 0;
+    for (size_t f = 0; f < s.factor_n_levels.size(); f++) {
+        const int l = std::max(s.factor_n_levels[f], 0);
+        if (!factor_is_sampled(s, f) && l > 0) {
+            const double* probs = s.factor_proportions.data() + off;
+            const std::vector<uint32_t> at_lo = fixed_allocation_counts(probs, l, lo);
+            if (std::any_of(at_lo.begin(), at_lo.end(), [&](uint32_t c) { return c < k_min; })) {
+                // min_inclusion_n (data_gen.rs:977-986): one forward walk up to the grid ceiling
+                const std::vector<uint8_t> lv = exact_walk_levels(probs, l, (int)std::min<uint64_t>(hi, 0x7fffffffu));
+                std::vector<uint32_t> run(l, 0);
+                uint64_t n_inc = 0;
+                for (size_t i = 0; i < lv.size() && !n_inc; i++) {
+                    run[lv[i]]++;
+                    if (std::all_of(run.begin(), run.end(), [&](uint32_t c) { return c >= k_min; })) n_inc = i + 1;
+                }
+                if (n_inc)
+                    out.push_back("factor " + std::to_string(f + 1) + ": levels reach the " + std::to_string(k_min) + "-observation minimum only at N >= " +
+                                  std::to_string(n_inc) + "; grid points below that exclude the factor and report power 0 for its effects");
+                else
+                    out.push_back("factor " + std::to_string(f + 1) + ": a level stays under the " + std::to_string(k_min) +
+                                  "-observation minimum across the whole [" + std::to_string(lo) + ", " + std::to_string(hi) +
+                                  "] range; the factor is excluded everywhere and its effects report power 0");
+            }
+        }
+        off += (size_t)l;
+    }
+    return out;
+}
+
+// The shared N grid of a find_sample_size call (find_sample_size.rs:99-107): cluster guards over every scenario, then build_grid.
+static std::vector<uint64_t> shared_grid(const std::vector<const Spec*>& specs, uint64_t from_size, uint64_t to_size, uint64_t by, int32_t by_auto,
+                                         int32_t log_grid, uint64_t& atom, std::vector<std::string>& warnings) {
+    uint64_t hard_min = 1;
+    cluster_grid_params(specs, atom, hard_min, warnings);
     std::vector<uint64_t> grid;
     const orch::GridError ge = orch::build_grid(from_size, to_size, by, by_auto != 0, log_grid != 0, atom, hard_min, grid, warnings);
     if (ge == orch::GRID_INVALID_BOUNDS) invalid("sample-size bounds: need 1 <= from <= to");
     if (ge == orch::GRID_EMPTY) invalid("no multiple of the cluster atom lies inside the sample-size bounds");
     if (ge == orch::GRID_SINGLE_POINT) invalid("the sample-size bounds leave a single grid point after cluster snapping");
     if (ge != orch::GRID_OK) invalid("cluster atom must be positive");
+    if (grid.size() > 65535) invalid("the sample-size grid has " + std::to_string(grid.size()) + " points (at most 65535 per call)");
+    if (grid.back() > 0xffffffffull) invalid("sample sizes above 2^32 - 1 are not supported");
+    return grid;
+}
+
+// find_sample_size for one lowered scenario (find_sample_size.rs:83-257): cluster-aware grid, one run_batch over the whole
+// grid (nested row prefixes of the same studies), per-N PowerResult fold, grid-empirical first-N and model-based
+// crossing fits per target / per joint count / for the overall test.  JSON object = SampleSizeResult.
+static std::string find_sample_size_json(const Spec& s, const Spec& report, const std::vector<uint64_t>& grid, uint64_t atom,
+                                         std::vector<std::string> warnings, double target_power, uint32_t n_sims, uint64_t base_seed,
+                                         const McpOptions* options, McpProgressFn progress, void* user, uint64_t progress_offset = 0,
+                                         uint64_t progress_total = 0) {
+    // per-scenario preflight: the allocation mode is a scenario knob, the grid is shared (find_sample_size.rs:142-146)
+    for (auto& w : factor_preflight_sample_size(s, grid)) warnings.push_back(w);
     std::vector<uint32_t> ss(grid.begin(), grid.end());
-    McpBatchResult* r = run_batch_core(s, ss.data(), (uint32_t)ss.size(), n_sims, base_seed, options, progress, user);
+    McpBatchResult* r = run_batch_core(s, ss.data(), (uint32_t)ss.size(), n_sims, base_seed, options, progress, user, progress_offset,
+                                       progress_total);
     struct Free { McpBatchResult* r; ~Free() { mcp_free_result(r); } } fr{r};
     const std::vector<orch::PowerResult> per_n = power_results_from(report, r, ss.data());
     const orch::SampleSizeDerivations d = orch::derive_sample_size_outputs(per_n, grid, target_power, atom);
@@ -1436,8 +1536,10 @@ int mcp_find_sample_size(const char* spec_json, size_t spec_len, uint64_t from_s
         if (!json_out) invalid("json_out pointer is NULL");
         *json_out = nullptr;
         Spec s = parse_spec(spec_json, spec_len);
-        *json_out = dup_json(find_sample_size_json(s, s, from_size, to_size, by, by_auto, log_grid, target_power, n_sims, base_seed, options,
-                                                   progress, user));
+        uint64_t atom = 1;
+        std::vector<std::string> warnings;
+        const std::vector<uint64_t> grid = shared_grid({&s}, from_size, to_size, by, by_auto, log_grid, atom, warnings);
+        *json_out = dup_json(find_sample_size_json(s, s, grid, atom, warnings, target_power, n_sims, base_seed, options, progress, user));
     });
 }
 
@@ -1463,13 +1565,11 @@ static std::vector<LoweredScenario> lower_contracts(const uint8_t* bytes, size_t
         try {
             const contract::Contract c = contract::parse_contract(raw[idx]);
             if (const JsonValue* nm = c.scenario.get("name")) sc.label = nm->str;
-            sc.low = contract::lower_contract(c);
+            sc.low = contract::lower_contract(c, /*factor_min_level_count: limits.factor_min_level_count*/ 5);
         } catch (const EngineError& e) {
             throw EngineError(e.code, "invalid scenarios input: contract " + std::to_string(idx) + " (\"" + sc.label + "\"): " + e.what());
         }
-        // single source: limits.factor_min_level_count
-        const std::string key = "\"factor_min_level_count\":0}";
-        sc.spec_json = sc.low.spec_json.substr(0, sc.low.spec_json.size() - key.size()) + "\"factor_min_level_count\":5}";
+        sc.spec_json = sc.low.spec_json;
         sc.spec = parse_spec(sc.spec_json.c_str(), sc.spec_json.size());
         sc.report = sc.spec;
         sc.report.target_indices.assign(sc.low.report_targets.begin(), sc.low.report_targets.end());
@@ -1537,7 +1637,9 @@ int mcp_find_power_contracts(const uint8_t* contracts, size_t len, int32_t forma
             if (i) o += ',';
             o += '[';
             orch::jstr(o, scs[i].label);
-            const std::string arr = find_power_json(scs[i].spec, scs[i].report, &n32, 1, n_sims, call_seed, options, progress, user, warnings);
+            // the sink sees one range over the whole call: scenario i starts at i * n_sims of n_sims * scenarios (find_power.rs:311-337)
+            const std::string arr = find_power_json(scs[i].spec, scs[i].report, &n32, 1, n_sims, call_seed, options, progress, user, warnings,
+                                                    (uint64_t)i * n_sims, (uint64_t)n_sims * scs.size());
             o += ',' + arr.substr(1, arr.size() - 2) + ']';
         }
         o += "]}";
@@ -1554,13 +1656,21 @@ int mcp_find_sample_size_contracts(const uint8_t* contracts, size_t len, int32_t
         *json_out = nullptr;
         const std::vector<LoweredScenario> scs = lower_contracts(contracts, len, format);
         const uint64_t call_seed = mcp_splitmix64(user_seed);
+        // ONE grid for the call: atom, floor and cluster warnings are resolved over every scenario (find_sample_size.rs:24-107)
+        std::vector<const Spec*> specs;
+        for (auto& sc : scs) specs.push_back(&sc.spec);
+        uint64_t atom = 1;
+        std::vector<std::string> warnings;
+        const std::vector<uint64_t> grid = shared_grid(specs, from_size, to_size, by, by_auto, log_grid, atom, warnings);
         std::string o = "{\"scenarios\":[";
         for (size_t i = 0; i < scs.size(); i++) {
             if (i) o += ',';
             o += '[';
             orch::jstr(o, scs[i].label);
-            o += ',' + find_sample_size_json(scs[i].spec, scs[i].report, from_size, to_size, by, by_auto, log_grid, target_power, n_sims, call_seed,
-                                             options, progress, user) + ']';
+            // progress in draws: scenario i starts at i * n_sims of n_sims * scenarios (the reference counts fits = draws x grid
+            // points, find_sample_size.rs:109-113; the ratio current / total is the same)
+            o += ',' + find_sample_size_json(scs[i].spec, scs[i].report, grid, atom, warnings, target_power, n_sims, call_seed, options, progress,
+                                             user, (uint64_t)i * n_sims, (uint64_t)n_sims * scs.size()) + ']';
         }
         o += "]}";
         *json_out = dup_json(o);
@@ -1679,6 +1789,118 @@ int mcp_fit_data(const double* x_colmajor, const double* y, uint32_t n, uint32_t
         }
         CUDA_CHECK(cudaStreamSynchronize(st));
         CUDA_CHECK(cudaMemcpy(out, dout, (3 * p + 4) * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* design_colmajor, uint32_t nrow, uint32_t ncol,
+                          const double* outcome, const uint32_t* cluster_ids, int32_t device, double* betas, double* se, double* statistic,
+                          McpFitInfo* info) {
+    return guarded([&] {
+        if (!design_colmajor || !outcome || !betas || !se || !statistic || !info) invalid("NULL pointer argument");
+        Spec s = parse_spec(spec_json, spec_len);
+        validate_spec(s, nullptr, 0);
+        check_supported(s);
+        const int P = s.P();
+        if ((int)ncol != P) invalid("design has " + std::to_string(ncol) + " columns, the spec " + std::to_string(P) + " predictors");
+        if (nrow <= ncol) invalid("df = N - P < 1");
+        const int nt = (int)s.target_indices.size();
+        std::memset(info, 0, sizeof *info);
+        info->n_targets = nt;
+        info->df_resid = (double)((long)nrow - (long)P);
+        {  // CritValueTable::build with the pipeline's arguments (introspect.rs:535-548)
+            double unc = 0.0;
+            crit_row(s, nrow, P, &unc, nullptr, nullptr, nullptr);
+            info->crit_sq_uncorrected = unc;
+        }
+        const double nan = crit::kNaN;
+        info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = nan;
+        DeviceCtx& cx = ctx_for(device);
+        std::lock_guard<std::mutex> lock(cx.mu);
+        const cudaStream_t st = cx.compute;
+        std::vector<double> all((size_t)3 * P + 8, 0.0);
+        if (s.estimator == E_OLS) {
+            Carver oc(cx.outputs.get(Carver::pad((size_t)nrow * P * sizeof(double)) + Carver::pad((size_t)nrow * sizeof(double)) +
+                                     Carver::pad((3 * P + 4) * sizeof(double))));
+            double* dx = oc.take<double>((size_t)nrow * P);
+            double* dy = oc.take<double>(nrow);
+            double* dout = oc.take<double>(3 * P + 4);
+            CUDA_CHECK(cudaMemcpyAsync(dx, design_colmajor, (size_t)nrow * P * sizeof(double), cudaMemcpyHostToDevice, st));
+            CUDA_CHECK(cudaMemcpyAsync(dy, outcome, (size_t)nrow * sizeof(double), cudaMemcpyHostToDevice, st));
+            cudaError_t err = cudaSuccess;
+            bool handled = false;
+#define X(id) if (!handled) handled = tu##id##_fit_data(P, dx, dy, (int)nrow, dout, st, &err);
+            MCP_TU_LIST(X)
+#undef X
+            if (!handled) unsupported("p = " + std::to_string(P));
+            CUDA_CHECK(err);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            std::vector<double> o(3 * P + 4);
+            CUDA_CHECK(cudaMemcpy(o.data(), dout, o.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int j = 0; j < P; j++) betas[j] = o[j];
+            for (int t = 0; t < nt; t++) {
+                se[t] = o[P + s.target_indices[t]];
+                statistic[t] = std::sqrt(o[2 * P + s.target_indices[t]]);
+            }
+            info->sigma_sq_hat = o[3 * P];
+            info->converged = o[3 * P + 3] != 0.0;
+            return;
+        }
+        // GLM / MLE: the f32 data plane [row][x_1 .. x_{P-1}, y]; the kernels take x_0 = 1 like the generated designs
+        std::vector<float> plane((size_t)nrow * P);
+        for (uint32_t i = 0; i < nrow; i++) {
+            if ((float)design_colmajor[i] != 1.0f) unsupported("a design whose first column is not the intercept (all ones)");
+            for (int j = 1; j < P; j++) plane[(size_t)i * P + (j - 1)] = (float)design_colmajor[(size_t)j * nrow + i];
+            plane[(size_t)i * P + (P - 1)] = (float)outcome[i];
+        }
+        const bool mle = s.estimator == E_MLE;
+        size_t n_clusters = 0;
+        if (mle) {
+            const uint32_t cs = (uint32_t)std::max(s.sizing_value, 1);
+            n_clusters = s.sizing_fixed_size ? ((size_t)nrow + cs - 1) / cs : cs;
+            if (cluster_ids)
+                for (uint32_t i = 0; i < nrow; i++)
+                    if (cluster_ids[i] != (s.sizing_fixed_size ? i / cs : i % cs))
+                        unsupported("cluster ids that do not follow the spec's cluster sizing (row " + std::to_string(i) + ")");
+        }
+        Lowered lw;
+        lower(s, &nrow, 1, lw, /*thresholds=*/false);
+        void* dblob = cx.tables.get(lw.blob.size());
+        CUDA_CHECK(cudaMemcpyAsync(dblob, lw.blob.data(), lw.blob.size(), cudaMemcpyHostToDevice, st));
+        bind_tables(lw, lw.plan, dblob);
+        CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
+        lw.plan.error_flag = cx.d_error;
+        const size_t n_out = (size_t)3 * P + 7, n_csum = n_clusters * (size_t)(P + 1);
+        Carver oc(cx.outputs.get(Carver::pad(plane.size() * sizeof(float)) + Carver::pad(n_csum * sizeof(double)) + Carver::pad(n_out * sizeof(double))));
+        float* dplane = oc.take<float>(plane.size());
+        double* dcsum = oc.take<double>(n_csum);
+        double* dout = oc.take<double>(n_out);
+        CUDA_CHECK(cudaMemcpyAsync(dplane, plane.data(), plane.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (n_csum) CUDA_CHECK(cudaMemsetAsync(dcsum, 0, n_csum * sizeof(double), st));
+        {
+            cudaError_t err = cudaSuccess;
+            bool handled = false;
+            const int kind = mle ? KIND_LMM : KIND_GLM;
+#define X(id) if (!handled) handled = tu##id##_fit_spec(P, kind, lw.plan, dplane, (int)nrow, dcsum, dout, st, &err);
+            MCP_TU_LIST(X)
+#undef X
+            if (!handled) unsupported("p = " + std::to_string(P));
+            CUDA_CHECK(err);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        std::vector<double> o(n_out);
+        CUDA_CHECK(cudaMemcpy(o.data(), dout, n_out * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < P; j++) betas[j] = o[j];
+        for (int t = 0; t < nt; t++) {
+            se[t] = std::sqrt(o[P + s.target_indices[t]]);
+            statistic[t] = std::sqrt(o[2 * P + s.target_indices[t]]);
+        }
+        info->converged = o[3 * P] != 0.0;
+        info->boundary_hit = (int32_t)o[3 * P + 1];
+        info->iterations = (int32_t)o[3 * P + 2];
+        info->sigma_sq_hat = o[3 * P + 3];
+        info->tau_sq_hat = o[3 * P + 4];
+        info->deviance = o[3 * P + 5];
+        info->deviance_null = o[3 * P + 6];
     });
 }
 

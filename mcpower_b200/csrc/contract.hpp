@@ -121,6 +121,7 @@ class MsgpackReader {
 
 // ------------------------------------------------------------------------------------------------ JsonValue → text
 inline void write_number(std::string& out, double d) {
+    if (!std::isfinite(d)) invalid("non-finite number in the contract (JSON cannot carry NaN / infinity)");
     char buf[40];
     if (d == std::floor(d) && std::fabs(d) < 9007199254740992.0) std::snprintf(buf, sizeof buf, "%.0f", d);
     else std::snprintf(buf, sizeof buf, "%.17g", d);  // round-trips every finite f64 through strtod
@@ -736,7 +737,9 @@ inline void write_u32s(std::string& out, const char* key, const std::vector<uint
 }  // namespace detail
 
 // contract_to_simulation_spec (contract_adapter.rs:74-230)
-inline Lowering lower_contract(const Contract& c) {
+// factor_min_level_count: the kernel default is 0; the orchestrator forces its configured limit on every lowered scenario
+// (find_power.rs:271, configs/config.json:31).
+inline Lowering lower_contract(const Contract& c, int factor_min_level_count = 0) {
     using namespace detail;
     validate_contract(c);
     const std::vector<Term>& dt = c.test_design();
@@ -939,7 +942,8 @@ inline Lowering lower_contract(const Contract& c) {
     write_json(o, c.cluster);
     o += ",\"scenario\":";
     write_json(o, c.scenario);
-    o += std::string(",\"report_overall\":") + (report_overall ? "true" : "false") + ",\"factor_min_level_count\":0}";
+    o += std::string(",\"report_overall\":") + (report_overall ? "true" : "false") + ",\"factor_min_level_count\":" +
+         std::to_string(factor_min_level_count) + "}";
     return out;
 }
 

@@ -217,6 +217,26 @@ static cudaError_t fit_one(const double* dx, const double* dy, int n, double* do
 #endif
 }
 
+// fit_provided_data twins of the GLM / mixed-model arms: one supplied dataset on the arm's own fit code.
+template <int PT>
+static cudaError_t fit_spec_one(const DevicePlan& pl, const float* plane, int n, double* scratch, double* dout, cudaStream_t st) {
+#if defined(MCP_TU_GLM)
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    (void)scratch;
+    glm_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, dout);
+    return cudaGetLastError();
+#elif defined(MCP_TU_LMM)
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    lmm_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, scratch, dout);
+    return cudaGetLastError();
+#else
+    (void)pl; (void)plane; (void)n; (void)scratch; (void)dout; (void)st;
+    return cudaErrorInvalidValue;
+#endif
+}
+
 #define MCP_CASE(p, expr) \
     case p:               \
         if (p >= MCP_P_LO && p <= MCP_P_HI) { *err = expr; return true; } \
@@ -229,12 +249,14 @@ struct Sel {
     static cudaError_t launch(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) { return launch_one<PT>(kind, scen, pl, a); }
     static cudaError_t dump(bool scen, const DevicePlan& pl, uint64_t s, uint64_t i, float* dx, float* dy, cudaStream_t st) { return dump_one<PT>(scen, pl, s, i, dx, dy, st); }
     static cudaError_t fit(const double* dx, const double* dy, int n, double* o, cudaStream_t st) { return fit_one<PT>(dx, dy, n, o, st); }
+    static cudaError_t fit_spec(const DevicePlan& pl, const float* plane, int n, double* sc, double* o, cudaStream_t st) { return fit_spec_one<PT>(pl, plane, n, sc, o, st); }
 };
 template <int PT>
 struct Sel<PT, false> {
     static cudaError_t launch(int, bool, const DevicePlan&, const KernelArgs&) { return cudaErrorInvalidValue; }
     static cudaError_t dump(bool, const DevicePlan&, uint64_t, uint64_t, float*, float*, cudaStream_t) { return cudaErrorInvalidValue; }
     static cudaError_t fit(const double*, const double*, int, double*, cudaStream_t) { return cudaErrorInvalidValue; }
+    static cudaError_t fit_spec(const DevicePlan&, const float*, int, double*, double*, cudaStream_t) { return cudaErrorInvalidValue; }
 };
 
 #define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
@@ -272,6 +294,22 @@ bool MCP_TU_FN(fit_data)(int P, const double* dx, const double* dy, int n, doubl
     if (P < MCP_P_LO || P > MCP_P_HI) return false;
     switch (P) {
 #define X(p) case p: *err = Sel<p>::fit(dx, dy, n, dout, st); return true;
+        MCP_ALL_P(X)
+#undef X
+    }
+    return false;
+#endif
+}
+
+bool MCP_TU_FN(fit_spec)(int P, int kind, const DevicePlan& plan, const float* plane, int n, double* scratch, double* dout,
+                         cudaStream_t st, cudaError_t* err) {
+#ifdef MCP_TU_IS_OLS
+    (void)P; (void)kind; (void)plan; (void)plane; (void)n; (void)scratch; (void)dout; (void)st; (void)err;
+    return false;  // the OLS arm is served by fit_data
+#else
+    if (P < MCP_P_LO || P > MCP_P_HI || kind != MCP_TU_KIND) return false;
+    switch (P) {
+#define X(p) case p: *err = Sel<p>::fit_spec(plan, plane, n, scratch, dout, st); return true;
         MCP_ALL_P(X)
 #undef X
     }

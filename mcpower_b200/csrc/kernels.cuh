@@ -136,6 +136,21 @@ struct RegSolver {
         if (!(var > MCP_FNZ) || isinf(var)) return __longlong_as_double(0x7ff8000000000000LL);
         return est * est / var;
     }
+
+    // Var(beta_pos) = sigma² ‖L⁻¹ e_pos‖² (fit_suff_stats_t_sq's var_diag; the introspection twins report its square root)
+    __device__ __forceinline__ double var_of(int pos) const {
+        double u[PT];
+        double q = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) {
+            double s = i == pos ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < i; k++) s = fma(-L[tri(i, k)], u[k], s);
+            u[i] = s * inv_d[i];
+            q = fma(u[i], u[i], q);
+        }
+        return out.sigma_sq * q;
+    }
 };
 
 // Generic solver on local-memory arrays (runtime p): sparse-factor-exclusion / test-design
@@ -207,6 +222,17 @@ struct MemSolver {
         const double var = out.sigma_sq * q;
         if (!(var > MCP_FNZ) || isinf(var)) return __longlong_as_double(0x7ff8000000000000LL);
         return est * est / var;
+    }
+
+    __device__ __noinline__ double var_of(int pos) {  // sigma² ‖L⁻¹ e_pos‖²; clobbers w like t_sq
+        double q = 0.0;
+        for (int i = pos; i < p; i++) {
+            double s = i == pos ? 1.0 : 0.0;
+            for (int k = pos; k < i; k++) s = fma(-L[tri(i, k)], w[k], s);
+            w[i] = s * inv_d[i];
+            q = fma(w[i], w[i], q);
+        }
+        return out.sigma_sq * q;
     }
 };
 

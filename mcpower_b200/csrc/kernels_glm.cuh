@@ -335,6 +335,41 @@ static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int va
     emit_fit(so, g, variant, fo, pl.variants[variant].p_red, all_t, excl_flags, ov);
 }
 
+// introspect::fit_provided_data twin, GLM arm (introspect.rs:395-447): ONE supplied dataset through the same register-resident
+// IRLS as the power kernel, from the same spec-derived truth start (beta0 = effect_sizes).  plane = [row][column] f32, columns
+// x_1 .. x_{P-1}, y (stride 1).  out: beta[P] | Var(beta)[P] | z²[P] | converged, boundary (0), iterations, sigma² (NaN),
+// tau² (NaN), deviance, null deviance.
+template <int PT>
+__global__ void glm_fit_data_kernel(const float* __restrict__ plane, int n, double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const DevicePlan& pl = c_plan;
+    const int family = pl.outcome == O_COUNT ? 2 : (pl.link_probit ? 1 : 0);
+    RegSolver<PT> sv;
+    double beta[PT];
+    GlmOut go;
+    glm_irls_reg<PT>(plane, 1, n, family, /*truth_start=*/true, sv, beta, go);
+#pragma unroll
+    for (int j = 0; j < PT; j++) sv.beta[j] = beta[j];
+    sv.out.sigma_sq = 1.0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int t = 0; t < PT; t++) {
+        double b = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++)
+            if (i == t) b = beta[i];
+        out[t] = b;
+        out[PT + t] = go.converged ? sv.var_of(t) : nan;
+        out[2 * PT + t] = go.converged ? sv.t_sq(t, -1) : nan;
+    }
+    out[3 * PT] = (double)go.converged;
+    out[3 * PT + 1] = 0.0;
+    out[3 * PT + 2] = (double)go.iters;
+    out[3 * PT + 3] = nan;
+    out[3 * PT + 4] = nan;
+    out[3 * PT + 5] = go.deviance;
+    out[3 * PT + 6] = go.deviance_null;
+}
+
 // Stage 1 is the lane-quad kernel in PLANE mode (kernels_q4.cuh): it generates the study's max_n rows once — the same gen_block /
 // row_xy as the OLS kernels, so the data plane is bit-identical to the reference fixtures — and parks the f32 plane in HBM,
 // [row][column][study-in-wave].

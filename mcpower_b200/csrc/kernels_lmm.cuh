@@ -271,7 +271,7 @@ __device__ __forceinline__ uint32_t lmm_cluster_rows(const DevicePlan& pl, int k
 //   csum element (k, j) = csum[(k * (PT+1) + j) * stride]; kept == nullptr → full model.
 template <int PT>
 static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restrict__ csum, size_t stride, int n, int n_clusters,
-                                            const int8_t* kept, int& converged, int& boundary) {
+                                            const int8_t* kept, int& converged, int& boundary, double* theta_out = nullptr) {
     const DevicePlan& pl = c_plan;
     const int p = c.p, nt = p * (p + 1) / 2;
     c.ng = 0;
@@ -317,6 +317,7 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
     else if (MCP_LMM_THETA_MAX - th < 1e-6 * MCP_LMM_THETA_MAX) { boundary = 2; converged = 0; }
     const double f = lmm_dev<PT>(c, th);  // leaves L, beta, sigma² at theta-hat
     if (isinf(f) || f != f) converged = 0;
+    if (theta_out) *theta_out = th;
 }
 
 // Joint Wald chi-square of the testable targets: beta_T' [Cov_TT]^-1 beta_T, Cov = sigma² A^-1.
@@ -438,6 +439,69 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
             }
         }
     }
+}
+
+// introspect::fit_provided_data twin, MLE arm (introspect.rs:448-530): ONE supplied dataset through the same statistics chains
+// (lmm_gen_kernel) and the same profiled-REML fit (lmm_fit) as the power kernels.  Cluster ids follow the spec's sizing
+// (generation.rs cluster_of_row; the host checks supplied ids against it).  plane = [row][column] f32, columns x_1 .. x_{P-1}, y;
+// csum = zeroed scratch of n_clusters x (P + 1) doubles.  out: beta[P] | Var(beta)[P] | z²[P] | converged, boundary_hit, 0,
+// sigma²-hat, tau²-hat = theta² sigma², profiled REML criterion at theta-hat, NaN.
+template <int PT>
+__global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, double* __restrict__ csum, double* __restrict__ out) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const DevicePlan& pl = c_plan;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    double acc[NACC], xty[PT];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PT; i++) xty[i] = 0.0;
+    double yty = 0.0;
+    for (int row = 0; row < n; row++) {
+        double xr[PT];
+        xr[0] = 1.0;
+#pragma unroll
+        for (int j = 1; j < PT; j++) xr[j] = (double)plane[(size_t)row * PT + (j - 1)];
+        const double yd = (double)plane[(size_t)row * PT + (PT - 1)];
+#pragma unroll
+        for (int a = 0; a < PT; a++) {
+#pragma unroll
+            for (int c = 0; c <= a; c++) acc[tri(a, c)] = fma(xr[a], xr[c], acc[tri(a, c)]);
+            xty[a] = fma(xr[a], yd, xty[a]);
+        }
+        yty = fma(yd, yd, yty);
+        const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
+        double* base = csum + (size_t)kc * (PT + 1);
+#pragma unroll
+        for (int j = 0; j < PT; j++) base[j] += xr[j];
+        base[PT] += yd;
+    }
+    LmmCtx<PT> c;
+    c.p = PT;
+    c.n_rows = (uint32_t)n;
+    c.yty = yty;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c.xtx[i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < PT; i++) c.xty[i] = xty[i];
+    const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
+    int conv = 0, bnd = 0;
+    double theta = 0.0;
+    lmm_fit<PT>(c, csum, 1, n, n_clusters, nullptr, conv, bnd, &theta);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int t = 0; t < PT; t++) {
+        out[t] = c.ms.beta[t];
+        out[PT + t] = conv ? c.ms.var_of(t) : nan;
+        out[2 * PT + t] = conv ? c.ms.t_sq(t, -1) : nan;
+    }
+    out[3 * PT] = (double)conv;
+    out[3 * PT + 1] = (double)bnd;
+    out[3 * PT + 2] = 0.0;
+    out[3 * PT + 3] = c.ms.out.sigma_sq;
+    out[3 * PT + 4] = theta * theta * c.ms.out.sigma_sq;
+    out[3 * PT + 5] = nan;
+    out[3 * PT + 6] = nan;
 }
 
 // Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): profiled REML by Brent over the cluster

@@ -25,7 +25,9 @@ struct KernelArgs {
     bool tu##id##_launch_power(int P, int kind, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err); \
     bool tu##id##_dump(int P, bool scen, const DevicePlan& plan, uint64_t base_seed, uint64_t sim_id, float* dx, float* dy, \
                        cudaStream_t st, cudaError_t* err);                                                                 \
-    bool tu##id##_fit_data(int P, const double* dx, const double* dy, int n, double* dout, cudaStream_t st, cudaError_t* err);
+    bool tu##id##_fit_data(int P, const double* dx, const double* dy, int n, double* dout, cudaStream_t st, cudaError_t* err); \
+    bool tu##id##_fit_spec(int P, int kind, const DevicePlan& plan, const float* plane, int n, double* scratch, double* dout,  \
+                           cudaStream_t st, cudaError_t* err);
 
 #define MCP_TU_LIST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
 MCP_TU_LIST(MCP_DECLARE_TU)

@@ -91,7 +91,15 @@ _PROGRESS = C.CFUNCTYPE(C.c_int, C.c_uint64, C.c_uint64, C.c_void_p)
 EXPORTS = ("mcp_run_batch", "mcp_free_result", "mcp_generate_sim", "mcp_fit_data", "mcp_crit_table", "mcp_splitmix64",
            "mcp_pipe_bench", "mcp_device_count", "mcp_last_error", "mcp_version", "mcp_find_power", "mcp_find_sample_size",
            "mcp_free_string", "mcp_fit_crossing", "mcp_build_grid", "mcp_wilson_ci", "mcp_lower_contracts",
-           "mcp_find_power_contracts", "mcp_find_sample_size_contracts", "mcp_test_force_ols_variant")
+           "mcp_find_power_contracts", "mcp_find_sample_size_contracts", "mcp_test_force_ols_variant",
+           "mcp_fit_provided_data")
+
+
+class _FitInfo(C.Structure):
+    """McpFitInfo (include/mcpower_b200.h)."""
+    _fields_ = [("converged", C.c_int32), ("boundary_hit", C.c_int32), ("iterations", C.c_int32), ("n_targets", C.c_int32),
+                ("crit_sq_uncorrected", C.c_double), ("df_resid", C.c_double), ("sigma_sq_hat", C.c_double),
+                ("tau_sq_hat", C.c_double), ("deviance", C.c_double), ("deviance_null", C.c_double)]
 
 
 class _CrossingFit(C.Structure):
@@ -122,6 +130,10 @@ def lib():
     L.mcp_fit_data.restype = C.c_int
     L.mcp_fit_data.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint32, C.c_uint32, C.c_int32,
                                C.POINTER(C.c_double)]
+    L.mcp_fit_provided_data.restype = C.c_int
+    L.mcp_fit_provided_data.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.c_uint32, C.c_uint32,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_int32, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_FitInfo)]
     L.mcp_crit_table.restype = C.c_int
     L.mcp_crit_table.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -318,6 +330,18 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
 ProgressSink = Callable[[int, int], bool]
 
 
+class _ResultOwner:
+    """Owns one McpBatchResult; mcp_free_result runs when the last view of its buffers is collected."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+
+    def __del__(self):
+        p, self._ptr = self._ptr, None
+        if p is not None and _lib is not None:
+            _lib.mcp_free_result(p)
+
+
 def force_ols_variant(variant: int) -> int:
     """Test hook: pin the OLS power kernel (1 thread per study, 4 lane quad solving by call, 5 lean pair, 6 split pair;
     0 = the library's own choice).  Process-wide; returns the previous setting.  The cross-check kernels compute the
@@ -345,37 +369,41 @@ def run_batch(spec: dict, sample_sizes: Sequence[int], n_sims: int, base_seed: i
                          base_seed & 0xFFFFFFFFFFFFFFFF, C.byref(opt), cb, None, C.byref(out))
     if rc != 0:
         _raise(rc)
-    try:
-        r = out.contents
-        n_ss, T, F = r.n_sample_sizes, r.n_targets, r.n_factors
+    # The tensors stay where the library put them (page-locked host memory the device copied into): the arrays below are
+    # views, not copies, and the C result is released when the last of them — and the BatchResult — is gone.
+    owner = _ResultOwner(out)
+    r = out.contents
+    n_ss, T, F = r.n_sample_sizes, r.n_targets, r.n_factors
 
-        def take(ptr, shape, dtype):
-            if not ptr:
-                return None
-            n = int(np.prod(shape))
-            if n == 0:
-                return np.zeros(shape, dtype=dtype)
-            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True).reshape(shape)
+    def take(ptr, shape, dtype):
+        if not ptr:
+            return None
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=dtype)
+        nbytes = n * np.dtype(dtype).itemsize
+        buf = (C.c_uint8 * nbytes).from_address(C.addressof(ptr.contents))
+        buf._owner = owner  # keeps the C result alive for as long as any view of it exists
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
 
-        res = BatchResult(
-            n_sims=r.n_sims, n_sample_sizes=n_ss, n_targets=T, n_factors=F,
-            counters=take(r.counters, (n_ss, r.counter_width), np.uint64),
-            uncorrected=take(r.uncorrected, (r.n_sims, n_ss, T), np.uint8),
-            corrected=take(r.corrected, (r.n_sims, n_ss, T), np.uint8),
-            converged=take(r.converged, (r.n_sims, n_ss), np.uint8),
-            overall=take(r.overall, (r.n_sims, n_ss), np.uint8),
-            factor_excluded=take(r.factor_excluded, (r.n_sims, n_ss, F), np.uint8),
-            n_posthoc=r.n_posthoc,
-            posthoc_unc=take(r.posthoc_unc, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
-            posthoc_cor=take(r.posthoc_cor, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
-            joint=take(r.joint, (r.n_sims, n_ss), np.uint8),
-            boundary_hit=take(r.boundary_hit, (r.n_sims, n_ss), np.uint8),
-            t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),
-            kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches), h2d_bytes=int(r.h2d_bytes),
-            d2h_bytes=int(r.d2h_bytes), n_devices=int(r.n_devices), n_waves=int(r.n_waves), lower_ms=float(r.lower_ms),
-            enqueue_ms=float(r.enqueue_ms), wait_ms=float(r.wait_ms))
-    finally:
-        L.mcp_free_result(out)
+    res = BatchResult(
+        n_sims=r.n_sims, n_sample_sizes=n_ss, n_targets=T, n_factors=F,
+        counters=take(r.counters, (n_ss, r.counter_width), np.uint64),
+        uncorrected=take(r.uncorrected, (r.n_sims, n_ss, T), np.uint8),
+        corrected=take(r.corrected, (r.n_sims, n_ss, T), np.uint8),
+        converged=take(r.converged, (r.n_sims, n_ss), np.uint8),
+        overall=take(r.overall, (r.n_sims, n_ss), np.uint8),
+        factor_excluded=take(r.factor_excluded, (r.n_sims, n_ss, F), np.uint8),
+        n_posthoc=r.n_posthoc,
+        posthoc_unc=take(r.posthoc_unc, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
+        posthoc_cor=take(r.posthoc_cor, (r.n_sims, n_ss, r.n_posthoc), np.uint8),
+        joint=take(r.joint, (r.n_sims, n_ss), np.uint8),
+        boundary_hit=take(r.boundary_hit, (r.n_sims, n_ss), np.uint8),
+        t_sq=take(r.t_sq, (r.n_sims, n_ss, T), np.float64),
+        kernel_ms=float(r.kernel_ms), gpu_launches=int(r.gpu_launches), h2d_bytes=int(r.h2d_bytes),
+        d2h_bytes=int(r.d2h_bytes), n_devices=int(r.n_devices), n_waves=int(r.n_waves), lower_ms=float(r.lower_ms),
+        enqueue_ms=float(r.enqueue_ms), wait_ms=float(r.wait_ms))
+    res.extras["_owner"] = owner
     return res
 
 
@@ -406,6 +434,31 @@ def fit_data(x, y, device: int = -1) -> dict:
         _raise(rc)
     return {"betas": out[:p].copy(), "se": out[p:2 * p].copy(), "t_sq": out[2 * p:3 * p].copy(),
             "sigma_sq": out[3 * p], "sst": out[3 * p + 1], "rss": out[3 * p + 2], "converged": bool(out[3 * p + 3])}
+
+
+def fit_provided_data(spec: dict, x, y, cluster_ids=None, device: int = -1) -> dict:
+    """introspect::fit_provided_data (introspect.rs:174-562): fit the supplied (design [n, P], outcome[, cluster ids]) with the
+    shipped fit code of `spec["estimator"]` — OLS, unclustered GLM (IRLS from the truth start), random-intercept MLE (profiled
+    REML) — and return IntrospectResults as a dict: betas per column, se / statistic per target, crit_sq_uncorrected, df_resid."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    blob = json.dumps(spec).encode()
+    nt = len(spec["target_indices"])
+    betas, se, stat = np.zeros(p), np.zeros(max(nt, 1)), np.zeros(max(nt, 1))
+    info = _FitInfo()
+    ids = None if cluster_ids is None else np.ascontiguousarray(cluster_ids, dtype=np.uint32)
+    dp = C.POINTER(C.c_double)
+    rc = lib().mcp_fit_provided_data(blob, len(blob), xc.ctypes.data_as(dp), n, p, yv.ctypes.data_as(dp),
+                                     None if ids is None else ids.ctypes.data_as(C.POINTER(C.c_uint32)), device,
+                                     betas.ctypes.data_as(dp), se.ctypes.data_as(dp), stat.ctypes.data_as(dp), C.byref(info))
+    if rc != 0:
+        _raise(rc)
+    return {"betas": betas, "se": se[:nt], "statistic": stat[:nt], "target_cols": list(spec["target_indices"]),
+            "converged": bool(info.converged), "crit_sq_uncorrected": info.crit_sq_uncorrected, "df_resid": info.df_resid,
+            "boundary_hit": int(info.boundary_hit), "iterations": int(info.iterations), "sigma_sq_hat": info.sigma_sq_hat,
+            "tau_sq_hat": info.tau_sq_hat, "deviance": info.deviance, "deviance_null": info.deviance_null}
 
 
 def crit_table(spec: dict, sample_sizes: Sequence[int], n_predictors: Optional[int] = None) -> dict:

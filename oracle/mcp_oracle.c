@@ -2389,7 +2389,7 @@ int orc_run_batch(const OrcSpec* s, const uint32_t* ss, int n_ss, uint32_t n_sim
     if (s->n_posthoc > 0 && s->estimator != ORC_EST_OLS)
         return fail(ORC_ERR_INVALID_SPEC, "posthoc tests are only supported for estimator=Ols");
     if (s->n_posthoc > 64) return fail(ORC_ERR_INVALID_SPEC, "posthoc contrasts > 64");
-    if (s->estimator == ORC_EST_MLE && (s->n_contrasts > 0 || s->has_lme || s->outcome_kind != ORC_OUT_CONTINUOUS))
+    if (s->estimator == ORC_EST_MLE && (s->n_contrasts > 0 || s->outcome_kind != ORC_OUT_CONTINUOUS))
         return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: only the Gaussian random-intercept MLE arm is restated");
     if (s->estimator == ORC_EST_GLM && (s->has_cluster || s->n_contrasts > 0))
         return fail(ORC_ERR_INVALID_SPEC, "oracle run_batch: clustered GLM (GLMM) / GLM contrasts are not restated");

@@ -290,3 +290,38 @@ def test_lowered_spec_is_accepted_by_the_spec_reader():
     two = copy.deepcopy(example1())
     two["scenario"]["name"] = "b"
     assert [s["label"] for s in M.lower_contracts([example1(), two])] == ["", "b"]
+
+
+# ------------------------------------------------------------------ find_sample_size guards that fire before any device work
+def _clustered(sizing, scen=None):
+    return contract([normal(), normal()], [CONST, direct(0), direct(1)], [0.0, 0.5, 0.3], [marginal(1), marginal(2)],
+                    estimator="mle", scen=scen,
+                    cluster={"sizing": sizing, "tau_squared": 0.25, "slopes": [], "extra_groupings": []})
+
+
+def test_scenarios_that_disagree_on_the_cluster_atom_are_rejected():  # find_sample_size.rs:33-44, result.rs:606-607
+    a = _clustered({"FixedClusters": {"n_clusters": 10}}, scenario(name="a"))
+    b = _clustered({"FixedClusters": {"n_clusters": 12}}, scenario(name="b"))
+    with pytest.raises(M.InvalidSpec, match=r"disagree on the cluster atom \(10 vs 12\)"):
+        M.find_sample_size_contracts([a, b], 40, 400, 64, by=40)
+    # an unclustered scenario next to a clustered one shares the clustered grid: the guard looks at clustered scenarios only
+    plain = example1()
+    with pytest.raises(M.EngineError) as e:  # passes the host-side guards; fails only for lack of a device here
+        M.find_sample_size_contracts([a, plain], 40, 400, 64, by=40)
+    assert "atom" not in str(e.value)
+
+
+def test_fixed_size_cluster_below_the_row_minimum_is_rejected():  # find_sample_size.rs:63-70, result.rs:608-609
+    with pytest.raises(M.InvalidSpec, match="cluster_size >= 2"):
+        M.find_sample_size_contracts([_clustered({"FixedSize": {"cluster_size": 1}})], 40, 400, 64, by=40)
+
+
+def test_non_finite_numbers_cannot_be_lowered():
+    c = example1()
+    c["outcome"]["coefficients"][1] = float("inf")
+    with pytest.raises(M.InvalidSpec):
+        M.lower_contracts(msgpack.packb([c], use_bin_type=True))
+
+
+def test_lowered_spec_carries_the_configured_factor_minimum():  # find_power.rs:271, configs/config.json:31
+    assert lower(example1())["spec"]["factor_min_level_count"] == 5

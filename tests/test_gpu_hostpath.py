@@ -167,3 +167,39 @@ def test_concurrent_calls_from_threads_are_serialised_per_device():
     [t.join() for t in th]
     assert not errs
     assert all(np.array_equal(o, want) for o in out)
+
+
+def test_contract_runners_report_one_progress_range_and_preflight_warnings():
+    """find_power over two scenarios: the sink sees offset + done of n_sims x scenarios (find_power.rs:311-337); a sparse level of a
+    fixed-allocation factor raises the pre-run advisory (find_power.rs:67-116, 364-368); find_sample_size shares one grid and names
+    the N at which the factor clears the minimum (find_power.rs:122-170)."""
+    import ctypes as C
+    import json
+    import msgpack
+    import test_contract_lowering as TC
+    from mcpower_b200 import engine
+    terms = [TC.CONST, TC.direct(0), TC.dummy(1, 1)]
+    base = TC.contract([TC.normal(), TC.factor(2, [0.9, 0.1])], terms, [0.0, 0.4, 0.5], [TC.marginal(1), TC.marginal(2)])
+    base["scenario"]["name"] = "optimistic"
+    second = __import__("copy").deepcopy(base)
+    second["scenario"] = TC.scenario(name="noisy", heterogeneity=0.3)
+    blob = msgpack.packb([base, second], use_bin_type=True)
+    seen = []
+    cb = engine._PROGRESS(lambda cur, tot, _u: seen.append((int(cur), int(tot))) or 1)
+    out = C.c_void_p()
+    opt = engine._options(0, M.MODE_COUNTS)
+    n_sims = 50_000
+    rc = engine.lib().mcp_find_power_contracts(blob, len(blob), 0, 40, n_sims, 2137, C.byref(opt), cb, None, C.byref(out))
+    assert rc == 0, engine.lib().mcp_last_error()
+    res = engine._take_json(out)
+    assert [t for _, t in seen] == [2 * n_sims] * len(seen)
+    cur = [c for c, _ in seen]
+    assert cur == sorted(cur) and cur[-1] == 2 * n_sims and n_sims in cur
+    for _, pr in res["scenarios"]:
+        w = [m for m in pr["grid_warnings"] if m.startswith("factor 1: level 2 receives 4 of 40 observations (minimum 5)")]
+        assert len(w) == 1, pr["grid_warnings"]
+        assert pr["factor_exclusion_counts"] == [n_sims]
+    ss = M.find_sample_size_contracts(blob, 20, 100, 2048, 2137, by=20)
+    for _, r in ss["scenarios"]:
+        assert [p["n"] for p in r["grid_or_trace"]] == [20, 40, 60, 80, 100]
+        assert any("factor 1: levels reach the 5-observation minimum only at N >= 46" in m for m in r["grid_warnings"]), r["grid_warnings"]
