@@ -223,11 +223,11 @@ struct Carver {
     char* base;
     size_t off = 0;
     explicit Carver(void* b) : base(static_cast<char*>(b)) {}
-    static size_t pad(size_t n) { return (n + 255) & ~(size_t)255; }
+    static size_t pad(size_t n) { return (std::max<size_t>(n, 1) + 255) & ~(size_t)255; }  // what take() advances by: never 0
     template <typename T>
     T* take(size_t n) {
         T* p = reinterpret_cast<T*>(base + off);
-        off += pad(std::max<size_t>(n, 1) * sizeof(T));
+        off += pad(n * sizeof(T));
         return p;
     }
 };
@@ -448,7 +448,7 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     for (int v : s.new_dists)
         if (v >= D_UPLOADED_FACTOR) unsupported("uploaded_* distributions in the scenario menu");
     if (s.k > MCP_MAX_K) unsupported("n_non_factor > " + std::to_string(MCP_MAX_K));
-    if (s.P() > MCP_MAX_TEMPLATE_P) unsupported("n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
+    if (s.P() > MCP_MAX_P) unsupported("n_predictors > " + std::to_string(MCP_MAX_P));
     if (s.T() > MCP_MAX_T) unsupported("targets > " + std::to_string(MCP_MAX_T));
     if (s.factor_n_levels.size() > MCP_MAX_FACTORS) unsupported("factors > " + std::to_string(MCP_MAX_FACTORS));
     if (s.factor_proportions.size() > MCP_MAX_LEVELS) unsupported("Σ factor levels > " + std::to_string(MCP_MAX_LEVELS));
@@ -501,7 +501,9 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     DevicePlan& pl = lw.plan;
     std::memset(&pl, 0, sizeof pl);
     const int P = s.P(), T = s.T(), F = (int)s.factor_n_levels.size();
-    lw.P = P; lw.T = T; lw.F = F; lw.n_ss = (int)n_ss;
+    // lw.P = the kernels' template width: P itself up to 16, else one of the padded wide widths (plan.h, mcp_template_p); the plan
+    // carries the real P, and on a padded width every fit variant below keeps only the real columns
+    lw.P = mcp_template_p(P); lw.T = T; lw.F = F; lw.n_ss = (int)n_ss;
     pl.k = s.k; pl.n_fd = s.n_fd; pl.n_factors = F; pl.n_inter = (int)s.interactions.size();
     pl.P = P; pl.T = T; pl.n_marg = (int)s.target_indices.size(); pl.n_contrasts = (int)s.contrast_pairs.size();
     pl.n_ss = (int)n_ss; pl.max_n = (int)ss[n_ss - 1];
@@ -565,7 +567,11 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.inter_ptr[s.interactions.size()] = q;
     for (int j = 0; j < P; j++) {
         pl.beta[j] = s.effect_sizes[j];
-        if (s.effect_sizes[j] != 0.0) pl.beta_nonzero_mask |= 1u << j;
+        if (s.effect_sizes[j] != 0.0) {
+            pl.beta_nonzero_mask |= 1u << j;
+            pl.nz_col[pl.n_nz] = (int8_t)j;
+            pl.nz_beta[pl.n_nz++] = s.effect_sizes[j];
+        }
     }
     pl.n_ph = (int)s.posthoc_contrasts.size();
     for (int c = 0; c < pl.n_ph; c++) {
@@ -789,6 +795,11 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
 }
 
 // ---- kernel dispatch: ask each kernel translation unit in turn (launch.h) -------------------------
+// bytes of one per-study scenario design at template width P (an upper bound within the width class)
+static size_t scen_design_bytes(int P) {
+    return P <= MCP_MAX_TEMPLATE_P ? sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>) : (P <= MCP_WIDE_P_A ? sizeof(ScenDesign<MCP_WIDE_P_A>) : sizeof(ScenDesign<MCP_WIDE_P_B>));
+}
+
 static void dispatch_power(int P, int kind, const DevicePlan& plan, const KernelArgs& a) {
     cudaError_t err = cudaSuccess;
     bool handled = false;
@@ -932,7 +943,7 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         // IRLS makes several passes over each study's data: the f32 plane of a wave is kept in HBM as
         // [row][column][sim] (coalesced across the sims of a warp); the wave is capped at ~6 GiB of scratch
         // (+ the per-study scenario designs behind the plane on the scenario path, sized for the widest template)
-        const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));
+        const size_t per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + (pl.optimistic ? 0 : scen_design_bytes(lw.P));
         const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)6 << 30) / std::max<size_t>(per_sim, 1), 128);
         wave = std::min(wave, cap);
         wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
@@ -941,7 +952,7 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
     double* lmm_scratch = nullptr;
     bool lmm_quad = false;  // mixed-model generator on the quad kernel (cluster sums fit in shared memory; kernel_tu.cu decides the same way)
     if (mle) {
-        const int P_ = lw.P, M_ = (P_ + 2) / 2, MH_ = (M_ + 1) & ~1, STUDY_ = 4 * (2 * MH_) + 2;
+        const int P_ = lw.P, STUDY_ = mcp_stage_geom((P_ + 2) / 2).study;
         const int cs_ = std::max(s.sizing_value, 1);
         const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
         const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
@@ -950,7 +961,7 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
         // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
         const size_t per_sim = (nc_ * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
-                               (pl.optimistic ? 0 : sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>));  // + scenario designs behind the layout
+                               (pl.optimistic ? 0 : scen_design_bytes(lw.P));  // + scenario designs behind the layout
         const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
         wave = std::min(wave, cap);
         wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs
@@ -964,7 +975,8 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
     //     (scenario designs from their own one-thread-per-study kernel), same statistics buffer, same solve kernel;
     //   4 general quad kernel solving by call, 1 thread-per-study kernel — kept for cross-checks (tests select them through
     //     the process-wide test hook mcp_test_force_ols_variant; the product path never reads the environment).
-    const bool lean_ok = kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
+    const bool wide = lw.P != pl.P;  // padded width: the split path's kernels only
+    const bool lean_ok = !wide && kind == KIND_OLS && pl.optimistic && pl.outcome == O_CONTINUOUS && pl.all_normal &&
                          (pl.n_factors == 0 || pl.exact_walk) && pl.residual_dist == R_NORMAL && !pl.has_cluster && !pl.bootstrap;
     int ols_variant = lean_ok ? 5 : 6;
     switch (g_force_ols_variant.load(std::memory_order_relaxed)) {
@@ -974,6 +986,7 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         case 6: ols_variant = 6; break;
         default: break;
     }
+    if (wide) ols_variant = 6;
     if (kind == KIND_OLS && (ols_variant == 5 || ols_variant == 6)) {
         // statistics buffer [grid point][entry][sim] in HBM (448 B per fit at P = 9); wave capped at ~4 GiB of scratch, ~12 GiB
         // on the scenario path: its one-thread-per-study design kernel is latency-bound (Jacobi repair in local memory)
@@ -985,7 +998,7 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         wave = std::min(wave, cap);
         if (wave < n_sims) wave = std::max<uint32_t>((wave / 128u) * 128u, 128u);
         // variant 6 on the scenario path keeps the per-study scenario designs behind the statistics (sized for the widest template)
-        const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? sizeof(ScenDesign<MCP_MAX_TEMPLATE_P>) : 0;
+        const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? scen_design_bytes(lw.P) : 0;
         lmm_scratch = static_cast<double*>(cx.scratch.get((size_t)wave * (n_ss * E * sizeof(double) + design_bytes)));
     }
     if (pl.n_between > 0) {  // representative-row values of the cluster-level predictors, [cluster][column][study in wave]
@@ -1757,7 +1770,7 @@ int mcp_generate_sim(const char* spec_json, size_t spec_len, uint32_t max_n, uin
         }
         // the caller's buffers are pageable: synchronous copies, ordered behind the kernel by the stream synchronisation
         CUDA_CHECK(cudaStreamSynchronize(st));
-        CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * P * sizeof(float), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(x_colmajor, dx, (size_t)max_n * lw.plan.P * sizeof(float), cudaMemcpyDeviceToHost));  // the real columns
         CUDA_CHECK(cudaMemcpy(y, dy, (size_t)max_n * sizeof(float), cudaMemcpyDeviceToHost));
         int err_flag = 0;
         CUDA_CHECK(cudaMemcpy(&err_flag, cx.d_error, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1845,6 +1858,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
             info->converged = o[3 * P + 3] != 0.0;
             return;
         }
+        if (P > MCP_MAX_TEMPLATE_P) unsupported("fit_provided_data for n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
         // GLM / MLE: the f32 data plane [row][x_1 .. x_{P-1}, y]; the kernels take x_0 = 1 like the generated designs
         std::vector<float> plane((size_t)nrow * P);
         for (uint32_t i = 0; i < nrow; i++) {

@@ -45,6 +45,12 @@ static size_t power_smem(const DevicePlan& pl, int P) {
 // the linker and registered by several modules: a launch could run another module's copy of the kernel, reading THAT
 // module's __constant__ plan (stale).  Guard with a real macro.
 
+// dynamic shared memory opt-in: 96 KiB covers every exact width; the padded wide widths ask for what they need
+template <typename K>
+static void allow_smem(K kernel, size_t bytes) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes > 96 * 1024 ? bytes : 96 * 1024));
+}
+
 template <int PT>
 static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const KernelArgs& a) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, a.stream);
@@ -66,11 +72,11 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
                 scen_design_kernel<PT, MCP_TU_KIND><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
                 e = cudaGetLastError();
                 if (e != cudaSuccess) return e;
-                cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                allow_smem(ols_power_kernel_q4<PT, true, true, false, true>, smem_q);
                 ols_power_kernel_q4<PT, true, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
                     a.base_seed, a.sim_begin, a.n_sims, nullptr, designs, stride, nullptr, 0, a.scratch);
             } else {
-                cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                allow_smem(ols_power_kernel_q4<PT, false, true, false, true>, smem_q);
                 ols_power_kernel_q4<PT, false, true, false, true><<<blocks_q, MCP_BLOCK, smem_q, a.stream>>>(
                     a.base_seed, a.sim_begin, a.n_sims, nullptr, nullptr, stride, nullptr, 0, a.scratch);
             }
@@ -114,7 +120,7 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
             }
         } else {
             const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
-            cudaFuncSetAttribute(lmm_gen_kernel<PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            allow_smem(lmm_gen_kernel<PT>, smem_gen);
             lmm_gen_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
         }
         e = cudaGetLastError();
@@ -123,7 +129,8 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         lmm_fit_kernel<PT><<<dim3(blocks, (unsigned)pl.n_ss), MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch_d, stride);
     }
 #else
-    if (a.ols_variant == 5) {  // plain-linear-model family: lane-quad generate + accumulate kernel, then one thread per fit
+    const int variant = PT > MCP_MAX_TEMPLATE_P ? 6 : a.ols_variant;  // padded wide widths: the split path only
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (variant == 5) {  // plain-linear-model family: lane-quad generate + accumulate kernel, then one thread per fit
         using G = LeanGeom<PT>;
         const size_t smem5 = G::smem_bytes();
         const uint32_t blocks5 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
@@ -151,7 +158,8 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
         const dim3 grid_s((a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK, (unsigned)pl.n_ss);
         ols_solve_kernel<PT><<<grid_s, MCP_BLOCK, smem_s, a.stream>>>(a.n_sims, a.scratch_d);
-    } else if (a.ols_variant == 6) {  // general quad generate + accumulate kernel, then one thread per fit (kernels_q4.cuh, SPLIT)
+    }
+    if (variant == 6) {  // general quad generate + accumulate kernel, then one thread per fit (kernels_q4.cuh, SPLIT)
         using G = Q4Geom<PT>;
         const size_t smem6 = G::smem_bytes(0, 0, false);
         const uint32_t blocks6 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
@@ -161,10 +169,10 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
             scen_design_kernel<PT, MCP_TU_KIND><<<blocks, MCP_BLOCK, 0, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, designs);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
-            cudaFuncSetAttribute(ols_power_kernel_q4<PT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            allow_smem(ols_power_kernel_q4<PT, true, true>, smem6);
             ols_power_kernel_q4<PT, true, true><<<blocks6, MCP_BLOCK, smem6, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d, designs);
         } else {
-            cudaFuncSetAttribute(ols_power_kernel_q4<PT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            allow_smem(ols_power_kernel_q4<PT, false, true>, smem6);
             ols_power_kernel_q4<PT, false, true><<<blocks6, MCP_BLOCK, smem6, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, a.scratch_d);
         }
         e = cudaGetLastError();
@@ -172,7 +180,8 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const size_t smem_s = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
         const dim3 grid_s((a.n_sims + MCP_BLOCK - 1) / MCP_BLOCK, (unsigned)pl.n_ss);
         ols_solve_kernel<PT><<<grid_s, MCP_BLOCK, smem_s, a.stream>>>(a.n_sims, a.scratch_d);
-    } else if (a.ols_variant == 4) {  // one study per lane quad (kernels_q4.cuh)
+    }
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (variant == 4) {  // one study per lane quad (kernels_q4.cuh)
         using G = Q4Geom<PT>;
         const size_t smem4 = G::smem_bytes(pl.n_ss, pl.counter_width, pl.smem_counters != 0);
         const uint32_t blocks4 = (a.n_sims + G::STUDIES - 1) / G::STUDIES;
@@ -183,12 +192,15 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
             cudaFuncSetAttribute(ols_power_kernel_q4<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
             ols_power_kernel_q4<PT, false><<<blocks4, MCP_BLOCK, smem4, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
         }
-    } else if (scen) {
-        cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        ols_power_kernel<PT, true><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
-    } else {
-        cudaFuncSetAttribute(ols_power_kernel<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        ols_power_kernel<PT, false><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+    }
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (variant != 4 && variant != 5 && variant != 6) {
+        if (scen) {
+            cudaFuncSetAttribute(ols_power_kernel<PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel<PT, true><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+        } else {
+            cudaFuncSetAttribute(ols_power_kernel<PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            ols_power_kernel<PT, false><<<blocks, MCP_BLOCK, smem, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims);
+        }
     }
 #endif
     return cudaGetLastError();
@@ -212,8 +224,13 @@ static cudaError_t fit_one(const double* dx, const double* dy, int n, double* do
 #ifndef MCP_TU_IS_OLS
     return cudaErrorInvalidValue;
 #else
-    fit_data_kernel<PT><<<1, 32, 0, st>>>(dx, dy, n, dout);
-    return cudaGetLastError();
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) {
+        fit_data_kernel<PT><<<1, 32, 0, st>>>(dx, dy, n, dout);
+        return cudaGetLastError();
+    } else {
+        (void)dx; (void)dy; (void)n; (void)dout; (void)st;
+        return cudaErrorInvalidValue;
+    }
 #endif
 }
 
@@ -224,8 +241,12 @@ static cudaError_t fit_spec_one(const DevicePlan& pl, const float* plane, int n,
     cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     (void)scratch;
-    glm_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, dout);
-    return cudaGetLastError();
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) {
+        glm_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, dout);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorInvalidValue;
+    }
 #elif defined(MCP_TU_LMM)
     cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
@@ -259,7 +280,7 @@ struct Sel<PT, false> {
     static cudaError_t fit_spec(const DevicePlan&, const float*, int, double*, double*, cudaStream_t) { return cudaErrorInvalidValue; }
 };
 
-#define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#define MCP_ALL_P(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(24) X(32)
 
 bool MCP_TU_FN(launch_power)(int P, int kind, bool scen, const DevicePlan& plan, const KernelArgs& a, cudaError_t* err) {
     if (P < MCP_P_LO || P > MCP_P_HI) return false;

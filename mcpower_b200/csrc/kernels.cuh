@@ -949,6 +949,10 @@ __device__ __forceinline__ void gen_block_post(int b, const SlabT slab, SimCtx& 
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
     if (pl.n_between > 0) between_load(slab, b, cx.sim_local);
+    if (PT > MCP_MAX_TEMPLATE_P) {  // padded width: the columns behind the real design are zeros (plan.h, mcp_template_p)
+        for (int j = pl.P; j < PT; j++)
+            for (int r = 0; r < 4; r++) slab[4 * (j - 1) + r] = 0.0f;
+    }
     if (pl.n_inter > 0) {
         for (int r = 0; r < 4; r++) {
             if (4 * b + r >= pl.max_n) break;
@@ -1053,7 +1057,9 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
     }
     const McpVariant& vr = pl.variants[variant];
     double all_t[MCP_MAX_T];
-    if (vr.p_red == PT) {
+    bool full = false;
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) full = vr.p_red == PT;  // padded widths always fit the kept (real) columns
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (full) {
         double acc[NACC], xty[PT];
 #pragma unroll
         for (int i = 0; i < NACC; i++) acc[i] = st[i * stride];
@@ -1066,7 +1072,8 @@ static __device__ __noinline__ void ols_fit_and_emit(const double* __restrict__ 
         double ph_t[MCP_MAX_PH];
         for (int c = 0; c < pl.n_ph; c++) ph_t[c] = sv.t_sq(pl.ph_contrast[2 * c], pl.ph_contrast[2 * c + 1]);
         emit_fit(so, g, variant, sv.out, PT, all_t, excl, -1, 0, 0, pl.n_ph > 0 ? ph_t : nullptr);
-    } else {
+    }
+    if (!full) {
         // reduced model: gather kept rows/cols of the sufficient statistics (batch.rs:970-1013)
         double Ar[NACC], br[PT];
         const int pr = vr.p_red;

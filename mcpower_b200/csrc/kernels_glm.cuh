@@ -341,6 +341,7 @@ static __device__ __noinline__ void emit_fit_glm(const SimOut& so, int g, int va
 // tau² (NaN), deviance, null deviance.
 template <int PT>
 __global__ void glm_fit_data_kernel(const float* __restrict__ plane, int n, double* __restrict__ out) {
+    static_assert(PT <= MCP_MAX_TEMPLATE_P, "exact widths only");
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const DevicePlan& pl = c_plan;
     const int family = pl.outcome == O_COUNT ? 2 : (pl.link_probit ? 1 : 0);
@@ -431,7 +432,9 @@ __global__ void __launch_bounds__(MCP_BLOCK, MINB) glm_fit_kernel(uint32_t n_sim
                 for (int f = 0; f < pl.n_factors; f++) variant |= (excl[f] != 0 ? 1 : 0) << f;
             }
             const McpVariant& vr = pl.variants[variant];
-            if (vr.p_red == PT) {
+            bool full = false;
+            if constexpr (PT <= MCP_MAX_TEMPLATE_P) full = vr.p_red == PT;  // padded widths always fit the kept (real) columns
+            if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (full) {
                 RegSolver<PT> sv;
                 double beta[PT];
                 glm_irls_reg<PT>(plane, stride, n, family, attempt == 0, sv, beta, go);
@@ -441,7 +444,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MINB) glm_fit_kernel(uint32_t n_sim
                     sv.out.sigma_sq = 1.0;
                     for (int t = 0; t < pl.n_marg; t++) all_t[t] = sv.t_sq(pl.target[t], -1);
                 }
-            } else {
+            }
+            if (!full) {
                 MemSolver<PT> ms;
                 double beta[PT];
                 glm_irls_mem<PT>(plane, stride, n, family, attempt == 0, vr, ms, beta, go);

@@ -38,6 +38,21 @@ namespace mcp {
 #ifndef MCP_LEAN_UNROLL
 #define MCP_LEAN_UNROLL 3
 #endif
+// Instruction-count switches of the headline kernel (profiles/r02_lean_kernel.md has the A/B numbers; every setting computes
+// the same bits):
+//   MCP_LEAN_DYNLP   linear predictor as a uniform loop over the non-zero effects (re-reads those x from the slab) instead of
+//                    DMUL + DADD + two selects for every column — ptxas if-converts the per-column zero-beta test
+//   MCP_LEAN_PUSH32  tail-queue push loop on two 32-bit masks instead of one 64-bit mask
+//   MCP_LEAN_SCAN    tail-queue slots from a warp prefix sum (shuffles) instead of one shared-memory atomic per lane
+#ifndef MCP_LEAN_DYNLP
+#define MCP_LEAN_DYNLP 1
+#endif
+#ifndef MCP_LEAN_PUSH32
+#define MCP_LEAN_PUSH32 1
+#endif
+#ifndef MCP_LEAN_SCAN
+#define MCP_LEAN_SCAN 0
+#endif
 
 
 // Philox4x32-10 with the 10 round keys precomputed per study (rk[2r] = k0 + r·W0, rk[2r+1] = k1 + r·W1).
@@ -62,8 +77,10 @@ struct LeanGeom {
     static constexpr int M = (PT + 2) / 2;        // slots per half = ceil((P+1)/2)
     static constexpr int NACCQ = M * (M + 1) / 2; // accumulators per lane
     static constexpr int MH = (M + 1) & ~1;       // half padded to an even count (16-byte vector loads)
-    static constexpr int ROW = 2 * MH;            // doubles per staged row: [z_0..z_{M-1} pad | z_N, z_{N-1} .. z_{N-M+1} pad]
-    static constexpr int STUDY = 4 * ROW + 2;     // 4 staged rows per study + 16 B: adjacent studies are 4 banks apart
+    static constexpr int HOFF = mcp_stage_geom(M).hoff;    // offset of the reversed high half inside a staged row
+    static constexpr int ROW = mcp_stage_geom(M).row;      // doubles per staged row: [z_0..z_{M-1} pad | z_N, z_{N-1} .. z_{N-M+1} pad]
+    static constexpr int STUDY = mcp_stage_geom(M).study;  // 4 staged rows per study; strides chosen conflict-free (plan.h)
+    static_assert(HOFF >= MH && ROW >= HOFF + MH && STUDY >= 4 * ROW, "staging geometry");
     static constexpr int STUDIES = MCP_BLOCK / 4; // studies per CTA
     static constexpr int WARPS = MCP_BLOCK / 32;
     static constexpr int SLAB_WARP = PT * 128;    // floats per warp: [PT columns][4 producers][8 slots][4 rows]
@@ -101,7 +118,8 @@ __device__ __forceinline__ void lean_acc_row(const double* __restrict__ prow, co
 // One column task of the generation phase: Philox block b of column t (t == k: the residual) -> 4 packed draws ->
 // the lane's float4 in the slab; tail draws keep v and are flagged in tmask (bits 4t.., residual at 60..).
 template <int PT>
-__device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const uint32_t (&rk)[20], float* own, unsigned long long& tmask) {
+__device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const uint32_t (&rk)[20], float* own, unsigned long long& tmask,
+                                              unsigned& tlo, unsigned& thi) {
     const bool is_x = t < k;
     const U4 w = philox4x32_10_rk(b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, rk);
     float4 z;
@@ -113,7 +131,13 @@ __device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const ui
     if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
     if (fabsf(v2) > MCP_NI_BP) { z.z = v2; tb |= 4u; }
     if (fabsf(v3) > MCP_NI_BP) { z.w = v3; tb |= 8u; }
+#if MCP_LEAN_PUSH32
+    // columns 0..7 in the low word, 8..14 in the high word; the residual (slab column PT - 1) takes the top nibble
+    if (is_x && t < 8) tlo |= tb << (4 * t);
+    else thi |= tb << (is_x ? 4 * (t - 8) : 28);
+#else
     tmask |= (unsigned long long)tb << (is_x ? 4 * t : 60);
+#endif
     *reinterpret_cast<float4*>(own + 128 * (is_x ? t : PT - 1)) = z;
 }
 
@@ -127,7 +151,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                                                                                   double* __restrict__ stats) {
     using G = LeanGeom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
-    constexpr int N = G::N, M = G::M, MH = G::MH;
+    constexpr int N = G::N, M = G::M, MH = G::MH, HOFF = G::HOFF;
     const DevicePlan& pl = c_plan;
     if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
@@ -160,18 +184,19 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
     for (int i = 0; i < G::NACCQ; i++) acc[i] = 0.0;
     int g = 0;
     uint32_t n_next = pl.ss[0];
-    const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
-    const double* const r_base = stage + (q >= 2 ? MH : 0);
+    const double* const p_base = stage + ((q == 1 || q == 2) ? HOFF : 0);
+    const double* const r_base = stage + (q >= 2 ? HOFF : 0);
     const int own_off = q * 32 + ((qi ^ (2 * q)) << 2);
     float* const own = wslab + own_off;  // + 128·column: this lane's float4 of 4 rows
     const int n_qsteps = (max_n + 15) >> 4;
     for (int sb = 0; sb < n_qsteps; sb++) {
         // ---- A. generate Philox block 4·sb + q (rows 16·sb + 4q .. +3) for every column
         unsigned long long tmask = 0ull;
+        unsigned tlo = 0u, thi = 0u;
         if (16 * sb + 4 * q < max_n) {
             const uint32_t b = (uint32_t)(4 * sb + q);
 #pragma unroll UNR
-            for (int t = 0; t <= k; t++) lean_gen_task<PT>(t, k, b, rk, own, tmask);
+            for (int t = 0; t <= k; t++) lean_gen_task<PT>(t, k, b, rk, own, tmask, tlo, thi);
         }
         // ---- B. deferred tail branch of the inverse-normal kernel (rng.rs:354-364), warp-cooperative: a lane sees
         // Binomial(4(k+1), 0.0485) tail draws per block, so a per-lane loop runs max-over-32-lanes (~5 at k = 8)
@@ -179,22 +204,56 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
         // offsets of its tail draws (the queue aliases the staged rows, dead in this phase) and the warp drains the
         // queue 32 entries at a time (~2 iterations).
         {
+#if MCP_LEAN_PUSH32
+            const int cnt = __popc(tlo) + __popc(thi);
+#else
             const int cnt = __popcll(tmask);
+#endif
+#if MCP_LEAN_SCAN
+            // exclusive prefix sum of the lanes' counts: five shuffles instead of up to 32 serialised shared-memory atomics
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)(threadIdx.x & 31u) >= d) incl += v;
+            }
+            unsigned slot = (unsigned)(incl - cnt);
+            const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+#else
             unsigned slot = cnt ? atomicAdd(wq_cnt, (unsigned)cnt) : 0u;
+#endif
+#if MCP_LEAN_PUSH32
+            while (tlo) {
+                const int bit = __ffs((int)tlo) - 1;
+                tlo &= tlo - 1u;
+                wq[slot++] = (unsigned short)(own_off + 128 * (bit >> 2) + (bit & 3));
+            }
+            while (thi) {
+                const int bit = __ffs((int)thi) - 1;
+                thi &= thi - 1u;
+                const int c = bit >> 2;
+                wq[slot++] = (unsigned short)(own_off + 128 * (c == 7 ? PT - 1 : 8 + c) + (bit & 3));
+            }
+#else
             while (tmask) {
                 const int bit = __ffsll((long long)tmask) - 1;
                 tmask &= tmask - 1ull;
                 const int c = bit >> 2;
                 wq[slot++] = (unsigned short)(own_off + 128 * (c == 15 ? PT - 1 : c) + (bit & 3));
             }
+#endif
             __syncwarp();
+#if !MCP_LEAN_SCAN
             const unsigned total = *(volatile unsigned*)wq_cnt;
+#endif
             for (unsigned e = threadIdx.x & 31u; e < total; e += 32u) {
                 float* const p = wslab + wq[e];
                 *p = ni_tail_inl(*p);
             }
             __syncwarp();
+#if !MCP_LEAN_SCAN
             if ((threadIdx.x & 31u) == 0u) *wq_cnt = 0u;
+#endif
         }
 #pragma unroll 1
         for (int qq = 0; qq < 4; qq++) {
@@ -252,10 +311,23 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                     }
                 }
                 double lp = 0.0;
-                const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
+#if MCP_LEAN_DYNLP
+                if (!MIX && !INTER && !FACT) {
+                    // every x of this row still sits in the slab: a uniform loop over the non-zero effects (ascending columns,
+                    // separately rounded product and sum — the same chain as below)
+                    for (int t = 0; t < pl.n_nz; t++) {
+                        const int j = pl.nz_col[t];
+                        const double zj = j == 0 ? 1.0 : (double)src[128 * (j - 1)];
+                        lp = lp + zj * pl.nz_beta[t];
+                    }
+                } else
+#endif
+                {
+                    const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
 #pragma unroll
-                for (int j = 0; j < PT; j++)
-                    if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
+                    for (int j = 0; j < PT; j++)
+                        if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
+                }
                 const double ef = (double)src[128 * (PT - 1)];
                 z[PT] = (double)(float)(lp + ef + 0.0);  // same association as row_xy: (lp + e) + u_re, u_re = +0
                 double2* const dst = reinterpret_cast<double2*>(stage + q * G::ROW);
@@ -263,7 +335,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                 for (int j = 0; j < MH / 2; j++) {
                     const int j0 = 2 * j, j1 = 2 * j + 1;
                     dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
-                    dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                    dst[HOFF / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
                 }
             }
             __syncwarp();

@@ -37,8 +37,10 @@ struct Q4Geom {
     static constexpr int N = PT;                 // index of y in Z
     static constexpr int M = (PT + 2) / 2;       // slots per half = ceil((P+1)/2)
     static constexpr int MH = (M + 1) & ~1;      // padded to an even count (16-byte vector loads)
-    static constexpr int ROW = 2 * MH;           // doubles per staged row
-    static constexpr int STUDY = 4 * ROW + 2;    // doubles per study: 4 staged rows + 16 B, so adjacent quads are 4 banks apart
+    static constexpr int HOFF = mcp_stage_geom(M).hoff;    // offset of the reversed high half inside a staged row
+    static constexpr int ROW = mcp_stage_geom(M).row;      // doubles per staged row
+    static constexpr int STUDY = mcp_stage_geom(M).study;  // doubles per study: 4 staged rows; strides chosen conflict-free (plan.h)
+    static_assert(HOFF >= MH && ROW >= HOFF + MH && STUDY >= 4 * ROW, "staging geometry");
     static constexpr int NACCQ = M * (M + 1) / 2;
     static constexpr int STUDIES = MCP_BLOCK / 4;
     // owner lane / local (a, c) of the true entry Z'Z[i][j], j <= i <= N
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
     using G = Q4Geom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int SP = PT | 1;
-    constexpr int N = G::N, M = G::M, MH = G::MH;
+    constexpr int N = G::N, M = G::M, MH = G::MH, HOFF = G::HOFF;
     const DevicePlan& pl = c_plan;
     if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         auto clus_add = [&](int row, const double* zr) {
             const int kc = pl.sizing_fixed_size ? row / clus_cs : row % clus_cs;
             double* const base = csm + kc * (PT + 1);
-            for (int j = q; j <= PT; j += 4) base[j] += j < M ? zr[j] : zr[MH + (N - j)];
+            for (int j = q; j <= PT; j += 4) base[j] += j < M ? zr[j] : zr[HOFF + (N - j)];
         };
         uint32_t lvl_counts[MCP_MAX_LEVELS];  // this lane's share (rows with r == q); summed over the quad at a fit
         uint8_t excl[MCP_MAX_FACTORS];
@@ -227,8 +229,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         int g = 0;
         uint32_t n_next = pl.ss[0];
         // lane-dependent halves of the staged row
-        const double* const p_base = stage + ((q == 1 || q == 2) ? MH : 0);
-        const double* const r_base = stage + (q >= 2 ? MH : 0);
+        const double* const p_base = stage + ((q == 1 || q == 2) ? HOFF : 0);
+        const double* const r_base = stage + (q >= 2 ? HOFF : 0);
         const int n_qsteps = (max_n + 15) >> 4;
         for (int sb = 0; sb < n_qsteps; sb++) {
             {
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
                         for (int j = 0; j < MH / 2; j++) {
                             const int j0 = 2 * j, j1 = 2 * j + 1;
                             dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
-                            dst[MH / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                            dst[HOFF / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
                         }
                     }
                 }

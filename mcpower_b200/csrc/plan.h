@@ -18,6 +18,33 @@
 #define MCP_MAX_INTER_COMP 48
 #define MCP_MAX_MENU 8
 #define MCP_MAX_TEMPLATE_P 16 // kernels with register-resident X'X exist for P <= this
+// Wider designs (17 .. 32 columns: many factor levels) run on the split path's kernels instantiated at two padded widths: the
+// plan carries the real P, the padding columns are generated as zeros with zero effects, and every fit variant keeps only the
+// real columns — i.e. the fit goes through the runtime-p solvers the sparse-factor exclusion already uses (reduced fits on kept
+// columns, batch.rs:970-1013).  Every real entry of X'X / X'y is the same fma chain as in an exact-width kernel.
+#define MCP_WIDE_P_A 24
+#define MCP_WIDE_P_B 32
+static inline constexpr int mcp_template_p(int P) { return P <= MCP_MAX_TEMPLATE_P ? P : (P <= MCP_WIDE_P_A ? MCP_WIDE_P_A : MCP_WIDE_P_B); }
+
+// Staging geometry of the lane-quad kernels (kernels_lean.cuh, kernels_q4.cuh).  Per study, four finished rows are staged in shared
+// memory as Z = [z_0 .. z_{M-1} | z_N, z_{N-1}, .. z_{N-M+1}] (M = ceil((P+1)/2) slots per half; the high half sits `hoff` doubles
+// behind the low one, a row takes `row` doubles, a study `study`).  The three strides decide the bank behaviour of the kernel's
+// shared-memory traffic — 16-byte stores of a finished row by the 4 lanes x 2 studies of a quarter-warp, 16-byte and (odd M)
+// 8-byte loads of the two halves by quarter- / half-warps — and are chosen per M so that every one of them is conflict-free
+// (tools/stage_geometry.py enumerates the candidates; ncu showed 2-way conflicts on the 8-byte loads at M = 5, the headline
+// shape, and 4-way conflicts on the stores at M = 7, 8 with the former 2·MH / 8·MH + 2 rule).
+struct McpStageGeom {
+    int hoff, row, study;
+};
+constexpr McpStageGeom mcp_stage_geom(int M) {
+    return M <= 1 ? McpStageGeom{2, 4, 18}
+         : M == 2 ? McpStageGeom{2, 4, 22}
+         : M == 4 ? McpStageGeom{4, 10, 40}
+         : M == 6 ? McpStageGeom{6, 12, 50}
+         : M == 9 ? McpStageGeom{10, 20, 82}
+         : M >= 10 ? McpStageGeom{(M + 1) & ~1, 2 * ((M + 1) & ~1), 8 * ((M + 1) & ~1) + 2}  // padded wide widths: not tuned
+                  : McpStageGeom{8, 20, 82};  // M = 3, 5, 7, 8
+}
 
 enum McpDist { D_NORMAL = 0, D_BINARY = 1, D_RIGHT_SKEWED = 2, D_LEFT_SKEWED = 3, D_HIGH_KURTOSIS = 4, D_UNIFORM = 5,
                D_UPLOADED_FACTOR = 6, D_UPLOADED_BINARY = 7, D_UPLOADED_DATA = 8 };  // engine-contract/src/distribution.rs:23-25
@@ -70,6 +97,9 @@ struct DevicePlan {
     int32_t inter_cols[MCP_MAX_INTER_COMP];
     double beta[MCP_MAX_P];
     uint32_t beta_nonzero_mask;        // bit j set ⇔ beta[j] != 0
+    int32_t n_nz;                      // the non-zero effects, ascending column order: the linear predictor only visits these ...
+    int8_t nz_col[MCP_MAX_P];          // ... (beta_j == 0 terms add ±0 to a +0-seeded sum: skipping them is bit-exact)
+    double nz_beta[MCP_MAX_P];
     int32_t target[MCP_MAX_T];         // marginal target columns
     int32_t contrast[2 * MCP_MAX_T];   // (pos, neg) pairs
     int32_t n_ph;                      // posthoc pairwise contrasts, flat over blocks (posthoc.rs:40-148)
