@@ -142,7 +142,7 @@ struct DeviceCtx {
     cudaStream_t compute = nullptr, copy = nullptr, ctl = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, done_compute = nullptr, done_copy = nullptr;
     std::vector<cudaEvent_t> wave_events;
-    Arena scratch, tables, outputs, small, between;
+    Arena scratch, tables, outputs, small, between, staging;
     Mailbox* mail = nullptr;            // page-locked, mapped
     unsigned long long* h_counters = nullptr;  // page-locked staging, grow-only
     size_t h_counters_cap = 0;
@@ -794,6 +794,56 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
 }
 
+// ---- wave transposition of the per-fit outputs ---------------------------------------------------------------------------
+// The fit kernels run one (study, grid point) fit per thread with the studies of a warp at the SAME grid point: in the
+// sim-major BatchResult layout their bytes lie n_ss·W apart (every store its own sector: the 50-point sweep wrote its 1.1 GB
+// at ~100 GB/s and took 15 % longer than in COUNTS mode).  Waves of a multi-point BYTES / CAPTURE call therefore write a
+// grid-point-major staging block ([g][sim][W], neighbouring studies = neighbouring bytes) and this kernel moves the wave into
+// the sim-major tensors: coalesced reads along the studies, coalesced writes along the grid points, through shared memory.
+struct TransposeDesc {
+    const uint8_t* in;   // [n_ss][cnt][w]
+    uint8_t* out;        // [cnt][n_ss][w] (already offset to the wave's first sim)
+    uint32_t w;          // bytes per cell
+};
+struct TransposeArgs {
+    TransposeDesc d[10];
+};
+constexpr int kTransposeSims = 32, kTransposeThreads = 256, kTransposeTileBytes = 32 * 1024;
+
+__global__ void __launch_bounds__(kTransposeThreads) transpose_outputs_kernel(TransposeArgs a, uint32_t cnt, uint32_t n_ss) {
+    extern __shared__ uint8_t tile[];  // [grid point in chunk][sim in tile][w]: a flat copy of the source rows
+    const TransposeDesc d = a.d[blockIdx.z];
+    const uint32_t w = d.w;
+    const uint32_t gc = max(1u, min(n_ss, (uint32_t)kTransposeTileBytes / (kTransposeSims * w)));  // grid points per chunk
+    const uint32_t s0 = blockIdx.x * kTransposeSims, ns = min((uint32_t)kTransposeSims, cnt - s0);
+    const uint32_t g0 = blockIdx.y * gc;
+    if (g0 >= n_ss) return;
+    const uint32_t ng = min(gc, n_ss - g0);
+    const uint32_t row = ns * w;  // contiguous bytes of one grid point of this tile
+    for (uint32_t gl = 0; gl < ng; gl++) {
+        const uint8_t* src = d.in + ((size_t)(g0 + gl) * cnt + s0) * w;
+        for (uint32_t i = threadIdx.x; i < row; i += kTransposeThreads) tile[gl * row + i] = src[i];
+    }
+    __syncthreads();
+    // destination: for sim s the ng·w bytes of its grid points g0 .. g0 + ng − 1 are contiguous; one warp per sim
+    const uint32_t out_row = ng * w;
+    for (uint32_t sl = threadIdx.x >> 5; sl < ns; sl += kTransposeThreads / 32) {
+        uint8_t* dst = d.out + ((size_t)(s0 + sl) * n_ss + g0) * w;
+        uint32_t i = threadIdx.x & 31u;
+        uint32_t gl = i / w, b = i - gl * w;  // i = gl·w + b, advanced by 32 per step without dividing again
+        const uint32_t dg = 32u / w, db = 32u - dg * w;
+        for (; i < out_row; i += 32u) {
+            dst[i] = tile[gl * row + sl * w + b];
+            gl += dg;
+            b += db;
+            if (b >= w) {
+                b -= w;
+                gl++;
+            }
+        }
+    }
+}
+
 // ---- kernel dispatch: ask each kernel translation unit in turn (launch.h) -------------------------
 // bytes of one per-study scenario design at template width P (an upper bound within the width class)
 static size_t scen_design_bytes(int P) {
@@ -1001,6 +1051,39 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         const size_t design_bytes = ols_variant == 6 && !pl.optimistic ? scen_design_bytes(lw.P) : 0;
         lmm_scratch = static_cast<double*>(cx.scratch.get((size_t)wave * (n_ss * E * sizeof(double) + design_bytes)));
     }
+    // grid-point-major staging of one wave's per-fit outputs (see transpose_outputs_kernel); a single grid point needs none
+    const bool staged = sh.copies && n_ss > 1;
+    DevicePlan stg;  // the out_* pointers of the staging block
+    std::memset(&stg, 0, sizeof stg);
+    if (staged) {
+        const size_t wc = (size_t)std::min<uint32_t>(wave, n_sims) * n_ss;
+        size_t total = 0;
+        if (bytes) {
+            total += 2 * Carver::pad(wc * T) + Carver::pad(wc);
+            if (pl.out_overall) total += Carver::pad(wc);
+            if (pl.out_fx) total += Carver::pad(wc * F);
+            if (pl.out_ph_unc) total += 2 * Carver::pad(wc * pl.n_ph);
+            if (pl.out_joint) total += 2 * Carver::pad(wc);
+        }
+        if (capture) total += Carver::pad(wc * T * sizeof(double));
+        Carver sc(cx.staging.get(total));
+        if (bytes) {
+            stg.out_unc = sc.take<uint8_t>(wc * T);
+            stg.out_cor = sc.take<uint8_t>(wc * T);
+            stg.out_conv = sc.take<uint8_t>(wc);
+            if (pl.out_overall) stg.out_overall = sc.take<uint8_t>(wc);
+            if (pl.out_fx) stg.out_fx = sc.take<uint8_t>(wc * F);
+            if (pl.out_ph_unc) {
+                stg.out_ph_unc = sc.take<uint8_t>(wc * pl.n_ph);
+                stg.out_ph_cor = sc.take<uint8_t>(wc * pl.n_ph);
+            }
+            if (pl.out_joint) {
+                stg.out_joint = sc.take<uint8_t>(wc);
+                stg.out_bh = sc.take<uint8_t>(wc);
+            }
+        }
+        if (capture) stg.out_tsq = sc.take<double>(wc * T);
+    }
     if (pl.n_between > 0) {  // representative-row values of the cluster-level predictors, [cluster][column][study in wave]
         const size_t cs = (size_t)std::max(s.sizing_value, 1);
         const size_t n_rep = s.sizing_fixed_size ? ((size_t)pl.max_n + cs - 1) / cs : std::min<size_t>(cs, (size_t)pl.max_n);
@@ -1016,7 +1099,13 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         const uint32_t cnt = (uint32_t)std::min<uint64_t>(wave, n_sims - done);
         // the byte tensors are indexed by the sim's position in the shard, so waves shift the base pointers
         DevicePlan shifted = pl;
-        if (done > 0 && sh.copies) {
+        if (staged) {  // this wave writes the staging block, grid-point-major with stride = its own study count
+            shifted.out_stride = cnt;
+            shifted.out_unc = stg.out_unc; shifted.out_cor = stg.out_cor; shifted.out_conv = stg.out_conv;
+            shifted.out_overall = stg.out_overall; shifted.out_fx = stg.out_fx; shifted.out_joint = stg.out_joint;
+            shifted.out_bh = stg.out_bh; shifted.out_ph_unc = stg.out_ph_unc; shifted.out_ph_cor = stg.out_ph_cor;
+            shifted.out_tsq = stg.out_tsq;
+        } else if (done > 0 && sh.copies) {
             if (bytes) {
                 shifted.out_unc = pl.out_unc + done * n_ss * T;
                 shifted.out_cor = pl.out_cor + done * n_ss * T;
@@ -1036,6 +1125,43 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         dispatch_power(lw.P, kind, shifted, ka);
         sh.h2d += sizeof(DevicePlan);
         sh.launches += launches_per_wave;
+        if (staged) {  // staging → the sim-major device tensors, all of the wave's tensors in one launch
+            TransposeArgs ta;
+            std::memset(&ta, 0, sizeof ta);
+            unsigned nt = 0, wmax = 1;
+            auto add = [&](const void* in, void* out, size_t w) {
+                if (!in || !out || w == 0) return;
+                ta.d[nt].in = static_cast<const uint8_t*>(in);
+                ta.d[nt].out = static_cast<uint8_t*>(out) + done * n_ss * w;
+                ta.d[nt].w = (uint32_t)w;
+                wmax = std::max<unsigned>(wmax, (unsigned)w);
+                nt++;
+            };
+            add(stg.out_unc, pl.out_unc, (size_t)T);
+            add(stg.out_cor, pl.out_cor, (size_t)T);
+            add(stg.out_conv, pl.out_conv, 1);
+            add(stg.out_overall, pl.out_overall, 1);
+            add(stg.out_fx, pl.out_fx, (size_t)F);
+            add(stg.out_joint, pl.out_joint, 1);
+            add(stg.out_bh, pl.out_bh, 1);
+            add(stg.out_ph_unc, pl.out_ph_unc, (size_t)pl.n_ph);
+            add(stg.out_ph_cor, pl.out_ph_cor, (size_t)pl.n_ph);
+            add(stg.out_tsq, pl.out_tsq, (size_t)T * sizeof(double));
+            if (nt > 0) {
+                // grid.y covers the tensor with the narrowest cells (most grid points per chunk is per tensor: blocks past a
+                // tensor's last chunk return at once)
+                const unsigned gc_min = std::max(1u, std::min<unsigned>(n_ss, (unsigned)kTransposeTileBytes / (kTransposeSims * wmax)));
+                const dim3 grid((cnt + kTransposeSims - 1) / kTransposeSims, (n_ss + gc_min - 1) / gc_min, nt);
+                static bool attr_set[64] = {};
+                if (!attr_set[cx.dev]) {
+                    CUDA_CHECK(cudaFuncSetAttribute(transpose_outputs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTransposeTileBytes + 8192));
+                    attr_set[cx.dev] = true;
+                }
+                transpose_outputs_kernel<<<grid, kTransposeThreads, kTransposeTileBytes + 8192, st>>>(ta, cnt, n_ss);
+                CUDA_CHECK(cudaGetLastError());
+                sh.launches += 1;
+            }
+        }
         if (sh.copies) {  // this wave's slices travel on the copy stream while the next wave computes
             cudaEvent_t ev = cx.wave_event(sh.waves);
             CUDA_CHECK(cudaEventRecord(ev, st));

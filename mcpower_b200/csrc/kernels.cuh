@@ -408,8 +408,9 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
         count_flag(cs, cg, pl.off_ph_cor + c, ph_cor[c] != 0);
     }
     // ---- BatchResult byte tensors (spec.rs:552-600), sim-major
+    // cell index: sim-major, or (waves of a multi-point BYTES / CAPTURE call) the grid-point-major staging layout
+    const size_t cell = pl.out_stride ? (size_t)g * pl.out_stride + so.sim_local : so.sim_local * pl.n_ss + g;
     if (pl.out_unc) {
-        const size_t cell = so.sim_local * pl.n_ss + g;
         for (int t = 0; t < T; t++) {
             pl.out_unc[cell * T + t] = unc[t];
             pl.out_cor[cell * T + t] = cor[t];
@@ -422,14 +423,12 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
             for (int f = 0; f < pl.n_factors; f++) pl.out_fx[cell * pl.n_factors + f] = excl_flags ? excl_flags[f] : 0;
     }
     if (pl.out_ph_unc && NPH > 0) {
-        const size_t cell = so.sim_local * pl.n_ss + g;
         for (int c = 0; c < NPH; c++) {
             pl.out_ph_unc[cell * NPH + c] = ph_unc[c];
             pl.out_ph_cor[cell * NPH + c] = ph_cor[c];
         }
     }
     if (pl.out_tsq) {
-        const size_t cell = so.sim_local * pl.n_ss + g;
         for (int t = 0; t < T; t++) pl.out_tsq[cell * T + t] = all_t[t];
     }
 }

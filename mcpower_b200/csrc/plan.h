@@ -154,6 +154,9 @@ struct DevicePlan {
     uint8_t* out_ph_unc;               // [n_sims][n_ss][n_ph] or NULL
     uint8_t* out_ph_cor;
     double* out_tsq;                   // [n_sims][n_ss][T] capture or NULL
+    uint32_t out_stride;               // 0: the out_* tensors are sim-major, [sim][grid point][..]; S > 0: they are one wave's
+                                       // grid-point-major staging, [grid point][S sims][..] — the studies of a warp then write
+                                       // neighbouring bytes — and the host transposes the wave into the sim-major tensors
     int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
     int32_t counter_width;             // 4T + 6 + n_factors + 4 n_ph
     int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor, off_sing, off_fsep;  // counter-row offsets (below)

@@ -1487,6 +1487,16 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
     return ORC_OK;
 }
 
+/* The lower Cholesky factor populate_design leaves for one study (column-major k x k; data_gen.rs:990-1093): test hook for the
+ * PSD-repair cross-check against an independent eigensolver (tests/test_oracle_golden.py). */
+int orc_design_factor(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, double* l_colmajor) {
+    Ws* w = ws_new(s, 4);
+    int rc = populate_design(s, base_seed, sim_id, w);
+    if (!rc) memcpy(l_colmajor, w->l_design, sizeof(double) * (size_t)w->k * w->k);
+    ws_free(w);
+    return rc;
+}
+
 static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* batch.rs:208-330 */
     if (s->estimator == ORC_EST_MLE && !s->has_cluster) return fail(ORC_ERR_INVALID_SPEC, "estimator Mle requires ClusterSpec");
     if (ss) {

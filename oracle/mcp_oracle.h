@@ -108,6 +108,9 @@ void orc_planar_normals(uint64_t base_seed, uint64_t sim_id, uint32_t cls, uint3
 void orc_sample_t(uint64_t base_seed, uint64_t sim_id, double df, int n, double* out);
 void orc_draw_residual(uint64_t base_seed, uint64_t sim_id, int dist, double df, int n, double* out);
 
+/* per-study lower Cholesky factor of the (perturbed, PSD-repaired) correlation, column-major k x k */
+int orc_design_factor(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, double* l_colmajor);
+
 /* ---- transforms (distributions.rs:32-56, data_gen.rs:1106-1182, marginals/t3.rs) ---- */
 double orc_exp(double x);
 double orc_log(double x);

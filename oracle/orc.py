@@ -112,6 +112,7 @@ def lib():
     L.orc_build_crit_table.argtypes = [P(OrcSpec), P(u32), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl)]
     L.orc_apply_correction.argtypes = [C.c_int, P(dbl), C.c_int, dbl, P(dbl), P(C.c_uint8)]
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
+    L.orc_design_factor.argtypes = [P(OrcSpec), u64, u64, P(dbl)]
     L.orc_fit_ols.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
                               P(C.c_int)]
     L.orc_fit_glm.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
@@ -348,6 +349,15 @@ def generate_sim(spec: dict, base_seed: int, sim_id: int, max_n: int):
     _check(lib().orc_generate_sim(C.byref(ps.c), base_seed, sim_id, max_n, _ptr(x, C.c_float), _ptr(y, C.c_float),
                                   _ptr(ids, C.c_int32)))
     return x.T, y, ids
+
+
+def design_factor(spec: dict, base_seed: int, sim_id: int) -> np.ndarray:
+    """Lower Cholesky factor L [k, k] of the study's (perturbed, PSD-repaired) correlation (populate_design)."""
+    ps = PackedSpec(spec)
+    k = int(spec["n_non_factor"])
+    out = np.zeros((k, k))
+    _check(lib().orc_design_factor(C.byref(ps.c), base_seed & 0xFFFFFFFFFFFFFFFF, sim_id, _ptr(out, C.c_double)))
+    return out.T.copy()  # column-major in C
 
 
 def fit_ols(x, y):
