@@ -101,9 +101,9 @@ def test_bytes_readback_is_pipelined_and_bit_identical():
 
 def test_large_bytes_call_splits_into_pipelined_waves():
     spec = S.headline_spec()
-    n = 1 << 24  # 16 Mi sims x (2 + 2 + 1) bytes = 80 MiB of byte tensors
-    got = M.run_batch(spec, [500], n, SEED, mode=M.MODE_COUNTS | M.MODE_BYTES)
-    assert got.n_waves >= 2
+    n = 1 << 26  # 64 Mi sims x (2 + 2 + 1) bytes = 320 MiB of byte tensors: two pieces of >= 128 MiB
+    got = M.run_batch(spec, [60], n, SEED, mode=M.MODE_COUNTS | M.MODE_BYTES)
+    assert got.n_waves == 2
     agg = np.zeros_like(got.counters)
     agg[0, :2] = got.uncorrected.sum(axis=0, dtype=np.uint64)[0]
     assert np.array_equal(agg[0, :2], got.counters[0, :2])

@@ -363,7 +363,7 @@ def test_glm_wave_split_is_invariant():
     a = M.run_batch(s, [100, 300], 700, SEED, mode=ALL)
     b = M.run_batch(s, [100, 300], 700, SEED, mode=ALL, wave_sims=256)
     assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
-    assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 6  # 3 waves x (generate, fit)
+    assert np.array_equal(a.t_sq, b.t_sq, equal_nan=True) and b.gpu_launches == 9  # 3 waves x (generate, fit, transpose the wave's per-fit outputs)
 
 
 # ------------------------------------------------------------------ random-intercept LMM, REML (BASELINE config 5)
@@ -387,14 +387,14 @@ def test_lmm_and_glm_under_scenarios_match_oracle():
     got = M.run_batch(m, [48, 96, 240], 384, SEED, mode=ALL)
     want = orc.run_batch(m, [48, 96, 240], 384, SEED, n_threads=orc.host_threads(), capture=True)
     assert_batch_equal(got, want)
-    assert got.gpu_launches == 3  # designs, generate, fit
+    assert got.gpu_launches == 4  # designs, generate, fit, transpose (BYTES / CAPTURE on a multi-point grid)
     g = S.logit_spec()
     g["correlation"] = [1, 0.4, 0.2, 0.4, 1, 0.3, 0.2, 0.3, 1]
     g["scenario"] = S.scenario("doomer")
     got = M.run_batch(g, [80, 200, 500], 384, SEED + 1, mode=ALL)
     want = orc.run_batch(g, [80, 200, 500], 384, SEED + 1, n_threads=orc.host_threads(), capture=True)
     assert_batch_equal(got, want)
-    assert got.gpu_launches == 3
+    assert got.gpu_launches == 4
 
 
 def test_lmm_fixed_size_unbalanced_prefixes_match_oracle():
@@ -431,7 +431,9 @@ def test_results_independent_of_wave_size_and_shard_offset(ols_kernel_choice):
     b = M.run_batch(s, grid, 1000, SEED, mode=ALL, wave_sims=137)
     assert np.array_equal(a.uncorrected, b.uncorrected) and np.array_equal(a.counters, b.counters)
     # the lean and split paths round a wave down to whole 128-study groups and launch two kernels per wave (accumulate, solve)
-    assert b.gpu_launches == (2 * math.ceil(1000 / 128) if ols_kernel_choice in ("lean", "split") else math.ceil(1000 / 137))  # optimistic spec
+    # per wave: accumulate + solve on the lean / split paths (one launch on the cross-check kernels), + the transposition of the
+    # wave's per-fit outputs (BYTES / CAPTURE on a multi-point grid)
+    assert b.gpu_launches == (3 * math.ceil(1000 / 128) if ols_kernel_choice in ("lean", "split") else 2 * math.ceil(1000 / 137))  # optimistic spec
     c1 = M.run_batch(s, grid, 600, SEED, mode=ALL, sim_begin=0)
     c2 = M.run_batch(s, grid, 400, SEED, mode=ALL, sim_begin=600)
     assert np.array_equal(np.concatenate([c1.uncorrected, c2.uncorrected]), a.uncorrected)
