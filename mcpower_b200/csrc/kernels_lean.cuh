@@ -53,6 +53,12 @@ namespace mcp {
 #ifndef MCP_LEAN_SCAN
 #define MCP_LEAN_SCAN 0
 #endif
+//   MCP_LEAN_SCALAR_PAIRS  how many of a column task's two draw pairs run the central polynomial in scalar FMUL / FADD (the
+//                    other(s) packed f32x2): packed halves the issue slots but runs on the FMA-heavy pipe next to Philox's
+//                    IMAD.WIDE; scalar can use the FMA-lite pipe
+#ifndef MCP_LEAN_SCALAR_PAIRS
+#define MCP_LEAN_SCALAR_PAIRS 0
+#endif
 
 
 // Philox4x32-10 with the 10 round keys precomputed per study (rk[2r] = k0 + r·W0, rk[2r+1] = k1 + r·W1).
@@ -124,8 +130,18 @@ __device__ __forceinline__ void lean_gen_task(int t, int k, uint32_t b, const ui
     const U4 w = philox4x32_10_rk(b, is_x ? (uint32_t)t : 0u, is_x ? 1u : 2u, 0u, rk);
     float4 z;
     float v0, v1, v2, v3;
+#if MCP_LEAN_SCALAR_PAIRS >= 2
+    v0 = word_to_v(w.x); v1 = word_to_v(w.y);
+    z.x = ni_central(v0); z.y = ni_central(v1);
+#else
     ni_central_pair_packed(w.x, w.y, z.x, z.y, v0, v1);
+#endif
+#if MCP_LEAN_SCALAR_PAIRS >= 1
+    v2 = word_to_v(w.z); v3 = word_to_v(w.w);
+    z.z = ni_central(v2); z.w = ni_central(v3);
+#else
     ni_central_pair_packed(w.z, w.w, z.z, z.w, v2, v3);
+#endif
     unsigned tb = 0u;
     if (fabsf(v0) > MCP_NI_BP) { z.x = v0; tb |= 1u; }
     if (fabsf(v1) > MCP_NI_BP) { z.y = v1; tb |= 2u; }
