@@ -443,7 +443,8 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     }
     if (s.between_cols.size() > MCP_MAX_P) unsupported("between_var_indices > " + std::to_string(MCP_MAX_P));
     if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
-    if (s.has_slopes_or_groupings) unsupported("random slopes / extra groupings");
+    if (s.has_slopes_or_groupings) unsupported("more than one random slope / extra groupings");
+    if (s.n_slopes > 0 && s.P() > MCP_MAX_TEMPLATE_P) unsupported("random slopes with n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
     if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
     for (int v : s.new_dists)
         if (v >= D_UPLOADED_FACTOR) unsupported("uploaded_* distributions in the scenario menu");
@@ -600,6 +601,10 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         const long long dfi = std::max<long long>(std::llround(df), 1);
         pl.re_words = pl.re_dist == R_HIGH_KURTOSIS ? (int)(1 + dfi) : ((pl.re_dist == R_RIGHT_SKEWED || pl.re_dist == R_LEFT_SKEWED) ? (int)dfi : 1);
     }
+    pl.n_slopes = s.has_cluster ? s.n_slopes : 0;
+    pl.slope_col = s.slope_col;
+    pl.slope_variance = s.slope_variance;
+    pl.slope_corr = s.slope_corr;
     // cluster-level predictors: only with a cluster (data_gen.rs:619-620).  A broadcast factor no longer follows the exact walk
     // row by row, so its per-level counts are read off the statistics like a sampled factor's.
     pl.n_between = s.has_cluster ? (int)s.between_cols.size() : 0;
@@ -1009,10 +1014,10 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
         const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
                               (size_t)(MCP_BLOCK / 4) * (((nc_ * (P_ + 1)) | 1) + (nc_ | 1)) * sizeof(double);
-        lmm_quad = smem_q <= 56 * 1024;
+        lmm_quad = smem_q <= 56 * 1024 && pl.n_slopes == 0;  // the random-slope sums live in HBM (one-thread-per-study generator)
         // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
         // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
-        const size_t per_sim = (nc_ * (lw.P + 1) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
+        const size_t per_sim = (nc_ * (lw.P + 1) * (1 + pl.n_slopes) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
                                (pl.optimistic ? 0 : scen_design_bytes(lw.P));  // + scenario designs behind the layout
         const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
         wave = std::min(wave, cap);
@@ -1954,7 +1959,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
             info->crit_sq_uncorrected = unc;
         }
         const double nan = crit::kNaN;
-        info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = nan;
+        info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = info->slope_var_hat = info->slope_corr_hat = nan;
         DeviceCtx& cx = ctx_for(device);
         std::lock_guard<std::mutex> lock(cx.mu);
         const cudaStream_t st = cx.compute;
@@ -2011,7 +2016,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         bind_tables(lw, lw.plan, dblob);
         CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
         lw.plan.error_flag = cx.d_error;
-        const size_t n_out = (size_t)3 * P + 7, n_csum = n_clusters * (size_t)(P + 1);
+        const size_t n_out = (size_t)3 * P + 9, n_csum = n_clusters * (size_t)(P + 1) * (size_t)(1 + lw.plan.n_slopes);
         Carver oc(cx.outputs.get(Carver::pad(plane.size() * sizeof(float)) + Carver::pad(n_csum * sizeof(double)) + Carver::pad(n_out * sizeof(double))));
         float* dplane = oc.take<float>(plane.size());
         double* dcsum = oc.take<double>(n_csum);
@@ -2043,6 +2048,8 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         info->tau_sq_hat = o[3 * P + 4];
         info->deviance = o[3 * P + 5];
         info->deviance_null = o[3 * P + 6];
+        info->slope_var_hat = o[3 * P + 7];
+        info->slope_corr_hat = o[3 * P + 8];
     });
 }
 

@@ -99,7 +99,7 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const int nc_cap = pl.sizing_fixed_size ? (pl.max_n + cs - 1) / cs : cs;
         const int clus_doubles = (int)LY::csum_doubles(nc_cap);
         const size_t smem_q = G::smem_bytes(0, 0, false) + (size_t)G::STUDIES * (size_t)((clus_doubles | 1) + (nc_cap | 1)) * sizeof(double);
-        if (smem_q <= 56 * 1024) {
+        if (smem_q <= 56 * 1024 && pl.n_slopes == 0) {  // (the random-slope sums live in HBM: one-thread-per-study generator)
             // generator on the lane-quad kernel: cluster sums in shared memory (4 CTAs per SM fit), no read-modify-write of HBM per
             // row; on the scenario path the per-study designs come from scen_design_kernel and sit behind the layout
             double* snap = a.scratch_d + LY::csum_doubles(nc_cap) * stride;

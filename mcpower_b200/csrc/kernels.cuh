@@ -442,6 +442,7 @@ struct SimCtx {
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
     uint32_t sim_local = 0;        // the study's index inside the launch (addresses per-wave scratch)
+    double sl10 = 0.0, sl11 = 0.0; // second row of chol(D) of this study's random-effect covariance (random slope)
 };
 
 // Residuals of the four rows of Philox block `blk` from the CLASS_RESID slots (data_gen.rs:412-484); slot0 = the slot-0
@@ -691,9 +692,9 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
 
 // Random effect of cluster c: u_c = f32(draw_residual(re_dist, re_df) · tau) (data_gen.rs:146-161, 1289-1320).  The draws sit
 // at the head of the study's sequential stream, re_words words each, so cluster c's draw is counter-addressed at c · re_words.
-static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
+// One draw_residual(re_dist, re_df) (data_gen.rs:1289-1320) whose first word is sequential-stream word w0.
+static __device__ __noinline__ double re_draw(SimCtx& cx, uint32_t w0) {
     const DevicePlan& pl = c_plan;
-    const uint32_t w0 = c * (uint32_t)pl.re_words;
     const int dist = pl.has_lme ? pl.re_dist : R_NORMAL;
     double d;
     if (dist == R_NORMAL) {
@@ -720,7 +721,21 @@ static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
             d = dist == R_LEFT_SKEWED ? -centered : centered;
         }
     }
-    return (double)(float)(d * cx.tau);
+    return d;
+}
+static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
+    return (double)(float)(re_draw(cx, c * (uint32_t)c_plan.re_words) * cx.tau);
+}
+// Random-slope effect of cluster c (data_gen.rs:163-213): z_1 is drawn behind ALL the intercept draws, z_0 is recovered from the
+// f32 intercept effect, u_1 = f32(L10 z_0 + L11 z_1) with L = chol(diag(tau) R diag(tau)).
+static __device__ __noinline__ double cluster_slope_effect(SimCtx& cx, uint32_t c, double u0) {
+    const DevicePlan& pl = c_plan;
+    const double z0 = cx.tau > 0.0 ? u0 / cx.tau : 0.0;
+    const double z1 = re_draw(cx, ((uint32_t)pl.n_clusters + c) * (uint32_t)pl.re_words);
+    double uk = 0.0;
+    uk += cx.sl10 * z0;
+    uk += cx.sl11 * z1;
+    return (double)(float)uk;
 }
 
 // Cluster-level predictors (data_gen.rs:605-640): on every non-representative row the marked columns take the value of the
@@ -980,8 +995,16 @@ __device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t 
     cx.k1 = (uint32_t)(key >> 32);
     cx.seq.init(key);
     cx.tau = !pl.has_cluster ? 0.0 : (sd ? sd->tau : sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0));
-    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words : 0u;
+    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words * (uint32_t)(1 + pl.n_slopes) : 0u;
     cx.sim_local = sim_local;
+    if (pl.n_slopes > 0) {  // chol_lower(D) (data_gen.rs:55-75), D = diag(tau) R diag(tau) with this study's tau0
+        const double tau1 = sqrt(pl.slope_variance > 0.0 ? pl.slope_variance : 0.0);
+        const double d00 = cx.tau * 1.0 * cx.tau, d10 = tau1 * pl.slope_corr * cx.tau, d11 = tau1 * 1.0 * tau1;
+        const double l00 = sqrt(d00 > 0.0 ? d00 : 0.0);
+        cx.sl10 = l00 > 0.0 ? d10 / l00 : 0.0;
+        const double r11 = d11 - cx.sl10 * cx.sl10;
+        cx.sl11 = sqrt(r11 > 0.0 ? r11 : 0.0);
+    }
 }
 
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
@@ -1005,6 +1028,8 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
         // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
         if (cx.utab) u_re = cx.utab[cid];
         else if (cid < (uint32_t)pl.n_clusters) u_re = cluster_effect(cx, cid);
+        if (pl.n_slopes > 0 && cid < (uint32_t)pl.n_clusters)  // data_gen.rs:836-842: u_re += u_1 · x[slope column]
+            u_re += cluster_slope_effect(cx, cid, u_re) * (double)slab[4 * (pl.slope_col - 1) + r];
     }
     if (SCEN) {
         // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)

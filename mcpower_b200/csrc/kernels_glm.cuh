@@ -369,6 +369,8 @@ __global__ void glm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     out[3 * PT + 4] = nan;
     out[3 * PT + 5] = go.deviance;
     out[3 * PT + 6] = go.deviance_null;
+    out[3 * PT + 7] = nan;
+    out[3 * PT + 8] = nan;
 }
 
 // Stage 1 is the lane-quad kernel in PLANE mode (kernels_q4.cuh): it generates the study's max_n rows once — the same gen_block /

@@ -271,7 +271,8 @@ __device__ __forceinline__ uint32_t lmm_cluster_rows(const DevicePlan& pl, int k
 //   csum element (k, j) = csum[(k * (PT+1) + j) * stride]; kept == nullptr → full model.
 template <int PT>
 static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restrict__ csum, size_t stride, int n, int n_clusters,
-                                            const int8_t* kept, int& converged, int& boundary, double* theta_out = nullptr) {
+                                            const int8_t* kept, int& converged, int& boundary, double* theta_out = nullptr,
+                                            int cluster_doubles = PT + 1) {
     const DevicePlan& pl = c_plan;
     const int p = c.p, nt = p * (p + 1) / 2;
     c.ng = 0;
@@ -291,7 +292,7 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
         else if ((double)cnk == c.grp_n[0]) g = 0;
         else { g = 1; if (c.ng == 1) { c.ng = 2; c.grp_n[1] = (double)cnk; } }
         c.grp_m[g] += 1.0;
-        const double* base = csum + (size_t)k * (PT + 1) * stride;
+        const double* base = csum + (size_t)k * cluster_doubles * stride;
         for (int j = 0; j < p; j++) sx[j] = base[(size_t)(kept ? kept[j] : j) * stride];
         sx[p] = base[(size_t)PT * stride];
         int t = 0;
@@ -318,6 +319,154 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
     const double f = lmm_dev<PT>(c, th);  // leaves L, beta, sigma² at theta-hat
     if (isinf(f) || f != f) converged = 0;
     if (theta_out) *theta_out = th;
+}
+
+// ---- random intercept + ONE random slope (q = 2): profiled REML over theta = (l00, l10, l11), Lambda = [[l00, 0], [l10, l11]].
+// Replaces glmm::fit_on + BOBYQA for this shape (batch.rs:1214-1561, mixed_workspace.rs:203-272); the oracle's slope_dev /
+// slope_nm / lmm_slope_fit are the op-for-op twins.  Per cluster: cs1 = sums of [x | y], cs2 = sums of x_s · [x | y];
+// Z'Z = [[n_c, cs1[s]], [cs1[s], cs2[s]]]; M_c = Lambda' Z'Z Lambda + I = L_c L_c'; R_c = L_c^-1 Lambda' Z_c'[X | y];
+// A = X'X − Σ R_c'R_c, b, c likewise; dev = Σ log det M_c + log det A + (n − p) log sigma².  Full model only: a reduced fit
+// (sparse-factor exclusion, test design) strips the slope like the reference (batch.rs:1357-1375).
+#define MCP_SLOPE_NM_MAXEVAL 900
+#define MCP_SLOPE_THETA_MAX 30.0
+template <int PT>
+struct SlopeData {
+    const double* cs;  // cluster k, entry j of cs1 at cs[(k·2(PT+1) + j)·stride], of cs2 at + (PT+1)
+    size_t stride;
+    int n, n_clusters, slope_col, n_eval;
+};
+
+template <int PT>
+static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d, const double* th) {
+    const DevicePlan& pl = c_plan;
+    constexpr int NT = PT * (PT + 1) / 2;
+    const double l00 = th[0] > 0.0 ? th[0] : 0.0, l10 = th[1], l11 = th[2] > 0.0 ? th[2] : 0.0;
+    for (int e = 0; e < NT; e++) c.A[e] = c.xtx[e];
+    for (int j = 0; j < PT; j++) c.b[j] = c.xty[j];
+    double cc = c.yty, ldv = 0.0;
+    double r0[PT + 1], r1[PT + 1];
+    for (int k = 0; k < d.n_clusters; k++) {
+        const uint32_t cnk = lmm_cluster_rows(pl, k, d.n);
+        if (cnk == 0) continue;
+        const double* s1 = d.cs + (size_t)k * 2 * (PT + 1) * d.stride;
+        const double* s2 = s1 + (size_t)(PT + 1) * d.stride;
+        const double S00 = (double)cnk, S01 = s1[(size_t)d.slope_col * d.stride], S11 = s2[(size_t)d.slope_col * d.stride];
+        const double a0 = l00 * S00 + l10 * S01, a1 = l00 * S01 + l10 * S11, b1 = l11 * S11, b0 = l11 * S01;
+        const double m00 = (a0 * l00 + a1 * l10) + 1.0, m10 = b0 * l00 + b1 * l10, m11 = b1 * l11 + 1.0;
+        const double c00 = sqrt(m00), c10 = m10 / c00, c11 = sqrt(m11 - c10 * c10);
+        ldv += own_log(c00) + own_log(c11);
+        for (int j = 0; j <= PT; j++) {
+            const double v1 = s1[(size_t)j * d.stride], v2 = s2[(size_t)j * d.stride];
+            const double t0 = l00 * v1 + l10 * v2, t1 = l11 * v2;
+            r0[j] = t0 / c00;
+            r1[j] = (t1 - c10 * r0[j]) / c11;
+        }
+        int t = 0;
+        for (int a = 0; a < PT; a++) {
+            for (int bb = 0; bb <= a; bb++) {
+                c.A[t] = fma(-r0[a], r0[bb], c.A[t]);
+                c.A[t] = fma(-r1[a], r1[bb], c.A[t]);
+                t++;
+            }
+            c.b[a] = fma(-r0[a], r0[PT], c.b[a]);
+            c.b[a] = fma(-r1[a], r1[PT], c.b[a]);
+        }
+        cc = fma(-r0[PT], r0[PT], cc);
+        cc = fma(-r1[PT], r1[PT], cc);
+    }
+    d.n_eval++;
+    c.ms.factor_and_solve(c.A, c.b, PT, cc, 0.0, c.n_rows);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    if (!c.ms.out.converged || !(c.ms.out.rss > 0.0) || isinf(c.ms.out.rss) || isinf(ldv) || ldv != ldv) return inf;
+    double lda = 0.0;
+    for (int j = 0; j < PT; j++) lda += own_log(c.ms.L[tri(j, j)]);
+    return 2.0 * ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
+}
+
+// Nelder–Mead in three dimensions; same comparisons in the same order as the oracle's slope_nm.
+template <int PT>
+static __device__ __noinline__ double slope_nm(LmmCtx<PT>& c, SlopeData<PT>& d, double* x, double step, int max_eval) {
+    double sx[4][3], sf[4];
+    for (int i = 0; i < 4; i++) {
+        for (int j = 0; j < 3; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
+        sf[i] = slope_dev<PT>(c, d, sx[i]);
+    }
+    for (;;) {
+        int lo = 0, hi = 0, nh;
+        for (int i = 1; i < 4; i++) {
+            if (sf[i] < sf[lo]) lo = i;
+            if (sf[i] > sf[hi] || !(sf[i] == sf[i])) hi = i;
+        }
+        nh = lo;
+        for (int i = 0; i < 4; i++)
+            if (i != hi && (sf[i] > sf[nh])) nh = i;
+        double size = 0.0;
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 3; j++) {
+                const double dd = fabs(sx[i][j] - sx[lo][j]);
+                if (dd > size) size = dd;
+            }
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval) {
+            for (int j = 0; j < 3; j++) x[j] = sx[lo][j];
+            return sf[lo];
+        }
+        double cen[3], xr[3], xe[3], xc[3];
+        for (int j = 0; j < 3; j++) {
+            double sum = 0.0;
+            for (int i = 0; i < 4; i++)
+                if (i != hi) sum += sx[i][j];
+            cen[j] = sum / 3.0;
+            xr[j] = cen[j] + (cen[j] - sx[hi][j]);
+        }
+        const double fr = slope_dev<PT>(c, d, xr);
+        if (fr < sf[lo]) {
+            for (int j = 0; j < 3; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
+            const double fe = slope_dev<PT>(c, d, xe);
+            if (fe < fr) {
+                for (int j = 0; j < 3; j++) sx[hi][j] = xe[j];
+                sf[hi] = fe;
+            } else {
+                for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+                sf[hi] = fr;
+            }
+        } else if (fr < sf[nh]) {
+            for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+            sf[hi] = fr;
+        } else {
+            const bool outside = fr < sf[hi];
+            for (int j = 0; j < 3; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
+            const double fc = slope_dev<PT>(c, d, xc);
+            if (fc < (outside ? fr : sf[hi])) {
+                for (int j = 0; j < 3; j++) sx[hi][j] = xc[j];
+                sf[hi] = fc;
+            } else {
+                for (int i = 0; i < 4; i++) {
+                    if (i == lo) continue;
+                    for (int j = 0; j < 3; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
+                    sf[i] = slope_dev<PT>(c, d, sx[i]);
+                }
+            }
+        }
+    }
+}
+
+template <int PT>
+static __device__ __noinline__ void lmm_slope_fit(LmmCtx<PT>& c, SlopeData<PT>& d, int& converged, int& boundary, double* theta) {
+    double x[3] = {1.0, 0.0, 1.0};
+    d.n_eval = 0;
+    slope_nm<PT>(c, d, x, 0.5, MCP_SLOPE_NM_MAXEVAL / 2);
+    double f = slope_nm<PT>(c, d, x, 0.05, MCP_SLOPE_NM_MAXEVAL);  // restart from the best vertex
+    x[0] = x[0] > 0.0 ? x[0] : 0.0;
+    x[2] = x[2] > 0.0 ? x[2] : 0.0;
+    f = slope_dev<PT>(c, d, x);  // leaves A, L, beta, sigma² at theta-hat
+    converged = !(isinf(f) || f != f) && d.n_eval < MCP_SLOPE_NM_MAXEVAL;
+    boundary = 0;
+    if (x[0] < 1e-6 || x[2] < 1e-6) boundary = 1;  // a variance component pinned at 0 (singular fit)
+    if (x[0] > MCP_SLOPE_THETA_MAX || fabs(x[1]) > MCP_SLOPE_THETA_MAX || x[2] > MCP_SLOPE_THETA_MAX) {
+        boundary = 2;
+        converged = 0;
+    }
+    for (int j = 0; j < 3; j++) theta[j] = x[j];
 }
 
 // Joint Wald chi-square of the testable targets: beta_T' [Cov_TT]^-1 beta_T, Cov = sigma² A^-1.
@@ -356,9 +505,11 @@ template <int PT>
 struct LmmLayout {
     static constexpr int NACC = PT * (PT + 1) / 2;
     static constexpr int E = NACC + PT + 1;
-    static __host__ __device__ size_t csum_doubles(int nc_cap) { return (size_t)nc_cap * (PT + 1); }
-    static __host__ __device__ size_t per_study_doubles(int nc_cap, int n_ss) {
-        return csum_doubles(nc_cap) * (size_t)(1 + n_ss) + (size_t)n_ss * E;
+    // per cluster: the sums of [x | y] and — with a random slope — behind them the sums of x_s · [x | y]
+    static __host__ __device__ size_t cluster_doubles(int n_slopes) { return (size_t)(PT + 1) * (size_t)(1 + n_slopes); }
+    static __host__ __device__ size_t csum_doubles(int nc_cap, int n_slopes = 0) { return (size_t)nc_cap * cluster_doubles(n_slopes); }
+    static __host__ __device__ size_t per_study_doubles(int nc_cap, int n_ss, int n_slopes = 0) {
+        return csum_doubles(nc_cap, n_slopes) * (size_t)(1 + n_ss) + (size_t)n_ss * E;
     }
 };
 
@@ -379,11 +530,11 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
     const int max_n = pl.max_n;
     const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
     const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
+    const int ns = pl.n_slopes, CD = (int)LY::cluster_doubles(ns);  // doubles per cluster: [x | y] sums (+ the x_s-weighted ones)
     double* const csum = scratch + sim;
-    double* const snap = csum + LY::csum_doubles(nc_cap) * stride;
-    double* const stat = snap + LY::csum_doubles(nc_cap) * (size_t)pl.n_ss * stride;
-    for (int k = 0; k < nc_cap; k++)
-        for (int j = 0; j <= PT; j++) csum[(size_t)(k * (PT + 1) + j) * stride] = 0.0;
+    double* const snap = csum + LY::csum_doubles(nc_cap, ns) * stride;
+    double* const stat = snap + LY::csum_doubles(nc_cap, ns) * (size_t)pl.n_ss * stride;
+    for (int e = 0; e < nc_cap * CD; e++) csum[(size_t)e * stride] = 0.0;
 
     double acc[NACC], xty[PT];
 #pragma unroll
@@ -419,10 +570,20 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
             yty = fma(yd, yd, yty);
             {  // cluster sums (plain adds in row order, like the host-side restatement)
                 const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
-                double* base = csum + (size_t)kc * (PT + 1) * stride;
+                double* base = csum + (size_t)kc * CD * stride;
 #pragma unroll
                 for (int j = 0; j < PT; j++) base[(size_t)j * stride] += xr[j];
                 base[(size_t)PT * stride] += yd;
+                if (ns > 0) {  // random slope: sums of x_s · [x | y], one fma per term in row order (the oracle's chains)
+                    double* b2 = base + (size_t)(PT + 1) * stride;
+                    double xs = 0.0;
+#pragma unroll
+                    for (int j = 0; j < PT; j++)
+                        if (j == pl.slope_col) xs = xr[j];
+#pragma unroll
+                    for (int j = 0; j < PT; j++) b2[(size_t)j * stride] = fma(xs, xr[j], b2[(size_t)j * stride]);
+                    b2[(size_t)PT * stride] = fma(xs, yd, b2[(size_t)PT * stride]);
+                }
             }
             if ((uint32_t)(row + 1) == n_next) {
                 double* const so = stat + (size_t)g * LY::E * stride;
@@ -432,8 +593,8 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
                 for (int i = 0; i < PT; i++) so[(size_t)(NACC + i) * stride] = xty[i];
                 so[(size_t)(NACC + PT) * stride] = yty;
                 const int n_clusters = pl.sizing_fixed_size ? (row + 1 + cs - 1) / cs : cs;
-                double* const sn = snap + (size_t)g * LY::csum_doubles(nc_cap) * stride;
-                for (int e = 0; e < n_clusters * (PT + 1); e++) sn[(size_t)e * stride] = csum[(size_t)e * stride];
+                double* const sn = snap + (size_t)g * LY::csum_doubles(nc_cap, ns) * stride;
+                for (int e = 0; e < n_clusters * CD; e++) sn[(size_t)e * stride] = csum[(size_t)e * stride];
                 g++;
                 n_next = g < pl.n_ss ? pl.ss[g] : 0xffffffffu;
             }
@@ -472,10 +633,20 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
         }
         yty = fma(yd, yd, yty);
         const int kc = pl.sizing_fixed_size ? row / cs : row % cs;
-        double* base = csum + (size_t)kc * (PT + 1);
+        double* base = csum + (size_t)kc * (PT + 1) * (1 + pl.n_slopes);
 #pragma unroll
         for (int j = 0; j < PT; j++) base[j] += xr[j];
         base[PT] += yd;
+        if (pl.n_slopes > 0) {
+            double* b2 = base + (PT + 1);
+            double xs = 0.0;
+#pragma unroll
+            for (int j = 0; j < PT; j++)
+                if (j == pl.slope_col) xs = xr[j];
+#pragma unroll
+            for (int j = 0; j < PT; j++) b2[j] = fma(xs, xr[j], b2[j]);
+            b2[PT] = fma(xs, yd, b2[PT]);
+        }
     }
     LmmCtx<PT> c;
     c.p = PT;
@@ -487,8 +658,14 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     for (int i = 0; i < PT; i++) c.xty[i] = xty[i];
     const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
     int conv = 0, bnd = 0;
-    double theta = 0.0;
-    lmm_fit<PT>(c, csum, 1, n, n_clusters, nullptr, conv, bnd, &theta);
+    double theta = 0.0, th3[3] = {0.0, 0.0, 0.0};
+    if (pl.n_slopes > 0) {
+        SlopeData<PT> sd{csum, 1, n, n_clusters, pl.slope_col, 0};
+        lmm_slope_fit<PT>(c, sd, conv, bnd, th3);
+        theta = th3[0];
+    } else {
+        lmm_fit<PT>(c, csum, 1, n, n_clusters, nullptr, conv, bnd, &theta);
+    }
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (int t = 0; t < PT; t++) {
         out[t] = c.ms.beta[t];
@@ -502,6 +679,9 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     out[3 * PT + 4] = theta * theta * c.ms.out.sigma_sq;
     out[3 * PT + 5] = nan;
     out[3 * PT + 6] = nan;
+    // random slope: variance of the slope effect sigma² (l10² + l11²) and corr(intercept, slope) = l10 / sqrt(l10² + l11²)
+    out[3 * PT + 7] = pl.n_slopes > 0 ? c.ms.out.sigma_sq * (th3[1] * th3[1] + th3[2] * th3[2]) : nan;
+    out[3 * PT + 8] = pl.n_slopes > 0 ? th3[1] / sqrt(th3[1] * th3[1] + th3[2] * th3[2]) : nan;
 }
 
 // Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): profiled REML by Brent over the cluster
@@ -527,8 +707,9 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
         const int max_n = pl.max_n;
         const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
         const int nc_cap = pl.sizing_fixed_size ? (max_n + cs - 1) / cs : cs;
-        const double* const snap = scratch + sim + LY::csum_doubles(nc_cap) * stride + (size_t)g * LY::csum_doubles(nc_cap) * stride;
-        const double* const st = scratch + sim + LY::csum_doubles(nc_cap) * (size_t)(1 + pl.n_ss) * stride + (size_t)g * LY::E * stride;
+        const int ns = pl.n_slopes;
+        const double* const snap = scratch + sim + LY::csum_doubles(nc_cap, ns) * stride + (size_t)g * LY::csum_doubles(nc_cap, ns) * stride;
+        const double* const st = scratch + sim + LY::csum_doubles(nc_cap, ns) * (size_t)(1 + pl.n_ss) * stride + (size_t)g * LY::E * stride;
         const int n = (int)pl.ss[g];
         uint8_t excl[MCP_MAX_FACTORS];
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
@@ -560,7 +741,13 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
             for (int rj = 0; rj <= ri; rj++) c.xtx[tri(ri, rj)] = st[(size_t)tri(vr.kept[ri], vr.kept[rj]) * stride];
         }
         int conv = 0, bnd = 0;
-        lmm_fit<PT>(c, snap, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd);
+        if (ns > 0 && !reduced) {  // random intercept + slope: 3-parameter REML (the reduced fit strips the slope, batch.rs:1357-1375)
+            SlopeData<PT> sd{snap, stride, n, n_clusters, pl.slope_col, 0};
+            double theta[3];
+            lmm_slope_fit<PT>(c, sd, conv, bnd, theta);
+        } else {
+            lmm_fit<PT>(c, snap, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd, nullptr, (int)LY::cluster_doubles(ns));
+        }
         double all_t[MCP_MAX_T];
         int cols[MCP_MAX_T];
         int k_red = 0;

@@ -118,6 +118,10 @@ struct DevicePlan {
     int32_t has_lme, re_dist;          // scenario.lme (spec.rs:175): random-effect distribution (a McpRes code), ...
     double re_df, icc_noise_sd;        // ... its df, and the sd of the per-study jitter added to tau² (data_gen.rs:1065-1075)
     int32_t re_words;                  // sequential-stream words one random-effect draw consumes (draw_residual, data_gen.rs:1289-1320)
+    // ---- one random slope on the primary grouping (cluster.slopes[0], cluster_slope_design_cols[0]; data_gen.rs:163-213, 836-842)
+    int32_t n_slopes;                  // 0 or 1
+    int32_t slope_col;                 // design column the slope effect multiplies
+    double slope_variance, slope_corr; // tau1², corr(intercept, slope): D = diag(tau) R diag(tau)
     // ---- cluster-level predictors (spec.between_var_indices, data_gen.rs:605-640)
     int32_t n_between;                 // 0 unless the spec has a cluster
     int8_t between_cols[MCP_MAX_P];    // design columns (>= 1) broadcast from the cluster's representative row

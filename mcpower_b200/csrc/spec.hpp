@@ -57,7 +57,9 @@ struct Spec {
     std::vector<double> upload_normal, upload_data;
     int un_rows = 0, un_cols = 0, ud_rows = 0, ud_cols = 0;
     std::vector<int> frame_map;  // bootstrap_frame_map, −1 = None; empty = not bootstrap
-    bool has_slopes_or_groupings = false;
+    bool has_slopes_or_groupings = false;  // what the CUDA path does not run: > 1 slope, slope-slope correlations, extra groupings
+    int n_slopes = 0, slope_col = -1;      // one random slope on the primary grouping
+    double slope_variance = 0.0, slope_corr = 0.0;
     std::vector<int> between_cols;  // between_var_indices (spec.rs:279): design columns broadcast within a cluster
     // cluster
     bool has_cluster = false;
@@ -229,7 +231,13 @@ inline Spec parse_spec(const char* json, size_t len) {
     if (auto* p = root.get("report_overall")) s.report_overall = !p->is_null() && to_bool(*p, "report_overall");
     if (auto* p = root.get("factor_min_level_count"))
         if (!p->is_null()) s.min_level_count = to_int(*p, "factor_min_level_count");
-    if (auto* p = root.get("cluster_slope_design_cols")) s.has_slopes_or_groupings |= p->kind == JsonValue::Array && !p->arr.empty();
+    std::vector<int> slope_cols;
+    if (auto* p = root.get("cluster_slope_design_cols"))
+        if (p->kind == JsonValue::Array)
+            for (auto& v : p->arr) slope_cols.push_back(to_int(v, "cluster_slope_design_cols"));
+    if (auto* p = root.get("extra_slope_cols"))
+        if (p->kind == JsonValue::Array)
+            for (auto& v : p->arr) s.has_slopes_or_groupings |= v.kind == JsonValue::Array && !v.arr.empty();
     if (auto* p = root.get("cluster")) {
         if (!p->is_null()) {
             s.has_cluster = true;
@@ -244,8 +252,17 @@ inline Spec parse_spec(const char* json, size_t len) {
                 invalid("cluster.sizing must be FixedClusters or FixedSize");
             }
             s.tau_squared = num(req(*p, "tau_squared"), "tau_squared");
-            for (const char* key : {"slopes", "extra_groupings"})
-                if (auto* q = p->get(key)) s.has_slopes_or_groupings |= q->kind == JsonValue::Array && !q->arr.empty();
+            if (auto* q = p->get("extra_groupings")) s.has_slopes_or_groupings |= q->kind == JsonValue::Array && !q->arr.empty();
+            if (auto* q = p->get("slopes"))
+                if (q->kind == JsonValue::Array && !q->arr.empty()) {
+                    if (q->arr.size() > 1) s.has_slopes_or_groupings = true;
+                    const JsonValue& sl = q->arr[0];
+                    s.n_slopes = 1;
+                    s.slope_variance = num(req(sl, "variance"), "slopes.variance");
+                    s.slope_corr = num(req(sl, "corr_with_intercept"), "slopes.corr_with_intercept");
+                    if (slope_cols.size() != q->arr.size()) invalid("cluster_slope_design_cols must name one design column per random slope");
+                    s.slope_col = slope_cols[0];
+                }
         }
     }
     {
@@ -333,6 +350,11 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
     for (auto& dummies : s.posthoc_blocks)
         for (int ti : dummies)
             if (ti < 0 || ti >= P) invalid("posthoc target index " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
+    if (s.n_slopes > 0) {
+        if (s.slope_col < 1 || s.slope_col >= P) invalid("cluster_slope_design_cols entry " + std::to_string(s.slope_col) + " out of range");
+        if (!(s.tau_squared > 0.0)) invalid("random slopes need tau_squared > 0");  // engine-contract validate(): z0 = u0 / tau0
+        if (!(s.slope_variance >= 0.0) || !(std::fabs(s.slope_corr) <= 1.0)) invalid("random slope variance / correlation out of range");
+    }
     for (int c : s.between_cols)  // the reference indexes x_full unchecked (data_gen.rs:631-633); reject instead
         if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("between_var_indices entry " + std::to_string(c) + " out of range");
     // uploaded-data tables: the reference indexes them unchecked (a malformed spec panics → RuntimeError); reject instead

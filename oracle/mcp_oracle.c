@@ -1076,6 +1076,7 @@ typedef struct {
     double residual_df_design;
     double tau_squared_design;
     float* cluster_u;
+    float* cluster_u1; /* random-slope effects */
     int32_t* cluster_ids;
     int n_cluster_cap;
     uint32_t* alloc_counts;
@@ -1117,6 +1118,7 @@ static Ws* ws_new(const OrcSpec* s, int max_n) {
                                       : (s->sizing_value > 0 ? s->sizing_value : 1);
         w->n_cluster_cap = nc;
         w->cluster_u = (float*)calloc((size_t)nc, sizeof(float));
+        w->cluster_u1 = (float*)calloc((size_t)nc, sizeof(float));
         w->cluster_ids = (int32_t*)calloc((size_t)max_n, sizeof(int32_t));
         for (int i = 0; i < max_n; i++) /* generation.rs cluster_of_row */
             w->cluster_ids[i] = s->sizing_fixed_size ? i / (s->sizing_value > 0 ? s->sizing_value : 1)
@@ -1129,7 +1131,7 @@ static void ws_free(Ws* w) {
     free(w->x); free(w->y); free(w->z_planar); free(w->residuals); free(w->resid_g); free(w->words);
     free(w->mix_acc); free(w->eta_acc); free(w->l_design); free(w->var_types_design); free(w->alloc_counts);
     free(w->prefix_counts); free(w->excl_flags); free(w->beta_eff); free(w->xtx); free(w->xty);
-    free(w->cluster_u); free(w->cluster_ids); free(w->red_memo);
+    free(w->cluster_u); free(w->cluster_u1); free(w->cluster_ids); free(w->red_memo);
     free(w);
 }
 
@@ -1270,6 +1272,24 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
         int nc = s->sizing_fixed_size ? max_n / (s->sizing_value > 0 ? s->sizing_value : 1)
                                       : (s->sizing_value > 0 ? s->sizing_value : 1);
         for (int c = 0; c < nc; c++) w->cluster_u[c] = (float)(draw_residual(&rng, re_dist, re_df) * tau);
+        /* 2a'. primary random slope (data_gen.rs:163-213): per cluster z_1 ~ draw_residual AFTER all the intercept draws; z_0 is
+         * recovered from the f32 intercept effect; (u_0, u_1) = chol(D) z with D = diag(tau) R diag(tau) */
+        if (s->n_slopes > 0) {
+            double tau1 = sqrt(s->slope_variance > 0.0 ? s->slope_variance : 0.0);
+            double d00 = tau * 1.0 * tau, d10 = tau1 * s->slope_corr * tau, d11 = tau1 * 1.0 * tau1;
+            double l00 = sqrt(d00 > 0.0 ? d00 : 0.0);
+            double l10 = l00 > 0.0 ? d10 / l00 : 0.0;
+            double r11 = d11 - l10 * l10;
+            double l11 = sqrt(r11 > 0.0 ? r11 : 0.0);
+            for (int c = 0; c < nc; c++) {
+                double z0 = tau > 0.0 ? (double)w->cluster_u[c] / tau : 0.0;
+                double z1 = draw_residual(&rng, re_dist, re_df);
+                double uk = 0.0;
+                uk += l10 * z0;
+                uk += l11 * z1;
+                w->cluster_u1[c] = (float)uk;
+            }
+        }
     }
     for (int i = 0; i < max_n; i++) w->x[i] = 1.0f;
 
@@ -1461,6 +1481,8 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
             w->mix_acc[i] = gamma * z;
         }
         double u_re = s->has_cluster ? (double)w->cluster_u[w->cluster_ids[i]] : 0.0;
+        if (s->has_cluster && s->n_slopes > 0) /* data_gen.rs:836-842 */
+            u_re += (double)w->cluster_u1[w->cluster_ids[i]] * (double)w->x[(size_t)s->slope_col * max_n + i];
         if (s->outcome_kind == ORC_OUT_CONTINUOUS && !apply_hsk) w->y[i] = (float)(lp + (double)w->residuals[i] + u_re);
         else w->eta_acc[i] = lp + u_re;
     }
@@ -1517,6 +1539,12 @@ static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* ba
     for (int c = 0; c < 2 * s->n_contrasts; c++)
         if (s->contrast_pairs[c] < 0 || s->contrast_pairs[c] >= P) return fail(ORC_ERR_INVALID_SPEC, "contrast_pairs entry out of range");
     int k = s->n_non_factor;
+    if (s->n_slopes > 0) {
+        if (!s->has_cluster || s->n_slopes > 1) return fail(ORC_ERR_INVALID_SPEC, "random slopes need a cluster (one slope at most)");
+        if (s->slope_col < 1 || s->slope_col >= 1 + s->n_non_factor + s->n_factor_dummies + s->n_interactions)
+            return fail(ORC_ERR_INVALID_SPEC, "cluster_slope_design_cols entry out of range");
+        if (!(s->tau_squared > 0.0)) return fail(ORC_ERR_INVALID_SPEC, "random slopes need tau_squared > 0"); /* validate.rs invariant */
+    }
     for (int b = 0; b < s->n_between; b++) /* the reference indexes x_full unchecked (a malformed spec panics); the backends reject it */
         if (s->between_cols[b] < 1 || s->between_cols[b] >= 1 + s->n_non_factor + s->n_factor_dummies)
             return fail(ORC_ERR_INVALID_SPEC, "between_var_indices entry out of range");
@@ -1959,6 +1987,154 @@ static void lmm_fit(LmmCtx* c, const double* csum, const uint32_t* cn, int n_clu
     out->tau_sq = th * th * c->fit.sigma_sq;
 }
 
+/* ---- random intercept + ONE random slope (q = 2): profiled REML over theta = (l00, l10, l11), Lambda = [[l00, 0], [l10, l11]] ----
+ * The reference fits these through glmm::fit_on + BOBYQA (batch.rs:1214-1561, mixed_workspace.rs:203-272; crates not in the
+ * tree).  Restated in the lme4 form over per-cluster sufficient statistics: with Z_c = [1, x_s],
+ *   M_c = Lambda' Z_c'Z_c Lambda + I,  L_c = chol(M_c),  R_c = L_c^-1 Lambda' Z_c'[X | y]  (2 x (p + 1)),
+ *   A = X'X - sum_c R_c[:, :p]' R_c[:, :p],  b = X'y - sum_c R_c[:, :p]' R_c[:, p],  c = y'y - sum_c |R_c[:, p]|^2,
+ *   dev(theta) = sum_c log det M_c + log det A + (n - p) log(rss / (n - p)).
+ * Per cluster the statistics are the sums of [x | y] (cs1) and of x_s * [x | y] (cs2): Z'Z = [[n_c, cs1[s]], [cs1[s], cs2[s]]].
+ * Minimised by a deterministic Nelder-Mead (one restart) with the diagonal of Lambda clamped at 0; restated op for op in the
+ * CUDA kernel.  Pinned to lme4's REML fits of the reference's lmm_slope datasets (tolerances.R:29-31, 38-49). */
+#define SLOPE_NM_MAXEVAL 900
+#define SLOPE_THETA_MAX 30.0
+typedef struct {
+    const double *cs1, *cs2; /* [n_clusters][p + 1] */
+    const uint32_t* cn;
+    int n_clusters, slope_col;
+    int n_eval;
+} SlopeData;
+
+static double slope_dev(LmmCtx* c, const SlopeData* d, const double th[3]) {
+    const int p = c->p;
+    const size_t nt = (size_t)p * (p + 1) / 2;
+    const double l00 = th[0] > 0.0 ? th[0] : 0.0, l10 = th[1], l11 = th[2] > 0.0 ? th[2] : 0.0;
+    for (size_t e = 0; e < nt; e++) c->A[e] = c->xtx[e];
+    for (int j = 0; j < p; j++) c->b[j] = c->xty[j];
+    double cc = c->yty, ldv = 0.0;
+    double r0[65], r1[65];
+    for (int k = 0; k < d->n_clusters; k++) {
+        if (d->cn[k] == 0) continue;
+        const double* s1 = d->cs1 + (size_t)k * (p + 1);
+        const double* s2 = d->cs2 + (size_t)k * (p + 1);
+        const double S00 = (double)d->cn[k], S01 = s1[d->slope_col], S11 = s2[d->slope_col];
+        const double a0 = l00 * S00 + l10 * S01, a1 = l00 * S01 + l10 * S11, b1 = l11 * S11, b0 = l11 * S01;
+        const double m00 = (a0 * l00 + a1 * l10) + 1.0, m10 = b0 * l00 + b1 * l10, m11 = b1 * l11 + 1.0;
+        const double c00 = sqrt(m00), c10 = m10 / c00, c11 = sqrt(m11 - c10 * c10);
+        ldv += orc_log(c00) + orc_log(c11);
+        for (int j = 0; j <= p; j++) {
+            const double t0 = l00 * s1[j] + l10 * s2[j], t1 = l11 * s2[j];
+            r0[j] = t0 / c00;
+            r1[j] = (t1 - c10 * r0[j]) / c11;
+        }
+        size_t t = 0;
+        for (int a = 0; a < p; a++) {
+            for (int bb = 0; bb <= a; bb++) {
+                c->A[t] = fma(-r0[a], r0[bb], c->A[t]);
+                c->A[t] = fma(-r1[a], r1[bb], c->A[t]);
+                t++;
+            }
+            c->b[a] = fma(-r0[a], r0[p], c->b[a]);
+            c->b[a] = fma(-r1[a], r1[p], c->b[a]);
+        }
+        cc = fma(-r0[p], r0[p], cc);
+        cc = fma(-r1[p], r1[p], cc);
+    }
+    ((SlopeData*)d)->n_eval++;
+    ols_solve(c->A, c->b, cc, 0.0, c->n_rows, p, c->L, c->inv_d, c->wv, c->beta, &c->fit);
+    if (!c->fit.converged || !(c->fit.rss > 0.0) || !isfinite(c->fit.rss) || !isfinite(ldv)) return INFINITY;
+    double lda = 0.0;
+    for (int j = 0; j < p; j++) lda += orc_log(c->L[TRI(j, j)]);
+    return 2.0 * ldv + 2.0 * lda + c->fit.df_resid * orc_log(c->fit.sigma_sq);
+}
+
+/* Nelder-Mead in 3 dimensions (reflection 1, expansion 2, contraction 1/2, shrink 1/2); x0 +- step initial simplex; stops when
+ * the simplex is flat (1e-11 relative in f) and small (1e-7 in every coordinate) or after max_eval evaluations.  Ties and
+ * orderings are resolved by strict comparisons in a fixed order, so the CUDA twin takes the same path. */
+static double slope_nm(LmmCtx* c, SlopeData* d, double x[3], const double step[3], int max_eval) {
+    double sx[4][3], sf[4];
+    for (int i = 0; i < 4; i++) {
+        for (int j = 0; j < 3; j++) sx[i][j] = x[j] + (i == j + 1 ? step[j] : 0.0);
+        sf[i] = slope_dev(c, d, sx[i]);
+    }
+    for (;;) {
+        /* order: best (lo), worst (hi), second worst (nh) */
+        int lo = 0, hi = 0, nh;
+        for (int i = 1; i < 4; i++) {
+            if (sf[i] < sf[lo]) lo = i;
+            if (sf[i] > sf[hi] || !(sf[i] == sf[i])) hi = i;
+        }
+        nh = lo;
+        for (int i = 0; i < 4; i++)
+            if (i != hi && (sf[i] > sf[nh])) nh = i;
+        double size = 0.0;
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 3; j++) {
+                double dd = fabs(sx[i][j] - sx[lo][j]);
+                if (dd > size) size = dd;
+            }
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d->n_eval >= max_eval) {
+            for (int j = 0; j < 3; j++) x[j] = sx[lo][j];
+            return sf[lo];
+        }
+        double cen[3], xr[3], xe[3], xc[3];
+        for (int j = 0; j < 3; j++) {
+            double sum = 0.0;
+            for (int i = 0; i < 4; i++)
+                if (i != hi) sum += sx[i][j];
+            cen[j] = sum / 3.0;
+            xr[j] = cen[j] + (cen[j] - sx[hi][j]);
+        }
+        double fr = slope_dev(c, d, xr);
+        if (fr < sf[lo]) {
+            for (int j = 0; j < 3; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
+            double fe = slope_dev(c, d, xe);
+            if (fe < fr) { for (int j = 0; j < 3; j++) sx[hi][j] = xe[j]; sf[hi] = fe; }
+            else { for (int j = 0; j < 3; j++) sx[hi][j] = xr[j]; sf[hi] = fr; }
+        } else if (fr < sf[nh]) {
+            for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+            sf[hi] = fr;
+        } else {
+            const int outside = fr < sf[hi];
+            for (int j = 0; j < 3; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
+            double fc = slope_dev(c, d, xc);
+            if (fc < (outside ? fr : sf[hi])) {
+                for (int j = 0; j < 3; j++) sx[hi][j] = xc[j];
+                sf[hi] = fc;
+            } else {
+                for (int i = 0; i < 4; i++) {
+                    if (i == lo) continue;
+                    for (int j = 0; j < 3; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
+                    sf[i] = slope_dev(c, d, sx[i]);
+                }
+            }
+        }
+    }
+}
+
+typedef struct {
+    int converged, boundary_hit, n_eval;
+    double theta[3], sigma_sq;
+} SlopeOut;
+
+static void lmm_slope_fit(LmmCtx* c, SlopeData* d, SlopeOut* out) {
+    double x[3] = {1.0, 0.0, 1.0};
+    const double step0[3] = {0.5, 0.5, 0.5}, step1[3] = {0.05, 0.05, 0.05};
+    d->n_eval = 0;
+    slope_nm(c, d, x, step0, SLOPE_NM_MAXEVAL / 2);
+    double f = slope_nm(c, d, x, step1, SLOPE_NM_MAXEVAL); /* restart from the best vertex: guards against a collapsed simplex */
+    x[0] = x[0] > 0.0 ? x[0] : 0.0;
+    x[2] = x[2] > 0.0 ? x[2] : 0.0;
+    f = slope_dev(c, d, x); /* leaves A, L, beta, sigma at theta-hat */
+    out->converged = isfinite(f) && d->n_eval < SLOPE_NM_MAXEVAL;
+    out->boundary_hit = 0;
+    if (x[0] < 1e-6 || x[2] < 1e-6) out->boundary_hit = 1; /* a variance component pinned at 0 (singular fit) */
+    if (x[0] > SLOPE_THETA_MAX || fabs(x[1]) > SLOPE_THETA_MAX || x[2] > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+    out->n_eval = d->n_eval;
+    for (int j = 0; j < 3; j++) out->theta[j] = x[j];
+    out->sigma_sq = c->fit.sigma_sq;
+}
+
 /* Joint Wald chi-square of the targets: beta_T' [Cov_TT]^-1 beta_T with Cov = sigma^2 A^-1. */
 static double lmm_joint_wald(const LmmCtx* c, const int* cols, int k) {
     if (k <= 0 || k > 32) return NAN;
@@ -2024,6 +2200,54 @@ int orc_fit_lmm(const double* xc, const double* yv, const int32_t* ids, int n, i
 /* ======================================================================= */
 
 /* batch.rs:2451-2496 */
+int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, int n, int p, int slope_col, double* betas,
+                      double* se, double* vc, int* converged, int* boundary, int* n_eval) {
+    if (p > 64 || slope_col < 0 || slope_col >= p) return fail(ORC_ERR_INVALID_SPEC, "bad p / slope column");
+    float* x = (float*)malloc(sizeof(float) * (size_t)n * p);
+    float* y = (float*)malloc(sizeof(float) * (size_t)n);
+    for (size_t i = 0; i < (size_t)n * p; i++) x[i] = (float)xc[i];
+    for (int i = 0; i < n; i++) y[i] = (float)yv[i];
+    int nc = 0;
+    for (int i = 0; i < n; i++) if (ids[i] + 1 > nc) nc = ids[i] + 1;
+    size_t nt = (size_t)p * (p + 1) / 2;
+    double* xtx = (double*)calloc(nt + (size_t)p + (size_t)nc * (p + 1) * 2, sizeof(double));
+    double *xty = xtx + nt, *cs1 = xty + p, *cs2 = cs1 + (size_t)nc * (p + 1);
+    uint32_t* cn = (uint32_t*)calloc((size_t)nc, sizeof(uint32_t));
+    SuffScalars sc = {0.0, 0.0, 0};
+    suff_add_rows(x, y, n, p, 0, n, xtx, xty, &sc);
+    for (int i = 0; i < n; i++) {
+        double* s1 = cs1 + (size_t)ids[i] * (p + 1);
+        double* s2 = cs2 + (size_t)ids[i] * (p + 1);
+        const double xs = (double)x[(size_t)slope_col * n + i];
+        for (int j = 0; j < p; j++) {
+            const double xv = (double)x[(size_t)j * n + i];
+            s1[j] += xv;
+            s2[j] = fma(xs, xv, s2[j]);
+        }
+        s1[p] += (double)y[i];
+        s2[p] = fma(xs, (double)y[i], s2[p]);
+        cn[ids[i]]++;
+    }
+    LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
+    c->p = p; c->n_rows = (uint32_t)n; c->xtx = xtx; c->xty = xty; c->yty = sc.yty;
+    SlopeData d = {cs1, cs2, cn, nc, slope_col, 0};
+    SlopeOut o;
+    lmm_slope_fit(c, &d, &o);
+    double u[64];
+    for (int t = 0; t < p; t++) {
+        betas[t] = c->beta[t];
+        se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
+    }
+    const double l00 = o.theta[0], l10 = o.theta[1], l11 = o.theta[2];
+    vc[0] = o.sigma_sq * l00 * l00;
+    vc[1] = o.sigma_sq * (l10 * l10 + l11 * l11);
+    vc[2] = l10 / sqrt(l10 * l10 + l11 * l11);
+    vc[3] = o.sigma_sq;
+    *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
+    free(c); free(cn); free(xtx); free(x); free(y);
+    return ORC_OK;
+}
+
 static void update_factor_exclusions(const OrcSpec* s, const float* x, int ld, int from, int to, uint32_t* counts, uint8_t* flags) {
     int off = 0, col = 1 + s->n_non_factor;
     for (int f = 0; f < s->n_factors; f++) {
@@ -2308,8 +2532,9 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
     int nprops = 0;
     for (int f = 0; f < s->n_factors; f++) nprops += s->factor_n_levels[f];
     int test_reduces = s->n_fit_columns > 0 && s->n_fit_columns < P;
-    double* csum = (double*)calloc((size_t)nc_cap * (P + 1) * 2, sizeof(double));
+    double* csum = (double*)calloc((size_t)nc_cap * (P + 1) * 3, sizeof(double));
     double* csum_red = csum + (size_t)nc_cap * (P + 1);
+    double* csum2 = csum_red + (size_t)nc_cap * (P + 1); /* random slope: per-cluster sums of x_s * [x | y] */
     uint32_t* cn = (uint32_t*)calloc((size_t)nc_cap, sizeof(uint32_t));
     LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
     memset(w->xtx, 0, sizeof(double) * nt);
@@ -2327,6 +2552,12 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
                 double* sx = csum + (size_t)k * (P + 1);
                 for (int j = 0; j < P; j++) sx[j] += (double)w->x[(size_t)j * ld + i];
                 sx[P] += (double)w->y[i];
+                if (s->n_slopes > 0) {
+                    double* s2 = csum2 + (size_t)k * (P + 1);
+                    const double xs = (double)w->x[(size_t)s->slope_col * ld + i];
+                    for (int j = 0; j < P; j++) s2[j] = fma(xs, (double)w->x[(size_t)j * ld + i], s2[j]);
+                    s2[P] = fma(xs, (double)w->y[i], s2[P]);
+                }
                 cn[k]++;
             }
             last = n;
@@ -2341,7 +2572,16 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
         int n_clusters = s->sizing_fixed_size ? (n + csz - 1) / csz : csz;
         LmmOut lo;
         c->n_rows = sc.n_rows; c->yty = sc.yty;
-        if (!reduced) {
+        if (!reduced && s->n_slopes > 0) {
+            /* full model with the random slope: 3-parameter REML; the reduced fit below strips the slope like the reference
+             * (batch.rs:1357-1375) */
+            c->p = P; c->xtx = w->xtx; c->xty = w->xty;
+            SlopeData sd = {csum, csum2, cn, n_clusters, s->slope_col, 0};
+            SlopeOut so;
+            lmm_slope_fit(c, &sd, &so);
+            lo.converged = so.converged; lo.boundary_hit = so.boundary_hit; lo.theta = so.theta[0]; lo.sigma_sq = so.sigma_sq;
+            lo.tau_sq = so.theta[0] * so.theta[0] * so.sigma_sq;
+        } else if (!reduced) {
             c->p = P; c->xtx = w->xtx; c->xty = w->xty;
             lmm_fit(c, csum, cn, n_clusters, P, &lo);
         } else {

@@ -93,6 +93,11 @@ typedef struct {
      * cluster is the value on the cluster's representative (first) row */
     int32_t n_between;
     const int32_t* between_cols;
+    /* one random slope on the primary grouping (cluster.slopes[0] + cluster_slope_design_cols[0]; data_gen.rs:163-213,
+     * 836-842): RE covariance D = [[tau0², rho tau0 tau1], [., tau1²]] */
+    int32_t n_slopes;               /* 0 or 1 */
+    int32_t slope_col;              /* design column the slope multiplies */
+    double slope_variance, slope_corr;
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
@@ -109,6 +114,10 @@ void orc_sample_t(uint64_t base_seed, uint64_t sim_id, double df, int n, double*
 void orc_draw_residual(uint64_t base_seed, uint64_t sim_id, int dist, double df, int n, double* out);
 
 /* per-study lower Cholesky factor of the (perturbed, PSD-repaired) correlation, column-major k x k */
+/* Random intercept + one random slope by profiled REML on supplied data (ids = cluster of each row).  vc = {var_intercept,
+ * var_slope, corr, sigma²}. */
+int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, int n, int p, int slope_col, double* betas,
+                      double* se, double* vc, int* converged, int* boundary, int* n_eval);
 int orc_design_factor(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, double* l_colmajor);
 
 /* ---- transforms (distributions.rs:32-56, data_gen.rs:1106-1182, marginals/t3.rs) ---- */

@@ -62,6 +62,7 @@ class OrcSpec(C.Structure):
         ("n_frame_map", C.c_int32), ("frame_map", C.POINTER(C.c_int32)),
         ("n_var_params", C.c_int32),
         ("n_between", C.c_int32), ("between_cols", C.POINTER(C.c_int32)),
+        ("n_slopes", C.c_int32), ("slope_col", C.c_int32), ("slope_variance", C.c_double), ("slope_corr", C.c_double),
     ]
 
 
@@ -113,6 +114,7 @@ def lib():
     L.orc_apply_correction.argtypes = [C.c_int, P(dbl), C.c_int, dbl, P(dbl), P(C.c_uint8)]
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
     L.orc_design_factor.argtypes = [P(OrcSpec), u64, u64, P(dbl)]
+    L.orc_fit_lmm_slope.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int), P(C.c_int)]
     L.orc_fit_ols.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
                               P(C.c_int)]
     L.orc_fit_glm.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
@@ -242,6 +244,16 @@ class PackedSpec:
             else:
                 s.sizing_fixed_size, s.sizing_value = 1, int(sizing["FixedSize"]["cluster_size"])
             s.tau_squared = float(cl["tau_squared"])
+            slopes = list(cl.get("slopes", []) or [])
+            if len(slopes) > 1 or (cl.get("extra_groupings") or []):
+                raise ValueError("oracle: one random slope on the primary grouping at most")
+            if slopes:
+                cols = list(spec.get("cluster_slope_design_cols", []) or [])
+                if len(cols) != 1:
+                    raise ValueError("invalid spec: cluster_slope_design_cols must name one design column per slope")
+                s.n_slopes, s.slope_col = 1, int(cols[0])
+                s.slope_variance = float(slopes[0]["variance"])
+                s.slope_corr = float(slopes[0]["corr_with_intercept"])
         sc = spec["scenario"]
         s.heterogeneity = float(sc.get("heterogeneity", 0.0))
         s.hsk_ratio = float(sc.get("heteroskedasticity_ratio", 1.0))
@@ -407,6 +419,23 @@ def fit_lmm(x, y, ids):
                              _ptr(se, C.c_double), C.byref(th), C.byref(s2), C.byref(conv), C.byref(bd)))
     return {"betas": b, "se": se, "theta": th.value, "sigma_sq": s2.value, "converged": bool(conv.value),
             "boundary": bd.value}
+
+
+def fit_lmm_slope(x, y, ids, slope_col: int):
+    """Random intercept + one random slope (on design column `slope_col`) by profiled REML on supplied data →
+    dict(betas, se, var_intercept, var_slope, corr, sigma_sq, converged, boundary, n_eval)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    idv = np.ascontiguousarray(ids, dtype=np.int32)
+    b, se, vc = np.zeros(p), np.zeros(p), np.zeros(4)
+    conv, bd, ne = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().orc_fit_lmm_slope(_ptr(xc, C.c_double), _ptr(yv, C.c_double), _ptr(idv, C.c_int32), n, p, int(slope_col),
+                                   _ptr(b, C.c_double), _ptr(se, C.c_double), _ptr(vc, C.c_double), C.byref(conv), C.byref(bd),
+                                   C.byref(ne)))
+    return {"betas": b, "se": se, "var_intercept": vc[0], "var_slope": vc[1], "corr": vc[2], "sigma_sq": vc[3],
+            "converged": bool(conv.value), "boundary": bd.value, "n_eval": ne.value}
 
 
 def run_batch(spec: dict, sample_sizes, n_sims: int, base_seed: int, sim_begin: int = 0, n_threads: int = 1,

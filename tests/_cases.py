@@ -36,7 +36,7 @@ def case_arrays(case: dict):
 
 def golden_arrays(case: dict):
     g = case["golden"]
-    return {k: np.array([float.fromhex(h) for h in g[k]]) for k in ("beta", "se", "stat", "crit")}
+    return {k: np.array([float.fromhex(h) for h in g[k]]) for k in g}
 
 
 def _phi_inv(p: float) -> float:
@@ -109,6 +109,11 @@ def case_spec(case: dict) -> dict:
         s["estimator"] = "mle"
         s["cluster"] = {"sizing": {"FixedClusters": {"n_clusters": int(_one(cl["n_clusters"]))}},
                         "tau_squared": icc / (1.0 - icc), "slopes": [], "extra_groupings": []}
+        for sl in d.get("slopes", []) or []:  # lmm_slope_*: random slope on generation column `column` (ColumnId)
+            col = int(_one(sl["column"]))
+            s["cluster"]["slopes"].append({"column": col, "variance": float(_one(sl["variance"])),
+                                           "corr_with_intercept": float(_one(sl["corr_with_intercept"])), "corr_with": []})
+            s["cluster_slope_design_cols"].append(1 + col)
     return s
 
 

@@ -168,11 +168,13 @@ def f64_hex(a):
 
 def main():
     cases = {}
-    families = ("ols_", "glm_", "probit_", "poisson_", "lme_")
+    families = ("ols_", "glm_", "probit_", "poisson_", "lme_", "lmm_slope_")
     for path in sorted(REF.glob("*.rds")):
         name = path.name[:-4]
         if name.endswith(".golden") or not name.startswith(families):
             continue
+        if name.startswith("lmm_slope_") and name not in ("lmm_slope_a", "lmm_slope_b"):
+            continue  # crossed / nested / extra-slope variants: outside the restated path
         d = read_rds(path)
         gpath = REF / f"{name}.golden.rds"
         g = read_rds(gpath) if gpath.exists() else None
@@ -189,7 +191,10 @@ def main():
             "cluster_ids": d.get("cluster_ids"),
             "mcpower_version": scalar(d.get("mcpower")),
         }
-        if g is not None:
+        if g is not None and "z" in g:  # lmer fits with variance components (validation/common.R: lmm goldens)
+            entry["golden"] = {"beta": f64_hex(g["beta"]), "z": f64_hex(g["z"]), "vars": f64_hex(g["vars"]),
+                               "corr": f64_hex(g["corr"]), "sigma2": f64_hex(g["sigma2"])}
+        elif g is not None:
             gb = g["beta"]
             entry["golden"] = {
                 "beta": f64_hex(gb["_data"] if isinstance(gb, dict) else gb),
