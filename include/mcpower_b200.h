@@ -182,8 +182,8 @@ typedef struct McpFitInfo {
     double tau_sq_hat;           /* MLE: the variance component theta² sigma²; else NaN */
     double deviance;             /* GLM; else NaN */
     double deviance_null;        /* GLM; else NaN */
-    double slope_var_hat;        /* MLE with a random slope: variance of the slope effect sigma² (l10² + l11²); else NaN */
-    double slope_corr_hat;       /* MLE with a random slope: corr(intercept effect, slope effect); else NaN */
+    double slope_var_hat[2];     /* MLE with random slopes: variances of the slope effects (Sigma-hat = sigma² Lambda Lambda'); else NaN */
+    double slope_corr_hat[3];    /* ... and the correlations (slope0, intercept), (slope1, intercept), (slope1, slope0); else NaN */
 } McpFitInfo;
 int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* design_colmajor, uint32_t nrow, uint32_t ncol,
                           const double* outcome, const uint32_t* cluster_ids, int32_t device, double* betas /* [ncol] */,

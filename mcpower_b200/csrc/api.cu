@@ -443,7 +443,7 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     }
     if (s.between_cols.size() > MCP_MAX_P) unsupported("between_var_indices > " + std::to_string(MCP_MAX_P));
     if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
-    if (s.has_slopes_or_groupings) unsupported("more than one random slope / extra groupings");
+    if (s.has_slopes_or_groupings) unsupported("more than two random slopes / extra groupings");
     if (s.n_slopes > 0 && s.P() > MCP_MAX_TEMPLATE_P) unsupported("random slopes with n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
     if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
     for (int v : s.new_dists)
@@ -602,9 +602,12 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         pl.re_words = pl.re_dist == R_HIGH_KURTOSIS ? (int)(1 + dfi) : ((pl.re_dist == R_RIGHT_SKEWED || pl.re_dist == R_LEFT_SKEWED) ? (int)dfi : 1);
     }
     pl.n_slopes = s.has_cluster ? s.n_slopes : 0;
-    pl.slope_col = s.slope_col;
-    pl.slope_variance = s.slope_variance;
-    pl.slope_corr = s.slope_corr;
+    for (int a = 0; a < 2; a++) {
+        pl.slope_col[a] = s.slope_col[a];
+        pl.slope_variance[a] = s.slope_variance[a];
+        pl.slope_corr[a] = s.slope_corr[a];
+    }
+    pl.slope_corr12 = s.slope_corr12;
     // cluster-level predictors: only with a cluster (data_gen.rs:619-620).  A broadcast factor no longer follows the exact walk
     // row by row, so its per-level counts are read off the statistics like a sampled factor's.
     pl.n_between = s.has_cluster ? (int)s.between_cols.size() : 0;
@@ -617,6 +620,12 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.heterogeneity = s.heterogeneity;
     pl.corr_noise_sd = s.corr_noise_sd;
     pl.dist_change_prob = s.dist_change_prob;
+#ifndef MCP_COOP_FORCE
+#define MCP_COOP_FORCE -1  // (tuning builds: 0 / 1 pins the choice)
+#endif
+    // the warp-cooperative marginal pass pays when a good share of the (study, column) blocks stays Normal — measured on the config-3
+    // sweep: +8 % at a swap probability of 0.5, -5 % at 0.8 (profiles/r02_config3.md)
+    pl.coop_marginals = MCP_COOP_FORCE >= 0 ? MCP_COOP_FORCE : (s.dist_change_prob > 0.0 && s.dist_change_prob < MCP_COOP_MAX_PROB ? 1 : 0);
     pl.resid_change_prob = s.resid_change_prob;
     pl.n_new_dists = (int)s.new_dists.size();
     for (size_t i = 0; i < s.new_dists.size(); i++) pl.new_dists[i] = s.new_dists[i];
@@ -1959,7 +1968,9 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
             info->crit_sq_uncorrected = unc;
         }
         const double nan = crit::kNaN;
-        info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = info->slope_var_hat = info->slope_corr_hat = nan;
+        info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = nan;
+        for (int a = 0; a < 2; a++) info->slope_var_hat[a] = nan;
+        for (int a = 0; a < 3; a++) info->slope_corr_hat[a] = nan;
         DeviceCtx& cx = ctx_for(device);
         std::lock_guard<std::mutex> lock(cx.mu);
         const cudaStream_t st = cx.compute;
@@ -2016,7 +2027,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         bind_tables(lw, lw.plan, dblob);
         CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
         lw.plan.error_flag = cx.d_error;
-        const size_t n_out = (size_t)3 * P + 9, n_csum = n_clusters * (size_t)(P + 1) * (size_t)(1 + lw.plan.n_slopes);
+        const size_t n_out = (size_t)3 * P + 12, n_csum = n_clusters * (size_t)(P + 1) * (size_t)(1 + lw.plan.n_slopes);
         Carver oc(cx.outputs.get(Carver::pad(plane.size() * sizeof(float)) + Carver::pad(n_csum * sizeof(double)) + Carver::pad(n_out * sizeof(double))));
         float* dplane = oc.take<float>(plane.size());
         double* dcsum = oc.take<double>(n_csum);
@@ -2048,8 +2059,8 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         info->tau_sq_hat = o[3 * P + 4];
         info->deviance = o[3 * P + 5];
         info->deviance_null = o[3 * P + 6];
-        info->slope_var_hat = o[3 * P + 7];
-        info->slope_corr_hat = o[3 * P + 8];
+        for (int a = 0; a < 2; a++) info->slope_var_hat[a] = o[3 * P + 7 + a];
+        for (int a = 0; a < 3; a++) info->slope_corr_hat[a] = o[3 * P + 9 + a];
     });
 }
 

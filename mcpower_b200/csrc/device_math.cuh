@@ -460,8 +460,10 @@ static __device__ __noinline__ float2 apply_marginal2(float x0, float x1, int di
         double e1 = -own_log_sel(u1 < FL ? FL : u1);
         e0 = e0 > MCP_EXP_CAP ? MCP_EXP_CAP : e0;
         e1 = e1 > MCP_EXP_CAP ? MCP_EXP_CAP : e1;
-        if (dist == 2) return make_float2((float)((e0 - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD), (float)((e1 - MCP_EXP_CENSORED_MEAN) / MCP_EXP_CENSORED_STD));
-        return make_float2((float)((MCP_EXP_CENSORED_MEAN - e0) / MCP_EXP_CENSORED_STD), (float)((MCP_EXP_CENSORED_MEAN - e1) / MCP_EXP_CENSORED_STD));
+        // one division sequence for both skew directions (a warp usually holds both kinds): the numerator is selected, not the path
+        const double n0 = dist == 2 ? e0 - MCP_EXP_CENSORED_MEAN : MCP_EXP_CENSORED_MEAN - e0;
+        const double n1 = dist == 2 ? e1 - MCP_EXP_CENSORED_MEAN : MCP_EXP_CENSORED_MEAN - e1;
+        return make_float2((float)(n0 / MCP_EXP_CENSORED_STD), (float)(n1 / MCP_EXP_CENSORED_STD));
     }
     if (dist == 1) return make_float2(u0 < 1.0 - param ? 0.0f : 1.0f, u1 < 1.0 - param ? 0.0f : 1.0f);
     if (dist == 4) return make_float2((float)t3_lookup(t3, u0), (float)t3_lookup(t3, u1));

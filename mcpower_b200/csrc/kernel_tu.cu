@@ -87,7 +87,11 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         const dim3 grid_fit(blocks, (unsigned)pl.n_ss);
         // resident CTAs per SM the fit kernel is compiled for: the IRLS accumulators (P(P+1)/2 + P doubles) and the two rows
         // in flight set the register floor; measured at P = 5 (config 4, two-row loop): 5 → 1.86e7, 4 → 2.30e7, 3 → 2.17e7 fits/s
+#ifdef MCP_GLM_MINB
+        constexpr int MINB = MCP_GLM_MINB;  // (tuning builds, tools/build_variant.sh)
+#else
         constexpr int MINB = PT <= 6 ? 4 : (PT <= 8 ? 3 : 2);
+#endif
         glm_fit_kernel<PT, MINB><<<grid_fit, MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch);
     }
 #elif defined(MCP_TU_LMM)

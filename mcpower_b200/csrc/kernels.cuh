@@ -442,7 +442,7 @@ struct SimCtx {
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
     uint32_t sim_local = 0;        // the study's index inside the launch (addresses per-wave scratch)
-    double sl10 = 0.0, sl11 = 0.0; // second row of chol(D) of this study's random-effect covariance (random slope)
+    double slL[3][3];              // chol(D) of this study's random-effect covariance (random slopes; rows 1.. are used)
 };
 
 // Residuals of the four rows of Philox block `blk` from the CLASS_RESID slots (data_gen.rs:412-484); slot0 = the slot-0
@@ -726,16 +726,19 @@ static __device__ __noinline__ double re_draw(SimCtx& cx, uint32_t w0) {
 static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
     return (double)(float)(re_draw(cx, c * (uint32_t)c_plan.re_words) * cx.tau);
 }
-// Random-slope effect of cluster c (data_gen.rs:163-213): z_1 is drawn behind ALL the intercept draws, z_0 is recovered from the
-// f32 intercept effect, u_1 = f32(L10 z_0 + L11 z_1) with L = chol(diag(tau) R diag(tau)).
-static __device__ __noinline__ double cluster_slope_effect(SimCtx& cx, uint32_t c, double u0) {
+// Random-slope effects of cluster c (data_gen.rs:163-213): z_1 (, z_2) are drawn behind ALL the intercept draws, cluster by
+// cluster; z_0 is recovered from the f32 intercept effect; u_k = f32(sum_{j <= k} L[k][j] z_j) with L = chol(diag(tau) R diag(tau)).
+static __device__ __noinline__ void cluster_slope_effects(SimCtx& cx, uint32_t c, double u0, double (&uk)[2]) {
     const DevicePlan& pl = c_plan;
-    const double z0 = cx.tau > 0.0 ? u0 / cx.tau : 0.0;
-    const double z1 = re_draw(cx, ((uint32_t)pl.n_clusters + c) * (uint32_t)pl.re_words);
-    double uk = 0.0;
-    uk += cx.sl10 * z0;
-    uk += cx.sl11 * z1;
-    return (double)(float)uk;
+    const int nsl = pl.n_slopes;
+    double z[3];
+    z[0] = cx.tau > 0.0 ? u0 / cx.tau : 0.0;
+    for (int j = 1; j <= nsl; j++) z[j] = re_draw(cx, ((uint32_t)pl.n_clusters + c * (uint32_t)nsl + (uint32_t)(j - 1)) * (uint32_t)pl.re_words);
+    for (int k = 1; k <= nsl; k++) {
+        double u = 0.0;
+        for (int j = 0; j <= k; j++) u += cx.slL[k][j] * z[j];
+        uk[k - 1] = (double)(float)u;
+    }
 }
 
 // Cluster-level predictors (data_gen.rs:605-640): on every non-representative row the marked columns take the value of the
@@ -813,15 +816,36 @@ static __device__ __noinline__ void bootstrap_block(const SlabT slab, int b, uin
 
 // Generate rows 4b..4b+3 of the f32 plane into the thread's slab:
 //   slab[4*(j-1) + r] = X[4b+r][j] for design columns j = 1..P-1,  slab[4*(P-1) + r] = residual draw.
+// marginal transforms of one generated block on the mixed f32 values, two rows of a column per call (same kind: their chains
+// interleave)
+template <int PT, bool SCEN, typename SlabT>
+__device__ __forceinline__ void gen_marginals(const SlabT slab, const ScenDesign<PT>* sd) {
+    const DevicePlan& pl = c_plan;
+#pragma unroll 1
+    for (int j = 0; j < pl.k; j++) {
+        const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
+        if (vt == D_NORMAL) continue;
+        const float2 lo = apply_marginal2(slab[4 * j + 0], slab[4 * j + 1], vt | (j << 8), pl.var_param[j], pl.t3_table);
+        const float2 hi = apply_marginal2(slab[4 * j + 2], slab[4 * j + 3], vt | (j << 8), pl.var_param[j], pl.t3_table);
+        slab[4 * j + 0] = lo.x;
+        slab[4 * j + 1] = lo.y;
+        slab[4 * j + 2] = hi.x;
+        slab[4 * j + 3] = hi.y;
+    }
+}
+
 // gen_block_pre: everything up to and including the factor / bootstrap block (+ the stores of cluster-level predictors);
 // gen_block_post: the loads of cluster-level predictors and the interaction columns.  gen_block = both, for one thread per study.
-template <int PT, bool SCEN, typename SlabT>
+// PHASE 0 = all of it; 1 = up to and including the Cholesky mix (the caller runs the marginal transforms itself: the lane-quad
+// kernels' warp-cooperative pass, kernels_q4.cuh); 2 = the rest (factor block, bootstrap, cluster-level stores).
+template <int PT, bool SCEN, int PHASE = 0, typename SlabT>
 __device__ __forceinline__ void gen_block_pre(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
     constexpr int KT = ScenDesign<PT>::KT;
     const DevicePlan& pl = c_plan;
     const int k = pl.k;
     const uint32_t k0 = cx.k0, k1 = cx.k1;
     const int residual_dist = SCEN ? sd->residual_dist : pl.residual_dist;
+    if (PHASE != 2) {
     // ---- A. normals for the continuous block (CLASS_XNORM=1, column j) and residual slot 0 (CLASS_RESID=2)
     // One "column task" = one Philox block → 4 draws → central polynomial → slab column.  Tasks are independent;
     // the loop is unrolled by 3 so that three Philox chains and six packed Horner chains are in flight per thread
@@ -910,21 +934,10 @@ __device__ __forceinline__ void gen_block_pre(int b, const SlabT slab, SimCtx& c
                 }
             }
         }
-        // marginal transforms on the mixed f32 values, two rows of a column per call (same kind: their chains interleave)
-        if (SCEN || !pl.all_normal) {
-#pragma unroll 1
-            for (int j = 0; j < k; j++) {
-                const int vt = SCEN ? sd->vt[j] : pl.var_type[j];
-                if (vt == D_NORMAL) continue;
-                const float2 lo = apply_marginal2(slab[4 * j + 0], slab[4 * j + 1], vt | (j << 8), pl.var_param[j], pl.t3_table);
-                const float2 hi = apply_marginal2(slab[4 * j + 2], slab[4 * j + 3], vt | (j << 8), pl.var_param[j], pl.t3_table);
-                slab[4 * j + 0] = lo.x;
-                slab[4 * j + 1] = lo.y;
-                slab[4 * j + 2] = hi.x;
-                slab[4 * j + 3] = hi.y;
-            }
-        }
+        if (PHASE == 0 && (SCEN || !pl.all_normal)) gen_marginals<PT, SCEN>(slab, sd);
     }
+    }  // PHASE != 2
+    if (PHASE == 1) return;
     // ---- D. factor dummies (data_gen.rs:509-551) and interactions (643-649), in the f32 plane
     if (pl.n_factors > 0) {
         for (int r = 0; r < 4; r++) {
@@ -982,7 +995,7 @@ __device__ __forceinline__ void gen_block_post(int b, const SlabT slab, SimCtx& 
 
 template <int PT, bool SCEN, typename SlabT>
 __device__ __forceinline__ void gen_block(int b, const SlabT slab, SimCtx& cx, const ScenDesign<PT>* sd) {
-    gen_block_pre<PT, SCEN>(b, slab, cx, sd);
+    gen_block_pre<PT, SCEN, 0>(b, slab, cx, sd);
     gen_block_post<PT, SCEN>(b, slab, cx);
 }
 
@@ -998,12 +1011,31 @@ __device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t 
     cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words * (uint32_t)(1 + pl.n_slopes) : 0u;
     cx.sim_local = sim_local;
     if (pl.n_slopes > 0) {  // chol_lower(D) (data_gen.rs:55-75), D = diag(tau) R diag(tau) with this study's tau0
-        const double tau1 = sqrt(pl.slope_variance > 0.0 ? pl.slope_variance : 0.0);
-        const double d00 = cx.tau * 1.0 * cx.tau, d10 = tau1 * pl.slope_corr * cx.tau, d11 = tau1 * 1.0 * tau1;
-        const double l00 = sqrt(d00 > 0.0 ? d00 : 0.0);
-        cx.sl10 = l00 > 0.0 ? d10 / l00 : 0.0;
-        const double r11 = d11 - cx.sl10 * cx.sl10;
-        cx.sl11 = sqrt(r11 > 0.0 ? r11 : 0.0);
+        const int q = 1 + pl.n_slopes;
+        double tv[3], R[3][3], D[3][3];
+        tv[0] = cx.tau;
+        for (int k = 0; k < pl.n_slopes; k++) tv[1 + k] = sqrt(pl.slope_variance[k] > 0.0 ? pl.slope_variance[k] : 0.0);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                R[i][j] = i == j ? 1.0 : 0.0;
+                cx.slL[i][j] = 0.0;
+            }
+        for (int k = 0; k < pl.n_slopes; k++) R[0][k + 1] = R[k + 1][0] = pl.slope_corr[k];
+        if (pl.n_slopes == 2) R[1][2] = R[2][1] = pl.slope_corr12;
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j < q; j++) D[i][j] = tv[i] * R[i][j] * tv[j];
+        for (int j = 0; j < q; j++) {
+            double diag = D[j][j];
+            for (int k = 0; k < j; k++) diag -= cx.slL[j][k] * cx.slL[j][k];
+            const double ljj = sqrt(diag > 0.0 ? diag : 0.0);
+            cx.slL[j][j] = ljj;
+            for (int i = j + 1; i < q; i++)
+                if (ljj > 0.0) {
+                    double sacc = D[i][j];
+                    for (int k = 0; k < j; k++) sacc -= cx.slL[i][k] * cx.slL[j][k];
+                    cx.slL[i][j] = sacc / ljj;
+                }
+        }
     }
 }
 
@@ -1028,8 +1060,11 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
         // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
         if (cx.utab) u_re = cx.utab[cid];
         else if (cid < (uint32_t)pl.n_clusters) u_re = cluster_effect(cx, cid);
-        if (pl.n_slopes > 0 && cid < (uint32_t)pl.n_clusters)  // data_gen.rs:836-842: u_re += u_1 · x[slope column]
-            u_re += cluster_slope_effect(cx, cid, u_re) * (double)slab[4 * (pl.slope_col - 1) + r];
+        if (pl.n_slopes > 0 && cid < (uint32_t)pl.n_clusters) {  // data_gen.rs:836-842: u_re += u_k · x[slope column k]
+            double uk[2];
+            cluster_slope_effects(cx, cid, u_re, uk);
+            for (int k = 0; k < pl.n_slopes; k++) u_re += uk[k] * (double)slab[4 * (pl.slope_col[k] - 1) + r];
+        }
     }
     if (SCEN) {
         // per-study jittered effects drive y; the clean predictor drives heteroskedasticity (data_gen.rs:781-809)

@@ -327,52 +327,88 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
 // Z'Z = [[n_c, cs1[s]], [cs1[s], cs2[s]]]; M_c = Lambda' Z'Z Lambda + I = L_c L_c'; R_c = L_c^-1 Lambda' Z_c'[X | y];
 // A = X'X − Σ R_c'R_c, b, c likewise; dev = Σ log det M_c + log det A + (n − p) log sigma².  Full model only: a reduced fit
 // (sparse-factor exclusion, test design) strips the slope like the reference (batch.rs:1357-1375).
-#define MCP_SLOPE_NM_MAXEVAL 900
+#define MCP_SLOPE_MAXQ 3
+#define MCP_SLOPE_MAXD 6  // q (q + 1) / 2
+#define MCP_SLOPE_NM_EVAL_PER_DIM 300
 #define MCP_SLOPE_THETA_MAX 30.0
 template <int PT>
 struct SlopeData {
-    const double* cs;  // cluster k, entry j of cs1 at cs[(k·2(PT+1) + j)·stride], of cs2 at + (PT+1)
+    const double* cs;  // cluster k, block a (0: sums of [x | y]; a >= 1: of x_{s_a} · [x | y]), entry j at cs[((k·q + a)(PT+1) + j)·stride]
     size_t stride;
-    int n, n_clusters, slope_col, n_eval;
+    int n, n_clusters, q;
+    int slope_col[MCP_SLOPE_MAXQ];  // slope_col[a] = design column of slope a (a >= 1)
+    int n_eval;
 };
 
+// theta = the lower triangle of Lambda row by row: (l00, l10, l11[, l20, l21, l22]); the diagonal enters as |.|.  Same operations
+// in the same order as the oracle's slope_dev.
 template <int PT>
 static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d, const double* th) {
     const DevicePlan& pl = c_plan;
     constexpr int NT = PT * (PT + 1) / 2;
-    const double l00 = th[0] > 0.0 ? th[0] : 0.0, l10 = th[1], l11 = th[2] > 0.0 ? th[2] : 0.0;
+    const int q = d.q;
+    double Lm[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = i == j ? fabs(th[t]) : th[t];
     for (int e = 0; e < NT; e++) c.A[e] = c.xtx[e];
     for (int j = 0; j < PT; j++) c.b[j] = c.xty[j];
     double cc = c.yty, ldv = 0.0;
-    double r0[PT + 1], r1[PT + 1];
+    double r[MCP_SLOPE_MAXQ][PT + 1];
     for (int k = 0; k < d.n_clusters; k++) {
         const uint32_t cnk = lmm_cluster_rows(pl, k, d.n);
         if (cnk == 0) continue;
-        const double* s1 = d.cs + (size_t)k * 2 * (PT + 1) * d.stride;
-        const double* s2 = s1 + (size_t)(PT + 1) * d.stride;
-        const double S00 = (double)cnk, S01 = s1[(size_t)d.slope_col * d.stride], S11 = s2[(size_t)d.slope_col * d.stride];
-        const double a0 = l00 * S00 + l10 * S01, a1 = l00 * S01 + l10 * S11, b1 = l11 * S11, b0 = l11 * S01;
-        const double m00 = (a0 * l00 + a1 * l10) + 1.0, m10 = b0 * l00 + b1 * l10, m11 = b1 * l11 + 1.0;
-        const double c00 = sqrt(m00), c10 = m10 / c00, c11 = sqrt(m11 - c10 * c10);
-        ldv += own_log(c00) + own_log(c11);
+        const double* sk[MCP_SLOPE_MAXQ];
+        for (int a = 0; a < q; a++) sk[a] = d.cs + (size_t)(k * q + a) * (PT + 1) * d.stride;
+        double S[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], T[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], M[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], C[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+        S[0][0] = (double)cnk;
+        for (int a = 1; a < q; a++) {
+            S[a][0] = S[0][a] = sk[0][(size_t)d.slope_col[a] * d.stride];
+            for (int b = 1; b <= a; b++) S[a][b] = S[b][a] = sk[b][(size_t)d.slope_col[a] * d.stride];
+        }
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j < q; j++) {
+                double acc = 0.0;
+                for (int m = j; m < q; m++) acc += Lm[m][j] * S[i][m];
+                T[i][j] = acc;
+            }
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j <= i; j++) {
+                double acc = 0.0;
+                for (int m = j; m < q; m++) acc += T[m][i] * Lm[m][j];
+                M[i][j] = i == j ? acc + 1.0 : acc;
+            }
+        for (int j = 0; j < q; j++) {
+            double dg = M[j][j];
+            for (int m = 0; m < j; m++) dg -= C[j][m] * C[j][m];
+            C[j][j] = sqrt(dg);
+            for (int i = j + 1; i < q; i++) {
+                double acc = M[i][j];
+                for (int m = 0; m < j; m++) acc -= C[i][m] * C[j][m];
+                C[i][j] = acc / C[j][j];
+            }
+        }
+        {
+            double l = own_log(C[0][0]);
+            for (int j = 1; j < q; j++) l += own_log(C[j][j]);
+            ldv += l;
+        }
         for (int j = 0; j <= PT; j++) {
-            const double v1 = s1[(size_t)j * d.stride], v2 = s2[(size_t)j * d.stride];
-            const double t0 = l00 * v1 + l10 * v2, t1 = l11 * v2;
-            r0[j] = t0 / c00;
-            r1[j] = (t1 - c10 * r0[j]) / c11;
+            for (int i = 0; i < q; i++) {
+                double t = 0.0;
+                for (int m = i; m < q; m++) t += Lm[m][i] * sk[m][(size_t)j * d.stride];
+                for (int m = 0; m < i; m++) t -= C[i][m] * r[m][j];
+                r[i][j] = t / C[i][i];
+            }
         }
         int t = 0;
         for (int a = 0; a < PT; a++) {
             for (int bb = 0; bb <= a; bb++) {
-                c.A[t] = fma(-r0[a], r0[bb], c.A[t]);
-                c.A[t] = fma(-r1[a], r1[bb], c.A[t]);
+                for (int i = 0; i < q; i++) c.A[t] = fma(-r[i][a], r[i][bb], c.A[t]);
                 t++;
             }
-            c.b[a] = fma(-r0[a], r0[PT], c.b[a]);
-            c.b[a] = fma(-r1[a], r1[PT], c.b[a]);
+            for (int i = 0; i < q; i++) c.b[a] = fma(-r[i][a], r[i][PT], c.b[a]);
         }
-        cc = fma(-r0[PT], r0[PT], cc);
-        cc = fma(-r1[PT], r1[PT], cc);
+        for (int i = 0; i < q; i++) cc = fma(-r[i][PT], r[i][PT], cc);
     }
     d.n_eval++;
     c.ms.factor_and_solve(c.A, c.b, PT, cc, 0.0, c.n_rows);
@@ -383,66 +419,67 @@ static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d,
     return 2.0 * ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
 }
 
-// Nelder–Mead in three dimensions; same comparisons in the same order as the oracle's slope_nm.
+// Nelder–Mead in D = q (q + 1) / 2 dimensions; same comparisons in the same order as the oracle's slope_nm.
 template <int PT>
 static __device__ __noinline__ double slope_nm(LmmCtx<PT>& c, SlopeData<PT>& d, double* x, double step, int max_eval) {
-    double sx[4][3], sf[4];
-    for (int i = 0; i < 4; i++) {
-        for (int j = 0; j < 3; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
+    const int D = d.q * (d.q + 1) / 2, V = D + 1;
+    double sx[MCP_SLOPE_MAXD + 1][MCP_SLOPE_MAXD], sf[MCP_SLOPE_MAXD + 1];
+    for (int i = 0; i < V; i++) {
+        for (int j = 0; j < D; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
         sf[i] = slope_dev<PT>(c, d, sx[i]);
     }
     for (;;) {
         int lo = 0, hi = 0, nh;
-        for (int i = 1; i < 4; i++) {
+        for (int i = 1; i < V; i++) {
             if (sf[i] < sf[lo]) lo = i;
             if (sf[i] > sf[hi] || !(sf[i] == sf[i])) hi = i;
         }
         nh = lo;
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < V; i++)
             if (i != hi && (sf[i] > sf[nh])) nh = i;
         double size = 0.0;
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < V; i++)
+            for (int j = 0; j < D; j++) {
                 const double dd = fabs(sx[i][j] - sx[lo][j]);
                 if (dd > size) size = dd;
             }
         if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval) {
-            for (int j = 0; j < 3; j++) x[j] = sx[lo][j];
+            for (int j = 0; j < D; j++) x[j] = sx[lo][j];
             return sf[lo];
         }
-        double cen[3], xr[3], xe[3], xc[3];
-        for (int j = 0; j < 3; j++) {
+        double cen[MCP_SLOPE_MAXD], xr[MCP_SLOPE_MAXD], xe[MCP_SLOPE_MAXD], xc[MCP_SLOPE_MAXD];
+        for (int j = 0; j < D; j++) {
             double sum = 0.0;
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < V; i++)
                 if (i != hi) sum += sx[i][j];
-            cen[j] = sum / 3.0;
+            cen[j] = sum / (double)D;
             xr[j] = cen[j] + (cen[j] - sx[hi][j]);
         }
         const double fr = slope_dev<PT>(c, d, xr);
         if (fr < sf[lo]) {
-            for (int j = 0; j < 3; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
+            for (int j = 0; j < D; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
             const double fe = slope_dev<PT>(c, d, xe);
             if (fe < fr) {
-                for (int j = 0; j < 3; j++) sx[hi][j] = xe[j];
+                for (int j = 0; j < D; j++) sx[hi][j] = xe[j];
                 sf[hi] = fe;
             } else {
-                for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+                for (int j = 0; j < D; j++) sx[hi][j] = xr[j];
                 sf[hi] = fr;
             }
         } else if (fr < sf[nh]) {
-            for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+            for (int j = 0; j < D; j++) sx[hi][j] = xr[j];
             sf[hi] = fr;
         } else {
             const bool outside = fr < sf[hi];
-            for (int j = 0; j < 3; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
+            for (int j = 0; j < D; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
             const double fc = slope_dev<PT>(c, d, xc);
             if (fc < (outside ? fr : sf[hi])) {
-                for (int j = 0; j < 3; j++) sx[hi][j] = xc[j];
+                for (int j = 0; j < D; j++) sx[hi][j] = xc[j];
                 sf[hi] = fc;
             } else {
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < V; i++) {
                     if (i == lo) continue;
-                    for (int j = 0; j < 3; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
+                    for (int j = 0; j < D; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
                     sf[i] = slope_dev<PT>(c, d, sx[i]);
                 }
             }
@@ -452,21 +489,45 @@ static __device__ __noinline__ double slope_nm(LmmCtx<PT>& c, SlopeData<PT>& d, 
 
 template <int PT>
 static __device__ __noinline__ void lmm_slope_fit(LmmCtx<PT>& c, SlopeData<PT>& d, int& converged, int& boundary, double* theta) {
-    double x[3] = {1.0, 0.0, 1.0};
+    const int q = d.q, D = q * (q + 1) / 2, max_eval = MCP_SLOPE_NM_EVAL_PER_DIM * D;
+    double x[MCP_SLOPE_MAXD];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) x[t] = i == j ? 1.0 : 0.0;
     d.n_eval = 0;
-    slope_nm<PT>(c, d, x, 0.5, MCP_SLOPE_NM_MAXEVAL / 2);
-    double f = slope_nm<PT>(c, d, x, 0.05, MCP_SLOPE_NM_MAXEVAL);  // restart from the best vertex
-    x[0] = x[0] > 0.0 ? x[0] : 0.0;
-    x[2] = x[2] > 0.0 ? x[2] : 0.0;
-    f = slope_dev<PT>(c, d, x);  // leaves A, L, beta, sigma² at theta-hat
-    converged = !(isinf(f) || f != f) && d.n_eval < MCP_SLOPE_NM_MAXEVAL;
+    slope_nm<PT>(c, d, x, 0.5, max_eval / 2);
+    double f = slope_nm<PT>(c, d, x, 0.05, max_eval);  // restart from the best vertex
     boundary = 0;
-    if (x[0] < 1e-6 || x[2] < 1e-6) boundary = 1;  // a variance component pinned at 0 (singular fit)
-    if (x[0] > MCP_SLOPE_THETA_MAX || fabs(x[1]) > MCP_SLOPE_THETA_MAX || x[2] > MCP_SLOPE_THETA_MAX) {
-        boundary = 2;
-        converged = 0;
-    }
-    for (int j = 0; j < 3; j++) theta[j] = x[j];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++)
+            if (i == j) {
+                x[t] = fabs(x[t]);
+                if (x[t] < 1e-6) boundary = 1;  // a variance component pinned at 0 (singular fit)
+            }
+    f = slope_dev<PT>(c, d, x);  // leaves A, L, beta, sigma² at theta-hat
+    converged = !(isinf(f) || f != f) && d.n_eval < max_eval;
+    for (int t = 0; t < D; t++)
+        if (fabs(x[t]) > MCP_SLOPE_THETA_MAX) {
+            boundary = 2;
+            converged = 0;
+        }
+    for (int j = 0; j < D; j++) theta[j] = x[j];
+}
+
+// Variance components of Lambda-hat (the oracle's slope_components): out = {Sigma_00 .., corr(1,0)[, corr(2,0), corr(2,1)]}.
+static __device__ __noinline__ void slope_components(const double* th, int q, double sigma_sq, double* var_out, double* corr_out) {
+    double Lm[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], G[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = th[t];
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j <= i; j++) {
+            double acc = 0.0;
+            for (int m = 0; m <= j; m++) acc += Lm[i][m] * Lm[j][m];
+            G[i][j] = acc;
+        }
+    for (int i = 0; i < q; i++) var_out[i] = sigma_sq * G[i][i];
+    int o = 0;
+    for (int i = 1; i < q; i++)
+        for (int j = 0; j < i; j++) corr_out[o++] = G[i][j] / sqrt(G[i][i] * G[j][j]);
 }
 
 // Joint Wald chi-square of the testable targets: beta_T' [Cov_TT]^-1 beta_T, Cov = sigma² A^-1.
@@ -574,12 +635,12 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_gen_kernel(uint64_t base_seed, 
 #pragma unroll
                 for (int j = 0; j < PT; j++) base[(size_t)j * stride] += xr[j];
                 base[(size_t)PT * stride] += yd;
-                if (ns > 0) {  // random slope: sums of x_s · [x | y], one fma per term in row order (the oracle's chains)
-                    double* b2 = base + (size_t)(PT + 1) * stride;
+                for (int a = 0; a < ns; a++) {  // random slopes: sums of x_s · [x | y], one fma per term in row order (the oracle's chains)
+                    double* b2 = base + (size_t)(a + 1) * (PT + 1) * stride;
                     double xs = 0.0;
 #pragma unroll
                     for (int j = 0; j < PT; j++)
-                        if (j == pl.slope_col) xs = xr[j];
+                        if (j == pl.slope_col[a]) xs = xr[j];
 #pragma unroll
                     for (int j = 0; j < PT; j++) b2[(size_t)j * stride] = fma(xs, xr[j], b2[(size_t)j * stride]);
                     b2[(size_t)PT * stride] = fma(xs, yd, b2[(size_t)PT * stride]);
@@ -637,12 +698,12 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
 #pragma unroll
         for (int j = 0; j < PT; j++) base[j] += xr[j];
         base[PT] += yd;
-        if (pl.n_slopes > 0) {
-            double* b2 = base + (PT + 1);
+        for (int a = 0; a < pl.n_slopes; a++) {
+            double* b2 = base + (a + 1) * (PT + 1);
             double xs = 0.0;
 #pragma unroll
             for (int j = 0; j < PT; j++)
-                if (j == pl.slope_col) xs = xr[j];
+                if (j == pl.slope_col[a]) xs = xr[j];
 #pragma unroll
             for (int j = 0; j < PT; j++) b2[j] = fma(xs, xr[j], b2[j]);
             b2[PT] = fma(xs, yd, b2[PT]);
@@ -658,9 +719,9 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     for (int i = 0; i < PT; i++) c.xty[i] = xty[i];
     const int n_clusters = pl.sizing_fixed_size ? (n + cs - 1) / cs : cs;
     int conv = 0, bnd = 0;
-    double theta = 0.0, th3[3] = {0.0, 0.0, 0.0};
+    double theta = 0.0, th3[MCP_SLOPE_MAXD] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (pl.n_slopes > 0) {
-        SlopeData<PT> sd{csum, 1, n, n_clusters, pl.slope_col, 0};
+        SlopeData<PT> sd{csum, 1, n, n_clusters, 1 + pl.n_slopes, {0, pl.slope_col[0], pl.slope_col[1]}, 0};
         lmm_slope_fit<PT>(c, sd, conv, bnd, th3);
         theta = th3[0];
     } else {
@@ -679,9 +740,15 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     out[3 * PT + 4] = theta * theta * c.ms.out.sigma_sq;
     out[3 * PT + 5] = nan;
     out[3 * PT + 6] = nan;
-    // random slope: variance of the slope effect sigma² (l10² + l11²) and corr(intercept, slope) = l10 / sqrt(l10² + l11²)
-    out[3 * PT + 7] = pl.n_slopes > 0 ? c.ms.out.sigma_sq * (th3[1] * th3[1] + th3[2] * th3[2]) : nan;
-    out[3 * PT + 8] = pl.n_slopes > 0 ? th3[1] / sqrt(th3[1] * th3[1] + th3[2] * th3[2]) : nan;
+    // random slopes: variances of the slope effects and the correlations (1,0) [(2,0) (2,1)] of Sigma-hat = sigma² Lambda Lambda'
+    for (int i = 7; i <= 11; i++) out[3 * PT + i] = nan;
+    if (pl.n_slopes > 0) {
+        double vv[MCP_SLOPE_MAXQ], cr[3];
+        slope_components(th3, 1 + pl.n_slopes, c.ms.out.sigma_sq, vv, cr);
+        out[3 * PT + 4] = vv[0];
+        for (int a = 0; a < pl.n_slopes; a++) out[3 * PT + 7 + a] = vv[1 + a];
+        for (int a = 0; a < (pl.n_slopes == 2 ? 3 : 1); a++) out[3 * PT + 9 + a] = cr[a];
+    }
 }
 
 // Stage 2 — one (study, sample size) fit per thread, grid = (blocks of studies, n_ss): profiled REML by Brent over the cluster
@@ -742,8 +809,8 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
         }
         int conv = 0, bnd = 0;
         if (ns > 0 && !reduced) {  // random intercept + slope: 3-parameter REML (the reduced fit strips the slope, batch.rs:1357-1375)
-            SlopeData<PT> sd{snap, stride, n, n_clusters, pl.slope_col, 0};
-            double theta[3];
+            SlopeData<PT> sd{snap, stride, n, n_clusters, 1 + ns, {0, pl.slope_col[0], pl.slope_col[1]}, 0};
+            double theta[MCP_SLOPE_MAXD];
             lmm_slope_fit<PT>(c, sd, conv, bnd, theta);
         } else {
             lmm_fit<PT>(c, snap, stride, n, n_clusters, reduced ? vr.kept : nullptr, conv, bnd, nullptr, (int)LY::cluster_doubles(ns));

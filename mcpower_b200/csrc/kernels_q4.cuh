@@ -118,6 +118,47 @@ static __device__ __noinline__ void q4_count_levels(const Slab<MCP_BLOCK> ps, in
     }
 }
 
+// Warp-cooperative marginal transforms of one generation step (scenario path).  Every lane of the warp has just generated and
+// mixed a 4-row block of ITS study (quad); which continuous columns carry a non-Normal marginal is a per-study draw
+// (data_gen.rs:1040-1060), so a per-lane column loop leaves the lanes of studies whose column j stayed Normal idle (19-22 of 32
+// active, profiles/r01k_split_path.md).  Here the warp's (lane, column) pairs that need a transform are listed in shared memory
+// (exclusive prefix sum of the per-lane counts) and dealt round-robin to all 32 lanes: each transforms four values of some
+// lane's slab in place.  An element sees exactly the arithmetic of gen_block_pre's own loop, so the plane is bit-identical.
+// `nn` = this lane's mask of non-Normal continuous columns (0 for a lane without a block this step).
+template <int PT>
+__device__ __forceinline__ void q4_coop_marginals(unsigned wmask, unsigned nn, const int* __restrict__ vt_of, float* __restrict__ smem,
+                                                  uint16_t* __restrict__ items) {
+    const DevicePlan& pl = c_plan;
+    const int lane = threadIdx.x & 31;
+    const int cnt = __popc(nn);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(wmask, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(wmask, incl, 31 - __clz(wmask));
+    int pos = incl - cnt;  // (a rank-major list — every round 32 different owners — measured slower: the ballot loop costs more than the
+                           //  bank conflicts of one owner's consecutive items, profiles/r02_config3.md)
+    for (unsigned m = nn; m; m &= m - 1u) {
+        const int j = __ffs(m) - 1;
+        items[pos++] = (uint16_t)(lane | (j << 5) | (vt_of[j] << 10));
+    }
+    __syncwarp(wmask);
+    for (int t = lane; t < total; t += 32) {
+        const unsigned it = items[t];
+        const int j = (it >> 5) & 31, vt = it >> 10;
+        const Slab<MCP_BLOCK> ps{smem + (threadIdx.x & ~31u) + (it & 31u)};
+        const float2 lo = apply_marginal2(ps[4 * j + 0], ps[4 * j + 1], vt | (j << 8), pl.var_param[j], pl.t3_table);
+        const float2 hi = apply_marginal2(ps[4 * j + 2], ps[4 * j + 3], vt | (j << 8), pl.var_param[j], pl.t3_table);
+        ps[4 * j + 0] = lo.x;
+        ps[4 * j + 1] = lo.y;
+        ps[4 * j + 2] = hi.x;
+        ps[4 * j + 3] = hi.y;
+    }
+    __syncwarp(wmask);
+}
+
 // SPLIT = true: generate + accumulate only.  At a grid point every lane writes its quarter of Z'Z straight to the wave's
 // statistics buffer stats[(g·E + e)·n_sims + sim] (the lean path's layout, coalesced over the studies of a warp) and
 // ols_solve_kernel (kernels_lean.cuh) fits from there, one thread per fit.  No solver call in the streaming kernel, so
@@ -180,9 +221,14 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         __syncthreads();
     }
     const uint32_t sim = blockIdx.x * G::STUDIES + (threadIdx.x >> 2);
+    // the scenario path's warp-cooperative marginal pass: (lane, column, kind) items of one generation step
+    __shared__ uint16_t coop_items[SCEN ? MCP_BLOCK * (PT > 1 ? PT - 1 : 1) : 1];
     // quads never straddle a warp; a quad past the end idles as a whole, so the quad-masked syncs below see full quads
     if (sim < n_sims) {
         const unsigned qmask = 0xFu << ((threadIdx.x & 31u) & ~3u);
+        // the warp's live lanes: its studies are consecutive, so the quads past the end of the wave are the highest ones
+        const uint32_t warp_first = blockIdx.x * G::STUDIES + ((threadIdx.x >> 5) << 3);
+        const unsigned wmask = n_sims - warp_first >= 8u ? 0xffffffffu : (1u << (4u * (n_sims - warp_first))) - 1u;
         const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
         const int max_n = pl.max_n;
         SimOut so{cnt_s, (uint64_t)sim};
@@ -231,14 +277,28 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_Q4_MIN_BLOCKS) ols_power_kernel
         // lane-dependent halves of the staged row
         const double* const p_base = stage + ((q == 1 || q == 2) ? HOFF : 0);
         const double* const r_base = stage + (q >= 2 ? HOFF : 0);
+        unsigned nn_cols = 0u;  // this study's non-Normal continuous columns
+        if (SCEN)
+            for (int j = 0; j < pl.k; j++) nn_cols |= (sd->vt[j] != D_NORMAL ? 1u : 0u) << j;
         const int n_qsteps = (max_n + 15) >> 4;
         for (int sb = 0; sb < n_qsteps; sb++) {
             {
                 const bool mine = 16 * sb + 4 * q < max_n;
-                if (pl.n_between == 0) {
+                if (SCEN) {
+                    if (mine) gen_block_pre<PT, SCEN, 1>(4 * sb + q, slab, cx, sd);
+                    if (pl.coop_marginals) {
+                        __syncwarp(wmask);
+                        q4_coop_marginals<PT>(wmask, mine ? nn_cols : 0u, sd->vt, smem, coop_items + (threadIdx.x >> 5) * 32 * (PT > 1 ? PT - 1 : 1));
+                    } else if (mine) {
+                        gen_marginals<PT, SCEN>(slab, sd);
+                    }
+                    if (mine) gen_block_pre<PT, SCEN, 2>(4 * sb + q, slab, cx, sd);
+                    if (pl.n_between > 0) __syncwarp(qmask);
+                    if (mine) gen_block_post<PT, SCEN>(4 * sb + q, slab, cx);
+                } else if (pl.n_between == 0) {
                     if (mine) gen_block<PT, SCEN>(4 * sb + q, slab, cx, sd);
                 } else {  // cluster-level predictors: the step's representative rows are stored before any lane loads one
-                    if (mine) gen_block_pre<PT, SCEN>(4 * sb + q, slab, cx, sd);
+                    if (mine) gen_block_pre<PT, SCEN, 0>(4 * sb + q, slab, cx, sd);
                     __syncwarp(qmask);
                     if (mine) gen_block_post<PT, SCEN>(4 * sb + q, slab, cx);
                 }

@@ -9,6 +9,8 @@
 #include <stdint.h>
 
 #define MCP_MAX_K 24          // continuous (non-factor) predictors
+#define MCP_MAX_SLOPES 2      // random slopes on the primary grouping (q = 1 + slopes <= 3 random effects per cluster)
+#define MCP_COOP_MAX_PROB 0.65  // marginal-swap probability below which the scenario kernels take the warp-cooperative marginal pass
 #define MCP_MAX_P 32          // total design columns incl. intercept
 #define MCP_MAX_T 32          // marginal targets + contrasts
 #define MCP_MAX_PH 32         // posthoc pairwise contrasts (all blocks)
@@ -113,15 +115,17 @@ struct DevicePlan {
     // ---- scenario knobs (spec.rs:117-176)
     int32_t optimistic;
     double heterogeneity, hsk_gamma, corr_noise_sd, dist_change_prob, resid_change_prob;
+    int coop_marginals;  // lane-quad scenario kernels: deal the warp's non-Normal (study, column) blocks to all 32 lanes (kernels_q4.cuh)
     int32_t n_new_dists, new_dists[MCP_MAX_MENU];
     int32_t n_resid_dists, resid_dists[MCP_MAX_MENU];
     int32_t has_lme, re_dist;          // scenario.lme (spec.rs:175): random-effect distribution (a McpRes code), ...
     double re_df, icc_noise_sd;        // ... its df, and the sd of the per-study jitter added to tau² (data_gen.rs:1065-1075)
     int32_t re_words;                  // sequential-stream words one random-effect draw consumes (draw_residual, data_gen.rs:1289-1320)
-    // ---- one random slope on the primary grouping (cluster.slopes[0], cluster_slope_design_cols[0]; data_gen.rs:163-213, 836-842)
-    int32_t n_slopes;                  // 0 or 1
-    int32_t slope_col;                 // design column the slope effect multiplies
-    double slope_variance, slope_corr; // tau1², corr(intercept, slope): D = diag(tau) R diag(tau)
+    // ---- random slopes on the primary grouping (cluster.slopes[k], cluster_slope_design_cols[k]; data_gen.rs:163-213, 836-842)
+    int32_t n_slopes;                  // 0, 1 or 2 (MCP_MAX_SLOPES)
+    int32_t slope_col[2];              // design column each slope effect multiplies
+    double slope_variance[2], slope_corr[2];  // tau_k², corr(intercept, slope k): D = diag(tau) R diag(tau) ...
+    double slope_corr12;               // ... and corr(slope 0, slope 1) (slopes[1].corr_with[0], generation.rs:225-240)
     // ---- cluster-level predictors (spec.between_var_indices, data_gen.rs:605-640)
     int32_t n_between;                 // 0 unless the spec has a cluster
     int8_t between_cols[MCP_MAX_P];    // design columns (>= 1) broadcast from the cluster's representative row

@@ -58,8 +58,8 @@ struct Spec {
     int un_rows = 0, un_cols = 0, ud_rows = 0, ud_cols = 0;
     std::vector<int> frame_map;  // bootstrap_frame_map, −1 = None; empty = not bootstrap
     bool has_slopes_or_groupings = false;  // what the CUDA path does not run: > 1 slope, slope-slope correlations, extra groupings
-    int n_slopes = 0, slope_col = -1;      // one random slope on the primary grouping
-    double slope_variance = 0.0, slope_corr = 0.0;
+    int n_slopes = 0, slope_col[2] = {-1, -1};  // random slopes on the primary grouping (two at most)
+    double slope_variance[2] = {0.0, 0.0}, slope_corr[2] = {0.0, 0.0}, slope_corr12 = 0.0;
     std::vector<int> between_cols;  // between_var_indices (spec.rs:279): design columns broadcast within a cluster
     // cluster
     bool has_cluster = false;
@@ -255,13 +255,18 @@ inline Spec parse_spec(const char* json, size_t len) {
             if (auto* q = p->get("extra_groupings")) s.has_slopes_or_groupings |= q->kind == JsonValue::Array && !q->arr.empty();
             if (auto* q = p->get("slopes"))
                 if (q->kind == JsonValue::Array && !q->arr.empty()) {
-                    if (q->arr.size() > 1) s.has_slopes_or_groupings = true;
-                    const JsonValue& sl = q->arr[0];
-                    s.n_slopes = 1;
-                    s.slope_variance = num(req(sl, "variance"), "slopes.variance");
-                    s.slope_corr = num(req(sl, "corr_with_intercept"), "slopes.corr_with_intercept");
+                    if (q->arr.size() > 2) s.has_slopes_or_groupings = true;
                     if (slope_cols.size() != q->arr.size()) invalid("cluster_slope_design_cols must name one design column per random slope");
-                    s.slope_col = slope_cols[0];
+                    s.n_slopes = (int)std::min<size_t>(q->arr.size(), 2);
+                    for (int a = 0; a < s.n_slopes; a++) {
+                        const JsonValue& sl = q->arr[a];
+                        s.slope_variance[a] = num(req(sl, "variance"), "slopes.variance");
+                        s.slope_corr[a] = num(req(sl, "corr_with_intercept"), "slopes.corr_with_intercept");
+                        s.slope_col[a] = slope_cols[a];
+                        if (a == 1)
+                            if (auto* cw = sl.get("corr_with"))
+                                if (cw->kind == JsonValue::Array && !cw->arr.empty()) s.slope_corr12 = num(cw->arr[0], "slopes.corr_with");
+                    }
                 }
         }
     }
@@ -351,9 +356,12 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
         for (int ti : dummies)
             if (ti < 0 || ti >= P) invalid("posthoc target index " + std::to_string(ti) + " out of range (n_predictors = " + std::to_string(P) + ")");
     if (s.n_slopes > 0) {
-        if (s.slope_col < 1 || s.slope_col >= P) invalid("cluster_slope_design_cols entry " + std::to_string(s.slope_col) + " out of range");
+        for (int a = 0; a < s.n_slopes; a++) {
+            if (s.slope_col[a] < 1 || s.slope_col[a] >= P) invalid("cluster_slope_design_cols entry " + std::to_string(s.slope_col[a]) + " out of range");
+            if (!(s.slope_variance[a] >= 0.0) || !(std::fabs(s.slope_corr[a]) <= 1.0)) invalid("random slope variance / correlation out of range");
+        }
+        if (!(std::fabs(s.slope_corr12) <= 1.0)) invalid("random slope variance / correlation out of range");
         if (!(s.tau_squared > 0.0)) invalid("random slopes need tau_squared > 0");  // engine-contract validate(): z0 = u0 / tau0
-        if (!(s.slope_variance >= 0.0) || !(std::fabs(s.slope_corr) <= 1.0)) invalid("random slope variance / correlation out of range");
     }
     for (int c : s.between_cols)  // the reference indexes x_full unchecked (data_gen.rs:631-633); reject instead
         if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("between_var_indices entry " + std::to_string(c) + " out of range");

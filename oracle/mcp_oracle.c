@@ -1118,7 +1118,7 @@ static Ws* ws_new(const OrcSpec* s, int max_n) {
                                       : (s->sizing_value > 0 ? s->sizing_value : 1);
         w->n_cluster_cap = nc;
         w->cluster_u = (float*)calloc((size_t)nc, sizeof(float));
-        w->cluster_u1 = (float*)calloc((size_t)nc, sizeof(float));
+        w->cluster_u1 = (float*)calloc((size_t)nc * 2, sizeof(float));
         w->cluster_ids = (int32_t*)calloc((size_t)max_n, sizeof(int32_t));
         for (int i = 0; i < max_n; i++) /* generation.rs cluster_of_row */
             w->cluster_ids[i] = s->sizing_fixed_size ? i / (s->sizing_value > 0 ? s->sizing_value : 1)
@@ -1275,19 +1275,37 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
         /* 2a'. primary random slope (data_gen.rs:163-213): per cluster z_1 ~ draw_residual AFTER all the intercept draws; z_0 is
          * recovered from the f32 intercept effect; (u_0, u_1) = chol(D) z with D = diag(tau) R diag(tau) */
         if (s->n_slopes > 0) {
-            double tau1 = sqrt(s->slope_variance > 0.0 ? s->slope_variance : 0.0);
-            double d00 = tau * 1.0 * tau, d10 = tau1 * s->slope_corr * tau, d11 = tau1 * 1.0 * tau1;
-            double l00 = sqrt(d00 > 0.0 ? d00 : 0.0);
-            double l10 = l00 > 0.0 ? d10 / l00 : 0.0;
-            double r11 = d11 - l10 * l10;
-            double l11 = sqrt(r11 > 0.0 ? r11 : 0.0);
+            const int nsl = s->n_slopes, q = 1 + nsl;
+            double tv[3], R[9], D[9], L[9], z[3];
+            tv[0] = tau;
+            for (int k = 0; k < nsl; k++) tv[1 + k] = sqrt(s->slope_variance[k] > 0.0 ? s->slope_variance[k] : 0.0);
+            for (int i = 0; i < q * q; i++) R[i] = 0.0;
+            for (int d = 0; d < q; d++) R[d * q + d] = 1.0;
+            for (int k = 0; k < nsl; k++) R[k + 1] = R[(k + 1) * q] = s->slope_corr[k];
+            if (nsl == 2) R[1 * q + 2] = R[2 * q + 1] = s->slope_corr12;
+            for (int i = 0; i < q; i++)
+                for (int j = 0; j < q; j++) D[i * q + j] = tv[i] * R[i * q + j] * tv[j];
+            for (int i = 0; i < q * q; i++) L[i] = 0.0;
+            for (int j = 0; j < q; j++) { /* chol_lower (data_gen.rs:55-75) */
+                double diag = D[j * q + j];
+                for (int k = 0; k < j; k++) diag -= L[j * q + k] * L[j * q + k];
+                const double ljj = sqrt(diag > 0.0 ? diag : 0.0);
+                L[j * q + j] = ljj;
+                for (int i = j + 1; i < q; i++)
+                    if (ljj > 0.0) {
+                        double sacc = D[i * q + j];
+                        for (int k = 0; k < j; k++) sacc -= L[i * q + k] * L[j * q + k];
+                        L[i * q + j] = sacc / ljj;
+                    }
+            }
             for (int c = 0; c < nc; c++) {
-                double z0 = tau > 0.0 ? (double)w->cluster_u[c] / tau : 0.0;
-                double z1 = draw_residual(&rng, re_dist, re_df);
-                double uk = 0.0;
-                uk += l10 * z0;
-                uk += l11 * z1;
-                w->cluster_u1[c] = (float)uk;
+                z[0] = tau > 0.0 ? (double)w->cluster_u[c] / tau : 0.0;
+                for (int j = 1; j < q; j++) z[j] = draw_residual(&rng, re_dist, re_df);
+                for (int k = 1; k < q; k++) {
+                    double uk = 0.0;
+                    for (int j = 0; j <= k; j++) uk += L[k * q + j] * z[j];
+                    w->cluster_u1[(size_t)c * nsl + (k - 1)] = (float)uk;
+                }
             }
         }
     }
@@ -1481,8 +1499,9 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
             w->mix_acc[i] = gamma * z;
         }
         double u_re = s->has_cluster ? (double)w->cluster_u[w->cluster_ids[i]] : 0.0;
-        if (s->has_cluster && s->n_slopes > 0) /* data_gen.rs:836-842 */
-            u_re += (double)w->cluster_u1[w->cluster_ids[i]] * (double)w->x[(size_t)s->slope_col * max_n + i];
+        if (s->has_cluster) /* data_gen.rs:836-842 */
+            for (int k = 0; k < s->n_slopes; k++)
+                u_re += (double)w->cluster_u1[(size_t)w->cluster_ids[i] * s->n_slopes + k] * (double)w->x[(size_t)s->slope_col[k] * max_n + i];
         if (s->outcome_kind == ORC_OUT_CONTINUOUS && !apply_hsk) w->y[i] = (float)(lp + (double)w->residuals[i] + u_re);
         else w->eta_acc[i] = lp + u_re;
     }
@@ -1540,9 +1559,10 @@ static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* ba
         if (s->contrast_pairs[c] < 0 || s->contrast_pairs[c] >= P) return fail(ORC_ERR_INVALID_SPEC, "contrast_pairs entry out of range");
     int k = s->n_non_factor;
     if (s->n_slopes > 0) {
-        if (!s->has_cluster || s->n_slopes > 1) return fail(ORC_ERR_INVALID_SPEC, "random slopes need a cluster (one slope at most)");
-        if (s->slope_col < 1 || s->slope_col >= 1 + s->n_non_factor + s->n_factor_dummies + s->n_interactions)
-            return fail(ORC_ERR_INVALID_SPEC, "cluster_slope_design_cols entry out of range");
+        if (!s->has_cluster || s->n_slopes > 2) return fail(ORC_ERR_INVALID_SPEC, "random slopes need a cluster (two slopes at most)");
+        for (int q = 0; q < s->n_slopes; q++)
+            if (s->slope_col[q] < 1 || s->slope_col[q] >= 1 + s->n_non_factor + s->n_factor_dummies + s->n_interactions)
+                return fail(ORC_ERR_INVALID_SPEC, "cluster_slope_design_cols entry out of range");
         if (!(s->tau_squared > 0.0)) return fail(ORC_ERR_INVALID_SPEC, "random slopes need tau_squared > 0"); /* validate.rs invariant */
     }
     for (int b = 0; b < s->n_between; b++) /* the reference indexes x_full unchecked (a malformed spec panics); the backends reject it */
@@ -1996,49 +2016,85 @@ static void lmm_fit(LmmCtx* c, const double* csum, const uint32_t* cn, int n_clu
  * Per cluster the statistics are the sums of [x | y] (cs1) and of x_s * [x | y] (cs2): Z'Z = [[n_c, cs1[s]], [cs1[s], cs2[s]]].
  * Minimised by a deterministic Nelder-Mead (one restart) with the diagonal of Lambda clamped at 0; restated op for op in the
  * CUDA kernel.  Pinned to lme4's REML fits of the reference's lmm_slope datasets (tolerances.R:29-31, 38-49). */
-#define SLOPE_NM_MAXEVAL 900
+#define SLOPE_MAXQ 3
+#define SLOPE_MAXD 6 /* q (q + 1) / 2 */
+#define SLOPE_NM_EVAL_PER_DIM 300
 #define SLOPE_THETA_MAX 30.0
 typedef struct {
-    const double *cs1, *cs2; /* [n_clusters][p + 1] */
+    const double* cs[SLOPE_MAXQ]; /* cs[0]: per-cluster sums of [x | y]; cs[a]: of x_{s_a} * [x | y]; each [n_clusters][p + 1] */
     const uint32_t* cn;
-    int n_clusters, slope_col;
+    int n_clusters, q;
+    int slope_col[SLOPE_MAXQ]; /* slope_col[a] = design column of slope a (a >= 1) */
     int n_eval;
 } SlopeData;
 
-static double slope_dev(LmmCtx* c, const SlopeData* d, const double th[3]) {
-    const int p = c->p;
+/* theta = the lower triangle of Lambda row by row: (l00, l10, l11[, l20, l21, l22]); diagonal entries clamped at 0 */
+static double slope_dev(LmmCtx* c, const SlopeData* d, const double* th) {
+    const int p = c->p, q = d->q;
     const size_t nt = (size_t)p * (p + 1) / 2;
-    const double l00 = th[0] > 0.0 ? th[0] : 0.0, l10 = th[1], l11 = th[2] > 0.0 ? th[2] : 0.0;
+    double Lm[SLOPE_MAXQ][SLOPE_MAXQ];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = i == j ? fabs(th[t]) : th[t];
     for (size_t e = 0; e < nt; e++) c->A[e] = c->xtx[e];
     for (int j = 0; j < p; j++) c->b[j] = c->xty[j];
     double cc = c->yty, ldv = 0.0;
-    double r0[65], r1[65];
+    double r[SLOPE_MAXQ][65];
     for (int k = 0; k < d->n_clusters; k++) {
         if (d->cn[k] == 0) continue;
-        const double* s1 = d->cs1 + (size_t)k * (p + 1);
-        const double* s2 = d->cs2 + (size_t)k * (p + 1);
-        const double S00 = (double)d->cn[k], S01 = s1[d->slope_col], S11 = s2[d->slope_col];
-        const double a0 = l00 * S00 + l10 * S01, a1 = l00 * S01 + l10 * S11, b1 = l11 * S11, b0 = l11 * S01;
-        const double m00 = (a0 * l00 + a1 * l10) + 1.0, m10 = b0 * l00 + b1 * l10, m11 = b1 * l11 + 1.0;
-        const double c00 = sqrt(m00), c10 = m10 / c00, c11 = sqrt(m11 - c10 * c10);
-        ldv += orc_log(c00) + orc_log(c11);
-        for (int j = 0; j <= p; j++) {
-            const double t0 = l00 * s1[j] + l10 * s2[j], t1 = l11 * s2[j];
-            r0[j] = t0 / c00;
-            r1[j] = (t1 - c10 * r0[j]) / c11;
+        const double* sk[SLOPE_MAXQ];
+        for (int a = 0; a < q; a++) sk[a] = d->cs[a] + (size_t)k * (p + 1);
+        /* S = Z'Z (symmetric q x q): S[0][0] = n_k, S[a][0] = sum x_a, S[a][b] = sum x_a x_b */
+        double S[SLOPE_MAXQ][SLOPE_MAXQ], T[SLOPE_MAXQ][SLOPE_MAXQ], M[SLOPE_MAXQ][SLOPE_MAXQ], C[SLOPE_MAXQ][SLOPE_MAXQ];
+        S[0][0] = (double)d->cn[k];
+        for (int a = 1; a < q; a++) {
+            S[a][0] = S[0][a] = sk[0][d->slope_col[a]];
+            for (int b = 1; b <= a; b++) S[a][b] = S[b][a] = sk[b][d->slope_col[a]];
+        }
+        /* T = S Lambda; M = Lambda' S Lambda + I (lower part: M[i][j] = sum_k T[k][i] Lambda[k][j]) */
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j < q; j++) {
+                double acc = 0.0;
+                for (int m = j; m < q; m++) acc += Lm[m][j] * S[i][m];
+                T[i][j] = acc;
+            }
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j <= i; j++) {
+                double acc = 0.0;
+                for (int m = j; m < q; m++) acc += T[m][i] * Lm[m][j];
+                M[i][j] = i == j ? acc + 1.0 : acc;
+            }
+        for (int j = 0; j < q; j++) { /* C = chol(M) */
+            double dg = M[j][j];
+            for (int m = 0; m < j; m++) dg -= C[j][m] * C[j][m];
+            C[j][j] = sqrt(dg);
+            for (int i = j + 1; i < q; i++) {
+                double acc = M[i][j];
+                for (int m = 0; m < j; m++) acc -= C[i][m] * C[j][m];
+                C[i][j] = acc / C[j][j];
+            }
+        }
+        { /* log det, summed pairwise from the front like the q = 2 form: log c00 + log c11 (+ log c22) */
+            double l = orc_log(C[0][0]);
+            for (int j = 1; j < q; j++) l += orc_log(C[j][j]);
+            ldv += l;
+        }
+        for (int j = 0; j <= p; j++) { /* R = C^-1 Lambda' Z'[X | y] */
+            for (int i = 0; i < q; i++) {
+                double t = 0.0;
+                for (int m = i; m < q; m++) t += Lm[m][i] * sk[m][j];
+                for (int m = 0; m < i; m++) t -= C[i][m] * r[m][j];
+                r[i][j] = t / C[i][i];
+            }
         }
         size_t t = 0;
         for (int a = 0; a < p; a++) {
             for (int bb = 0; bb <= a; bb++) {
-                c->A[t] = fma(-r0[a], r0[bb], c->A[t]);
-                c->A[t] = fma(-r1[a], r1[bb], c->A[t]);
+                for (int i = 0; i < q; i++) c->A[t] = fma(-r[i][a], r[i][bb], c->A[t]);
                 t++;
             }
-            c->b[a] = fma(-r0[a], r0[p], c->b[a]);
-            c->b[a] = fma(-r1[a], r1[p], c->b[a]);
+            for (int i = 0; i < q; i++) c->b[a] = fma(-r[i][a], r[i][p], c->b[a]);
         }
-        cc = fma(-r0[p], r0[p], cc);
-        cc = fma(-r1[p], r1[p], cc);
+        for (int i = 0; i < q; i++) cc = fma(-r[i][p], r[i][p], cc);
     }
     ((SlopeData*)d)->n_eval++;
     ols_solve(c->A, c->b, cc, 0.0, c->n_rows, p, c->L, c->inv_d, c->wv, c->beta, &c->fit);
@@ -2048,63 +2104,64 @@ static double slope_dev(LmmCtx* c, const SlopeData* d, const double th[3]) {
     return 2.0 * ldv + 2.0 * lda + c->fit.df_resid * orc_log(c->fit.sigma_sq);
 }
 
-/* Nelder-Mead in 3 dimensions (reflection 1, expansion 2, contraction 1/2, shrink 1/2); x0 +- step initial simplex; stops when
- * the simplex is flat (1e-11 relative in f) and small (1e-7 in every coordinate) or after max_eval evaluations.  Ties and
- * orderings are resolved by strict comparisons in a fixed order, so the CUDA twin takes the same path. */
-static double slope_nm(LmmCtx* c, SlopeData* d, double x[3], const double step[3], int max_eval) {
-    double sx[4][3], sf[4];
-    for (int i = 0; i < 4; i++) {
-        for (int j = 0; j < 3; j++) sx[i][j] = x[j] + (i == j + 1 ? step[j] : 0.0);
+/* Nelder-Mead in D = q (q + 1) / 2 dimensions (reflection 1, expansion 2, contraction 1/2, shrink 1/2); x0 + step initial
+ * simplex; stops when the simplex is flat (1e-11 relative in f) and small (1e-7 in every coordinate) or after max_eval
+ * evaluations.  Ties and orderings are resolved by strict comparisons in a fixed order, so the CUDA twin takes the same path. */
+static double slope_nm(LmmCtx* c, SlopeData* d, double* x, double step, int max_eval) {
+    const int D = d->q * (d->q + 1) / 2, V = D + 1;
+    double sx[SLOPE_MAXD + 1][SLOPE_MAXD], sf[SLOPE_MAXD + 1];
+    for (int i = 0; i < V; i++) {
+        for (int j = 0; j < D; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
         sf[i] = slope_dev(c, d, sx[i]);
     }
     for (;;) {
         /* order: best (lo), worst (hi), second worst (nh) */
         int lo = 0, hi = 0, nh;
-        for (int i = 1; i < 4; i++) {
+        for (int i = 1; i < V; i++) {
             if (sf[i] < sf[lo]) lo = i;
             if (sf[i] > sf[hi] || !(sf[i] == sf[i])) hi = i;
         }
         nh = lo;
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < V; i++)
             if (i != hi && (sf[i] > sf[nh])) nh = i;
         double size = 0.0;
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 3; j++) {
+        for (int i = 0; i < V; i++)
+            for (int j = 0; j < D; j++) {
                 double dd = fabs(sx[i][j] - sx[lo][j]);
                 if (dd > size) size = dd;
             }
         if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d->n_eval >= max_eval) {
-            for (int j = 0; j < 3; j++) x[j] = sx[lo][j];
+            for (int j = 0; j < D; j++) x[j] = sx[lo][j];
             return sf[lo];
         }
-        double cen[3], xr[3], xe[3], xc[3];
-        for (int j = 0; j < 3; j++) {
+        double cen[SLOPE_MAXD], xr[SLOPE_MAXD], xe[SLOPE_MAXD], xc[SLOPE_MAXD];
+        for (int j = 0; j < D; j++) {
             double sum = 0.0;
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < V; i++)
                 if (i != hi) sum += sx[i][j];
-            cen[j] = sum / 3.0;
+            cen[j] = sum / (double)D;
             xr[j] = cen[j] + (cen[j] - sx[hi][j]);
         }
         double fr = slope_dev(c, d, xr);
         if (fr < sf[lo]) {
-            for (int j = 0; j < 3; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
+            for (int j = 0; j < D; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
             double fe = slope_dev(c, d, xe);
-            if (fe < fr) { for (int j = 0; j < 3; j++) sx[hi][j] = xe[j]; sf[hi] = fe; }
-            else { for (int j = 0; j < 3; j++) sx[hi][j] = xr[j]; sf[hi] = fr; }
+            if (fe < fr) { for (int j = 0; j < D; j++) sx[hi][j] = xe[j]; sf[hi] = fe; }
+            else { for (int j = 0; j < D; j++) sx[hi][j] = xr[j]; sf[hi] = fr; }
         } else if (fr < sf[nh]) {
-            for (int j = 0; j < 3; j++) sx[hi][j] = xr[j];
+            for (int j = 0; j < D; j++) sx[hi][j] = xr[j];
             sf[hi] = fr;
         } else {
             const int outside = fr < sf[hi];
-            for (int j = 0; j < 3; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
+            for (int j = 0; j < D; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
             double fc = slope_dev(c, d, xc);
             if (fc < (outside ? fr : sf[hi])) {
-                for (int j = 0; j < 3; j++) sx[hi][j] = xc[j];
+                for (int j = 0; j < D; j++) sx[hi][j] = xc[j];
                 sf[hi] = fc;
             } else {
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < V; i++) {
                     if (i == lo) continue;
-                    for (int j = 0; j < 3; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
+                    for (int j = 0; j < D; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
                     sf[i] = slope_dev(c, d, sx[i]);
                 }
             }
@@ -2114,24 +2171,30 @@ static double slope_nm(LmmCtx* c, SlopeData* d, double x[3], const double step[3
 
 typedef struct {
     int converged, boundary_hit, n_eval;
-    double theta[3], sigma_sq;
+    double theta[SLOPE_MAXD], sigma_sq;
 } SlopeOut;
 
 static void lmm_slope_fit(LmmCtx* c, SlopeData* d, SlopeOut* out) {
-    double x[3] = {1.0, 0.0, 1.0};
-    const double step0[3] = {0.5, 0.5, 0.5}, step1[3] = {0.05, 0.05, 0.05};
+    const int q = d->q, D = q * (q + 1) / 2, max_eval = SLOPE_NM_EVAL_PER_DIM * D;
+    double x[SLOPE_MAXD];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) x[t] = i == j ? 1.0 : 0.0;
     d->n_eval = 0;
-    slope_nm(c, d, x, step0, SLOPE_NM_MAXEVAL / 2);
-    double f = slope_nm(c, d, x, step1, SLOPE_NM_MAXEVAL); /* restart from the best vertex: guards against a collapsed simplex */
-    x[0] = x[0] > 0.0 ? x[0] : 0.0;
-    x[2] = x[2] > 0.0 ? x[2] : 0.0;
-    f = slope_dev(c, d, x); /* leaves A, L, beta, sigma at theta-hat */
-    out->converged = isfinite(f) && d->n_eval < SLOPE_NM_MAXEVAL;
+    slope_nm(c, d, x, 0.5, max_eval / 2);
+    double f = slope_nm(c, d, x, 0.05, max_eval); /* restart from the best vertex: guards against a collapsed simplex */
     out->boundary_hit = 0;
-    if (x[0] < 1e-6 || x[2] < 1e-6) out->boundary_hit = 1; /* a variance component pinned at 0 (singular fit) */
-    if (x[0] > SLOPE_THETA_MAX || fabs(x[1]) > SLOPE_THETA_MAX || x[2] > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++)
+            if (i == j) {
+                x[t] = fabs(x[t]);
+                if (x[t] < 1e-6) out->boundary_hit = 1; /* a variance component pinned at 0 (singular fit) */
+            }
+    f = slope_dev(c, d, x); /* leaves A, L, beta, sigma at theta-hat */
+    out->converged = isfinite(f) && d->n_eval < max_eval;
+    for (int t = 0; t < D; t++)
+        if (fabs(x[t]) > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
     out->n_eval = d->n_eval;
-    for (int j = 0; j < 3; j++) out->theta[j] = x[j];
+    for (int j = 0; j < D; j++) out->theta[j] = x[j];
     out->sigma_sq = c->fit.sigma_sq;
 }
 
@@ -2200,37 +2263,57 @@ int orc_fit_lmm(const double* xc, const double* yv, const int32_t* ids, int n, i
 /* ======================================================================= */
 
 /* batch.rs:2451-2496 */
-int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, int n, int p, int slope_col, double* betas,
-                      double* se, double* vc, int* converged, int* boundary, int* n_eval) {
-    if (p > 64 || slope_col < 0 || slope_col >= p) return fail(ORC_ERR_INVALID_SPEC, "bad p / slope column");
+/* variance components of Lambda-hat: Sigma = sigma² Lambda Lambda'; out = {Sigma_00 .. Sigma_{q-1,q-1}, corr(1,0)[, corr(2,0), corr(2,1)], sigma²} */
+static void slope_components(const double* th, int q, double sigma_sq, double* out) {
+    double Lm[SLOPE_MAXQ][SLOPE_MAXQ] = {{0}}, G[SLOPE_MAXQ][SLOPE_MAXQ];
+    for (int i = 0, t = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = th[t];
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j <= i; j++) {
+            double acc = 0.0;
+            for (int m = 0; m <= j; m++) acc += Lm[i][m] * Lm[j][m];
+            G[i][j] = acc;
+        }
+    int o = 0;
+    for (int i = 0; i < q; i++) out[o++] = sigma_sq * G[i][i];
+    for (int i = 1; i < q; i++)
+        for (int j = 0; j < i; j++) out[o++] = G[i][j] / sqrt(G[i][i] * G[j][j]);
+    out[o] = sigma_sq;
+}
+
+int orc_fit_lmm_slopes(const double* xc, const double* yv, const int32_t* ids, int n, int p, int n_slopes, const int32_t* slope_cols,
+                       double* betas, double* se, double* vc, int* converged, int* boundary, int* n_eval) {
+    if (p > 64 || n_slopes < 1 || n_slopes > 2) return fail(ORC_ERR_INVALID_SPEC, "bad p / slope count");
+    for (int a = 0; a < n_slopes; a++)
+        if (slope_cols[a] < 0 || slope_cols[a] >= p) return fail(ORC_ERR_INVALID_SPEC, "bad slope column");
+    const int q = 1 + n_slopes;
     float* x = (float*)malloc(sizeof(float) * (size_t)n * p);
     float* y = (float*)malloc(sizeof(float) * (size_t)n);
     for (size_t i = 0; i < (size_t)n * p; i++) x[i] = (float)xc[i];
     for (int i = 0; i < n; i++) y[i] = (float)yv[i];
     int nc = 0;
     for (int i = 0; i < n; i++) if (ids[i] + 1 > nc) nc = ids[i] + 1;
-    size_t nt = (size_t)p * (p + 1) / 2;
-    double* xtx = (double*)calloc(nt + (size_t)p + (size_t)nc * (p + 1) * 2, sizeof(double));
-    double *xty = xtx + nt, *cs1 = xty + p, *cs2 = cs1 + (size_t)nc * (p + 1);
+    size_t nt = (size_t)p * (p + 1) / 2, cl = (size_t)nc * (p + 1);
+    double* xtx = (double*)calloc(nt + (size_t)p + cl * 3, sizeof(double));
+    double *xty = xtx + nt, *cs0 = xty + p;
     uint32_t* cn = (uint32_t*)calloc((size_t)nc, sizeof(uint32_t));
     SuffScalars sc = {0.0, 0.0, 0};
     suff_add_rows(x, y, n, p, 0, n, xtx, xty, &sc);
     for (int i = 0; i < n; i++) {
-        double* s1 = cs1 + (size_t)ids[i] * (p + 1);
-        double* s2 = cs2 + (size_t)ids[i] * (p + 1);
-        const double xs = (double)x[(size_t)slope_col * n + i];
-        for (int j = 0; j < p; j++) {
-            const double xv = (double)x[(size_t)j * n + i];
-            s1[j] += xv;
-            s2[j] = fma(xs, xv, s2[j]);
-        }
+        double* s1 = cs0 + (size_t)ids[i] * (p + 1);
+        for (int j = 0; j < p; j++) s1[j] += (double)x[(size_t)j * n + i];
         s1[p] += (double)y[i];
-        s2[p] = fma(xs, (double)y[i], s2[p]);
+        for (int a = 1; a < q; a++) {
+            double* s2 = cs0 + cl * a + (size_t)ids[i] * (p + 1);
+            const double xs = (double)x[(size_t)slope_cols[a - 1] * n + i];
+            for (int j = 0; j < p; j++) s2[j] = fma(xs, (double)x[(size_t)j * n + i], s2[j]);
+            s2[p] = fma(xs, (double)y[i], s2[p]);
+        }
         cn[ids[i]]++;
     }
     LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
     c->p = p; c->n_rows = (uint32_t)n; c->xtx = xtx; c->xty = xty; c->yty = sc.yty;
-    SlopeData d = {cs1, cs2, cn, nc, slope_col, 0};
+    SlopeData d = {{cs0, cs0 + cl, cs0 + 2 * cl}, cn, nc, q, {0, slope_cols[0], n_slopes > 1 ? slope_cols[1] : 0}, 0};
     SlopeOut o;
     lmm_slope_fit(c, &d, &o);
     double u[64];
@@ -2238,14 +2321,16 @@ int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, in
         betas[t] = c->beta[t];
         se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
     }
-    const double l00 = o.theta[0], l10 = o.theta[1], l11 = o.theta[2];
-    vc[0] = o.sigma_sq * l00 * l00;
-    vc[1] = o.sigma_sq * (l10 * l10 + l11 * l11);
-    vc[2] = l10 / sqrt(l10 * l10 + l11 * l11);
-    vc[3] = o.sigma_sq;
+    slope_components(o.theta, q, o.sigma_sq, vc);
     *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
     free(c); free(cn); free(xtx); free(x); free(y);
     return ORC_OK;
+}
+
+int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, int n, int p, int slope_col, double* betas,
+                      double* se, double* vc, int* converged, int* boundary, int* n_eval) {
+    const int32_t cols[1] = {slope_col};
+    return orc_fit_lmm_slopes(xc, yv, ids, n, p, 1, cols, betas, se, vc, converged, boundary, n_eval);
 }
 
 static void update_factor_exclusions(const OrcSpec* s, const float* x, int ld, int from, int to, uint32_t* counts, uint8_t* flags) {
@@ -2532,9 +2617,10 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
     int nprops = 0;
     for (int f = 0; f < s->n_factors; f++) nprops += s->factor_n_levels[f];
     int test_reduces = s->n_fit_columns > 0 && s->n_fit_columns < P;
-    double* csum = (double*)calloc((size_t)nc_cap * (P + 1) * 3, sizeof(double));
+    double* csum = (double*)calloc((size_t)nc_cap * (P + 1) * 4, sizeof(double));
     double* csum_red = csum + (size_t)nc_cap * (P + 1);
-    double* csum2 = csum_red + (size_t)nc_cap * (P + 1); /* random slope: per-cluster sums of x_s * [x | y] */
+    double* csum2 = csum_red + (size_t)nc_cap * (P + 1); /* random slopes: per-cluster sums of x_s * [x | y], one block per slope */
+    const size_t cs_block = (size_t)nc_cap * (P + 1);
     uint32_t* cn = (uint32_t*)calloc((size_t)nc_cap, sizeof(uint32_t));
     LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
     memset(w->xtx, 0, sizeof(double) * nt);
@@ -2552,9 +2638,9 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
                 double* sx = csum + (size_t)k * (P + 1);
                 for (int j = 0; j < P; j++) sx[j] += (double)w->x[(size_t)j * ld + i];
                 sx[P] += (double)w->y[i];
-                if (s->n_slopes > 0) {
-                    double* s2 = csum2 + (size_t)k * (P + 1);
-                    const double xs = (double)w->x[(size_t)s->slope_col * ld + i];
+                for (int a = 0; a < s->n_slopes; a++) {
+                    double* s2 = csum2 + cs_block * a + (size_t)k * (P + 1);
+                    const double xs = (double)w->x[(size_t)s->slope_col[a] * ld + i];
                     for (int j = 0; j < P; j++) s2[j] = fma(xs, (double)w->x[(size_t)j * ld + i], s2[j]);
                     s2[P] = fma(xs, (double)w->y[i], s2[P]);
                 }
@@ -2573,10 +2659,11 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
         LmmOut lo;
         c->n_rows = sc.n_rows; c->yty = sc.yty;
         if (!reduced && s->n_slopes > 0) {
-            /* full model with the random slope: 3-parameter REML; the reduced fit below strips the slope like the reference
+            /* full model with the random slopes: 3- / 6-parameter REML; the reduced fit below strips the slopes like the reference
              * (batch.rs:1357-1375) */
             c->p = P; c->xtx = w->xtx; c->xty = w->xty;
-            SlopeData sd = {csum, csum2, cn, n_clusters, s->slope_col, 0};
+            SlopeData sd = {{csum, csum2, csum2 + cs_block}, cn, n_clusters, 1 + s->n_slopes,
+                            {0, s->slope_col[0], s->n_slopes > 1 ? s->slope_col[1] : 0}, 0};
             SlopeOut so;
             lmm_slope_fit(c, &sd, &so);
             lo.converged = so.converged; lo.boundary_hit = so.boundary_hit; lo.theta = so.theta[0]; lo.sigma_sq = so.sigma_sq;

@@ -93,11 +93,13 @@ typedef struct {
      * cluster is the value on the cluster's representative (first) row */
     int32_t n_between;
     const int32_t* between_cols;
-    /* one random slope on the primary grouping (cluster.slopes[0] + cluster_slope_design_cols[0]; data_gen.rs:163-213,
-     * 836-842): RE covariance D = [[tau0², rho tau0 tau1], [., tau1²]] */
-    int32_t n_slopes;               /* 0 or 1 */
-    int32_t slope_col;              /* design column the slope multiplies */
-    double slope_variance, slope_corr;
+    /* random slopes on the primary grouping (cluster.slopes[k] + cluster_slope_design_cols[k]; data_gen.rs:163-213, 836-842):
+     * RE covariance D = diag(tau) R diag(tau) over [intercept, slope_0, slope_1], R from re_correlation_from_slopes
+     * (engine-contract generation.rs:225-240) */
+    int32_t n_slopes;               /* 0, 1 or 2 */
+    int32_t slope_col[2];           /* design column each slope multiplies */
+    double slope_variance[2], slope_corr[2]; /* corr_with_intercept */
+    double slope_corr12;            /* slopes[1].corr_with[0] */
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
@@ -118,6 +120,10 @@ void orc_draw_residual(uint64_t base_seed, uint64_t sim_id, int dist, double df,
  * var_slope, corr, sigma²}. */
 int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, int n, int p, int slope_col, double* betas,
                       double* se, double* vc, int* converged, int* boundary, int* n_eval);
+/* ... with n_slopes (1 or 2) slopes, q = 1 + n_slopes.  vc = {variances[q] (intercept first), correlations (1,0) [(2,0) (2,1)],
+ * sigma²}. */
+int orc_fit_lmm_slopes(const double* xc, const double* yv, const int32_t* ids, int n, int p, int n_slopes, const int32_t* slope_cols,
+                       double* betas, double* se, double* vc, int* converged, int* boundary, int* n_eval);
 int orc_design_factor(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, double* l_colmajor);
 
 /* ---- transforms (distributions.rs:32-56, data_gen.rs:1106-1182, marginals/t3.rs) ---- */

@@ -62,7 +62,8 @@ class OrcSpec(C.Structure):
         ("n_frame_map", C.c_int32), ("frame_map", C.POINTER(C.c_int32)),
         ("n_var_params", C.c_int32),
         ("n_between", C.c_int32), ("between_cols", C.POINTER(C.c_int32)),
-        ("n_slopes", C.c_int32), ("slope_col", C.c_int32), ("slope_variance", C.c_double), ("slope_corr", C.c_double),
+        ("n_slopes", C.c_int32), ("slope_col", C.c_int32 * 2), ("slope_variance", C.c_double * 2), ("slope_corr", C.c_double * 2),
+        ("slope_corr12", C.c_double),
     ]
 
 
@@ -115,6 +116,8 @@ def lib():
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
     L.orc_design_factor.argtypes = [P(OrcSpec), u64, u64, P(dbl)]
     L.orc_fit_lmm_slope.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.orc_fit_lmm_slopes.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int),
+                                     P(C.c_int)]
     L.orc_fit_ols.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
                               P(C.c_int)]
     L.orc_fit_glm.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
@@ -245,15 +248,20 @@ class PackedSpec:
                 s.sizing_fixed_size, s.sizing_value = 1, int(sizing["FixedSize"]["cluster_size"])
             s.tau_squared = float(cl["tau_squared"])
             slopes = list(cl.get("slopes", []) or [])
-            if len(slopes) > 1 or (cl.get("extra_groupings") or []):
-                raise ValueError("oracle: one random slope on the primary grouping at most")
+            if len(slopes) > 2 or (cl.get("extra_groupings") or []):
+                raise ValueError("oracle: two random slopes on the primary grouping at most, no extra groupings")
             if slopes:
                 cols = list(spec.get("cluster_slope_design_cols", []) or [])
-                if len(cols) != 1:
+                if len(cols) != len(slopes):
                     raise ValueError("invalid spec: cluster_slope_design_cols must name one design column per slope")
-                s.n_slopes, s.slope_col = 1, int(cols[0])
-                s.slope_variance = float(slopes[0]["variance"])
-                s.slope_corr = float(slopes[0]["corr_with_intercept"])
+                s.n_slopes = len(slopes)
+                for a, sl in enumerate(slopes):
+                    s.slope_col[a] = int(cols[a])
+                    s.slope_variance[a] = float(sl["variance"])
+                    s.slope_corr[a] = float(sl["corr_with_intercept"])
+                if len(slopes) == 2:
+                    cw = list(slopes[1].get("corr_with", []) or [])
+                    s.slope_corr12 = float(cw[0]) if cw else 0.0
         sc = spec["scenario"]
         s.heterogeneity = float(sc.get("heterogeneity", 0.0))
         s.hsk_ratio = float(sc.get("heteroskedasticity_ratio", 1.0))
@@ -419,6 +427,25 @@ def fit_lmm(x, y, ids):
                              _ptr(se, C.c_double), C.byref(th), C.byref(s2), C.byref(conv), C.byref(bd)))
     return {"betas": b, "se": se, "theta": th.value, "sigma_sq": s2.value, "converged": bool(conv.value),
             "boundary": bd.value}
+
+
+def fit_lmm_slopes(x, y, ids, slope_cols):
+    """Random intercept + one or two random slopes (design columns `slope_cols`) by profiled REML on supplied data →
+    dict(betas, se, variances [intercept, slopes...], corr [(1,0), (2,0), (2,1)], sigma_sq, converged, boundary, n_eval)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    q = 1 + len(slope_cols)
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    idv = np.ascontiguousarray(ids, dtype=np.int32)
+    cols = np.ascontiguousarray(slope_cols, dtype=np.int32)
+    b, se, vc = np.zeros(p), np.zeros(p), np.zeros(q + q * (q - 1) // 2 + 1)
+    conv, bd, ne = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().orc_fit_lmm_slopes(_ptr(xc, C.c_double), _ptr(yv, C.c_double), _ptr(idv, C.c_int32), n, p, len(slope_cols),
+                                    _ptr(cols, C.c_int32), _ptr(b, C.c_double), _ptr(se, C.c_double), _ptr(vc, C.c_double),
+                                    C.byref(conv), C.byref(bd), C.byref(ne)))
+    return {"betas": b, "se": se, "variances": vc[:q].copy(), "corr": vc[q:-1].copy(), "sigma_sq": vc[-1],
+            "converged": bool(conv.value), "boundary": bd.value, "n_eval": ne.value}
 
 
 def fit_lmm_slope(x, y, ids, slope_col: int):

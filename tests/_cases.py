@@ -112,7 +112,9 @@ def case_spec(case: dict) -> dict:
         for sl in d.get("slopes", []) or []:  # lmm_slope_*: random slope on generation column `column` (ColumnId)
             col = int(_one(sl["column"]))
             s["cluster"]["slopes"].append({"column": col, "variance": float(_one(sl["variance"])),
-                                           "corr_with_intercept": float(_one(sl["corr_with_intercept"])), "corr_with": []})
+                                           "corr_with_intercept": float(_one(sl["corr_with_intercept"])),
+                                           "corr_with": [float(v) for v in (sl.get("corr_with") or [])] if isinstance(sl.get("corr_with"), list)
+                                           else ([float(sl["corr_with"])] if sl.get("corr_with") not in (None, [], {}) else [])})
             s["cluster_slope_design_cols"].append(1 + col)
     return s
 

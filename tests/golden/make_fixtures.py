@@ -168,7 +168,7 @@ def f64_hex(a):
 
 def main():
     cases = {}
-    families = ("ols_", "glm_", "probit_", "poisson_", "lme_", "lmm_slope_")
+    families = ("ols_", "glm_", "probit_", "poisson_", "lme_", "lmm_slope_", "lmm_multislope")
     for path in sorted(REF.glob("*.rds")):
         name = path.name[:-4]
         if name.endswith(".golden") or not name.startswith(families):

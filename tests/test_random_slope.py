@@ -1,6 +1,6 @@
 """Random slope on the primary grouping, q = 2 (reference: the slope draws `draw_cluster_effects_with_slopes`,
 data_gen.rs:1075-1145; `y += b0[c] + b1[c]·x_s`, data_gen.rs:955-1010; the general-q REML fit, lmm/general.rs; the reduced fit
-strips the slope, batch.rs:1357-1375).  The slice restated here: ONE slope, no extra groupings.
+strips the slope, batch.rs:1357-1375).  The slice restated here: ONE or TWO slopes (q <= 3), no extra groupings.
 
 * CPU: the oracle's generator reproduces the reference's saved `lmm_slope_*` sim-0 datasets bit for bit
   (tests/test_oracle_golden.py walks every fixture); here its 3-parameter profiled REML is held against lme4::lmer on those bytes
@@ -20,15 +20,16 @@ from oracle import orc
 
 SEED = 0x5EED5107E5EED510
 ALL = M.MODE_COUNTS | M.MODE_BYTES | M.MODE_CAPTURE
-SLOPE = sorted(n for n in CS.validation_cases() if n.startswith("lmm_slope_"))
+SLOPE = sorted(n for n in CS.validation_cases() if n.startswith(("lmm_slope_", "lmm_multislope")))
 
 
 def _rel(a, b):
     return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b)))
 
 
-def slope_spec(n_clusters=24, icc=0.2, var=0.1, corr=0.3, col=0, preset="optimistic", k=2):
-    """y ~ x1 + ... + xk + (1 + x_{col+1} | cluster)."""
+def slope_spec(n_clusters=24, icc=0.2, var=0.1, corr=0.3, col=0, preset="optimistic", k=2, second=None):
+    """y ~ x1 + ... + xk + (1 + x_{col+1} | cluster); second = (column, variance, corr with the intercept, corr with the first
+    slope) adds a second slope."""
     s = S.lmm_spec(n_clusters, icc, preset=preset) if k == 2 else None
     if s is None:
         s = S.base_spec(k)
@@ -41,12 +42,16 @@ def slope_spec(n_clusters=24, icc=0.2, var=0.1, corr=0.3, col=0, preset="optimis
         s["max_failed_fraction"] = 0.25
     s["cluster"]["slopes"] = [{"column": col, "variance": var, "corr_with_intercept": corr, "corr_with": []}]
     s["cluster_slope_design_cols"] = [1 + col]
+    if second is not None:
+        c2, v2, r02, r12 = second
+        s["cluster"]["slopes"].append({"column": c2, "variance": v2, "corr_with_intercept": r02, "corr_with": [r12]})
+        s["cluster_slope_design_cols"].append(1 + c2)
     return s
 
 
 # --------------------------------------------------------------------------------------------------------------- CPU
-def test_fixture_set_holds_the_two_single_slope_cases():
-    assert SLOPE == ["lmm_slope_a", "lmm_slope_b"]
+def test_fixture_set_holds_the_primary_slope_cases():
+    assert SLOPE == ["lmm_multislope", "lmm_slope_a", "lmm_slope_b"]
 
 
 @pytest.mark.parametrize("name", SLOPE)
@@ -57,14 +62,16 @@ def test_oracle_slope_reml_matches_lmer(name):
     g = CS.golden_arrays(case)
     ids = np.asarray(case["cluster_ids"], dtype=np.int32)
     ids = ids - ids.min()
-    fit = orc.fit_lmm_slope(x.astype(np.float64), y.astype(np.float64), ids, spec["cluster_slope_design_cols"][0])
+    cols = spec["cluster_slope_design_cols"]
+    fit = orc.fit_lmm_slopes(x.astype(np.float64), y.astype(np.float64), ids, cols)
     assert fit["converged"] and fit["boundary"] == 0
     assert _rel(fit["betas"], g["beta"]) < 1e-4                  # tolerances.R: estimate_rel_iter
     assert _rel(fit["betas"] / fit["se"], g["z"]) < 1e-4
-    assert _rel([fit["var_intercept"], fit["var_slope"]], g["vars"]) < 1e-3   # variance components
+    assert _rel(fit["variances"], g["vars"]) < 1e-3              # variance components (intercept, slopes)
     assert _rel(fit["sigma_sq"], g["sigma2"][0]) < 1e-3
-    assert abs(fit["corr"] - g["corr"][0]) < 2e-3
-    assert fit["n_eval"] < 600  # the simplex search has a hard budget (2 x 300); a fit that ran out is flagged unconverged
+    assert np.max(np.abs(fit["corr"] - g["corr"])) < 2e-3        # (1,0) [(2,0) (2,1)]
+    # the simplex search has a hard budget (300 evaluations per parameter); a fit that ran out is flagged unconverged
+    assert fit["n_eval"] < 300 * (len(cols) + 1) * (len(cols) + 2) // 2
 
 
 def test_oracle_slope_draws_have_the_specified_covariance():
@@ -112,10 +119,20 @@ def test_oracle_run_batch_with_a_slope_has_calibrated_size_and_sane_power():
     assert r["uncorrected"][conv, 0, 1].mean() > 0.9
 
 
-def test_more_than_one_slope_is_refused_without_a_gpu():
-    s = slope_spec(k=3)
-    s["cluster"]["slopes"].append({"column": 1, "variance": 0.1, "corr_with_intercept": 0.0, "corr_with": [0.0]})
-    s["cluster_slope_design_cols"] = [1, 2]
+def test_oracle_two_slopes_batch_converges_and_keeps_size():
+    s = slope_spec(30, 0.2, var=0.1, corr=0.3, second=(1, 0.08, 0.1, 0.2))
+    s["effect_sizes"] = [0.0, 0.0, 0.25]
+    r = orc.run_batch(s, [600], 600, SEED, n_threads=orc.host_threads())
+    conv = r["converged"][:, 0].astype(bool)
+    assert conv.mean() > 0.95
+    assert 0.02 < r["uncorrected"][conv, 0, 0].mean() < 0.1
+    assert r["uncorrected"][conv, 0, 1].mean() > 0.8
+
+
+def test_more_than_two_slopes_are_refused_without_a_gpu():
+    s = slope_spec(k=3, second=(1, 0.1, 0.0, 0.0))
+    s["cluster"]["slopes"].append({"column": 2, "variance": 0.1, "corr_with_intercept": 0.0, "corr_with": [0.0, 0.0]})
+    s["cluster_slope_design_cols"] = [1, 2, 3]
     with pytest.raises(M.Unsupported, match="random slope"):
         M.run_batch(s, [240], 4, SEED)
 
@@ -148,7 +165,7 @@ def test_gpu_generator_reproduces_the_reference_slope_datasets(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout", ["clusters_24", "size_10", "p5_col3", "doomer"])
+@pytest.mark.parametrize("layout", ["clusters_24", "size_10", "p5_col3", "doomer", "two_slopes", "two_slopes_p5_size"])
 def test_gpu_run_batch_with_a_slope_matches_the_oracle(layout):
     s = slope_spec(24, 0.2, var=0.1, corr=0.3)
     grid = [240, 480]
@@ -160,6 +177,13 @@ def test_gpu_run_batch_with_a_slope_matches_the_oracle(layout):
         grid = [200, 400, 600]
     elif layout == "doomer":
         s = slope_spec(30, 0.2, var=0.1, corr=0.3, preset="doomer")
+    elif layout == "two_slopes":
+        s = slope_spec(30, 0.2, var=0.1, corr=0.3, second=(1, 0.08, 0.1, 0.2))
+        grid = [300, 600]
+    elif layout == "two_slopes_p5_size":
+        s = slope_spec(20, 0.25, var=0.2, corr=-0.3, col=3, k=4, preset="realistic", second=(0, 0.15, 0.2, -0.4))
+        s["cluster"]["sizing"] = {"FixedSize": {"cluster_size": 12}}
+        grid = [240, 350]
     n = 256
     got = M.run_batch(s, grid, n, SEED, mode=ALL)
     want = orc.run_batch(s, grid, n, SEED, n_threads=orc.host_threads(), capture=True)
@@ -191,10 +215,12 @@ def test_gpu_slope_reml_on_reference_bytes_matches_lmer_and_the_oracle(name):
     assert got["converged"] and got["boundary_hit"] == 0
     assert _rel(got["betas"], g["beta"]) < 1e-4
     assert _rel(got["statistic"], np.abs(g["z"][1:])) < 1e-4
-    assert _rel([got["tau_sq_hat"], got["slope_var_hat"]], g["vars"]) < 1e-3
+    ns = len(spec["cluster_slope_design_cols"])
+    nc = 1 if ns == 1 else 3
+    assert _rel([got["tau_sq_hat"]] + got["slope_var_hat"][:ns], g["vars"]) < 1e-3
     assert _rel(got["sigma_sq_hat"], g["sigma2"][0]) < 1e-3
-    assert abs(got["slope_corr_hat"] - g["corr"][0]) < 2e-3
-    want = orc.fit_lmm_slope(x.astype(np.float64), y.astype(np.float64), ids.astype(np.int32), spec["cluster_slope_design_cols"][0])
+    assert np.max(np.abs(np.array(got["slope_corr_hat"][:nc]) - g["corr"])) < 2e-3
+    want = orc.fit_lmm_slopes(x.astype(np.float64), y.astype(np.float64), ids.astype(np.int32), spec["cluster_slope_design_cols"])
     assert np.array_equal(got["betas"], want["betas"]) and np.array_equal(got["se"], want["se"][1:])
-    assert got["sigma_sq_hat"] == want["sigma_sq"] and got["tau_sq_hat"] == want["var_intercept"]
-    assert got["slope_var_hat"] == want["var_slope"] and got["slope_corr_hat"] == want["corr"]
+    assert got["sigma_sq_hat"] == want["sigma_sq"] and got["tau_sq_hat"] == want["variances"][0]
+    assert got["slope_var_hat"][:ns] == list(want["variances"][1:]) and got["slope_corr_hat"][:nc] == list(want["corr"])

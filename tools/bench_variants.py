@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Developer tool: device-time fits/s of the headline shape (and the config-2 sweep) for every library variant under
 build_variants/ (tools/build_variant.sh) plus the in-tree library; every variant must produce the same counters.
-usage: bench_variants.py [n_sims]   — each variant runs in its own process (MCPOWER_B200_LIB)."""
+usage: [MCP_VARIANT_SET=ols|glm|c3|lmm] bench_variants.py [n_sims]   — each variant runs in its own process (MCPOWER_B200_LIB)."""
 import json
 import os
 import subprocess
@@ -17,8 +17,16 @@ from mcpower_b200 import spec as S
 n = int(sys.argv[1])
 seed = M.splitmix64(2137)
 out = {}
-for name, spec, grid, ns in (("headline", S.headline_spec(), [500], n), ("c2_sweep", S.sweep_spec(), list(range(20, 1001, 20)), n // 8),
-                            ("c1", S.add_interaction(S.base_spec(2), [1, 2], 0.2), [100], n)):
+import os
+SETS = {"ols": (("headline", S.headline_spec(), [500], n), ("c2_sweep", S.sweep_spec(), list(range(20, 1001, 20)), n // 8),
+                ("c1", S.add_interaction(S.base_spec(2), [1, 2], 0.2), [100], n)),
+        "glm": (("c4_logit", S.logit_spec(), [50, 100, 200, 500, 1000, 2000], n // 16),
+                ("logit_n300", S.logit_spec(), [300], n // 4)),
+        "c3": (("c3_doomer", dict(S.sweep_spec(), scenario=S.scenario("doomer"), crit_values={"alpha": 5e-7, "posthoc_alpha": None}),
+                list(range(20, 1001, 20)), n // 8),
+               ("c3_realistic", dict(S.sweep_spec(), scenario=S.scenario("realistic")), list(range(20, 1001, 20)), n // 8)),
+        "lmm": (("c5_lmm", S.lmm_spec(30, 0.2), [60, 120, 300, 600, 900], n // 4),)}
+for name, spec, grid, ns in SETS[os.environ.get("MCP_VARIANT_SET", "ols")]:
     M.run_batch(spec, grid, 4096, seed)
     best, cnt = None, None
     for _ in range(3):
