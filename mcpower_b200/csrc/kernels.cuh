@@ -442,7 +442,7 @@ struct SimCtx {
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
     uint32_t sim_local = 0;        // the study's index inside the launch (addresses per-wave scratch)
-    double slL[3][3];              // chol(D) of this study's random-effect covariance (random slopes; rows 1.. are used)
+    double sl[5];                  // rows 1, 2 of chol(D) of this study's random-effect covariance (random slopes): L10 L11 L20 L21 L22
 };
 
 // Residuals of the four rows of Philox block `blk` from the CLASS_RESID slots (data_gen.rs:412-484); slot0 = the slot-0
@@ -730,15 +730,56 @@ static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
 // cluster; z_0 is recovered from the f32 intercept effect; u_k = f32(sum_{j <= k} L[k][j] z_j) with L = chol(diag(tau) R diag(tau)).
 static __device__ __noinline__ void cluster_slope_effects(SimCtx& cx, uint32_t c, double u0, double (&uk)[2]) {
     const DevicePlan& pl = c_plan;
-    const int nsl = pl.n_slopes;
-    double z[3];
-    z[0] = cx.tau > 0.0 ? u0 / cx.tau : 0.0;
-    for (int j = 1; j <= nsl; j++) z[j] = re_draw(cx, ((uint32_t)pl.n_clusters + c * (uint32_t)nsl + (uint32_t)(j - 1)) * (uint32_t)pl.re_words);
-    for (int k = 1; k <= nsl; k++) {
-        double u = 0.0;
-        for (int j = 0; j <= k; j++) u += cx.slL[k][j] * z[j];
-        uk[k - 1] = (double)(float)u;
+    const uint32_t nsl = (uint32_t)pl.n_slopes, w1 = ((uint32_t)pl.n_clusters + c * nsl) * (uint32_t)pl.re_words;
+    const double z0 = cx.tau > 0.0 ? u0 / cx.tau : 0.0;
+    const double z1 = re_draw(cx, w1);
+    double u = 0.0;
+    u += cx.sl[0] * z0;
+    u += cx.sl[1] * z1;
+    uk[0] = (double)(float)u;
+    uk[1] = 0.0;
+    if (nsl == 2u) {
+        const double z2 = re_draw(cx, w1 + (uint32_t)pl.re_words);
+        u = 0.0;
+        u += cx.sl[2] * z0;
+        u += cx.sl[3] * z1;
+        u += cx.sl[4] * z2;
+        uk[1] = (double)(float)u;
     }
+}
+// chol_lower(D) (data_gen.rs:55-75), D = diag(tau) R diag(tau) with this study's tau0 (the ICC jitter makes it per study)
+static __device__ __noinline__ void slope_factor(SimCtx& cx) {
+    const DevicePlan& pl = c_plan;
+    const int q = 1 + pl.n_slopes;
+    double tv[3], R[3][3], D[3][3], L[3][3];
+    tv[0] = cx.tau;
+    for (int k = 0; k < pl.n_slopes; k++) tv[1 + k] = sqrt(pl.slope_variance[k] > 0.0 ? pl.slope_variance[k] : 0.0);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            R[i][j] = i == j ? 1.0 : 0.0;
+            L[i][j] = 0.0;
+        }
+    for (int k = 0; k < pl.n_slopes; k++) R[0][k + 1] = R[k + 1][0] = pl.slope_corr[k];
+    if (pl.n_slopes == 2) R[1][2] = R[2][1] = pl.slope_corr12;
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j < q; j++) D[i][j] = tv[i] * R[i][j] * tv[j];
+    for (int j = 0; j < q; j++) {
+        double diag = D[j][j];
+        for (int k = 0; k < j; k++) diag -= L[j][k] * L[j][k];
+        const double ljj = sqrt(diag > 0.0 ? diag : 0.0);
+        L[j][j] = ljj;
+        for (int i = j + 1; i < q; i++)
+            if (ljj > 0.0) {
+                double sacc = D[i][j];
+                for (int k = 0; k < j; k++) sacc -= L[i][k] * L[j][k];
+                L[i][j] = sacc / ljj;
+            }
+    }
+    cx.sl[0] = L[1][0];
+    cx.sl[1] = L[1][1];
+    cx.sl[2] = L[2][0];
+    cx.sl[3] = L[2][1];
+    cx.sl[4] = L[2][2];
 }
 
 // Cluster-level predictors (data_gen.rs:605-640): on every non-representative row the marked columns take the value of the
@@ -1010,33 +1051,7 @@ __device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t 
     cx.tau = !pl.has_cluster ? 0.0 : (sd ? sd->tau : sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0));
     cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words * (uint32_t)(1 + pl.n_slopes) : 0u;
     cx.sim_local = sim_local;
-    if (pl.n_slopes > 0) {  // chol_lower(D) (data_gen.rs:55-75), D = diag(tau) R diag(tau) with this study's tau0
-        const int q = 1 + pl.n_slopes;
-        double tv[3], R[3][3], D[3][3];
-        tv[0] = cx.tau;
-        for (int k = 0; k < pl.n_slopes; k++) tv[1 + k] = sqrt(pl.slope_variance[k] > 0.0 ? pl.slope_variance[k] : 0.0);
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                R[i][j] = i == j ? 1.0 : 0.0;
-                cx.slL[i][j] = 0.0;
-            }
-        for (int k = 0; k < pl.n_slopes; k++) R[0][k + 1] = R[k + 1][0] = pl.slope_corr[k];
-        if (pl.n_slopes == 2) R[1][2] = R[2][1] = pl.slope_corr12;
-        for (int i = 0; i < q; i++)
-            for (int j = 0; j < q; j++) D[i][j] = tv[i] * R[i][j] * tv[j];
-        for (int j = 0; j < q; j++) {
-            double diag = D[j][j];
-            for (int k = 0; k < j; k++) diag -= cx.slL[j][k] * cx.slL[j][k];
-            const double ljj = sqrt(diag > 0.0 ? diag : 0.0);
-            cx.slL[j][j] = ljj;
-            for (int i = j + 1; i < q; i++)
-                if (ljj > 0.0) {
-                    double sacc = D[i][j];
-                    for (int k = 0; k < j; k++) sacc -= cx.slL[i][k] * cx.slL[j][k];
-                    cx.slL[i][j] = sacc / ljj;
-                }
-        }
-    }
+    if (pl.n_slopes > 0) slope_factor(cx);
 }
 
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.

@@ -26,9 +26,6 @@ namespace mcp {
 #define MCP_GLM_TOL 1e-8
 #define MCP_GLM_WCLAMP 1e-10
 #define MCP_GLM_BETA_CAP 30.0
-#ifndef MCP_GLM_ROWS
-#define MCP_GLM_ROWS 2  // rows per IRLS loop iteration (their exp / division / log chains interleave; sums stay in row order)
-#endif
 
 // family 0 logit, 1 probit, 2 poisson(log)
 __device__ __forceinline__ void glm_row(int family, double eta, double y, double& w, double& z, double& dev) {
@@ -125,94 +122,101 @@ __device__ __forceinline__ void glm_irls_reg(const float* __restrict__ plane, si
 #pragma unroll
         for (int i = 0; i < PT; i++) b[i] = 0.0;
         dev = 0.0;
-        // MCP_GLM_ROWS rows per iteration.  Every accumulator still sees the rows in order (row i, then row i + 1), so the sums are
-        // bit-identical to a one-row loop; the two rows' exp / division / log chains are independent and interleave.  Rows
+        // Two rows per iteration (three and four were measured slower, profiles/r02_glm_kernel.md).  Every accumulator still sees
+        // the rows in order (row i, then row i + 1), so the sums are bit-identical to a one-row loop; the two rows' exp / division / log chains are independent and interleave.  Rows
         // i + 2 / i + 3 are fetched (coalesced, L2 / HBM) while rows i / i + 1 are processed.  The family is uniform over the
         // launch: one of the three instantiations runs.
         auto pass = [&](auto fam_tag) {
             constexpr int FAM = decltype(fam_tag)::value;
-            constexpr int R = MCP_GLM_ROWS;  // rows per loop iteration
-            float nx[R][PT];
+            float nx0[PT], nx1[PT];
 #pragma unroll
-            for (int r = 0; r < R; r++)
+            for (int j = 0; j < PT; j++) {
+                nx0[j] = n > 0 ? plane[(size_t)j * stride] : 0.0f;
+                nx1[j] = n > 1 ? plane[(size_t)(PT + j) * stride] : 0.0f;
+            }
+            int i = 0;
+            for (; i + 1 < n; i += 2) {
+                float c0[PT], c1[PT];
 #pragma unroll
-                for (int j = 0; j < PT; j++) nx[r][j] = r < n ? plane[(size_t)(r * PT + j) * stride] : 0.0f;
-            auto one_row = [&](const float (&c)[PT]) {
-                double x[PT];
-                x[0] = 1.0;
+                for (int j = 0; j < PT; j++) {
+                    c0[j] = nx0[j];
+                    c1[j] = nx1[j];
+                }
+                if (i + 2 < n) {
+                    const float* rowp = plane + (size_t)(i + 2) * PT * stride;
 #pragma unroll
-                for (int j = 1; j < PT; j++) x[j] = (double)c[j - 1];
-                const double y = (double)c[PT - 1];
-                double eta = 0.0;
+                    for (int j = 0; j < PT; j++) nx0[j] = rowp[(size_t)j * stride];
+                }
+                if (i + 3 < n) {
+                    const float* rowp = plane + (size_t)(i + 3) * PT * stride;
 #pragma unroll
-                for (int j = 0; j < PT; j++) eta = fma(x[j], beta[j], eta);
-                double w, z, d;
-                glm_row_sel<FAM>(eta, y, w, z, d);
-                dev += d;
+                    for (int j = 0; j < PT; j++) nx1[j] = rowp[(size_t)j * stride];
+                }
+                double x0[PT], x1[PT];
+                x0[0] = 1.0;
+                x1[0] = 1.0;
+#pragma unroll
+                for (int j = 1; j < PT; j++) {
+                    x0[j] = (double)c0[j - 1];
+                    x1[j] = (double)c1[j - 1];
+                }
+                const double y0 = (double)c0[PT - 1], y1 = (double)c1[PT - 1];
+                double eta0 = 0.0, eta1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < PT; j++) {
+                    eta0 = fma(x0[j], beta[j], eta0);
+                    eta1 = fma(x1[j], beta[j], eta1);
+                }
+                double w0, z0, d0, w1, z1, d1;
+                glm_row_sel<FAM>(eta0, y0, w0, z0, d0);
+                glm_row_sel<FAM>(eta1, y1, w1, z1, d1);
+                dev += d0;
+                dev += d1;
                 if (it == 0) {
-                    s0 += y;
-                    if (FAM == 2 && y > 1.0) s1 += y * own_log(y);
+                    s0 += y0;
+                    if (FAM == 2 && y0 > 1.0) s1 += y0 * own_log(y0);
+                    s0 += y1;
+                    if (FAM == 2 && y1 > 1.0) s1 += y1 * own_log(y1);
                 }
 #pragma unroll
                 for (int a = 0; a < PT; a++) {
-                    const double wa = w * x[a];
+                    const double wa = w0 * x0[a];
 #pragma unroll
-                    for (int cc = 0; cc <= a; cc++) A[tri(a, cc)] = fma(wa, x[cc], A[tri(a, cc)]);
-                    b[a] = fma(wa, z, b[a]);
-                }
-            };
-            int i = 0;
-            for (; i + R <= n; i += R) {
-                float c[R][PT];
-#pragma unroll
-                for (int r = 0; r < R; r++)
-#pragma unroll
-                    for (int j = 0; j < PT; j++) c[r][j] = nx[r][j];
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (i + R + r < n) {
-                        const float* rowp = plane + (size_t)(i + R + r) * PT * stride;
-#pragma unroll
-                        for (int j = 0; j < PT; j++) nx[r][j] = rowp[(size_t)j * stride];
-                    }
-                double x[R][PT], y[R], eta[R], w[R], z[R], d[R];
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    x[r][0] = 1.0;
-#pragma unroll
-                    for (int j = 1; j < PT; j++) x[r][j] = (double)c[r][j - 1];
-                    y[r] = (double)c[r][PT - 1];
-                    eta[r] = 0.0;
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x0[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z0, b[a]);
                 }
 #pragma unroll
-                for (int j = 0; j < PT; j++)
+                for (int a = 0; a < PT; a++) {
+                    const double wa = w1 * x1[a];
 #pragma unroll
-                    for (int r = 0; r < R; r++) eta[r] = fma(x[r][j], beta[j], eta[r]);
-#pragma unroll
-                for (int r = 0; r < R; r++) glm_row_sel<FAM>(eta[r], y[r], w[r], z[r], d[r]);
-#pragma unroll
-                for (int r = 0; r < R; r++) dev += d[r];
-                if (it == 0) {
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        s0 += y[r];
-                        if (FAM == 2 && y[r] > 1.0) s1 += y[r] * own_log(y[r]);
-                    }
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x1[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z1, b[a]);
                 }
-#pragma unroll
-                for (int r = 0; r < R; r++)
-#pragma unroll
-                    for (int a = 0; a < PT; a++) {
-                        const double wa = w[r] * x[r][a];
-#pragma unroll
-                        for (int cc = 0; cc <= a; cc++) A[tri(a, cc)] = fma(wa, x[r][cc], A[tri(a, cc)]);
-                        b[a] = fma(wa, z[r], b[a]);
-                    }
             }
-            // the last n mod R rows, one at a time (they sit in nx[0 .. n - i))
+            if (i < n) {  // odd row count: the last row alone (it sits in nx0)
+                double x0[PT];
+                x0[0] = 1.0;
 #pragma unroll
-            for (int r = 0; r < R - 1; r++)
-                if (i + r < n) one_row(nx[r]);
+                for (int j = 1; j < PT; j++) x0[j] = (double)nx0[j - 1];
+                const double y0 = (double)nx0[PT - 1];
+                double eta0 = 0.0;
+#pragma unroll
+                for (int j = 0; j < PT; j++) eta0 = fma(x0[j], beta[j], eta0);
+                double w0, z0, d0;
+                glm_row_sel<FAM>(eta0, y0, w0, z0, d0);
+                dev += d0;
+                if (it == 0) {
+                    s0 += y0;
+                    if (FAM == 2 && y0 > 1.0) s1 += y0 * own_log(y0);
+                }
+#pragma unroll
+                for (int a = 0; a < PT; a++) {
+                    const double wa = w0 * x0[a];
+#pragma unroll
+                    for (int c = 0; c <= a; c++) A[tri(a, c)] = fma(wa, x0[c], A[tri(a, c)]);
+                    b[a] = fma(wa, z0, b[a]);
+                }
+            }
         };
         if (family == 0) pass(std::integral_constant<int, 0>{});
         else if (family == 1) pass(std::integral_constant<int, 1>{});

@@ -342,60 +342,80 @@ struct SlopeData {
 
 // theta = the lower triangle of Lambda row by row: (l00, l10, l11[, l20, l21, l22]); the diagonal enters as |.|.  Same operations
 // in the same order as the oracle's slope_dev.
-template <int PT>
-static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d, const double* th) {
+// (Q is a template parameter so that the q x q blocks live in registers: the runtime-q form ran 2.7x slower.)
+template <int PT, int Q>
+static __device__ __noinline__ double slope_dev_q(LmmCtx<PT>& c, SlopeData<PT>& d, const double* th) {
     const DevicePlan& pl = c_plan;
     constexpr int NT = PT * (PT + 1) / 2;
-    const int q = d.q;
-    double Lm[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+    constexpr int q = Q;
+    double Lm[Q][Q];
+#pragma unroll
     for (int i = 0, t = 0; i < q; i++)
+#pragma unroll
         for (int j = 0; j <= i; j++, t++) Lm[i][j] = i == j ? fabs(th[t]) : th[t];
     for (int e = 0; e < NT; e++) c.A[e] = c.xtx[e];
     for (int j = 0; j < PT; j++) c.b[j] = c.xty[j];
     double cc = c.yty, ldv = 0.0;
-    double r[MCP_SLOPE_MAXQ][PT + 1];
+    double r[Q][PT + 1];
     for (int k = 0; k < d.n_clusters; k++) {
         const uint32_t cnk = lmm_cluster_rows(pl, k, d.n);
         if (cnk == 0) continue;
-        const double* sk[MCP_SLOPE_MAXQ];
+        const double* sk[Q];
+#pragma unroll
         for (int a = 0; a < q; a++) sk[a] = d.cs + (size_t)(k * q + a) * (PT + 1) * d.stride;
-        double S[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], T[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], M[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], C[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+        double S[Q][Q], T[Q][Q], M[Q][Q], C[Q][Q];
         S[0][0] = (double)cnk;
+#pragma unroll
         for (int a = 1; a < q; a++) {
             S[a][0] = S[0][a] = sk[0][(size_t)d.slope_col[a] * d.stride];
+#pragma unroll
             for (int b = 1; b <= a; b++) S[a][b] = S[b][a] = sk[b][(size_t)d.slope_col[a] * d.stride];
         }
+#pragma unroll
         for (int i = 0; i < q; i++)
+#pragma unroll
             for (int j = 0; j < q; j++) {
                 double acc = 0.0;
+#pragma unroll
                 for (int m = j; m < q; m++) acc += Lm[m][j] * S[i][m];
                 T[i][j] = acc;
             }
+#pragma unroll
         for (int i = 0; i < q; i++)
+#pragma unroll
             for (int j = 0; j <= i; j++) {
                 double acc = 0.0;
+#pragma unroll
                 for (int m = j; m < q; m++) acc += T[m][i] * Lm[m][j];
                 M[i][j] = i == j ? acc + 1.0 : acc;
             }
+#pragma unroll
         for (int j = 0; j < q; j++) {
             double dg = M[j][j];
+#pragma unroll
             for (int m = 0; m < j; m++) dg -= C[j][m] * C[j][m];
             C[j][j] = sqrt(dg);
+#pragma unroll
             for (int i = j + 1; i < q; i++) {
                 double acc = M[i][j];
+#pragma unroll
                 for (int m = 0; m < j; m++) acc -= C[i][m] * C[j][m];
                 C[i][j] = acc / C[j][j];
             }
         }
         {
             double l = own_log(C[0][0]);
+#pragma unroll
             for (int j = 1; j < q; j++) l += own_log(C[j][j]);
             ldv += l;
         }
         for (int j = 0; j <= PT; j++) {
+#pragma unroll
             for (int i = 0; i < q; i++) {
                 double t = 0.0;
+#pragma unroll
                 for (int m = i; m < q; m++) t += Lm[m][i] * sk[m][(size_t)j * d.stride];
+#pragma unroll
                 for (int m = 0; m < i; m++) t -= C[i][m] * r[m][j];
                 r[i][j] = t / C[i][i];
             }
@@ -403,11 +423,14 @@ static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d,
         int t = 0;
         for (int a = 0; a < PT; a++) {
             for (int bb = 0; bb <= a; bb++) {
+#pragma unroll
                 for (int i = 0; i < q; i++) c.A[t] = fma(-r[i][a], r[i][bb], c.A[t]);
                 t++;
             }
+#pragma unroll
             for (int i = 0; i < q; i++) c.b[a] = fma(-r[i][a], r[i][PT], c.b[a]);
         }
+#pragma unroll
         for (int i = 0; i < q; i++) cc = fma(-r[i][PT], r[i][PT], cc);
     }
     d.n_eval++;
@@ -417,6 +440,11 @@ static __device__ __noinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d,
     double lda = 0.0;
     for (int j = 0; j < PT; j++) lda += own_log(c.ms.L[tri(j, j)]);
     return 2.0 * ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
+}
+
+template <int PT>
+static __device__ __forceinline__ double slope_dev(LmmCtx<PT>& c, SlopeData<PT>& d, const double* th) {
+    return d.q == 2 ? slope_dev_q<PT, 2>(c, d, th) : slope_dev_q<PT, 3>(c, d, th);
 }
 
 // Nelder–Mead in D = q (q + 1) / 2 dimensions; same comparisons in the same order as the oracle's slope_nm.
