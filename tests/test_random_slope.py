@@ -224,3 +224,38 @@ def test_gpu_slope_reml_on_reference_bytes_matches_lmer_and_the_oracle(name):
     assert np.array_equal(got["betas"], want["betas"]) and np.array_equal(got["se"], want["se"][1:])
     assert got["sigma_sq_hat"] == want["sigma_sq"] and got["tau_sq_hat"] == want["variances"][0]
     assert got["slope_var_hat"][:ns] == list(want["variances"][1:]) and got["slope_corr_hat"][:nc] == list(want["corr"])
+
+
+def _slope_contract(n_slopes):
+    import test_contract_lowering as TC
+    slopes = [{"column": 0, "variance": 0.1, "corr_with_intercept": 0.3, "corr_with": []}]
+    if n_slopes == 2:
+        slopes.append({"column": 1, "variance": 0.08, "corr_with_intercept": 0.1, "corr_with": [0.2]})
+    return TC.contract([TC.normal(), TC.normal()], [TC.CONST, TC.direct(0), TC.direct(1)], [0.0, 0.3, 0.2],
+                       [TC.marginal(1), TC.marginal(2)], estimator="mle",
+                       cluster={"sizing": {"FixedClusters": {"n_clusters": 30}}, "tau_squared": 0.25, "slopes": slopes, "extra_groupings": []})
+
+
+@pytest.mark.parametrize("n_slopes", [1, 2])
+def test_contract_with_primary_slopes_lowers_to_design_columns(n_slopes):  # contract_adapter.rs:132-140, 2267-2340
+    import msgpack
+    low = M.lower_contracts(msgpack.packb([_slope_contract(n_slopes)], use_bin_type=True))[0]
+    assert low["spec"]["cluster_slope_design_cols"] == [1, 2][:n_slopes]
+    assert len(low["spec"]["cluster"]["slopes"]) == n_slopes
+    r = orc.run_batch(low["spec"], [300], 16, 5)
+    assert r["converged"].shape == (16, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_slopes", [1, 2])
+def test_gpu_contract_with_primary_slopes_runs_end_to_end(n_slopes):
+    """The hosts' payload (msgpack contract) for `y ~ x1 + x2 + (1 + x1 [+ x2] | g)` through the contract entry point: it used to
+    come back UNSUPPORTED; the counts are the oracle's."""
+    import msgpack
+    blob = msgpack.packb([_slope_contract(n_slopes)], use_bin_type=True)
+    low = M.lower_contracts(blob)[0]
+    got = M.find_power_contracts(blob, 600, 512, 2137)
+    pr = got["scenarios"][0][1]
+    want = orc.run_batch(low["spec"], [600], 512, M.splitmix64(2137), n_threads=orc.host_threads())
+    assert pr["success_counts_uncorrected"] == [int(v) for v in want["uncorrected"].sum(axis=0)[0]]
+    assert pr["convergence_count"] == int(want["converged"].sum())
