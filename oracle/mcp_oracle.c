@@ -1077,6 +1077,8 @@ typedef struct {
     double tau_squared_design;
     float* cluster_u;
     float* cluster_u1; /* random-slope effects */
+    float* extra_u[2]; /* extra-grouping random intercepts */
+    double extra_tau_sq_design[2];
     int32_t* cluster_ids;
     int n_cluster_cap;
     uint32_t* alloc_counts;
@@ -1119,6 +1121,7 @@ static Ws* ws_new(const OrcSpec* s, int max_n) {
         w->n_cluster_cap = nc;
         w->cluster_u = (float*)calloc((size_t)nc, sizeof(float));
         w->cluster_u1 = (float*)calloc((size_t)nc * 2, sizeof(float));
+        for (int g = 0; g < s->n_extra; g++) w->extra_u[g] = (float*)calloc((size_t)orc_extra_levels_at(s, g, max_n) + 1, sizeof(float));
         w->cluster_ids = (int32_t*)calloc((size_t)max_n, sizeof(int32_t));
         for (int i = 0; i < max_n; i++) /* generation.rs cluster_of_row */
             w->cluster_ids[i] = s->sizing_fixed_size ? i / (s->sizing_value > 0 ? s->sizing_value : 1)
@@ -1131,13 +1134,32 @@ static void ws_free(Ws* w) {
     free(w->x); free(w->y); free(w->z_planar); free(w->residuals); free(w->resid_g); free(w->words);
     free(w->mix_acc); free(w->eta_acc); free(w->l_design); free(w->var_types_design); free(w->alloc_counts);
     free(w->prefix_counts); free(w->excl_flags); free(w->beta_eff); free(w->xtx); free(w->xty);
-    free(w->cluster_u); free(w->cluster_u1); free(w->cluster_ids); free(w->red_memo);
+    free(w->cluster_u); free(w->cluster_u1); free(w->extra_u[0]); free(w->extra_u[1]); free(w->cluster_ids); free(w->red_memo);
     free(w);
 }
 
 static int is_optimistic(const OrcSpec* s) { /* spec.rs:229-236 */
     return s->heterogeneity == 0.0 && s->hsk_ratio == 1.0 && s->corr_noise_sd == 0.0 && s->dist_change_prob == 0.0 &&
            s->resid_change_prob == 0.0 && !s->has_lme;
+}
+
+/* generation.rs:370-430: one lexicographic stride chain, primary fastest, extras in declaration order */
+int orc_extra_level_of_row(const OrcSpec* s, int g, int i) {
+    const int bl = s->extra_count[g] > 0 ? s->extra_count[g] : 1;
+    const int sv = s->sizing_value > 0 ? s->sizing_value : 1;
+    if (!s->sizing_fixed_size) {
+        long stride = sv;
+        for (int h = 0; h < g; h++) stride *= s->extra_count[h] > 0 ? s->extra_count[h] : 1;
+        const int within = (int)(((long)i / stride) % bl);
+        return s->extra_nested[g] ? (i % sv) * bl + within : within;
+    }
+    return (i / sv) * bl + (i % sv) % bl; /* FixedSize: nested only (validate() rejects crossed) */
+}
+int orc_extra_levels_at(const OrcSpec* s, int g, int n) { /* generation.rs:301-320 */
+    const int bl = s->extra_count[g] > 0 ? s->extra_count[g] : 1;
+    if (!s->extra_nested[g]) return bl;
+    const int sv = s->sizing_value > 0 ? s->sizing_value : 1;
+    return (s->sizing_fixed_size ? (n + sv - 1) / sv : sv) * bl;
 }
 
 /* data_gen.rs:990-1093 + scenarios.rs:67-186 */
@@ -1150,6 +1172,7 @@ static int populate_design(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id
         w->residual_dist_design = s->residual_dist;
         w->residual_df_design = s->residual_df;
         w->tau_squared_design = s->has_cluster ? s->tau_squared : 0.0;
+        for (int g = 0; g < s->n_extra; g++) w->extra_tau_sq_design[g] = s->extra_tau_squared[g];
         return ORC_OK;
     }
     SeqRng sr;
@@ -1202,6 +1225,14 @@ static int populate_design(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id
         w->tau_squared_design = t > 0.0 ? t : 0.0;
     } else {
         w->tau_squared_design = base_tau;
+    }
+    for (int g = 0; g < s->n_extra; g++) { /* one independent jitter draw per extra grouping, declaration order (data_gen.rs:1077-1091) */
+        if (s->has_lme && s->icc_noise_sd > 0.0) {
+            double t = s->extra_tau_squared[g] + (double)seq_normal(&sr) * s->icc_noise_sd;
+            w->extra_tau_sq_design[g] = t > 0.0 ? t : 0.0;
+        } else {
+            w->extra_tau_sq_design[g] = s->extra_tau_squared[g];
+        }
     }
     return ORC_OK;
 }
@@ -1307,6 +1338,12 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
                     w->cluster_u1[(size_t)c * nsl + (k - 1)] = (float)uk;
                 }
             }
+        }
+        /* 2b. extra-grouping intercepts, one block per grouping behind the primary's draws (data_gen.rs:214-236) */
+        for (int g = 0; g < s->n_extra; g++) {
+            const double tau_g = sqrt(w->extra_tau_sq_design[g] > 0.0 ? w->extra_tau_sq_design[g] : 0.0);
+            const int nl = orc_extra_levels_at(s, g, max_n);
+            for (int c = 0; c < nl; c++) w->extra_u[g][c] = (float)(draw_residual(&rng, re_dist, re_df) * tau_g);
         }
     }
     for (int i = 0; i < max_n; i++) w->x[i] = 1.0f;
@@ -1499,7 +1536,9 @@ static int gen_sim(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, Ws* w)
             w->mix_acc[i] = gamma * z;
         }
         double u_re = s->has_cluster ? (double)w->cluster_u[w->cluster_ids[i]] : 0.0;
-        if (s->has_cluster) /* data_gen.rs:836-842 */
+        if (s->has_cluster) /* extras first (data_gen.rs:818-835), then the primary slopes (836-842) */
+            for (int g = 0; g < s->n_extra; g++) u_re += (double)w->extra_u[g][orc_extra_level_of_row(s, g, i)];
+        if (s->has_cluster)
             for (int k = 0; k < s->n_slopes; k++)
                 u_re += (double)w->cluster_u1[(size_t)w->cluster_ids[i] * s->n_slopes + k] * (double)w->x[(size_t)s->slope_col[k] * max_n + i];
         if (s->outcome_kind == ORC_OUT_CONTINUOUS && !apply_hsk) w->y[i] = (float)(lp + (double)w->residuals[i] + u_re);
@@ -1564,6 +1603,21 @@ static int validate_spec(const OrcSpec* s, const uint32_t* ss, int n_ss) { /* ba
             if (s->slope_col[q] < 1 || s->slope_col[q] >= 1 + s->n_non_factor + s->n_factor_dummies + s->n_interactions)
                 return fail(ORC_ERR_INVALID_SPEC, "cluster_slope_design_cols entry out of range");
         if (!(s->tau_squared > 0.0)) return fail(ORC_ERR_INVALID_SPEC, "random slopes need tau_squared > 0"); /* validate.rs invariant */
+    }
+    if (s->n_extra > 0) { /* validate.rs:720-745 */
+        if (!s->has_cluster || s->n_extra > 2) return fail(ORC_ERR_INVALID_SPEC, "extra groupings need a cluster (two at most)");
+        int n_nested = 0;
+        for (int g = 0; g < s->n_extra; g++) {
+            if (s->extra_count[g] < 1) return fail(ORC_ERR_INVALID_SPEC, "extra grouping needs at least one level");
+            if (!(s->extra_tau_squared[g] >= 0.0)) return fail(ORC_ERR_INVALID_SPEC, "extra grouping tau_squared must be >= 0");
+            if (!s->extra_nested[g] && s->sizing_fixed_size) return fail(ORC_ERR_INVALID_SPEC, "GroupingRelation::Crossed requires ClusterSizing::FixedClusters");
+            if (s->extra_nested[g]) {
+                n_nested++;
+                if (s->sizing_fixed_size && s->sizing_value % s->extra_count[g] != 0)
+                    return fail(ORC_ERR_INVALID_SPEC, "NestedWithin requires cluster_size % n_per_parent == 0");
+            }
+        }
+        if (n_nested > 1) return fail(ORC_ERR_INVALID_SPEC, "at most one NestedWithin grouping is supported");
     }
     for (int b = 0; b < s->n_between; b++) /* the reference indexes x_full unchecked (a malformed spec panics); the backends reject it */
         if (s->between_cols[b] < 1 || s->between_cols[b] >= 1 + s->n_non_factor + s->n_factor_dummies)
@@ -2017,7 +2071,7 @@ static void lmm_fit(LmmCtx* c, const double* csum, const uint32_t* cn, int n_clu
  * Minimised by a deterministic Nelder-Mead (one restart) with the diagonal of Lambda clamped at 0; restated op for op in the
  * CUDA kernel.  Pinned to lme4's REML fits of the reference's lmm_slope datasets (tolerances.R:29-31, 38-49). */
 #define SLOPE_MAXQ 3
-#define SLOPE_MAXD 6 /* q (q + 1) / 2 */
+#define SLOPE_MAXD 8 /* q (q + 1) / 2 for the primary grouping + one scale per extra grouping */
 #define SLOPE_NM_EVAL_PER_DIM 300
 #define SLOPE_THETA_MAX 30.0
 typedef struct {
@@ -2107,8 +2161,14 @@ static double slope_dev(LmmCtx* c, const SlopeData* d, const double* th) {
 /* Nelder-Mead in D = q (q + 1) / 2 dimensions (reflection 1, expansion 2, contraction 1/2, shrink 1/2); x0 + step initial
  * simplex; stops when the simplex is flat (1e-11 relative in f) and small (1e-7 in every coordinate) or after max_eval
  * evaluations.  Ties and orderings are resolved by strict comparisons in a fixed order, so the CUDA twin takes the same path. */
+typedef double (*NmEval)(LmmCtx*, void*, const double*);
+static double nm_minimise(LmmCtx* c, void* d, NmEval ev, int* n_eval, int D, double* x, double step, int max_eval);
+static double slope_eval(LmmCtx* c, void* d, const double* th) { return slope_dev(c, (const SlopeData*)d, th); }
 static double slope_nm(LmmCtx* c, SlopeData* d, double* x, double step, int max_eval) {
-    const int D = d->q * (d->q + 1) / 2, V = D + 1;
+    return nm_minimise(c, d, slope_eval, &d->n_eval, d->q * (d->q + 1) / 2, x, step, max_eval);
+}
+static double nm_minimise(LmmCtx* c, void* d, NmEval slope_dev, int* n_eval_p, int D, double* x, double step, int max_eval) {
+    const int V = D + 1;
     double sx[SLOPE_MAXD + 1][SLOPE_MAXD], sf[SLOPE_MAXD + 1];
     for (int i = 0; i < V; i++) {
         for (int j = 0; j < D; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
@@ -2130,7 +2190,7 @@ static double slope_nm(LmmCtx* c, SlopeData* d, double* x, double step, int max_
                 double dd = fabs(sx[i][j] - sx[lo][j]);
                 if (dd > size) size = dd;
             }
-        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d->n_eval >= max_eval) {
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || *n_eval_p >= max_eval) {
             for (int j = 0; j < D; j++) x[j] = sx[lo][j];
             return sf[lo];
         }
@@ -2196,6 +2256,150 @@ static void lmm_slope_fit(LmmCtx* c, SlopeData* d, SlopeOut* out) {
     out->n_eval = d->n_eval;
     for (int j = 0; j < D; j++) out->theta[j] = x[j];
     out->sigma_sq = c->fit.sigma_sq;
+}
+
+/* ---- general structure: primary grouping (intercept + up to two slopes) plus up to two intercept-only extra groupings (crossed /
+ * nested).  The reference fits these through glmm::fit_on + BOBYQA (batch.rs:1214-1561, mixed_workspace.rs; crates not in the tree).
+ * Restated in lme4's penalised-least-squares form on dense matrices: random-effect columns ordered [primary (level, component) |
+ * extra 1 levels | extra 2 levels], Z'Z and Z'[X | y] accumulated once from the rows (one fma per term, rows in order), then per
+ * evaluation  M = Lambda' Z'Z Lambda + I,  L = chol(M) (left-looking, one fma chain per entry),  R = L^-1 Lambda' Z'[X | y],
+ *   A = X'X - R_x' R_x,  b = X'y - R_x' R_y,  c = y'y - |R_y|²,  dev = 2 sum log L_jj + log det A + (n - p) log(rss / (n - p)),
+ * theta = (lower triangle of the primary's Lambda row by row, one scale per extra grouping), minimised by the same Nelder-Mead.
+ * Structural zeros contribute exact zeros to every chain, so an implementation that skips them (the CUDA kernel keeps the primary
+ * block diagonal and only the extras dense) produces the same bits. */
+typedef struct {
+    int Q, q0, K, n_extra, E[2], off[2]; /* off[g] = first column of extra grouping g */
+    const double* ZtZ;  /* Q x Q, lower triangle used, row-major [i * Q + j] */
+    const double* ZtXy; /* Q x (p + 1) */
+    double *T, *M, *L, *R; /* work: Q x Q (T, M, L), Q x (p + 1) (R) */
+    int n_eval;
+} GenData;
+
+static double gen_dev(LmmCtx* c, GenData* d, const double* th) {
+    const int p = c->p, Q = d->Q, q0 = d->q0, nprim = d->K * q0;
+    const size_t nt = (size_t)p * (p + 1) / 2;
+    double Lm[SLOPE_MAXQ][SLOPE_MAXQ], te[2];
+    int t = 0;
+    for (int i = 0; i < q0; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = i == j ? fabs(th[t]) : th[t];
+    for (int g = 0; g < d->n_extra; g++) te[g] = fabs(th[t++]);
+    double *T = d->T, *M = d->M, *L = d->L, *R = d->R;
+    /* T = Z'Z Lambda (column j), M = Lambda' T + I (lower part) */
+    for (int r = 0; r < Q; r++)
+        for (int j = 0; j <= r; j++) {
+            double acc = 0.0;
+            if (j < nprim) {
+                const int k = j / q0, aj = j % q0;
+                for (int bb = aj; bb < q0; bb++) {
+                    const int col = k * q0 + bb;
+                    acc += Lm[bb][aj] * (r >= col ? d->ZtZ[(size_t)r * Q + col] : d->ZtZ[(size_t)col * Q + r]);
+                }
+            } else {
+                acc += te[j >= d->off[1] && d->n_extra > 1 ? 1 : 0] * d->ZtZ[(size_t)r * Q + j];
+            }
+            T[(size_t)r * Q + j] = acc;
+        }
+    for (int i = 0; i < Q; i++)
+        for (int j = 0; j <= i; j++) {
+            double acc = 0.0;
+            if (i < nprim) {
+                const int k = i / q0, ai = i % q0;
+                for (int aa = ai; aa < q0; aa++) acc += Lm[aa][ai] * T[(size_t)(k * q0 + aa) * Q + j];
+            } else {
+                acc += te[i >= d->off[1] && d->n_extra > 1 ? 1 : 0] * T[(size_t)i * Q + j];
+            }
+            M[(size_t)i * Q + j] = i == j ? acc + 1.0 : acc;
+        }
+    double ldv = 0.0;
+    for (int j = 0; j < Q; j++) {
+        double dg = M[(size_t)j * Q + j];
+        for (int m = 0; m < j; m++) dg = fma(-L[(size_t)j * Q + m], L[(size_t)j * Q + m], dg);
+        if (!(dg > 0.0)) { d->n_eval++; return INFINITY; }
+        const double ljj = sqrt(dg);
+        L[(size_t)j * Q + j] = ljj;
+        ldv += orc_log(ljj);
+        for (int i = j + 1; i < Q; i++) {
+            double sacc = M[(size_t)i * Q + j];
+            for (int m = 0; m < j; m++) sacc = fma(-L[(size_t)i * Q + m], L[(size_t)j * Q + m], sacc);
+            L[(size_t)i * Q + j] = sacc / ljj;
+        }
+    }
+    for (int cc = 0; cc <= p; cc++)
+        for (int i = 0; i < Q; i++) {
+            double u = 0.0;
+            if (i < nprim) {
+                const int k = i / q0, ai = i % q0;
+                for (int aa = ai; aa < q0; aa++) u += Lm[aa][ai] * d->ZtXy[(size_t)(k * q0 + aa) * (p + 1) + cc];
+            } else {
+                u += te[i >= d->off[1] && d->n_extra > 1 ? 1 : 0] * d->ZtXy[(size_t)i * (p + 1) + cc];
+            }
+            for (int m = 0; m < i; m++) u = fma(-L[(size_t)i * Q + m], R[(size_t)m * (p + 1) + cc], u);
+            R[(size_t)i * (p + 1) + cc] = u / L[(size_t)i * Q + i];
+        }
+    for (size_t e = 0; e < nt; e++) c->A[e] = c->xtx[e];
+    for (int j = 0; j < p; j++) c->b[j] = c->xty[j];
+    double cc = c->yty;
+    for (int i = 0; i < Q; i++) {
+        const double* ri = R + (size_t)i * (p + 1);
+        size_t e = 0;
+        for (int a = 0; a < p; a++) {
+            for (int bb = 0; bb <= a; bb++, e++) c->A[e] = fma(-ri[a], ri[bb], c->A[e]);
+            c->b[a] = fma(-ri[a], ri[p], c->b[a]);
+        }
+        cc = fma(-ri[p], ri[p], cc);
+    }
+    d->n_eval++;
+    ols_solve(c->A, c->b, cc, 0.0, c->n_rows, p, c->L, c->inv_d, c->wv, c->beta, &c->fit);
+    if (!c->fit.converged || !(c->fit.rss > 0.0) || !isfinite(c->fit.rss) || !isfinite(ldv)) return INFINITY;
+    double lda = 0.0;
+    for (int j = 0; j < p; j++) lda += orc_log(c->L[TRI(j, j)]);
+    return 2.0 * ldv + 2.0 * lda + c->fit.df_resid * orc_log(c->fit.sigma_sq);
+}
+
+static double gen_eval(LmmCtx* c, void* d, const double* th) { return gen_dev(c, (GenData*)d, th); }
+
+static void lmm_general_fit(LmmCtx* c, GenData* d, SlopeOut* out) {
+    const int q0 = d->q0, D = q0 * (q0 + 1) / 2 + d->n_extra, max_eval = SLOPE_NM_EVAL_PER_DIM * D;
+    double x[SLOPE_MAXD];
+    int t = 0;
+    for (int i = 0; i < q0; i++)
+        for (int j = 0; j <= i; j++, t++) x[t] = i == j ? 1.0 : 0.0;
+    for (int g = 0; g < d->n_extra; g++) x[t++] = 1.0;
+    d->n_eval = 0;
+    nm_minimise(c, d, gen_eval, &d->n_eval, D, x, 0.5, max_eval / 2);
+    double f = nm_minimise(c, d, gen_eval, &d->n_eval, D, x, 0.05, max_eval);
+    out->boundary_hit = 0;
+    t = 0;
+    for (int i = 0; i < q0; i++)
+        for (int j = 0; j <= i; j++, t++)
+            if (i == j) {
+                x[t] = fabs(x[t]);
+                if (x[t] < 1e-6) out->boundary_hit = 1;
+            }
+    for (int g = 0; g < d->n_extra; g++, t++) {
+        x[t] = fabs(x[t]);
+        if (x[t] < 1e-6) out->boundary_hit = 1;
+    }
+    f = gen_dev(c, d, x);
+    out->converged = isfinite(f) && d->n_eval < max_eval;
+    for (int j = 0; j < D; j++)
+        if (fabs(x[j]) > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+    out->n_eval = d->n_eval;
+    for (int j = 0; j < D; j++) out->theta[j] = x[j];
+    out->sigma_sq = c->fit.sigma_sq;
+}
+
+/* one row into Z'Z (lower) and Z'[X | y]: the row's non-zero random-effect columns are (primary level, component a) with value
+ * z_a = 1, x_s1, x_s2 and one column of value 1 per extra grouping, in column order */
+static void gen_add_row(double* ZtZ, double* ZtXy, int Q, int p, const int* cols, const double* zv, int nz, const double* xy) {
+    for (int u = 0; u < nz; u++) {
+        for (int v = 0; v <= u; v++) {
+            double* e = ZtZ + (size_t)cols[u] * Q + cols[v];
+            *e = fma(zv[u], zv[v], *e);
+        }
+        double* r = ZtXy + (size_t)cols[u] * (p + 1);
+        for (int cc = 0; cc <= p; cc++) r[cc] = fma(zv[u], xy[cc], r[cc]);
+    }
 }
 
 /* Joint Wald chi-square of the targets: beta_T' [Cov_TT]^-1 beta_T with Cov = sigma^2 A^-1. */
@@ -2324,6 +2528,66 @@ int orc_fit_lmm_slopes(const double* xc, const double* yv, const int32_t* ids, i
     slope_components(o.theta, q, o.sigma_sq, vc);
     *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
     free(c); free(cn); free(xtx); free(x); free(y);
+    return ORC_OK;
+}
+
+int orc_fit_lmm_general(const double* xc, const double* yv, const int32_t* ids, int n, int p, int n_slopes, const int32_t* slope_cols,
+                        int n_extra, double* betas, double* se, double* vc, int* converged, int* boundary, int* n_eval) {
+    if (p > 64 || n_slopes < 0 || n_slopes > 2 || n_extra < 0 || n_extra > 2) return fail(ORC_ERR_INVALID_SPEC, "bad p / slope / grouping count");
+    const int q0 = 1 + n_slopes;
+    float* x = (float*)malloc(sizeof(float) * (size_t)n * p);
+    float* y = (float*)malloc(sizeof(float) * (size_t)n);
+    for (size_t i = 0; i < (size_t)n * p; i++) x[i] = (float)xc[i];
+    for (int i = 0; i < n; i++) y[i] = (float)yv[i];
+    int K = 0, E[2] = {0, 0};
+    for (int i = 0; i < n; i++) {
+        if (ids[i] + 1 > K) K = ids[i] + 1;
+        for (int g = 0; g < n_extra; g++) if (ids[(size_t)(1 + g) * n + i] + 1 > E[g]) E[g] = ids[(size_t)(1 + g) * n + i] + 1;
+    }
+    const int Q = K * q0 + E[0] + E[1];
+    size_t nt = (size_t)p * (p + 1) / 2;
+    double* xtx = (double*)calloc(nt + (size_t)p, sizeof(double));
+    double* xty = xtx + nt;
+    double* ZtZ = (double*)calloc((size_t)Q * Q * 4 + (size_t)Q * (p + 1) * 2, sizeof(double));
+    double* ZtXy = ZtZ + (size_t)Q * Q * 4;
+    SuffScalars sc = {0.0, 0.0, 0};
+    suff_add_rows(x, y, n, p, 0, n, xtx, xty, &sc);
+    for (int i = 0; i < n; i++) {
+        int cols[5];
+        double zv[5], xy[65];
+        int nz = 0;
+        for (int a = 0; a < q0; a++) {
+            cols[nz] = ids[i] * q0 + a;
+            zv[nz++] = a == 0 ? 1.0 : (double)x[(size_t)slope_cols[a - 1] * n + i];
+        }
+        for (int g = 0; g < n_extra; g++) {
+            cols[nz] = K * q0 + (g ? E[0] : 0) + ids[(size_t)(1 + g) * n + i];
+            zv[nz++] = 1.0;
+        }
+        for (int j = 0; j < p; j++) xy[j] = (double)x[(size_t)j * n + i];
+        xy[p] = (double)y[i];
+        gen_add_row(ZtZ, ZtXy, Q, p, cols, zv, nz, xy);
+    }
+    LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
+    c->p = p; c->n_rows = (uint32_t)n; c->xtx = xtx; c->xty = xty; c->yty = sc.yty;
+    GenData d = {Q, q0, K, n_extra, {E[0], E[1]}, {K * q0, K * q0 + E[0]}, ZtZ, ZtXy, ZtZ + (size_t)Q * Q, ZtZ + (size_t)Q * Q * 2,
+                 ZtZ + (size_t)Q * Q * 3, ZtXy + (size_t)Q * (p + 1), 0};
+    SlopeOut o;
+    lmm_general_fit(c, &d, &o);
+    double u[64];
+    for (int t = 0; t < p; t++) {
+        betas[t] = c->beta[t];
+        se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
+    }
+    double pv[8];
+    slope_components(o.theta, q0, o.sigma_sq, pv); /* {variances[q0], correlations, sigma²} */
+    const int ncorr = q0 * (q0 - 1) / 2, D0 = q0 * (q0 + 1) / 2;
+    int w = 0;
+    for (int i = 0; i < q0 + ncorr; i++) vc[w++] = pv[i];
+    for (int g = 0; g < n_extra; g++) vc[w++] = o.sigma_sq * (o.theta[D0 + g] * o.theta[D0 + g]);
+    vc[w] = o.sigma_sq;
+    *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
+    free(c); free(ZtZ); free(xtx); free(x); free(y);
     return ORC_OK;
 }
 
@@ -2623,6 +2887,17 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
     const size_t cs_block = (size_t)nc_cap * (P + 1);
     uint32_t* cn = (uint32_t*)calloc((size_t)nc_cap, sizeof(uint32_t));
     LmmCtx* c = (LmmCtx*)calloc(1, sizeof(LmmCtx));
+    /* extra groupings: dense Z'Z / Z'[X | y] over the capacity layout (levels that have no row yet stay all-zero columns: they
+     * contribute exact zeros to every chain) */
+    const int gq0 = 1 + s->n_slopes, gK = nc_cap;
+    const int gE0 = s->n_extra > 0 ? orc_extra_levels_at(s, 0, ld) : 0, gE1 = s->n_extra > 1 ? orc_extra_levels_at(s, 1, ld) : 0;
+    const int gQ = gK * gq0 + gE0 + gE1, gQr = gK + gE0 + gE1;
+    double *gZtZ = NULL, *gZtXy = NULL, *gwork = NULL;
+    if (s->n_extra > 0) {
+        gZtZ = (double*)calloc((size_t)gQ * gQ + (size_t)gQ * (P + 1), sizeof(double));
+        gZtXy = gZtZ + (size_t)gQ * gQ;
+        gwork = (double*)calloc((size_t)gQ * gQ * 5 + (size_t)gQ * (P + 1) * 3, sizeof(double));
+    }
     memset(w->xtx, 0, sizeof(double) * nt);
     memset(w->xty, 0, sizeof(double) * (size_t)P);
     SuffScalars sc = {0.0, 0.0, 0};
@@ -2645,6 +2920,22 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
                     s2[P] = fma(xs, (double)w->y[i], s2[P]);
                 }
                 cn[k]++;
+                if (s->n_extra > 0) {
+                    int cols[5];
+                    double zv[5], xy[65];
+                    int nz = 0;
+                    for (int a = 0; a < gq0; a++) {
+                        cols[nz] = k * gq0 + a;
+                        zv[nz++] = a == 0 ? 1.0 : (double)w->x[(size_t)s->slope_col[a - 1] * ld + i];
+                    }
+                    for (int e = 0; e < s->n_extra; e++) {
+                        cols[nz] = gK * gq0 + (e ? gE0 : 0) + orc_extra_level_of_row(s, e, i);
+                        zv[nz++] = 1.0;
+                    }
+                    for (int j = 0; j < P; j++) xy[j] = (double)w->x[(size_t)j * ld + i];
+                    xy[P] = (double)w->y[i];
+                    gen_add_row(gZtZ, gZtXy, gQ, P, cols, zv, nz, xy);
+                }
             }
             last = n;
         }
@@ -2658,7 +2949,40 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
         int n_clusters = s->sizing_fixed_size ? (n + csz - 1) / csz : csz;
         LmmOut lo;
         c->n_rows = sc.n_rows; c->yty = sc.yty;
-        if (!reduced && s->n_slopes > 0) {
+        if (s->n_extra > 0) {
+            /* extra groupings: the dense penalised-least-squares fit; a reduced fit keeps every grouping's intercept and strips the
+             * primary slopes (batch.rs:1357-1375) */
+            SlopeOut so;
+            if (!reduced) {
+                c->p = P; c->xtx = w->xtx; c->xty = w->xty;
+                GenData gd = {gQ, gq0, gK, s->n_extra, {gE0, gE1}, {gK * gq0, gK * gq0 + gE0}, gZtZ, gZtXy, gwork, gwork + (size_t)gQ * gQ,
+                              gwork + (size_t)gQ * gQ * 2, gwork + (size_t)gQ * gQ * 3, 0};
+                lmm_general_fit(c, &gd, &so);
+            } else {
+                p_red = build_exclusion_remap(s, w->excl_flags, kept, remap);
+                for (int ri = 0; ri < p_red; ri++) {
+                    bred[ri] = w->xty[kept[ri]];
+                    for (int rj = 0; rj <= ri; rj++) Ared[TRI(ri, rj)] = w->xtx[TRI(kept[ri], kept[rj])];
+                }
+                double* rZ = gwork + (size_t)gQ * gQ * 3 + (size_t)gQ * (P + 1); /* behind R: Qr x Qr, then Qr x (p_red + 1) */
+                double* rX = rZ + (size_t)gQr * gQr;
+                for (int i = 0; i < gQr; i++) {
+                    const int fi = i < gK ? i * gq0 : gK * gq0 + (i - gK);
+                    for (int j = 0; j <= i; j++) {
+                        const int fj = j < gK ? j * gq0 : gK * gq0 + (j - gK);
+                        rZ[(size_t)i * gQr + j] = gZtZ[(size_t)fi * gQ + fj];
+                    }
+                    for (int rj = 0; rj < p_red; rj++) rX[(size_t)i * (p_red + 1) + rj] = gZtXy[(size_t)fi * (P + 1) + kept[rj]];
+                    rX[(size_t)i * (p_red + 1) + p_red] = gZtXy[(size_t)fi * (P + 1) + P];
+                }
+                c->p = p_red; c->xtx = Ared; c->xty = bred;
+                GenData gd = {gQr, 1, gK, s->n_extra, {gE0, gE1}, {gK, gK + gE0}, rZ, rX, gwork, gwork + (size_t)gQ * gQ,
+                              gwork + (size_t)gQ * gQ * 2, gwork + (size_t)gQ * gQ * 3, 0};
+                lmm_general_fit(c, &gd, &so);
+            }
+            lo.converged = so.converged; lo.boundary_hit = so.boundary_hit; lo.theta = so.theta[0]; lo.sigma_sq = so.sigma_sq;
+            lo.tau_sq = so.theta[0] * so.theta[0] * so.sigma_sq;
+        } else if (!reduced && s->n_slopes > 0) {
             /* full model with the random slopes: 3- / 6-parameter REML; the reduced fit below strips the slopes like the reference
              * (batch.rs:1357-1375) */
             c->p = P; c->xtx = w->xtx; c->xty = w->xty;
@@ -2713,7 +3037,7 @@ static int run_one_sim_mle(const OrcSpec* s, const uint32_t* ss, int n_ss, uint6
         if (overall) overall[g] = 0;
         if (fx && s->n_factors > 0) memcpy(fx + (size_t)g * s->n_factors, w->excl_flags, (size_t)s->n_factors);
     }
-    free(c); free(cn); free(csum);
+    free(c); free(cn); free(csum); free(gZtZ); free(gwork);
     return ORC_OK;
 }
 

@@ -100,6 +100,11 @@ typedef struct {
     int32_t slope_col[2];           /* design column each slope multiplies */
     double slope_variance[2], slope_corr[2]; /* corr_with_intercept */
     double slope_corr12;            /* slopes[1].corr_with[0] */
+    /* extra groupings, random intercepts only (cluster.extra_groupings[g]; generation.rs:243-430, data_gen.rs:214-236, 818-835) */
+    int32_t n_extra;                /* 0, 1 or 2 */
+    int32_t extra_nested[2];        /* 0 = Crossed { n_clusters }, 1 = NestedWithin { n_per_parent } */
+    int32_t extra_count[2];         /* n_clusters resp. n_per_parent */
+    double extra_tau_squared[2];
 } OrcSpec;
 
 /* ---- RNG primitives (rng.rs:36-128,154-178,354-364) ---- */
@@ -124,6 +129,13 @@ int orc_fit_lmm_slope(const double* xc, const double* yv, const int32_t* ids, in
  * sigma²}. */
 int orc_fit_lmm_slopes(const double* xc, const double* yv, const int32_t* ids, int n, int p, int n_slopes, const int32_t* slope_cols,
                        double* betas, double* se, double* vc, int* converged, int* boundary, int* n_eval);
+/* General structure: primary grouping (ids[0], intercept + n_slopes slopes) plus n_extra intercept-only groupings (ids[1 + g],
+ * n x 1 each, 0-based levels).  vc = {primary variances[q], primary correlations, extra variances[n_extra], sigma²}. */
+int orc_fit_lmm_general(const double* xc, const double* yv, const int32_t* ids, int n, int p, int n_slopes, const int32_t* slope_cols,
+                        int n_extra, double* betas, double* se, double* vc, int* converged, int* boundary, int* n_eval);
+/* level of row i in extra grouping g (ClusterSpec::extra_level_of_row) and the number of levels within the first n rows */
+int orc_extra_level_of_row(const OrcSpec* s, int g, int i);
+int orc_extra_levels_at(const OrcSpec* s, int g, int n);
 int orc_design_factor(const OrcSpec* s, uint64_t base_seed, uint64_t sim_id, double* l_colmajor);
 
 /* ---- transforms (distributions.rs:32-56, data_gen.rs:1106-1182, marginals/t3.rs) ---- */

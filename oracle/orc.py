@@ -64,6 +64,7 @@ class OrcSpec(C.Structure):
         ("n_between", C.c_int32), ("between_cols", C.POINTER(C.c_int32)),
         ("n_slopes", C.c_int32), ("slope_col", C.c_int32 * 2), ("slope_variance", C.c_double * 2), ("slope_corr", C.c_double * 2),
         ("slope_corr12", C.c_double),
+        ("n_extra", C.c_int32), ("extra_nested", C.c_int32 * 2), ("extra_count", C.c_int32 * 2), ("extra_tau_squared", C.c_double * 2),
     ]
 
 
@@ -116,6 +117,8 @@ def lib():
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
     L.orc_design_factor.argtypes = [P(OrcSpec), u64, u64, P(dbl)]
     L.orc_fit_lmm_slope.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.orc_fit_lmm_general.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(i32), C.c_int, P(dbl), P(dbl), P(dbl),
+                                      P(C.c_int), P(C.c_int), P(C.c_int)]
     L.orc_fit_lmm_slopes.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int),
                                      P(C.c_int)]
     L.orc_fit_ols.argtypes = [P(dbl), P(dbl), C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(dbl),
@@ -248,8 +251,15 @@ class PackedSpec:
                 s.sizing_fixed_size, s.sizing_value = 1, int(sizing["FixedSize"]["cluster_size"])
             s.tau_squared = float(cl["tau_squared"])
             slopes = list(cl.get("slopes", []) or [])
-            if len(slopes) > 2 or (cl.get("extra_groupings") or []):
-                raise ValueError("oracle: two random slopes on the primary grouping at most, no extra groupings")
+            extras = list(cl.get("extra_groupings", []) or [])
+            if len(slopes) > 2 or len(extras) > 2 or any(e.get("slopes") for e in extras):
+                raise ValueError("oracle: two random slopes on the primary grouping, two intercept-only extra groupings at most")
+            s.n_extra = len(extras)
+            for g, e in enumerate(extras):
+                rel = e["relation"]
+                s.extra_nested[g] = 1 if "NestedWithin" in rel else 0
+                s.extra_count[g] = int(rel["NestedWithin"]["n_per_parent"] if "NestedWithin" in rel else rel["Crossed"]["n_clusters"])
+                s.extra_tau_squared[g] = float(e["tau_squared"])
             if slopes:
                 cols = list(spec.get("cluster_slope_design_cols", []) or [])
                 if len(cols) != len(slopes):
@@ -446,6 +456,28 @@ def fit_lmm_slopes(x, y, ids, slope_cols):
                                     C.byref(conv), C.byref(bd), C.byref(ne)))
     return {"betas": b, "se": se, "variances": vc[:q].copy(), "corr": vc[q:-1].copy(), "sigma_sq": vc[-1],
             "converged": bool(conv.value), "boundary": bd.value, "n_eval": ne.value}
+
+
+def fit_lmm_general(x, y, ids, slope_cols=(), extra_ids=()):
+    """Primary grouping `ids` (intercept + slopes on design columns `slope_cols`) plus intercept-only extra groupings (`extra_ids`:
+    one 0-based level vector each) by profiled REML on supplied data → dict(betas, se, variances [primary intercept, slopes...],
+    corr, extra_variances, sigma_sq, converged, boundary, n_eval)."""
+    x = np.asarray(x, dtype=np.float64)
+    n, p = x.shape
+    q = 1 + len(slope_cols)
+    ne = len(extra_ids)
+    xc = np.ascontiguousarray(x.T)
+    yv = np.ascontiguousarray(y, dtype=np.float64)
+    idv = np.ascontiguousarray(np.concatenate([np.asarray(ids, dtype=np.int32)] + [np.asarray(e, dtype=np.int32) for e in extra_ids]))
+    cols = np.ascontiguousarray(list(slope_cols) + [0], dtype=np.int32)
+    nc = q * (q - 1) // 2
+    b, se, vc = np.zeros(p), np.zeros(p), np.zeros(q + nc + ne + 1)
+    conv, bd, nev = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().orc_fit_lmm_general(_ptr(xc, C.c_double), _ptr(yv, C.c_double), _ptr(idv, C.c_int32), n, p, len(slope_cols),
+                                     _ptr(cols, C.c_int32), ne, _ptr(b, C.c_double), _ptr(se, C.c_double), _ptr(vc, C.c_double),
+                                     C.byref(conv), C.byref(bd), C.byref(nev)))
+    return {"betas": b, "se": se, "variances": vc[:q].copy(), "corr": vc[q:q + nc].copy(), "extra_variances": vc[q + nc:-1].copy(),
+            "sigma_sq": vc[-1], "converged": bool(conv.value), "boundary": bd.value, "n_eval": nev.value}
 
 
 def fit_lmm_slope(x, y, ids, slope_col: int):

@@ -116,6 +116,17 @@ def case_spec(case: dict) -> dict:
                                            "corr_with": [float(v) for v in (sl.get("corr_with") or [])] if isinstance(sl.get("corr_with"), list)
                                            else ([float(sl["corr_with"])] if sl.get("corr_with") not in (None, [], {}) else [])})
             s["cluster_slope_design_cols"].append(1 + col)
+        for eg in d.get("extra_groupings", []) or []:  # lmm_crossed_* / lmm_nested_*: GroupingSpec as the contract carries it
+            rel = eg["relation"]
+            if "Crossed" in rel:
+                relation = {"Crossed": {"n_clusters": int(_one(rel["Crossed"]["n_clusters"]))}}
+            else:
+                relation = {"NestedWithin": {"n_per_parent": int(_one(rel["NestedWithin"]["n_per_parent"]))}}
+            s["cluster"]["extra_groupings"].append({"relation": relation, "tau_squared": float(_one(eg["tau_squared"])), "slopes": []})
+        for eg in d.get("extra", []) or []:  # lmm_slope_crossed: the composition cases' shorthand
+            kind, cnt = _one(eg["kind"]), int(_one(eg["n_clusters"]))
+            relation = {"Crossed": {"n_clusters": cnt}} if kind == "crossed" else {"NestedWithin": {"n_per_parent": cnt}}
+            s["cluster"]["extra_groupings"].append({"relation": relation, "tau_squared": float(_one(eg["tau_squared"])), "slopes": []})
     return s
 
 

@@ -163,18 +163,20 @@ def f32_bits(a):
 
 
 def f64_hex(a):
+    if isinstance(a, dict):  # a named numeric vector
+        a = a["_data"]
     return [float(v).hex() for v in np.atleast_1d(np.asarray(a, dtype=np.float64))]
 
 
 def main():
     cases = {}
-    families = ("ols_", "glm_", "probit_", "poisson_", "lme_", "lmm_slope_", "lmm_multislope")
+    families = ("ols_", "glm_", "probit_", "poisson_", "lme_", "lmm_")
     for path in sorted(REF.glob("*.rds")):
         name = path.name[:-4]
         if name.endswith(".golden") or not name.startswith(families):
             continue
-        if name.startswith("lmm_slope_") and name not in ("lmm_slope_a", "lmm_slope_b"):
-            continue  # crossed / nested / extra-slope variants: outside the restated path
+        if name.endswith("_extra_slopes"):
+            continue  # slopes on extra groupings: outside the restated path
         d = read_rds(path)
         gpath = REF / f"{name}.golden.rds"
         g = read_rds(gpath) if gpath.exists() else None
@@ -189,6 +191,7 @@ def main():
             "design_f32_colmajor": f32_bits(design["_data"]),
             "outcome_f32": f32_bits(d["outcome"]),
             "cluster_ids": d.get("cluster_ids"),
+            "extra_grouping_ids": d.get("extra_grouping_ids"),
             "mcpower_version": scalar(d.get("mcpower")),
         }
         if g is not None and "z" in g:  # lmer fits with variance components (validation/common.R: lmm goldens)
