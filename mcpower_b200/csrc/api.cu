@@ -443,7 +443,9 @@ static void check_supported(const Spec& s, bool generation_only = false) {
     }
     if (s.between_cols.size() > MCP_MAX_P) unsupported("between_var_indices > " + std::to_string(MCP_MAX_P));
     if (s.posthoc_contrasts.size() > MCP_MAX_PH) unsupported("posthoc contrasts > " + std::to_string(MCP_MAX_PH));
-    if (s.has_slopes_or_groupings) unsupported("more than two random slopes / extra groupings");
+    if (s.has_slopes_or_groupings) unsupported("more than two random slopes / more than two extra groupings / slopes on extra groupings");
+    if (s.n_extra > 0 && s.P() > MCP_MAX_TEMPLATE_P) unsupported("extra groupings with n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
+    if (s.n_extra > 0 && s.estimator != E_MLE) unsupported("extra groupings outside the mixed-model estimator");
     if (s.n_slopes > 0 && s.P() > MCP_MAX_TEMPLATE_P) unsupported("random slopes with n_predictors > " + std::to_string(MCP_MAX_TEMPLATE_P));
     if (s.new_dists.size() > MCP_MAX_MENU || s.resid_dists.size() > MCP_MAX_MENU) unsupported("scenario menus > " + std::to_string(MCP_MAX_MENU));
     for (int v : s.new_dists)
@@ -608,6 +610,16 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
         pl.slope_corr[a] = s.slope_corr[a];
     }
     pl.slope_corr12 = s.slope_corr12;
+    pl.n_extra = s.has_cluster ? s.n_extra : 0;
+    for (int g = 0; g < 2; g++) {
+        pl.extra_nested[g] = s.extra_nested[g];
+        pl.extra_count[g] = std::max(s.extra_count[g], 1);
+        pl.extra_tau_squared[g] = s.extra_tau_squared[g];
+        const int sv = std::max(s.sizing_value, 1);
+        pl.extra_levels[g] = g >= pl.n_extra ? 0
+                             : (!s.extra_nested[g] ? pl.extra_count[g]
+                                                   : (s.sizing_fixed_size ? (pl.max_n + sv - 1) / sv : sv) * pl.extra_count[g]);  // generation.rs:301-320
+    }
     // cluster-level predictors: only with a cluster (data_gen.rs:619-620).  A broadcast factor no longer follows the exact walk
     // row by row, so its per-level counts are read off the statistics like a sampled factor's.
     pl.n_between = s.has_cluster ? (int)s.between_cols.size() : 0;
@@ -1023,11 +1035,17 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         const size_t nc_ = s.sizing_fixed_size ? (size_t)(pl.max_n + cs_ - 1) / cs_ : (size_t)cs_;
         const size_t smem_q = (size_t)MCP_BLOCK * 4 * (P_ | 1) * sizeof(float) + (size_t)(MCP_BLOCK / 4) * STUDY_ * sizeof(double) +
                               (size_t)(MCP_BLOCK / 4) * (((nc_ * (P_ + 1)) | 1) + (nc_ | 1)) * sizeof(double);
-        lmm_quad = smem_q <= 56 * 1024 && pl.n_slopes == 0;  // the random-slope sums live in HBM (one-thread-per-study generator)
+        lmm_quad = smem_q <= 56 * 1024 && pl.n_slopes == 0 && pl.n_extra == 0;  // slope sums / extra groupings: one-thread-per-study generators
         // per-cluster sums [cluster][column][sim] in HBM; wave capped at ~4 GiB of scratch
         // + a snapshot of them and the X'X | X'y | y'y statistics per grid point (LmmLayout in kernels_lmm.cuh)
-        const size_t per_sim = (nc_ * (lw.P + 1) * (1 + pl.n_slopes) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
-                               (pl.optimistic ? 0 : scen_design_bytes(lw.P));  // + scenario designs behind the layout
+        size_t per_sim = (nc_ * (lw.P + 1) * (1 + pl.n_slopes) * (1 + (size_t)n_ss) + (size_t)n_ss * ((size_t)lw.P * (lw.P + 1) / 2 + lw.P + 1)) * sizeof(double) +
+                         (pl.optimistic ? 0 : scen_design_bytes(lw.P));  // + scenario designs behind the layout
+        if (pl.n_extra > 0) {  // extra groupings: the f32 plane + one dense scratch region per (study, sample size) fit (GenLayout)
+            const size_t K = nc_, q0 = 1 + (size_t)pl.n_slopes, Qe = (size_t)pl.extra_levels[0] + (size_t)pl.extra_levels[1];
+            const size_t fit_doubles = 2 * (K * q0 * (q0 + 1) / 2 + Qe * K * q0 + Qe * (Qe + 1) / 2 + (K * q0 + Qe) * (size_t)(lw.P + 1));
+            per_sim = (size_t)pl.max_n * lw.P * sizeof(float) + 8 + (size_t)n_ss * fit_doubles * sizeof(double);
+            lmm_quad = false;
+        }
         const uint32_t cap = (uint32_t)std::max<size_t>(((size_t)4 << 30) / std::max<size_t>(per_sim, 1), 128);
         wave = std::min(wave, cap);
         wave = std::max<uint32_t>(((wave + 127u) / 128u) * 128u, 128u);  // the kernels' stride: whole 128-study CTAs

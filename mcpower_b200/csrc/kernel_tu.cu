@@ -95,6 +95,20 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         glm_fit_kernel<PT, MINB><<<grid_fit, MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, a.scratch);
     }
 #elif defined(MCP_TU_LMM)
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) if (pl.n_extra > 0) {
+        // extra groupings: the f32 data plane, then one dense penalised-least-squares fit per (study, sample size)
+        const size_t stride = (size_t)blocks * MCP_BLOCK;
+        float* const plane = reinterpret_cast<float*>(a.scratch_d);
+        double* const fit_scratch = a.scratch_d + ((size_t)pl.max_n * PT * stride + 1) / 2;
+        const size_t smem_gen = (size_t)MCP_BLOCK * 4 * (PT | 1) * sizeof(float);
+        allow_smem(lmm_plane_kernel<PT>, smem_gen);
+        lmm_plane_kernel<PT><<<blocks, MCP_BLOCK, smem_gen, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims, plane);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem_fit = pl.smem_counters ? (size_t)pl.n_ss * pl.counter_width * sizeof(unsigned) : 0;
+        lmm_general_kernel<PT><<<dim3(blocks, (unsigned)pl.n_ss), MCP_BLOCK, smem_fit, a.stream>>>(a.n_sims, plane, fit_scratch, stride);
+        return cudaGetLastError();
+    }
     {
         using LY = LmmLayout<PT>;
         using G = Q4Geom<PT>;

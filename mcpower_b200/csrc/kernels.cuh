@@ -439,6 +439,7 @@ struct SimCtx {
     uint32_t k0, k1;       // Philox key words (rng.rs:62-64)
     SeqRng seq;            // counter-addressed view of the sequential stream
     double tau;            // sqrt(tau²) of the random intercept
+    double tau_extra[2];   // ... and of the extra groupings' intercepts
     uint32_t seq_row_base; // first sequential-stream word of the per-row factor draws
     const double* utab = nullptr;  // optional table of the study's cluster effects u_c (shared memory), else drawn per row
     uint32_t sim_local = 0;        // the study's index inside the launch (addresses per-wave scratch)
@@ -505,6 +506,7 @@ struct ScenDesign {
     int use_het;
     double beta_eff[PT];
     double tau;         // sqrt of this study's effective tau² (base + ICC jitter, clamped at 0; data_gen.rs:1065-1075)
+    double tau_extra[2];  // the same per extra grouping: one independent jitter draw each, declaration order (data_gen.rs:1077-1091)
     int ok;
 };
 
@@ -671,6 +673,14 @@ static __device__ __noinline__ void scen_populate(ScenDesign<PT>& sd, uint64_t b
             tsq = tsq > 0.0 ? tsq : 0.0;
         }
         sd.tau = sqrt(tsq > 0.0 ? tsq : 0.0);
+        for (int g = 0; g < 2; g++) {
+            double te = g < pl.n_extra ? pl.extra_tau_squared[g] : 0.0;
+            if (g < pl.n_extra && pl.has_lme && pl.icc_noise_sd > 0.0) {
+                te = te + (double)sr.next_normal() * pl.icc_noise_sd;
+                te = te > 0.0 ? te : 0.0;
+            }
+            sd.tau_extra[g] = sqrt(te > 0.0 ? te : 0.0);
+        }
     }
     // ---- per-study effect draw (data_gen.rs:709-751), domain-separated stream (scenarios.rs:28)
     const double het = pl.heterogeneity > 0.0 ? pl.heterogeneity : 0.0;
@@ -725,6 +735,29 @@ static __device__ __noinline__ double re_draw(SimCtx& cx, uint32_t w0) {
 }
 static __device__ __noinline__ double cluster_effect(SimCtx& cx, uint32_t c) {
     return (double)(float)(re_draw(cx, c * (uint32_t)c_plan.re_words) * cx.tau);
+}
+// Level of row i in extra grouping g (ClusterSpec::extra_level_of_row, generation.rs:370-430): one lexicographic stride chain,
+// primary fastest, extras in declaration order; nested levels are parent · n_per_parent + within.
+__device__ __forceinline__ int extra_level_of_row(const DevicePlan& pl, int g, int i) {
+    const int bl = pl.extra_count[g], sv = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    if (!pl.sizing_fixed_size) {
+        const int stride = g == 0 ? sv : sv * pl.extra_count[0];
+        const int within = (i / stride) % bl;
+        return pl.extra_nested[g] ? (i % sv) * bl + within : within;
+    }
+    return (i / sv) * bl + (i % sv) % bl;
+}
+// Sum of the extra groupings' intercept effects of one row (data_gen.rs:214-236, 818-835): grouping g's draws sit behind the
+// primary's (intercepts, then slopes) and behind the earlier groupings' blocks on the sequential stream.
+static __device__ __noinline__ double extra_effects(SimCtx& cx, int row, double u_re) {
+    const DevicePlan& pl = c_plan;
+    uint32_t base = (uint32_t)pl.n_clusters * (uint32_t)(1 + pl.n_slopes);
+    for (int g = 0; g < pl.n_extra; g++) {
+        const uint32_t lvl = (uint32_t)extra_level_of_row(pl, g, row);
+        u_re += (double)(float)(re_draw(cx, (base + lvl) * (uint32_t)pl.re_words) * cx.tau_extra[g]);
+        base += (uint32_t)pl.extra_levels[g];
+    }
+    return u_re;
 }
 // Random-slope effects of cluster c (data_gen.rs:163-213): z_1 (, z_2) are drawn behind ALL the intercept draws, cluster by
 // cluster; z_0 is recovered from the f32 intercept effect; u_k = f32(sum_{j <= k} L[k][j] z_j) with L = chol(diag(tau) R diag(tau)).
@@ -1049,7 +1082,11 @@ __device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t 
     cx.k1 = (uint32_t)(key >> 32);
     cx.seq.init(key);
     cx.tau = !pl.has_cluster ? 0.0 : (sd ? sd->tau : sqrt(pl.tau_squared > 0.0 ? pl.tau_squared : 0.0));
-    cx.seq_row_base = pl.has_cluster ? (uint32_t)pl.n_clusters * (uint32_t)pl.re_words * (uint32_t)(1 + pl.n_slopes) : 0u;
+    cx.seq_row_base = pl.has_cluster ? ((uint32_t)pl.n_clusters * (uint32_t)(1 + pl.n_slopes) + (uint32_t)(pl.extra_levels[0] + pl.extra_levels[1])) *
+                                           (uint32_t)pl.re_words
+                                     : 0u;
+    for (int g = 0; g < 2; g++)
+        cx.tau_extra[g] = g >= pl.n_extra ? 0.0 : (sd ? sd->tau_extra[g] : sqrt(pl.extra_tau_squared[g] > 0.0 ? pl.extra_tau_squared[g] : 0.0));
     cx.sim_local = sim_local;
     if (pl.n_slopes > 0) slope_factor(cx);
 }
@@ -1075,9 +1112,11 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
         // rows of a trailing partial cluster (FixedSize, max_n not a multiple of cluster_size) have no drawn effect
         if (cx.utab) u_re = cx.utab[cid];
         else if (cid < (uint32_t)pl.n_clusters) u_re = cluster_effect(cx, cid);
+        const double u0 = u_re;
+        if (pl.n_extra > 0) u_re = extra_effects(cx, row, u_re);  // extras first (data_gen.rs:818-835), then the primary slopes
         if (pl.n_slopes > 0 && cid < (uint32_t)pl.n_clusters) {  // data_gen.rs:836-842: u_re += u_k · x[slope column k]
             double uk[2];
-            cluster_slope_effects(cx, cid, u_re, uk);
+            cluster_slope_effects(cx, cid, u0, uk);
             for (int k = 0; k < pl.n_slopes; k++) u_re += uk[k] * (double)slab[4 * (pl.slope_col[k] - 1) + r];
         }
     }

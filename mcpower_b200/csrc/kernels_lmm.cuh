@@ -328,7 +328,7 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
 // A = X'X − Σ R_c'R_c, b, c likewise; dev = Σ log det M_c + log det A + (n − p) log sigma².  Full model only: a reduced fit
 // (sparse-factor exclusion, test design) strips the slope like the reference (batch.rs:1357-1375).
 #define MCP_SLOPE_MAXQ 3
-#define MCP_SLOPE_MAXD 6  // q (q + 1) / 2
+#define MCP_SLOPE_MAXD 8  // q (q + 1) / 2 for the primary grouping (+ one scale per extra grouping)
 #define MCP_SLOPE_NM_EVAL_PER_DIM 300
 #define MCP_SLOPE_THETA_MAX 30.0
 template <int PT>
@@ -867,6 +867,484 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LMM_FIT_MINB(PT)) lmm_fit_kerne
         emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
     }
     mcp_report_warp((blockIdx.x * MCP_BLOCK + threadIdx.x) & ~31u, 32u, n_sims);  // unit = one fit; the host divides by n_ss
+    if (cnt_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {
+            const unsigned v = cnt_s[i];
+            if (v) atomicAdd(&pl.counters[i], (unsigned long long)v);
+        }
+    }
+}
+
+// =====================================================================================================================
+// General structure: primary grouping (random intercept + up to two slopes) plus up to two intercept-only extra groupings
+// (crossed / nested).  Replaces the glmm::fit_on arm of run_one_sim (batch.rs:1214-1561, mixed_workspace.rs).  The oracle
+// (its gen_dev) states the penalised-least-squares criterion on dense matrices; here the primary block stays
+// block diagonal (q x q per level) and only the extras' levels are dense — every entry is the oracle's fma chain with the
+// structurally-zero terms left out, so the deviances, the simplex path and the fit agree bit for bit.
+//   stage 1  lmm_plane_kernel   one study per thread: the f32 data plane [row][column][study] (as the GLM arm's)
+//   stage 2  lmm_general_kernel one (study, sample size) fit per thread: Z'Z / Z'[X | y] / X'X from the plane rows (one fma per
+//            term, rows in order), then the search; matrices in a per-fit scratch region [entry][fit] (coalesced over a warp).
+struct GenLayout {
+    int K, q0, Qe, tq;
+    size_t o_spp, o_sep, o_see, o_zxy, o_cp, o_l21, o_l22, o_r, total;
+    __host__ __device__ GenLayout(int K_, int q0_, int Qe_, int PT) : K(K_), q0(q0_), Qe(Qe_), tq(q0_ * (q0_ + 1) / 2) {
+        const size_t spp = (size_t)K * tq, sep = (size_t)Qe * K * q0, see = (size_t)Qe * (Qe + 1) / 2,
+                     zxy = ((size_t)K * q0 + Qe) * (PT + 1);
+        o_spp = 0;
+        o_sep = o_spp + spp;
+        o_see = o_sep + sep;
+        o_zxy = o_see + see;
+        o_cp = o_zxy + zxy;   // work: Cholesky factors of the primary blocks
+        o_l21 = o_cp + spp;   //       L21 (extras x primary)
+        o_l22 = o_l21 + sep;  //       L22 (extras x extras, lower)
+        o_r = o_l22 + see;    //       R = L^-1 Lambda' Z'[X | y]
+        total = o_r + zxy;
+    }
+};
+
+template <int PT>
+struct GenFit {
+    double* sc;  // this fit's scratch: entry e at sc[e · stride]
+    size_t stride;
+    GenLayout ly;
+    int q;             // random-effect components of the primary grouping in THIS fit (the reduced fit strips the slopes)
+    const int* kept;   // design columns of this fit (nullptr: all)
+    int n_extra, E0;
+    int n_eval;
+    __device__ __forceinline__ double& at(size_t e) const { return sc[e * stride]; }
+};
+
+template <int PT>
+static __device__ __noinline__ double gen_dev(LmmCtx<PT>& c, GenFit<PT>& d, const double* th) {
+    const GenLayout& ly = d.ly;
+    const int p = c.p, q = d.q, q0 = ly.q0, K = ly.K, Qe = ly.Qe, tq = ly.tq;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double Lm[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], te[2];
+    int t = 0;
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) Lm[i][j] = i == j ? fabs(th[t]) : th[t];
+    for (int g = 0; g < d.n_extra; g++) te[g] = fabs(th[t++]);
+    d.n_eval++;
+    double ldv = 0.0;
+    // ---- primary blocks: M_k = Lambda' S_k Lambda + I, C_k = chol(M_k)
+    for (int k = 0; k < K; k++) {
+        double S[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], T[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], M[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ], C[MCP_SLOPE_MAXQ][MCP_SLOPE_MAXQ];
+        for (int a = 0; a < q; a++)
+            for (int b = 0; b <= a; b++) S[a][b] = S[b][a] = d.at(ly.o_spp + (size_t)k * tq + tri(a, b));
+        for (int r = 0; r < q; r++)
+            for (int j = 0; j <= r; j++) {
+                double acc = 0.0;
+                for (int bb = j; bb < q; bb++) acc += Lm[bb][j] * S[r][bb];
+                T[r][j] = acc;
+            }
+        for (int i = 0; i < q; i++)
+            for (int j = 0; j <= i; j++) {
+                double acc = 0.0;
+                for (int aa = i; aa < q; aa++) acc += Lm[aa][i] * T[aa][j];
+                M[i][j] = i == j ? acc + 1.0 : acc;
+            }
+        for (int j = 0; j < q; j++) {
+            double dg = M[j][j];
+            for (int m = 0; m < j; m++) dg = fma(-C[j][m], C[j][m], dg);
+            if (!(dg > 0.0)) return inf;
+            const double cjj = sqrt(dg);
+            C[j][j] = cjj;
+            ldv += own_log(cjj);
+            for (int i = j + 1; i < q; i++) {
+                double sacc = M[i][j];
+                for (int m = 0; m < j; m++) sacc = fma(-C[i][m], C[j][m], sacc);
+                C[i][j] = sacc / cjj;
+            }
+        }
+        for (int a = 0; a < q; a++)
+            for (int b = 0; b <= a; b++) d.at(ly.o_cp + (size_t)k * tq + tri(a, b)) = C[a][b];
+        // L21 rows of this block: for every extra level e, L21[e][(k, a)] = (M[e][(k, a)] - sum_{m < a} L21[e][(k, m)] C[a][m]) / C[a][a]
+        for (int e = 0; e < Qe; e++) {
+            const double tg = te[e >= d.E0 ? 1 : 0];
+            double w[MCP_SLOPE_MAXQ], l21[MCP_SLOPE_MAXQ];
+            for (int a = 0; a < q; a++) w[a] = d.at(ly.o_sep + ((size_t)e * K + k) * q0 + a);
+            for (int a = 0; a < q; a++) {
+                double acc = 0.0;
+                for (int bb = a; bb < q; bb++) acc += Lm[bb][a] * w[bb];
+                double sacc = 0.0;
+                sacc += tg * acc;
+                for (int m = 0; m < a; m++) sacc = fma(-l21[m], C[a][m], sacc);
+                l21[a] = sacc / C[a][a];
+                d.at(ly.o_l21 + ((size_t)e * K + k) * q0 + a) = l21[a];
+            }
+        }
+    }
+    // ---- extras: the oracle's dense left-looking Cholesky continued over the extra columns (primary terms first, then extras)
+    for (int j = 0; j < Qe; j++) {
+        const double tj = te[j >= d.E0 ? 1 : 0];
+        double dg;
+        {
+            double acc = 0.0;
+            acc += tj * d.at(ly.o_see + tri(j, j));
+            double m = 0.0;
+            m += tj * acc;
+            dg = m + 1.0;
+        }
+        for (int k = 0; k < K; k++)
+            for (int a = 0; a < q; a++) {
+                const double l = d.at(ly.o_l21 + ((size_t)j * K + k) * q0 + a);
+                dg = fma(-l, l, dg);
+            }
+        for (int m = 0; m < j; m++) {
+            const double l = d.at(ly.o_l22 + tri(j, m));
+            dg = fma(-l, l, dg);
+        }
+        if (!(dg > 0.0)) return inf;
+        const double ljj = sqrt(dg);
+        d.at(ly.o_l22 + tri(j, j)) = ljj;
+        ldv += own_log(ljj);
+        for (int i = j + 1; i < Qe; i++) {
+            const double ti = te[i >= d.E0 ? 1 : 0];
+            double sacc;
+            {
+                double acc = 0.0;
+                acc += tj * d.at(ly.o_see + tri(i, j));
+                double m = 0.0;
+                m += ti * acc;
+                sacc = m;
+            }
+            for (int k = 0; k < K; k++)
+                for (int a = 0; a < q; a++)
+                    sacc = fma(-d.at(ly.o_l21 + ((size_t)i * K + k) * q0 + a), d.at(ly.o_l21 + ((size_t)j * K + k) * q0 + a), sacc);
+            for (int m = 0; m < j; m++) sacc = fma(-d.at(ly.o_l22 + tri(i, m)), d.at(ly.o_l22 + tri(j, m)), sacc);
+            d.at(ly.o_l22 + tri(i, j)) = sacc / ljj;
+        }
+    }
+    // ---- R = L^-1 Lambda' Z'[X | y], column by column
+    for (int cc = 0; cc <= p; cc++) {
+        const int col = cc == p ? PT : (d.kept ? d.kept[cc] : cc);
+        for (int k = 0; k < K; k++) {
+            double rr[MCP_SLOPE_MAXQ];
+            for (int a = 0; a < q; a++) {
+                double u = 0.0;
+                for (int aa = a; aa < q; aa++) u += Lm[aa][a] * d.at(ly.o_zxy + ((size_t)k * q0 + aa) * (PT + 1) + col);
+                for (int m = 0; m < a; m++) u = fma(-d.at(ly.o_cp + (size_t)k * tq + tri(a, m)), rr[m], u);
+                rr[a] = u / d.at(ly.o_cp + (size_t)k * tq + tri(a, a));
+                d.at(ly.o_r + ((size_t)k * q0 + a) * (PT + 1) + cc) = rr[a];
+            }
+        }
+        for (int e = 0; e < Qe; e++) {
+            double u = 0.0;
+            u += te[e >= d.E0 ? 1 : 0] * d.at(ly.o_zxy + ((size_t)K * q0 + e) * (PT + 1) + col);
+            for (int k = 0; k < K; k++)
+                for (int a = 0; a < q; a++)
+                    u = fma(-d.at(ly.o_l21 + ((size_t)e * K + k) * q0 + a), d.at(ly.o_r + ((size_t)k * q0 + a) * (PT + 1) + cc), u);
+            for (int m = 0; m < e; m++) u = fma(-d.at(ly.o_l22 + tri(e, m)), d.at(ly.o_r + ((size_t)K * q0 + m) * (PT + 1) + cc), u);
+            d.at(ly.o_r + ((size_t)K * q0 + e) * (PT + 1) + cc) = u / d.at(ly.o_l22 + tri(e, e));
+        }
+    }
+    // ---- A = X'X - R_x' R_x, b = X'y - R_x' R_y, c = y'y - |R_y|²: every random-effect column in order
+    const int nt = p * (p + 1) / 2;
+    for (int e = 0; e < nt; e++) c.A[e] = c.xtx[e];
+    for (int j = 0; j < p; j++) c.b[j] = c.xty[j];
+    double cc0 = c.yty;
+    for (int i = 0; i < K * q + Qe; i++) {
+        const size_t row = i < K * q ? (size_t)(i / q) * q0 + (size_t)(i % q) : (size_t)K * q0 + (size_t)(i - K * q);
+        double ri[PT + 1];
+        for (int j = 0; j <= p; j++) ri[j] = d.at(ly.o_r + row * (PT + 1) + j);
+        int e = 0;
+        for (int a = 0; a < p; a++) {
+            for (int bb = 0; bb <= a; bb++, e++) c.A[e] = fma(-ri[a], ri[bb], c.A[e]);
+            c.b[a] = fma(-ri[a], ri[p], c.b[a]);
+        }
+        cc0 = fma(-ri[p], ri[p], cc0);
+    }
+    c.ms.factor_and_solve(c.A, c.b, p, cc0, 0.0, c.n_rows);
+    if (!c.ms.out.converged || !(c.ms.out.rss > 0.0) || isinf(c.ms.out.rss) || isinf(ldv) || ldv != ldv) return inf;
+    double lda = 0.0;
+    for (int j = 0; j < p; j++) lda += own_log(c.ms.L[tri(j, j)]);
+    return 2.0 * ldv + 2.0 * lda + c.ms.out.df_resid * own_log(c.ms.out.sigma_sq);
+}
+
+// The oracle's nm_minimise over gen_dev (same comparisons in the same order as slope_nm above).
+template <int PT>
+static __device__ __noinline__ double gen_nm(LmmCtx<PT>& c, GenFit<PT>& d, int D, double* x, double step, int max_eval) {
+    const int V = D + 1;
+    double sx[MCP_SLOPE_MAXD + 1][MCP_SLOPE_MAXD], sf[MCP_SLOPE_MAXD + 1];
+    for (int i = 0; i < V; i++) {
+        for (int j = 0; j < D; j++) sx[i][j] = x[j] + (i == j + 1 ? step : 0.0);
+        sf[i] = gen_dev<PT>(c, d, sx[i]);
+    }
+    for (;;) {
+        int lo = 0, hi = 0, nh;
+        for (int i = 1; i < V; i++) {
+            if (sf[i] < sf[lo]) lo = i;
+            if (sf[i] > sf[hi] || !(sf[i] == sf[i])) hi = i;
+        }
+        nh = lo;
+        for (int i = 0; i < V; i++)
+            if (i != hi && (sf[i] > sf[nh])) nh = i;
+        double size = 0.0;
+        for (int i = 0; i < V; i++)
+            for (int j = 0; j < D; j++) {
+                const double dd = fabs(sx[i][j] - sx[lo][j]);
+                if (dd > size) size = dd;
+            }
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval) {
+            for (int j = 0; j < D; j++) x[j] = sx[lo][j];
+            return sf[lo];
+        }
+        double cen[MCP_SLOPE_MAXD], xr[MCP_SLOPE_MAXD], xe[MCP_SLOPE_MAXD], xc[MCP_SLOPE_MAXD];
+        for (int j = 0; j < D; j++) {
+            double sum = 0.0;
+            for (int i = 0; i < V; i++)
+                if (i != hi) sum += sx[i][j];
+            cen[j] = sum / (double)D;
+            xr[j] = cen[j] + (cen[j] - sx[hi][j]);
+        }
+        const double fr = gen_dev<PT>(c, d, xr);
+        if (fr < sf[lo]) {
+            for (int j = 0; j < D; j++) xe[j] = cen[j] + 2.0 * (cen[j] - sx[hi][j]);
+            const double fe = gen_dev<PT>(c, d, xe);
+            if (fe < fr) {
+                for (int j = 0; j < D; j++) sx[hi][j] = xe[j];
+                sf[hi] = fe;
+            } else {
+                for (int j = 0; j < D; j++) sx[hi][j] = xr[j];
+                sf[hi] = fr;
+            }
+        } else if (fr < sf[nh]) {
+            for (int j = 0; j < D; j++) sx[hi][j] = xr[j];
+            sf[hi] = fr;
+        } else {
+            const bool outside = fr < sf[hi];
+            for (int j = 0; j < D; j++) xc[j] = outside ? cen[j] + 0.5 * (xr[j] - cen[j]) : cen[j] + 0.5 * (sx[hi][j] - cen[j]);
+            const double fc = gen_dev<PT>(c, d, xc);
+            if (fc < (outside ? fr : sf[hi])) {
+                for (int j = 0; j < D; j++) sx[hi][j] = xc[j];
+                sf[hi] = fc;
+            } else {
+                for (int i = 0; i < V; i++) {
+                    if (i == lo) continue;
+                    for (int j = 0; j < D; j++) sx[i][j] = sx[lo][j] + 0.5 * (sx[i][j] - sx[lo][j]);
+                    sf[i] = gen_dev<PT>(c, d, sx[i]);
+                }
+            }
+        }
+    }
+}
+
+template <int PT>
+static __device__ __noinline__ void lmm_general_fit(LmmCtx<PT>& c, GenFit<PT>& d, int& converged, int& boundary) {
+    const int q = d.q, D = q * (q + 1) / 2 + d.n_extra, max_eval = MCP_SLOPE_NM_EVAL_PER_DIM * D;
+    double x[MCP_SLOPE_MAXD];
+    int t = 0;
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++) x[t] = i == j ? 1.0 : 0.0;
+    for (int g = 0; g < d.n_extra; g++) x[t++] = 1.0;
+    d.n_eval = 0;
+    gen_nm<PT>(c, d, D, x, 0.5, max_eval / 2);
+    double f = gen_nm<PT>(c, d, D, x, 0.05, max_eval);
+    boundary = 0;
+    t = 0;
+    for (int i = 0; i < q; i++)
+        for (int j = 0; j <= i; j++, t++)
+            if (i == j) {
+                x[t] = fabs(x[t]);
+                if (x[t] < 1e-6) boundary = 1;
+            }
+    for (int g = 0; g < d.n_extra; g++, t++) {
+        x[t] = fabs(x[t]);
+        if (x[t] < 1e-6) boundary = 1;
+    }
+    f = gen_dev<PT>(c, d, x);
+    converged = !(isinf(f) || f != f) && d.n_eval < max_eval;
+    for (int j = 0; j < D; j++)
+        if (fabs(x[j]) > MCP_SLOPE_THETA_MAX) {
+            boundary = 2;
+            converged = 0;
+        }
+}
+
+// Stage 1 — one study per thread: generate the rows and park them as f32, plane[(row · PT + column) · stride + study]
+// (columns x_1 .. x_{P-1}, y), like the GLM arm's plane.
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_plane_kernel(uint64_t base_seed, uint64_t sim_begin, uint32_t n_sims, float* __restrict__ plane) {
+    const DevicePlan& pl = c_plan;
+    extern __shared__ __align__(16) float smem[];
+    const Slab<MCP_BLOCK> slab{smem + threadIdx.x};
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * MCP_BLOCK;
+    if (sim >= n_sims || mcp_cancelled()) return;
+    const uint64_t key = pcg_mix64(base_seed, sim_begin + sim);
+    ScenDesign<PT> sdv;
+    const bool scen = !pl.optimistic;
+    if (scen) {
+        scen_populate<PT>(sdv, base_seed, sim_begin + sim);
+        if (!sdv.ok) atomicExch(pl.error_flag, 2);
+    }
+    SimCtx cx;
+    init_sim_ctx<PT>(cx, key, sim, scen ? &sdv : nullptr);
+    for (int b = 0; b < (pl.max_n + 3) >> 2; b++) {
+        if (scen) gen_block<PT, true>(b, slab, cx, &sdv);
+        else gen_block<PT, false>(b, slab, cx, nullptr);
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const int row = 4 * b + r;
+            if (row >= pl.max_n) break;
+            double xr[PT];
+            const double yd = scen ? row_xy<PT, true>(b, r, slab, cx, xr, &sdv) : row_xy<PT, false>(b, r, slab, cx, xr, nullptr);
+            float* const rowp = plane + (size_t)row * PT * stride + sim;
+#pragma unroll
+            for (int j = 1; j < PT; j++) rowp[(size_t)(j - 1) * stride] = (float)xr[j];
+            rowp[(size_t)(PT - 1) * stride] = (float)yd;
+        }
+    }
+}
+
+// Stage 2 — one (study, sample size) fit per thread.
+template <int PT>
+__global__ void __launch_bounds__(MCP_BLOCK) lmm_general_kernel(uint32_t n_sims, const float* __restrict__ plane, double* __restrict__ fit_scratch,
+                                                                size_t stride) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    const DevicePlan& pl = c_plan;
+    if (mcp_cancelled()) return;
+    extern __shared__ __align__(16) float smem[];
+    unsigned int* cnt_s = nullptr;
+    if (pl.smem_counters) {
+        cnt_s = reinterpret_cast<unsigned int*>(smem);
+        for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) cnt_s[i] = 0u;
+        __syncthreads();
+    }
+    const uint32_t sim = blockIdx.x * MCP_BLOCK + threadIdx.x;
+    const int g = pl.n_ss - 1 - (int)blockIdx.y;  // longest fits first
+    if (sim < n_sims) {
+        SimOut so{cnt_s, (uint64_t)sim};
+        const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+        const int K = pl.sizing_fixed_size ? (pl.max_n + cs - 1) / cs : cs;  // capacity layout: levels without a row stay zero columns
+        const int q0 = 1 + pl.n_slopes, E0 = pl.extra_levels[0], Qe = pl.extra_levels[0] + pl.extra_levels[1];
+        const GenLayout ly(K, q0, Qe, PT);
+        double* const sc = fit_scratch + (size_t)g * ly.total * stride + sim;
+        const int n = (int)pl.ss[g];
+        for (size_t e = 0; e < ly.o_cp; e++) sc[e * stride] = 0.0;
+        LmmCtx<PT> c;
+        double acc[NACC], xty[PT];
+#pragma unroll
+        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < PT; i++) xty[i] = 0.0;
+        double yty = 0.0;
+        const float* const pp = plane + sim;
+        for (int row = 0; row < n; row++) {
+            double xy[PT + 1];
+            xy[0] = 1.0;
+#pragma unroll
+            for (int j = 1; j <= PT; j++) xy[j] = (double)pp[((size_t)row * PT + (j - 1)) * stride];
+#pragma unroll
+            for (int a = 0; a < PT; a++) {
+#pragma unroll
+                for (int b = 0; b <= a; b++) acc[tri(a, b)] = fma(xy[a], xy[b], acc[tri(a, b)]);
+                xty[a] = fma(xy[a], xy[PT], xty[a]);
+            }
+            yty = fma(xy[PT], xy[PT], yty);
+            const int k = pl.sizing_fixed_size ? row / cs : row % cs;
+            double z[MCP_SLOPE_MAXQ];
+            z[0] = 1.0;
+            for (int a = 1; a < q0; a++) {
+                double xs = 0.0;
+#pragma unroll
+                for (int j = 0; j < PT; j++)
+                    if (j == pl.slope_col[a - 1]) xs = xy[j];
+                z[a] = xs;
+            }
+            int ecol[2];
+            for (int e = 0; e < pl.n_extra; e++) ecol[e] = (e ? E0 : 0) + extra_level_of_row(pl, e, row);
+            // Z'Z: the row's non-zero columns in order — primary components, then one column per extra grouping
+            for (int a = 0; a < q0; a++) {
+                for (int b = 0; b <= a; b++) {
+                    double& v = sc[(ly.o_spp + (size_t)k * ly.tq + tri(a, b)) * stride];
+                    v = fma(z[a], z[b], v);
+                }
+                double* zr = sc + (ly.o_zxy + ((size_t)k * q0 + a) * (PT + 1)) * stride;
+#pragma unroll
+                for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(z[a], xy[j], zr[(size_t)j * stride]);
+            }
+            for (int e = 0; e < pl.n_extra; e++) {
+                for (int a = 0; a < q0; a++) {
+                    double& v = sc[(ly.o_sep + ((size_t)ecol[e] * K + k) * q0 + a) * stride];
+                    v = fma(1.0, z[a], v);
+                }
+                for (int e2 = 0; e2 <= e; e2++) {
+                    double& v = sc[(ly.o_see + tri(ecol[e], ecol[e2])) * stride];
+                    v = fma(1.0, 1.0, v);
+                }
+                double* zr = sc + (ly.o_zxy + ((size_t)K * q0 + ecol[e]) * (PT + 1)) * stride;
+#pragma unroll
+                for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(1.0, xy[j], zr[(size_t)j * stride]);
+            }
+        }
+        uint8_t excl[MCP_MAX_FACTORS];
+        for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
+        const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;
+        int variant = pl.base_variant;
+        if (track_excl) {  // a reference-coded dummy is exactly 0 / 1: its column sum X'X[dummy][0] is the level count
+            variant = 0;
+            for (int f = 0; f < pl.n_factors; f++) {
+                uint32_t rest = (uint32_t)n, mn = 0xffffffffu;
+                for (int l = 1; l < pl.f_levels[f]; l++) {
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int j = 0; j < PT; j++)
+                        if (j == pl.f_col[f] + l - 1) cnt = (uint32_t)acc[tri(j, 0)];
+                    mn = min(mn, cnt);
+                    rest -= cnt;
+                }
+                mn = min(mn, rest);
+                excl[f] = mn < (uint32_t)pl.min_level_count;
+                variant |= (int)excl[f] << f;
+            }
+        }
+        const McpVariant& vr = pl.variants[variant];
+        const bool reduced = vr.p_red != PT;
+        c.p = vr.p_red;
+        c.n_rows = (uint32_t)n;
+        c.yty = yty;
+        {
+            double full[NACC], fxty[PT];
+#pragma unroll
+            for (int i = 0; i < NACC; i++) full[i] = acc[i];
+#pragma unroll
+            for (int i = 0; i < PT; i++) fxty[i] = xty[i];
+            for (int ri = 0; ri < vr.p_red; ri++) {
+                c.xty[ri] = fxty[vr.kept[ri]];
+                for (int rj = 0; rj <= ri; rj++) c.xtx[tri(ri, rj)] = full[tri(vr.kept[ri], vr.kept[rj])];
+            }
+        }
+        int kept_i[PT];
+        for (int ri = 0; ri < vr.p_red; ri++) kept_i[ri] = vr.kept[ri];
+        GenFit<PT> gd{sc, stride, ly, reduced ? 1 : q0, reduced ? kept_i : nullptr, pl.n_extra, E0, 0};
+        int conv = 0, bnd = 0;
+        lmm_general_fit<PT>(c, gd, conv, bnd);
+        double all_t[MCP_MAX_T];
+        int cols[MCP_MAX_T];
+        int k_red = 0;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int t = 0; t < pl.n_marg; t++) {
+            const int col = vr.remap[pl.target[t]];
+            all_t[t] = nan;
+            if (col >= 0) cols[k_red++] = col;
+        }
+        int jsig = 0;
+        if (conv) {
+            for (int t = 0; t < pl.n_marg; t++) {
+                const int col = vr.remap[pl.target[t]];
+                if (col >= 0) all_t[t] = c.ms.t_sq(col, -1);
+            }
+            const double jc = pl.crit_joint[(size_t)variant * pl.n_ss + g];
+            const double jt = lmm_joint_wald<PT>(c, cols, k_red);
+            jsig = !(isinf(jt) || jt != jt) && jt > jc;
+        }
+        FitOut fo = c.ms.out;
+        fo.converged = conv;
+        emit_fit(so, g, variant, fo, vr.p_red, all_t, excl, /*ov_given=*/0, jsig, bnd);
+    }
+    mcp_report_warp((blockIdx.x * MCP_BLOCK + threadIdx.x) & ~31u, 32u, n_sims);
     if (cnt_s) {
         __syncthreads();
         for (int i = threadIdx.x; i < pl.n_ss * pl.counter_width; i += MCP_BLOCK) {

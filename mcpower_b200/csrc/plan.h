@@ -126,6 +126,12 @@ struct DevicePlan {
     int32_t slope_col[2];              // design column each slope effect multiplies
     double slope_variance[2], slope_corr[2];  // tau_k², corr(intercept, slope k): D = diag(tau) R diag(tau) ...
     double slope_corr12;               // ... and corr(slope 0, slope 1) (slopes[1].corr_with[0], generation.rs:225-240)
+    // ---- extra groupings, random intercepts only (cluster.extra_groupings[g]; generation.rs:243-430, data_gen.rs:214-236, 818-835)
+    int32_t n_extra;                   // 0, 1 or 2
+    int32_t extra_nested[2];           // 0 = Crossed { n_clusters }, 1 = NestedWithin { n_per_parent }
+    int32_t extra_count[2];            // n_clusters resp. n_per_parent
+    int32_t extra_levels[2];           // levels within max_n rows (extra_n_levels_at): the length of the grouping's draw block
+    double extra_tau_squared[2];
     // ---- cluster-level predictors (spec.between_var_indices, data_gen.rs:605-640)
     int32_t n_between;                 // 0 unless the spec has a cluster
     int8_t between_cols[MCP_MAX_P];    // design columns (>= 1) broadcast from the cluster's representative row

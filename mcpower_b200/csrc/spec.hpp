@@ -60,6 +60,8 @@ struct Spec {
     bool has_slopes_or_groupings = false;  // what the CUDA path does not run: > 1 slope, slope-slope correlations, extra groupings
     int n_slopes = 0, slope_col[2] = {-1, -1};  // random slopes on the primary grouping (two at most)
     double slope_variance[2] = {0.0, 0.0}, slope_corr[2] = {0.0, 0.0}, slope_corr12 = 0.0;
+    int n_extra = 0, extra_nested[2] = {0, 0}, extra_count[2] = {0, 0};  // intercept-only extra groupings (two at most)
+    double extra_tau_squared[2] = {0.0, 0.0};
     std::vector<int> between_cols;  // between_var_indices (spec.rs:279): design columns broadcast within a cluster
     // cluster
     bool has_cluster = false;
@@ -252,7 +254,26 @@ inline Spec parse_spec(const char* json, size_t len) {
                 invalid("cluster.sizing must be FixedClusters or FixedSize");
             }
             s.tau_squared = num(req(*p, "tau_squared"), "tau_squared");
-            if (auto* q = p->get("extra_groupings")) s.has_slopes_or_groupings |= q->kind == JsonValue::Array && !q->arr.empty();
+            if (auto* q = p->get("extra_groupings"))
+                if (q->kind == JsonValue::Array && !q->arr.empty()) {
+                    if (q->arr.size() > 2) s.has_slopes_or_groupings = true;
+                    s.n_extra = (int)std::min<size_t>(q->arr.size(), 2);
+                    for (int g = 0; g < s.n_extra; g++) {
+                        const JsonValue& eg = q->arr[g];
+                        const JsonValue& rel = req(eg, "relation");
+                        if (auto* cr = rel.get("Crossed")) {
+                            s.extra_nested[g] = 0;
+                            s.extra_count[g] = to_int(req(*cr, "n_clusters"), "Crossed.n_clusters");
+                        } else if (auto* ne = rel.get("NestedWithin")) {
+                            s.extra_nested[g] = 1;
+                            s.extra_count[g] = to_int(req(*ne, "n_per_parent"), "NestedWithin.n_per_parent");
+                        } else {
+                            invalid("extra_groupings.relation must be Crossed or NestedWithin");
+                        }
+                        s.extra_tau_squared[g] = num(req(eg, "tau_squared"), "extra_groupings.tau_squared");
+                        if (auto* sl = eg.get("slopes")) s.has_slopes_or_groupings |= sl->kind == JsonValue::Array && !sl->arr.empty();
+                    }
+                }
             if (auto* q = p->get("slopes"))
                 if (q->kind == JsonValue::Array && !q->arr.empty()) {
                     if (q->arr.size() > 2) s.has_slopes_or_groupings = true;
@@ -362,6 +383,19 @@ inline void validate_spec(const Spec& s, const uint32_t* sample_sizes, uint32_t 
         }
         if (!(std::fabs(s.slope_corr12) <= 1.0)) invalid("random slope variance / correlation out of range");
         if (!(s.tau_squared > 0.0)) invalid("random slopes need tau_squared > 0");  // engine-contract validate(): z0 = u0 / tau0
+    }
+    if (s.n_extra > 0) {  // engine-contract validate.rs:720-745
+        int n_nested = 0;
+        for (int g = 0; g < s.n_extra; g++) {
+            if (s.extra_count[g] < 1) invalid("extra grouping needs at least one level");
+            if (!(s.extra_tau_squared[g] >= 0.0)) invalid("extra grouping tau_squared must be >= 0");
+            if (!s.extra_nested[g] && s.sizing_fixed_size) invalid("GroupingRelation::Crossed requires ClusterSizing::FixedClusters");
+            if (s.extra_nested[g]) {
+                n_nested++;
+                if (s.sizing_fixed_size && s.sizing_value % s.extra_count[g] != 0) invalid("NestedWithin requires cluster_size % n_per_parent == 0");
+            }
+        }
+        if (n_nested > 1) invalid("at most one NestedWithin grouping is supported by this engine version");
     }
     for (int c : s.between_cols)  // the reference indexes x_full unchecked (data_gen.rs:631-633); reject instead
         if (c < 1 || c >= 1 + s.k + s.n_fd) invalid("between_var_indices entry " + std::to_string(c) + " out of range");

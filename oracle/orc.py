@@ -117,6 +117,8 @@ def lib():
     L.orc_generate_sim.argtypes = [P(OrcSpec), u64, u64, C.c_int, P(C.c_float), P(C.c_float), P(i32)]
     L.orc_design_factor.argtypes = [P(OrcSpec), u64, u64, P(dbl)]
     L.orc_fit_lmm_slope.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.orc_extra_level_of_row.argtypes = [P(OrcSpec), C.c_int, C.c_int]
+    L.orc_extra_levels_at.argtypes = [P(OrcSpec), C.c_int, C.c_int]
     L.orc_fit_lmm_general.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(i32), C.c_int, P(dbl), P(dbl), P(dbl),
                                       P(C.c_int), P(C.c_int), P(C.c_int)]
     L.orc_fit_lmm_slopes.argtypes = [P(dbl), P(dbl), P(i32), C.c_int, C.c_int, C.c_int, P(i32), P(dbl), P(dbl), P(dbl), P(C.c_int), P(C.c_int),
@@ -456,6 +458,17 @@ def fit_lmm_slopes(x, y, ids, slope_cols):
                                     C.byref(conv), C.byref(bd), C.byref(ne)))
     return {"betas": b, "se": se, "variances": vc[:q].copy(), "corr": vc[q:-1].copy(), "sigma_sq": vc[-1],
             "converged": bool(conv.value), "boundary": bd.value, "n_eval": ne.value}
+
+
+def extra_level_of_row(spec: dict, g: int, i: int) -> int:
+    """ClusterSpec::extra_level_of_row (generation.rs:386-430)."""
+    s = PackedSpec(spec)
+    return int(lib().orc_extra_level_of_row(C.byref(s.c), g, i))
+
+
+def extra_levels_at(spec: dict, g: int, n: int) -> int:
+    s = PackedSpec(spec)
+    return int(lib().orc_extra_levels_at(C.byref(s.c), g, n))
 
 
 def fit_lmm_general(x, y, ids, slope_cols=(), extra_ids=()):

@@ -133,6 +133,19 @@ def random_spec(case: int):
             s["cluster_slope_design_cols"].append(1 + c)
         if g.random() < 0.3 and k >= 2:
             s["between_var_indices"] = [int(v) for v in g.choice(np.arange(1, 1 + k), size=1)]
+        if g.random() < 0.5:  # extra groupings: crossed needs FixedClusters, one nested at most, cluster_size % n_per_parent == 0
+            kinds = ["nested"] if "FixedSize" in sizing else [str(v) for v in g.choice(["crossed", "nested"], size=int(g.integers(1, 3)))]
+            if kinds.count("nested") > 1:
+                kinds = ["crossed", "nested"]
+            for kind in kinds:
+                if kind == "crossed":
+                    rel = {"Crossed": {"n_clusters": int(g.integers(2, 7))}}
+                else:
+                    npp = int(g.integers(2, 4))
+                    if "FixedSize" in sizing:
+                        sizing["FixedSize"]["cluster_size"] = max(npp, (sizing["FixedSize"]["cluster_size"] // npp) * npp)
+                    rel = {"NestedWithin": {"n_per_parent": npp}}
+                s["cluster"]["extra_groupings"].append({"relation": rel, "tau_squared": float(g.uniform(0.0, 0.3)), "slopes": []})
         if s["scenario"]["lme"] is not None and g.random() < 0.5:
             s["scenario"]["lme"] = {"random_effect_dist": str(g.choice(["normal", "high_kurtosis", "right_skewed", "uniform"])),
                                     "random_effect_df": float(g.choice([4.0, 7.0])), "icc_noise_sd": float(g.choice([0.0, 0.2]))}
@@ -166,6 +179,9 @@ def test_the_generator_covers_every_arm():
             ("mle", "continuous", None)} <= kinds
     assert presets == {"optimistic", "realistic", "doomer", "custom"}
     assert slopes == {0, 1, 2} and posthoc >= 3 and fitcols >= 2 and between >= 2
+    groupings = {tuple("N" if "NestedWithin" in e["relation"] else "C" for e in random_spec(c)[0]["cluster"]["extra_groupings"])
+                 for c in CASES if random_spec(c)[0]["cluster"]}
+    assert {(), ("C",), ("N",)} <= groupings and any(len(t) == 2 for t in groupings)
 
 
 @pytest.mark.gpu
