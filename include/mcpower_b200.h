@@ -184,6 +184,7 @@ typedef struct McpFitInfo {
     double deviance_null;        /* GLM; else NaN */
     double slope_var_hat[2];     /* MLE with random slopes: variances of the slope effects (Sigma-hat = sigma² Lambda Lambda'); else NaN */
     double slope_corr_hat[3];    /* ... and the correlations (slope0, intercept), (slope1, intercept), (slope1, slope0); else NaN */
+    double extra_var_hat[2];     /* MLE with extra groupings: variance of each grouping's random intercept; else NaN */
 } McpFitInfo;
 int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* design_colmajor, uint32_t nrow, uint32_t ncol,
                           const double* outcome, const uint32_t* cluster_ids, int32_t device, double* betas /* [ncol] */,

@@ -620,6 +620,9 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
                              : (!s.extra_nested[g] ? pl.extra_count[g]
                                                    : (s.sizing_fixed_size ? (pl.max_n + sv - 1) / sv : sv) * pl.extra_count[g]);  // generation.rs:301-320
     }
+    // the fit keeps the extras' levels dense (Schur complement + Cholesky per REML evaluation, one thread per fit): bounded
+    if (pl.extra_levels[0] + pl.extra_levels[1] > MCP_MAX_EXTRA_LEVELS)
+        unsupported("extra groupings with more than " + std::to_string(MCP_MAX_EXTRA_LEVELS) + " levels in total at the largest sample size");
     // cluster-level predictors: only with a cluster (data_gen.rs:619-620).  A broadcast factor no longer follows the exact walk
     // row by row, so its per-level counts are read off the statistics like a sampled factor's.
     pl.n_between = s.has_cluster ? (int)s.between_cols.size() : 0;
@@ -1989,6 +1992,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         info->sigma_sq_hat = info->tau_sq_hat = info->deviance = info->deviance_null = nan;
         for (int a = 0; a < 2; a++) info->slope_var_hat[a] = nan;
         for (int a = 0; a < 3; a++) info->slope_corr_hat[a] = nan;
+        for (int a = 0; a < 2; a++) info->extra_var_hat[a] = nan;
         DeviceCtx& cx = ctx_for(device);
         std::lock_guard<std::mutex> lock(cx.mu);
         const cudaStream_t st = cx.compute;
@@ -2045,7 +2049,12 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         bind_tables(lw, lw.plan, dblob);
         CUDA_CHECK(cudaMemsetAsync(cx.d_prog, 0, 256, st));
         lw.plan.error_flag = cx.d_error;
-        const size_t n_out = (size_t)3 * P + 12, n_csum = n_clusters * (size_t)(P + 1) * (size_t)(1 + lw.plan.n_slopes);
+        size_t n_csum = n_clusters * (size_t)(P + 1) * (size_t)(1 + lw.plan.n_slopes);
+        if (mle && lw.plan.n_extra > 0) {  // GenLayout (kernels_lmm.cuh): statistics + work
+            const size_t K = n_clusters, q0 = 1 + (size_t)lw.plan.n_slopes, Qe = (size_t)lw.plan.extra_levels[0] + (size_t)lw.plan.extra_levels[1];
+            n_csum = 2 * (K * q0 * (q0 + 1) / 2 + Qe * K * q0 + Qe * (Qe + 1) / 2 + (K * q0 + Qe) * (size_t)(P + 1));
+        }
+        const size_t n_out = (size_t)3 * P + 14;
         Carver oc(cx.outputs.get(Carver::pad(plane.size() * sizeof(float)) + Carver::pad(n_csum * sizeof(double)) + Carver::pad(n_out * sizeof(double))));
         float* dplane = oc.take<float>(plane.size());
         double* dcsum = oc.take<double>(n_csum);
@@ -2079,6 +2088,7 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
         info->deviance_null = o[3 * P + 6];
         for (int a = 0; a < 2; a++) info->slope_var_hat[a] = o[3 * P + 7 + a];
         for (int a = 0; a < 3; a++) info->slope_corr_hat[a] = o[3 * P + 9 + a];
+        for (int a = 0; a < 2; a++) info->extra_var_hat[a] = o[3 * P + 12 + a];
     });
 }
 

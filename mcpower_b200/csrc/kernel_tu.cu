@@ -268,6 +268,12 @@ static cudaError_t fit_spec_one(const DevicePlan& pl, const float* plane, int n,
 #elif defined(MCP_TU_LMM)
     cudaError_t e = cudaMemcpyToSymbolAsync(c_plan, &pl, sizeof(DevicePlan), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
+    if constexpr (PT <= MCP_MAX_TEMPLATE_P) {
+        if (pl.n_extra > 0) {
+            lmm_general_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, scratch, dout);
+            return cudaGetLastError();
+        }
+    }
     lmm_fit_data_kernel<PT><<<1, 32, 0, st>>>(plane, n, scratch, dout);
     return cudaGetLastError();
 #else

@@ -369,7 +369,7 @@ __global__ void glm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     out[3 * PT + 4] = nan;
     out[3 * PT + 5] = go.deviance;
     out[3 * PT + 6] = go.deviance_null;
-    for (int i = 7; i <= 11; i++) out[3 * PT + i] = nan;
+    for (int i = 7; i <= 13; i++) out[3 * PT + i] = nan;
 }
 
 // Stage 1 is the lane-quad kernel in PLANE mode (kernels_q4.cuh): it generates the study's max_n rows once — the same gen_block /

@@ -769,7 +769,7 @@ __global__ void lmm_fit_data_kernel(const float* __restrict__ plane, int n, doub
     out[3 * PT + 5] = nan;
     out[3 * PT + 6] = nan;
     // random slopes: variances of the slope effects and the correlations (1,0) [(2,0) (2,1)] of Sigma-hat = sigma² Lambda Lambda'
-    for (int i = 7; i <= 11; i++) out[3 * PT + i] = nan;
+    for (int i = 7; i <= 13; i++) out[3 * PT + i] = nan;
     if (pl.n_slopes > 0) {
         double vv[MCP_SLOPE_MAXQ], cr[3];
         slope_components(th3, 1 + pl.n_slopes, c.ms.out.sigma_sq, vv, cr);
@@ -1131,7 +1131,7 @@ static __device__ __noinline__ double gen_nm(LmmCtx<PT>& c, GenFit<PT>& d, int D
 }
 
 template <int PT>
-static __device__ __noinline__ void lmm_general_fit(LmmCtx<PT>& c, GenFit<PT>& d, int& converged, int& boundary) {
+static __device__ __noinline__ void lmm_general_fit(LmmCtx<PT>& c, GenFit<PT>& d, int& converged, int& boundary, double* theta_out = nullptr) {
     const int q = d.q, D = q * (q + 1) / 2 + d.n_extra, max_eval = MCP_SLOPE_NM_EVAL_PER_DIM * D;
     double x[MCP_SLOPE_MAXD];
     int t = 0;
@@ -1160,6 +1160,120 @@ static __device__ __noinline__ void lmm_general_fit(LmmCtx<PT>& c, GenFit<PT>& d
             boundary = 2;
             converged = 0;
         }
+    if (theta_out)
+        for (int j = 0; j < D; j++) theta_out[j] = x[j];
+}
+
+// Z'Z / Z'[X | y] (scratch, zeroed here) and X'X / X'y / y'y (registers) of rows [0, n) of one study's plane: one fma per term, rows
+// in order — the oracle's gen_add_row / suff_add_rows.
+template <int PT>
+__device__ __forceinline__ void gen_accumulate(const float* __restrict__ pp, size_t pstride, int n, double* __restrict__ sc, size_t stride,
+                                               const GenLayout& ly, int E0, double (&acc)[PT * (PT + 1) / 2], double (&xty)[PT], double& yty) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    const DevicePlan& pl = c_plan;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    const int K = ly.K, q0 = ly.q0;
+    for (size_t e = 0; e < ly.o_cp; e++) sc[e * stride] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < PT; i++) xty[i] = 0.0;
+    yty = 0.0;
+    for (int row = 0; row < n; row++) {
+        double xy[PT + 1];
+        xy[0] = 1.0;
+#pragma unroll
+        for (int j = 1; j <= PT; j++) xy[j] = (double)pp[((size_t)row * PT + (j - 1)) * pstride];
+#pragma unroll
+        for (int a = 0; a < PT; a++) {
+#pragma unroll
+            for (int b = 0; b <= a; b++) acc[tri(a, b)] = fma(xy[a], xy[b], acc[tri(a, b)]);
+            xty[a] = fma(xy[a], xy[PT], xty[a]);
+        }
+        yty = fma(xy[PT], xy[PT], yty);
+        const int k = pl.sizing_fixed_size ? row / cs : row % cs;
+        double z[MCP_SLOPE_MAXQ];
+        z[0] = 1.0;
+        for (int a = 1; a < q0; a++) {
+            double xs = 0.0;
+#pragma unroll
+            for (int j = 0; j < PT; j++)
+                if (j == pl.slope_col[a - 1]) xs = xy[j];
+            z[a] = xs;
+        }
+        int ecol[2];
+        for (int e = 0; e < pl.n_extra; e++) ecol[e] = (e ? E0 : 0) + extra_level_of_row(pl, e, row);
+        // the row's non-zero random-effect columns in order: primary components, then one column per extra grouping
+        for (int a = 0; a < q0; a++) {
+            for (int b = 0; b <= a; b++) {
+                double& v = sc[(ly.o_spp + (size_t)k * ly.tq + tri(a, b)) * stride];
+                v = fma(z[a], z[b], v);
+            }
+            double* zr = sc + (ly.o_zxy + ((size_t)k * q0 + a) * (PT + 1)) * stride;
+#pragma unroll
+            for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(z[a], xy[j], zr[(size_t)j * stride]);
+        }
+        for (int e = 0; e < pl.n_extra; e++) {
+            for (int a = 0; a < q0; a++) {
+                double& v = sc[(ly.o_sep + ((size_t)ecol[e] * K + k) * q0 + a) * stride];
+                v = fma(1.0, z[a], v);
+            }
+            for (int e2 = 0; e2 <= e; e2++) {
+                double& v = sc[(ly.o_see + tri(ecol[e], ecol[e2])) * stride];
+                v = fma(1.0, 1.0, v);
+            }
+            double* zr = sc + (ly.o_zxy + ((size_t)K * q0 + ecol[e]) * (PT + 1)) * stride;
+#pragma unroll
+            for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(1.0, xy[j], zr[(size_t)j * stride]);
+        }
+    }
+}
+
+// fit_provided_data twin for a spec with extra groupings (introspect.rs:174-562): plane = [row][x_1 .. x_{P-1}, y] f32, scratch =
+// GenLayout::total doubles.  out as lmm_fit_data_kernel's, plus the extra groupings' variances at [3P + 12], [3P + 13].
+template <int PT>
+__global__ void lmm_general_fit_data_kernel(const float* __restrict__ plane, int n, double* __restrict__ scratch, double* __restrict__ out) {
+    constexpr int NACC = PT * (PT + 1) / 2;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const DevicePlan& pl = c_plan;
+    const int cs = pl.sizing_value > 0 ? pl.sizing_value : 1;
+    const int K = pl.sizing_fixed_size ? (pl.max_n + cs - 1) / cs : cs;
+    const int q0 = 1 + pl.n_slopes, E0 = pl.extra_levels[0], Qe = pl.extra_levels[0] + pl.extra_levels[1];
+    const GenLayout ly(K, q0, Qe, PT);
+    LmmCtx<PT> c;
+    double acc[NACC], xty[PT], yty;
+    gen_accumulate<PT>(plane, 1, n, scratch, 1, ly, E0, acc, xty, yty);
+    c.p = PT;
+    c.n_rows = (uint32_t)n;
+    c.yty = yty;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) c.xtx[i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < PT; i++) c.xty[i] = xty[i];
+    GenFit<PT> gd{scratch, 1, ly, q0, nullptr, pl.n_extra, E0, 0};
+    int conv = 0, bnd = 0;
+    double th[MCP_SLOPE_MAXD] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    lmm_general_fit<PT>(c, gd, conv, bnd, th);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int t = 0; t < PT; t++) {
+        out[t] = c.ms.beta[t];
+        out[PT + t] = conv ? c.ms.var_of(t) : nan;
+        out[2 * PT + t] = conv ? c.ms.t_sq(t, -1) : nan;
+    }
+    out[3 * PT] = (double)conv;
+    out[3 * PT + 1] = (double)bnd;
+    out[3 * PT + 2] = 0.0;
+    out[3 * PT + 3] = c.ms.out.sigma_sq;
+    out[3 * PT + 5] = nan;
+    out[3 * PT + 6] = nan;
+    for (int i = 7; i <= 13; i++) out[3 * PT + i] = nan;
+    double vv[MCP_SLOPE_MAXQ], cr[3];
+    slope_components(th, q0, c.ms.out.sigma_sq, vv, cr);
+    out[3 * PT + 4] = vv[0];
+    for (int a = 0; a < pl.n_slopes; a++) out[3 * PT + 7 + a] = vv[1 + a];
+    for (int a = 0; a < (pl.n_slopes == 2 ? 3 : (pl.n_slopes == 1 ? 1 : 0)); a++) out[3 * PT + 9 + a] = cr[a];
+    const int D0 = q0 * (q0 + 1) / 2;
+    for (int g = 0; g < pl.n_extra; g++) out[3 * PT + 12 + g] = c.ms.out.sigma_sq * (th[D0 + g] * th[D0 + g]);
 }
 
 // Stage 1 — one study per thread: generate the rows and park them as f32, plane[(row · PT + column) · stride + study]
@@ -1222,63 +1336,9 @@ __global__ void __launch_bounds__(MCP_BLOCK) lmm_general_kernel(uint32_t n_sims,
         const GenLayout ly(K, q0, Qe, PT);
         double* const sc = fit_scratch + (size_t)g * ly.total * stride + sim;
         const int n = (int)pl.ss[g];
-        for (size_t e = 0; e < ly.o_cp; e++) sc[e * stride] = 0.0;
         LmmCtx<PT> c;
-        double acc[NACC], xty[PT];
-#pragma unroll
-        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < PT; i++) xty[i] = 0.0;
-        double yty = 0.0;
-        const float* const pp = plane + sim;
-        for (int row = 0; row < n; row++) {
-            double xy[PT + 1];
-            xy[0] = 1.0;
-#pragma unroll
-            for (int j = 1; j <= PT; j++) xy[j] = (double)pp[((size_t)row * PT + (j - 1)) * stride];
-#pragma unroll
-            for (int a = 0; a < PT; a++) {
-#pragma unroll
-                for (int b = 0; b <= a; b++) acc[tri(a, b)] = fma(xy[a], xy[b], acc[tri(a, b)]);
-                xty[a] = fma(xy[a], xy[PT], xty[a]);
-            }
-            yty = fma(xy[PT], xy[PT], yty);
-            const int k = pl.sizing_fixed_size ? row / cs : row % cs;
-            double z[MCP_SLOPE_MAXQ];
-            z[0] = 1.0;
-            for (int a = 1; a < q0; a++) {
-                double xs = 0.0;
-#pragma unroll
-                for (int j = 0; j < PT; j++)
-                    if (j == pl.slope_col[a - 1]) xs = xy[j];
-                z[a] = xs;
-            }
-            int ecol[2];
-            for (int e = 0; e < pl.n_extra; e++) ecol[e] = (e ? E0 : 0) + extra_level_of_row(pl, e, row);
-            // Z'Z: the row's non-zero columns in order — primary components, then one column per extra grouping
-            for (int a = 0; a < q0; a++) {
-                for (int b = 0; b <= a; b++) {
-                    double& v = sc[(ly.o_spp + (size_t)k * ly.tq + tri(a, b)) * stride];
-                    v = fma(z[a], z[b], v);
-                }
-                double* zr = sc + (ly.o_zxy + ((size_t)k * q0 + a) * (PT + 1)) * stride;
-#pragma unroll
-                for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(z[a], xy[j], zr[(size_t)j * stride]);
-            }
-            for (int e = 0; e < pl.n_extra; e++) {
-                for (int a = 0; a < q0; a++) {
-                    double& v = sc[(ly.o_sep + ((size_t)ecol[e] * K + k) * q0 + a) * stride];
-                    v = fma(1.0, z[a], v);
-                }
-                for (int e2 = 0; e2 <= e; e2++) {
-                    double& v = sc[(ly.o_see + tri(ecol[e], ecol[e2])) * stride];
-                    v = fma(1.0, 1.0, v);
-                }
-                double* zr = sc + (ly.o_zxy + ((size_t)K * q0 + ecol[e]) * (PT + 1)) * stride;
-#pragma unroll
-                for (int j = 0; j <= PT; j++) zr[(size_t)j * stride] = fma(1.0, xy[j], zr[(size_t)j * stride]);
-            }
-        }
+        double acc[NACC], xty[PT], yty;
+        gen_accumulate<PT>(plane + sim, stride, n, sc, stride, ly, E0, acc, xty, yty);
         uint8_t excl[MCP_MAX_FACTORS];
         for (int f = 0; f < MCP_MAX_FACTORS; f++) excl[f] = 0;
         const bool track_excl = pl.n_factors > 0 && pl.min_level_count > 0;

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #define MCP_MAX_K 24          // continuous (non-factor) predictors
+#define MCP_MAX_EXTRA_LEVELS 96  // levels of the extra groupings together (the dense part of the mixed-model fit)
 #define MCP_MAX_SLOPES 2      // random slopes on the primary grouping (q = 1 + slopes <= 3 random effects per cluster)
 #define MCP_COOP_MAX_PROB 0.65  // marginal-swap probability below which the scenario kernels take the warp-cooperative marginal pass
 #define MCP_MAX_P 32          // total design columns incl. intercept

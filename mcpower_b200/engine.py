@@ -100,7 +100,7 @@ class _FitInfo(C.Structure):
     _fields_ = [("converged", C.c_int32), ("boundary_hit", C.c_int32), ("iterations", C.c_int32), ("n_targets", C.c_int32),
                 ("crit_sq_uncorrected", C.c_double), ("df_resid", C.c_double), ("sigma_sq_hat", C.c_double),
                 ("tau_sq_hat", C.c_double), ("deviance", C.c_double), ("deviance_null", C.c_double),
-                ("slope_var_hat", C.c_double * 2), ("slope_corr_hat", C.c_double * 3)]
+                ("slope_var_hat", C.c_double * 2), ("slope_corr_hat", C.c_double * 3), ("extra_var_hat", C.c_double * 2)]
 
 
 class _CrossingFit(C.Structure):
@@ -460,7 +460,7 @@ def fit_provided_data(spec: dict, x, y, cluster_ids=None, device: int = -1) -> d
             "converged": bool(info.converged), "crit_sq_uncorrected": info.crit_sq_uncorrected, "df_resid": info.df_resid,
             "boundary_hit": int(info.boundary_hit), "iterations": int(info.iterations), "sigma_sq_hat": info.sigma_sq_hat,
             "tau_sq_hat": info.tau_sq_hat, "deviance": info.deviance, "deviance_null": info.deviance_null,
-            "slope_var_hat": [float(v) for v in info.slope_var_hat], "slope_corr_hat": [float(v) for v in info.slope_corr_hat]}
+            "slope_var_hat": [float(v) for v in info.slope_var_hat], "slope_corr_hat": [float(v) for v in info.slope_corr_hat], "extra_var_hat": [float(v) for v in info.extra_var_hat]}
 
 
 def crit_table(spec: dict, sample_sizes: Sequence[int], n_predictors: Optional[int] = None) -> dict:

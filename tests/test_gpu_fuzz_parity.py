@@ -134,11 +134,16 @@ def random_spec(case: int):
         if g.random() < 0.3 and k >= 2:
             s["between_var_indices"] = [int(v) for v in g.choice(np.arange(1, 1 + k), size=1)]
         if g.random() < 0.5:  # extra groupings: crossed needs FixedClusters, one nested at most, cluster_size % n_per_parent == 0
+            # (few levels: the oracle's dense Cholesky is cubic in the number of random-effect columns)
+            if "FixedSize" in sizing:
+                sizing["FixedSize"]["cluster_size"] = int(g.integers(24, 40))
+            else:
+                sizing["FixedClusters"]["n_clusters"] = int(g.integers(4, 13))
             kinds = ["nested"] if "FixedSize" in sizing else [str(v) for v in g.choice(["crossed", "nested"], size=int(g.integers(1, 3)))]
             if kinds.count("nested") > 1:
                 kinds = ["crossed", "nested"]
-            for kind in kinds:
-                if kind == "crossed":
+            for rel_kind in kinds:
+                if rel_kind == "crossed":
                     rel = {"Crossed": {"n_clusters": int(g.integers(2, 7))}}
                 else:
                     npp = int(g.integers(2, 4))
@@ -151,6 +156,8 @@ def random_spec(case: int):
                                     "random_effect_df": float(g.choice([4.0, 7.0])), "icc_noise_sd": float(g.choice([0.0, 0.2]))}
         grid = [max(n, 90) for n in grid]
     n_sims = 96 if kind != "mle" else 64
+    if kind == "mle" and s["cluster"]["extra_groupings"]:
+        grid, n_sims = grid[-2:], 32
     return s, sorted(set(grid)), n_sims, int(g.integers(1, 2**62)), f"case{case}:{kind}:{preset}:P{P}:f{n_factors}"
 
 

@@ -197,3 +197,29 @@ def test_gpu_factor_exclusion_with_extra_groupings_matches_the_oracle():
     for key in ("uncorrected", "corrected", "converged", "joint", "boundary_hit", "factor_excluded"):
         assert np.array_equal(getattr(got, key), want[key]), key
     assert np.array_equal(got.t_sq, want["t_sq"], equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GROUPED)
+def test_gpu_reml_on_reference_bytes_matches_lmer_and_the_oracle(name):
+    """fit_provided_data (introspect.rs:174-562) through the CUDA fit on the reference's saved bytes: lme4's answers within the
+    reference's own gates, and the oracle's doubles exactly."""
+    case = CS.validation_cases()[name]
+    spec = CS.case_spec(case)
+    x, y = CS.case_arrays(case)
+    g = CS.golden_arrays(case)
+    ids = (np.asarray(case["cluster_ids"]) - min(case["cluster_ids"])).astype(np.uint32)
+    got = M.fit_provided_data(spec, x.astype(np.float64), y.astype(np.float64), cluster_ids=ids)
+    assert got["converged"] and got["boundary_hit"] == 0
+    assert _rel(got["betas"], g["beta"]) < 1e-4
+    assert _rel(got["statistic"], np.abs(g["z"][1:])) < 1e-4
+    ns, ne = len(spec["cluster_slope_design_cols"]), len(spec["cluster"]["extra_groupings"])
+    assert _rel([got["tau_sq_hat"]] + got["slope_var_hat"][:ns] + got["extra_var_hat"][:ne], g["vars"]) < 1e-3
+    assert _rel(got["sigma_sq_hat"], g["sigma2"][0]) < 1e-3
+    if ns:
+        assert abs(got["slope_corr_hat"][0] - g["corr"][0]) < 2e-3
+    extra = [np.asarray(e) - min(e) for e in case["extra_grouping_ids"]]
+    want = orc.fit_lmm_general(x.astype(np.float64), y.astype(np.float64), ids.astype(np.int32), spec["cluster_slope_design_cols"], extra)
+    assert np.array_equal(got["betas"], want["betas"]) and np.array_equal(got["se"], want["se"][1:])
+    assert got["sigma_sq_hat"] == want["sigma_sq"] and got["tau_sq_hat"] == want["variances"][0]
+    assert got["extra_var_hat"][:ne] == list(want["extra_variances"])
