@@ -223,3 +223,36 @@ def test_gpu_reml_on_reference_bytes_matches_lmer_and_the_oracle(name):
     assert np.array_equal(got["betas"], want["betas"]) and np.array_equal(got["se"], want["se"][1:])
     assert got["sigma_sq_hat"] == want["sigma_sq"] and got["tau_sq_hat"] == want["variances"][0]
     assert got["extra_var_hat"][:ne] == list(want["extra_variances"])
+
+
+def _grouped_contract():
+    import test_contract_lowering as TC
+    cluster = {"sizing": {"FixedClusters": {"n_clusters": 10}}, "tau_squared": 0.25,
+               "slopes": [{"column": 0, "variance": 0.1, "corr_with_intercept": 0.3, "corr_with": []}],
+               "extra_groupings": [{"relation": {"Crossed": {"n_clusters": 6}}, "tau_squared": 0.15, "slopes": []},
+                                   {"relation": {"NestedWithin": {"n_per_parent": 2}}, "tau_squared": 0.08, "slopes": []}]}
+    return TC.contract([TC.normal(), TC.normal()], [TC.CONST, TC.direct(0), TC.direct(1)], [0.0, 0.3, 0.2],
+                       [TC.marginal(1), TC.marginal(2)], estimator="mle", cluster=cluster)
+
+
+def test_contract_with_extra_groupings_lowers_and_runs_on_the_oracle():
+    import msgpack
+    low = M.lower_contracts(msgpack.packb([_grouped_contract()], use_bin_type=True))[0]
+    eg = low["spec"]["cluster"]["extra_groupings"]
+    assert [list(e["relation"]) for e in eg] == [["Crossed"], ["NestedWithin"]]
+    assert low["spec"]["cluster_slope_design_cols"] == [1] and low["spec"]["extra_slope_cols"] == [[], []]
+    r = orc.run_batch(low["spec"], [240], 8, 5)
+    assert r["converged"].shape == (8, 1)
+
+
+@pytest.mark.gpu
+def test_gpu_contract_with_extra_groupings_runs_end_to_end():
+    """The hosts' payload for `y ~ x1 + x2 + (1 + x1 | g) + (1 | item) + (1 | g:half)` through the contract entry point."""
+    import msgpack
+    blob = msgpack.packb([_grouped_contract()], use_bin_type=True)
+    low = M.lower_contracts(blob)[0]
+    got = M.find_power_contracts(blob, 240, 256, 2137)
+    pr = got["scenarios"][0][1]
+    want = orc.run_batch(low["spec"], [240], 256, M.splitmix64(2137), n_threads=orc.host_threads())
+    assert pr["success_counts_uncorrected"] == [int(v) for v in want["uncorrected"].sum(axis=0)[0]]
+    assert pr["convergence_count"] == int(want["converged"].sum())
