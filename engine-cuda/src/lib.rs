@@ -113,6 +113,80 @@ extern "C" {
         json_out: *mut *mut c_char,
     ) -> c_int;
     fn mcp_free_string(s: *mut c_char);
+    fn mcp_fit_provided_data(
+        spec_json: *const c_char,
+        spec_len: usize,
+        design_colmajor: *const f64,
+        nrow: u32,
+        ncol: u32,
+        outcome: *const f64,
+        cluster_ids: *const u32,
+        device: i32,
+        betas: *mut f64,
+        se: *mut f64,
+        statistic: *mut f64,
+        info: *mut McpFitInfo,
+    ) -> c_int;
+}
+
+/// `McpFitInfo` (include/mcpower_b200.h): what `introspect::fit_provided_data` reports next to beta / SE / statistic.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct McpFitInfo {
+    pub converged: i32,
+    pub boundary_hit: i32,
+    pub iterations: i32,
+    pub n_targets: i32,
+    pub crit_sq_uncorrected: f64,
+    pub df_resid: f64,
+    pub sigma_sq_hat: f64,
+    pub tau_sq_hat: f64,
+    pub deviance: f64,
+    pub deviance_null: f64,
+    pub slope_var_hat: [f64; 2],
+    pub slope_corr_hat: [f64; 3],
+    pub extra_var_hat: [f64; 2],
+}
+
+/// The shipped fit code of `spec.estimator` on supplied bytes (`introspect.rs:174-562`): OLS solve, IRLS from the truth start, or
+/// profiled REML (random intercept, slopes on the primary grouping, crossed / nested extra groupings) on the CUDA kernels.
+/// `design` is column-major `nrow x ncol` with the intercept column first; returns (betas[ncol], se[n_targets],
+/// statistic[n_targets], info).
+pub fn fit_provided_data(
+    spec: &SimulationSpec,
+    design: &[f64],
+    nrow: usize,
+    ncol: usize,
+    outcome: &[f64],
+    cluster_ids: Option<&[u32]>,
+) -> Result<(Vec<f64>, Vec<f64>, Vec<f64>, McpFitInfo), EngineError> {
+    let json = serde_json::to_vec(spec).map_err(|e| EngineError::InvalidSpec(e.to_string()))?;
+    if design.len() != nrow * ncol || outcome.len() != nrow {
+        return Err(EngineError::InvalidSpec("design / outcome shape".into()));
+    }
+    let nt = spec.target_indices.len();
+    let (mut betas, mut se, mut stat) = (vec![0.0; ncol], vec![0.0; nt], vec![0.0; nt]);
+    let mut info = McpFitInfo::default();
+    let rc = unsafe {
+        mcp_fit_provided_data(
+            json.as_ptr() as *const c_char,
+            json.len(),
+            design.as_ptr(),
+            nrow as u32,
+            ncol as u32,
+            outcome.as_ptr(),
+            cluster_ids.map_or(std::ptr::null(), |c| c.as_ptr()),
+            0,
+            betas.as_mut_ptr(),
+            se.as_mut_ptr(),
+            stat.as_mut_ptr(),
+            &mut info,
+        )
+    };
+    if rc != 0 {
+        return Err(status_to_error(rc));
+    }
+    Ok((betas, se, stat, info))
 }
 
 /// Visible CUDA devices; 0 = fall back to the CPU engine.
