@@ -23,7 +23,9 @@ DEPS = ["api.cu", "kernel_tu.cu", "kernels.cuh", "kernels_q4.cuh", "kernels_lean
         "plan.h", "spec.hpp", "contract.hpp", "orchestrator.hpp", "critvals.hpp", "json.hpp", "../../include/mcpower_b200.h"]
 # (tu id, P_lo, P_hi, glm) — must match MCP_TU_LIST in csrc/launch.h
 TUS = [(0, 1, 6, False), (1, 7, 9, False), (2, 10, 11, False), (3, 12, 13, False), (4, 14, 15, False), (5, 16, 16, False),
-       (6, 1, 8, "GLM"), (7, 9, 12, "GLM"), (8, 13, 16, "GLM"), (9, 1, 9, "LMM"), (10, 10, 16, "LMM"),
+       (6, 1, 8, "GLM"), (7, 9, 12, "GLM"), (8, 13, 16, "GLM"),
+       # the mixed-model units are the slowest to compile (random-slope and extra-grouping fits per width): four of them
+       (9, 1, 6, "LMM"), (10, 7, 10, "LMM"), (17, 11, 13, "LMM"), (18, 14, 16, "LMM"),
        # padded wide widths (plan.h: MCP_WIDE_P_A / MCP_WIDE_P_B): the split path's kernels only
        (11, 24, 24, False), (12, 32, 32, False), (13, 24, 24, "GLM"), (14, 32, 32, "GLM"), (15, 24, 24, "LMM"), (16, 32, 32, "LMM")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

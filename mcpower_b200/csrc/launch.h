@@ -29,7 +29,7 @@ struct KernelArgs {
     bool tu##id##_fit_spec(int P, int kind, const DevicePlan& plan, const float* plane, int n, double* scratch, double* dout,  \
                            cudaStream_t st, cudaError_t* err);
 
-#define MCP_TU_LIST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#define MCP_TU_LIST(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18)
 MCP_TU_LIST(MCP_DECLARE_TU)
 
 }  // namespace mcp
