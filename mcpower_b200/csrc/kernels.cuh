@@ -312,11 +312,16 @@ __device__ __forceinline__ void mcp_report_warp(uint32_t first, uint32_t per_war
     if ((threadIdx.x & 31u) == 0u && first < total) mcp_report_units(total - first < per_warp ? total - first : per_warp);
 }
 
-// Warp-aggregated counter add: one atomic per warp per flag.
+// Warp-aggregated counter add: one atomic per cell per convergence group.  The lanes that execute this call together need not be
+// the whole warp, and — after divergent per-fit searches of different length — lanes that sit in different iterations of the
+// caller's loops can be scheduled together at this instruction: the group is therefore split by the cell the lanes count into
+// (match.any on the address) before the ballot is folded.
 __device__ __forceinline__ void count_flag(unsigned int* cnt_s, unsigned long long* cnt_g, int idx, bool flag) {
     const unsigned am = __activemask();
-    const unsigned b = __ballot_sync(am, flag);
-    if (b != 0u && (threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) {
+    const unsigned long long cell = cnt_s ? (unsigned long long)(cnt_s + idx) : (unsigned long long)(cnt_g + idx);
+    const unsigned peers = __match_any_sync(am, cell);
+    const unsigned b = __ballot_sync(am, flag) & peers;
+    if (b != 0u && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
         if (cnt_s) atomicAdd(&cnt_s[idx], (unsigned)__popc(b));
         else atomicAdd(&cnt_g[idx], (unsigned long long)__popc(b));
     }

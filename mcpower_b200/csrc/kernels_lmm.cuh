@@ -471,7 +471,8 @@ static __device__ __noinline__ double slope_nm(LmmCtx<PT>& c, SlopeData<PT>& d, 
                 const double dd = fabs(sx[i][j] - sx[lo][j]);
                 if (dd > size) size = dd;
             }
-        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval) {
+        // (a cancelled batch is discarded: leaving the search early only shortens the wait — these fits run for milliseconds)
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval || mcp_cancelled()) {
             for (int j = 0; j < D; j++) x[j] = sx[lo][j];
             return sf[lo];
         }
@@ -1086,7 +1087,8 @@ static __device__ __noinline__ double gen_nm(LmmCtx<PT>& c, GenFit<PT>& d, int D
                 const double dd = fabs(sx[i][j] - sx[lo][j]);
                 if (dd > size) size = dd;
             }
-        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval) {
+        // (a cancelled batch is discarded: leaving the search early only shortens the wait — these fits run for milliseconds)
+        if ((fabs(sf[hi] - sf[lo]) <= 1e-11 * (fabs(sf[lo]) + 1.0) && size <= 1e-7) || d.n_eval >= max_eval || mcp_cancelled()) {
             for (int j = 0; j < D; j++) x[j] = sx[lo][j];
             return sf[lo];
         }

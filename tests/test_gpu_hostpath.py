@@ -82,6 +82,30 @@ def test_is_cancelled_poll_stops_the_batch():
     assert len(polls) == 5
 
 
+def test_cancel_reaches_a_running_mixed_model_search():
+    """The fits with extra groupings run for milliseconds per thread: the simplex search polls the cancel flag, so a cancelled call
+    returns while the launch is still in flight instead of after its slowest fit."""
+    import time
+    s = S.lmm_spec(12, 0.2)
+    s["cluster"]["extra_groupings"] = [{"relation": {"Crossed": {"n_clusters": 6}}, "tau_squared": 0.15, "slopes": []}]
+    t0 = time.perf_counter()
+    full = M.run_batch(s, [144, 288], 8192, SEED)
+    t_full = time.perf_counter() - t0
+    polls = []
+
+    def is_cancelled():
+        polls.append(1)
+        return len(polls) >= 20
+
+    t0 = time.perf_counter()
+    with pytest.raises(M.Cancelled):
+        M.run_batch(s, [144, 288], 8192, SEED, is_cancelled=is_cancelled)
+    t_cancel = time.perf_counter() - t0
+    assert t_cancel < 0.8 * t_full + 0.05, (t_cancel, t_full)
+    again = M.run_batch(s, [144, 288], 8192, SEED)
+    assert np.array_equal(again.counters, full.counters)
+
+
 def test_bytes_readback_is_pipelined_and_bit_identical():
     spec = S.sweep_spec()
     grid = [40, 120, 400]
