@@ -1013,11 +1013,13 @@ static void enqueue_shard(Shard& sh, const Lowered& lw, const Spec& s, uint32_t 
         size_t per_sim = 0;
         if (bytes) per_sim += (size_t)n_ss * (2 * T + 1 + (s.report_overall ? 1 : 0) + F + 2 * pl.n_ph + (mle ? 2 : 0));
         if (capture) per_sim += (size_t)n_ss * T * sizeof(double);
-        // pieces of >= 128 MiB and >= 128 Ki studies, at most 8: every wave boundary drains the device once (a 62 Ki-study wave
-        // is 3.3 rounds of resident CTAs: sixteen of them cost the 50-point sweep 12 %), and one wave's copy hides behind the next
+        // pieces of >= 64 MiB and >= 64 Ki studies, at most 8: every wave boundary drains the device once (a 62 Ki-study wave is 3.3
+        // rounds of resident CTAs: sixteen of them cost the 50-point sweep 12 % of its kernel time), while one wave's copy hides behind
+        // the next wave's kernels — on a shard of a multi-device call (8 GPUs x 144 MB of config 2) two waves hide half of the host
+        // ingest that otherwise follows the kernels
         const size_t out_bytes = per_sim * n_sims;
-        const uint32_t pieces = (uint32_t)std::min<size_t>(std::max<size_t>(out_bytes >> 27, 1), 8);
-        if (pieces > 1) wave = std::max<uint32_t>((((n_sims + pieces - 1) / pieces + 127u) / 128u) * 128u, 1u << 17);
+        const uint32_t pieces = (uint32_t)std::min<size_t>(std::max<size_t>(out_bytes >> 26, 1), 8);
+        if (pieces > 1) wave = std::max<uint32_t>((((n_sims + pieces - 1) / pieces + 127u) / 128u) * 128u, 1u << 16);
     }
     float* glm_scratch = nullptr;
     if (glm) {
