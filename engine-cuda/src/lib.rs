@@ -146,6 +146,7 @@ pub struct McpFitInfo {
     pub slope_var_hat: [f64; 2],
     pub slope_corr_hat: [f64; 3],
     pub extra_var_hat: [f64; 2],
+    pub pinned_components: i32,
 }
 
 /// The shipped fit code of `spec.estimator` on supplied bytes (`introspect.rs:174-562`): OLS solve, IRLS from the truth start, or
@@ -293,13 +294,13 @@ pub fn run_batch(
         posthoc_unc: unsafe { take(r.posthoc_unc, cells * c) },
         posthoc_cor: unsafe { take(r.posthoc_cor, cells * c) },
         converged: unsafe { take(r.converged, cells) },
-        // random intercept = one variance component: bit 0 pinned <=> boundary_hit == 1 (spec.rs:566-572)
+        // the library packs BatchResult::boundary_hit (bits 0-1) and ::pinned_components (bits 2-6) into one byte per fit
         pinned_components: if boundary_hit.is_empty() {
             vec![0u64; cells]
         } else {
-            boundary_hit.iter().map(|&b| (b == 1) as u64).collect()
+            boundary_hit.iter().map(|&b| (b >> 2) as u64).collect()
         },
-        boundary_hit: if boundary_hit.is_empty() { zeros() } else { boundary_hit },
+        boundary_hit: if boundary_hit.is_empty() { zeros() } else { boundary_hit.iter().map(|&b| b & 3).collect() },
         joint_unc: if joint.is_empty() { zeros() } else { joint.clone() },
         joint_cor: if joint.is_empty() { zeros() } else { joint },
         overall: unsafe { take(r.overall, cells) },

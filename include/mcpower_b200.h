@@ -58,7 +58,7 @@ typedef struct McpOptions {
     McpCancelFn is_cancelled; /* may be NULL */
 } McpOptions;
 
-/* Counter row layout per sample-size index (width = 4T + 7 + 2F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
+/* Counter row layout per sample-size index (width = 4T + 12 + 2F + 4C, C = n_posthoc, J = T + C; aggregation.rs:91-242):
  *   [0,T) uncorrected successes   [T,2T) corrected successes   2T converged   2T+1 overall
  *   [2T+2, +J+1) histogram of #uncorrected-significant tests per sim (targets AND posthoc contrasts)
  *   [2T+3+J, +J+1) histogram of #corrected-significant tests per sim
@@ -66,7 +66,8 @@ typedef struct McpOptions {
  *   then joint Wald successes (MLE arm), fits with boundary_hit != 0 (MLE arm)
  *   then C posthoc uncorrected successes, C posthoc corrected successes
  *   then converged fits with boundary_hit == 1 (singular fits), then F: sims where the GLM separation fallback
- *   dropped factor f (factor_excluded code 2). */
+ *   dropped factor f (factor_excluded code 2), then 5: converged fits with variance component k pinned at 0
+ *   (k = intercept, slopes, extra groupings: EstimatorExtras::Mle::boundary_component_counts, result.rs:362-398). */
 typedef struct McpBatchResult {
     uint32_t n_sims, n_sample_sizes, n_targets, n_factors;
     uint8_t* uncorrected;     /* [n_sims][n_ss][T]  or NULL */
@@ -75,7 +76,9 @@ typedef struct McpBatchResult {
     uint8_t* overall;         /* [n_sims][n_ss]     or NULL (spec.report_overall) */
     uint8_t* factor_excluded; /* [n_sims][n_ss][F]  or NULL; 0 included, 1 sparse-excluded, 2 separation fallback */
     uint8_t* joint;           /* [n_sims][n_ss]     or NULL (MLE arm: joint_unc == joint_cor, spec.rs:574-582) */
-    uint8_t* boundary_hit;    /* [n_sims][n_ss]     or NULL (MLE arm: 0 none, 1 tau-hat = 0, 2 upper bound) */
+    uint8_t* boundary_hit;    /* [n_sims][n_ss]     or NULL (MLE arm).  bits 0-1: BatchResult::boundary_hit (0 none, 1 a variance
+                               * component at 0, 2 optimiser at its bound); bits 2-6: BatchResult::pinned_components bits 0-4
+                               * (intercept, slopes, extra groupings of the fitted model; spec.rs:562-574) */
     double* t_sq;             /* [n_sims][n_ss][T]  or NULL (CAPTURE) */
     uint32_t counter_width;
     uint32_t gpu_launches;    /* kernels launched for this call */
@@ -185,6 +188,7 @@ typedef struct McpFitInfo {
     double slope_var_hat[2];     /* MLE with random slopes: variances of the slope effects (Sigma-hat = sigma² Lambda Lambda'); else NaN */
     double slope_corr_hat[3];    /* ... and the correlations (slope0, intercept), (slope1, intercept), (slope1, slope0); else NaN */
     double extra_var_hat[2];     /* MLE with extra groupings: variance of each grouping's random intercept; else NaN */
+    int32_t pinned_components;   /* MLE: bit k set iff variance component k (intercept, slopes, extra groupings) sat at 0 */
 } McpFitInfo;
 int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* design_colmajor, uint32_t nrow, uint32_t ncol,
                           const double* outcome, const uint32_t* cluster_ids, int32_t device, double* betas /* [ncol] */,

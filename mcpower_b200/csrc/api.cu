@@ -819,6 +819,7 @@ static void lower(const Spec& s, const uint32_t* ss, uint32_t n_ss, Lowered& lw,
     pl.off_ph_cor = pl.off_ph_unc + NPH;
     pl.off_sing = pl.off_ph_cor + NPH;
     pl.off_fsep = pl.off_sing + 1;
+    pl.off_pin = pl.off_fsep + F;
     lw.cw = pl.counter_width;
     pl.smem_counters = (size_t)n_ss * pl.counter_width * sizeof(unsigned) <= 16 * 1024;
 }
@@ -1469,7 +1470,7 @@ int mcp_run_batch(const char* spec_json, size_t spec_len, const uint32_t* sample
 static std::vector<orch::PowerResult> power_results_from(const Spec& s, const McpBatchResult* r, const uint32_t* ss) {
     const int T = (int)r->n_targets, F = (int)r->n_factors, C = (int)r->n_posthoc, J = T + C;
     const int off_hc = 2 * T + 3 + J, off_fx = off_hc + J + 1, off_joint = off_fx + F, off_bh = off_joint + 1;
-    const int off_pu = off_bh + 1, off_pc = off_pu + C, off_sing = off_pc + C, off_fsep = off_sing + 1;
+    const int off_pu = off_bh + 1, off_pc = off_pu + C, off_sing = off_pc + C, off_fsep = off_sing + 1, off_pin = off_fsep + F;
     std::vector<orch::PowerResult> out(r->n_sample_sizes);
     for (uint32_t g = 0; g < r->n_sample_sizes; g++) {
         const uint64_t* row = r->counters + (size_t)g * r->counter_width;
@@ -1491,6 +1492,8 @@ static std::vector<orch::PowerResult> power_results_from(const Spec& s, const Mc
         pr.joint_count = row[off_joint];
         pr.boundary_hits = row[off_bh];
         pr.singular_count = row[off_sing];
+        pr.n_components = s.has_cluster ? 1 + s.n_slopes + s.n_extra : 0;
+        for (int k = 0; k < MCP_MAX_PIN; k++) pr.pin_counts[k] = row[off_pin + k];
         size_t o = 0;
         for (size_t b = 0; b < s.posthoc_block_ncontrasts.size(); b++) {
             orch::PosthocPower ph;
@@ -1502,7 +1505,7 @@ static std::vector<orch::PowerResult> power_results_from(const Spec& s, const Mc
             pr.posthoc.push_back(ph);
         }
         if (r->boundary_hit)
-            for (uint32_t i = 0; i < r->n_sims; i++) pr.boundary_hit.push_back(r->boundary_hit[(size_t)i * r->n_sample_sizes + g]);
+            for (uint32_t i = 0; i < r->n_sims; i++) pr.boundary_hit.push_back(r->boundary_hit[(size_t)i * r->n_sample_sizes + g] & 3);  // the code; bits 2.. are the pinned components
     }
     return out;
 }
@@ -2082,7 +2085,8 @@ int mcp_fit_provided_data(const char* spec_json, size_t spec_len, const double* 
             statistic[t] = std::sqrt(o[2 * P + s.target_indices[t]]);
         }
         info->converged = o[3 * P] != 0.0;
-        info->boundary_hit = (int32_t)o[3 * P + 1];
+        info->boundary_hit = (int32_t)o[3 * P + 1] & 3;
+        info->pinned_components = (int32_t)o[3 * P + 1] >> 2;
         info->iterations = (int32_t)o[3 * P + 2];
         info->sigma_sq_hat = o[3 * P + 3];
         info->tau_sq_hat = o[3 * P + 4];

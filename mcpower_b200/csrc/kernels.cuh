@@ -406,8 +406,12 @@ __device__ __noinline__ void emit_fit(const SimOut& so, int g, int variant, cons
         count_flag(cs, cg, pl.off_fsep + f, excl_flags && excl_flags[f] == 2);
     }
     count_flag(cs, cg, pl.off_joint, joint_sig != 0);
-    count_flag(cs, cg, pl.off_bh, boundary != 0);
-    count_flag(cs, cg, pl.off_sing, fit.converged && boundary == 1);
+    // boundary = code (bits 0-1: 0 none, 1 a variance component at 0, 2 optimiser at its bound) | pinned-component mask << 2
+    const int bcode = boundary & 3, bpins = boundary >> 2;
+    count_flag(cs, cg, pl.off_bh, bcode != 0);
+    count_flag(cs, cg, pl.off_sing, fit.converged && bcode == 1);
+    if (pl.has_cluster)
+        for (int k = 0; k < MCP_MAX_PIN; k++) count_flag(cs, cg, pl.off_pin + k, fit.converged && ((bpins >> k) & 1));
     for (int c = 0; c < NPH; c++) {
         count_flag(cs, cg, pl.off_ph_unc + c, ph_unc[c] != 0);
         count_flag(cs, cg, pl.off_ph_cor + c, ph_cor[c] != 0);

@@ -314,7 +314,7 @@ static __device__ __noinline__ void lmm_fit(LmmCtx<PT>& c, const double* __restr
     if (!searched) th = lmm_fmin<PT>(c, 0.0, MCP_LMM_THETA_MAX, MCP_LMM_TOL, fbest, f0);
     boundary = 0;
     converged = 1;
-    if (!(fbest < f0)) { th = 0.0; boundary = 1; }  // tau-hat = 0: OLS fallback (spec.rs:562-565)
+    if (!(fbest < f0)) { th = 0.0; boundary = 1 | (1 << 2); }  // tau-hat = 0: OLS fallback (spec.rs:562-565); component 0 pinned
     else if (MCP_LMM_THETA_MAX - th < 1e-6 * MCP_LMM_THETA_MAX) { boundary = 2; converged = 0; }
     const double f = lmm_dev<PT>(c, th);  // leaves L, beta, sigma² at theta-hat
     if (isinf(f) || f != f) converged = 0;
@@ -530,13 +530,13 @@ static __device__ __noinline__ void lmm_slope_fit(LmmCtx<PT>& c, SlopeData<PT>& 
         for (int j = 0; j <= i; j++, t++)
             if (i == j) {
                 x[t] = fabs(x[t]);
-                if (x[t] < 1e-6) boundary = 1;  // a variance component pinned at 0 (singular fit)
+                if (x[t] < 1e-6) boundary |= 1 | (4 << i);  // variance component i pinned at 0 (singular fit): code 1, mask bit i
             }
     f = slope_dev<PT>(c, d, x);  // leaves A, L, beta, sigma² at theta-hat
     converged = !(isinf(f) || f != f) && d.n_eval < max_eval;
     for (int t = 0; t < D; t++)
         if (fabs(x[t]) > MCP_SLOPE_THETA_MAX) {
-            boundary = 2;
+            boundary = 2 | (boundary & ~3);
             converged = 0;
         }
     for (int j = 0; j < D; j++) theta[j] = x[j];
@@ -1149,17 +1149,17 @@ static __device__ __noinline__ void lmm_general_fit(LmmCtx<PT>& c, GenFit<PT>& d
         for (int j = 0; j <= i; j++, t++)
             if (i == j) {
                 x[t] = fabs(x[t]);
-                if (x[t] < 1e-6) boundary = 1;
+                if (x[t] < 1e-6) boundary |= 1 | (4 << i);
             }
     for (int g = 0; g < d.n_extra; g++, t++) {
         x[t] = fabs(x[t]);
-        if (x[t] < 1e-6) boundary = 1;
+        if (x[t] < 1e-6) boundary |= 1 | (4 << (q + g));  // components of the fitted model: primary diagonal, then the extras
     }
     f = gen_dev<PT>(c, d, x);
     converged = !(isinf(f) || f != f) && d.n_eval < max_eval;
     for (int j = 0; j < D; j++)
         if (fabs(x[j]) > MCP_SLOPE_THETA_MAX) {
-            boundary = 2;
+            boundary = 2 | (boundary & ~3);
             converged = 0;
         }
     if (theta_out)

@@ -269,6 +269,8 @@ struct PowerResult {
     std::vector<uint64_t> excl_sparse, excl_sep;  // per factor
     int estimator = 0;                            // 0 ols, 1 glm, 2 mle
     uint64_t boundary_hits = 0, joint_count = 0, singular_count = 0;
+    int n_components = 0;          // variance components of the model (1 + slopes + extra groupings; result.rs:362)
+    uint64_t pin_counts[5] = {0, 0, 0, 0, 0};  // converged fits with component k pinned at 0
     std::vector<uint8_t> boundary_hit;            // per sim (only when the byte tensors were requested)
     std::vector<std::string> grid_warnings;
 
@@ -378,9 +380,15 @@ inline void power_result_json(std::string& o, const PowerResult& r) {
         o += ",\"singular_n\":";
         jint(o, r.conv_count);
         o += ",\"boundary_rate_per_component\":[";
-        jnum(o, r.conv_count ? (double)r.singular_count / (double)r.conv_count : 0.0);
+        for (int k = 0; k < r.n_components; k++) {
+            if (k) o += ',';
+            jnum(o, r.conv_count ? (double)r.pin_counts[k] / (double)r.conv_count : 0.0);
+        }
         o += "],\"boundary_component_counts\":[";
-        jint(o, r.singular_count);
+        for (int k = 0; k < r.n_components; k++) {
+            if (k) o += ',';
+            jint(o, r.pin_counts[k]);
+        }
         o += "]}";
     }
     o += ",\"overall_significant_rate\":";

@@ -174,7 +174,7 @@ struct DevicePlan {
                                        // neighbouring bytes — and the host transposes the wave into the sim-major tensors
     int* error_flag;                   // device int: 0 ok, 2 = CorrelationNotPSD raised by a sim
     int32_t counter_width;             // 4T + 6 + n_factors + 4 n_ph
-    int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor, off_sing, off_fsep;  // counter-row offsets (below)
+    int32_t off_hist_cor, off_fx, off_joint, off_bh, off_ph_unc, off_ph_cor, off_sing, off_fsep, off_pin;  // counter-row offsets (below)
     int32_t smem_counters;             // counters staged in shared memory (fits)
     // ---- progress / cancellation mailbox (ProgressSink, spec.rs:38-52); all NULL / 0 when no sink is attached
     unsigned int* prog_counter;        // device counter of finished work units (OLS: studies generated; GLM / MLE: fits)
@@ -197,5 +197,8 @@ struct DevicePlan {
 //   [off_ph_unc, +n_ph)      posthoc uncorrected successes per contrast
 //   [off_ph_cor, +n_ph)      posthoc corrected successes per contrast
 //   off_sing                 converged fits pinned at the variance boundary (boundary_hit == 1: singular_count)
+//   off_pin + k, k < 5       converged fits whose variance component k sat at 0 (pinned_components bit k, spec.rs:566-574; order
+//                            intercept, slopes, extra groupings of the FITTED model)
 //   [off_fsep, +F)           sims where the GLM separation fallback dropped factor f (code 2: factor_separation_counts)
-static inline int mcp_counter_width(int T, int F, int n_ph) { return 4 * T + 7 + 2 * F + 4 * n_ph; }
+#define MCP_MAX_PIN 5  // variance components a mixed-model fit reports pins for: intercept, two slopes, two extra groupings
+static inline int mcp_counter_width(int T, int F, int n_ph) { return 4 * T + 7 + 2 * F + 4 * n_ph + MCP_MAX_PIN; }

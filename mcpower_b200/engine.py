@@ -100,7 +100,8 @@ class _FitInfo(C.Structure):
     _fields_ = [("converged", C.c_int32), ("boundary_hit", C.c_int32), ("iterations", C.c_int32), ("n_targets", C.c_int32),
                 ("crit_sq_uncorrected", C.c_double), ("df_resid", C.c_double), ("sigma_sq_hat", C.c_double),
                 ("tau_sq_hat", C.c_double), ("deviance", C.c_double), ("deviance_null", C.c_double),
-                ("slope_var_hat", C.c_double * 2), ("slope_corr_hat", C.c_double * 3), ("extra_var_hat", C.c_double * 2)]
+                ("slope_var_hat", C.c_double * 2), ("slope_corr_hat", C.c_double * 3), ("extra_var_hat", C.c_double * 2),
+                ("pinned_components", C.c_int32)]
 
 
 class _CrossingFit(C.Structure):
@@ -202,7 +203,8 @@ class BatchResult:
     overall: Optional[np.ndarray] = None
     factor_excluded: Optional[np.ndarray] = None
     joint: Optional[np.ndarray] = None         # [n_sims, n_ss] joint Wald decision (estimator mle)
-    boundary_hit: Optional[np.ndarray] = None  # [n_sims, n_ss] 0 none / 1 tau-hat = 0 / 2 upper bound (estimator mle)
+    boundary_hit: Optional[np.ndarray] = None  # [n_sims, n_ss] (estimator mle) bits 0-1: 0 none / 1 a variance component at 0 /
+    #                                            2 optimiser at its bound; bits 2-6: pinned_components (see the properties below)
     t_sq: Optional[np.ndarray] = None          # [n_sims, n_ss, T] float64 (MODE_CAPTURE)
     n_posthoc: int = 0                         # C = pairwise posthoc contrasts over all blocks
     posthoc_unc: Optional[np.ndarray] = None   # [n_sims, n_ss, C] uint8 (BatchResult::posthoc_unc, spec.rs:557-559)
@@ -230,6 +232,21 @@ class BatchResult:
     @property
     def n_converged(self):
         return self.counters[:, 2 * self.n_targets]
+
+    @property
+    def boundary_code(self):
+        """BatchResult::boundary_hit (spec.rs:562-565): 0 none, 1 a variance component at 0, 2 optimiser at its bound."""
+        return None if self.boundary_hit is None else self.boundary_hit & 3
+
+    @property
+    def pinned_components(self):
+        """BatchResult::pinned_components (spec.rs:566-574): bit k set iff variance component k of the fitted model sat at 0."""
+        return None if self.boundary_hit is None else (self.boundary_hit >> 2).astype(np.uint64)
+
+    @property
+    def pinned_component_counts(self):
+        """[n_ss, 5]: converged fits with component k (intercept, slopes, extra groupings) pinned — EstimatorExtras::Mle."""
+        return self.counters[:, -5:]
 
     @property
     def success_overall(self):
@@ -298,7 +315,7 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
     F = 0 if factor_excluded is None else factor_excluded.shape[2]
     Cph = 0 if posthoc_unc is None else posthoc_unc.shape[2]
     J = T + Cph
-    out = np.zeros((n_ss, 4 * T + 7 + 2 * F + 4 * Cph), dtype=np.uint64)
+    out = np.zeros((n_ss, 4 * T + 12 + 2 * F + 4 * Cph), dtype=np.uint64)
     out[:, :T] = uncorrected.sum(axis=0)
     out[:, T:2 * T] = corrected.sum(axis=0)
     out[:, 2 * T] = converged.sum(axis=0)
@@ -320,8 +337,11 @@ def counters_from_bytes(uncorrected, corrected, converged, overall=None, factor_
     if joint is not None:
         out[:, o_fx + F] = joint.sum(axis=0)
     if boundary_hit is not None:
-        out[:, o_fx + F + 1] = (boundary_hit != 0).sum(axis=0)
-        out[:, o_fx + F + 2 + 2 * Cph] = ((boundary_hit == 1) & (converged != 0)).sum(axis=0)
+        code, pins = boundary_hit & 3, boundary_hit >> 2  # BatchResult::boundary_hit | pinned_components << 2
+        out[:, o_fx + F + 1] = (code != 0).sum(axis=0)
+        out[:, o_fx + F + 2 + 2 * Cph] = ((code == 1) & (converged != 0)).sum(axis=0)
+        for k in range(5):
+            out[:, o_fx + 2 * F + 3 + 2 * Cph + k] = ((((pins >> k) & 1) != 0) & (converged != 0)).sum(axis=0)
     if Cph:
         out[:, o_fx + F + 2:o_fx + F + 2 + Cph] = posthoc_unc.sum(axis=0)
         out[:, o_fx + F + 2 + Cph:o_fx + F + 2 + 2 * Cph] = posthoc_cor.sum(axis=0)
@@ -460,7 +480,7 @@ def fit_provided_data(spec: dict, x, y, cluster_ids=None, device: int = -1) -> d
             "converged": bool(info.converged), "crit_sq_uncorrected": info.crit_sq_uncorrected, "df_resid": info.df_resid,
             "boundary_hit": int(info.boundary_hit), "iterations": int(info.iterations), "sigma_sq_hat": info.sigma_sq_hat,
             "tau_sq_hat": info.tau_sq_hat, "deviance": info.deviance, "deviance_null": info.deviance_null,
-            "slope_var_hat": [float(v) for v in info.slope_var_hat], "slope_corr_hat": [float(v) for v in info.slope_corr_hat], "extra_var_hat": [float(v) for v in info.extra_var_hat]}
+            "slope_var_hat": [float(v) for v in info.slope_var_hat], "slope_corr_hat": [float(v) for v in info.slope_corr_hat], "extra_var_hat": [float(v) for v in info.extra_var_hat], "pinned_components": int(info.pinned_components)}
 
 
 def crit_table(spec: dict, sample_sizes: Sequence[int], n_predictors: Optional[int] = None) -> dict:

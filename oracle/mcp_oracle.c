@@ -2052,7 +2052,7 @@ static void lmm_fit(LmmCtx* c, const double* csum, const uint32_t* cn, int n_clu
     double f0 = lmm_dev(c, 0.0);
     out->boundary_hit = 0;
     out->converged = 1;
-    if (!(fbest < f0)) { th = 0.0; out->boundary_hit = 1; }      /* tau-hat = 0: OLS fallback (spec.rs:562-565) */
+    if (!(fbest < f0)) { th = 0.0; out->boundary_hit = 1 | (1 << 2); } /* tau-hat = 0: OLS fallback (spec.rs:562-565); component 0 pinned */
     else if (LMM_THETA_MAX - th < 1e-6 * LMM_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
     double f = lmm_dev(c, th);                                    /* leaves A, L, beta, sigma at theta-hat */
     if (!isfinite(f)) out->converged = 0;
@@ -2247,12 +2247,12 @@ static void lmm_slope_fit(LmmCtx* c, SlopeData* d, SlopeOut* out) {
         for (int j = 0; j <= i; j++, t++)
             if (i == j) {
                 x[t] = fabs(x[t]);
-                if (x[t] < 1e-6) out->boundary_hit = 1; /* a variance component pinned at 0 (singular fit) */
+                if (x[t] < 1e-6) out->boundary_hit |= 1 | (4 << i); /* variance component i pinned at 0: code 1, pinned-mask bit i */
             }
     f = slope_dev(c, d, x); /* leaves A, L, beta, sigma at theta-hat */
     out->converged = isfinite(f) && d->n_eval < max_eval;
     for (int t = 0; t < D; t++)
-        if (fabs(x[t]) > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+        if (fabs(x[t]) > SLOPE_THETA_MAX) { out->boundary_hit = 2 | (out->boundary_hit & ~3); out->converged = 0; }
     out->n_eval = d->n_eval;
     for (int j = 0; j < D; j++) out->theta[j] = x[j];
     out->sigma_sq = c->fit.sigma_sq;
@@ -2374,16 +2374,16 @@ static void lmm_general_fit(LmmCtx* c, GenData* d, SlopeOut* out) {
         for (int j = 0; j <= i; j++, t++)
             if (i == j) {
                 x[t] = fabs(x[t]);
-                if (x[t] < 1e-6) out->boundary_hit = 1;
+                if (x[t] < 1e-6) out->boundary_hit |= 1 | (4 << i);
             }
     for (int g = 0; g < d->n_extra; g++, t++) {
         x[t] = fabs(x[t]);
-        if (x[t] < 1e-6) out->boundary_hit = 1;
+        if (x[t] < 1e-6) out->boundary_hit |= 1 | (4 << (q0 + g)); /* components of the fitted model: primary diagonal, extras */
     }
     f = gen_dev(c, d, x);
     out->converged = isfinite(f) && d->n_eval < max_eval;
     for (int j = 0; j < D; j++)
-        if (fabs(x[j]) > SLOPE_THETA_MAX) { out->boundary_hit = 2; out->converged = 0; }
+        if (fabs(x[j]) > SLOPE_THETA_MAX) { out->boundary_hit = 2 | (out->boundary_hit & ~3); out->converged = 0; }
     out->n_eval = d->n_eval;
     for (int j = 0; j < D; j++) out->theta[j] = x[j];
     out->sigma_sq = c->fit.sigma_sq;
@@ -2457,7 +2457,7 @@ int orc_fit_lmm(const double* xc, const double* yv, const int32_t* ids, int n, i
         betas[t] = c->beta[t];
         se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
     }
-    *theta = o.theta; *sigma_sq = o.sigma_sq; *converged = o.converged; *boundary = o.boundary_hit;
+    *theta = o.theta; *sigma_sq = o.sigma_sq; *converged = o.converged; *boundary = o.boundary_hit & 3;
     free(c); free(cn); free(xtx); free(x); free(y);
     return ORC_OK;
 }
@@ -2526,7 +2526,7 @@ int orc_fit_lmm_slopes(const double* xc, const double* yv, const int32_t* ids, i
         se[t] = sqrt(c->fit.sigma_sq * linv_norm_sq(c->L, c->inv_d, p, t, -1, u));
     }
     slope_components(o.theta, q, o.sigma_sq, vc);
-    *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
+    *converged = o.converged; *boundary = o.boundary_hit & 3; *n_eval = o.n_eval;
     free(c); free(cn); free(xtx); free(x); free(y);
     return ORC_OK;
 }
@@ -2586,7 +2586,7 @@ int orc_fit_lmm_general(const double* xc, const double* yv, const int32_t* ids, 
     for (int i = 0; i < q0 + ncorr; i++) vc[w++] = pv[i];
     for (int g = 0; g < n_extra; g++) vc[w++] = o.sigma_sq * (o.theta[D0 + g] * o.theta[D0 + g]);
     vc[w] = o.sigma_sq;
-    *converged = o.converged; *boundary = o.boundary_hit; *n_eval = o.n_eval;
+    *converged = o.converged; *boundary = o.boundary_hit & 3; *n_eval = o.n_eval;
     free(c); free(ZtZ); free(xtx); free(x); free(y);
     return ORC_OK;
 }

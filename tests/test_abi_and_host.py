@@ -154,6 +154,6 @@ def test_counters_from_bytes_matches_manual_aggregation():
     cor = (unc & (rng.random((50, 3, 4)) < 0.7)).astype(np.uint8)
     conv = np.ones((50, 3), dtype=np.uint8)
     c = M.counters_from_bytes(unc, cor, conv, None, None)
-    assert c.shape == (3, 23)  # 4T + 7 + 2F + 4C with T = 4, F = C = 0
+    assert c.shape == (3, 28)  # 4T + 12 + 2F + 4C with T = 4, F = C = 0
     assert c[1, 2] == unc[:, 1, 2].sum() and c[2, 4 + 1] == cor[:, 2, 1].sum() and c[0, 8] == 50
     assert c[0, 10:15].sum() == 50 and c[0, 15:20].sum() == 50

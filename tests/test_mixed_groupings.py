@@ -256,3 +256,8 @@ def test_gpu_contract_with_extra_groupings_runs_end_to_end():
     want = orc.run_batch(low["spec"], [240], 256, M.splitmix64(2137), n_threads=orc.host_threads())
     assert pr["success_counts_uncorrected"] == [int(v) for v in want["uncorrected"].sum(axis=0)[0]]
     assert pr["convergence_count"] == int(want["converged"].sum())
+    ex = pr["estimator_extras"]  # four variance components: intercept, slope, item, half (result.rs:362-398)
+    conv = want["converged"][:, 0] != 0
+    pins = want["boundary_hit"][:, 0] >> 2
+    assert ex["boundary_component_counts"] == [int((((pins >> k) & 1) != 0)[conv].sum()) for k in range(4)]
+    assert sum(ex["boundary_component_counts"]) > 0

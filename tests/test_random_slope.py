@@ -259,3 +259,10 @@ def test_gpu_contract_with_primary_slopes_runs_end_to_end(n_slopes):
     want = orc.run_batch(low["spec"], [600], 512, M.splitmix64(2137), n_threads=orc.host_threads())
     assert pr["success_counts_uncorrected"] == [int(v) for v in want["uncorrected"].sum(axis=0)[0]]
     assert pr["convergence_count"] == int(want["converged"].sum())
+    # EstimatorExtras::Mle (result.rs:341-398): per-component pin counts over the converged fits, one entry per variance component
+    ex = pr["estimator_extras"]
+    conv = want["converged"][:, 0] != 0
+    code, pins = want["boundary_hit"][:, 0] & 3, want["boundary_hit"][:, 0] >> 2
+    assert ex["boundary_component_counts"] == [int((((pins >> k) & 1) != 0)[conv].sum()) for k in range(1 + n_slopes)]
+    assert ex["singular_count"] == int((code == 1)[conv].sum()) and ex["boundary_hits"] == int((code != 0).sum())
+    assert len(ex["boundary_rate_per_component"]) == 1 + n_slopes
