@@ -40,12 +40,17 @@ namespace mcp {
 #endif
 // Instruction-count switches of the headline kernel (profiles/r02_lean_kernel.md has the A/B numbers; every setting computes
 // the same bits):
-//   MCP_LEAN_DYNLP   linear predictor as a uniform loop over the non-zero effects (re-reads those x from the slab) instead of
-//                    DMUL + DADD + two selects for every column — ptxas if-converts the per-column zero-beta test
+//   MCP_LEAN_DYNLP   linear predictor of the plain kernels.  0: DMUL + DADD + two selects per column (ptxas if-converts the
+//                    per-column zero-beta test).  1: a uniform loop over the non-zero effects that re-reads those x from the
+//                    slab (LDC -> LDS -> F2F -> DMUL -> DADD: few instructions, one long dependent chain per row).  2 (default):
+//                    every column, no test — z·(±0) leaves the +0-seeded sum unchanged bit for bit; 17 FP64 instructions on
+//                    values that already sit in registers.  Measured on top of the interior path: 0 -> 8.97e7, 1 -> 8.90e7,
+//                    2 -> 9.26e7 fits/s.  A two-slot variant of 1 (at most two non-zero slopes, 10 instructions per row) ran
+//                    SLOWER than 2 (9.43e7 against 9.56e7): the chain's latency costs more than the FP64 issue slots
 //   MCP_LEAN_PUSH32  tail-queue push loop on two 32-bit masks instead of one 64-bit mask
 //   MCP_LEAN_SCAN    tail-queue slots from a warp prefix sum (shuffles) instead of one shared-memory atomic per lane
 #ifndef MCP_LEAN_DYNLP
-#define MCP_LEAN_DYNLP 1
+#define MCP_LEAN_DYNLP 2
 #endif
 #ifndef MCP_LEAN_PUSH32
 #define MCP_LEAN_PUSH32 1
@@ -58,6 +63,28 @@ namespace mcp {
 //                    IMAD.WIDE; scalar can use the FMA-lite pipe
 #ifndef MCP_LEAN_SCALAR_PAIRS
 #define MCP_LEAN_SCALAR_PAIRS 0
+#endif
+//   MCP_LEAN_INTERIOR  a quad step that lies wholly inside the design (16 more rows exist) and ahead of the next grid point
+//                    runs its four finishing / accumulation sub-steps fully unrolled and without the per-row bounds and
+//                    grid-point tests (the slab addresses of the sub-step fold to constants).  Plain kernels only (no MIX /
+//                    INTER / FACT): measured 8.55e7 -> 8.91e7 fits/s on the headline shape at 126 registers, while the
+//                    MIX / FACT instantiations spill with it (config-2 sweep 5.96e8 -> 5.29e8) and keep the rolled loop
+#ifndef MCP_LEAN_INTERIOR
+#define MCP_LEAN_INTERIOR 1
+#endif
+//   MCP_LEAN_PAD     value stored in the padding slots of a staged row (never read): 0.0 is one CS2R, z[0] two MOVs
+#ifndef MCP_LEAN_PAD
+#define MCP_LEAN_PAD 0.0
+#endif
+//   MCP_LEAN_PUSH_UNROLL  unroll factor of the tail-queue push loops (4 = what ptxas picked on its own; 1 measured +1 % with the
+//                    rolled generation loop and -0.5 % with the fully unrolled one)
+#ifndef MCP_LEAN_PUSH_UNROLL
+#define MCP_LEAN_PUSH_UNROLL 4
+#endif
+//   MCP_LEAN_FULL_GEN  plain kernels of at most this many columns unroll the generation loop completely (k is a compile-time
+//                    constant there: the residual / column-half selects of a task fold away): 9.27e7 -> 9.55e7 fits/s at P = 9
+#ifndef MCP_LEAN_FULL_GEN
+#define MCP_LEAN_FULL_GEN 10
 #endif
 
 
@@ -168,6 +195,7 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
     using G = LeanGeom<PT>;
     constexpr int NACC = PT * (PT + 1) / 2;
     constexpr int N = G::N, M = G::M, MH = G::MH, HOFF = G::HOFF;
+    constexpr int PUSH_UNR = MCP_LEAN_PUSH_UNROLL;
     const DevicePlan& pl = c_plan;
     if (mcp_cancelled()) return;
     extern __shared__ __align__(16) float smem[];
@@ -211,8 +239,13 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
         unsigned tlo = 0u, thi = 0u;
         if (16 * sb + 4 * q < max_n) {
             const uint32_t b = (uint32_t)(4 * sb + q);
+            if constexpr (!MIX && !INTER && !FACT && PT <= MCP_LEAN_FULL_GEN) {
+#pragma unroll
+                for (int t = 0; t < PT; t++) lean_gen_task<PT>(t, PT - 1, b, rk, own, tmask, tlo, thi);
+            } else {
 #pragma unroll UNR
-            for (int t = 0; t <= k; t++) lean_gen_task<PT>(t, k, b, rk, own, tmask, tlo, thi);
+                for (int t = 0; t <= k; t++) lean_gen_task<PT>(t, k, b, rk, own, tmask, tlo, thi);
+            }
         }
         // ---- B. deferred tail branch of the inverse-normal kernel (rng.rs:354-364), warp-cooperative: a lane sees
         // Binomial(4(k+1), 0.0485) tail draws per block, so a per-lane loop runs max-over-32-lanes (~5 at k = 8)
@@ -239,11 +272,13 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
             unsigned slot = cnt ? atomicAdd(wq_cnt, (unsigned)cnt) : 0u;
 #endif
 #if MCP_LEAN_PUSH32
+#pragma unroll PUSH_UNR
             while (tlo) {
                 const int bit = __ffs((int)tlo) - 1;
                 tlo &= tlo - 1u;
                 wq[slot++] = (unsigned short)(own_off + 128 * (bit >> 2) + (bit & 3));
             }
+#pragma unroll PUSH_UNR
             while (thi) {
                 const int bit = __ffs((int)thi) - 1;
                 thi &= thi - 1u;
@@ -271,13 +306,10 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
             if ((threadIdx.x & 31u) == 0u) *wq_cnt = 0u;
 #endif
         }
-#pragma unroll 1
-        for (int qq = 0; qq < 4; qq++) {
-            const int row0 = 16 * sb + 4 * qq;
-            if (row0 >= max_n) break;
-            // ---- C. lane q finishes row row0 + q (generated by lane qq) — Cholesky mix (MIX), interaction products
-            // (INTER), linear predictor, y — and stages it in f64 (widened ONCE) as [z_0..z_{M-1} | z_N .. z_{N-M+1}]
-            if (row0 + q < max_n) {
+        // ---- C. lane q finishes row row0 + q (generated by lane qq) — Cholesky mix (MIX), interaction products
+        // (INTER), linear predictor, y — and stages it in f64 (widened ONCE) as [z_0..z_{M-1} | z_N .. z_{N-M+1}]
+        auto finish_row = [&](const int qq, const int row0) {
+            {
                 float* const src = wslab + qq * 32 + ((qi ^ (2 * qq)) << 2) + q;  // + 128·column
                 double z[PT + 1];
                 z[0] = 1.0;
@@ -327,7 +359,14 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                     }
                 }
                 double lp = 0.0;
-#if MCP_LEAN_DYNLP
+#if MCP_LEAN_DYNLP == 2
+                if (!MIX && !INTER && !FACT) {
+                    // every column, no test: a zero effect contributes z·(±0) = ±0, and a +0-seeded sum of such terms never
+                    // reaches -0 (round to nearest), so s + ±0 == s bit for bit — the same value as skipping the term
+#pragma unroll
+                    for (int j = 0; j < PT; j++) lp = lp + z[j] * pl.beta[j];
+                } else
+#elif MCP_LEAN_DYNLP
                 if (!MIX && !INTER && !FACT) {
                     // every x of this row still sits in the slab: a uniform loop over the non-zero effects (ascending columns,
                     // separately rounded product and sum — the same chain as below)
@@ -350,10 +389,30 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
 #pragma unroll
                 for (int j = 0; j < MH / 2; j++) {
                     const int j0 = 2 * j, j1 = 2 * j + 1;
-                    dst[j] = make_double2(z[j0 < M ? j0 : 0], z[j1 < M ? j1 : 0]);
-                    dst[HOFF / 2 + j] = make_double2(z[j0 < M ? N - j0 : 0], z[j1 < M ? N - j1 : 0]);
+                    // (padding slots are never read by the accumulation)
+                    dst[j] = make_double2(j0 < M ? z[j0] : MCP_LEAN_PAD, j1 < M ? z[j1] : MCP_LEAN_PAD);
+                    dst[HOFF / 2 + j] = make_double2(j0 < M ? z[N - j0] : MCP_LEAN_PAD, j1 < M ? z[N - j1] : MCP_LEAN_PAD);
                 }
             }
+        };
+        if constexpr (MCP_LEAN_INTERIOR && !MIX && !INTER && !FACT) {
+            if (16 * sb + 16 <= max_n && n_next > (uint32_t)(16 * sb + 16)) {
+#pragma unroll
+                for (int qq = 0; qq < 4; qq++) {
+                    finish_row(qq, 16 * sb + 4 * qq);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < 4; r++) lean_acc_row<PT>(p_base + r * G::ROW, r_base + r * G::ROW, acc);
+                    __syncwarp();
+                }
+                continue;
+            }
+        }
+#pragma unroll 1
+        for (int qq = 0; qq < 4; qq++) {
+            const int row0 = 16 * sb + 4 * qq;
+            if (row0 >= max_n) break;
+            if (row0 + q < max_n) finish_row(qq, row0);
             __syncwarp();
             // ---- D. row pass: the same local pattern in every lane
             const int nr = max_n - row0 < 4 ? max_n - row0 : 4;
