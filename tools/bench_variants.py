@@ -19,7 +19,8 @@ seed = M.splitmix64(2137)
 out = {}
 import os
 SETS = {"ols": (("headline", S.headline_spec(), [500], n), ("c2_sweep", S.sweep_spec(), list(range(20, 1001, 20)), n // 8),
-                ("c1", S.add_interaction(S.base_spec(2), [1, 2], 0.2), [100], n)),
+                ("c1", S.add_interaction(S.base_spec(2), [1, 2], 0.2), [100], n),
+                ("mix9", dict(S.headline_spec(), correlation=[0.3 ** abs(i - j) for j in range(8) for i in range(8)]), [500], n // 2)),
         "glm": (("c4_logit", S.logit_spec(), [50, 100, 200, 500, 1000, 2000], n // 16),
                 ("logit_n300", S.logit_spec(), [300], n // 4)),
         "c3": (("c3_doomer", dict(S.sweep_spec(), scenario=S.scenario("doomer"), crit_values={"alpha": 5e-7, "posthoc_alpha": None}),
