@@ -158,7 +158,12 @@ static cudaError_t launch_one(int kind, bool scen, const DevicePlan& pl, const K
         ols_lean_kernel<__VA_ARGS__><<<blocks5, MCP_BLOCK, smem5, a.stream>>>(a.base_seed, a.sim_begin, a.n_sims,        \
                                                                               a.scratch_d);                               \
     } while (0)
+#if MCP_LEAN_FACT_ONLY
+        if (pl.n_inter > 0) MCP_LAUNCH_LEAN(PT, true, true);
+        else if (pl.n_factors > 0) MCP_LAUNCH_LEAN(PT, true, false, MCP_LEAN_UNROLL, true);  // dummies, no interaction: x is not written back to the slab
+#else
         if (pl.n_inter > 0 || pl.n_factors > 0) MCP_LAUNCH_LEAN(PT, true, true);
+#endif
         else if (!pl.l_identity) MCP_LAUNCH_LEAN(PT, true, false);
         else {
 #ifdef MCP_LEAN_TUNE  // tuning build only: MCPOWER_B200_LEAN_TUNE=u<unroll> picks an instantiation at P = 9

@@ -1100,6 +1100,9 @@ __device__ __forceinline__ void init_sim_ctx(SimCtx& cx, uint64_t key, uint32_t 
     if (pl.n_slopes > 0) slope_factor(cx);
 }
 
+#ifndef MCP_ROW_LP_ALL
+#define MCP_ROW_LP_ALL 0
+#endif
 // Widen row r of the slab to f64 registers and assemble y (data_gen.rs:781-922).  Returns y as f64 of the f32 value.
 template <int PT, bool SCEN, typename SlabT>
 __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx& cx, double (&xr)[PT], const ScenDesign<PT>* sd) {
@@ -1109,10 +1112,16 @@ __device__ __forceinline__ double row_xy(int b, int r, const SlabT slab, SimCtx&
 #pragma unroll
     for (int j = 1; j < PT; j++) xr[j] = (double)slab[4 * (j - 1) + r];
     double lp = 0.0;
+#if MCP_ROW_LP_ALL
+    // every column, as the reference's loop does (data_gen.rs:781-795): two FP64 instructions per column on registers
+#pragma unroll
+    for (int j = 0; j < PT; j++) lp = lp + xr[j] * pl.beta[j];
+#else
     const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum: skipping them is bit-exact
 #pragma unroll
     for (int j = 0; j < PT; j++)
         if (bm & (1u << j)) lp = lp + xr[j] * pl.beta[j];
+#endif
     float ef = slab[4 * (PT - 1) + r];
     double u_re = 0.0;
     if (pl.has_cluster) {  // u_c = f32(normal(word c) * tau), drawn first on the sequential stream (data_gen.rs:146-161)

@@ -86,6 +86,17 @@ namespace mcp {
 #ifndef MCP_LEAN_FULL_GEN
 #define MCP_LEAN_FULL_GEN 10
 #endif
+//   MCP_LEAN_LP_ALL_EVERYWHERE  the MIX / FACT / INTER instantiations multiply every column into the linear predictor as well
+//                    (instead of DMUL + DADD + two selects per column): config-2 sweep 6.61e8 -> 6.90e8 fits/s
+#ifndef MCP_LEAN_LP_ALL_EVERYWHERE
+#define MCP_LEAN_LP_ALL_EVERYWHERE 1
+#endif
+//   MCP_LEAN_FACT_ONLY  designs with factor dummies but no interaction run <P, MIX, INTER = false, FACT = true>: the finished x of
+//                    a row are not written back to the slab (only interaction products read them there): config-2 sweep
+//                    6.61e8 -> 7.41e8, with the switch above 7.58e8 fits/s (kernel_tu.cu picks the instantiation)
+#ifndef MCP_LEAN_FACT_ONLY
+#define MCP_LEAN_FACT_ONLY 1
+#endif
 
 
 // Philox4x32-10 with the 10 round keys precomputed per study (rk[2r] = k0 + r·W0, rk[2r+1] = k1 + r·W1).
@@ -378,10 +389,17 @@ __global__ void __launch_bounds__(MCP_BLOCK, MCP_LEAN_MIN_BLOCKS) ols_lean_kerne
                 } else
 #endif
                 {
+#if MCP_LEAN_LP_ALL_EVERYWHERE
+                    // the same unconditional chain in the MIX / FACT / INTER instantiations (every column of z is defined there:
+                    // a column is continuous, a dummy or an interaction)
+#pragma unroll
+                    for (int j = 0; j < PT; j++) lp = lp + z[j] * pl.beta[j];
+#else
                     const uint32_t bm = pl.beta_nonzero_mask;  // β_j == 0 terms add ±0 to a +0-seeded sum
 #pragma unroll
                     for (int j = 0; j < PT; j++)
                         if (bm & (1u << j)) lp = lp + z[j] * pl.beta[j];
+#endif
                 }
                 const double ef = (double)src[128 * (PT - 1)];
                 z[PT] = (double)(float)(lp + ef + 0.0);  // same association as row_xy: (lp + e) + u_re, u_re = +0

@@ -237,6 +237,32 @@ def test_every_template_width():
         assert_batch_equal(got, want)
 
 
+@pytest.mark.parametrize("k", [2, 8, 9])
+def test_plain_grid_points_around_step_boundaries(k):
+    """The plain kernels run a 16-row step without per-row tests when it lies inside the design and ahead of the next grid point
+    (kernels_lean.cuh, interior steps) and multiply every column into the linear predictor, zero effects included: grid points on,
+    one before and one after every kind of step boundary, zero / negative-zero / non-zero effects and a non-zero intercept."""
+    s = S.base_spec(k)
+    s["target_indices"] = list(range(1, 1 + k))
+    eff = [0.35] + [0.0] * k
+    eff[1] = 0.3
+    eff[k] = -0.25
+    if k >= 8:
+        eff[4] = -0.0
+        eff[6] = 0.15
+    s["effect_sizes"] = eff
+    s["report_overall"] = True
+    grid = [k + 2, 15, 16, 17, 31, 32, 33, 48, 63, 65, 80, 81, 96, 111, 113, 128, 130]
+    grid = sorted(set(g for g in grid if g >= k + 2))
+    got = M.run_batch(s, grid, 160, SEED ^ k, mode=ALL)
+    want = oracle_once(("step_boundaries", k), lambda: orc.run_batch(s, grid, 160, SEED ^ k, n_threads=orc.host_threads(), capture=True))
+    assert_batch_equal(got, want)
+    # a single distant grid point: every step but the last is interior
+    got = M.run_batch(s, [203], 96, SEED ^ k, mode=ALL)
+    want = oracle_once(("step_boundaries_single", k), lambda: orc.run_batch(s, [203], 96, SEED ^ k, n_threads=orc.host_threads(), capture=True))
+    assert_batch_equal(got, want)
+
+
 # ------------------------------------------------------------------ robustness scenarios (BASELINE config 3)
 def _scenario_spec(preset: str, alpha: float = 0.05) -> dict:
     s = S.sweep_spec()
