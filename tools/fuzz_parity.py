@@ -20,4 +20,6 @@ for case in range(lo, hi):
     except Exception as e:  # noqa: BLE001
         bad += 1
         print("ERROR", case, type(e).__name__, str(e)[:300], flush=True)
+    if (case - lo + 1) % 25 == 0:
+        print(f"... {case - lo + 1} cases done, {bad} failures", flush=True)  # a run cut off by a time limit still says how far it got
 print(f"cases {lo}..{hi - 1}: {bad} failures")
