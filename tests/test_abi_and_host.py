@@ -157,3 +157,23 @@ def test_counters_from_bytes_matches_manual_aggregation():
     assert c.shape == (3, 28)  # 4T + 12 + 2F + 4C with T = 4, F = C = 0
     assert c[1, 2] == unc[:, 1, 2].sum() and c[2, 4 + 1] == cor[:, 2, 1].sum() and c[0, 8] == 50
     assert c[0, 10:15].sum() == 50 and c[0, 15:20].sum() == 50
+
+
+def test_reference_arm_of_bench_prints_the_contract_line():
+    """`bench.py --impl reference` times the CPU restatement alone (no GPU needed) and prints ONE JSON line with the arm's
+    contract keys: same metric / unit / config as the CUDA arm, impl = reference, a cpu_baseline describing the run and an e2e
+    object that repeats the value with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-400:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ols_fits_per_sec" and d["unit"] == "fits/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["config"]["workload"].startswith("ols_n500_k8_p9") and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
