@@ -1410,7 +1410,9 @@ static McpBatchResult* run_batch_core(const Spec& s, const uint32_t* sample_size
                     }
                 }
             }
-            if (++spins < 64) std::this_thread::yield();
+            // a default-size call (1600 sims: ~50 µs of kernels) ends inside the spinning phase; a sleep costs ~100 µs of timer
+            // slack, so the thread only starts sleeping once the call has outlived 300 µs
+            if (++spins < 64 || std::chrono::steady_clock::now() - t_wait < std::chrono::microseconds(300)) std::this_thread::yield();
             else std::this_thread::sleep_for(std::chrono::microseconds(50));
         }
         if (cancelled)
